@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- LID-VAE train samples/s (BASELINE.json metric) on N B200s of one node, plus the fused ICNN
+decode+grad-psi kernel against its roofline and the CPU oracle port as baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--precision fp32]
+    N>1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N
+
+Workload (config.workload): BASELINE.json configs[1] -- LIDVAE(dataset='pinwheel'), latent_dim 2, ICNN(2,512) +
+ICNN(2,1024) Brenier decoder, synthetic chessboard 2-D points, per-GPU batch 65536 (weak scaling).  One step =
+forward -> loss -> backward -> gradient all-reduce (N>1) -> Adam, i.e. lipschitz.py:36-43.
+`value`  : inputs resident in HBM.           `e2e`: same step through the public module API with pinned HOST
+inputs (H2D copy) and the loss read back (D2H) inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def chessboard(n, rng):
+    """Synthetic 2-D chessboard points in [-4,4]^2 (own generator; shape/statistics of dataset.py:72-102)."""
+    pts = np.empty((0, 2), dtype=np.float32)
+    while pts.shape[0] < n:
+        c = rng.uniform(-4, 4, (2 * n, 2)).astype(np.float32)
+        keep = (np.floor(c[:, 0]) + np.floor(c[:, 1])) % 2 == 0
+        pts = np.concatenate([pts, c[keep]], 0)
+    return pts[:n]
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows[-3:]]
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(rows)}
+        try:
+            sm = sorted(float(r[0]) for r in rows)
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = float(rows[0][1])
+            out["power_w_max"] = max(float(r[2]) for r in rows)
+            for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+                if any(r[3 + i].lower().startswith("active") for r in rows):
+                    out["reasons"].append(name)
+        except Exception:
+            pass
+        return out
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+# ----------------------------------------------------------------------------------------- CPU (oracle) arm
+def oracle_step_factory(seed=0):
+    """The oracle port of one LID-VAE decoder train step (decode fwd + double-backward + losses), fp32 numpy
+    (multi-threaded BLAS).  The tiny [2,2,2,2] encoder is omitted (<1% of the flops)."""
+    from oracle import icnn_oracle as io
+    from oracle import loss_oracle as lo
+    rng = np.random.default_rng(seed)
+    p0 = io.random_params(rng, 2, 512, np.float32, "mixed")
+    p1 = io.random_params(rng, 2, 1024, np.float32, "mixed")
+
+    def step(x, eps):
+        mu, lv = x * np.float32(0.5), np.abs(x) * np.float32(0.1)      # stand-in encoder outputs
+        z = lo.reparam(mu, lv, eps)
+        y, _, _, _ = io.lidvae_decode(z, p0, p1, 2, 0, 0.1)
+        rec, kl = lo.recon_mse(x, y), lo.kl(mu, lv)
+        vy = lo.recon_mse_grad(x, y).astype(np.float32)
+        io.lidvae_decode_backward(z, vy, p0, p1, 2, 0, 0.1)
+        return float(rec + kl)
+    return step
+
+
+def time_oracle(sample, reps):
+    rng = np.random.default_rng(1)
+    step = oracle_step_factory()
+    x, eps = chessboard(sample, rng), rng.normal(0, 1, (sample, 2)).astype(np.float32)
+    step(x[:256], eps[:256])
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); step(x, eps); ts.append(time.perf_counter() - t0)
+    return sample / min(ts), float(np.mean(ts))
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 8192
+    ts = []
+    rng = np.random.default_rng(1)
+    step = oracle_step_factory()
+    x, eps = chessboard(sample, rng), rng.normal(0, 1, (sample, 2)).astype(np.float32)
+    for _ in range(max(args.warmup, 1)):
+        step(x, eps)
+    for _ in range(args.steps):
+        t0 = time.perf_counter(); step(x, eps); ts.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(ts))
+    val = sample / (ms * 1e-3)
+    line = {"impl": "reference", "metric": "LID-VAE train samples/s", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU oracle port (numpy, multithreaded BLAS) of the decoder train step; "
+                       "the reference is pure Python/PyTorch and cannot travel to the GPU box"},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} samples per step x {args.steps} steps"},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+WORKLOAD = "configs[1]: LIDVAE(pinwheel/chessboard 2-D, latent 2, encoder [2,2,2,2], ICNN(2,512)+ICNN(2,1024)) train step"
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from oracle import icnn_oracle as io
+    from vae_song_b200 import _C, model, ops, train
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(42)
+    B = args.batch
+    m = model.LIDVAE(dataset="pinwheel", inverse_lipschitz=0.2, beta=1.0, precision=args.precision).to(dev).train()
+    wr = np.random.default_rng(7)
+    with torch.no_grad():   # O(1)-scale random weights (default exp(W)~1 init gives 1e20 losses whose squares overflow Adam's v)
+        for ic in (m.decoder[0], m.decoder[1]):
+            H = ic.hidden_channel
+            ic.W[0].param.copy_(torch.tensor(wr.normal(np.log(1.0 / H), 1.0, (H, H)), dtype=torch.float32))
+            ic.W[1].param.copy_(torch.tensor(wr.normal(np.log(2.0 / H), 1.0, (1, H)), dtype=torch.float32))
+            ic.A[0].bias.copy_(torch.tensor(wr.normal(-0.3, 1.0, (H,)), dtype=torch.float32))
+    tr = train.DataParallelTrainer(m, lr=1e-3)
+    rng = np.random.default_rng(100 + rank)
+    n_pool = 4
+    host_pool = [torch.from_numpy(chessboard(B, rng)).pin_memory() for _ in range(n_pool)]
+    dev_pool = [h.to(dev) for h in host_pool]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, K, W):
+        for i in range(W):
+            step_fn(i)
+        barrier()
+        evs = []
+        for i in range(K):
+            flush.fill_(1.0)                      # evict L2 between timed iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step_fn(i); e1.record()
+            evs.append((e0, e1))
+        barrier()
+        tot = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([tot], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t) / K
+
+    def step_resident(i):
+        tr.step(dev_pool[i % n_pool])
+
+    def step_e2e(i):
+        x = host_pool[i % n_pool].to(dev, non_blocking=True)
+        total, _, _ = tr.step(x)
+        loss_host.copy_(total.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    n0 = _C.launch_count()
+    t_start = time.time()
+    ms = timed(step_resident, args.steps, args.warmup)
+    t_end = time.time()
+    launches = (_C.launch_count() - n0) * args.steps // (args.steps + args.warmup)
+    clocks = sampler.window(t_start, t_end) if sampler else {}
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    value = world * B / (ms * 1e-3)
+    e2e = world * B / (ms_e2e * 1e-3)
+
+    # ---- dominant kernel vs roofline: fused ICNN decode + grad-psi, H=1024, batch 65536 (north_star) ----
+    roof, extra = None, {}
+    if rank == 0:
+        pk, pk_kind = peaks()
+        Bk = 65536
+        prec = _C.PRECISIONS[args.precision]
+        z = torch.randn(Bk, 2, device=dev)
+        res = {}
+        for H in (512, 1024):
+            ic = m.decoder[0] if H == 512 else m.decoder[1]
+            params = [p.detach() for p in ic._flat_params()]
+            ws = ops.icnn_prepare(params, 2, H, 0, prec, Bk, False)
+            for _ in range(3):
+                ops.icnn_decode_fwd(z, ws, 2, H, 0, 0.1, prec)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(10):
+                flush.fill_(1.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); ops.icnn_decode_fwd(z, ws, 2, H, 0, 0.1, prec); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            res[H] = float(np.mean(ts))
+        fl = io.flops_decode(2, 1024) * Bk
+        ach = fl / (res[1024] * 1e-3) / 1e12
+        tensor_peak = {"fp32": pk["bf16_tflops"], "bf16": pk["bf16_tflops"], "tf32": pk["bf16_tflops"] / 2,
+                       "tf32x3": pk["bf16_tflops"] / 2}[args.precision]
+        roof = {"bound": "tensor", "kernel": "icnn_decode_fwd (psi + grad psi), d=2, H=1024, B=65536", "achieved": ach,
+                "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak, "traffic": None,
+                "peak_kind": f"{pk_kind} cuBLAS bf16 burst" + (" / 2 (tf32)" if args.precision.startswith("tf32") else ""),
+                "precision": args.precision, "kernel_ms": res[1024],
+                "fp32_simt_peak_tflops": 74.4, "frac_of_fp32_simt_peak": ach / 74.4 if args.precision == "fp32" else None,
+                "algorithmic_flop_per_sample": io.flops_decode(2, 1024)}
+        both = Bk / ((res[512] + res[1024]) * 1e-3)
+        extra = {"decode_samples_per_s_B65536": both, "decode_ms_H512": res[512], "decode_ms_H1024": res[1024],
+                 "decode_tflops_2icnn": both * (io.flops_decode(2, 512) + io.flops_decode(2, 1024)) / 1e12}
+        sample = 8192
+        cpu_val, cpu_s = time_oracle(sample, 3)
+        cpu = {"value": cpu_val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"oracle port (numpy fp32), decoder train step on {sample} samples, best of 3 ({cpu_s:.2f} s each)"}
+        line = {"metric": "LID-VAE train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
+                "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "precision": args.precision,
+                           "parallelism": f"dp{world}", "l2": "flushed between timed iterations (256 MB write)",
+                           "optimizer": "fused Adam lr 1e-3 over flat buffer"},
+                "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 2 * 4 * world,
+                        "d2h_bytes_per_step": 4 * world},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extra": extra}
+        print(json.dumps(line))
+    if sampler:
+        sampler.stop()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="per-GPU batch")
+    ap.add_argument("--precision", default=os.environ.get("B200VAE_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16", "tf32x3"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,144 @@
+/* b200vae.h -- C ABI of libb200vae.so: the B200 (sm_100a) decoder-and-loss hot path of vae-song.
+ *
+ * The reference (claviclecrusher/vae-song) is pure Python/PyTorch and has NO FFI of its own
+ * (SURVEY.md section 8(b)); each entry point below replaces a block of PyTorch-eager ops and names
+ * the reference lines it stands in for.  The Python host side (vae_song_b200/_C.py) binds these
+ * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous row-major data (fp32 unless noted),
+ *     16-byte aligned; the caller owns every buffer, the library allocates nothing persistent.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it.
+ *   - return value: 0 OK, <0 error (B200VAE_E*); nothing is launched on error.
+ *   - thread-safe for distinct streams/workspaces; no global state except a device-attribute cache.
+ *   - there is NO CPU path: without a CUDA device every compute entry returns B200VAE_ECUDA.
+ */
+#ifndef B200VAE_H
+#define B200VAE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VAE_OK 0
+#define B200VAE_ESHAPE (-1)   /* bad / inconsistent sizes                                 */
+#define B200VAE_EUNSUP (-2)   /* configuration not supported by this build                */
+#define B200VAE_EALIGN (-3)   /* null or misaligned pointer                               */
+#define B200VAE_ECUDA (-4)    /* CUDA launch / runtime error, see b200vae_last_cuda_error  */
+#define B200VAE_EWS (-5)      /* workspace too small (see b200vae_icnn_workspace_bytes)    */
+
+/* weight reparameterisation of PositiveLinear, module.py:110 (exp) / module.py:114 (clamp) */
+#define B200VAE_WEIGHT_EXP 0
+#define B200VAE_WEIGHT_CLAMP 1
+
+/* arithmetic of the two H x H contractions */
+#define B200VAE_PREC_FP32 0   /* FP32 SIMT FMA: the parity path (rtol 1e-5)                */
+#define B200VAE_PREC_TF32 1   /* tcgen05 kind::tf32, fp32 accumulate in TMEM               */
+#define B200VAE_PREC_BF16 2   /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate        */
+#define B200VAE_PREC_TF32X3 3 /* tcgen05 3xTF32 split (hi*hi + hi*lo + lo*hi): fp32-grade  */
+
+/* Parameters of one module.ICNN(in_channel=d, hidden_channel=H) -- module.py:117-140.
+ * Field <- state_dict key:  A0w<-A0.weight [H,d]  A0b<-A0.bias [H]  A1w<-A.0.weight [H,d]
+ * A1b<-A.0.bias [H]  A2w<-A.1.weight [1,d]  A2b<-A.1.bias [1]  W0<-W.0.param [H,H] (raw)
+ * W1<-W.1.param [1,H] (raw). */
+typedef struct b200vae_icnn_params {
+  const float *A0w, *A0b, *A1w, *A1b, *A2w, *A2b, *W0, *W1;
+} b200vae_icnn_params;
+
+/* Same shapes; every non-null field is OVERWRITTEN with the batch-summed gradient. */
+typedef struct b200vae_icnn_grads {
+  float *A0w, *A0b, *A1w, *A1b, *A2w, *A2b, *W0, *W1;
+} b200vae_icnn_grads;
+
+/* Bytes of caller-owned workspace needed by prepare/fwd/bwd for these sizes. `for_backward`=0
+ * sizes it for prepare+fwd only. */
+size_t b200vae_icnn_workspace_bytes(int B, int d, int H, int precision, int for_backward);
+
+/* Materialise the positive weights P = exp(W) | clamp(W,1e-2) (module.py:110/114) and the padded,
+ * kernel-layout copies of all parameters into `ws`.  Must precede fwd/bwd whenever parameters
+ * changed.  Replaces: the per-call `self.param.exp()` of PositiveLinear.forward. */
+int b200vae_icnn_prepare(const b200vae_icnn_params* p, int d, int H, int weight_mode, int precision,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* Fused potential + Brenier map:  psi[b] = ICNN(z_b)  (module.py:142-148)  and
+ * xhat[b,:] = grad_z( psi(z_b) + kappa*|z_b|^2 )      (model.py:820-822 / :826-828),
+ * one forward-then-reverse sweep, activations never leave the SM.
+ *   z [B,d]; psi [B] or NULL; xhat [B,d] or NULL;
+ *   mask1 [B, Hp/32] uint32 (bit n of row b = h1[b,n] > 0; Hp = H rounded up to 128) or NULL;
+ *   mask2 [B] uint8 (h2 > 0) or NULL.  Save both masks when a backward will follow. */
+int b200vae_icnn_decode_fwd(const float* z, int B, int d, int H, int weight_mode, float kappa,
+                            float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2,
+                            int precision, const void* ws, size_t ws_bytes, void* stream);
+
+/* Double-backward of the Brenier map (what autograd runs for lipschitz.py:41 through
+ * model.py:822/828):  gradients of  L = sum_b <v_b, xhat_b> + sum_b gpsi_b * psi_b.
+ *   v [B,d] (dL/dxhat) or NULL; gpsi [B] (dL/dpsi) or NULL; masks as written by decode_fwd;
+ *   dz [B,d] or NULL; grads: see b200vae_icnn_grads (raw-parameter gradients, i.e. already
+ *   chained through exp / clamp). */
+int b200vae_icnn_decode_bwd(const float* z, const float* v, const float* gpsi, const uint32_t* mask1,
+                            const uint8_t* mask2, int B, int d, int H,
+                            const b200vae_icnn_params* p, int weight_mode, float kappa,
+                            const b200vae_icnn_grads* grads, float* dz, int precision, void* ws,
+                            size_t ws_bytes, void* stream);
+
+/* Fused reparameterisation + Gaussian KL + reconstruction (+ latent reconstruction).
+ * Replaces model.py:843 / :423-424 (z = mu + eps*exp(lv/2)), :884/:550/:606 (KL), :870/:542/:589
+ * (MSE) or :872-882 (log-MSE), :551/:603 (latent recon, mean over dim 0 = L).
+ *   reparam:  mu, lv [B,D]; eps [L,B,D]; z [L,B,D]   (any may be NULL to skip)
+ *   KL:       out[1] = sum_{b,j} -0.5(1+lv-mu^2-e^lv) / B
+ *   recon:    x, xhat [B,Dx];  logmse=0: out[0] = sum (x-xhat)^2 / B
+ *                              logmse=1: out[0] = mean_b 0.5*Dx*(log(2*pi*mse_b+1e-5)+1);
+ *             mse_rows [B] scratch (needed when logmse=1, else may be NULL)
+ *   latent:   z_in, z_rec [Lz,Bz,Dz]: out[2] = sum (z_in-z_rec)^2 / Lz
+ *   out: B200VAE_LOSS_OUT_FLOATS fp32; out[0..2] = (recon, kl, latent).  The tail is reduction scratch
+ *   (ordered block partials + a ticket): it must be ZERO before the first call and is left zeroed by
+ *   every call, so one zero-initialised buffer can be reused; results are bit-reproducible. */
+#define B200VAE_LOSS_OUT_FLOATS 2048
+int b200vae_loss_fwd(const float* mu, const float* lv, const float* eps, float* z, int L, int B, int D,
+                     const float* x, const float* xhat, int Dx, int logmse, float* mse_rows,
+                     const float* z_in, const float* z_rec, int Lz, int Bz, int Dz, float* out,
+                     void* stream);
+
+/* Backward of the above given upstream scalars (device pointers, fp32):
+ *   g_recon, g_kl, g_lat : dL/d out[0..2]  (NULL = 0)
+ *   gz [L,B,D] : dL/dz from the decoder (NULL = 0)
+ *   writes d_mu, d_lv [B,D] (KL + reparam paths), d_xhat [B,Dx], d_zrec [Lz,Bz,Dz] (NULL to skip) */
+int b200vae_loss_bwd(const float* mu, const float* lv, const float* eps, const float* gz, int L, int B,
+                     int D, const float* x, const float* xhat, int Dx, int logmse, const float* mse_rows,
+                     const float* z_in, const float* z_rec, int Lz, int Bz, int Dz, const float* g_recon,
+                     const float* g_kl, const float* g_lat, float* d_mu, float* d_lv, float* d_xhat,
+                     float* d_zrec, void* stream);
+
+/* Random-pair Lipschitz ratios, utils.py:548-562:
+ *   ratio[p] = clamp(|Y[i1]-Y[i2]|_2, eps) / clamp(|X[i1]-X[i2]|_2, eps);  X [N,dx], Y [N,dy]. */
+int b200vae_lipschitz_pairs(const float* X, const float* Y, const int64_t* i1, const int64_t* i2, int P,
+                            int N, int dx, int dy, float eps, float* ratio, void* stream);
+
+/* Tiled all-pairs estimator (north_star kernel 4): over unordered pairs i<j whose 64x64 tile index
+ * t (row-major over the upper triangle incl. diagonal tiles) satisfies tile_begin <= t < tile_end.
+ *   stats [4] fp64: max, min, sum, count -- overwritten;
+ *   hist [nbins] uint32 or NULL: log2-spaced histogram of ratios over [2^hist_lo, 2^hist_hi).
+ * Shard tiles across ranks and combine stats with MAX/MIN/SUM all-reduces. */
+int b200vae_lipschitz_allpairs(const float* X, const float* Y, int N, int dx, int dy, float eps,
+                               long long tile_begin, long long tile_end, double* stats, uint32_t* hist,
+                               int nbins, float hist_lo, float hist_hi, void* stream);
+long long b200vae_lipschitz_num_tiles(int N);
+
+/* Fused Adam step over a flat fp32 parameter buffer (torch.optim.Adam semantics, lipschitz.py:25,43):
+ *   m,v moments; step = 1-based step count; grad_scale multiplies g first (e.g. 1/world_size). */
+int b200vae_adam_step(float* param, const float* grad, float* m, float* v, long long n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, long long step,
+                      float grad_scale, void* stream);
+
+int b200vae_last_cuda_error(void);
+const char* b200vae_version(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
+long long b200vae_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VAE_H */

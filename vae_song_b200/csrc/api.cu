@@ -1,0 +1,100 @@
+// api.cu -- extern "C" entry points of libb200vae.so for the ICNN path (validation + dispatch).
+#include "common.cuh"
+
+namespace b200vae {
+int g_last_cuda_error = 0;
+long long g_launch_count = 0;
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      n = 148;
+  }
+  return n;
+}
+
+int simt_prepare(const b200vae_icnn_params* p, int d, int H, int mode, float* ws, cudaStream_t st);
+int simt_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1,
+             uint8_t* mask2, const float* ws, cudaStream_t st);
+int simt_bwd(const float* z, const float* v, const float* gpsi, const uint32_t* mask1, const uint8_t* mask2,
+             int B, int d, int H, const b200vae_icnn_params* p, int mode, float kappa,
+             const b200vae_icnn_grads* g, float* dz, float* ws, cudaStream_t st);
+// tensor-core (tcgen05) variants, icnn_tc.cu
+int tc_prepare(const b200vae_icnn_params* p, int d, int H, int mode, int precision, float* ws, cudaStream_t st);
+int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1,
+           uint8_t* mask2, int precision, const float* ws, cudaStream_t st);
+size_t tc_extra_ws_floats(int d, int H, int precision);
+
+static bool params_ok(const b200vae_icnn_params* p) {
+  return p && p->A0w && p->A0b && p->A1w && p->A1b && p->A2w && p->A2b && p->W0 && p->W1 && aligned4(p->A0w) &&
+         aligned4(p->W0);
+}
+static int shape_ok(int B, int d, int H) {
+  if (B <= 0 || d <= 0 || H <= 0) return B200VAE_ESHAPE;
+  if (d > 4) return B200VAE_EUNSUP;      // fused small-d path; wider inputs go through the tiled path
+  if (H > 4096) return B200VAE_EUNSUP;
+  return B200VAE_OK;
+}
+static bool prec_ok(int precision) { return precision >= B200VAE_PREC_FP32 && precision <= B200VAE_PREC_TF32X3; }
+}  // namespace b200vae
+
+using namespace b200vae;
+
+extern "C" size_t b200vae_icnn_workspace_bytes(int B, int d, int H, int precision, int for_backward) {
+  if (B <= 0 || d <= 0 || H <= 0) return 0;
+  const WsLayout L = ws_layout(B, d, H);
+  size_t fl = for_backward ? L.end : L.fwd_end;
+  if (precision != B200VAE_PREC_FP32) fl += tc_extra_ws_floats(d, H, precision);
+  return fl * sizeof(float) + 256;
+}
+
+static float* ws_base(const void* ws) {
+  return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+}
+
+extern "C" int b200vae_icnn_prepare(const b200vae_icnn_params* p, int d, int H, int weight_mode, int precision,
+                                    void* ws, size_t ws_bytes, void* stream) {
+  if (!params_ok(p) || !ws) return B200VAE_EALIGN;
+  int rc = shape_ok(1, d, H);
+  if (rc) return rc;
+  if (weight_mode != B200VAE_WEIGHT_EXP && weight_mode != B200VAE_WEIGHT_CLAMP) return B200VAE_EUNSUP;
+  if (!prec_ok(precision)) return B200VAE_EUNSUP;
+  if (ws_bytes < b200vae_icnn_workspace_bytes(1, d, H, precision, 0)) return B200VAE_EWS;
+  rc = simt_prepare(p, d, H, weight_mode, ws_base(ws), (cudaStream_t)stream);
+  if (rc || precision == B200VAE_PREC_FP32) return rc;
+  return tc_prepare(p, d, H, weight_mode, precision, ws_base(ws), (cudaStream_t)stream);
+}
+
+extern "C" int b200vae_icnn_decode_fwd(const float* z, int B, int d, int H, int weight_mode, float kappa, float* psi,
+                                       float* xhat, uint32_t* mask1, uint8_t* mask2, int precision, const void* ws,
+                                       size_t ws_bytes, void* stream) {
+  (void)weight_mode;
+  if (!z || !ws || !aligned4(z)) return B200VAE_EALIGN;
+  int rc = shape_ok(B, d, H);
+  if (rc) return rc;
+  if (!prec_ok(precision)) return B200VAE_EUNSUP;
+  if (ws_bytes < b200vae_icnn_workspace_bytes(B, d, H, precision, 0)) return B200VAE_EWS;
+  if (precision == B200VAE_PREC_FP32)
+    return simt_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, ws_base(ws), (cudaStream_t)stream);
+  return tc_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), (cudaStream_t)stream);
+}
+
+extern "C" int b200vae_icnn_decode_bwd(const float* z, const float* v, const float* gpsi, const uint32_t* mask1,
+                                       const uint8_t* mask2, int B, int d, int H, const b200vae_icnn_params* p,
+                                       int weight_mode, float kappa, const b200vae_icnn_grads* grads, float* dz,
+                                       int precision, void* ws, size_t ws_bytes, void* stream) {
+  if (!z || !mask1 || !mask2 || !ws || !params_ok(p)) return B200VAE_EALIGN;
+  if (!v && !gpsi) return B200VAE_ESHAPE;
+  int rc = shape_ok(B, d, H);
+  if (rc) return rc;
+  if (!prec_ok(precision)) return B200VAE_EUNSUP;
+  if (ws_bytes < b200vae_icnn_workspace_bytes(B, d, H, precision, 1)) return B200VAE_EWS;
+  // the backward contractions run in FP32 SIMT for every precision in this build
+  return simt_bwd(z, v, gpsi, mask1, mask2, B, d, H, p, weight_mode, kappa, grads, dz, ws_base(ws), (cudaStream_t)stream);
+}
+
+extern "C" int b200vae_last_cuda_error(void) { return g_last_cuda_error; }
+extern "C" const char* b200vae_version(void) { return "b200vae 0.1 (sm_100a)"; }
+extern "C" long long b200vae_launch_count(void) { return g_launch_count; }

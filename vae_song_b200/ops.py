@@ -1,0 +1,303 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (vae_song_b200/_C.py).
+
+PyTorch is plumbing here: it owns device memory and the stream; every Function hands raw pointers to
+libb200vae.so.  No CPU path -- tensors must be CUDA fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _C
+from ._C import PARAM_FIELDS
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _C.B200VaeError(f"{name}: expected a CUDA tensor; vae_song_b200 has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise _C.B200VaeError(f"{name}: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _params_struct(params):
+    s = _C.IcnnParams()
+    for k, t in zip(PARAM_FIELDS, params):
+        setattr(s, k, t.data_ptr())
+    return s
+
+
+# ------------------------------------------------------------------------------------------ ICNN
+def icnn_prepare(params, d, H, mode, precision, B, for_backward):
+    """params: 8 tensors in PARAM_FIELDS order -> workspace tensor (uint8) holding the positive weights."""
+    lib = _C.load()
+    params = [_req(p.detach(), k) for p, k in zip(params, PARAM_FIELDS)]
+    nbytes = lib.b200vae_icnn_workspace_bytes(B, d, H, precision, 1 if for_backward else 0)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=params[0].device)
+    ps = _params_struct(params)
+    _C.check(lib.b200vae_icnn_prepare(C.byref(ps), d, H, mode, precision, _ptr(ws), nbytes, _stream()), "icnn_prepare")
+    return ws
+
+
+def icnn_decode_fwd(z, ws, d, H, mode, kappa, precision, want_psi=True, want_xhat=True, save_masks=False):
+    lib = _C.load()
+    B = z.shape[0]
+    Hp = (H + 127) // 128 * 128
+    psi = torch.empty(B, dtype=torch.float32, device=z.device) if want_psi else None
+    xhat = torch.empty(B, d, dtype=torch.float32, device=z.device) if want_xhat else None
+    mask1 = torch.empty(B, Hp // 32, dtype=torch.int32, device=z.device) if save_masks else None
+    mask2 = torch.empty(B, dtype=torch.uint8, device=z.device) if save_masks else None
+    _C.check(lib.b200vae_icnn_decode_fwd(_ptr(z), B, d, H, mode, float(kappa), _ptr(psi), _ptr(xhat), _ptr(mask1),
+                                         _ptr(mask2), precision, _ptr(ws), ws.numel(), _stream()), "icnn_decode_fwd")
+    return psi, xhat, mask1, mask2
+
+
+def icnn_decode_bwd(z, v, gpsi, mask1, mask2, params, ws, d, H, mode, kappa, precision, need_dz=True,
+                    need_params=True):
+    lib = _C.load()
+    B = z.shape[0]
+    dz = torch.empty_like(z) if need_dz else None
+    grads = [torch.empty_like(p) for p in params] if need_params else None
+    gs = _C.IcnnGrads()
+    if grads is not None:
+        for k, t in zip(PARAM_FIELDS, grads):
+            setattr(gs, k, t.data_ptr())
+    ps = _params_struct(params)
+    _C.check(lib.b200vae_icnn_decode_bwd(_ptr(z), _ptr(v), _ptr(gpsi), _ptr(mask1), _ptr(mask2), B, d, H, C.byref(ps),
+                                         mode, float(kappa), C.byref(gs) if grads is not None else None, _ptr(dz),
+                                         precision, _ptr(ws), ws.numel(), _stream()), "icnn_decode_bwd")
+    return dz, grads
+
+
+class IcnnBrenierFn(torch.autograd.Function):
+    """(psi [B], xhat [B,d]) = fused ICNN potential + Brenier map.  Replaces module.py:142-148 followed
+    by model.py:820-822.  backward = the double-backward PyTorch would run through autograd.grad."""
+
+    @staticmethod
+    def forward(ctx, z, kappa, mode, precision, *params):
+        z = _req(z, "z")
+        params = [_req(p, k) for p, k in zip(params, PARAM_FIELDS)]
+        H, d = params[0].shape
+        if z.dim() != 2 or z.shape[1] != d:
+            raise _C.B200VaeError(f"z must be [B,{d}], got {tuple(z.shape)}")
+        needs_bwd = any(ctx.needs_input_grad)
+        ws = icnn_prepare(params, d, H, mode, precision, z.shape[0], needs_bwd)
+        psi, xhat, m1, m2 = icnn_decode_fwd(z, ws, d, H, mode, kappa, precision, True, True, needs_bwd)
+        if needs_bwd:
+            ctx.save_for_backward(z, m1, m2, ws, *params)
+            ctx.cfg = (d, H, mode, float(kappa), precision)
+        ctx.set_materialize_grads(False)
+        return psi, xhat
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gpsi, gxhat):
+        z, m1, m2, ws, *params = ctx.saved_tensors
+        d, H, mode, kappa, precision = ctx.cfg
+        if gpsi is None and gxhat is None:
+            return (None,) * (4 + len(params))
+        v = None if gxhat is None else _req(gxhat, "grad_xhat")
+        gp = None if gpsi is None else _req(gpsi, "grad_psi")
+        need_params = any(ctx.needs_input_grad[4:])
+        dz, grads = icnn_decode_bwd(z, v, gp, m1, m2, params, ws, d, H, mode, kappa, precision,
+                                    need_dz=ctx.needs_input_grad[0], need_params=need_params)
+        if grads is None:
+            grads = [None] * len(params)
+        return (dz, None, None, None, *grads)
+
+
+class IcnnPotentialFn(torch.autograd.Function):
+    """psi = ICNN(z) [B,1] exactly as module.ICNN.forward returns it, and -- like the reference -- it stays
+    differentiable TWICE in z: backward computes grad_z = gpsi * xhat through IcnnBrenierFn (itself a
+    Function with a backward), so `torch.autograd.grad(psi, [z], ones, create_graph=True)` followed by
+    `.backward()` (model.py:822, lipschitz.py:41) works on this module unchanged."""
+
+    @staticmethod
+    def forward(ctx, z, mode, precision, *params):
+        z = _req(z, "z")
+        params = [_req(p, k) for p, k in zip(params, PARAM_FIELDS)]
+        H, d = params[0].shape
+        ws = icnn_prepare(params, d, H, mode, precision, z.shape[0], False)
+        psi, _, _, _ = icnn_decode_fwd(z, ws, d, H, mode, 0.0, precision, True, False, False)
+        ctx.save_for_backward(z, *params)
+        ctx.cfg = (mode, precision)
+        return psi.unsqueeze(1)
+
+    @staticmethod
+    def backward(ctx, gpsi):
+        z, *params = ctx.saved_tensors
+        mode, precision = ctx.cfg
+        need_z = ctx.needs_input_grad[0]
+        need_p = any(ctx.needs_input_grad[3:])
+        g = gpsi[:, 0]
+        dz, pgrads = None, [None] * len(params)
+        if need_z:
+            # differentiable in (z, params, gpsi) when create_graph=True: the Brenier map is a Function too
+            _, xhat = IcnnBrenierFn.apply(z, 0.0, mode, precision, *params)
+            dz = g.unsqueeze(1) * xhat
+        if need_p:
+            with torch.no_grad():
+                H, d = params[0].shape
+                zz = z.detach()
+                ws = icnn_prepare(params, d, H, mode, precision, zz.shape[0], True)
+                _, _, m1, m2 = icnn_decode_fwd(zz, ws, d, H, mode, 0.0, precision, False, False, True)
+                _, grads = icnn_decode_bwd(zz, None, _req(g.detach(), "grad_psi"), m1, m2, [p.detach() for p in params],
+                                           ws, d, H, mode, 0.0, precision, need_dz=False, need_params=True)
+            pgrads = [gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[3:])]
+        return (dz, None, None, *pgrads)
+
+
+# ------------------------------------------------------------------------------------------ losses
+_loss_scratch = {}
+
+
+def _loss_out(device):
+    """Zero-initialised reduction scratch (+ results) per (device, stream); the kernel leaves it zeroed."""
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    buf = _loss_scratch.get(key)
+    if buf is None:
+        buf = torch.zeros(_C.LOSS_OUT_FLOATS, dtype=torch.float32, device=device)
+        _loss_scratch[key] = buf
+    return buf
+
+
+class ReparamFn(torch.autograd.Function):
+    """z[l] = mu + eps[l] * exp(0.5*lv).  eps [B,D] or [L,B,D] (model.py:843 / :423-424)."""
+
+    @staticmethod
+    def forward(ctx, mu, lv, eps):
+        mu, lv, eps = _req(mu, "mu"), _req(lv, "log_var"), _req(eps, "eps")
+        B, D = mu.shape
+        L = 1 if eps.dim() == 2 else eps.shape[0]
+        z = torch.empty_like(eps)
+        out = _loss_out(mu.device)
+        _C.check(_C.load().b200vae_loss_fwd(_ptr(mu), _ptr(lv), _ptr(eps), _ptr(z), L, B, D, None, None, 0, 0, None,
+                                            None, None, 0, 0, 0, _ptr(out), _stream()), "reparam_fwd")
+        ctx.save_for_backward(mu, lv, eps)
+        return z
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gz):
+        mu, lv, eps = ctx.saved_tensors
+        B, D = mu.shape
+        L = 1 if eps.dim() == 2 else eps.shape[0]
+        gz = _req(gz, "grad_z")
+        d_mu, d_lv = torch.empty_like(mu), torch.empty_like(lv)
+        _C.check(_C.load().b200vae_loss_bwd(_ptr(mu), _ptr(lv), _ptr(eps), _ptr(gz), L, B, D, None, None, 0, 0, None,
+                                            None, None, 0, 0, 0, None, None, None, _ptr(d_mu), _ptr(d_lv), None, None,
+                                            _stream()), "reparam_bwd")
+        return d_mu, d_lv, None
+
+
+class VaeLossFn(torch.autograd.Function):
+    """(recon, kl, latent) scalars in one launch.  x/xhat [B,...]; mu/lv [B,D]; z_in/z_rec [L,B,D] or None."""
+
+    @staticmethod
+    def forward(ctx, x, xhat, mu, lv, z_in, z_rec, logmse):
+        dev = (xhat if xhat is not None else mu).device
+        x_ = None if x is None else _req(x, "x")
+        xh = None if xhat is None else _req(xhat, "xhat")
+        mu_ = None if mu is None else _req(mu, "mu")
+        lv_ = None if lv is None else _req(lv, "log_var")
+        zi = None if z_in is None else _req(z_in, "z_in")
+        zr = None if z_rec is None else _req(z_rec, "z_rec")
+        B = (xh if xh is not None else mu_).shape[0]
+        Dx = 0 if xh is None else xh.numel() // B
+        D = 0 if mu_ is None else mu_.shape[1]
+        Lz = Bz = Dz = 0
+        if zi is not None:
+            if zi.shape != zr.shape:
+                raise _C.B200VaeError("z_in / z_rec shape mismatch")
+            Lz = zi.shape[0]
+            Bz = zi.shape[1] if zi.dim() > 1 else 1
+            Dz = zi.numel() // (Lz * Bz)
+        mse_rows = torch.empty(B, dtype=torch.float32, device=dev) if (logmse and xh is not None) else None
+        out = _loss_out(dev)
+        _C.check(_C.load().b200vae_loss_fwd(_ptr(mu_), _ptr(lv_), None, None, 0, B, D, _ptr(x_), _ptr(xh), Dx,
+                                            1 if logmse else 0, _ptr(mse_rows), _ptr(zi), _ptr(zr), Lz, Bz, Dz,
+                                            _ptr(out), _stream()), "loss_fwd")
+        res = out[:3].clone()
+        ctx.save_for_backward(x_, xh, mu_, lv_, zi, zr, mse_rows)
+        ctx.dims = (B, D, Dx, Lz, Bz, Dz, bool(logmse))
+        ctx.set_materialize_grads(False)
+        return res[0], res[1], res[2]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_rec, g_kl, g_lat):
+        x_, xh, mu_, lv_, zi, zr, mse_rows = ctx.saved_tensors
+        B, D, Dx, Lz, Bz, Dz, logmse = ctx.dims
+        need_xh = ctx.needs_input_grad[1] and xh is not None and g_rec is not None
+        need_ml = (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]) and mu_ is not None and g_kl is not None
+        need_zr = ctx.needs_input_grad[5] and zr is not None and g_lat is not None
+        d_xh = torch.empty_like(xh) if need_xh else None
+        d_mu = torch.empty_like(mu_) if need_ml else None
+        d_lv = torch.empty_like(lv_) if need_ml else None
+        d_zr = torch.empty_like(zr) if need_zr else None
+        if need_xh or need_ml or need_zr:
+            f = lambda g: None if g is None else _req(g.reshape(1), "grad")
+            gr, gk, gl = f(g_rec), f(g_kl), f(g_lat)
+            _C.check(_C.load().b200vae_loss_bwd(_ptr(mu_), _ptr(lv_), None, None, 0, B, D, _ptr(x_), _ptr(xh), Dx,
+                                                1 if logmse else 0, _ptr(mse_rows), _ptr(zi), _ptr(zr), Lz, Bz, Dz,
+                                                _ptr(gr), _ptr(gk), _ptr(gl), _ptr(d_mu), _ptr(d_lv), _ptr(d_xh),
+                                                _ptr(d_zr), _stream()), "loss_bwd")
+        d_zi = None
+        if ctx.needs_input_grad[4] and d_zr is not None:
+            d_zi = -d_zr
+        d_x = None
+        if ctx.needs_input_grad[0] and d_xh is not None:
+            d_x = -d_xh
+        return d_x, d_xh, d_mu, d_lv, d_zi, d_zr, None
+
+
+# ------------------------------------------------------------------------------------------ Lipschitz
+def lipschitz_pair_ratios(X, Y, i1, i2, eps=1e-3):
+    """ratio[p] = clamp(|Y[i1]-Y[i2]|,eps)/clamp(|X[i1]-X[i2]|,eps)  (utils.py:548-562)."""
+    X = _req(X.detach().reshape(X.shape[0], -1), "X")
+    Y = _req(Y.detach().reshape(Y.shape[0], -1), "Y")
+    i1 = i1.to(torch.int64).contiguous()
+    i2 = i2.to(torch.int64).contiguous()
+    P = i1.numel()
+    ratio = torch.empty(P, dtype=torch.float32, device=X.device)
+    _C.check(_C.load().b200vae_lipschitz_pairs(_ptr(X), _ptr(Y), _ptr(i1), _ptr(i2), P, X.shape[0], X.shape[1],
+                                               Y.shape[1], float(eps), _ptr(ratio), _stream()), "lipschitz_pairs")
+    return ratio
+
+
+def lipschitz_allpairs(X, Y, eps=1e-3, tile_begin=0, tile_end=None, nbins=0, hist_lo=-20.0, hist_hi=20.0):
+    """All unordered pairs i<j in tiles [tile_begin, tile_end): returns (stats fp64 [max,min,sum,count], hist)."""
+    lib = _C.load()
+    X = _req(X.detach().reshape(X.shape[0], -1), "X")
+    Y = _req(Y.detach().reshape(Y.shape[0], -1), "Y")
+    N = X.shape[0]
+    nt = lib.b200vae_lipschitz_num_tiles(N)
+    if tile_end is None:
+        tile_end = nt
+    stats = torch.empty(4, dtype=torch.float64, device=X.device)
+    hist = torch.empty(nbins, dtype=torch.int32, device=X.device) if nbins > 0 else None
+    _C.check(lib.b200vae_lipschitz_allpairs(_ptr(X), _ptr(Y), N, X.shape[1], Y.shape[1], float(eps), int(tile_begin),
+                                            int(tile_end), _ptr(stats), _ptr(hist), nbins, float(hist_lo),
+                                            float(hist_hi), _stream()), "lipschitz_allpairs")
+    return stats, hist
+
+
+def lipschitz_num_tiles(N):
+    return int(_C.load().b200vae_lipschitz_num_tiles(N))
+
+
+# ------------------------------------------------------------------------------------------ Adam
+def adam_step_(param, grad, m, v, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    """In-place fused Adam over flat fp32 buffers (torch.optim.Adam semantics; lipschitz.py:25,43)."""
+    _C.check(_C.load().b200vae_adam_step(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), float(lr),
+                                         float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
+                                         float(grad_scale), _stream()), "adam_step")

@@ -1,0 +1,112 @@
+"""Host-side helpers with the reference's utils.py signatures for the hot path
+(reparameterize utils.py:40-47, kld :140-141, apply_grad_clip :12-38, estimate_local_lipschitz :532-567)
+plus the tiled all-pairs estimator the north_star adds."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def apply_grad_clip(model, grad_clip_cfg):
+    """Same config contract as the reference: {'enabled', 'clip_type': 'norm'|'value', 'max_norm',
+    'norm_type', 'clip_value'}; anything else is a no-op."""
+    if not grad_clip_cfg or not grad_clip_cfg.get("enabled", False):
+        return
+    kind = grad_clip_cfg.get("clip_type", "norm")
+    if kind == "norm":
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=float(grad_clip_cfg.get("max_norm", 1.0)),
+                                       norm_type=float(grad_clip_cfg.get("norm_type", 2.0)))
+    elif kind == "value":
+        torch.nn.utils.clip_grad_value_(model.parameters(), float(grad_clip_cfg.get("clip_value", 1.0)))
+
+
+def reparameterize(mu, logvar, nsamples=1, generator=None):
+    """Posterior samples [batch, nsamples, nz] (fused kernel; eps drawn exactly like the reference:
+    randn_like on the expanded [B,ns,nz] std)."""
+    B, nz = mu.size()
+    eps = torch.randn_like(mu.unsqueeze(1).expand(B, nsamples, nz))          # [B,ns,nz], same RNG stream
+    z = ops.ReparamFn.apply(mu, logvar, eps.permute(1, 0, 2).contiguous())   # kernel layout [L,B,D]
+    return z.permute(1, 0, 2)
+
+
+def kld(mu, log_var):
+    _, kl, _ = ops.VaeLossFn.apply(None, None, mu.detach(), log_var.detach(), None, None, False)
+    return kl.item()
+
+
+def estimate_local_lipschitz(func, X, num_pairs=2000, metric=2, quantile=0.05, eps=1e-3, generator=None,
+                             use_grad=False):
+    """Random-pair local Lipschitz estimate, reference semantics (utils.py:532-567):
+    returns (inverse_lipschitz, lipschitz, bi_lipschitz) as Python floats."""
+    if X.size(0) < 2:
+        return 0.0, 0.0, 0.0
+    N = X.size(0)
+    if generator is None:
+        generator = torch.Generator(device=X.device).manual_seed(0)
+    idx1 = torch.randint(0, N, (num_pairs,), device=X.device, generator=generator)
+    idx2 = torch.randint(0, N, (num_pairs,), device=X.device, generator=generator)
+    x1, x2 = X[idx1], X[idx2]
+    if use_grad:   # kept for API parity: our decode needs no autograd graph (reference defect D4)
+        x1 = x1.detach().clone().requires_grad_(True)
+        x2 = x2.detach().clone().requires_grad_(True)
+        y1, y2 = func(x1), func(x2)
+    else:
+        with torch.no_grad():
+            y1, y2 = func(x1), func(x2)
+    if metric == 2:
+        Xc = torch.cat([x1.detach().reshape(num_pairs, -1), x2.detach().reshape(num_pairs, -1)], 0)
+        Yc = torch.cat([y1.detach().reshape(num_pairs, -1), y2.detach().reshape(num_pairs, -1)], 0)
+        ar = torch.arange(num_pairs, device=X.device)
+        ratio = ops.lipschitz_pair_ratios(Xc, Yc, ar, ar + num_pairs, eps)
+    else:
+        dy = (y1 - y2).reshape(num_pairs, -1).norm(dim=1, p=metric).clamp(min=eps)
+        dx = (x1 - x2).reshape(num_pairs, -1).norm(dim=1, p=metric).clamp(min=eps)
+        ratio = (dy / dx).detach()
+    A = torch.quantile(ratio, quantile).clamp(min=eps)
+    Bq = torch.quantile(ratio, 1 - quantile)
+    invA = 1.0 / A
+    res = torch.stack([invA, Bq, torch.maximum(invA, Bq)]).tolist()   # one sync instead of three
+    return res[0], res[1], res[2]
+
+
+def estimate_lipschitz_allpairs(func, X, eps=1e-3, process_group=None, nbins=0, hist_range=(-20.0, 20.0)):
+    """All-pairs max / min / mean of |f(x)-f(y)|/|x-y| over every unordered pair (north_star kernel 4).
+    With a process group the 64x64 pair tiles are sharded round-robin-by-range across ranks and combined
+    with MAX / MIN / SUM all-reduces.  Returns dict(max, min, mean, count[, hist])."""
+    with torch.no_grad():
+        Y = func(X)
+    nt = ops.lipschitz_num_tiles(X.shape[0])
+    rank, world = 0, 1
+    if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        rank = torch.distributed.get_rank(process_group)
+        world = torch.distributed.get_world_size(process_group)
+    lo, hi = tile_range(nt, rank, world)
+    stats, hist = ops.lipschitz_allpairs(X, Y, eps, lo, hi, nbins, *hist_range)
+    if world > 1:
+        stats, hist = combine_allpairs(stats, hist, process_group)
+    mx, mn, sm, cnt = stats.tolist()
+    out = dict(max=mx, min=mn, mean=sm / max(cnt, 1.0), count=int(cnt))
+    if hist is not None:
+        out["hist"] = hist
+    return out
+
+
+def tile_range(num_tiles, rank, world):
+    """Contiguous, balanced tile ranges per rank (host logic; unit-tested on CPU)."""
+    base, rem = divmod(num_tiles, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def combine_allpairs(stats, hist, process_group=None):
+    """MAX / MIN / SUM all-reduce of per-rank [max, min, sum, count] (+ histogram)."""
+    import torch.distributed as dist
+    mx, mn, sc = stats[0:1].clone(), stats[1:2].clone(), stats[2:4].clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=process_group)
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=process_group)
+    dist.all_reduce(sc, op=dist.ReduceOp.SUM, group=process_group)
+    if hist is not None:
+        hist = hist.clone()
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=process_group)
+    return torch.cat([mx, mn, sc]), hist
