@@ -19,14 +19,14 @@ def f32_as_f64(a):
     return np.asarray(a, dtype=np.float32).astype(np.float64)
 
 
-def close_report(ours, ref, rtol, name, bad_frac=0.0):
+def close_report(ours, ref, rtol, name, bad_frac=0.0, floor=0.0):
     """|ours-ref| <= rtol*|ref| + rtol*max|ref| elementwise, except a fraction `bad_frac` of elements
     (kink flips: a LeakyReLU unit whose pre-activation is within rounding of 0 changes xhat by O(1/H),
     SURVEY.md section 7).  Returns the worst normalised error for logging."""
     ours = np.asarray(ours, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     assert ours.shape == ref.shape, (name, ours.shape, ref.shape)
-    scale = np.abs(ref).max() + 1e-300
+    scale = max(np.abs(ref).max(), floor) + 1e-300   # floor: tensors that are mathematically zero (rounding noise)
     err = np.abs(ours - ref)
     tol = rtol * np.abs(ref) + rtol * scale
     bad = (err > tol)

@@ -47,12 +47,15 @@ def test_lidvae_forward_loss_grads(name):
         close_report(recon.detach().cpu().numpy(), G[pre + "recon"], 1e-4 * rt, "recon", bad_frac=0.02)
         np.testing.assert_allclose([float(total), float(lrec), float(lreg)], G[pre + "loss"], rtol=1e-4 * rt)
         worst = 0.0
+        # Linear biases feeding a BatchNorm have mathematically zero gradients (pure rounding noise in both
+        # implementations): compare those against the model-wide gradient scale instead of their own.
+        gscale = max(np.abs(G[pre + "grad/" + k]).max() for k, _ in m.named_parameters())
         for k, q in m.named_parameters():
             ref = G[pre + "grad/" + k]
             if np.abs(ref).max() == 0:
                 assert q.grad is None or float(q.grad.abs().max()) == 0.0, k
             else:
-                worst = max(worst, close_report(q.grad.cpu().numpy(), ref, 1e-3 * rt, "grad " + k))
+                worst = max(worst, close_report(q.grad.cpu().numpy(), ref, 1e-3 * rt, "grad " + k, floor=1e-4 * gscale))
         assert worst < 2e-3
 
 

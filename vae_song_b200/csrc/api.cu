@@ -20,7 +20,7 @@ int simt_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float
              uint8_t* mask2, const float* ws, cudaStream_t st);
 int simt_bwd(const float* z, const float* v, const float* gpsi, const uint32_t* mask1, const uint8_t* mask2,
              int B, int d, int H, const b200vae_icnn_params* p, int mode, float kappa,
-             const b200vae_icnn_grads* g, float* dz, float* ws, cudaStream_t st);
+             const b200vae_icnn_grads* g, float* dz, float* ws, size_t mid_extra, cudaStream_t st);
 // tensor-core (tcgen05) variants, icnn_tc.cu
 int tc_prepare(const b200vae_icnn_params* p, int d, int H, int mode, int precision, float* ws, cudaStream_t st);
 int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1,
@@ -44,9 +44,9 @@ using namespace b200vae;
 
 extern "C" size_t b200vae_icnn_workspace_bytes(int B, int d, int H, int precision, int for_backward) {
   if (B <= 0 || d <= 0 || H <= 0) return 0;
-  const WsLayout L = ws_layout(B, d, H);
-  size_t fl = for_backward ? L.end : L.fwd_end;
-  if (precision != B200VAE_PREC_FP32) fl += tc_extra_ws_floats(d, H, precision);
+  const size_t extra = (precision != B200VAE_PREC_FP32) ? tc_extra_ws_floats(d, H, precision) : 0;
+  const WsLayout L = ws_layout(B, d, H, extra);
+  const size_t fl = for_backward ? L.end : L.fwd_end + extra + 64;
   return fl * sizeof(float) + 256;
 }
 
@@ -92,7 +92,9 @@ extern "C" int b200vae_icnn_decode_bwd(const float* z, const float* v, const flo
   if (!prec_ok(precision)) return B200VAE_EUNSUP;
   if (ws_bytes < b200vae_icnn_workspace_bytes(B, d, H, precision, 1)) return B200VAE_EWS;
   // the backward contractions run in FP32 SIMT for every precision in this build
-  return simt_bwd(z, v, gpsi, mask1, mask2, B, d, H, p, weight_mode, kappa, grads, dz, ws_base(ws), (cudaStream_t)stream);
+  const size_t extra = (precision != B200VAE_PREC_FP32) ? tc_extra_ws_floats(d, H, precision) : 0;
+  return simt_bwd(z, v, gpsi, mask1, mask2, B, d, H, p, weight_mode, kappa, grads, dz, ws_base(ws), extra,
+                  (cudaStream_t)stream);
 }
 
 extern "C" int b200vae_last_cuda_error(void) { return g_last_cuda_error; }

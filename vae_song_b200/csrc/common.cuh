@@ -60,7 +60,8 @@ inline int bwd_splits(int B, int Hp) {
   return s;
 }
 
-inline WsLayout ws_layout(int B, int d, int H) {
+// `mid_extra` floats (the tensor-core operand copies, icnn_tc.cu) sit between the forward arrays and the backward scratch
+inline WsLayout ws_layout(int B, int d, int H, size_t mid_extra = 0) {
   WsLayout L;
   L.d = d; L.H = H; L.Hp = round_up(H, 128);
   size_t Hp = (size_t)L.Hp;
@@ -73,6 +74,7 @@ inline WsLayout ws_layout(int B, int d, int H) {
   L.A1p = o; o += up(Hp * (d + 1));
   L.A2p = o; o += up(16 > d + 1 ? 16 : d + 1);
   L.fwd_end = o;
+  o += up(mid_extra);
   L.n_mtiles = (B + 127) / 128;
   L.splits = bwd_splits(B, L.Hp);
   L.colpart = o; o += up((size_t)L.n_mtiles * Hp * (2 * d + 3));

@@ -743,8 +743,8 @@ int simt_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float
 
 int simt_bwd(const float* z, const float* v, const float* gpsi, const uint32_t* mask1, const uint8_t* mask2,
              int B, int d, int H, const b200vae_icnn_params* p, int mode, float kappa,
-             const b200vae_icnn_grads* g, float* dz, float* ws, cudaStream_t st) {
-  const WsLayout L = ws_layout(B, d, H);
+             const b200vae_icnn_grads* g, float* dz, float* ws, size_t mid_extra, cudaStream_t st) {
+  const WsLayout L = ws_layout(B, d, H, mid_extra);
   const bool need_W0 = g && g->W0;
   int rc;
 #define B200VAE_BWD(DD)                                                                                   \

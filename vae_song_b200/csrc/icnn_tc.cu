@@ -1,10 +1,526 @@
-// icnn_tc.cu -- tcgen05 (TF32 / BF16 / 3xTF32) variants of the fused ICNN decode.  Placeholder until the
-// tensor-core kernel lands: every entry reports "unsupported" so callers fail loudly.
+// icnn_tc.cu -- tcgen05 / TMEM / TMA version of the fused ICNN potential + Brenier map (forward).
+//
+// One CTA = 256 samples (two M=128 UMMA row blocks), one accumulator pass = 256 output columns:
+// the whole 512-column TMEM of the SM holds D[256 x 256] fp32.  Per pass the K loop streams
+//   B (positive weights, [N=256 rows][K] K-major, 64 B swizzled rows)  by TMA from the L2-resident
+//     prepared copy (P for h1 = x1.P^T,  P^T for gx1 = g1.P), shared by both row blocks, and
+//   A (x1 = leaky(A0 z+b0)^2  or  g1 = s2*P1*s1) which never exists in memory: the 256 "worker"
+//     threads own one sample row each and write their row of every K-block straight into the
+//     swizzled UMMA layout in shared memory (generic proxy -> fence.proxy.async -> mbarrier).
+// The same thread later drains its row of the accumulator with tcgen05.ld, so every reduction of
+// the algorithm (h2 = P1.x2, xhat = A0^T g0 + A1^T g1, the LeakyReLU bit masks) is THREAD-LOCAL:
+// no shuffles, no atomics, deterministic.
+//
+// Warp roles (320 threads): warps 0-7 workers (A generation + epilogue; warp%4 = TMEM lane quarter),
+// warp 8 TMA producer + TMEM allocator, warp 9 MMA issuer (one elected lane).
+// Precisions: TF32 (kind::tf32, operands rounded-to-nearest to tf32) and 3xTF32
+// (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulate in TMEM: fp32-grade accuracy).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
+
 namespace b200vae {
-size_t tc_extra_ws_floats(int, int, int) { return 0; }
-int tc_prepare(const b200vae_icnn_params*, int, int, int, int, float*, cudaStream_t) { return B200VAE_EUNSUP; }
-int tc_fwd(const float*, int, int, int, float, float*, float*, uint32_t*, uint8_t*, int, const float*, cudaStream_t) {
-  return B200VAE_EUNSUP;
+
+constexpr int kTM = 256;          // samples per CTA
+constexpr int kTN = 256;          // accumulator columns per pass
+constexpr int kKB = 16;           // K elements per block (64 B rows, SWIZZLE_64B)
+constexpr int kWorkers = 256;
+constexpr int kTcThreads = 320;
+constexpr int kTileBytes = 256 * 64;   // one 256-row x 64-byte operand tile = 16 KB
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 |
+// SBO(512 B >> 4)<<32 | version(1)<<46 | layout SWIZZLE_64B(4)<<61.  8-row atoms of 64-byte rows.
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
+}
+// kind::tf32 instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 at 17, M>>4 at 24
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+// byte offset of 16-byte chunk c (0..3) of row r (0..255) inside a 256-row x 64 B SWIZZLE_64B tile
+__device__ __forceinline__ uint32_t sw64_off(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
+
+// ------------------------------------------------------------------------------------ TC workspace
+// (floats, after the SIMT layout's `end`)  Hq = H rounded up to 256.
+//   B1hi,B1lo [Hq][Hq]  B1[o][i] = P[o][i]   (GEMM1: rows = output unit o, K = input unit i)
+//   B2hi,B2lo [Hq][Hq]  B2[i][o] = P[o][i]   (GEMM2: rows = input unit i,  K = output unit o)
+//   A0q, A1q  float4[Hq] = (w0, w1, w2, bias)   P1q [Hq]
+struct TcLayout {
+  int Hq;
+  size_t B1hi, B1lo, B2hi, B2lo, A0q, A1q, P1q, end;
+};
+inline TcLayout tc_layout(int d, int H) {
+  (void)d;
+  TcLayout T;
+  T.Hq = round_up(H, 256);
+  const size_t q = (size_t)T.Hq * T.Hq;
+  size_t o = 0;
+  T.B1hi = o; o += q; T.B1lo = o; o += q; T.B2hi = o; o += q; T.B2lo = o; o += q;
+  T.A0q = o; o += (size_t)4 * T.Hq; T.A1q = o; o += (size_t)4 * T.Hq; T.P1q = o; o += T.Hq;
+  T.end = o + 64;
+  return T;
+}
+size_t tc_extra_ws_floats(int d, int H, int precision) {
+  (void)precision;
+  return tc_layout(d, H).end;
+}
+static float* tc_base(float* ws, int d, int H) {
+  // TC arrays start after the largest SIMT layout we might share the buffer with; use a fixed, B-independent
+  // offset: the forward part of the SIMT layout (the backward scratch is placed AFTER the TC arrays, see api.cu)
+  return ws + ws_layout(1, d, H).fwd_end;
+}
+
+__global__ void tc_prepare_kernel(const float* __restrict__ P0, const float* __restrict__ P0T, const float* __restrict__ P1,
+                                  const float* __restrict__ A0p, const float* __restrict__ A1p, int d, int Hp, int Hq,
+                                  float* __restrict__ B1hi, float* __restrict__ B1lo, float* __restrict__ B2hi,
+                                  float* __restrict__ B2lo, float4* __restrict__ A0q, float4* __restrict__ A1q,
+                                  float* __restrict__ P1q) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c < Hq) {
+    const bool in = (r < Hp && c < Hp);
+    const float a = in ? P0[(size_t)r * Hp + c] : 0.f, b = in ? P0T[(size_t)r * Hp + c] : 0.f;
+    const float ah = to_tf32(a), bh = to_tf32(b);
+    B1hi[(size_t)r * Hq + c] = ah; B1lo[(size_t)r * Hq + c] = to_tf32(a - ah);
+    B2hi[(size_t)r * Hq + c] = bh; B2lo[(size_t)r * Hq + c] = to_tf32(b - bh);
+    if (r == 0) {
+      const bool inr = c < Hp;
+      float w[4] = {0.f, 0.f, 0.f, 0.f}, u[4] = {0.f, 0.f, 0.f, 0.f};
+      if (inr) {
+        for (int j = 0; j < d; ++j) { w[j] = A0p[(size_t)c * (d + 1) + j]; u[j] = A1p[(size_t)c * (d + 1) + j]; }
+        w[3] = A0p[(size_t)c * (d + 1) + d]; u[3] = A1p[(size_t)c * (d + 1) + d];
+      }
+      A0q[c] = make_float4(w[0], w[1], w[2], w[3]);
+      A1q[c] = make_float4(u[0], u[1], u[2], u[3]);
+      P1q[c] = inr ? P1[c] : 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ the kernel
+struct TcMaps { CUtensorMap b1hi, b1lo, b2hi, b2lo; };
+
+template <int D>
+__device__ __forceinline__ float lin_of(const float4 q, const float (&z)[D]) {
+  float h = q.w;
+  h = fmaf(q.x, z[0], h);
+  if (D > 1) h = fmaf(q.y, z[D > 1 ? 1 : 0], h);
+  if (D > 2) h = fmaf(q.z, z[D > 2 ? 2 : 0], h);
+  return h;
+}
+__device__ __forceinline__ float comp(const float4 q, int j) { return j == 0 ? q.x : (j == 1 ? q.y : q.z); }
+
+template <int D, bool X3>
+__global__ void __launch_bounds__(kTcThreads, 1)
+icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ z, int B, int Hq, int Hw_out,
+                   float kappa, const float4* __restrict__ A0q_g, const float4* __restrict__ A1q_g,
+                   const float* __restrict__ P1q_g, const float* __restrict__ A2p, float* __restrict__ psi,
+                   float* __restrict__ xhat, uint32_t* __restrict__ mask1, uint8_t* __restrict__ mask2) {
+  constexpr int S = X3 ? 2 : 4;                       // pipeline stages
+  constexpr int kStageBytes = (X3 ? 4 : 2) * kTileBytes;   // A(hi[,lo]) + B(hi[,lo])
+  constexpr int kOffAlo = kTileBytes, kOffB = (X3 ? 2 : 1) * kTileBytes, kOffBlo = 3 * kTileBytes;
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // swizzled operand tiles need a 1024-byte aligned base: align by hand (the launch adds 1 KB of slack)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* stages = smem;                                   // S * kStageBytes
+  float4* A0s = reinterpret_cast<float4*>(smem + S * kStageBytes);
+  float4* A1s = A0s + Hq;
+  float* P1s = reinterpret_cast<float*>(A1s + Hq);
+  uint32_t* maskw = reinterpret_cast<uint32_t*>(P1s + Hq);        // [Hq/32][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(maskw + (Hq / 32) * 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * kTM;
+  const int NP = Hq / kTN, NKB = Hq / kKB;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S),
+                 accempty = smem_u32(bars + 2 * S + 1);
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 8 + 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(accfull, 1);
+    mbar_init(accempty, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  for (int i = tid; i < Hq; i += kTcThreads) { A0s[i] = A0q_g[i]; A1s[i] = A1q_g[i]; P1s[i] = P1q_g[i]; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // =============================== workers: one sample row per thread ===============================
+    const int row = tid;                       // == (warp/4)*128 + (warp%4)*32 + lane
+    const bool valid = (m0 + row) < B;
+    float zr[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) zr[j] = valid ? z[(size_t)(m0 + row) * D + j] : 0.f;
+    const uint32_t taddr_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * kTN);
+    const uint32_t a_row_off = (uint32_t)row * 64u;           // row base; swizzled chunk position added per chunk
+    const int rsw = (row >> 1) & 3;
+    uint32_t it = 0, pp = 0;
+
+    // -------- GEMM1: h1 = x1 . P^T  -> masks, h2 --------
+    float h2 = 0.f;
+    for (int p = 0; p < NP; ++p) {
+      for (int kb = 0; kb < NKB; ++kb, ++it) {
+        const uint32_t s = it % S, ph = (it / S) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        unsigned char* At = stages + s * kStageBytes;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float h = lin_of<D>(A0s[kb * kKB + c * 4 + e], zr);
+            const float a0 = fmaxf(h, kSlope * h);            // LeakyReLU(0.2): max(h, 0.2h)
+            v[e] = a0 * a0;
+          }
+          const uint32_t off = a_row_off + ((uint32_t)(c ^ rsw) << 4);
+          const float4 hi = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+          *reinterpret_cast<float4*>(At + off) = hi;
+          if (X3)
+            *reinterpret_cast<float4*>(At + kOffAlo + off) =
+                make_float4(to_tf32(v[0] - hi.x), to_tf32(v[1] - hi.y), to_tf32(v[2] - hi.z), to_tf32(v[3] - hi.w));
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full0 + 8 * s);
+      }
+      // epilogue of pass p: my row of D[:, p*256 .. +256)
+      mbar_wait(accfull, pp & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < kTN / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(taddr_row + cc * 32, r);
+        tmem_ld_wait();
+        uint32_t word = 0;
+        const int nb = p * kTN + cc * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float h1 = __uint_as_float(r[j]) + lin_of<D>(A1s[nb + j], zr);
+          const bool pos = h1 > 0.f;
+          h2 = fmaf(P1s[nb + j], pos ? h1 : kSlope * h1, h2);
+          word |= (pos ? 1u : 0u) << j;
+        }
+        maskw[(nb >> 5) * 256 + row] = word;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accempty);
+      ++pp;
+    }
+    {
+      float lin = A2p[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) lin = fmaf(A2p[j], zr[j], lin);
+      h2 += lin;
+    }
+    const bool pos2 = h2 > 0.f;
+    const float s2 = pos2 ? 1.f : kSlope;
+    if (valid) {
+      if (psi) psi[m0 + row] = pos2 ? h2 : kSlope * h2;
+      if (mask2) mask2[m0 + row] = pos2 ? 1 : 0;
+      if (mask1)
+        for (int wd = 0; wd < Hw_out; ++wd) mask1[(size_t)(m0 + row) * Hw_out + wd] = maskw[wd * 256 + row];
+    }
+    if (xhat != nullptr) {
+      // -------- GEMM2: gx1 = g1 . P -> g0 -> xhat --------
+      float xacc[D], xa[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) { xacc[j] = 0.f; xa[j] = 0.f; }
+      for (int p = 0; p < NP; ++p) {
+        for (int kb = 0; kb < NKB; ++kb, ++it) {
+          const uint32_t s = it % S, ph = (it / S) & 1;
+          const uint32_t bits = maskw[(kb >> 1) * 256 + row] >> ((kb & 1) * 16);
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          unsigned char* At = stages + s * kStageBytes;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int k = kb * kKB + c * 4 + e;
+              const float c1 = s2 * P1s[k];
+              v[e] = ((bits >> (c * 4 + e)) & 1u) ? c1 : kSlope * c1;
+              if (p == 0) {
+                const float4 q = A1s[k];
+#pragma unroll
+                for (int j = 0; j < D; ++j) xa[j] = fmaf(comp(q, j), v[e], xa[j]);
+              }
+            }
+            const uint32_t off = a_row_off + ((uint32_t)(c ^ rsw) << 4);
+            const float4 hi = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+            *reinterpret_cast<float4*>(At + off) = hi;
+            if (X3)
+              *reinterpret_cast<float4*>(At + kOffAlo + off) =
+                  make_float4(to_tf32(v[0] - hi.x), to_tf32(v[1] - hi.y), to_tf32(v[2] - hi.z), to_tf32(v[3] - hi.w));
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full0 + 8 * s);
+        }
+        mbar_wait(accfull, pp & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < kTN / 32; ++cc) {
+          uint32_t r[32];
+          tmem_ld32(taddr_row + cc * 32, r);
+          tmem_ld_wait();
+          const int nb = p * kTN + cc * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float4 q = A0s[nb + j];
+            const float h = lin_of<D>(q, zr);
+            const float s0 = slope_of(h), a0 = h * s0;
+            const float g0 = __uint_as_float(r[j]) * (2.f * a0) * s0;
+#pragma unroll
+            for (int jj = 0; jj < D; ++jj) xacc[jj] = fmaf(comp(q, jj), g0, xacc[jj]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accempty);
+        ++pp;
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+          xhat[(size_t)(m0 + row) * D + j] = fmaf(2.f * kappa, zr[j], fmaf(s2, A2p[j], xacc[j] + xa[j]));
+      }
+    }
+  } else if (warp == 8) {
+    // =============================== TMA producer: B tiles ===============================
+    if (lane == 0) {
+      const int ngemm = (xhat != nullptr) ? 2 : 1;
+      uint32_t it = 0;
+      for (int g = 0; g < ngemm; ++g) {
+        const CUtensorMap* mhi = g == 0 ? &maps.b1hi : &maps.b2hi;
+        const CUtensorMap* mlo = g == 0 ? &maps.b1lo : &maps.b2lo;
+        for (int p = 0; p < NP; ++p)
+          for (int kb = 0; kb < NKB; ++kb, ++it) {
+            const uint32_t s = it % S, ph = (it / S) & 1;
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            const uint32_t bar = full0 + 8 * s;
+            const uint32_t dst = smem_u32(stages + s * kStageBytes);
+            mbar_arrive_expect_tx(bar, (X3 ? 2 : 1) * kTileBytes);
+            tma_load_2d(dst + kOffB, mhi, bar, kb * kKB, p * kTN);
+            if (X3) tma_load_2d(dst + kOffBlo, mlo, bar, kb * kKB, p * kTN);
+          }
+      }
+    }
+  } else {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const int npass = (xhat != nullptr ? 2 : 1) * NP;
+      uint32_t it = 0;
+      for (int pp = 0; pp < npass; ++pp) {
+        mbar_wait(accempty, (pp & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < NKB; ++kb, ++it) {
+          const uint32_t s = it % S, ph = (it / S) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stages + s * kStageBytes);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t d_t = tmem_base + (uint32_t)(half * kTN);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {                         // two K=8 steps per 64-byte row
+              const uint64_t a_hi = make_desc_sw64(sa + half * (kTileBytes / 2) + ks * 32);
+              const uint64_t b_hi = make_desc_sw64(sa + kOffB + ks * 32);
+              const uint32_t acc = (kb | ks) ? 1u : 0u;
+              if (X3) {
+                const uint64_t a_lo = make_desc_sw64(sa + kOffAlo + half * (kTileBytes / 2) + ks * 32);
+                const uint64_t b_lo = make_desc_sw64(sa + kOffBlo + ks * 32);
+                umma_tf32(d_t, a_lo, b_hi, kIdescTf32, acc);
+                umma_tf32(d_t, a_hi, b_lo, kIdescTf32, 1u);
+                umma_tf32(d_t, a_hi, b_hi, kIdescTf32, 1u);
+              } else {
+                umma_tf32(d_t, a_hi, b_hi, kIdescTf32, acc);
+              }
+            }
+          }
+          umma_commit(empty0 + 8 * s);       // frees the smem stage when these MMAs have read it
+        }
+        umma_commit(accfull);                // accumulator pass complete
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+static int make_map(CUtensorMap* m, const float* base, int Hq) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return B200VAE_ECUDA;
+  const cuuint64_t dims[2] = {(cuuint64_t)Hq, (cuuint64_t)Hq};
+  const cuuint64_t strides[1] = {(cuuint64_t)Hq * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)kTN};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_last_cuda_error = 100000 + (int)r; return B200VAE_ECUDA; }
+  return B200VAE_OK;
+}
+
+int tc_prepare(const b200vae_icnn_params* p, int d, int H, int mode, int precision, float* ws, cudaStream_t st) {
+  (void)p; (void)mode;
+  if (precision == B200VAE_PREC_BF16) return B200VAE_EUNSUP;
+  if (d > 3) return B200VAE_EUNSUP;
+  const WsLayout L = ws_layout(1, d, H);
+  const TcLayout T = tc_layout(d, H);
+  float* tb = tc_base(ws, d, H);
+  dim3 grid((T.Hq + 255) / 256, T.Hq);
+  tc_prepare_kernel<<<grid, 256, 0, st>>>(ws + L.P0, ws + L.P0T, ws + L.P1, ws + L.A0p, ws + L.A1p, d, L.Hp, T.Hq,
+                                          tb + T.B1hi, tb + T.B1lo, tb + T.B2hi, tb + T.B2lo,
+                                          reinterpret_cast<float4*>(tb + T.A0q), reinterpret_cast<float4*>(tb + T.A1q),
+                                          tb + T.P1q);
+  return check_launch();
+}
+
+template <int D, bool X3>
+static int launch_tc(const TcMaps& maps, const float* z, int B, const TcLayout& T, const float* tb, const float* A2p,
+                     int Hw_out, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2, cudaStream_t st) {
+  constexpr int S = X3 ? 2 : 4;
+  const size_t smem = (size_t)S * (X3 ? 4 : 2) * kTileBytes + (size_t)T.Hq * (16 + 16 + 4) + (size_t)(T.Hq / 32) * 256 * 4 +
+                      (2 * S + 2) * 8 + 16 + 1024;
+  if (smem > 227 * 1024) return B200VAE_EUNSUP;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(icnn_tc_fwd_kernel<D, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_done = true;
+  }
+  const int grid = (B + kTM - 1) / kTM;
+  icnn_tc_fwd_kernel<D, X3><<<grid, kTcThreads, smem, st>>>(
+      maps, z, B, T.Hq, Hw_out, kappa, reinterpret_cast<const float4*>(tb + T.A0q),
+      reinterpret_cast<const float4*>(tb + T.A1q), tb + T.P1q, A2p, psi, xhat, mask1, mask2);
+  return check_launch();
+}
+
+int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2,
+           int precision, const float* ws, cudaStream_t st) {
+  if (precision == B200VAE_PREC_BF16 || d > 3) return B200VAE_EUNSUP;
+  const WsLayout L = ws_layout(1, d, H);
+  const TcLayout T = tc_layout(d, H);
+  const float* tb = tc_base(const_cast<float*>(ws), d, H);
+  // tensor maps only encode (address, shape): cache them per prepared buffer
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, TcMaps> cache;
+  TcMaps maps;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    const uint64_t key = reinterpret_cast<uint64_t>(tb) ^ ((uint64_t)T.Hq << 48);
+    auto itc = cache.find(key);
+    if (itc == cache.end()) {
+      int rc = make_map(&maps.b1hi, tb + T.B1hi, T.Hq);
+      if (!rc) rc = make_map(&maps.b1lo, tb + T.B1lo, T.Hq);
+      if (!rc) rc = make_map(&maps.b2hi, tb + T.B2hi, T.Hq);
+      if (!rc) rc = make_map(&maps.b2lo, tb + T.B2lo, T.Hq);
+      if (rc) return rc;
+      if (cache.size() > 256) cache.clear();
+      cache.emplace(key, maps);
+    } else {
+      maps = itc->second;
+    }
+  }
+  const bool x3 = (precision == B200VAE_PREC_TF32X3);
+  const int Hw_out = L.Hp / 32;
+#define B200VAE_TC(DD)                                                                                          \
+  return x3 ? launch_tc<DD, true>(maps, z, B, T, tb, ws + L.A2p, Hw_out, kappa, psi, xhat, mask1, mask2, st)   \
+            : launch_tc<DD, false>(maps, z, B, T, tb, ws + L.A2p, Hw_out, kappa, psi, xhat, mask1, mask2, st)
+  switch (d) {
+    case 1: B200VAE_TC(1);
+    case 2: B200VAE_TC(2);
+    case 3: B200VAE_TC(3);
+    default: return B200VAE_EUNSUP;
+  }
+#undef B200VAE_TC
+}
+
 }  // namespace b200vae
