@@ -1,0 +1,87 @@
+"""tcgen05 (TF32 / 3xTF32) variants of the fused ICNN forward: stated, looser bounds than the FP32 path.
+
+Bounds (vs the fp64 oracle on fp32-rounded inputs, |a-b| <= rtol*|b| + rtol*max|b|):
+    tf32x3 : psi 3e-5, xhat 1e-4 (kink flips excepted)   -- fp32-grade split; residual error is the tensor
+             core's truncating fp32 accumulation over K (grows ~linearly with H)
+    tf32   : psi 2e-4, xhat 5e-3 (kink flips excepted)
+The backward of these modes reuses the saved masks and runs the FP32 kernels, so parameter gradients keep
+the FP32 bound (1e-4) whenever no mask flipped."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import icnn_oracle as io
+
+from helpers import KEYS, close_report, f32_as_f64, params_f32_as_f64, params_to_torch
+
+pytestmark = pytest.mark.gpu
+BOUNDS = {3: (3e-5, 1e-4), 1: (2e-4, 5e-3)}
+CASES = [(2, 256, 256, "mixed"), (2, 96, 77, "mixed"), (1, 64, 300, "mixed"), (3, 512, 1000, "mixed"),
+         (2, 1024, 2048, "mixed"), (2, 512, 513, "default")]
+
+
+@pytest.mark.parametrize("prec", [3, 1], ids=["tf32x3", "tf32"])
+@pytest.mark.parametrize("case", CASES, ids=[f"d{c[0]}_h{c[1]}_b{c[2]}_{c[3]}" for c in CASES])
+def test_tc_forward_vs_oracle(case, prec):
+    from vae_song_b200 import ops
+    d, H, B, regime = case
+    rng = np.random.default_rng(H + B)
+    p = io.random_params(rng, d, H, np.float64, regime)
+    z = rng.normal(0, 1, (B, d))
+    zt = torch.tensor(z, dtype=torch.float32, device="cuda")
+    psi, xhat = ops.IcnnBrenierFn.apply(zt, 0.15, 0, prec, *params_to_torch(p))
+    rpsi, rxhat, _ = io.icnn_brenier(f32_as_f64(z), params_f32_as_f64(p), 0, 0.15)
+    rp, rx = BOUNDS[prec]
+    close_report(psi.cpu().numpy(), rpsi, rp, "psi")
+    close_report(xhat.cpu().numpy(), rxhat, rx, "xhat", bad_frac=0.02)
+
+
+@pytest.mark.parametrize("prec", [3, 1], ids=["tf32x3", "tf32"])
+def test_tc_matches_fp32_path_and_backward_runs(prec):
+    """Same module, precision switched: outputs agree with the FP32 kernels within the stated bound, and the
+    training backward (masks from the tensor-core forward) matches the oracle evaluated with those masks'
+    semantics (FP32 bound on the gradients)."""
+    from vae_song_b200 import ops
+    rng = np.random.default_rng(77)
+    d, H, B = 2, 512, 700
+    p = io.random_params(rng, d, H, np.float64, "mixed")
+    z, v = rng.normal(0, 1, (B, d)), rng.normal(0, 1, (B, d))
+    outs = {}
+    for pr in (0, prec):
+        ps = [t.requires_grad_(True) for t in params_to_torch(p)]
+        zt = torch.tensor(z, dtype=torch.float32, device="cuda", requires_grad=True)
+        psi, xhat = ops.IcnnBrenierFn.apply(zt, 0.1, 0, pr, *ps)
+        (xhat * torch.tensor(v, dtype=torch.float32, device="cuda")).sum().backward()
+        outs[pr] = (psi.detach().cpu().numpy(), xhat.detach().cpu().numpy(), zt.grad.cpu().numpy(),
+                    {k: t.grad.cpu().numpy() for k, t in zip(KEYS, ps)})
+    rp, rx = BOUNDS[prec]
+    close_report(outs[prec][0], outs[0][0], rp, "psi vs fp32 path")
+    close_report(outs[prec][1], outs[0][1], rx, "xhat vs fp32 path", bad_frac=0.02)
+    close_report(outs[prec][2], outs[0][2], 5e-3, "dz vs fp32 path", bad_frac=0.02)
+    for k in ("A0w", "A0b", "A1w", "A2w", "W0", "W1"):
+        close_report(outs[prec][3][k], outs[0][3][k], 5e-3, "grad " + k)
+
+
+def test_tc_full_size_tiling_invariance():
+    from vae_song_b200 import ops
+    rng = np.random.default_rng(3)
+    p = io.random_params(rng, 2, 1024, np.float64, "mixed")
+    params = params_to_torch(p)
+    z = torch.tensor(rng.normal(0, 1, (65536, 2)), dtype=torch.float32, device="cuda")
+    for prec in (1, 3):
+        psi, xhat = ops.IcnnBrenierFn.apply(z, 0.1, 0, prec, *params)
+        sel = torch.arange(0, 65536, 509, device="cuda")
+        psi_s, xhat_s = ops.IcnnBrenierFn.apply(z[sel].contiguous(), 0.1, 0, prec, *params)
+        assert torch.equal(psi[sel], psi_s) and torch.equal(xhat[sel], xhat_s)     # row results are tile independent
+        assert torch.isfinite(xhat).all()
+
+
+def test_tc_unsupported_is_loud():
+    from vae_song_b200 import _C, ops
+    rng = np.random.default_rng(1)
+    p = io.random_params(rng, 4, 64, np.float64, "mixed")
+    with pytest.raises(_C.B200VaeError):
+        ops.IcnnBrenierFn.apply(torch.zeros(8, 4, device="cuda"), 0.0, 0, 1, *params_to_torch(p))   # d=4 on the TC path
+    with pytest.raises(_C.B200VaeError):
+        ops.IcnnBrenierFn.apply(torch.zeros(8, 2, device="cuda"), 0.0, 0, 2,
+                                *params_to_torch(io.random_params(rng, 2, 64, np.float64, "mixed")))  # bf16 not built
