@@ -13,6 +13,15 @@ from helpers import close_report
 
 pytestmark = pytest.mark.gpu
 
+
+def bn_shadowed(name, model):
+    """Bias of a Linear that feeds a BatchNorm directly (block index 0 -> BN at index 1): its gradient is
+    mathematically zero, both implementations return pure rounding noise (and Adam turns that noise into
+    +-lr steps that no output depends on), so these entries are excluded from elementwise comparisons."""
+    if not name.endswith(".0.bias"):
+        return False
+    return name[:-len("0.bias")] + "1.running_mean" in model.state_dict()
+
 CASES = {
     "pin_small": dict(dataset="pinwheel", icnn_channels=[64, 128], hidden_channels=[16, 8], inverse_lipschitz=0.3, beta=0.7),
     "pin_logmse": dict(dataset="chessboard", icnn_channels=[32, 64], hidden_channels=[8, 8, 4], inverse_lipschitz=0.0,
@@ -52,6 +61,9 @@ def test_lidvae_forward_loss_grads(name):
         gscale = max(np.abs(G[pre + "grad/" + k]).max() for k, _ in m.named_parameters())
         for k, q in m.named_parameters():
             ref = G[pre + "grad/" + k]
+            if bn_shadowed(k, m):
+                assert float(q.grad.abs().max()) <= 1e-4 * gscale, k
+                continue
             if np.abs(ref).max() == 0:
                 assert q.grad is None or float(q.grad.abs().max()) == 0.0, k
             else:
@@ -117,7 +129,8 @@ def test_train_loop_matches_torch_composition():
         l2.backward(); o2.step()
         assert abs(float(l1) - float(l2)) <= 2e-4 * abs(float(l2)), (step, float(l1), float(l2))
     for (k, a), (_, b) in zip(m.named_parameters(), ref.named_parameters()):
-        close_report(a.detach().cpu().numpy(), b.detach().cpu().numpy(), 1e-3, "param " + k)
+        if not bn_shadowed(k, m):
+            close_report(a.detach().cpu().numpy(), b.detach().cpu().numpy(), 1e-3, "param " + k)
 
 
 def test_flexible_family_losses_and_staged_backward():
@@ -143,6 +156,8 @@ def test_flexible_family_losses_and_staged_backward():
     lreg.backward(retain_graph=True)
     lrec.backward()
     staged = [q.grad.clone() for q in m.parameters()]
+    names = [k for k, _ in m.named_parameters()]
+    gscale = max(float(g.abs().max()) for g in staged)
     # same thing composed from plain torch ops on the same graph inputs
     m.zero_grad()
     recon, mu, lv, z_in, z_rec = m(x, L=4, eps=eps)
@@ -155,5 +170,8 @@ def test_flexible_family_losses_and_staged_backward():
             q.grad *= 1e-4
     l_reg.backward(retain_graph=True)
     l_rec.backward()
-    for a, q in zip(staged, m.parameters()):
-        close_report(a.cpu().numpy(), q.grad.cpu().numpy(), 1e-4, "staged grad")
+    for k, a, q in zip(names, staged, m.parameters()):
+        if bn_shadowed(k, m):
+            assert float(a.abs().max()) <= 1e-4 * gscale
+        else:
+            close_report(a.cpu().numpy(), q.grad.cpu().numpy(), 1e-4, "staged grad " + k, floor=1e-6 * gscale)
