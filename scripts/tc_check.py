@@ -50,3 +50,24 @@ if __name__ == "__main__":
             ms = e0.elapsed_time(e1) / 10
             tf = io.flops_decode(2, H) * 65536 / ms / 1e9
             print(f"   TIMING {names[prec]} H={H}: {ms:.3f} ms  -> {tf:.1f} TFLOP/s algorithmic, {65536/ms/1e3:.2f} M samples/s")
+            # backward (rows + dP0 + finalize)
+            rng = np.random.default_rng(5)
+            p = io.random_params(rng, 2, H, np.float64, "mixed")
+            P = params_t(p)
+            wsb = ops.icnn_prepare(P, 2, H, 0, prec, 65536, True)
+            vt = torch.randn(65536, 2, device="cuda")
+            _, _, m1, m2 = ops.icnn_decode_fwd(zt, wsb, 2, H, 0, 0.1, prec, True, True, True)
+            for _ in range(2):
+                ops.icnn_decode_bwd(zt, vt, None, m1, m2, P, wsb, 2, H, 0, 0.1, prec)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                dzz, gg = ops.icnn_decode_bwd(zt, vt, None, m1, m2, P, wsb, 2, H, 0, 0.1, prec)
+            e1.record(); torch.cuda.synchronize()
+            msb = e0.elapsed_time(e1) / 5
+            print(f"   TIMING {names[prec]} H={H} backward: {msb:.3f} ms ({io.flops_train(2,H)*65536/ (ms+msb)/1e9:.1f} TFLOP/s train-algorithmic fwd+bwd)")
+            if prec != 0:
+                ws0 = ops.icnn_prepare(P, 2, H, 0, 0, 65536, True)
+                dz0, g0 = ops.icnn_decode_bwd(zt, vt, None, m1, m2, P, ws0, 2, H, 0, 0.1, 0)
+                rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+                print("      bwd vs fp32 kernels (same masks): dz %.2e" % rel(dzz, dz0), " ".join(f"{k}:{rel(a, b):.1e}" for k, a, b in zip(io.PARAM_KEYS, gg, g0) if float(b.abs().max()) > 0))

@@ -57,9 +57,11 @@ def test_tc_matches_fp32_path_and_backward_runs(prec):
     rp, rx = BOUNDS[prec]
     close_report(outs[prec][0], outs[0][0], rp, "psi vs fp32 path")
     close_report(outs[prec][1], outs[0][1], rx, "xhat vs fp32 path", bad_frac=0.02)
-    close_report(outs[prec][2], outs[0][2], 5e-3, "dz vs fp32 path", bad_frac=0.02)
+    gtol = 3e-4 if prec == 3 else 5e-3     # tensor-core backward (rows kernel) in the same precision
+    close_report(outs[prec][2], outs[0][2], gtol, "dz vs fp32 path", bad_frac=0.02)
     for k in ("A0w", "A0b", "A1w", "A2w", "W0", "W1"):
-        close_report(outs[prec][3][k], outs[0][3][k], 5e-3, "grad " + k)
+        close_report(outs[prec][3][k], outs[0][3][k], gtol, "grad " + k)
+    assert float(np.abs(outs[prec][3]["A1b"]).max()) == 0.0 and float(np.abs(outs[prec][3]["A2b"]).max()) == 0.0
 
 
 def test_tc_full_size_tiling_invariance():

@@ -26,6 +26,10 @@ int tc_prepare(const b200vae_icnn_params* p, int d, int H, int mode, int precisi
 int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1,
            uint8_t* mask2, int precision, const float* ws, cudaStream_t st);
 size_t tc_extra_ws_floats(int d, int H, int precision);
+size_t tc_bwd_ws_floats(int B, int d, int H);
+int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H,
+           const b200vae_icnn_params* p, int mode, float kappa, const b200vae_icnn_grads* g, float* dz, int precision,
+           float* ws, cudaStream_t st);
 
 static bool params_ok(const b200vae_icnn_params* p) {
   return p && p->A0w && p->A0b && p->A1w && p->A1b && p->A2w && p->A2b && p->W0 && p->W1 && aligned4(p->A0w) &&
@@ -46,7 +50,7 @@ extern "C" size_t b200vae_icnn_workspace_bytes(int B, int d, int H, int precisio
   if (B <= 0 || d <= 0 || H <= 0) return 0;
   const size_t extra = (precision != B200VAE_PREC_FP32) ? tc_extra_ws_floats(d, H, precision) : 0;
   const WsLayout L = ws_layout(B, d, H, extra);
-  const size_t fl = for_backward ? L.end : L.fwd_end + extra + 64;
+  const size_t fl = for_backward ? L.end + (extra ? tc_bwd_ws_floats(B, d, H) : 0) : L.fwd_end + extra + 64;
   return fl * sizeof(float) + 256;
 }
 
@@ -91,7 +95,8 @@ extern "C" int b200vae_icnn_decode_bwd(const float* z, const float* v, const flo
   if (rc) return rc;
   if (!prec_ok(precision)) return B200VAE_EUNSUP;
   if (ws_bytes < b200vae_icnn_workspace_bytes(B, d, H, precision, 1)) return B200VAE_EWS;
-  // the backward contractions run in FP32 SIMT for every precision in this build
+  if (precision != B200VAE_PREC_FP32 && !gpsi)   // tensor-core backward (gpsi path stays on the FP32 kernels)
+    return tc_bwd(z, v, mask1, mask2, B, d, H, p, weight_mode, kappa, grads, dz, precision, ws_base(ws), (cudaStream_t)stream);
   const size_t extra = (precision != B200VAE_PREC_FP32) ? tc_extra_ws_floats(d, H, precision) : 0;
   return simt_bwd(z, v, gpsi, mask1, mask2, B, d, H, p, weight_mode, kappa, grads, dz, ws_base(ws), extra,
                   (cudaStream_t)stream);

@@ -721,6 +721,35 @@ static int launch_bwd(const float* z, const float* v, const float* gpsi, const u
   return rc;
 }
 
+template <int D>
+static int launch_dP0_only(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B,
+                           const WsLayout& L, float* ws, cudaStream_t st) {
+  int rows = (B + L.splits - 1) / L.splits;
+  rows = round_up(rows, kBK);
+  dim3 grid(L.Hp / kBN, L.Hp / kBM, L.splits);
+  icnn_bwd_dP0_kernel<D, false><<<grid, kThreads, 0, st>>>(z, v, nullptr, mask1, mask2, B, L.Hp, rows, ws + L.A0p,
+                                                            ws + L.dP0part);
+  return check_launch();
+}
+
+// dW0 only (FP32 SIMT): used by the tensor-core backward until its own dP0 kernel takes over
+int simt_bwd_W0(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H,
+                const b200vae_icnn_params* p, int mode, float* gW0, float* ws, size_t mid_extra, cudaStream_t st) {
+  const WsLayout L = ws_layout(B, d, H, mid_extra);
+  int rc;
+  switch (d) {
+    case 1: rc = launch_dP0_only<1>(z, v, mask1, mask2, B, L, ws, st); break;
+    case 2: rc = launch_dP0_only<2>(z, v, mask1, mask2, B, L, ws, st); break;
+    case 3: rc = launch_dP0_only<3>(z, v, mask1, mask2, B, L, ws, st); break;
+    case 4: rc = launch_dP0_only<4>(z, v, mask1, mask2, B, L, ws, st); break;
+    default: return B200VAE_EUNSUP;
+  }
+  if (rc) return rc;
+  dim3 grid((H + 255) / 256, H);
+  finalize_W0_kernel<<<grid, 256, 0, st>>>(ws + L.dP0part, L.splits, H, L.Hp, ws + L.P0, ws + L.P1, p->W0, mode, gW0);
+  return check_launch();
+}
+
 int simt_prepare(const b200vae_icnn_params* p, int d, int H, int mode, float* ws, cudaStream_t st) {
   const WsLayout L = ws_layout(128, d, H);
   dim3 grid(L.Hp / 32, L.Hp / 32), block(32, 8);

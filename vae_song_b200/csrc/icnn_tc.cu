@@ -27,8 +27,6 @@ namespace b200vae {
 constexpr int kTM = 256;          // samples per CTA
 constexpr int kTN = 256;          // accumulator columns per pass
 constexpr int kKB = 16;           // K elements per block (64 B rows, SWIZZLE_64B)
-constexpr int kWorkers = 256;
-constexpr int kTcThreads = 320;
 constexpr int kTileBytes = 256 * 64;   // one 256-row x 64-byte operand tile = 16 KB
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -157,8 +155,11 @@ __global__ void tc_prepare_kernel(const float* __restrict__ P0, const float* __r
   }
 }
 
-// ------------------------------------------------------------------------------------ the kernel
+// ------------------------------------------------------------------------------------ the kernels
 struct TcMaps { CUtensorMap b1hi, b1lo, b2hi, b2lo; };
+
+constexpr int kNW = 16;                 // worker warps: 2 threads per sample row (K halves / column halves)
+constexpr int kTcThreads = (kNW + 2) * 32;
 
 template <int D>
 __device__ __forceinline__ float lin_of(const float4 q, const float (&z)[D]) {
@@ -168,114 +169,271 @@ __device__ __forceinline__ float lin_of(const float4 q, const float (&z)[D]) {
   if (D > 2) h = fmaf(q.z, z[D > 2 ? 2 : 0], h);
   return h;
 }
+template <int D>
+__device__ __forceinline__ float dot_of(const float4 q, const float (&v)[D]) {
+  float h = q.x * v[0];
+  if (D > 1) h = fmaf(q.y, v[D > 1 ? 1 : 0], h);
+  if (D > 2) h = fmaf(q.z, v[D > 2 ? 2 : 0], h);
+  return h;
+}
 __device__ __forceinline__ float comp(const float4 q, int j) { return j == 0 ? q.x : (j == 1 ? q.y : q.z); }
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kNW * 32) : "memory"); }
 
+template <bool X3>
+struct TcCfg {
+  static constexpr int S = X3 ? 2 : 4;                          // pipeline stages
+  static constexpr int kStageBytes = (X3 ? 4 : 2) * kTileBytes; // A(hi[,lo]) + B(hi[,lo])
+  static constexpr int kOffAlo = kTileBytes, kOffB = (X3 ? 2 : 1) * kTileBytes, kOffBlo = 3 * kTileBytes;
+};
+
+// shared-memory carve-up common to the forward and backward kernels
+struct TcSmem {
+  unsigned char* stages;
+  float4 *A0s, *A1s;
+  float* P1s;
+  uint32_t* maskw;     // [Hq/32][256]  word-major so that a thread's own row is bank-conflict free
+  float* xch;          // [2][256][4] exchange between the two threads of a row
+  uint32_t full0, empty0, accfull, accempty;
+  uint32_t* tmem_slot;
+};
+template <bool X3>
+__device__ __forceinline__ TcSmem carve(unsigned char* smem_raw, int Hq) {
+  using C = TcCfg<X3>;
+  TcSmem m;
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle needs 1 KB alignment
+  m.stages = smem;
+  m.A0s = reinterpret_cast<float4*>(smem + C::S * C::kStageBytes);
+  m.A1s = m.A0s + Hq;
+  m.P1s = reinterpret_cast<float*>(m.A1s + Hq);
+  m.maskw = reinterpret_cast<uint32_t*>(m.P1s + Hq);
+  m.xch = reinterpret_cast<float*>(m.maskw + (Hq / 32) * 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(m.xch + 2 * 256 * 4);
+  m.full0 = smem_u32(bars); m.empty0 = smem_u32(bars + C::S);
+  m.accfull = smem_u32(bars + 2 * C::S); m.accempty = smem_u32(bars + 2 * C::S + 1);
+  m.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::S + 2);
+  return m;
+}
+template <bool X3>
+static size_t tc_smem_bytes(int Hq) {
+  using C = TcCfg<X3>;
+  return (size_t)C::S * C::kStageBytes + (size_t)Hq * (16 + 16 + 4) + (size_t)(Hq / 32) * 256 * 4 + 2 * 256 * 4 * 4 +
+         (2 * C::S + 2) * 8 + 16 + 1024;
+}
+
+template <bool X3>
+__device__ __forceinline__ uint32_t tc_setup(const TcSmem& m, int Hq, const float4* A0q_g, const float4* A1q_g,
+                                              const float* P1q_g) {
+  using C = TcCfg<X3>;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < C::S; ++s) { mbar_init(m.full0 + 8 * s, kNW + 1); mbar_init(m.empty0 + 8 * s, 1); }
+    mbar_init(m.accfull, 1);
+    mbar_init(m.accempty, kNW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kNW) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(m.tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  for (int i = tid; i < Hq; i += kTcThreads) { m.A0s[i] = A0q_g[i]; m.A1s[i] = A1q_g[i]; m.P1s[i] = P1q_g[i]; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *m.tmem_slot;
+}
+__device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == kNW) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// TMA producer: for each GEMM g (maps hi[g]/lo[g]) stream NP x NKB B tiles through the stage ring
+template <bool X3>
+__device__ __forceinline__ void tc_tma_role(const TcSmem& m, const CUtensorMap* const* hi, const CUtensorMap* const* lo,
+                                            int ngemm, int NP, int NKB) {
+  using C = TcCfg<X3>;
+  uint32_t it = 0;
+  for (int g = 0; g < ngemm; ++g)
+    for (int p = 0; p < NP; ++p)
+      for (int kb = 0; kb < NKB; ++kb, ++it) {
+        const uint32_t s = it % C::S, ph = (it / C::S) & 1;
+        mbar_wait(m.empty0 + 8 * s, ph ^ 1);
+        const uint32_t bar = m.full0 + 8 * s;
+        const uint32_t dst = smem_u32(m.stages + s * C::kStageBytes);
+        mbar_arrive_expect_tx(bar, (X3 ? 2 : 1) * kTileBytes);
+        tma_load_2d(dst + C::kOffB, hi[g], bar, kb * kKB, p * kTN);
+        if (X3) tma_load_2d(dst + C::kOffBlo, lo[g], bar, kb * kKB, p * kTN);
+      }
+}
+// MMA issuer: npass accumulator passes of NKB K-blocks; D[256 x 256] = two M=128 blocks sharing B
+template <bool X3>
+__device__ __forceinline__ void tc_mma_role(const TcSmem& m, uint32_t tmem_base, int npass, int NKB) {
+  using C = TcCfg<X3>;
+  uint32_t it = 0;
+  for (int pp = 0; pp < npass; ++pp) {
+    mbar_wait(m.accempty, (pp & 1) ^ 1);
+    tc_fence_after();
+    for (int kb = 0; kb < NKB; ++kb, ++it) {
+      const uint32_t s = it % C::S, ph = (it / C::S) & 1;
+      mbar_wait(m.full0 + 8 * s, ph);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(m.stages + s * C::kStageBytes);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t d_t = tmem_base + (uint32_t)(half * kTN);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {                         // two K=8 steps per 64-byte row
+          const uint64_t a_hi = make_desc_sw64(sa + half * (kTileBytes / 2) + ks * 32);
+          const uint64_t b_hi = make_desc_sw64(sa + C::kOffB + ks * 32);
+          const uint32_t acc = (kb | ks) ? 1u : 0u;
+          if (X3) {
+            const uint64_t a_lo = make_desc_sw64(sa + C::kOffAlo + half * (kTileBytes / 2) + ks * 32);
+            const uint64_t b_lo = make_desc_sw64(sa + C::kOffBlo + ks * 32);
+            umma_tf32(d_t, a_lo, b_hi, kIdescTf32, acc);
+            umma_tf32(d_t, a_hi, b_lo, kIdescTf32, 1u);
+            umma_tf32(d_t, a_hi, b_hi, kIdescTf32, 1u);
+          } else {
+            umma_tf32(d_t, a_hi, b_hi, kIdescTf32, acc);
+          }
+        }
+      }
+      umma_commit(m.empty0 + 8 * s);       // frees the smem stage when these MMAs have read it
+    }
+    umma_commit(m.accfull);                // accumulator pass complete
+  }
+}
+
+// per-thread worker context: row = tid & 255; `kh` selects the K half it generates and the column half it drains
+struct Worker {
+  int row, kh, warp, lane, rsw;
+  uint32_t a_row_off, taddr, it, pp;
+};
+__device__ __forceinline__ Worker make_worker(uint32_t tmem_base) {
+  Worker w;
+  const int tid = threadIdx.x;
+  w.row = tid & 255; w.kh = tid >> 8; w.warp = tid >> 5; w.lane = tid & 31;
+  w.rsw = (w.row >> 1) & 3;
+  w.a_row_off = (uint32_t)w.row * 64u;
+  // TMEM: lane quarter = warp%4, accumulator half (rows 128..255) = (warp>>2)&1, column half = kh
+  w.taddr = tmem_base + ((uint32_t)((w.warp & 3) * 32) << 16) + (uint32_t)(((w.warp >> 2) & 1) * kTN + w.kh * (kTN / 2));
+  w.it = 0; w.pp = 0;
+  return w;
+}
+// generate my 8 K-elements (2 chunks) of K-block `kb` with gen(k) and publish the stage
+template <bool X3, class Gen>
+__device__ __forceinline__ void worker_produce(const TcSmem& m, Worker& w, int kb, Gen&& gen) {
+  using C = TcCfg<X3>;
+  const uint32_t s = w.it % C::S, ph = (w.it / C::S) & 1;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = gen(kb * kKB + w.kh * 8 + e, e);
+  mbar_wait(m.empty0 + 8 * s, ph ^ 1);
+  unsigned char* At = m.stages + s * C::kStageBytes;
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c = w.kh * 2 + cc;
+    const uint32_t off = w.a_row_off + ((uint32_t)(c ^ w.rsw) << 4);
+    const float4 hi = make_float4(to_tf32(v[cc * 4 + 0]), to_tf32(v[cc * 4 + 1]), to_tf32(v[cc * 4 + 2]), to_tf32(v[cc * 4 + 3]));
+    *reinterpret_cast<float4*>(At + off) = hi;
+    if (X3)
+      *reinterpret_cast<float4*>(At + C::kOffAlo + off) =
+          make_float4(to_tf32(v[cc * 4 + 0] - hi.x), to_tf32(v[cc * 4 + 1] - hi.y), to_tf32(v[cc * 4 + 2] - hi.z),
+                      to_tf32(v[cc * 4 + 3] - hi.w));
+  }
+  fence_async_smem();
+  __syncwarp();
+  if (w.lane == 0) mbar_arrive(m.full0 + 8 * s);
+  ++w.it;
+}
+// drain my row's 128 accumulator columns of the finished pass: chunk(r[32], first_column_in_pass)
+template <class Chunk>
+__device__ __forceinline__ void worker_drain(const TcSmem& m, Worker& w, Chunk&& chunk) {
+  mbar_wait(m.accfull, w.pp & 1);
+  tc_fence_after();
+#pragma unroll 1
+  for (int cc = 0; cc < kTN / 64; ++cc) {
+    uint32_t r[32];
+    tmem_ld32(w.taddr + cc * 32, r);
+    tmem_ld_wait();
+    chunk(r, w.kh * (kTN / 2) + cc * 32);
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (w.lane == 0) mbar_arrive(m.accempty);
+  ++w.pp;
+}
+
+// sum over the 32 lanes of a warp of 32 per-lane values: lane l returns sum_lanes e[l] (31 shuffles).
+// `a` holds the 16 values left after the caller folded lane bit 4 (columns i / i+16).
+__device__ __forceinline__ float fold16(float (&a)[16], int lane) {
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? a[i] : a[i + off];
+      const float keep = up ? a[i + off] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return a[0];
+}
+__device__ __forceinline__ float fold_first(float lo_col, float hi_col, int lane) {   // lane bit 4: columns i vs i+16
+  const bool up = (lane & 16) != 0;
+  const float send = up ? lo_col : hi_col, keep = up ? hi_col : lo_col;
+  return keep + __shfl_xor_sync(0xffffffffu, send, 16);
+}
+
+// =========================================== forward =================================================
 template <int D, bool X3>
 __global__ void __launch_bounds__(kTcThreads, 1)
 icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ z, int B, int Hq, int Hw_out,
                    float kappa, const float4* __restrict__ A0q_g, const float4* __restrict__ A1q_g,
                    const float* __restrict__ P1q_g, const float* __restrict__ A2p, float* __restrict__ psi,
                    float* __restrict__ xhat, uint32_t* __restrict__ mask1, uint8_t* __restrict__ mask2) {
-  constexpr int S = X3 ? 2 : 4;                       // pipeline stages
-  constexpr int kStageBytes = (X3 ? 4 : 2) * kTileBytes;   // A(hi[,lo]) + B(hi[,lo])
-  constexpr int kOffAlo = kTileBytes, kOffB = (X3 ? 2 : 1) * kTileBytes, kOffBlo = 3 * kTileBytes;
-
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // swizzled operand tiles need a 1024-byte aligned base: align by hand (the launch adds 1 KB of slack)
-  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* stages = smem;                                   // S * kStageBytes
-  float4* A0s = reinterpret_cast<float4*>(smem + S * kStageBytes);
-  float4* A1s = A0s + Hq;
-  float* P1s = reinterpret_cast<float*>(A1s + Hq);
-  uint32_t* maskw = reinterpret_cast<uint32_t*>(P1s + Hq);        // [Hq/32][256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(maskw + (Hq / 32) * 256);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 2);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TcSmem m = carve<X3>(smem_raw, Hq);
+  const uint32_t tmem_base = tc_setup<X3>(m, Hq, A0q_g, A1q_g, P1q_g);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kTM;
   const int NP = Hq / kTN, NKB = Hq / kKB;
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S),
-                 accempty = smem_u32(bars + 2 * S + 1);
+  const int ngemm = (xhat != nullptr) ? 2 : 1;
 
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 8 + 1); mbar_init(empty0 + 8 * s, 1); }
-    mbar_init(accfull, 1);
-    mbar_init(accempty, 8);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  for (int i = tid; i < Hq; i += kTcThreads) { A0s[i] = A0q_g[i]; A1s[i] = A1q_g[i]; P1s[i] = P1q_g[i]; }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 8) {
-    // =============================== workers: one sample row per thread ===============================
-    const int row = tid;                       // == (warp/4)*128 + (warp%4)*32 + lane
-    const bool valid = (m0 + row) < B;
+  if (warp < kNW) {
+    Worker w = make_worker(tmem_base);
+    const bool valid = (m0 + w.row) < B;
     float zr[D];
 #pragma unroll
-    for (int j = 0; j < D; ++j) zr[j] = valid ? z[(size_t)(m0 + row) * D + j] : 0.f;
-    const uint32_t taddr_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * kTN);
-    const uint32_t a_row_off = (uint32_t)row * 64u;           // row base; swizzled chunk position added per chunk
-    const int rsw = (row >> 1) & 3;
-    uint32_t it = 0, pp = 0;
+    for (int j = 0; j < D; ++j) zr[j] = valid ? z[(size_t)(m0 + w.row) * D + j] : 0.f;
 
     // -------- GEMM1: h1 = x1 . P^T  -> masks, h2 --------
     float h2 = 0.f;
     for (int p = 0; p < NP; ++p) {
-      for (int kb = 0; kb < NKB; ++kb, ++it) {
-        const uint32_t s = it % S, ph = (it / S) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        unsigned char* At = stages + s * kStageBytes;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float h = lin_of<D>(A0s[kb * kKB + c * 4 + e], zr);
-            const float a0 = fmaxf(h, kSlope * h);            // LeakyReLU(0.2): max(h, 0.2h)
-            v[e] = a0 * a0;
-          }
-          const uint32_t off = a_row_off + ((uint32_t)(c ^ rsw) << 4);
-          const float4 hi = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
-          *reinterpret_cast<float4*>(At + off) = hi;
-          if (X3)
-            *reinterpret_cast<float4*>(At + kOffAlo + off) =
-                make_float4(to_tf32(v[0] - hi.x), to_tf32(v[1] - hi.y), to_tf32(v[2] - hi.z), to_tf32(v[3] - hi.w));
-        }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full0 + 8 * s);
-      }
-      // epilogue of pass p: my row of D[:, p*256 .. +256)
-      mbar_wait(accfull, pp & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < kTN / 32; ++cc) {
-        uint32_t r[32];
-        tmem_ld32(taddr_row + cc * 32, r);
-        tmem_ld_wait();
+      for (int kb = 0; kb < NKB; ++kb)
+        worker_produce<X3>(m, w, kb, [&](int k, int) {
+          const float h = lin_of<D>(m.A0s[k], zr);
+          const float a0 = fmaxf(h, kSlope * h);            // LeakyReLU(0.2) = max(h, 0.2h)
+          return a0 * a0;
+        });
+      worker_drain(m, w, [&](uint32_t (&r)[32], int c0) {
+        const int nb = p * kTN + c0;
         uint32_t word = 0;
-        const int nb = p * kTN + cc * 32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float h1 = __uint_as_float(r[j]) + lin_of<D>(A1s[nb + j], zr);
+          const float h1 = __uint_as_float(r[j]) + lin_of<D>(m.A1s[nb + j], zr);
           const bool pos = h1 > 0.f;
-          h2 = fmaf(P1s[nb + j], pos ? h1 : kSlope * h1, h2);
+          h2 = fmaf(m.P1s[nb + j], pos ? h1 : kSlope * h1, h2);
           word |= (pos ? 1u : 0u) << j;
         }
-        maskw[(nb >> 5) * 256 + row] = word;
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(accempty);
-      ++pp;
+        m.maskw[(nb >> 5) * 256 + w.row] = word;
+      });
     }
+    m.xch[w.kh * 256 + w.row] = h2;
+    worker_bar();                                            // h2 halves + all mask words visible
+    h2 = m.xch[w.row] + m.xch[256 + w.row];
     {
       float lin = A2p[D];
 #pragma unroll
@@ -285,140 +443,243 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
     const bool pos2 = h2 > 0.f;
     const float s2 = pos2 ? 1.f : kSlope;
     if (valid) {
-      if (psi) psi[m0 + row] = pos2 ? h2 : kSlope * h2;
-      if (mask2) mask2[m0 + row] = pos2 ? 1 : 0;
+      if (w.kh == 0) {
+        if (psi) psi[m0 + w.row] = pos2 ? h2 : kSlope * h2;
+        if (mask2) mask2[m0 + w.row] = pos2 ? 1 : 0;
+      }
       if (mask1)
-        for (int wd = 0; wd < Hw_out; ++wd) mask1[(size_t)(m0 + row) * Hw_out + wd] = maskw[wd * 256 + row];
+        for (int wd = w.kh; wd < Hw_out; wd += 2) mask1[(size_t)(m0 + w.row) * Hw_out + wd] = m.maskw[wd * 256 + w.row];
     }
     if (xhat != nullptr) {
       // -------- GEMM2: gx1 = g1 . P -> g0 -> xhat --------
-      float xacc[D], xa[D];
+      float xacc[D];
 #pragma unroll
-      for (int j = 0; j < D; ++j) { xacc[j] = 0.f; xa[j] = 0.f; }
+      for (int j = 0; j < D; ++j) xacc[j] = 0.f;
       for (int p = 0; p < NP; ++p) {
-        for (int kb = 0; kb < NKB; ++kb, ++it) {
-          const uint32_t s = it % S, ph = (it / S) & 1;
-          const uint32_t bits = maskw[(kb >> 1) * 256 + row] >> ((kb & 1) * 16);
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
-          unsigned char* At = stages + s * kStageBytes;
+        for (int kb = 0; kb < NKB; ++kb) {
+          const uint32_t bits = m.maskw[(kb >> 1) * 256 + w.row] >> ((kb & 1) * 16 + w.kh * 8);
+          worker_produce<X3>(m, w, kb, [&](int k, int e) {
+            const float c1 = s2 * m.P1s[k];
+            const float g1 = ((bits >> e) & 1u) ? c1 : kSlope * c1;
+            if (p == 0) {                                    // xhat += A1^T g1, once
+              const float4 q = m.A1s[k];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float v[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int k = kb * kKB + c * 4 + e;
-              const float c1 = s2 * P1s[k];
-              v[e] = ((bits >> (c * 4 + e)) & 1u) ? c1 : kSlope * c1;
-              if (p == 0) {
-                const float4 q = A1s[k];
-#pragma unroll
-                for (int j = 0; j < D; ++j) xa[j] = fmaf(comp(q, j), v[e], xa[j]);
-              }
+              for (int j = 0; j < D; ++j) xacc[j] = fmaf(comp(q, j), g1, xacc[j]);
             }
-            const uint32_t off = a_row_off + ((uint32_t)(c ^ rsw) << 4);
-            const float4 hi = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
-            *reinterpret_cast<float4*>(At + off) = hi;
-            if (X3)
-              *reinterpret_cast<float4*>(At + kOffAlo + off) =
-                  make_float4(to_tf32(v[0] - hi.x), to_tf32(v[1] - hi.y), to_tf32(v[2] - hi.z), to_tf32(v[3] - hi.w));
-          }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full0 + 8 * s);
+            return g1;
+          });
         }
-        mbar_wait(accfull, pp & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < kTN / 32; ++cc) {
-          uint32_t r[32];
-          tmem_ld32(taddr_row + cc * 32, r);
-          tmem_ld_wait();
-          const int nb = p * kTN + cc * 32;
+        worker_drain(m, w, [&](uint32_t (&r)[32], int c0) {
+          const int nb = p * kTN + c0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float4 q = A0s[nb + j];
+            const float4 q = m.A0s[nb + j];
             const float h = lin_of<D>(q, zr);
             const float s0 = slope_of(h), a0 = h * s0;
             const float g0 = __uint_as_float(r[j]) * (2.f * a0) * s0;
 #pragma unroll
             for (int jj = 0; jj < D; ++jj) xacc[jj] = fmaf(comp(q, jj), g0, xacc[jj]);
           }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(accempty);
-        ++pp;
+        });
       }
-      if (valid) {
+      worker_bar();                                          // xch reuse
+#pragma unroll
+      for (int j = 0; j < D; ++j) m.xch[(w.kh * 256 + w.row) * 4 + j] = xacc[j];
+      worker_bar();
+      if (valid && w.kh == 0) {
 #pragma unroll
         for (int j = 0; j < D; ++j)
-          xhat[(size_t)(m0 + row) * D + j] = fmaf(2.f * kappa, zr[j], fmaf(s2, A2p[j], xacc[j] + xa[j]));
+          xhat[(size_t)(m0 + w.row) * D + j] =
+              fmaf(2.f * kappa, zr[j], fmaf(s2, A2p[j], m.xch[w.row * 4 + j] + m.xch[(256 + w.row) * 4 + j]));
       }
     }
-  } else if (warp == 8) {
-    // =============================== TMA producer: B tiles ===============================
+  } else if (warp == kNW) {
     if (lane == 0) {
-      const int ngemm = (xhat != nullptr) ? 2 : 1;
-      uint32_t it = 0;
-      for (int g = 0; g < ngemm; ++g) {
-        const CUtensorMap* mhi = g == 0 ? &maps.b1hi : &maps.b2hi;
-        const CUtensorMap* mlo = g == 0 ? &maps.b1lo : &maps.b2lo;
-        for (int p = 0; p < NP; ++p)
-          for (int kb = 0; kb < NKB; ++kb, ++it) {
-            const uint32_t s = it % S, ph = (it / S) & 1;
-            mbar_wait(empty0 + 8 * s, ph ^ 1);
-            const uint32_t bar = full0 + 8 * s;
-            const uint32_t dst = smem_u32(stages + s * kStageBytes);
-            mbar_arrive_expect_tx(bar, (X3 ? 2 : 1) * kTileBytes);
-            tma_load_2d(dst + kOffB, mhi, bar, kb * kKB, p * kTN);
-            if (X3) tma_load_2d(dst + kOffBlo, mlo, bar, kb * kKB, p * kTN);
-          }
-      }
+      const CUtensorMap* hi[2] = {&maps.b1hi, &maps.b2hi};
+      const CUtensorMap* lo[2] = {&maps.b1lo, &maps.b2lo};
+      tc_tma_role<X3>(m, hi, lo, ngemm, NP, NKB);
     }
   } else {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const int npass = (xhat != nullptr ? 2 : 1) * NP;
-      uint32_t it = 0;
-      for (int pp = 0; pp < npass; ++pp) {
-        mbar_wait(accempty, (pp & 1) ^ 1);
-        tc_fence_after();
-        for (int kb = 0; kb < NKB; ++kb, ++it) {
-          const uint32_t s = it % S, ph = (it / S) & 1;
-          mbar_wait(full0 + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(stages + s * kStageBytes);
+    if (lane == 0) tc_mma_role<X3>(m, tmem_base, ngemm * NP, NKB);
+  }
+  tc_teardown(tmem_base);
+}
+
+// ====================================== backward, sample rows =========================================
+// GEMM-A  gx1 = g1 . P      -> t0, g0: row-local dz, column sums dA0w / dA0b
+// GEMM-B  w1  = u1 + q1.P^T -> column sums dP1 / dA1w
+// Column sums over the CTA's 256 rows are reduced inside each warp (32 rows) with a transposing shuffle
+// reduction and written as ordered partials  part[(mtile*8 + rowgroup)][f][Hq]  (finalize sums them).
+template <int D, bool X3>
+__global__ void __launch_bounds__(kTcThreads, 1)
+icnn_tc_bwd_rows_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ z, const float* __restrict__ v,
+                        const uint32_t* __restrict__ mask1, const uint8_t* __restrict__ mask2, int B, int Hq,
+                        int Hw_in, float kappa, const float4* __restrict__ A0q_g, const float4* __restrict__ A1q_g,
+                        const float* __restrict__ P1q_g, float* __restrict__ dz, float* __restrict__ partA,
+                        float* __restrict__ partB, float* __restrict__ a2part) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const TcSmem m = carve<X3>(smem_raw, Hq);
+  const uint32_t tmem_base = tc_setup<X3>(m, Hq, A0q_g, A1q_g, P1q_g);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kTM;
+  const int NP = Hq / kTN, NKB = Hq / kKB;
+  constexpr int NF = D + 1;
+
+  if (warp < kNW) {
+    Worker w = make_worker(tmem_base);
+    const bool valid = (m0 + w.row) < B;
+    float zr[D], vr[D];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const uint32_t d_t = tmem_base + (uint32_t)(half * kTN);
+    for (int j = 0; j < D; ++j) {
+      zr[j] = valid ? z[(size_t)(m0 + w.row) * D + j] : 0.f;
+      vr[j] = valid ? v[(size_t)(m0 + w.row) * D + j] : 0.f;
+    }
+    const float s2 = valid ? (mask2[m0 + w.row] ? 1.f : kSlope) : 0.f;     // 0 kills every term of padded rows
+    for (int wd = w.kh; wd < Hq / 32; wd += 2)
+      m.maskw[wd * 256 + w.row] = (valid && wd < Hw_in) ? mask1[(size_t)(m0 + w.row) * Hw_in + wd] : 0u;
+    worker_bar();
+    float* pA = partA + (size_t)(blockIdx.x * 8 + (w.warp & 7)) * NF * Hq;
+    float* pB = partB + (size_t)(blockIdx.x * 8 + (w.warp & 7)) * NF * Hq;
+    float dzacc[D];
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {                         // two K=8 steps per 64-byte row
-              const uint64_t a_hi = make_desc_sw64(sa + half * (kTileBytes / 2) + ks * 32);
-              const uint64_t b_hi = make_desc_sw64(sa + kOffB + ks * 32);
-              const uint32_t acc = (kb | ks) ? 1u : 0u;
-              if (X3) {
-                const uint64_t a_lo = make_desc_sw64(sa + kOffAlo + half * (kTileBytes / 2) + ks * 32);
-                const uint64_t b_lo = make_desc_sw64(sa + kOffBlo + ks * 32);
-                umma_tf32(d_t, a_lo, b_hi, kIdescTf32, acc);
-                umma_tf32(d_t, a_hi, b_lo, kIdescTf32, 1u);
-                umma_tf32(d_t, a_hi, b_hi, kIdescTf32, 1u);
-              } else {
-                umma_tf32(d_t, a_hi, b_hi, kIdescTf32, acc);
-              }
+    for (int j = 0; j < D; ++j) dzacc[j] = 0.f;
+
+    // -------- GEMM-A --------
+    for (int p = 0; p < NP; ++p) {
+      for (int kb = 0; kb < NKB; ++kb) {
+        const uint32_t bits = m.maskw[(kb >> 1) * 256 + w.row] >> ((kb & 1) * 16 + w.kh * 8);
+        worker_produce<X3>(m, w, kb, [&](int k, int e) {
+          const float c1 = s2 * m.P1s[k];
+          return ((bits >> e) & 1u) ? c1 : kSlope * c1;
+        });
+      }
+      worker_drain(m, w, [&](uint32_t (&r)[32], int c0) {
+        const int nb = p * kTN + c0;
+        float acc[NF][16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float e[2][NF];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int j = i + 16 * hh;
+            const float4 q = m.A0s[nb + j];
+            const float h = lin_of<D>(q, zr), u0 = dot_of<D>(q, vr);
+            const float s0 = slope_of(h), a0 = h * s0, gx1 = __uint_as_float(r[j]);
+            const float g0 = gx1 * (2.f * a0) * s0;
+            const float t0 = u0 * (2.f * gx1) * s0 * s0;
+#pragma unroll
+            for (int jj = 0; jj < D; ++jj) {
+              dzacc[jj] = fmaf(comp(q, jj), t0, dzacc[jj]);
+              e[hh][jj] = fmaf(g0, vr[jj], t0 * zr[jj]);
             }
+            e[hh][D] = t0;
           }
-          umma_commit(empty0 + 8 * s);       // frees the smem stage when these MMAs have read it
+#pragma unroll
+          for (int f = 0; f < NF; ++f) acc[f][i] = fold_first(e[0][f], e[1][f], lane);
         }
-        umma_commit(accfull);                // accumulator pass complete
+#pragma unroll
+        for (int f = 0; f < NF; ++f) pA[(size_t)f * Hq + nb + lane] = fold16(acc[f], lane);
+      });
+    }
+    // -------- GEMM-B --------
+    for (int p = 0; p < NP; ++p) {
+      for (int kb = 0; kb < NKB; ++kb)
+        worker_produce<X3>(m, w, kb, [&](int k, int) {
+          const float4 q = m.A0s[k];
+          const float h = lin_of<D>(q, zr), u0 = dot_of<D>(q, vr);
+          const float s0 = slope_of(h), a0 = h * s0;
+          return u0 * (2.f * a0) * s0;
+        });
+      worker_drain(m, w, [&](uint32_t (&r)[32], int c0) {
+        const int nb = p * kTN + c0;
+        const uint32_t word = m.maskw[(nb >> 5) * 256 + w.row];
+        float acc[NF][16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float e[2][NF];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int j = i + 16 * hh;
+            const float4 q = m.A1s[nb + j];
+            const float s1 = ((word >> j) & 1u) ? 1.f : kSlope;
+            const float w1 = __uint_as_float(r[j]) + dot_of<D>(q, vr);
+            const float g1 = (s2 * m.P1s[nb + j]) * s1;
+#pragma unroll
+            for (int jj = 0; jj < D; ++jj) e[hh][jj] = g1 * vr[jj];
+            e[hh][D] = (s2 * s1) * w1;
+          }
+#pragma unroll
+          for (int f = 0; f < NF; ++f) acc[f][i] = fold_first(e[0][f], e[1][f], lane);
+        }
+#pragma unroll
+        for (int f = 0; f < NF; ++f) pB[(size_t)f * Hq + nb + lane] = fold16(acc[f], lane);
+      });
+    }
+    // -------- rows: dz = A0^T t0 + 2 kappa v ; dA2w = sum_m s2 v --------
+#pragma unroll
+    for (int j = 0; j < D; ++j) m.xch[(w.kh * 256 + w.row) * 4 + j] = dzacc[j];
+    worker_bar();
+    if (w.kh == 0) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const float g = fmaf(2.f * kappa, vr[j], m.xch[w.row * 4 + j] + m.xch[(256 + w.row) * 4 + j]);
+        if (valid && dz) dz[(size_t)(m0 + w.row) * D + j] = g;
       }
     }
+    worker_bar();
+    if (w.kh == 0) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const float sred = warp_sum(s2 * vr[j]);
+        if (lane == 0) m.xch[w.warp * 4 + j] = sred;
+      }
+    }
+    worker_bar();
+    if (threadIdx.x < D) {
+      float sred = 0.f;
+      for (int q = 0; q < 8; ++q) sred += m.xch[q * 4 + threadIdx.x];
+      a2part[(size_t)blockIdx.x * D + threadIdx.x] = sred;
+    }
+  } else if (warp == kNW) {
+    if (lane == 0) {
+      const CUtensorMap* hi[2] = {&maps.b2hi, &maps.b1hi};
+      const CUtensorMap* lo[2] = {&maps.b2lo, &maps.b1lo};
+      tc_tma_role<X3>(m, hi, lo, 2, NP, NKB);
+    }
+  } else {
+    if (lane == 0) tc_mma_role<X3>(m, tmem_base, 2 * NP, NKB);
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  tc_teardown(tmem_base);
+}
+
+// ordered reduction of the row-kernel partials + chain through the positive reparam for W1
+__global__ void tc_finalize_small_kernel(const float* __restrict__ partA, const float* __restrict__ partB,
+                                         const float* __restrict__ a2part, int nslots, int nmt, int d, int H, int Hq,
+                                         const float* __restrict__ P1, const float* __restrict__ W1raw, int mode,
+                                         b200vae_icnn_grads g) {
+  const int NF = d + 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < H * NF * 2) {
+    const int which = idx / (H * NF), rem = idx - which * H * NF;
+    const int f = rem / H, n = rem - f * H;
+    const float* part = which ? partB : partA;
+    float s = 0.f;
+    for (int sl = 0; sl < nslots; ++sl) s += part[((size_t)sl * NF + f) * Hq + n];
+    if (!which) {
+      if (f < d) { if (g.A0w) g.A0w[(size_t)n * d + f] = s; }
+      else if (g.A0b) g.A0b[n] = s;
+    } else {
+      if (f < d) { if (g.A1w) g.A1w[(size_t)n * d + f] = s; }
+      else if (g.W1) g.W1[n] = (mode == B200VAE_WEIGHT_EXP) ? s * P1[n] : (W1raw[n] >= kClampMin ? s : 0.f);
+    }
+    if (which && f == 0 && g.A1b) g.A1b[n] = 0.f;            // exact zeros on the <v, xhat> path (Appendix A)
   }
+  if (idx < d) {
+    float s = 0.f;
+    for (int mt = 0; mt < nmt; ++mt) s += a2part[(size_t)mt * d + idx];
+    if (g.A2w) g.A2w[idx] = s;
+  }
+  if (idx == 0 && g.A2b) g.A2b[0] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -467,9 +728,7 @@ int tc_prepare(const b200vae_icnn_params* p, int d, int H, int mode, int precisi
 template <int D, bool X3>
 static int launch_tc(const TcMaps& maps, const float* z, int B, const TcLayout& T, const float* tb, const float* A2p,
                      int Hw_out, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2, cudaStream_t st) {
-  constexpr int S = X3 ? 2 : 4;
-  const size_t smem = (size_t)S * (X3 ? 4 : 2) * kTileBytes + (size_t)T.Hq * (16 + 16 + 4) + (size_t)(T.Hq / 32) * 256 * 4 +
-                      (2 * S + 2) * 8 + 16 + 1024;
+  const size_t smem = tc_smem_bytes<X3>(T.Hq);
   if (smem > 227 * 1024) return B200VAE_EUNSUP;
   static bool attr_done = false;
   if (!attr_done) {
@@ -483,32 +742,35 @@ static int launch_tc(const TcMaps& maps, const float* z, int B, const TcLayout& 
   return check_launch();
 }
 
+static int get_maps(const float* tb, const TcLayout& T, TcMaps* out) {
+  // tensor maps only encode (address, shape): cache them per prepared buffer
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, TcMaps> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  const uint64_t key = reinterpret_cast<uint64_t>(tb) ^ ((uint64_t)T.Hq << 48);
+  auto itc = cache.find(key);
+  if (itc != cache.end()) { *out = itc->second; return B200VAE_OK; }
+  TcMaps maps;
+  int rc = make_map(&maps.b1hi, tb + T.B1hi, T.Hq);
+  if (!rc) rc = make_map(&maps.b1lo, tb + T.B1lo, T.Hq);
+  if (!rc) rc = make_map(&maps.b2hi, tb + T.B2hi, T.Hq);
+  if (!rc) rc = make_map(&maps.b2lo, tb + T.B2lo, T.Hq);
+  if (rc) return rc;
+  if (cache.size() > 256) cache.clear();
+  cache.emplace(key, maps);
+  *out = maps;
+  return B200VAE_OK;
+}
+
 int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2,
            int precision, const float* ws, cudaStream_t st) {
   if (precision == B200VAE_PREC_BF16 || d > 3) return B200VAE_EUNSUP;
   const WsLayout L = ws_layout(1, d, H);
   const TcLayout T = tc_layout(d, H);
   const float* tb = tc_base(const_cast<float*>(ws), d, H);
-  // tensor maps only encode (address, shape): cache them per prepared buffer
-  static std::mutex mu;
-  static std::unordered_map<uint64_t, TcMaps> cache;
   TcMaps maps;
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    const uint64_t key = reinterpret_cast<uint64_t>(tb) ^ ((uint64_t)T.Hq << 48);
-    auto itc = cache.find(key);
-    if (itc == cache.end()) {
-      int rc = make_map(&maps.b1hi, tb + T.B1hi, T.Hq);
-      if (!rc) rc = make_map(&maps.b1lo, tb + T.B1lo, T.Hq);
-      if (!rc) rc = make_map(&maps.b2hi, tb + T.B2hi, T.Hq);
-      if (!rc) rc = make_map(&maps.b2lo, tb + T.B2lo, T.Hq);
-      if (rc) return rc;
-      if (cache.size() > 256) cache.clear();
-      cache.emplace(key, maps);
-    } else {
-      maps = itc->second;
-    }
-  }
+  int rc = get_maps(tb, T, &maps);
+  if (rc) return rc;
   const bool x3 = (precision == B200VAE_PREC_TF32X3);
   const int Hw_out = L.Hp / 32;
 #define B200VAE_TC(DD)                                                                                          \
@@ -521,6 +783,72 @@ int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* 
     default: return B200VAE_EUNSUP;
   }
 #undef B200VAE_TC
+}
+
+// ---- backward ----
+size_t tc_bwd_ws_floats(int B, int d, int H) {
+  const TcLayout T = tc_layout(d, H);
+  const size_t nmt = (size_t)(B + kTM - 1) / kTM;
+  return 2 * nmt * 8 * (d + 1) * T.Hq + nmt * 4 + 64;
+}
+
+template <int D, bool X3>
+static int launch_tc_bwd(const TcMaps& maps, const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2,
+                         int B, const TcLayout& T, const float* tb, int Hw_in, float kappa, float* dz, float* partA,
+                         float* partB, float* a2part, cudaStream_t st) {
+  const size_t smem = tc_smem_bytes<X3>(T.Hq);
+  if (smem > 227 * 1024) return B200VAE_EUNSUP;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(icnn_tc_bwd_rows_kernel<D, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_done = true;
+  }
+  const int grid = (B + kTM - 1) / kTM;
+  icnn_tc_bwd_rows_kernel<D, X3><<<grid, kTcThreads, smem, st>>>(
+      maps, z, v, mask1, mask2, B, T.Hq, Hw_in, kappa, reinterpret_cast<const float4*>(tb + T.A0q),
+      reinterpret_cast<const float4*>(tb + T.A1q), tb + T.P1q, dz, partA, partB, a2part);
+  return check_launch();
+}
+
+int simt_bwd_W0(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H,
+                const b200vae_icnn_params* p, int mode, float* gW0, float* ws, size_t mid_extra, cudaStream_t st);
+
+int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H,
+           const b200vae_icnn_params* p, int mode, float kappa, const b200vae_icnn_grads* g, float* dz, int precision,
+           float* ws, cudaStream_t st) {
+  if (precision == B200VAE_PREC_BF16 || d > 3 || !v) return B200VAE_EUNSUP;
+  const size_t extra = tc_extra_ws_floats(d, H, precision);
+  const WsLayout L = ws_layout(B, d, H, extra);
+  const TcLayout T = tc_layout(d, H);
+  const float* tb = tc_base(ws, d, H);
+  TcMaps maps;
+  int rc = get_maps(tb, T, &maps);
+  if (rc) return rc;
+  const size_t nmt = (size_t)(B + kTM - 1) / kTM;
+  float* partA = ws + L.end;
+  float* partB = partA + nmt * 8 * (d + 1) * T.Hq;
+  float* a2part = partB + nmt * 8 * (d + 1) * T.Hq;
+  const bool x3 = (precision == B200VAE_PREC_TF32X3);
+  const int Hw_in = L.Hp / 32;
+#define B200VAE_TCB(DD)                                                                                                 \
+  rc = x3 ? launch_tc_bwd<DD, true>(maps, z, v, mask1, mask2, B, T, tb, Hw_in, kappa, dz, partA, partB, a2part, st)    \
+          : launch_tc_bwd<DD, false>(maps, z, v, mask1, mask2, B, T, tb, Hw_in, kappa, dz, partA, partB, a2part, st)
+  switch (d) {
+    case 1: B200VAE_TCB(1); break;
+    case 2: B200VAE_TCB(2); break;
+    case 3: B200VAE_TCB(3); break;
+    default: return B200VAE_EUNSUP;
+  }
+#undef B200VAE_TCB
+  if (rc || !g) return rc;
+  if (g->W0) {
+    rc = simt_bwd_W0(z, v, mask1, mask2, B, d, H, p, mode, g->W0, ws, extra, st);
+    if (rc) return rc;
+  }
+  const int total = H * (d + 1) * 2;
+  tc_finalize_small_kernel<<<(total + 255) / 256, 256, 0, st>>>(partA, partB, a2part, (int)nmt * 8, (int)nmt, d, H, T.Hq,
+                                                                ws + L.P1, p->W1, mode, *g);
+  return check_launch();
 }
 
 }  // namespace b200vae
