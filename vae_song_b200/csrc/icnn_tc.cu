@@ -652,6 +652,157 @@ icnn_tc_bwd_rows_kernel(const __grid_constant__ TcMaps maps, const float* __rest
   tc_teardown(tmem_base);
 }
 
+// ====================================== backward, dP0 (batch-reduced) ===================================
+// dP0part[split][o][n] = sum_{m in split} s2[m] s1[m,o] * q1[m,n]      (P1[o] and the exp/clamp chain: finalize)
+// Output-stationary 256 x 256 tile in TMEM, K = the CTA's batch slice.  BOTH operands are generated: a sample
+// (= K index) is owned by a thread, which emits 8 consecutive o's / n's as 16-byte chunks -> MN-major UMMA
+// layout (SWIZZLE_128B atoms of 8 k-rows x 128 B; LBO = 1 KB between 32-wide MN blocks).  No TMA, no B matrix.
+constexpr int kDpThreads = (kNW + 1) * 32;
+constexpr uint32_t kIdescTf32MN = kIdescTf32 | (1u << 15) | (1u << 16);     // a_major = b_major = MN
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(8192 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+template <int D, bool X3>
+__global__ void __launch_bounds__(kDpThreads, 1)
+icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, const uint32_t* __restrict__ mask1,
+                   const uint8_t* __restrict__ mask2, int B, int Hq, int Hw_in, int rows_per_split,
+                   const float4* __restrict__ A0q_g, float* __restrict__ dP0part) {
+  constexpr int S = X3 ? 3 : 6;
+  constexpr int kStage = (X3 ? 4 : 2) * kTileBytes;
+  constexpr int kOffAlo = kTileBytes, kOffB = (X3 ? 2 : 1) * kTileBytes, kOffBlo = 3 * kTileBytes;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + S * kStage);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * kTN, o0 = blockIdx.y * kTM, split = blockIdx.z;
+  const int b0 = split * rows_per_split;
+  const int b1 = min(B, b0 + rows_per_split);
+  const int NKB = (max(b1 - b0, 0) + kKB - 1) / kKB;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, kNW); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(accfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kNW) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kNW) {
+    const int ks = tid & 15, u = tid >> 4, blk = u >> 2, qd = u & 3;     // sample-in-stage, MN block, 8-wide quarter
+    const int g = ks >> 3, kk = ks & 7;
+    float4 q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[e] = A0q_g[n0 + blk * 32 + qd * 8 + e];
+    const int wcol = (o0 >> 5) + blk;                                    // mask word holding my 8 o's
+    const uint32_t atom = (uint32_t)((g * 8 + blk) * 1024 + kk * 128);
+    const uint32_t off0 = atom + ((uint32_t)((2 * qd) ^ kk) << 4), off1 = atom + ((uint32_t)((2 * qd + 1) ^ kk) << 4);
+    auto load = [&](int kb, float (&zr)[D], float (&vr)[D], float& s2f, uint32_t& bits) {
+      const int mrow = b0 + kb * kKB + ks;
+      const bool in = mrow < b1;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        zr[j] = in ? __ldg(z + (size_t)mrow * D + j) : 0.f;
+        vr[j] = in ? __ldg(v + (size_t)mrow * D + j) : 0.f;
+      }
+      s2f = in ? (__ldg(mask2 + mrow) ? 1.f : kSlope) : 0.f;
+      bits = (in && wcol < Hw_in) ? (__ldg(mask1 + (size_t)mrow * Hw_in + wcol) >> (qd * 8)) : 0u;
+    };
+    float zr[D], vr[D], s2f; uint32_t bits;
+    if (NKB > 0) load(0, zr, vr, s2f, bits);
+    for (int kb = 0; kb < NKB; ++kb) {
+      float av[8], bv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        av[e] = ((bits >> e) & 1u) ? s2f : kSlope * s2f;
+        const float h = lin_of<D>(q[e], zr), u0 = dot_of<D>(q[e], vr);
+        const float s0 = slope_of(h), a0 = h * s0;
+        bv[e] = u0 * (2.f * a0) * s0;
+      }
+      if (kb + 1 < NKB) load(kb + 1, zr, vr, s2f, bits);                 // prefetch next sample's inputs
+      const uint32_t s = kb % S, ph = (kb / S) & 1;
+      mbar_wait(empty0 + 8 * s, ph ^ 1);
+      unsigned char* st = stages + s * kStage;
+      auto put = [&](unsigned char* base, const float (&x)[8]) {
+        const float4 h0 = make_float4(to_tf32(x[0]), to_tf32(x[1]), to_tf32(x[2]), to_tf32(x[3]));
+        const float4 h1 = make_float4(to_tf32(x[4]), to_tf32(x[5]), to_tf32(x[6]), to_tf32(x[7]));
+        *reinterpret_cast<float4*>(base + off0) = h0;
+        *reinterpret_cast<float4*>(base + off1) = h1;
+        if (X3) {
+          *reinterpret_cast<float4*>(base + kTileBytes + off0) =
+              make_float4(to_tf32(x[0] - h0.x), to_tf32(x[1] - h0.y), to_tf32(x[2] - h0.z), to_tf32(x[3] - h0.w));
+          *reinterpret_cast<float4*>(base + kTileBytes + off1) =
+              make_float4(to_tf32(x[4] - h1.x), to_tf32(x[5] - h1.y), to_tf32(x[6] - h1.z), to_tf32(x[7] - h1.w));
+        }
+      };
+      put(st, av);
+      put(st + kOffB, bv);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full0 + 8 * s);
+    }
+    // epilogue: my o-row, 128 of the 256 columns
+    const int orow = o0 + ((warp >> 2) & 1) * 128 + (warp & 3) * 32 + lane;
+    const int chalf = warp >> 3;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp >> 2) & 1) * kTN + chalf * 128);
+    float* out = dP0part + ((size_t)split * Hq + orow) * Hq + n0 + chalf * 128;
+    if (NKB > 0) {
+      mbar_wait(accfull, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(taddr + cc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(out + cc * 32 + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      }
+    } else {
+      for (int j = 0; j < 128; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else if (lane == 0) {
+    for (int kb = 0; kb < NKB; ++kb) {
+      const uint32_t s = kb % S, ph = (kb / S) & 1;
+      mbar_wait(full0 + 8 * s, ph);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(stages + s * kStage);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t d_t = tmem_base + (uint32_t)(half * kTN);
+          const uint64_t a_hi = make_desc_mn_sw128(sa + g * 8192 + half * 4096);
+          const uint64_t b_hi = make_desc_mn_sw128(sa + kOffB + g * 8192);
+          const uint32_t acc = (kb | g) ? 1u : 0u;
+          if (X3) {
+            const uint64_t a_lo = make_desc_mn_sw128(sa + kOffAlo + g * 8192 + half * 4096);
+            const uint64_t b_lo = make_desc_mn_sw128(sa + kOffBlo + g * 8192);
+            umma_tf32(d_t, a_lo, b_hi, kIdescTf32MN, acc);
+            umma_tf32(d_t, a_hi, b_lo, kIdescTf32MN, 1u);
+            umma_tf32(d_t, a_hi, b_hi, kIdescTf32MN, 1u);
+          } else {
+            umma_tf32(d_t, a_hi, b_hi, kIdescTf32MN, acc);
+          }
+        }
+      }
+      umma_commit(empty0 + 8 * s);
+    }
+    if (NKB > 0) umma_commit(accfull);
+  }
+  tc_teardown(tmem_base);
+}
+
 // ordered reduction of the row-kernel partials + chain through the positive reparam for W1
 __global__ void tc_finalize_small_kernel(const float* __restrict__ partA, const float* __restrict__ partB,
                                          const float* __restrict__ a2part, int nslots, int nmt, int d, int H, int Hq,
@@ -786,10 +937,19 @@ int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* 
 }
 
 // ---- backward ----
+static int tc_dp0_splits(int B, int Hq) {
+  const int tiles = (Hq / kTM) * (Hq / kTN);
+  int s = 148 / tiles;                          // one wave of long-running CTAs
+  const int maxs = (B + 255) / 256;
+  if (s > maxs) s = maxs;
+  if (s < 1) s = 1;
+  return s;
+}
+
 size_t tc_bwd_ws_floats(int B, int d, int H) {
   const TcLayout T = tc_layout(d, H);
   const size_t nmt = (size_t)(B + kTM - 1) / kTM;
-  return 2 * nmt * 8 * (d + 1) * T.Hq + nmt * 4 + 64;
+  return 2 * nmt * 8 * (d + 1) * T.Hq + nmt * 4 + 64 + 16 + (size_t)tc_dp0_splits(B, T.Hq) * T.Hq * T.Hq;
 }
 
 template <int D, bool X3>
@@ -810,8 +970,26 @@ static int launch_tc_bwd(const TcMaps& maps, const float* z, const float* v, con
   return check_launch();
 }
 
-int simt_bwd_W0(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H,
-                const b200vae_icnn_params* p, int mode, float* gW0, float* ws, size_t mid_extra, cudaStream_t st);
+int finalize_W0_launch(const float* part, int splits, int H, int Hp, int ldp, const float* P0, const float* P1,
+                       const float* W0raw, int mode, float* dW0, cudaStream_t st);
+
+template <int D, bool X3>
+static int launch_tc_dp0(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B,
+                         const TcLayout& T, const float* tb, int Hw_in, int splits, float* part, cudaStream_t st) {
+  constexpr int S = X3 ? 3 : 6;
+  const size_t smem = (size_t)S * (X3 ? 4 : 2) * kTileBytes + (2 * S + 1) * 8 + 16 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(icnn_tc_dP0_kernel<D, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_done = true;
+  }
+  int rows = (B + splits - 1) / splits;
+  rows = round_up(rows, kKB);
+  dim3 grid(T.Hq / kTN, T.Hq / kTM, splits);
+  icnn_tc_dP0_kernel<D, X3><<<grid, kDpThreads, smem, st>>>(z, v, mask1, mask2, B, T.Hq, Hw_in, rows,
+                                                           reinterpret_cast<const float4*>(tb + T.A0q), part);
+  return check_launch();
+}
 
 int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H,
            const b200vae_icnn_params* p, int mode, float kappa, const b200vae_icnn_grads* g, float* dz, int precision,
@@ -842,7 +1020,20 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
 #undef B200VAE_TCB
   if (rc || !g) return rc;
   if (g->W0) {
-    rc = simt_bwd_W0(z, v, mask1, mask2, B, d, H, p, mode, g->W0, ws, extra, st);
+    float* part = a2part + nmt * 4 + 64;
+    part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(part) + 15) & ~(uintptr_t)15);
+    const int splits = tc_dp0_splits(B, T.Hq);
+#define B200VAE_TCD(DD)                                                                                       \
+  rc = x3 ? launch_tc_dp0<DD, true>(z, v, mask1, mask2, B, T, tb, Hw_in, splits, part, st)                    \
+          : launch_tc_dp0<DD, false>(z, v, mask1, mask2, B, T, tb, Hw_in, splits, part, st)
+    switch (d) {
+      case 1: B200VAE_TCD(1); break;
+      case 2: B200VAE_TCD(2); break;
+      default: B200VAE_TCD(3); break;
+    }
+#undef B200VAE_TCD
+    if (rc) return rc;
+    rc = finalize_W0_launch(part, splits, H, L.Hp, T.Hq, ws + L.P0, ws + L.P1, p->W0, mode, g->W0, st);
     if (rc) return rc;
   }
   const int total = H * (d + 1) * 2;
