@@ -656,12 +656,14 @@ icnn_tc_bwd_rows_kernel(const __grid_constant__ TcMaps maps, const float* __rest
 // dP0part[split][o][n] = sum_{m in split} s2[m] s1[m,o] * q1[m,n]      (P1[o] and the exp/clamp chain: finalize)
 // Output-stationary 256 x 256 tile in TMEM, K = the CTA's batch slice.  BOTH operands are generated: a sample
 // (= K index) is owned by a thread, which emits 8 consecutive o's / n's as 16-byte chunks -> MN-major UMMA
-// layout (SWIZZLE_128B atoms of 8 k-rows x 128 B; LBO = 1 KB between 32-wide MN blocks).  No TMA, no B matrix.
+// layout.  For 32-bit MN-major operands the only legal UMMA layout is SWIZZLE_128B_BASE32B (cute
+// Layout_MN_SW128_32B_Atom): atoms of 4 k-rows x 128 B (32 MN elements), 32-byte chunks XOR-ed with the k-row;
+// LBO = 512 B between 32-wide MN blocks, SBO = 4 KB between groups of 4 k.  No TMA, no B matrix.
 constexpr int kDpThreads = (kNW + 1) * 32;
 constexpr uint32_t kIdescTf32MN = kIdescTf32 | (1u << 15) | (1u << 16);     // a_major = b_major = MN
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(8192 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)(4096 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)1 << 61);     // layout type 1 = SWIZZLE_128B_BASE32B
 }
 
 template <int D, bool X3>
@@ -699,13 +701,12 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
 
   if (warp < kNW) {
     const int ks = tid & 15, u = tid >> 4, blk = u >> 2, qd = u & 3;     // sample-in-stage, MN block, 8-wide quarter
-    const int g = ks >> 3, kk = ks & 7;
+    const int g4 = ks >> 2, kr = ks & 3;                                 // group of 4 k, k-row inside the atom
     float4 q[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) q[e] = A0q_g[n0 + blk * 32 + qd * 8 + e];
     const int wcol = (o0 >> 5) + blk;                                    // mask word holding my 8 o's
-    const uint32_t atom = (uint32_t)((g * 8 + blk) * 1024 + kk * 128);
-    const uint32_t off0 = atom + ((uint32_t)((2 * qd) ^ kk) << 4), off1 = atom + ((uint32_t)((2 * qd + 1) ^ kk) << 4);
+    const uint32_t off0 = (uint32_t)((g4 * 8 + blk) * 512 + kr * 128) + ((uint32_t)(qd ^ kr) << 5), off1 = off0 + 16;
     auto load = [&](int kb, float (&zr)[D], float (&vr)[D], float& s2f, uint32_t& bits) {
       const int mrow = b0 + kb * kKB + ks;
       const bool in = mrow < b1;
@@ -782,11 +783,11 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const uint32_t d_t = tmem_base + (uint32_t)(half * kTN);
-          const uint64_t a_hi = make_desc_mn_sw128(sa + g * 8192 + half * 4096);
+          const uint64_t a_hi = make_desc_mn_sw128(sa + g * 8192 + half * 2048);     // K=8 = two 4-k groups
           const uint64_t b_hi = make_desc_mn_sw128(sa + kOffB + g * 8192);
           const uint32_t acc = (kb | g) ? 1u : 0u;
           if (X3) {
-            const uint64_t a_lo = make_desc_mn_sw128(sa + kOffAlo + g * 8192 + half * 4096);
+            const uint64_t a_lo = make_desc_mn_sw128(sa + kOffAlo + g * 8192 + half * 2048);
             const uint64_t b_lo = make_desc_mn_sw128(sa + kOffBlo + g * 8192);
             umma_tf32(d_t, a_lo, b_hi, kIdescTf32MN, acc);
             umma_tf32(d_t, a_hi, b_lo, kIdescTf32MN, 1u);
