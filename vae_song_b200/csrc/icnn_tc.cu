@@ -671,12 +671,14 @@ __global__ void __launch_bounds__(kDpThreads, 1)
 icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, const uint32_t* __restrict__ mask1,
                    const uint8_t* __restrict__ mask2, int B, int Hq, int Hw_in, int rows_per_split,
                    const float4* __restrict__ A0q_g, float* __restrict__ dP0part) {
-  constexpr int S = X3 ? 3 : 6;
+  constexpr int S = X3 ? 2 : 5;
   constexpr int kStage = (X3 ? 4 : 2) * kTileBytes;
   constexpr int kOffAlo = kTileBytes, kOffB = (X3 ? 2 : 1) * kTileBytes, kOffBlo = 3 * kTileBytes;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + S * kStage);
+  float* samp = reinterpret_cast<float*>(stages + S * kStage);            // [2][2D+1][256]  z, v, s2 per sample
+  uint32_t* sampw = reinterpret_cast<uint32_t*>(samp + 2 * 256 * (2 * D + 1));   // [2][8][256] mask words
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sampw + 2 * 8 * 256);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -707,20 +709,48 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
     for (int e = 0; e < 8; ++e) q[e] = A0q_g[n0 + blk * 32 + qd * 8 + e];
     const int wcol = (o0 >> 5) + blk;                                    // mask word holding my 8 o's
     const uint32_t off0 = (uint32_t)((g4 * 8 + blk) * 512 + kr * 128) + ((uint32_t)(qd ^ kr) << 5), off1 = off0 + 16;
-    auto load = [&](int kb, float (&zr)[D], float (&vr)[D], float& s2f, uint32_t& bits) {
-      const int mrow = b0 + kb * kKB + ks;
+    // per-sample inputs (z, v, s2, the 8 mask words of this o-tile) are staged through shared memory in
+    // chunks of 256 samples, fetched one chunk ahead (register staged) so no global latency is exposed
+    constexpr int CH = 256, ZV = 2 * D + 1;                  // floats per sample: z, v, s2
+    const int nchunk = (NKB * kKB + CH - 1) / CH;
+    float pre_f[ZV];
+    uint32_t pre_w[4];
+    auto fetch = [&](int c) {                                // thread -> sample (tid&255), word half (tid>>8)
+      const int mrow = b0 + c * CH + (tid & 255);
       const bool in = mrow < b1;
+      if (tid < CH) {
 #pragma unroll
-      for (int j = 0; j < D; ++j) {
-        zr[j] = in ? __ldg(z + (size_t)mrow * D + j) : 0.f;
-        vr[j] = in ? __ldg(v + (size_t)mrow * D + j) : 0.f;
+        for (int j = 0; j < D; ++j) {
+          pre_f[j] = in ? __ldg(z + (size_t)mrow * D + j) : 0.f;
+          pre_f[D + j] = in ? __ldg(v + (size_t)mrow * D + j) : 0.f;
+        }
+        pre_f[2 * D] = in ? (__ldg(mask2 + mrow) ? 1.f : kSlope) : 0.f;
       }
-      s2f = in ? (__ldg(mask2 + mrow) ? 1.f : kSlope) : 0.f;
-      bits = (in && wcol < Hw_in) ? (__ldg(mask1 + (size_t)mrow * Hw_in + wcol) >> (qd * 8)) : 0u;
+      const int w0 = (o0 >> 5) + (tid >> 8) * 4;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) pre_w[q4] = (in && w0 + q4 < Hw_in) ? __ldg(mask1 + (size_t)mrow * Hw_in + w0 + q4) : 0u;
     };
-    float zr[D], vr[D], s2f; uint32_t bits;
-    if (NKB > 0) load(0, zr, vr, s2f, bits);
+    auto stash = [&](int buf) {
+      float* zf = samp + buf * (CH * ZV);
+      uint32_t* mw = sampw + buf * (CH * 8);
+      if (tid < CH) {
+#pragma unroll
+        for (int j = 0; j < ZV; ++j) zf[j * CH + tid] = pre_f[j];
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) mw[((tid >> 8) * 4 + q4) * CH + (tid & 255)] = pre_w[q4];
+    };
+    if (nchunk > 0) { fetch(0); stash(0); }
+    worker_bar();
     for (int kb = 0; kb < NKB; ++kb) {
+      const int c = kb >> 4, buf = c & 1, sl = (kb & 15) * kKB + ks;       // sample slot inside the chunk
+      if ((kb & 15) == 0 && c + 1 < nchunk) fetch(c + 1);
+      const float* zf = samp + buf * (CH * ZV);
+      float zr[D], vr[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) { zr[j] = zf[j * CH + sl]; vr[j] = zf[(D + j) * CH + sl]; }
+      const float s2f = zf[2 * D * CH + sl];
+      const uint32_t bits = sampw[buf * (CH * 8) + blk * CH + sl] >> (qd * 8);
       float av[8], bv[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -729,7 +759,11 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
         const float s0 = slope_of(h), a0 = h * s0;
         bv[e] = u0 * (2.f * a0) * s0;
       }
-      if (kb + 1 < NKB) load(kb + 1, zr, vr, s2f, bits);                 // prefetch next sample's inputs
+      if ((kb & 15) == 15 && c + 1 < nchunk) {               // next chunk's buffer was last read 16 stages ago
+        worker_bar();
+        stash(buf ^ 1);
+        worker_bar();
+      }
       const uint32_t s = kb % S, ph = (kb / S) & 1;
       mbar_wait(empty0 + 8 * s, ph ^ 1);
       unsigned char* st = stages + s * kStage;
@@ -804,34 +838,50 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
   tc_teardown(tmem_base);
 }
 
-// ordered reduction of the row-kernel partials + chain through the positive reparam for W1
-__global__ void tc_finalize_small_kernel(const float* __restrict__ partA, const float* __restrict__ partB,
-                                         const float* __restrict__ a2part, int nslots, int nmt, int d, int H, int Hq,
-                                         const float* __restrict__ P1, const float* __restrict__ W1raw, int mode,
-                                         b200vae_icnn_grads g) {
+// ordered reduction of the row-kernel partials + chain through the positive reparam for W1.
+// grid (Hq/32, NF, 2): one block sums all `nslots` partial rows of 32 columns (8 slot lanes x 32 columns,
+// coalesced 128-byte reads, fixed summation order -> deterministic).
+__global__ void __launch_bounds__(256)
+tc_finalize_small_kernel(const float* __restrict__ partA, const float* __restrict__ partB,
+                         const float* __restrict__ a2part, int nslots, int nmt, int d, int H, int Hq,
+                         const float* __restrict__ P1, const float* __restrict__ W1raw, int mode, b200vae_icnn_grads g) {
+  __shared__ float red[8][33];
   const int NF = d + 1;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < H * NF * 2) {
-    const int which = idx / (H * NF), rem = idx - which * H * NF;
-    const int f = rem / H, n = rem - f * H;
-    const float* part = which ? partB : partA;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx, f = blockIdx.y, which = blockIdx.z;
+  const float* part = (which ? partB : partA) + (size_t)f * Hq + n;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int sl = ty;
+  for (; sl + 24 < nslots; sl += 32) {
+    s0 += part[(size_t)sl * NF * Hq];
+    s1 += part[(size_t)(sl + 8) * NF * Hq];
+    s2 += part[(size_t)(sl + 16) * NF * Hq];
+    s3 += part[(size_t)(sl + 24) * NF * Hq];
+  }
+  for (; sl < nslots; sl += 8) s0 += part[(size_t)sl * NF * Hq];
+  red[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && n < H) {
     float s = 0.f;
-    for (int sl = 0; sl < nslots; ++sl) s += part[((size_t)sl * NF + f) * Hq + n];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][tx];
     if (!which) {
       if (f < d) { if (g.A0w) g.A0w[(size_t)n * d + f] = s; }
       else if (g.A0b) g.A0b[n] = s;
     } else {
       if (f < d) { if (g.A1w) g.A1w[(size_t)n * d + f] = s; }
       else if (g.W1) g.W1[n] = (mode == B200VAE_WEIGHT_EXP) ? s * P1[n] : (W1raw[n] >= kClampMin ? s : 0.f);
+      if (f == 0 && g.A1b) g.A1b[n] = 0.f;                   // exact zeros on the <v, xhat> path (Appendix A)
     }
-    if (which && f == 0 && g.A1b) g.A1b[n] = 0.f;            // exact zeros on the <v, xhat> path (Appendix A)
   }
-  if (idx < d) {
-    float s = 0.f;
-    for (int mt = 0; mt < nmt; ++mt) s += a2part[(size_t)mt * d + idx];
-    if (g.A2w) g.A2w[idx] = s;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    if (threadIdx.x < d) {
+      float s = 0.f;
+      for (int mt = 0; mt < nmt; ++mt) s += a2part[(size_t)mt * d + threadIdx.x];
+      if (g.A2w) g.A2w[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0 && g.A2b) g.A2b[0] = 0.f;
   }
-  if (idx == 0 && g.A2b) g.A2b[0] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -977,8 +1027,9 @@ int finalize_W0_launch(const float* part, int splits, int H, int Hp, int ldp, co
 template <int D, bool X3>
 static int launch_tc_dp0(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B,
                          const TcLayout& T, const float* tb, int Hw_in, int splits, float* part, cudaStream_t st) {
-  constexpr int S = X3 ? 3 : 6;
-  const size_t smem = (size_t)S * (X3 ? 4 : 2) * kTileBytes + (2 * S + 1) * 8 + 16 + 1024;
+  constexpr int S = X3 ? 2 : 5;
+  const size_t smem = (size_t)S * (X3 ? 4 : 2) * kTileBytes + (size_t)2 * 256 * (2 * D + 1) * 4 + 2 * 8 * 256 * 4 +
+                      (2 * S + 1) * 8 + 16 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(icnn_tc_dP0_kernel<D, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1037,9 +1088,9 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
     rc = finalize_W0_launch(part, splits, H, L.Hp, T.Hq, ws + L.P0, ws + L.P1, p->W0, mode, g->W0, st);
     if (rc) return rc;
   }
-  const int total = H * (d + 1) * 2;
-  tc_finalize_small_kernel<<<(total + 255) / 256, 256, 0, st>>>(partA, partB, a2part, (int)nmt * 8, (int)nmt, d, H, T.Hq,
-                                                                ws + L.P1, p->W1, mode, *g);
+  dim3 fgrid(T.Hq / 32, d + 1, 2);
+  tc_finalize_small_kernel<<<fgrid, 256, 0, st>>>(partA, partB, a2part, (int)nmt * 8, (int)nmt, d, H, T.Hq, ws + L.P1,
+                                                  p->W1, mode, *g);
   return check_launch();
 }
 
