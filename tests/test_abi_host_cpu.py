@@ -96,7 +96,8 @@ class _ToyVAE(torch.nn.Module):
 
     def __init__(self):
         super().__init__()
-        self.enc = torch.nn.Linear(2, 4)
+        self.enc = torch.nn.Sequential(torch.nn.Linear(2, 6, bias=False), torch.nn.BatchNorm1d(6), torch.nn.LeakyReLU(),
+                                       torch.nn.Linear(6, 4))
         self.dec = torch.nn.Linear(2, 2)
         self.beta = 0.3
 
@@ -129,8 +130,9 @@ def _dp_worker(rank, world, port, x, eps, out):
     lo, hi = train.shard_rows(x.shape[0], rank, world)
     for _ in range(3):
         tr.step(x[lo:hi], eps[lo:hi])
+    assert any(type(mod).__name__ == "SyncBatchNorm1d" for mod in tr.model.modules())
     if rank == 0:
-        out.put(tr.fp.flat.clone().numpy())
+        out.put((tr.fp.flat.clone().numpy(), tr.model.enc[1].running_var.clone().numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -149,11 +151,12 @@ def test_data_parallel_trainer_gloo_world2_equals_single():
     procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, x, eps, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=120)
+    got, rvar = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    np.testing.assert_allclose(got, single.fp.flat.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(got, single.fp.flat.numpy(), rtol=2e-4, atol=2e-6)      # cross-rank BatchNorm statistics
+    np.testing.assert_allclose(rvar, single.model.enc[1].running_var.numpy(), rtol=1e-5)
 
 
 def test_flat_params_views():
@@ -161,8 +164,9 @@ def test_flat_params_views():
     m = _ToyVAE()
     fp = train.FlatParams(m)
     assert fp.numel == sum(p.numel() for p in m.parameters())
-    m.enc.weight.data.fill_(2.0)
-    assert float(fp.flat[:8].sum()) == 16.0
-    out = m(torch.ones(3, 2), eps=torch.zeros(3, 2))
-    m.loss(torch.ones(3, 2), *out)[0].backward()
-    assert float(fp.grad.abs().sum()) > 0 and m.enc.weight.grad.data_ptr() == fp.grad.data_ptr()
+    m.enc[0].weight.data.fill_(2.0)
+    assert float(fp.flat[:12].sum()) == 24.0
+    x = torch.randn(5, 2)
+    out = m(x, eps=torch.zeros(5, 2))
+    m.loss(x, *out)[0].backward()
+    assert float(fp.grad.abs().sum()) > 0 and m.enc[0].weight.grad.data_ptr() == fp.grad.data_ptr()

@@ -38,6 +38,83 @@ def train_model(model, loader, epochs, lr, device, grad_clip=None, wu_strat="lin
     return model
 
 
+class _SyncBN1dFn(torch.autograd.Function):
+    """Cross-rank BatchNorm1d on [B,C]: ONE all_gather of (mean, biased var, count) in forward and ONE
+    all_reduce of (sum dy, sum dy*xhat) in backward -- and, unlike nn.SyncBatchNorm outside graph capture,
+    no host synchronisation (its count mask indexing stalls the launch queue once per layer per step)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, training, group):
+        world = dist.get_world_size(group)
+        n = x.shape[0]
+        if training:
+            mean_l = x.mean(0)
+            var_l = x.var(0, unbiased=False)
+            pack = torch.cat([mean_l, var_l, torch.full((1,), float(n), device=x.device, dtype=x.dtype)])
+            outs = [torch.empty_like(pack) for _ in range(world)]
+            dist.all_gather(outs, pack, group=group)                 # (works on gloo/CPU as well as NCCL)
+            allp = torch.stack(outs)
+            C = x.shape[1]
+            means, vars_, cnt = allp[:, :C], allp[:, C:2 * C], allp[:, 2 * C:]
+            N = cnt.sum()
+            mean = (means * cnt).sum(0) / N
+            var = ((vars_ + (means - mean) ** 2) * cnt).sum(0) / N
+            if running_mean is not None:
+                with torch.no_grad():
+                    running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+                    running_var.mul_(1 - momentum).add_(var * (N / (N - 1)), alpha=momentum)
+        else:
+            mean, var, N = running_mean, running_var, torch.tensor(float(n), device=x.device)
+        invstd = torch.rsqrt(var + eps)
+        xhat = (x - mean) * invstd
+        ctx.save_for_backward(xhat, weight, invstd, N.reshape(()))
+        ctx.group, ctx.training = group, training
+        return xhat * weight + bias
+
+    @staticmethod
+    def backward(ctx, dy):
+        xhat, weight, invstd, N = ctx.saved_tensors
+        dw = (dy * xhat).sum(0)
+        db = dy.sum(0)
+        if ctx.training:
+            sums = torch.stack([db, dw])
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
+            dx = (dy - sums[0] / N - xhat * (sums[1] / N)) * (invstd * weight)
+        else:
+            dx = dy * (invstd * weight)
+        return dx, dw, db, None, None, None, None, None, None
+
+
+class SyncBatchNorm1d(nn.BatchNorm1d):
+    """Drop-in for nn.BatchNorm1d on [B,C] inputs (same parameter / buffer names) with cross-rank statistics."""
+
+    def __init__(self, bn: nn.BatchNorm1d, group=None):
+        super().__init__(bn.num_features, bn.eps, bn.momentum, bn.affine, bn.track_running_stats)
+        self.load_state_dict(bn.state_dict())
+        self.to(bn.weight.device)
+        self.group = group
+
+    def forward(self, x):
+        if x.dim() != 2:
+            raise ValueError("SyncBatchNorm1d expects [B, C] inputs")
+        if self.training and self.track_running_stats:
+            self.num_batches_tracked.add_(1)
+        return _SyncBN1dFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
+                                 self.momentum if self.momentum is not None else 0.1, self.training, self.group)
+
+
+def convert_sync_batchnorm(model, group=None):
+    """BatchNorm1d -> SyncBatchNorm1d (lean, works on CPU/gloo too); other BatchNorms -> nn.SyncBatchNorm."""
+    for name, child in list(model.named_children()):
+        if type(child) is nn.BatchNorm1d:
+            setattr(model, name, SyncBatchNorm1d(child, group))
+        else:
+            convert_sync_batchnorm(child, group)
+    if any(isinstance(mod, (nn.BatchNorm2d, nn.BatchNorm3d)) for mod in model.modules()):
+        model = nn.SyncBatchNorm.convert_sync_batchnorm(model, group)
+    return model
+
+
 class FlatParams:
     """Re-homes every parameter (and its .grad) of `model` as a view into one flat fp32 buffer."""
 
@@ -89,8 +166,8 @@ class DataParallelTrainer:
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
         self.pg = process_group
-        if self.world > 1 and sync_bn and next(model.parameters()).is_cuda:
-            model = nn.SyncBatchNorm.convert_sync_batchnorm(model, process_group)
+        if self.world > 1 and sync_bn:
+            model = convert_sync_batchnorm(model, process_group)
         self.model = model
         self.fp = FlatParams(model)
         self.m = torch.zeros_like(self.fp.flat)
