@@ -194,21 +194,31 @@ def run_ours(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t) / K
 
+    n_before = _C.launch_count()
+    tr.step(dev_pool[0])                                   # one eager step: counts this library's launches per step
+    torch.cuda.synchronize()
+    launches_per_step = _C.launch_count() - n_before
+    use_graph = not args.no_graph
+    if use_graph:                                          # whole step (incl. the NCCL all-reduce) as one CUDA graph
+        tr.capture(dev_pool[0])
+    run_step = tr.step_graphed if use_graph else tr.step
+
     def step_resident(i):
-        tr.step(dev_pool[i % n_pool])
+        run_step(dev_pool[i % n_pool])
 
     def step_e2e(i):
-        x = host_pool[i % n_pool].to(dev, non_blocking=True)
-        total, _, _ = tr.step(x)
+        if use_graph:
+            total, _, _ = tr.step_graphed(host_pool[i % n_pool])          # H2D straight into the graph's input
+        else:
+            total, _, _ = tr.step(host_pool[i % n_pool].to(dev, non_blocking=True))
         loss_host.copy_(total.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    n0 = _C.launch_count()
     t_start = time.time()
     ms = timed(step_resident, args.steps, args.warmup)
     t_end = time.time()
-    launches = (_C.launch_count() - n0) * args.steps // (args.steps + args.warmup)
+    launches = launches_per_step * args.steps
     clocks = sampler.window(t_start, t_end) if sampler else {}
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
     value = world * B / (ms * 1e-3)
@@ -263,7 +273,8 @@ def run_ours(args, rank, local_rank, world):
                 "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
                 "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "precision": args.precision,
                            "parallelism": f"dp{world}", "l2": "flushed between timed iterations (256 MB write)",
-                           "optimizer": "fused Adam lr 1e-3 over flat buffer"},
+                           "optimizer": "fused Adam lr 1e-3 over flat buffer",
+                           "cuda_graph": bool(use_graph), "own_kernel_launches_per_step": int(launches_per_step)},
                 "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 2 * 4 * world,
                         "d2h_bytes_per_step": 4 * world},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extra": extra}
@@ -284,6 +295,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="per-GPU batch")
     ap.add_argument("--precision", default=os.environ.get("B200VAE_PRECISION", "tf32x3"), choices=["fp32", "tf32", "tf32x3"],
                     help="arithmetic of the H x H contractions in the train step (fp32 = SIMT parity path)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--roofline-precision", default="tf32", choices=["fp32", "tf32", "tf32x3"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -133,6 +133,12 @@ int b200vae_adam_step(float* param, const float* grad, float* m, float* v, long 
                       float beta1, float beta2, float eps, float weight_decay, long long step,
                       float grad_scale, void* stream);
 
+/* Same, with the 1-based step counter on the device (*step_dev is incremented, then used): the whole train
+ * step can then be captured in a CUDA graph and replayed. */
+int b200vae_adam_step_dev(float* param, const float* grad, float* m, float* v, long long n, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, long long* step_dev,
+                          float grad_scale, void* stream);
+
 int b200vae_last_cuda_error(void);
 const char* b200vae_version(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */

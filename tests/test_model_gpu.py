@@ -175,3 +175,25 @@ def test_flexible_family_losses_and_staged_backward():
             assert float(a.abs().max()) <= 1e-4 * gscale
         else:
             close_report(a.cpu().numpy(), q.grad.cpu().numpy(), 1e-4, "staged grad " + k, floor=1e-6 * gscale)
+
+
+def test_graphed_step_equals_eager_step():
+    """DataParallelTrainer.capture(): replaying the whole-step CUDA graph == launching the step eagerly
+    (same eps), and capturing does not advance the optimiser."""
+    from vae_song_b200 import train
+    import copy
+    m, _ = _load("pin_small")
+    m2 = copy.deepcopy(m)
+    a = train.DataParallelTrainer(m, lr=1e-3)
+    b = train.DataParallelTrainer(m2, lr=1e-3)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xs = [torch.randn(256, 2, device="cuda", generator=g) for _ in range(4)]
+    es = [torch.randn(256, 2, device="cuda", generator=g) for _ in range(4)]
+    a.capture(xs[0], es[0])
+    assert torch.equal(a.fp.flat, b.fp.flat) and int(a.t_dev) == 0
+    for x, e in zip(xs, es):
+        la = a.step_graphed(x, e)[0].clone()
+        lb = b.step(x, e)[0]
+        assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(lb))
+    close_report(a.fp.flat.cpu().numpy(), b.fp.flat.cpu().numpy(), 1e-5, "params after 4 steps", floor=1e-3)
+    assert int(a.t_dev) == 4 == int(b.t_dev)

@@ -184,6 +184,29 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+// graph-capturable variant: the step counter lives on the device (incremented here by block 0 *after* every
+// block has read it is not possible without a grid sync, so a 1-thread tick kernel runs first)
+__global__ void adam_tick_kernel(long long* step) { *step += 1; }
+__global__ void __launch_bounds__(256)
+adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                long long n, float lr, float b1, float b2, float eps, float wd, const long long* __restrict__ step,
+                float gscale) {
+  const double t = (double)*step;
+  const float bc1 = (float)(1.0 - pow((double)b1, t));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  const float step_size = lr / bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
+    float gi = g[i] * gscale;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] = pi - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+
 static int loss_grid(long long work) {
   long long blocks = (work + kLossThreads - 1) / kLossThreads;
   if (blocks < 1) blocks = 1;
@@ -245,5 +268,20 @@ extern "C" int b200vae_adam_step(float* param, const float* grad, float* m, floa
   if (blocks > 148 * 8) blocks = 148 * 8;
   adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, lr, beta1, beta2, eps, weight_decay,
                                                             (float)bc1, (float)sqrt(bc2), grad_scale);
+  return check_launch();
+}
+
+extern "C" int b200vae_adam_step_dev(float* param, const float* grad, float* m, float* v, long long n, float lr,
+                                     float beta1, float beta2, float eps, float weight_decay, long long* step_dev,
+                                     float grad_scale, void* stream) {
+  if (!param || !grad || !m || !v || !step_dev) return B200VAE_EALIGN;
+  if (n <= 0) return B200VAE_ESHAPE;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  int rc = check_launch();
+  if (rc) return rc;
+  adam_dev_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, lr, beta1, beta2, eps, weight_decay,
+                                                                step_dev, grad_scale);
   return check_launch();
 }

@@ -301,3 +301,10 @@ def adam_step_(param, grad, m, v, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, w
     _C.check(_C.load().b200vae_adam_step(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), float(lr),
                                          float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
                                          float(grad_scale), _stream()), "adam_step")
+
+
+def adam_step_dev_(param, grad, m, v, step_dev, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    """Graph-capturable fused Adam: `step_dev` is an int64 device scalar, incremented by the call."""
+    _C.check(_C.load().b200vae_adam_step_dev(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), float(lr),
+                                             float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                             _ptr(step_dev), float(grad_scale), _stream()), "adam_step_dev")

@@ -173,6 +173,8 @@ class DataParallelTrainer:
         self.m = torch.zeros_like(self.fp.flat)
         self.v = torch.zeros_like(self.fp.flat)
         self.t = 0
+        self.t_dev = torch.zeros((), dtype=torch.int64, device=self.fp.flat.device)   # device step counter (graphs)
+        self._graph = None
         self.hp = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         self.grad_clip = grad_clip
         self._opt = optimizer_step or self._fused_adam
@@ -180,7 +182,46 @@ class DataParallelTrainer:
             dist.broadcast(self.fp.flat, src=0, group=self.pg)
 
     def _fused_adam(self, flat, grad, m, v, t, scale, hp):
-        ops.adam_step_(flat, grad, m, v, t, hp["lr"], hp["betas"], hp["eps"], hp["weight_decay"], scale)
+        # step count kept on the device so that the call is identical every step (CUDA-graph capturable)
+        ops.adam_step_dev_(flat, grad, m, v, self.t_dev, hp["lr"], hp["betas"], hp["eps"], hp["weight_decay"], scale)
+
+    # ---- whole-step CUDA graph (launch-bound regimes: small batches, multi-GPU with many tiny collectives) ----
+    def capture(self, x_example, eps_example=None, warmup=3):
+        """Capture forward -> loss -> backward -> all-reduce -> Adam into one CUDA graph.  Optimiser / BatchNorm
+        state touched by the warm-up steps is restored, so capturing does not advance training."""
+        dev = x_example.device
+        self._sx = x_example.clone()
+        self._se = None if eps_example is None else eps_example.clone()
+        snap = [t.clone() for t in (self.fp.flat, self.m, self.v, self.t_dev)]
+        bufs = [(b, b.clone()) for b in self.model.buffers()]
+        t_host = self.t
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(self._sx, self._se)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._sout = self.step(self._sx, self._se)
+        for dst, src in zip((self.fp.flat, self.m, self.v, self.t_dev), snap):
+            dst.copy_(src)
+        for b, old in bufs:
+            b.copy_(old)
+        self.t = t_host
+        self._graph = g
+        return self
+
+    def step_graphed(self, x_local, eps_local=None):
+        if self._graph is None:
+            raise RuntimeError("call capture() first")
+        self._sx.copy_(x_local, non_blocking=True)
+        if eps_local is not None:
+            self._se.copy_(eps_local, non_blocking=True)
+        self._graph.replay()
+        self.t += 1
+        return self._sout
 
     def step(self, x_local, eps_local=None):
         model, W = self.model, self.world
