@@ -295,12 +295,17 @@ def run_ours(args, rank, local_rank, world):
                 "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 2 * 4 * world,
                         "d2h_bytes_per_step": 4 * world},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extra": extra}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if sampler:
         sampler.stop()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+    # Tearing down NCCL communicators that are referenced by a live CUDA graph can block for minutes:
+    # release the graph first and leave without the (optional) communicator destruction.
+    tr._graph = None
+    sys.stdout.flush()
+    os._exit(0)
 
 
 def main():
