@@ -75,11 +75,18 @@ class ICNN(nn.Module):
         except KeyError:
             raise ValueError(f"unknown precision {self.precision!r}; choose from {list(_C.PRECISIONS)}")
 
+    FUSED_MAX_D = 4      # widest input the fused kernels keep in registers; wider inputs take the GEMM-composed path
+
     def forward(self, input):
+        if self.in_channel > self.FUSED_MAX_D:
+            if not input.is_cuda:
+                raise _C.B200VaeError("expected a CUDA tensor; vae_song_b200 has no CPU fallback")
+            return ops.icnn_potential_wide(input, self._mode(), *self._flat_params())
         return ops.IcnnPotentialFn.apply(input, self._mode(), self._prec(), *self._flat_params())
 
     def brenier(self, input, kappa=0.0):
-        return ops.IcnnBrenierFn.apply(input, float(kappa), self._mode(), self._prec(), *self._flat_params())
+        fn = ops.IcnnBrenierWideFn if self.in_channel > self.FUSED_MAX_D else ops.IcnnBrenierFn
+        return fn.apply(input, float(kappa), self._mode(), self._prec(), *self._flat_params())
 
 
 def _bn_act(norm, act=True):
