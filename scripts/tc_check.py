@@ -32,11 +32,14 @@ def run(d, H, B, regime, prec, kappa=0.1, seed=0):
 
 if __name__ == "__main__":
     names = {0: "fp32", 1: "tf32", 3: "tf32x3"}
-    for prec in (0, 3, 1):
+    fwd_only = "--fwd-only" in sys.argv
+    precs = (3, 1) if fwd_only else (0, 3, 1)
+    print("B200VAE_TC2 =", os.environ.get("B200VAE_TC2", "0"))
+    for prec in precs:
         for (d, H, B, regime) in ((2, 256, 256, "mixed"), (2, 96, 77, "mixed"), (3, 512, 1000, "mixed"), (2, 1024, 4096, "mixed"), (2, 1024, 512, "default")):
             run(d, H, B, regime, prec)
     # timing at the headline size
-    for prec in (0, 3, 1):
+    for prec in precs:
         for H in (512, 1024):
             zt, ws = run(2, H, 65536, "mixed", prec)
             for _ in range(3):
@@ -50,6 +53,8 @@ if __name__ == "__main__":
             ms = e0.elapsed_time(e1) / 10
             tf = io.flops_decode(2, H) * 65536 / ms / 1e9
             print(f"   TIMING {names[prec]} H={H}: {ms:.3f} ms  -> {tf:.1f} TFLOP/s algorithmic, {65536/ms/1e3:.2f} M samples/s")
+            if fwd_only:
+                continue
             # backward (rows + dP0 + finalize)
             rng = np.random.default_rng(5)
             p = io.random_params(rng, 2, H, np.float64, "mixed")

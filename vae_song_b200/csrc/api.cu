@@ -1,4 +1,6 @@
 // api.cu -- extern "C" entry points of libb200vae.so for the ICNN path (validation + dispatch).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200vae {
@@ -25,6 +27,8 @@ int simt_bwd(const float* z, const float* v, const float* gpsi, const uint32_t* 
 int tc_prepare(const b200vae_icnn_params* p, int d, int H, int mode, int precision, float* ws, cudaStream_t st);
 int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1,
            uint8_t* mask2, int precision, const float* ws, cudaStream_t st);
+int tc2_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1,
+            uint8_t* mask2, int precision, const float* ws, cudaStream_t st);
 size_t tc_extra_ws_floats(int d, int H, int precision);
 size_t tc_bwd_ws_floats(int B, int d, int H);
 int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H,
@@ -82,6 +86,9 @@ extern "C" int b200vae_icnn_decode_fwd(const float* z, int B, int d, int H, int 
   if (ws_bytes < b200vae_icnn_workspace_bytes(B, d, H, precision, 0)) return B200VAE_EWS;
   if (precision == B200VAE_PREC_FP32)
     return simt_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, ws_base(ws), (cudaStream_t)stream);
+  // forward kernel variant: CTA pairs (tcgen05 cta_group::2, double-buffered TMEM) or single CTA; B200VAE_TC2=0/1
+  static const int use_pair = [] { const char* e = getenv("B200VAE_TC2"); return e ? atoi(e) : 0; }();
+  if (use_pair) return tc2_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), (cudaStream_t)stream);
   return tc_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), (cudaStream_t)stream);
 }
 

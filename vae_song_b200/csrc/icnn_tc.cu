@@ -15,118 +15,18 @@
 // warp 8 TMA producer + TMEM allocator, warp 9 MMA issuer (one elected lane).
 // Precisions: TF32 (kind::tf32, operands rounded-to-nearest to tf32) and 3xTF32
 // (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulate in TMEM: fp32-grade accuracy).
-#include <cuda.h>
-
 #include <mutex>
 #include <unordered_map>
 
 #include "common.cuh"
 
+#include "tc_common.cuh"
+
 namespace b200vae {
 
-constexpr int kTM = 256;          // samples per CTA
-constexpr int kTN = 256;          // accumulator columns per pass
-constexpr int kKB = 16;           // K elements per block (64 B rows, SWIZZLE_64B)
-constexpr int kTileBytes = 256 * 64;   // one 256-row x 64-byte operand tile = 16 KB
-
-// ------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
-
-// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 |
-// SBO(512 B >> 4)<<32 | version(1)<<46 | layout SWIZZLE_64B(4)<<61.  8-row atoms of 64-byte rows.
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)4 << 61);
-}
-// kind::tf32 instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 at 17, M>>4 at 24
-constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
-// byte offset of 16-byte chunk c (0..3) of row r (0..255) inside a 256-row x 64 B SWIZZLE_64B tile
-__device__ __forceinline__ uint32_t sw64_off(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
-
-// ------------------------------------------------------------------------------------ TC workspace
-// (floats, after the SIMT layout's `end`)  Hq = H rounded up to 256.
-//   B1hi,B1lo [Hq][Hq]  B1[o][i] = P[o][i]   (GEMM1: rows = output unit o, K = input unit i)
-//   B2hi,B2lo [Hq][Hq]  B2[i][o] = P[o][i]   (GEMM2: rows = input unit i,  K = output unit o)
-//   A0q, A1q  float4[Hq] = (w0, w1, w2, bias)   P1q [Hq]
-struct TcLayout {
-  int Hq;
-  size_t B1hi, B1lo, B2hi, B2lo, A0q, A1q, P1q, end;
-};
-inline TcLayout tc_layout(int d, int H) {
-  (void)d;
-  TcLayout T;
-  T.Hq = round_up(H, 256);
-  const size_t q = (size_t)T.Hq * T.Hq;
-  size_t o = 0;
-  T.B1hi = o; o += q; T.B1lo = o; o += q; T.B2hi = o; o += q; T.B2lo = o; o += q;
-  T.A0q = o; o += (size_t)4 * T.Hq; T.A1q = o; o += (size_t)4 * T.Hq; T.P1q = o; o += T.Hq;
-  T.end = o + 64;
-  return T;
-}
 size_t tc_extra_ws_floats(int d, int H, int precision) {
   (void)precision;
   return tc_layout(d, H).end;
-}
-static float* tc_base(float* ws, int d, int H) {
-  // TC arrays start after the largest SIMT layout we might share the buffer with; use a fixed, B-independent
-  // offset: the forward part of the SIMT layout (the backward scratch is placed AFTER the TC arrays, see api.cu)
-  return ws + ws_layout(1, d, H).fwd_end;
 }
 
 __global__ void tc_prepare_kernel(const float* __restrict__ P0, const float* __restrict__ P0T, const float* __restrict__ P1,
@@ -161,22 +61,6 @@ struct TcMaps { CUtensorMap b1hi, b1lo, b2hi, b2lo; };
 constexpr int kNW = 16;                 // worker warps: 2 threads per sample row (K halves / column halves)
 constexpr int kTcThreads = (kNW + 2) * 32;
 
-template <int D>
-__device__ __forceinline__ float lin_of(const float4 q, const float (&z)[D]) {
-  float h = q.w;
-  h = fmaf(q.x, z[0], h);
-  if (D > 1) h = fmaf(q.y, z[D > 1 ? 1 : 0], h);
-  if (D > 2) h = fmaf(q.z, z[D > 2 ? 2 : 0], h);
-  return h;
-}
-template <int D>
-__device__ __forceinline__ float dot_of(const float4 q, const float (&v)[D]) {
-  float h = q.x * v[0];
-  if (D > 1) h = fmaf(q.y, v[D > 1 ? 1 : 0], h);
-  if (D > 2) h = fmaf(q.z, v[D > 2 ? 2 : 0], h);
-  return h;
-}
-__device__ __forceinline__ float comp(const float4 q, int j) { return j == 0 ? q.x : (j == 1 ? q.y : q.z); }
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kNW * 32) : "memory"); }
 
 template <bool X3>

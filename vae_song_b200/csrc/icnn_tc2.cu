@@ -1,0 +1,415 @@
+// icnn_tc2.cu -- CTA-pair (tcgen05 cta_group::2) version of the fused ICNN forward.
+//
+// A cluster of 2 CTAs (one TPC) owns a 256-sample tile: CTA r holds sample rows [128r, 128r+128) -- its A
+// rows in its own shared memory and its D rows in its own TMEM -- and HALF of every B tile (128 of the 256
+// weight rows of the pass).  One `tcgen05.mma.cta_group::2` (M=256, N=256, K=8) issued by the leader CTA
+// drives both SMs' tensor cores, so per SM and per MMA only 4 KB of A + 4 KB of B are read from shared
+// memory (vs 4 + 8 KB in the single-CTA kernel) and each SM fetches only its half of B from L2.
+// With 128 rows per SM a pass needs 256 TMEM columns, so the 512 columns hold TWO accumulator buffers:
+// the epilogue of pass p (8 dedicated warps) overlaps the MMAs of pass p+1 fed by 8 dedicated generator
+// warps.  Same thread-local reductions as icnn_tc.cu (one sample row per thread pair).
+//
+// Barriers (per CTA, same offsets in both):  full[s] (leader's counts 16 generator-warp arrivals from BOTH
+// CTAs + its own expect_tx covering both TMA halves), empty[s] / accfull[b] (tcgen05.commit multicast to
+// both CTAs), accempty[b] (leader's counts 16 epilogue-warp arrivals from both CTAs).
+#include <mutex>
+#include <unordered_map>
+
+#include "tc_common.cuh"
+
+namespace b200vae {
+
+constexpr int k2Rows = 128;                       // sample rows per CTA
+constexpr int k2Threads = 18 * 32;                // 8 epilogue warps, 8 generator warps, TMA warp, MMA warp
+constexpr int k2TileBytes = k2Rows * 64;          // 128 rows x 64 B = 8 KB (A tile, and this CTA's half of a B tile)
+// kind::tf32, D=F32, K-major A/B, N=256, M=256 (cta_group::2)
+constexpr uint32_t kIdescTf32M256 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t lead_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(lead_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void bar_all_workers() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+struct Tc2Maps { CUtensorMap b1hi, b1lo, b2hi, b2lo; };   // boxes of 16 x 128 (this CTA's half of a 256-row B tile)
+
+template <bool X3>
+struct Tc2Cfg {
+  static constexpr int S = X3 ? 4 : 6;
+  static constexpr int kStageBytes = (X3 ? 4 : 2) * k2TileBytes;          // A(hi[,lo]) + B half (hi[,lo])
+  static constexpr int kOffAlo = k2TileBytes, kOffB = (X3 ? 2 : 1) * k2TileBytes, kOffBlo = 3 * k2TileBytes;
+};
+template <bool X3>
+static size_t tc2_smem_bytes(int Hq) {
+  using C = Tc2Cfg<X3>;
+  return (size_t)C::S * C::kStageBytes + (size_t)Hq * (16 + 16 + 4) + (size_t)(Hq / 32) * k2Rows * 4 + 4 * k2Rows * 4 * 4 +
+         (2 * C::S + 4) * 8 + 16 + 1024;
+}
+
+template <int D, bool X3>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+icnn_tc2_fwd_kernel(const __grid_constant__ Tc2Maps maps, const float* __restrict__ z, int B, int Hq, int Hw_out,
+                    float kappa, const float4* __restrict__ A0q_g, const float4* __restrict__ A1q_g,
+                    const float* __restrict__ P1q_g, const float* __restrict__ A2p, float* __restrict__ psi,
+                    float* __restrict__ xhat, uint32_t* __restrict__ mask1, uint8_t* __restrict__ mask2) {
+  using C = Tc2Cfg<X3>;
+  constexpr int S = C::S;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* stages = smem;
+  float4* A0s = reinterpret_cast<float4*>(smem + S * C::kStageBytes);
+  float4* A1s = A0s + Hq;
+  float* P1s = reinterpret_cast<float*>(A1s + Hq);
+  uint32_t* maskw = reinterpret_cast<uint32_t*>(P1s + Hq);             // [Hq/32][128]
+  float* xch = reinterpret_cast<float*>(maskw + (Hq / 32) * k2Rows);   // [4][128][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 4 * k2Rows * 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull0 = smem_u32(bars + 2 * S),
+                 accempty0 = smem_u32(bars + 2 * S + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int m0 = (blockIdx.x >> 1) * 256 + (int)rank * k2Rows;
+  const int NP = Hq / kTN, NKB = Hq / kKB;
+  const int ngemm = (xhat != nullptr) ? 2 : 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 16 + 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(accfull0 + 8 * b, 1); mbar_init(accempty0 + 8 * b, 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 16) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  for (int i = tid; i < Hq; i += k2Threads) { A0s[i] = A0q_g[i]; A1s[i] = A1q_g[i]; P1s[i] = P1q_g[i]; }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // peer barriers initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lead_full0 = mapa_u32(full0, 0), lead_accempty0 = mapa_u32(accempty0, 0);
+
+  if (warp < 8) {
+    // =========================== epilogue warps: drain my row, 128 of the pass's 256 columns ===========================
+    const int row = (warp & 3) * 32 + lane, chalf = warp >> 2;
+    const bool valid = (m0 + row) < B;
+    float zr[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) zr[j] = valid ? z[(size_t)(m0 + row) * D + j] : 0.f;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chalf * 128);
+    float h2 = 0.f;
+    float xacc[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) xacc[j] = 0.f;
+    for (int pp = 0; pp < ngemm * NP; ++pp) {
+      const int buf = pp & 1, p = pp % NP;
+      const bool g2 = pp >= NP;
+      mbar_wait(accfull0 + 8 * buf, (pp >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(taddr + buf * kTN + cc * 32, r);
+        tmem_ld_wait();
+        const int nb = p * kTN + chalf * 128 + cc * 32;
+        if (!g2) {
+          uint32_t word = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float h1 = __uint_as_float(r[j]) + lin_of<D>(A1s[nb + j], zr);
+            const bool pos = h1 > 0.f;
+            h2 = fmaf(P1s[nb + j], pos ? h1 : kSlope * h1, h2);
+            word |= (pos ? 1u : 0u) << j;
+          }
+          maskw[(nb >> 5) * k2Rows + row] = word;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float4 q = A0s[nb + j];
+            const float h = lin_of<D>(q, zr);
+            const float s0 = slope_of(h), a0 = h * s0;
+            const float g0 = __uint_as_float(r[j]) * (2.f * a0) * s0;
+#pragma unroll
+            for (int jj = 0; jj < D; ++jj) xacc[jj] = fmaf(comp(q, jj), g0, xacc[jj]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_accempty0 + 8 * buf);
+      if (pp == NP - 1) {                                     // GEMM1 finished: publish h2 halves + masks
+        xch[chalf * k2Rows + row] = h2;
+        bar_all_workers();
+        h2 = xch[row] + xch[k2Rows + row];
+        float lin = A2p[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) lin = fmaf(A2p[j], zr[j], lin);
+        h2 += lin;
+        const bool pos2 = h2 > 0.f;
+        if (valid) {
+          if (chalf == 0) {
+            if (psi) psi[m0 + row] = pos2 ? h2 : kSlope * h2;
+            if (mask2) mask2[m0 + row] = pos2 ? 1 : 0;
+          }
+          if (mask1)
+            for (int wd = chalf; wd < Hw_out; wd += 2) mask1[(size_t)(m0 + row) * Hw_out + wd] = maskw[wd * k2Rows + row];
+        }
+      }
+    }
+    if (xhat != nullptr) {
+      bar_all_workers();                                      // [A] xch free: everybody has read the h2 halves
+#pragma unroll
+      for (int j = 0; j < D; ++j) xch[(chalf * k2Rows + row) * 4 + j] = xacc[j];
+      bar_all_workers();                                      // [B] partials visible to the row's writer thread
+    }
+  } else if (warp < 16) {
+    // =========================== generator warps: A rows for every K-block ===========================
+    const int t2 = tid - 256, row = t2 & 127, kh = t2 >> 7, rsw = (row >> 1) & 3;
+    const bool valid = (m0 + row) < B;
+    float zr[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) zr[j] = valid ? z[(size_t)(m0 + row) * D + j] : 0.f;
+    const uint32_t a_row_off = (uint32_t)row * 64u;
+    uint32_t it = 0;
+    auto produce = [&](int kb, auto&& gen) {
+      const uint32_t s = it % S, ph = (it / S) & 1;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = gen(kb * kKB + kh * 8 + e, e);
+      mbar_wait(empty0 + 8 * s, ph ^ 1);
+      unsigned char* At = stages + s * C::kStageBytes;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = kh * 2 + cc;
+        const uint32_t off = a_row_off + ((uint32_t)(c ^ rsw) << 4);
+        const float4 hi = make_float4(to_tf32(v[cc * 4 + 0]), to_tf32(v[cc * 4 + 1]), to_tf32(v[cc * 4 + 2]), to_tf32(v[cc * 4 + 3]));
+        *reinterpret_cast<float4*>(At + off) = hi;
+        if (X3)
+          *reinterpret_cast<float4*>(At + C::kOffAlo + off) =
+              make_float4(to_tf32(v[cc * 4 + 0] - hi.x), to_tf32(v[cc * 4 + 1] - hi.y), to_tf32(v[cc * 4 + 2] - hi.z),
+                          to_tf32(v[cc * 4 + 3] - hi.w));
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_full0 + 8 * s);
+      ++it;
+    };
+    for (int p = 0; p < NP; ++p)
+      for (int kb = 0; kb < NKB; ++kb)
+        produce(kb, [&](int k, int) {
+          const float h = lin_of<D>(A0s[k], zr);
+          const float a0 = fmaxf(h, kSlope * h);
+          return a0 * a0;
+        });
+    bar_all_workers();                                        // h2 halves + mask words from the epilogue warps
+    float h2 = xch[row] + xch[k2Rows + row];
+    {
+      float lin = A2p[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) lin = fmaf(A2p[j], zr[j], lin);
+      h2 += lin;
+    }
+    const float s2 = h2 > 0.f ? 1.f : kSlope;
+    if (xhat != nullptr) {
+      float xa[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) xa[j] = 0.f;
+      for (int p = 0; p < NP; ++p)
+        for (int kb = 0; kb < NKB; ++kb) {
+          const uint32_t bits = maskw[(kb >> 1) * k2Rows + row] >> ((kb & 1) * 16 + kh * 8);
+          produce(kb, [&](int k, int e) {
+            const float c1 = s2 * P1s[k];
+            const float g1 = ((bits >> e) & 1u) ? c1 : kSlope * c1;
+            if (p == 0) {
+              const float4 q = A1s[k];
+#pragma unroll
+              for (int j = 0; j < D; ++j) xa[j] = fmaf(comp(q, j), g1, xa[j]);
+            }
+            return g1;
+          });
+        }
+      bar_all_workers();                                      // [A]
+#pragma unroll
+      for (int j = 0; j < D; ++j) xch[((2 + kh) * k2Rows + row) * 4 + j] = xa[j];
+      bar_all_workers();                                      // [B]
+      if (valid && kh == 0) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          const float sum = (xch[(0 * k2Rows + row) * 4 + j] + xch[(1 * k2Rows + row) * 4 + j]) +
+                            (xch[(2 * k2Rows + row) * 4 + j] + xch[(3 * k2Rows + row) * 4 + j]);
+          xhat[(size_t)(m0 + row) * D + j] = fmaf(2.f * kappa, zr[j], fmaf(s2, A2p[j], sum));
+        }
+      }
+    }
+  } else if (warp == 16) {
+    // =========================== TMA producer: this CTA's half of every B tile ===========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int g = 0; g < ngemm; ++g) {
+        const CUtensorMap* mhi = g == 0 ? &maps.b1hi : &maps.b2hi;
+        const CUtensorMap* mlo = g == 0 ? &maps.b1lo : &maps.b2lo;
+        for (int p = 0; p < NP; ++p)
+          for (int kb = 0; kb < NKB; ++kb, ++it) {
+            const uint32_t s = it % S, ph = (it / S) & 1;
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            const uint32_t dst = smem_u32(stages + s * C::kStageBytes);
+            if (rank == 0) mbar_arrive_expect_tx(full0 + 8 * s, 2 * (X3 ? 2 : 1) * k2TileBytes);   // both halves
+            tma_load_2d_2sm(dst + C::kOffB, mhi, lead_full0 + 8 * s, kb * kKB, p * kTN + (int)rank * k2Rows);
+            if (X3) tma_load_2d_2sm(dst + C::kOffBlo, mlo, lead_full0 + 8 * s, kb * kKB, p * kTN + (int)rank * k2Rows);
+          }
+      }
+    }
+  } else {
+    // =========================== MMA issuer (leader CTA only) ===========================
+    if (lane == 0 && rank == 0) {
+      uint32_t it = 0;
+      for (int pp = 0; pp < ngemm * NP; ++pp) {
+        const int buf = pp & 1;
+        mbar_wait(accempty0 + 8 * buf, ((pp >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_t = tmem_base + (uint32_t)(buf * kTN);
+        for (int kb = 0; kb < NKB; ++kb, ++it) {
+          const uint32_t s = it % S, ph = (it / S) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stages + s * C::kStageBytes);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t a_hi = make_desc_sw64(sa + ks * 32);
+            const uint64_t b_hi = make_desc_sw64(sa + C::kOffB + ks * 32);
+            const uint32_t acc = (kb | ks) ? 1u : 0u;
+            if (X3) {
+              const uint64_t a_lo = make_desc_sw64(sa + C::kOffAlo + ks * 32);
+              const uint64_t b_lo = make_desc_sw64(sa + C::kOffBlo + ks * 32);
+              umma_tf32_2sm(d_t, a_lo, b_hi, kIdescTf32M256, acc);
+              umma_tf32_2sm(d_t, a_hi, b_lo, kIdescTf32M256, 1u);
+              umma_tf32_2sm(d_t, a_hi, b_hi, kIdescTf32M256, 1u);
+            } else {
+              umma_tf32_2sm(d_t, a_hi, b_hi, kIdescTf32M256, acc);
+            }
+          }
+          umma_commit_2sm(empty0 + 8 * s);
+        }
+        umma_commit_2sm(accfull0 + 8 * buf);
+      }
+    }
+  }
+  // teardown: nobody may leave (or free TMEM) while the peer can still touch this CTA's smem / TMEM
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 16) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_map128(CUtensorMap* m, const float* base, int Hq) {
+  static EncodeTiledFn2 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p)
+      fn = reinterpret_cast<EncodeTiledFn2>(p);
+  }
+  if (!fn) return B200VAE_ECUDA;
+  const cuuint64_t dims[2] = {(cuuint64_t)Hq, (cuuint64_t)Hq};
+  const cuuint64_t strides[1] = {(cuuint64_t)Hq * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)k2Rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_last_cuda_error = 100000 + (int)r; return B200VAE_ECUDA; }
+  return B200VAE_OK;
+}
+
+template <int D, bool X3>
+static int launch_tc2(const Tc2Maps& maps, const float* z, int B, const TcLayout& T, const float* tb, const float* A2p,
+                      int Hw_out, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2, cudaStream_t st) {
+  const size_t smem = tc2_smem_bytes<X3>(T.Hq);
+  if (smem > 227 * 1024) return B200VAE_EUNSUP;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(icnn_tc2_fwd_kernel<D, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_done = true;
+  }
+  const int grid = 2 * ((B + 255) / 256);
+  icnn_tc2_fwd_kernel<D, X3><<<grid, k2Threads, smem, st>>>(
+      maps, z, B, T.Hq, Hw_out, kappa, reinterpret_cast<const float4*>(tb + T.A0q),
+      reinterpret_cast<const float4*>(tb + T.A1q), tb + T.P1q, A2p, psi, xhat, mask1, mask2);
+  return check_launch();
+}
+
+int tc2_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2,
+            int precision, const float* ws, cudaStream_t st) {
+  if (precision == B200VAE_PREC_BF16 || d > 3) return B200VAE_EUNSUP;
+  const WsLayout L = ws_layout(1, d, H);
+  const TcLayout T = tc_layout(d, H);
+  const float* tb = tc_base(const_cast<float*>(ws), d, H);
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, Tc2Maps> cache;
+  Tc2Maps maps;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    const uint64_t key = reinterpret_cast<uint64_t>(tb) ^ ((uint64_t)T.Hq << 48);
+    auto itc = cache.find(key);
+    if (itc == cache.end()) {
+      int rc = make_map128(&maps.b1hi, tb + T.B1hi, T.Hq);
+      if (!rc) rc = make_map128(&maps.b1lo, tb + T.B1lo, T.Hq);
+      if (!rc) rc = make_map128(&maps.b2hi, tb + T.B2hi, T.Hq);
+      if (!rc) rc = make_map128(&maps.b2lo, tb + T.B2lo, T.Hq);
+      if (rc) return rc;
+      if (cache.size() > 256) cache.clear();
+      cache.emplace(key, maps);
+    } else {
+      maps = itc->second;
+    }
+  }
+  const bool x3 = (precision == B200VAE_PREC_TF32X3);
+  const int Hw_out = L.Hp / 32;
+#define B200VAE_TC2(DD)                                                                                          \
+  return x3 ? launch_tc2<DD, true>(maps, z, B, T, tb, ws + L.A2p, Hw_out, kappa, psi, xhat, mask1, mask2, st)   \
+            : launch_tc2<DD, false>(maps, z, B, T, tb, ws + L.A2p, Hw_out, kappa, psi, xhat, mask1, mask2, st)
+  switch (d) {
+    case 1: B200VAE_TC2(1);
+    case 2: B200VAE_TC2(2);
+    case 3: B200VAE_TC2(3);
+    default: return B200VAE_EUNSUP;
+  }
+#undef B200VAE_TC2
+}
+
+}  // namespace b200vae
