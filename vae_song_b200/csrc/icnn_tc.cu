@@ -110,7 +110,7 @@ __device__ __forceinline__ uint32_t tc_setup(const TcSmem& m, int Hq, const floa
   using C = TcCfg<X3>;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < C::S; ++s) { mbar_init(m.full0 + 8 * s, kNW + 1); mbar_init(m.empty0 + 8 * s, 1); }
+    for (int s = 0; s < C::S; ++s) { mbar_init(m.full0 + 8 * s, kNW / 2 + 1); mbar_init(m.empty0 + 8 * s, 1); }
     mbar_init(m.accfull, 1);
     mbar_init(m.accempty, kNW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -206,26 +206,28 @@ __device__ __forceinline__ Worker make_worker(uint32_t tmem_base) {
   w.it = 0; w.pp = 0;
   return w;
 }
-// generate my 8 K-elements (2 chunks) of K-block `kb` with gen(k) and publish the stage
+// The two threads of a row ALTERNATE K-blocks (thread kh produces the blocks with kb % 2 == kh, all 16 elements of
+// the row): every warp then has two MMA stage-times to turn one stage around, which hides the LDS -> FMA -> STS ->
+// proxy-fence -> arrive latency chain that otherwise paces the pipeline.  gen(k, e) -> A[row, k], e = k - 16*kb.
 template <bool X3, class Gen>
 __device__ __forceinline__ void worker_produce(const TcSmem& m, Worker& w, int kb, Gen&& gen) {
   using C = TcCfg<X3>;
+  if ((kb & 1) != w.kh) { ++w.it; return; }
   const uint32_t s = w.it % C::S, ph = (w.it / C::S) & 1;
-  float v[8];
+  float v[16];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) v[e] = gen(kb * kKB + w.kh * 8 + e, e);
+  for (int e = 0; e < 16; ++e) v[e] = gen(kb * kKB + e, e);
   mbar_wait(m.empty0 + 8 * s, ph ^ 1);
   unsigned char* At = m.stages + s * C::kStageBytes;
 #pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    const int c = w.kh * 2 + cc;
+  for (int c = 0; c < 4; ++c) {
     const uint32_t off = w.a_row_off + ((uint32_t)(c ^ w.rsw) << 4);
-    const float4 hi = make_float4(to_tf32(v[cc * 4 + 0]), to_tf32(v[cc * 4 + 1]), to_tf32(v[cc * 4 + 2]), to_tf32(v[cc * 4 + 3]));
+    const float4 hi = make_float4(to_tf32(v[c * 4 + 0]), to_tf32(v[c * 4 + 1]), to_tf32(v[c * 4 + 2]), to_tf32(v[c * 4 + 3]));
     *reinterpret_cast<float4*>(At + off) = hi;
     if (X3)
       *reinterpret_cast<float4*>(At + C::kOffAlo + off) =
-          make_float4(to_tf32(v[cc * 4 + 0] - hi.x), to_tf32(v[cc * 4 + 1] - hi.y), to_tf32(v[cc * 4 + 2] - hi.z),
-                      to_tf32(v[cc * 4 + 3] - hi.w));
+          make_float4(to_tf32(v[c * 4 + 0] - hi.x), to_tf32(v[c * 4 + 1] - hi.y), to_tf32(v[c * 4 + 2] - hi.z),
+                      to_tf32(v[c * 4 + 3] - hi.w));
   }
   fence_async_smem();
   __syncwarp();
@@ -341,7 +343,7 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
       for (int j = 0; j < D; ++j) xacc[j] = 0.f;
       for (int p = 0; p < NP; ++p) {
         for (int kb = 0; kb < NKB; ++kb) {
-          const uint32_t bits = m.maskw[(kb >> 1) * 256 + w.row] >> ((kb & 1) * 16 + w.kh * 8);
+          const uint32_t bits = m.maskw[(kb >> 1) * 256 + w.row] >> ((kb & 1) * 16);
           worker_produce<X3>(m, w, kb, [&](int k, int e) {
             const float c1 = s2 * m.P1s[k];
             const float g1 = ((bits >> e) & 1u) ? c1 : kSlope * c1;
@@ -431,7 +433,7 @@ icnn_tc_bwd_rows_kernel(const __grid_constant__ TcMaps maps, const float* __rest
     // -------- GEMM-A --------
     for (int p = 0; p < NP; ++p) {
       for (int kb = 0; kb < NKB; ++kb) {
-        const uint32_t bits = m.maskw[(kb >> 1) * 256 + w.row] >> ((kb & 1) * 16 + w.kh * 8);
+        const uint32_t bits = m.maskw[(kb >> 1) * 256 + w.row] >> ((kb & 1) * 16);
         worker_produce<X3>(m, w, kb, [&](int k, int e) {
           const float c1 = s2 * m.P1s[k];
           return ((bits >> e) & 1u) ? c1 : kSlope * c1;
