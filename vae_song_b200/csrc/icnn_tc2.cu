@@ -39,7 +39,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release.cta): the data stays in THIS CTA's shared memory and was already made visible to
+  // the async proxy by fence.proxy.async; a cluster-scope release costs ~1 us per arrive and paced the pipeline
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t lead_bar, int c0, int c1) {
   asm volatile(
@@ -101,7 +103,7 @@ icnn_tc2_fwd_kernel(const __grid_constant__ Tc2Maps maps, const float* __restric
   const int ngemm = (xhat != nullptr) ? 2 : 1;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 16 + 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 8 + 1); mbar_init(empty0 + 8 * s, 1); }   // 4 generator warps x 2 CTAs + TMA
     for (int b = 0; b < 2; ++b) { mbar_init(accfull0 + 8 * b, 1); mbar_init(accempty0 + 8 * b, 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -199,23 +201,23 @@ icnn_tc2_fwd_kernel(const __grid_constant__ Tc2Maps maps, const float* __restric
     for (int j = 0; j < D; ++j) zr[j] = valid ? z[(size_t)(m0 + row) * D + j] : 0.f;
     const uint32_t a_row_off = (uint32_t)row * 64u;
     uint32_t it = 0;
-    auto produce = [&](int kb, auto&& gen) {
+    auto produce = [&](int kb, auto&& gen) {                   // group kh produces the K-blocks with kb % 2 == kh
+      if ((kb & 1) != kh) { ++it; return; }
       const uint32_t s = it % S, ph = (it / S) & 1;
-      float v[8];
+      float v[16];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = gen(kb * kKB + kh * 8 + e, e);
+      for (int e = 0; e < 16; ++e) v[e] = gen(kb * kKB + e, e);
       mbar_wait(empty0 + 8 * s, ph ^ 1);
       unsigned char* At = stages + s * C::kStageBytes;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = kh * 2 + cc;
+      for (int c = 0; c < 4; ++c) {
         const uint32_t off = a_row_off + ((uint32_t)(c ^ rsw) << 4);
-        const float4 hi = make_float4(to_tf32(v[cc * 4 + 0]), to_tf32(v[cc * 4 + 1]), to_tf32(v[cc * 4 + 2]), to_tf32(v[cc * 4 + 3]));
+        const float4 hi = make_float4(to_tf32(v[c * 4 + 0]), to_tf32(v[c * 4 + 1]), to_tf32(v[c * 4 + 2]), to_tf32(v[c * 4 + 3]));
         *reinterpret_cast<float4*>(At + off) = hi;
         if (X3)
           *reinterpret_cast<float4*>(At + C::kOffAlo + off) =
-              make_float4(to_tf32(v[cc * 4 + 0] - hi.x), to_tf32(v[cc * 4 + 1] - hi.y), to_tf32(v[cc * 4 + 2] - hi.z),
-                          to_tf32(v[cc * 4 + 3] - hi.w));
+              make_float4(to_tf32(v[c * 4 + 0] - hi.x), to_tf32(v[c * 4 + 1] - hi.y), to_tf32(v[c * 4 + 2] - hi.z),
+                          to_tf32(v[c * 4 + 3] - hi.w));
       }
       fence_async_smem();
       __syncwarp();
@@ -244,7 +246,7 @@ icnn_tc2_fwd_kernel(const __grid_constant__ Tc2Maps maps, const float* __restric
       for (int j = 0; j < D; ++j) xa[j] = 0.f;
       for (int p = 0; p < NP; ++p)
         for (int kb = 0; kb < NKB; ++kb) {
-          const uint32_t bits = maskw[(kb >> 1) * k2Rows + row] >> ((kb & 1) * 16 + kh * 8);
+          const uint32_t bits = maskw[(kb >> 1) * k2Rows + row] >> ((kb & 1) * 16);
           produce(kb, [&](int k, int e) {
             const float c1 = s2 * P1s[k];
             const float g1 = ((bits >> e) & 1u) ? c1 : kSlope * c1;
