@@ -64,7 +64,7 @@ struct Tc2Maps { CUtensorMap b1hi, b1lo, b2hi, b2lo; };   // boxes of 16 x 128 (
 
 template <bool X3>
 struct Tc2Cfg {
-  static constexpr int S = X3 ? 4 : 6;
+  static constexpr int S = X3 ? 5 : 10;
   static constexpr int kStageBytes = (X3 ? 4 : 2) * k2TileBytes;          // A(hi[,lo]) + B half (hi[,lo])
   static constexpr int kOffAlo = k2TileBytes, kOffB = (X3 ? 2 : 1) * k2TileBytes, kOffBlo = 3 * k2TileBytes;
 };
