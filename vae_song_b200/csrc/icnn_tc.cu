@@ -65,8 +65,13 @@ __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::
 
 template <bool X3>
 struct TcCfg {
-  static constexpr int S = X3 ? 2 : 4;                          // pipeline stages
-  static constexpr int kStageBytes = (X3 ? 4 : 2) * kTileBytes; // A(hi[,lo]) + B(hi[,lo])
+  // A stage holds KPS K-blocks of 16 (one mbarrier round trip per stage).  At 1xTF32 a 16-wide block is only 512
+  // tensor cycles, about what the single MMA-issuing thread needs per loop iteration (wait, fence, issue, commit),
+  // so two blocks share a stage; at 3xTF32 a block is 1536 cycles and one per stage suffices.
+  static constexpr int KPS = X3 ? 1 : 2;
+  static constexpr int S = 2;                                   // pipeline stages
+  static constexpr int kSubBytes = (X3 ? 4 : 2) * kTileBytes;   // one K-block: A(hi[,lo]) + B(hi[,lo])
+  static constexpr int kStageBytes = KPS * kSubBytes;
   static constexpr int kOffAlo = kTileBytes, kOffB = (X3 ? 2 : 1) * kTileBytes, kOffBlo = 3 * kTileBytes;
 };
 
@@ -110,7 +115,7 @@ __device__ __forceinline__ uint32_t tc_setup(const TcSmem& m, int Hq, const floa
   using C = TcCfg<X3>;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < C::S; ++s) { mbar_init(m.full0 + 8 * s, kNW / 2 + 1); mbar_init(m.empty0 + 8 * s, 1); }
+    for (int s = 0; s < C::S; ++s) { mbar_init(m.full0 + 8 * s, (C::KPS == 2 ? kNW : kNW / 2) + 1); mbar_init(m.empty0 + 8 * s, 1); }
     mbar_init(m.accfull, 1);
     mbar_init(m.accempty, kNW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -140,16 +145,21 @@ __device__ __forceinline__ void tc_tma_role(const TcSmem& m, const CUtensorMap* 
                                             int ngemm, int NP, int NKB) {
   using C = TcCfg<X3>;
   uint32_t it = 0;
+  const int NST = NKB / C::KPS;
   for (int g = 0; g < ngemm; ++g)
     for (int p = 0; p < NP; ++p)
-      for (int kb = 0; kb < NKB; ++kb, ++it) {
+      for (int st = 0; st < NST; ++st, ++it) {
         const uint32_t s = it % C::S, ph = (it / C::S) & 1;
         mbar_wait(m.empty0 + 8 * s, ph ^ 1);
         const uint32_t bar = m.full0 + 8 * s;
-        const uint32_t dst = smem_u32(m.stages + s * C::kStageBytes);
-        mbar_arrive_expect_tx(bar, (X3 ? 2 : 1) * kTileBytes);
-        tma_load_2d(dst + C::kOffB, hi[g], bar, kb * kKB, p * kTN);
-        if (X3) tma_load_2d(dst + C::kOffBlo, lo[g], bar, kb * kKB, p * kTN);
+        mbar_arrive_expect_tx(bar, C::KPS * (X3 ? 2 : 1) * kTileBytes);
+#pragma unroll
+        for (int j = 0; j < C::KPS; ++j) {
+          const uint32_t dst = smem_u32(m.stages + s * C::kStageBytes + j * C::kSubBytes);
+          const int kb = st * C::KPS + j;
+          tma_load_2d(dst + C::kOffB, hi[g], bar, kb * kKB, p * kTN);
+          if (X3) tma_load_2d(dst + C::kOffBlo, lo[g], bar, kb * kKB, p * kTN);
+        }
       }
 }
 // MMA issuer: npass accumulator passes of NKB K-blocks; D[256 x 256] = two M=128 blocks sharing B
@@ -157,30 +167,34 @@ template <bool X3>
 __device__ __forceinline__ void tc_mma_role(const TcSmem& m, uint32_t tmem_base, int npass, int NKB) {
   using C = TcCfg<X3>;
   uint32_t it = 0;
+  const int NST = NKB / C::KPS;
   for (int pp = 0; pp < npass; ++pp) {
     mbar_wait(m.accempty, (pp & 1) ^ 1);
     tc_fence_after();
-    for (int kb = 0; kb < NKB; ++kb, ++it) {
+    for (int st = 0; st < NST; ++st, ++it) {
       const uint32_t s = it % C::S, ph = (it / C::S) & 1;
       mbar_wait(m.full0 + 8 * s, ph);
       tc_fence_after();
-      const uint32_t sa = smem_u32(m.stages + s * C::kStageBytes);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint32_t d_t = tmem_base + (uint32_t)(half * kTN);
+      for (int j = 0; j < C::KPS; ++j) {
+        const uint32_t sa = smem_u32(m.stages + s * C::kStageBytes + j * C::kSubBytes);
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {                         // two K=8 steps per 64-byte row
-          const uint64_t a_hi = make_desc_sw64(sa + half * (kTileBytes / 2) + ks * 32);
-          const uint64_t b_hi = make_desc_sw64(sa + C::kOffB + ks * 32);
-          const uint32_t acc = (kb | ks) ? 1u : 0u;
-          if (X3) {
-            const uint64_t a_lo = make_desc_sw64(sa + C::kOffAlo + half * (kTileBytes / 2) + ks * 32);
-            const uint64_t b_lo = make_desc_sw64(sa + C::kOffBlo + ks * 32);
-            umma_tf32(d_t, a_lo, b_hi, kIdescTf32, acc);
-            umma_tf32(d_t, a_hi, b_lo, kIdescTf32, 1u);
-            umma_tf32(d_t, a_hi, b_hi, kIdescTf32, 1u);
-          } else {
-            umma_tf32(d_t, a_hi, b_hi, kIdescTf32, acc);
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t d_t = tmem_base + (uint32_t)(half * kTN);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {                         // two K=8 steps per 64-byte row
+            const uint64_t a_hi = make_desc_sw64(sa + half * (kTileBytes / 2) + ks * 32);
+            const uint64_t b_hi = make_desc_sw64(sa + C::kOffB + ks * 32);
+            const uint32_t acc = (st | j | ks) ? 1u : 0u;
+            if (X3) {
+              const uint64_t a_lo = make_desc_sw64(sa + C::kOffAlo + half * (kTileBytes / 2) + ks * 32);
+              const uint64_t b_lo = make_desc_sw64(sa + C::kOffBlo + ks * 32);
+              umma_tf32(d_t, a_lo, b_hi, kIdescTf32, acc);
+              umma_tf32(d_t, a_hi, b_lo, kIdescTf32, 1u);
+              umma_tf32(d_t, a_hi, b_hi, kIdescTf32, 1u);
+            } else {
+              umma_tf32(d_t, a_hi, b_hi, kIdescTf32, acc);
+            }
           }
         }
       }
@@ -212,13 +226,13 @@ __device__ __forceinline__ Worker make_worker(uint32_t tmem_base) {
 template <bool X3, class Gen>
 __device__ __forceinline__ void worker_produce(const TcSmem& m, Worker& w, int kb, Gen&& gen) {
   using C = TcCfg<X3>;
-  if ((kb & 1) != w.kh) { ++w.it; return; }
-  const uint32_t s = w.it % C::S, ph = (w.it / C::S) & 1;
+  if ((kb & 1) != w.kh) { ++w.it; return; }                    // w.it counts K-blocks (same sequence in every role)
+  const uint32_t stg = w.it / C::KPS, s = stg % C::S, ph = (stg / C::S) & 1, sub = w.it % C::KPS;
   float v[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = gen(kb * kKB + e, e);
   mbar_wait(m.empty0 + 8 * s, ph ^ 1);
-  unsigned char* At = m.stages + s * C::kStageBytes;
+  unsigned char* At = m.stages + s * C::kStageBytes + sub * C::kSubBytes;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const uint32_t off = w.a_row_off + ((uint32_t)(c ^ w.rsw) << 4);
