@@ -24,47 +24,6 @@
 
 namespace b200vae {
 
-// Per-unit parameters (A0q, A1q as float4 (w0,w1,w2,bias); P1q) live in CONSTANT memory while a tensor-core kernel
-// runs: every access is warp-uniform (same hidden unit for all 32 rows of a warp), so it is served by the constant
-// cache instead of shared-memory wavefronts -- the smem pipe is the scarce resource here (each UMMA reads 12 KB of
-// operands from it).  The bank is refreshed (device-to-device, stream ordered) before every launch; an event
-// serialises launches that arrive on different streams.
-constexpr int kMaxHq = 1024;
-__constant__ float c_par[9 * kMaxHq];
-#define TC_A0(k) (reinterpret_cast<const float4*>(c_par)[(k)])
-#define TC_A1(k) (reinterpret_cast<const float4*>(c_par)[Hq + (k)])
-#define TC_P1(k) (c_par[8 * Hq + (k)])
-
-struct ConstBank {
-  std::mutex mu;
-  cudaEvent_t last = nullptr;     // recorded after the most recent kernel that reads c_par
-};
-static ConstBank& bank() { static ConstBank b; return b; }
-static bool capturing(cudaStream_t st) {
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(st, &cap);
-  return cap != cudaStreamCaptureStatusNone;
-}
-// copy [A0q | A1q | P1q] (contiguous in the prepared workspace) into the constant bank, ordered on `st`
-static int stage_constants(const float* par_dev, int Hq, cudaStream_t st) {
-  if (Hq > kMaxHq) return B200VAE_EUNSUP;
-  ConstBank& b = bank();
-  std::lock_guard<std::mutex> lk(b.mu);
-  if (!capturing(st) && b.last) cudaStreamWaitEvent(st, b.last, 0);
-  if (cudaMemcpyToSymbolAsync(c_par, par_dev, sizeof(float) * 9 * (size_t)Hq, 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
-    g_last_cuda_error = (int)cudaGetLastError();
-    return B200VAE_ECUDA;
-  }
-  return B200VAE_OK;
-}
-static void constants_in_use(cudaStream_t st) {
-  if (capturing(st)) return;      // inside a captured stream ordering is implicit
-  ConstBank& b = bank();
-  std::lock_guard<std::mutex> lk(b.mu);
-  if (!b.last) cudaEventCreateWithFlags(&b.last, cudaEventDisableTiming);
-  cudaEventRecord(b.last, st);
-}
-
 size_t tc_extra_ws_floats(int d, int H, int precision) {
   (void)precision;
   return tc_layout(d, H).end;
@@ -106,10 +65,11 @@ __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::
 
 template <bool X3>
 struct TcCfg {
-  // A stage holds KPS K-blocks of 16 (one mbarrier round trip per stage).  KPS = 2 was measured: no gain (the
-  // MMA-issuing thread is not the limiter), so one block per stage and a deeper ring.
-  static constexpr int KPS = 1;
-  static constexpr int S = X3 ? 2 : 5;                          // pipeline stages
+  // A stage holds KPS K-blocks of 16 (one mbarrier round trip per stage).  At 1xTF32 a 16-wide block is only 512
+  // tensor cycles, about what the single MMA-issuing thread needs per loop iteration (wait, fence, issue, commit),
+  // so two blocks share a stage; at 3xTF32 a block is 1536 cycles and one per stage suffices.
+  static constexpr int KPS = X3 ? 1 : 2;
+  static constexpr int S = 2;                                   // pipeline stages
   static constexpr int kSubBytes = (X3 ? 4 : 2) * kTileBytes;   // one K-block: A(hi[,lo]) + B(hi[,lo])
   static constexpr int kStageBytes = KPS * kSubBytes;
   static constexpr int kOffAlo = kTileBytes, kOffB = (X3 ? 2 : 1) * kTileBytes, kOffBlo = 3 * kTileBytes;
@@ -118,6 +78,8 @@ struct TcCfg {
 // shared-memory carve-up common to the forward and backward kernels
 struct TcSmem {
   unsigned char* stages;
+  float4 *A0s, *A1s;
+  float* P1s;
   uint32_t* maskw;     // [Hq/32][256]  word-major so that a thread's own row is bank-conflict free
   float* xch;          // [2][256][4] exchange between the two threads of a row
   uint32_t full0, empty0, accfull, accempty;
@@ -129,7 +91,10 @@ __device__ __forceinline__ TcSmem carve(unsigned char* smem_raw, int Hq) {
   TcSmem m;
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle needs 1 KB alignment
   m.stages = smem;
-  m.maskw = reinterpret_cast<uint32_t*>(smem + C::S * C::kStageBytes);
+  m.A0s = reinterpret_cast<float4*>(smem + C::S * C::kStageBytes);
+  m.A1s = m.A0s + Hq;
+  m.P1s = reinterpret_cast<float*>(m.A1s + Hq);
+  m.maskw = reinterpret_cast<uint32_t*>(m.P1s + Hq);
   m.xch = reinterpret_cast<float*>(m.maskw + (Hq / 32) * 256);
   uint64_t* bars = reinterpret_cast<uint64_t*>(m.xch + 2 * 256 * 4);
   m.full0 = smem_u32(bars); m.empty0 = smem_u32(bars + C::S);
@@ -140,12 +105,13 @@ __device__ __forceinline__ TcSmem carve(unsigned char* smem_raw, int Hq) {
 template <bool X3>
 static size_t tc_smem_bytes(int Hq) {
   using C = TcCfg<X3>;
-  return (size_t)C::S * C::kStageBytes + (size_t)(Hq / 32) * 256 * 4 + 2 * 256 * 4 * 4 +
+  return (size_t)C::S * C::kStageBytes + (size_t)Hq * (16 + 16 + 4) + (size_t)(Hq / 32) * 256 * 4 + 2 * 256 * 4 * 4 +
          (2 * C::S + 2) * 8 + 16 + 1024;
 }
 
 template <bool X3>
-__device__ __forceinline__ uint32_t tc_setup(const TcSmem& m) {
+__device__ __forceinline__ uint32_t tc_setup(const TcSmem& m, int Hq, const float4* A0q_g, const float4* A1q_g,
+                                              const float* P1q_g) {
   using C = TcCfg<X3>;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
@@ -158,6 +124,7 @@ __device__ __forceinline__ uint32_t tc_setup(const TcSmem& m) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(m.tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  for (int i = tid; i < Hq; i += kTcThreads) { m.A0s[i] = A0q_g[i]; m.A1s[i] = A1q_g[i]; m.P1s[i] = P1q_g[i]; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -329,7 +296,7 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
                    float* __restrict__ xhat, uint32_t* __restrict__ mask1, uint8_t* __restrict__ mask2) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const TcSmem m = carve<X3>(smem_raw, Hq);
-  const uint32_t tmem_base = tc_setup<X3>(m);
+  const uint32_t tmem_base = tc_setup<X3>(m, Hq, A0q_g, A1q_g, P1q_g);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kTM;
   const int NP = Hq / kTN, NKB = Hq / kKB;
@@ -347,7 +314,7 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
     for (int p = 0; p < NP; ++p) {
       for (int kb = 0; kb < NKB; ++kb)
         worker_produce<X3>(m, w, kb, [&](int k, int) {
-          const float h = lin_of<D>(TC_A0(k), zr);
+          const float h = lin_of<D>(m.A0s[k], zr);
           const float a0 = fmaxf(h, kSlope * h);            // LeakyReLU(0.2) = max(h, 0.2h)
           return a0 * a0;
         });
@@ -356,9 +323,9 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
         uint32_t word = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float h1 = __uint_as_float(r[j]) + lin_of<D>(TC_A1(nb + j), zr);
+          const float h1 = __uint_as_float(r[j]) + lin_of<D>(m.A1s[nb + j], zr);
           const bool pos = h1 > 0.f;
-          h2 = fmaf(TC_P1(nb + j), pos ? h1 : kSlope * h1, h2);
+          h2 = fmaf(m.P1s[nb + j], pos ? h1 : kSlope * h1, h2);
           word |= (pos ? 1u : 0u) << j;
         }
         m.maskw[(nb >> 5) * 256 + w.row] = word;
@@ -392,10 +359,10 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
         for (int kb = 0; kb < NKB; ++kb) {
           const uint32_t bits = m.maskw[(kb >> 1) * 256 + w.row] >> ((kb & 1) * 16);
           worker_produce<X3>(m, w, kb, [&](int k, int e) {
-            const float c1 = s2 * TC_P1(k);
+            const float c1 = s2 * m.P1s[k];
             const float g1 = ((bits >> e) & 1u) ? c1 : kSlope * c1;
             if (p == 0) {                                    // xhat += A1^T g1, once
-              const float4 q = TC_A1(k);
+              const float4 q = m.A1s[k];
 #pragma unroll
               for (int j = 0; j < D; ++j) xacc[j] = fmaf(comp(q, j), g1, xacc[j]);
             }
@@ -406,7 +373,7 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
           const int nb = p * kTN + c0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float4 q = TC_A0(nb + j);
+            const float4 q = m.A0s[nb + j];
             const float h = lin_of<D>(q, zr);
             const float s0 = slope_of(h), a0 = h * s0;
             const float g0 = __uint_as_float(r[j]) * (2.f * a0) * s0;
@@ -452,7 +419,7 @@ icnn_tc_bwd_rows_kernel(const __grid_constant__ TcMaps maps, const float* __rest
                         float* __restrict__ partB, float* __restrict__ a2part) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const TcSmem m = carve<X3>(smem_raw, Hq);
-  const uint32_t tmem_base = tc_setup<X3>(m);
+  const uint32_t tmem_base = tc_setup<X3>(m, Hq, A0q_g, A1q_g, P1q_g);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kTM;
   const int NP = Hq / kTN, NKB = Hq / kKB;
@@ -482,7 +449,7 @@ icnn_tc_bwd_rows_kernel(const __grid_constant__ TcMaps maps, const float* __rest
       for (int kb = 0; kb < NKB; ++kb) {
         const uint32_t bits = m.maskw[(kb >> 1) * 256 + w.row] >> ((kb & 1) * 16);
         worker_produce<X3>(m, w, kb, [&](int k, int e) {
-          const float c1 = s2 * TC_P1(k);
+          const float c1 = s2 * m.P1s[k];
           return ((bits >> e) & 1u) ? c1 : kSlope * c1;
         });
       }
@@ -495,7 +462,7 @@ icnn_tc_bwd_rows_kernel(const __grid_constant__ TcMaps maps, const float* __rest
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             const int j = i + 16 * hh;
-            const float4 q = TC_A0(nb + j);
+            const float4 q = m.A0s[nb + j];
             const float h = lin_of<D>(q, zr), u0 = dot_of<D>(q, vr);
             const float s0 = slope_of(h), a0 = h * s0, gx1 = __uint_as_float(r[j]);
             const float g0 = gx1 * (2.f * a0) * s0;
@@ -518,7 +485,7 @@ icnn_tc_bwd_rows_kernel(const __grid_constant__ TcMaps maps, const float* __rest
     for (int p = 0; p < NP; ++p) {
       for (int kb = 0; kb < NKB; ++kb)
         worker_produce<X3>(m, w, kb, [&](int k, int) {
-          const float4 q = TC_A0(k);
+          const float4 q = m.A0s[k];
           const float h = lin_of<D>(q, zr), u0 = dot_of<D>(q, vr);
           const float s0 = slope_of(h), a0 = h * s0;
           return u0 * (2.f * a0) * s0;
@@ -533,10 +500,10 @@ icnn_tc_bwd_rows_kernel(const __grid_constant__ TcMaps maps, const float* __rest
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             const int j = i + 16 * hh;
-            const float4 q = TC_A1(nb + j);
+            const float4 q = m.A1s[nb + j];
             const float s1 = ((word >> j) & 1u) ? 1.f : kSlope;
             const float w1 = __uint_as_float(r[j]) + dot_of<D>(q, vr);
-            const float g1 = (s2 * TC_P1(nb + j)) * s1;
+            const float g1 = (s2 * m.P1s[nb + j]) * s1;
 #pragma unroll
             for (int jj = 0; jj < D; ++jj) e[hh][jj] = g1 * vr[jj];
             e[hh][D] = (s2 * s1) * w1;
@@ -871,14 +838,10 @@ static int launch_tc(const TcMaps& maps, const float* z, int B, const TcLayout& 
     attr_done = true;
   }
   const int grid = (B + kTM - 1) / kTM;
-  int rc = stage_constants(tb + T.A0q, T.Hq, st);
-  if (rc) return rc;
   icnn_tc_fwd_kernel<D, X3><<<grid, kTcThreads, smem, st>>>(
       maps, z, B, T.Hq, Hw_out, kappa, reinterpret_cast<const float4*>(tb + T.A0q),
       reinterpret_cast<const float4*>(tb + T.A1q), tb + T.P1q, A2p, psi, xhat, mask1, mask2);
-  rc = check_launch();
-  constants_in_use(st);
-  return rc;
+  return check_launch();
 }
 
 static int get_maps(const float* tb, const TcLayout& T, TcMaps* out) {
@@ -952,14 +915,10 @@ static int launch_tc_bwd(const TcMaps& maps, const float* z, const float* v, con
     attr_done = true;
   }
   const int grid = (B + kTM - 1) / kTM;
-  int rc = stage_constants(tb + T.A0q, T.Hq, st);
-  if (rc) return rc;
   icnn_tc_bwd_rows_kernel<D, X3><<<grid, kTcThreads, smem, st>>>(
       maps, z, v, mask1, mask2, B, T.Hq, Hw_in, kappa, reinterpret_cast<const float4*>(tb + T.A0q),
       reinterpret_cast<const float4*>(tb + T.A1q), tb + T.P1q, dz, partA, partB, a2part);
-  rc = check_launch();
-  constants_in_use(st);
-  return rc;
+  return check_launch();
 }
 
 int finalize_W0_launch(const float* part, int splits, int H, int Hp, int ldp, const float* P0, const float* P1,
