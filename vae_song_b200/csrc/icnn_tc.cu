@@ -81,7 +81,7 @@ struct TcSmem {
   float4 *A0s, *A1s;
   float* P1s;
   uint32_t* maskw;     // [Hq/32][256]  word-major so that a thread's own row is bank-conflict free
-  float* xch;          // [2][256][4] exchange between the two threads of a row
+  float* xch;          // [4][256][4] exchange between the threads that own parts of a row
   uint32_t full0, empty0, accfull, accempty;
   uint32_t* tmem_slot;
 };
@@ -96,7 +96,7 @@ __device__ __forceinline__ TcSmem carve(unsigned char* smem_raw, int Hq) {
   m.P1s = reinterpret_cast<float*>(m.A1s + Hq);
   m.maskw = reinterpret_cast<uint32_t*>(m.P1s + Hq);
   m.xch = reinterpret_cast<float*>(m.maskw + (Hq / 32) * 256);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(m.xch + 2 * 256 * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(m.xch + 4 * 256 * 4);
   m.full0 = smem_u32(bars); m.empty0 = smem_u32(bars + C::S);
   m.accfull = smem_u32(bars + 2 * C::S); m.accempty = smem_u32(bars + 2 * C::S + 1);
   m.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::S + 2);
@@ -105,7 +105,7 @@ __device__ __forceinline__ TcSmem carve(unsigned char* smem_raw, int Hq) {
 template <bool X3>
 static size_t tc_smem_bytes(int Hq) {
   using C = TcCfg<X3>;
-  return (size_t)C::S * C::kStageBytes + (size_t)Hq * (16 + 16 + 4) + (size_t)(Hq / 32) * 256 * 4 + 2 * 256 * 4 * 4 +
+  return (size_t)C::S * C::kStageBytes + (size_t)Hq * (16 + 16 + 4) + (size_t)(Hq / 32) * 256 * 4 + 4 * 256 * 4 * 4 +
          (2 * C::S + 2) * 8 + 16 + 1024;
 }
 
@@ -248,6 +248,52 @@ __device__ __forceinline__ void worker_produce(const TcSmem& m, Worker& w, int k
   if (w.lane == 0) mbar_arrive(m.full0 + 8 * s);
   ++w.it;
 }
+// ---- 4-rows-per-thread generator (forward kernel) ----------------------------------------------------------
+// Shared memory bandwidth is the scarce resource (every UMMA reads 12 KB of operands from it; ncu: LSU wavefronts
+// 54 % + tensor reads 45 % of the pipe).  With one row per thread every A element costs one broadcast LDS.128 of
+// the unit's parameters; here a thread owns ONE 16-byte chunk (4 consecutive k) of FOUR rows (rb, rb+64, rb+128,
+// rb+192), so a parameter load is reused by 4 rows: 4x fewer parameter wavefronts, same STS traffic.
+struct Gen4 {
+  int c, rb;            // chunk (0..3) and base row (0..63)
+  uint32_t off;         // byte offset of my chunk in row rb of an A tile (rows rb+64j: + j*4096)
+};
+__device__ __forceinline__ Gen4 make_gen4() {
+  Gen4 g;
+  const int t = threadIdx.x & 255;
+  g.c = t & 3; g.rb = t >> 2;
+  g.off = (uint32_t)g.rb * 64u + ((uint32_t)(g.c ^ ((g.rb >> 1) & 3)) << 4);
+  return g;
+}
+// gen(k, e, out[4]) fills the value of column k for my 4 rows
+template <bool X3, class Gen>
+__device__ __forceinline__ void worker_produce4(const TcSmem& m, Worker& w, const Gen4& g, int kb, Gen&& gen) {
+  using C = TcCfg<X3>;
+  if ((kb & 1) != w.kh) { ++w.it; return; }
+  const uint32_t stg = w.it / C::KPS, s = stg % C::S, ph = (stg / C::S) & 1, sub = w.it % C::KPS;
+  float v[4][4];        // [row j][e]
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float o[4];
+    gen(kb * kKB + g.c * 4 + e, e, o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j][e] = o[j];
+  }
+  mbar_wait(m.empty0 + 8 * s, ph ^ 1);
+  unsigned char* At = m.stages + s * C::kStageBytes + sub * C::kSubBytes + g.off;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 hi = make_float4(to_tf32(v[j][0]), to_tf32(v[j][1]), to_tf32(v[j][2]), to_tf32(v[j][3]));
+    *reinterpret_cast<float4*>(At + j * 4096) = hi;
+    if (X3)
+      *reinterpret_cast<float4*>(At + C::kOffAlo + j * 4096) =
+          make_float4(to_tf32(v[j][0] - hi.x), to_tf32(v[j][1] - hi.y), to_tf32(v[j][2] - hi.z), to_tf32(v[j][3] - hi.w));
+  }
+  fence_async_smem();
+  __syncwarp();
+  if (w.lane == 0) mbar_arrive(m.full0 + 8 * s);
+  ++w.it;
+}
+
 // drain my row's 128 accumulator columns of the finished pass: chunk(r[32], first_column_in_pass)
 template <class Chunk>
 __device__ __forceinline__ void worker_drain(const TcSmem& m, Worker& w, Chunk&& chunk) {
@@ -304,19 +350,30 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
 
   if (warp < kNW) {
     Worker w = make_worker(tmem_base);
+    const Gen4 g = make_gen4();
     const bool valid = (m0 + w.row) < B;
-    float zr[D];
+    float zr[D];                       // my drain row
+    float z4[4][D];                    // my 4 generator rows
 #pragma unroll
     for (int j = 0; j < D; ++j) zr[j] = valid ? z[(size_t)(m0 + w.row) * D + j] : 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < D; ++j)
+        z4[r][j] = (m0 + g.rb + 64 * r < B) ? z[(size_t)(m0 + g.rb + 64 * r) * D + j] : 0.f;
 
     // -------- GEMM1: h1 = x1 . P^T  -> masks, h2 --------
     float h2 = 0.f;
     for (int p = 0; p < NP; ++p) {
       for (int kb = 0; kb < NKB; ++kb)
-        worker_produce<X3>(m, w, kb, [&](int k, int) {
-          const float h = lin_of<D>(m.A0s[k], zr);
-          const float a0 = fmaxf(h, kSlope * h);            // LeakyReLU(0.2) = max(h, 0.2h)
-          return a0 * a0;
+        worker_produce4<X3>(m, w, g, kb, [&](int k, int, float (&o)[4]) {
+          const float4 q = m.A0s[k];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float h = lin_of<D>(q, z4[r]);
+            const float a0 = fmaxf(h, kSlope * h);          // LeakyReLU(0.2) = max(h, 0.2h)
+            o[r] = a0 * a0;
+          }
         });
       worker_drain(m, w, [&](uint32_t (&r)[32], int c0) {
         const int nb = p * kTN + c0;
@@ -333,15 +390,19 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
     }
     m.xch[w.kh * 256 + w.row] = h2;
     worker_bar();                                            // h2 halves + all mask words visible
-    h2 = m.xch[w.row] + m.xch[256 + w.row];
-    {
+    auto s2_of = [&](int row, const float (&zz)[D]) {
+      float hh = m.xch[row] + m.xch[256 + row];
       float lin = A2p[D];
 #pragma unroll
-      for (int j = 0; j < D; ++j) lin = fmaf(A2p[j], zr[j], lin);
-      h2 += lin;
-    }
+      for (int j = 0; j < D; ++j) lin = fmaf(A2p[j], zz[j], lin);
+      return hh + lin;
+    };
+    h2 = s2_of(w.row, zr);
     const bool pos2 = h2 > 0.f;
     const float s2 = pos2 ? 1.f : kSlope;
+    float s24[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s24[r] = s2_of(g.rb + 64 * r, z4[r]) > 0.f ? 1.f : kSlope;
     if (valid) {
       if (w.kh == 0) {
         if (psi) psi[m0 + w.row] = pos2 ? h2 : kSlope * h2;
@@ -352,21 +413,34 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
     }
     if (xhat != nullptr) {
       // -------- GEMM2: gx1 = g1 . P -> g0 -> xhat --------
-      float xacc[D];
+      float xacc[D], xa4[4][D];
 #pragma unroll
-      for (int j = 0; j < D; ++j) xacc[j] = 0.f;
+      for (int j = 0; j < D; ++j) {
+        xacc[j] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) xa4[r][j] = 0.f;
+      }
       for (int p = 0; p < NP; ++p) {
         for (int kb = 0; kb < NKB; ++kb) {
-          const uint32_t bits = m.maskw[(kb >> 1) * 256 + w.row] >> ((kb & 1) * 16);
-          worker_produce<X3>(m, w, kb, [&](int k, int e) {
-            const float c1 = s2 * m.P1s[k];
-            const float g1 = ((bits >> e) & 1u) ? c1 : kSlope * c1;
-            if (p == 0) {                                    // xhat += A1^T g1, once
-              const float4 q = m.A1s[k];
+          uint32_t bits4[4];
+          if ((kb & 1) == w.kh) {
 #pragma unroll
-              for (int j = 0; j < D; ++j) xacc[j] = fmaf(comp(q, j), g1, xacc[j]);
+            for (int r = 0; r < 4; ++r)
+              bits4[r] = m.maskw[(kb >> 1) * 256 + g.rb + 64 * r] >> ((kb & 1) * 16 + g.c * 4);
+          }
+          worker_produce4<X3>(m, w, g, kb, [&](int k, int e, float (&o)[4]) {
+            const float p1 = m.P1s[k];
+            const float4 q = m.A1s[k];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const float c1 = s24[r] * p1;
+              const float g1 = ((bits4[r] >> e) & 1u) ? c1 : kSlope * c1;
+              o[r] = g1;
+              if (p == 0) {                                  // xhat += A1^T g1, once
+#pragma unroll
+                for (int j = 0; j < D; ++j) xa4[r][j] = fmaf(comp(q, j), g1, xa4[r][j]);
+              }
             }
-            return g1;
           });
         }
         worker_drain(m, w, [&](uint32_t (&r)[32], int c0) {
@@ -382,15 +456,33 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
           }
         });
       }
-      worker_bar();                                          // xch reuse
+      // combine: 2 drain threads per row (xacc) + 2 groups x 4 chunk lanes per row (xa4)
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          float t = xa4[r][j];
+          t += __shfl_xor_sync(0xffffffffu, t, 1);
+          t += __shfl_xor_sync(0xffffffffu, t, 2);
+          xa4[r][j] = t;
+        }
+      worker_bar();                                          // xch reuse (everybody has read the h2 halves)
 #pragma unroll
       for (int j = 0; j < D; ++j) m.xch[(w.kh * 256 + w.row) * 4 + j] = xacc[j];
+      if (g.c == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int j = 0; j < D; ++j) m.xch[((2 + w.kh) * 256 + g.rb + 64 * r) * 4 + j] = xa4[r][j];
+      }
       worker_bar();
       if (valid && w.kh == 0) {
 #pragma unroll
-        for (int j = 0; j < D; ++j)
-          xhat[(size_t)(m0 + w.row) * D + j] =
-              fmaf(2.f * kappa, zr[j], fmaf(s2, A2p[j], m.xch[w.row * 4 + j] + m.xch[(256 + w.row) * 4 + j]));
+        for (int j = 0; j < D; ++j) {
+          const float sum = (m.xch[w.row * 4 + j] + m.xch[(256 + w.row) * 4 + j]) +
+                            (m.xch[(512 + w.row) * 4 + j] + m.xch[(768 + w.row) * 4 + j]);
+          xhat[(size_t)(m0 + w.row) * D + j] = fmaf(2.f * kappa, zr[j], fmaf(s2, A2p[j], sum));
+        }
       }
     }
   } else if (warp == kNW) {
