@@ -241,6 +241,25 @@ def run_ours(args, rank, local_rank, world):
     value = world * B / (ms * 1e-3)
     e2e = world * B / (ms_e2e * 1e-3)
 
+    # ---- the same train step in the other arithmetic modes (1 GPU only; same weights, graph replay) ----
+    by_prec_train = {args.precision: {"ms_per_step": ms, "samples_per_s": value}}
+    if world == 1:
+        import copy
+        for pname in ("fp32", "tf32x3", "tf32"):
+            if pname == args.precision:
+                continue
+            m2 = copy.deepcopy(m)
+            m2.precision = pname
+            tr2 = train.DataParallelTrainer(m2, lr=1e-3)
+            tr2.step(dev_pool[0])
+            if use_graph:
+                tr2.capture(dev_pool[0])
+            stepf = tr2.step_graphed if use_graph else tr2.step
+            ms2 = timed(lambda i: stepf(dev_pool[i % n_pool]), max(3, min(args.steps, 10)), 3)
+            by_prec_train[pname] = {"ms_per_step": ms2, "samples_per_s": B / (ms2 * 1e-3)}
+            tr2._graph = None
+            del tr2, m2
+
     # ---- fused ICNN decode + grad-psi kernel vs roofline at batch 65536 (north_star), every precision ----
     roof, extra = None, {}
     if rank == 0:
@@ -280,7 +299,7 @@ def run_ours(args, rank, local_rank, world):
                 "algorithmic_flop_per_sample": io.flops_decode(2, 1024),
                 "note": "achieved = algorithmic flops / CUDA-event time; tf32x3 executes 3 MMAs per algorithmic MAC, "
                         "fp32 is the SIMT parity path (FP32 FMA peak 74.4 TFLOP/s at 1965 MHz)"}
-        extra = {"decode_by_precision": byp}
+        extra = {"decode_by_precision": byp, "train_step_by_precision": by_prec_train}
         sample = 8192
         cpu_val, cpu_s = time_oracle(sample, 3)
         cpu = {"value": cpu_val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
