@@ -291,9 +291,13 @@ def run_ours(args, rank, local_rank, world):
                           "tflops_2icnn": both * (io.flops_decode(2, 512) + io.flops_decode(2, 1024)) / 1e12}
         rp = args.roofline_precision
         ach = byp[rp]["tflops_H1024"]
+        try:      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"icnn_decode_fwd_{rp}_H1024_B65536")
+        except Exception:
+            traffic = None
         tensor_peak = pk["bf16_tflops"] / 2 if rp.startswith("tf32") else pk["bf16_tflops"]
         roof = {"bound": "tensor", "kernel": f"icnn_decode_fwd (psi + grad psi), d=2, H=1024, B=65536, {rp}", "achieved": ach,
-                "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak, "traffic": None,
+                "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak, "traffic": traffic,
                 "peak_kind": f"{pk_kind} cuBLAS bf16 burst" + (" / 2 (TF32 runs at half the bf16 rate)" if rp.startswith("tf32") else ""),
                 "precision": rp, "kernel_ms": byp[rp]["decode_ms_H1024"],
                 "algorithmic_flop_per_sample": io.flops_decode(2, 1024),
