@@ -148,3 +148,15 @@ def test_fused_adam_matches_torch():
         opt.step()
         ops.adam_step_(p, g * 4.0, m, v, t, lr=1e-3, weight_decay=0.01, grad_scale=0.25)
     close_report(p.cpu().numpy(), q.detach().cpu().numpy(), 1e-6, "adam")
+
+
+def test_batched_cell_estimator_equals_per_cell_calls():
+    """lipschitz.py:48-154 evaluates up to 512 cells one by one; the batched helper must reproduce every cell."""
+    from vae_song_b200 import model, utils
+    torch.manual_seed(1)
+    m = model.LIDVAE(dataset="pinwheel", icnn_channels=[64, 128], hidden_channels=[8]).cuda().eval()
+    cells = [torch.randn(n, 2, device="cuda") * 0.3 + i for i, n in enumerate([40, 2, 1, 0, 333, 100])]
+    got = utils.estimate_local_lipschitz_batched(m.decode, cells, num_pairs=500)
+    for i, X in enumerate(cells):
+        ref = utils.estimate_local_lipschitz(m.decode, X, num_pairs=500) if X.size(0) >= 2 else (0.0, 0.0, 0.0)
+        np.testing.assert_allclose(got[i], ref, rtol=1e-5)

@@ -70,6 +70,45 @@ def estimate_local_lipschitz(func, X, num_pairs=2000, metric=2, quantile=0.05, e
     return res[0], res[1], res[2]
 
 
+def estimate_local_lipschitz_batched(func, X_list, num_pairs=2000, quantile=0.05, eps=1e-3, use_grad=False):
+    """`estimate_local_lipschitz` for MANY sample sets at once (the per-cell loops of lipschitz.py:48-154 call the
+    estimator up to 512 times, each with 2 small decodes, 2 sorts and 3 `.item()` syncs).  Here all cells share
+    TWO decodes, ONE ratio-kernel launch, ONE batched quantile and ONE device->host copy.  Pair indices are drawn
+    exactly like the reference (a fresh seed-0 generator on X.device per cell), so every cell's result equals the
+    one-cell call.  Returns a float64 numpy array [n_cells, 3] = (inverse_lipschitz, lipschitz, bi_lipschitz);
+    cells with fewer than 2 samples get (0, 0, 0) like the reference."""
+    import numpy as np
+    out = np.zeros((len(X_list), 3), dtype=np.float64)
+    live = [i for i, X in enumerate(X_list) if X.size(0) >= 2]
+    if not live:
+        return out
+    dev = X_list[live[0]].device
+    i1s, i2s, offs, off = [], [], [], 0
+    for i in live:
+        N = X_list[i].size(0)
+        gen = torch.Generator(device=dev).manual_seed(0)
+        i1s.append(torch.randint(0, N, (num_pairs,), device=dev, generator=gen) + off)
+        i2s.append(torch.randint(0, N, (num_pairs,), device=dev, generator=gen) + off)
+        offs.append(off)
+        off += N
+    Xall = torch.cat([X_list[i].detach().reshape(X_list[i].size(0), -1) for i in live], 0)
+    i1, i2 = torch.cat(i1s), torch.cat(i2s)
+    x1, x2 = Xall[i1], Xall[i2]
+    shape_tail = X_list[live[0]].shape[1:]
+    with torch.no_grad():                       # our decode needs no autograd graph (use_grad kept for API parity)
+        y1 = func(x1.reshape(-1, *shape_tail))
+        y2 = func(x2.reshape(-1, *shape_tail))
+    P = i1.numel()
+    ar = torch.arange(P, device=dev)
+    ratio = ops.lipschitz_pair_ratios(torch.cat([x1, x2], 0), torch.cat([y1.reshape(P, -1), y2.reshape(P, -1)], 0),
+                                      ar, ar + P, eps).view(len(live), num_pairs)
+    q = torch.quantile(ratio, torch.tensor([quantile, 1 - quantile], device=dev), dim=1)     # [2, n_live]
+    invA = 1.0 / q[0].clamp(min=eps)
+    res = torch.stack([invA, q[1], torch.maximum(invA, q[1])], 1).double().cpu().numpy()     # one sync
+    out[live] = res
+    return out
+
+
 def estimate_lipschitz_allpairs(func, X, eps=1e-3, process_group=None, nbins=0, hist_range=(-20.0, 20.0)):
     """All-pairs max / min / mean of |f(x)-f(y)|/|x-y| over every unordered pair (north_star kernel 4).
     With a process group the 64x64 pair tiles are sharded round-robin-by-range across ranks and combined
