@@ -139,6 +139,31 @@ int b200vae_adam_step_dev(float* param, const float* grad, float* m, float* v, l
                           float beta1, float beta2, float eps, float weight_decay, long long* step_dev,
                           float grad_scale, void* stream);
 
+/* ---- fused [Linear -> BatchNorm1d -> LeakyReLU] encoder layers (model.py:711-734) ------------
+ * Widths <= 128 (backward: powers of two).  A layer INPUT is described by the previous layer's pre-BN output
+ * `*_y` [B,w] plus its BatchNorm statistics `*_stats` [4][w] = (mean, biased var, invstd, count), gamma, beta; the
+ * LeakyReLU(BN(.)) is applied while loading.  `*_stats` == NULL means "raw input, no BN/activation".
+ * `scratch`: b200vae_mlp_scratch_bytes(B) bytes of caller-owned device memory. */
+size_t b200vae_mlp_scratch_bytes(int B);
+/* y_out [B,wo] = act(in) W^T + bias, W [wo,wi]; if stats_out != NULL also the batch statistics of y_out (and, when
+ * running_mean/var != NULL, their momentum update with the unbiased variance -- torch.nn.BatchNorm1d semantics). */
+int b200vae_mlp_layer_fwd(const float* in_y, const float* in_stats, const float* in_gamma, const float* in_beta,
+                          float slope, const float* W, const float* bias, int B, int wi, int wo, float* y_out,
+                          float* stats_out, float eps, float* running_mean, float* running_var, float momentum,
+                          void* scratch, void* stream);
+/* da [B,w] = dL/d act(y).  Writes dyhat = da*lrelu'(.) [B,w] and sums [2][w] = (sum dyhat, sum dyhat*xhat)
+ * (= dbeta, dgamma).  stats == NULL: no BN (dyhat = da, sums[0] = bias gradient). */
+int b200vae_mlp_layer_bwd_reduce(const float* da, const float* y, const float* stats, const float* gamma,
+                                 const float* beta, float slope, int B, int w, float* dyhat, float* sums,
+                                 void* scratch, void* stream);
+/* With dy = gamma*invstd*(dyhat - sums[0]*inv_n - xhat*sums[1]*inv_n) (or dyhat when stats == NULL):
+ * da_prev [B,wi] = dy W (NULL to skip) and dW [wo,wi] = dy^T act(prev) (NULL to skip). */
+int b200vae_mlp_layer_bwd(const float* dyhat, const float* y, const float* stats, const float* gamma,
+                          const float* beta, const float* sums, float inv_n, float slope, const float* W,
+                          const float* prev_y, const float* prev_stats, const float* prev_gamma,
+                          const float* prev_beta, int B, int wo, int wi, float* da_prev, float* dW,
+                          void* scratch, void* stream);
+
 int b200vae_last_cuda_error(void);
 const char* b200vae_version(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */

@@ -245,3 +245,41 @@ def test_lidvae_mnist_constructs_and_trains_one_step():
     total, lrec, lreg, _ = m.loss(x, recon, mu, lv, z, None)
     total.backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+@pytest.mark.parametrize("hidden", [[2, 2, 2, 2], [128, 64, 64, 32, 16, 8, 4, 2], [16]])
+@pytest.mark.parametrize("training", [True, False])
+def test_fused_encoder_matches_stock_modules(hidden, training):
+    """Fused Linear+BN+LeakyReLU layers (csrc/mlp.cu) vs the very same nn.Modules run by PyTorch: outputs, every
+    gradient, and the BatchNorm running statistics."""
+    from vae_song_b200 import model
+    import copy
+    torch.manual_seed(0)
+    m = model.LIDVAE(dataset="pinwheel", icnn_channels=[32, 32], hidden_channels=hidden).cuda()
+    with torch.no_grad():
+        for mod in m.encoder.modules():
+            if isinstance(mod, torch.nn.BatchNorm1d):
+                mod.weight.uniform_(0.5, 1.5); mod.bias.uniform_(-0.5, 0.5)
+                mod.running_mean.uniform_(-0.2, 0.2); mod.running_var.uniform_(0.5, 1.5)
+    ref = copy.deepcopy(m)
+    ref.fused_encoder = False
+    m.train(training); ref.train(training)
+    assert m._encoder_plan() is not None
+    x = torch.randn(777, 2, device="cuda", requires_grad=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    g = torch.randn(777, 4, device="cuda")
+    mu, lv = m.encode(x)
+    (torch.cat([mu, lv], 1) * g).sum().backward()
+    mu2, lv2 = ref.encode(x2)
+    (torch.cat([mu2, lv2], 1) * g).sum().backward()
+    close_report(mu.detach().cpu().numpy(), mu2.detach().cpu().numpy(), 2e-5, "mu")
+    close_report(lv.detach().cpu().numpy(), lv2.detach().cpu().numpy(), 2e-5, "lv")
+    gscale = max(float(q.grad.abs().max()) for q in ref.encoder.parameters())
+    close_report(x.grad.cpu().numpy(), x2.grad.cpu().numpy(), 2e-4, "dx", floor=1e-4 * gscale)
+    for (k, a), (_, b) in zip(m.encoder.named_parameters(), ref.encoder.named_parameters()):
+        if bn_shadowed("encoder." + k, m):
+            assert float(a.grad.abs().max()) <= 1e-4 * gscale
+        else:
+            close_report(a.grad.cpu().numpy(), b.grad.cpu().numpy(), 2e-4, "grad " + k, floor=1e-5 * gscale)
+    for (k, a), (_, b) in zip(m.encoder.named_buffers(), ref.encoder.named_buffers()):
+        close_report(a.float().cpu().numpy(), b.float().cpu().numpy(), 1e-5, "buffer " + k)

@@ -25,7 +25,8 @@ _ERR = {-1: "bad shape", -2: "unsupported configuration", -3: "null or misaligne
 EXPORTS = [
     "b200vae_icnn_workspace_bytes", "b200vae_icnn_prepare", "b200vae_icnn_decode_fwd", "b200vae_icnn_decode_bwd",
     "b200vae_loss_fwd", "b200vae_loss_bwd", "b200vae_lipschitz_pairs", "b200vae_lipschitz_allpairs",
-    "b200vae_lipschitz_num_tiles", "b200vae_adam_step", "b200vae_adam_step_dev", "b200vae_last_cuda_error", "b200vae_version",
+    "b200vae_lipschitz_num_tiles", "b200vae_adam_step", "b200vae_adam_step_dev", "b200vae_mlp_scratch_bytes", "b200vae_mlp_layer_fwd",
+    "b200vae_mlp_layer_bwd_reduce", "b200vae_mlp_layer_bwd", "b200vae_last_cuda_error", "b200vae_version",
     "b200vae_launch_count",
 ]
 
@@ -91,6 +92,14 @@ def load():
     lib.b200vae_adam_step.argtypes = [vp, vp, vp, vp, ll, f, f, f, f, f, ll, f, vp]
     lib.b200vae_adam_step_dev.restype = i
     lib.b200vae_adam_step_dev.argtypes = [vp, vp, vp, vp, ll, f, f, f, f, f, vp, f, vp]
+    lib.b200vae_mlp_scratch_bytes.restype = sz
+    lib.b200vae_mlp_scratch_bytes.argtypes = [i]
+    lib.b200vae_mlp_layer_fwd.restype = i
+    lib.b200vae_mlp_layer_fwd.argtypes = [vp, vp, vp, vp, f, vp, vp, i, i, i, vp, vp, f, vp, vp, f, vp, vp]
+    lib.b200vae_mlp_layer_bwd_reduce.restype = i
+    lib.b200vae_mlp_layer_bwd_reduce.argtypes = [vp, vp, vp, vp, vp, f, i, i, vp, vp, vp, vp]
+    lib.b200vae_mlp_layer_bwd.restype = i
+    lib.b200vae_mlp_layer_bwd.argtypes = [vp, vp, vp, vp, vp, vp, f, f, vp, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp]
     lib.b200vae_last_cuda_error.restype = i
     lib.b200vae_version.restype = C.c_char_p
     lib.b200vae_launch_count.restype = ll

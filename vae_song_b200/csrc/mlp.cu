@@ -1,0 +1,392 @@
+// mlp.cu -- fused [Linear -> BatchNorm1d -> LeakyReLU] encoder stack.
+//
+// The reference's 1-D encoders (model.py:711-734 LIDVAE.make_encoder_1d, model.py:186-208 FlexibleVAE MLP) are chains
+// of narrow (width <= 128) Linear+BN+LeakyReLU(0.01) blocks: in eager PyTorch each block is ~6 launches forward and ~8
+// backward on [B, w] tensors (cuBLAS picks split-K sgemm kernels for the [B,2]x[2,2] products).  Here one layer is
+//   forward : y = act(prev) W^T + b   with act = LeakyReLU(BN(prev)) applied while loading, per-column (count, mean, M2)
+//             partials per CTA (Chan-combined in fixed order -> deterministic batch statistics);
+//   backward: (1) dyhat = da * lrelu'(.) + per-column sums S1 = sum dyhat, S2 = sum dyhat*xhat,
+//             (2) da_prev = dy W  and  dW = dy^T act(prev)  with dy = gamma*invstd*(dyhat - S1/N - xhat*S2/N) formed on
+//                 the fly, both on the 128x128x16 FP32 tile core (gemm_simt.cuh).
+// Everything but y / dyhat / da stays on chip; cross-rank BatchNorm only needs the tiny (mean,var) / (S1,S2) vectors
+// exchanged between launches (done by the host side, train.py).
+#include "gemm_simt.cuh"
+
+namespace b200vae {
+
+struct ActSrc {          // how a layer input a[b][k] is obtained from the previous layer's pre-BN output
+  const float* y;        // [B, w]
+  const float* mean;     // [w]; nullptr => identity (raw network input)
+  const float* invstd;
+  const float* gamma;
+  const float* beta;
+  int w;
+  float slope;
+};
+
+struct ActSmem {
+  float mean[128], invstd[128], gamma[128], beta[128];
+  __device__ __forceinline__ void load(const ActSrc& s) {
+    if (s.mean && threadIdx.x < 128) {
+      const int k = threadIdx.x;
+      const bool in = k < s.w;
+      mean[k] = in ? s.mean[k] : 0.f; invstd[k] = in ? s.invstd[k] : 0.f;
+      gamma[k] = in ? s.gamma[k] : 0.f; beta[k] = in ? s.beta[k] : 0.f;
+    }
+  }
+  __device__ __forceinline__ float xhat(float yv, int k) const { return (yv - mean[k]) * invstd[k]; }
+  __device__ __forceinline__ float act(bool has_bn, float slope, float yv, int k) const {
+    if (!has_bn) return yv;
+    const float t = fmaf(xhat(yv, k), gamma[k], beta[k]);
+    return t > 0.f ? t : slope * t;
+  }
+};
+
+// A tile from activations: As[kk][m] = act(prev[m0+m][k0+kk])
+struct AGenAct {
+  ActSrc s; const ActSmem* sm; int m0, B;
+  __device__ __forceinline__ void post(int, float (*)[kBM]) {}
+  __device__ __forceinline__ void pre(int kt, float (*As)[kBM]) {
+    const int m = threadIdx.x & 127, kg = threadIdx.x >> 7, row = m0 + m;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kt * kBK + kg * 8 + e;
+      float v = 0.f;
+      if (row < B && k < s.w) v = sm->act(s.mean != nullptr, s.slope, __ldg(s.y + (size_t)row * s.w + k), k);
+      As[kg * 8 + e][m] = v;
+    }
+  }
+};
+// B tile from a small row-major weight: Bs[kk][n] = W[n][k0+kk] (transposed read) or W[k0+kk][n] (direct)
+template <bool kTransposed>
+struct BGenW {
+  const float* W; int rows, cols;     // W is [rows][cols]
+  __device__ __forceinline__ void post(int, float (*)[kBN]) {}
+  __device__ __forceinline__ void pre(int kt, float (*Bs)[kBN]) {
+    const int n = threadIdx.x & 127, kg = threadIdx.x >> 7;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kt * kBK + kg * 8 + e;
+      float v = 0.f;
+      if (kTransposed) { if (n < rows && k < cols) v = __ldg(W + (size_t)n * cols + k); }
+      else             { if (k < rows && n < cols) v = __ldg(W + (size_t)k * cols + n); }
+      Bs[kg * 8 + e][n] = v;
+    }
+  }
+};
+
+// ----------------------------------------------------------------------------------------- forward
+// part: [nCTA][128][3] = (count, mean, M2) of this CTA's rows per output column
+__global__ void __launch_bounds__(kThreads, 2)
+mlp_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ bias, int B, int wo,
+               float* __restrict__ y_out, float* __restrict__ part, int do_stats) {
+  __shared__ GemmSmem gs;
+  __shared__ ActSmem am;
+  const TileCoord tc;
+  const int m0 = blockIdx.x * kBM;
+  am.load(src);
+  __syncthreads();
+  AGenAct ag{src, &am, m0, B};
+  BGenW<true> bg{W, wo, src.w};
+  float acc[8][8];
+  gemm_tile(acc, gs, (src.w + kBK - 1) / kBK, ag, bg, tc);
+  const int nvalid = min(kBM, B - m0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = tc.col(j);
+    const float bj = (n < wo && bias) ? bias[n] : 0.f;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = m0 + tc.row(i);
+      const float yv = acc[i][j] + bj;
+      acc[i][j] = yv;
+      if (row < B && n < wo) { y_out[(size_t)row * wo + n] = yv; s += yv; }
+    }
+    if (do_stats) {
+      s = colsum16(s);
+      const float mean_c = s / (float)nvalid;
+      float m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dlt = acc[i][j] - mean_c;
+        if (m0 + tc.row(i) < B) m2 = fmaf(dlt, dlt, m2);
+      }
+      m2 = colsum16(m2);
+      if (tc.ty == 0 && n < wo) {
+        float* o = part + ((size_t)blockIdx.x * 128 + n) * 3;
+        o[0] = (float)nvalid; o[1] = mean_c; o[2] = m2;
+      }
+    }
+  }
+}
+
+// Chan et al. pairwise combination in CTA order; stats: [4][w] = mean, biased var, invstd, (spare)
+__global__ void mlp_stats_finalize_kernel(const float* __restrict__ part, int ncta, int w, float eps, float* __restrict__ stats,
+                                          float* __restrict__ running_mean, float* __restrict__ running_var, float momentum) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= w) return;
+  float cnt = 0.f, mean = 0.f, m2 = 0.f;
+  for (int c = 0; c < ncta; ++c) {
+    const float* p = part + ((size_t)c * 128 + n) * 3;
+    const float nb = p[0], mb = p[1], m2b = p[2];
+    const float tot = cnt + nb, dlt = mb - mean;
+    mean += dlt * (nb / tot);
+    m2 += m2b + dlt * dlt * (cnt * nb / tot);
+    cnt = tot;
+  }
+  const float var = m2 / cnt;
+  stats[n] = mean; stats[w + n] = var; stats[2 * w + n] = rsqrtf(var + eps); stats[3 * w + n] = cnt;
+  if (running_mean) {
+    running_mean[n] = (1.f - momentum) * running_mean[n] + momentum * mean;
+    running_var[n] = (1.f - momentum) * running_var[n] + momentum * (m2 / fmaxf(cnt - 1.f, 1.f));
+  }
+}
+
+// ----------------------------------------------------------------------------------------- backward (1): reduce
+// dyhat = da * lrelu'(gamma*xhat+beta) ; S1 = sum dyhat ; S2 = sum dyhat*xhat.  w must divide 256 (power of two <= 128).
+__global__ void __launch_bounds__(256)
+mlp_bwd_reduce_kernel(const float* __restrict__ da, ActSrc cur, int has_bn, long long n_elem, long long per_block,
+                      float* __restrict__ dyhat, float* __restrict__ part /*[nblk][128][2]*/) {
+  __shared__ ActSmem am;
+  __shared__ float red[256][2];
+  am.load(cur);
+  __syncthreads();
+  const int w = cur.w, n = threadIdx.x % w;
+  const long long e0 = (long long)blockIdx.x * per_block, e1 = min(n_elem, e0 + per_block);
+  float s1 = 0.f, s2 = 0.f;
+  for (long long i = e0 + threadIdx.x; i < e1; i += 256) {
+    float g = da[i];
+    if (has_bn) {
+      const float xh = am.xhat(cur.y[i], n);
+      const float t = fmaf(xh, am.gamma[n], am.beta[n]);
+      g = t > 0.f ? g : cur.slope * g;
+      s2 = fmaf(g, xh, s2);
+    }
+    s1 += g;
+    dyhat[i] = g;
+  }
+  red[threadIdx.x][0] = s1; red[threadIdx.x][1] = s2;
+  __syncthreads();
+  if (threadIdx.x < w) {
+    float a = 0.f, b = 0.f;
+    for (int t = threadIdx.x; t < 256; t += w) { a += red[t][0]; b += red[t][1]; }
+    part[((size_t)blockIdx.x * 128 + threadIdx.x) * 2 + 0] = a;
+    part[((size_t)blockIdx.x * 128 + threadIdx.x) * 2 + 1] = b;
+  }
+}
+__global__ void mlp_sum_finalize_kernel(const float* __restrict__ part, int nblk, int w, float* __restrict__ sums /*[2][w]*/) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= w) return;
+  float a = 0.f, b = 0.f;
+  for (int c = 0; c < nblk; ++c) { a += part[((size_t)c * 128 + n) * 2]; b += part[((size_t)c * 128 + n) * 2 + 1]; }
+  sums[n] = a; sums[w + n] = b;
+}
+
+// dy[b][o] formed on the fly from dyhat, y, stats and the (global) sums
+struct DyCtx {
+  const float* dyhat; ActSrc cur; const float* sums; float invN; int has_bn;
+  __device__ __forceinline__ float dy(const ActSmem& am, const float* s1, const float* s2, long long idx, int o) const {
+    const float g = __ldg(dyhat + idx);
+    if (!has_bn) return g;
+    const float xh = am.xhat(__ldg(cur.y + idx), o);
+    return am.gamma[o] * am.invstd[o] * (g - s1[o] * invN - xh * (s2[o] * invN));
+  }
+};
+
+// ----------------------------------------------------------------------------------------- backward (2a): da_prev = dy W
+struct AGenDy {
+  DyCtx c; const ActSmem* am; const float* s1; const float* s2; int m0, B;
+  __device__ __forceinline__ void post(int, float (*)[kBM]) {}
+  __device__ __forceinline__ void pre(int kt, float (*As)[kBM]) {
+    const int m = threadIdx.x & 127, kg = threadIdx.x >> 7, row = m0 + m, wo = c.cur.w;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int o = kt * kBK + kg * 8 + e;
+      As[kg * 8 + e][m] = (row < B && o < wo) ? c.dy(*am, s1, s2, (long long)row * wo + o, o) : 0.f;
+    }
+  }
+};
+__global__ void __launch_bounds__(kThreads, 2)
+mlp_bwd_gemm_kernel(DyCtx c, const float* __restrict__ W /*[wo][wi]*/, int B, int wi, float* __restrict__ da_prev) {
+  __shared__ GemmSmem gs;
+  __shared__ ActSmem am;
+  __shared__ float s1[128], s2[128];
+  const TileCoord tc;
+  const int m0 = blockIdx.x * kBM, wo = c.cur.w;
+  am.load(c.cur);
+  if (threadIdx.x < 128) {
+    s1[threadIdx.x] = (c.has_bn && threadIdx.x < wo) ? c.sums[threadIdx.x] : 0.f;
+    s2[threadIdx.x] = (c.has_bn && threadIdx.x < wo) ? c.sums[wo + threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  AGenDy ag{c, &am, s1, s2, m0, B};
+  BGenW<false> bg{W, wo, wi};
+  float acc[8][8];
+  gemm_tile(acc, gs, (wo + kBK - 1) / kBK, ag, bg, tc);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m0 + tc.row(i);
+    if (row >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = tc.col(j);
+      if (n < wi) da_prev[(size_t)row * wi + n] = acc[i][j];
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------- backward (2b): dW = dy^T act(prev)
+struct AGenDyT {   // As[kk = sample][m = o]
+  DyCtx c; const ActSmem* am; const float* s1; const float* s2; int b0, b1;
+  __device__ __forceinline__ void post(int, float (*)[kBM]) {}
+  __device__ __forceinline__ void pre(int kt, float (*As)[kBM]) {
+    const int o = threadIdx.x & 127, kg = threadIdx.x >> 7, wo = c.cur.w;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int b = b0 + kt * kBK + kg * 8 + e;
+      As[kg * 8 + e][o] = (b < b1 && o < wo) ? c.dy(*am, s1, s2, (long long)b * wo + o, o) : 0.f;
+    }
+  }
+};
+struct BGenActT {  // Bs[kk = sample][n = i]
+  ActSrc s; const ActSmem* sm; int b0, b1;
+  __device__ __forceinline__ void post(int, float (*)[kBN]) {}
+  __device__ __forceinline__ void pre(int kt, float (*Bs)[kBN]) {
+    const int i = threadIdx.x & 127, kg = threadIdx.x >> 7;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int b = b0 + kt * kBK + kg * 8 + e;
+      float v = 0.f;
+      if (b < b1 && i < s.w) v = sm->act(s.mean != nullptr, s.slope, __ldg(s.y + (size_t)b * s.w + i), i);
+      Bs[kg * 8 + e][i] = v;
+    }
+  }
+};
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_bwd_dw_kernel(DyCtx c, ActSrc prev, int B, int rows_per_split, float* __restrict__ part /*[nsplit][wo][wi]*/) {
+  __shared__ GemmSmem gs;
+  __shared__ ActSmem am, pm;
+  __shared__ float s1[128], s2[128];
+  const TileCoord tc;
+  const int wo = c.cur.w, wi = prev.w;
+  am.load(c.cur);
+  pm.load(prev);
+  if (threadIdx.x < 128) {
+    s1[threadIdx.x] = (c.has_bn && threadIdx.x < wo) ? c.sums[threadIdx.x] : 0.f;
+    s2[threadIdx.x] = (c.has_bn && threadIdx.x < wo) ? c.sums[wo + threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  const int b0 = blockIdx.x * rows_per_split, b1 = min(B, b0 + rows_per_split);
+  AGenDyT ag{c, &am, s1, s2, b0, b1};
+  BGenActT bg{prev, &pm, b0, b1};
+  float acc[8][8];
+  gemm_tile(acc, gs, (max(b1 - b0, 0) + kBK - 1) / kBK, ag, bg, tc);
+  float* out = part + (size_t)blockIdx.x * wo * wi;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int o = tc.row(i);
+    if (o >= wo) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = tc.col(j);
+      if (n < wi) out[(size_t)o * wi + n] = acc[i][j];
+    }
+  }
+}
+__global__ void mlp_dw_finalize_kernel(const float* __restrict__ part, int nsplit, int n, float* __restrict__ dW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int c = 0; c < nsplit; ++c) s += part[(size_t)c * n + i];
+  dW[i] = s;
+}
+
+static bool pow2_le128(int w) { return w >= 1 && w <= 128 && (w & (w - 1)) == 0; }
+static ActSrc make_src(const float* y, const float* stats, const float* gamma, const float* beta, int w, float slope) {
+  ActSrc s;
+  s.y = y; s.w = w; s.slope = slope;
+  s.mean = stats; s.invstd = stats ? stats + 2 * w : nullptr; s.gamma = gamma; s.beta = beta;
+  return s;
+}
+
+}  // namespace b200vae
+
+using namespace b200vae;
+
+extern "C" size_t b200vae_mlp_scratch_bytes(int B) {
+  const size_t ncta = (size_t)(B + 127) / 128;
+  const size_t a = ncta * 128 * 3, b = (size_t)296 * 128 * 2, c = (size_t)148 * 128 * 128;
+  size_t m = a > b ? a : b;
+  if (c > m) m = c;
+  return m * sizeof(float);
+}
+
+extern "C" int b200vae_mlp_layer_fwd(const float* in_y, const float* in_stats, const float* in_gamma, const float* in_beta,
+                                     float slope, const float* W, const float* bias, int B, int wi, int wo, float* y_out,
+                                     float* stats_out, float eps, float* running_mean, float* running_var, float momentum,
+                                     void* scratch, void* stream) {
+  if (!in_y || !W || !y_out || !scratch) return B200VAE_EALIGN;
+  if (B <= 0 || wi < 1 || wi > 128 || wo < 1 || wo > 128) return B200VAE_ESHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ncta = (B + 127) / 128;
+  const ActSrc src = make_src(in_y, in_stats, in_gamma, in_beta, wi, slope);
+  mlp_fwd_kernel<<<ncta, kThreads, 0, st>>>(src, W, bias, B, wo, y_out, (float*)scratch, stats_out ? 1 : 0);
+  int rc = check_launch();
+  if (rc || !stats_out) return rc;
+  mlp_stats_finalize_kernel<<<1, 128, 0, st>>>((const float*)scratch, ncta, wo, eps, stats_out, running_mean, running_var, momentum);
+  return check_launch();
+}
+
+extern "C" int b200vae_mlp_layer_bwd_reduce(const float* da, const float* y, const float* stats, const float* gamma,
+                                            const float* beta, float slope, int B, int w, float* dyhat, float* sums,
+                                            void* scratch, void* stream) {
+  if (!da || !dyhat || !sums || !scratch) return B200VAE_EALIGN;
+  if (B <= 0 || !pow2_le128(w)) return B200VAE_EUNSUP;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)B * w;
+  int nblk = (int)((n + 256 * 32 - 1) / (256 * 32));
+  if (nblk > 296) nblk = 296;
+  if (nblk < 1) nblk = 1;
+  long long per = (n + nblk - 1) / nblk;
+  per = (per + 255) / 256 * 256;                       // keeps (element index % w) == (thread index % w)
+  const ActSrc cur = make_src(y, stats, gamma, beta, w, slope);
+  mlp_bwd_reduce_kernel<<<nblk, 256, 0, st>>>(da, cur, stats ? 1 : 0, n, per, dyhat, (float*)scratch);
+  int rc = check_launch();
+  if (rc) return rc;
+  mlp_sum_finalize_kernel<<<1, 128, 0, st>>>((const float*)scratch, nblk, w, sums);
+  return check_launch();
+}
+
+extern "C" int b200vae_mlp_layer_bwd(const float* dyhat, const float* y, const float* stats, const float* gamma,
+                                     const float* beta, const float* sums, float inv_n, float slope, const float* W,
+                                     const float* prev_y, const float* prev_stats, const float* prev_gamma,
+                                     const float* prev_beta, int B, int wo, int wi, float* da_prev, float* dW,
+                                     void* scratch, void* stream) {
+  if (!dyhat || !W || !prev_y || !scratch) return B200VAE_EALIGN;
+  if (B <= 0 || wi < 1 || wi > 128 || wo < 1 || wo > 128) return B200VAE_ESHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  DyCtx c;
+  c.dyhat = dyhat; c.cur = make_src(y, stats, gamma, beta, wo, slope); c.sums = sums; c.invN = inv_n; c.has_bn = stats ? 1 : 0;
+  if (c.has_bn && !sums) return B200VAE_EALIGN;
+  int rc = B200VAE_OK;
+  if (da_prev) {
+    mlp_bwd_gemm_kernel<<<(B + 127) / 128, kThreads, 0, st>>>(c, W, B, wi, da_prev);
+    rc = check_launch();
+    if (rc) return rc;
+  }
+  if (dW) {
+    int nsplit = (B + 511) / 512;
+    if (nsplit > 148) nsplit = 148;
+    int rows = (B + nsplit - 1) / nsplit;
+    rows = round_up(rows, kBK);
+    const ActSrc prev = make_src(prev_y, prev_stats, prev_gamma, prev_beta, wi, slope);
+    mlp_bwd_dw_kernel<<<nsplit, kThreads, 0, st>>>(c, prev, B, rows, (float*)scratch);
+    rc = check_launch();
+    if (rc) return rc;
+    const int n = wo * wi;
+    mlp_dw_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float*)scratch, nsplit, n, dW);
+    rc = check_launch();
+  }
+  return rc;
+}

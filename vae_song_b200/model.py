@@ -324,8 +324,21 @@ class LIDVAE(VAE):
         return self._make_decoder(input_dim ** 2 * in_channel, latent_channel, icnn_channels,
                                   nn.Unflatten(1, (in_channel, input_dim, input_dim)))
 
+    fused_encoder = True    # 1-D MLP encoders run through the fused Linear+BN+LeakyReLU layer kernels when they match
+
+    def _encoder_plan(self):
+        plan = self.__dict__.get("_mlp_plan", False)
+        if plan is False or (plan is not None and plan.linears[0] is not self.encoder[0][0]):
+            plan = ops.MlpPlan.from_sequential(self.encoder)
+            self.__dict__["_mlp_plan"] = plan
+        return plan
+
     def encode(self, input):
-        ret = self.encoder(input)
+        plan = self._encoder_plan() if (self.fused_encoder and input.is_cuda and input.dim() == 2) else None
+        # the plan caches module references: rebuild it if BatchNorms were swapped (e.g. SyncBatchNorm conversion)
+        if plan is not None and any(b is not blk[1] for b, blk in zip(plan.bns, self.encoder)):
+            self.__dict__["_mlp_plan"] = plan = ops.MlpPlan.from_sequential(self.encoder)
+        ret = ops.fused_mlp(plan, input, self.training) if plan is not None else self.encoder(input)
         mu, var = ret.split(ret.shape[1] // 2, 1)
         return mu, F.softplus(var)
 

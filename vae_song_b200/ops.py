@@ -355,6 +355,180 @@ class VaeLossFn(torch.autograd.Function):
         return d_x, d_xh, d_mu, d_lv, d_zi, d_zr, None
 
 
+# ------------------------------------------------------------------------------------------ fused MLP encoder
+class MlpPlan:
+    """Structure of a [Linear -> BatchNorm1d -> LeakyReLU] x n (+ trailing Linear) stack, extracted from stock
+    nn.Modules (which keep owning the parameters / buffers, so state_dict keys do not change)."""
+
+    def __init__(self, linears, bns, slope):
+        self.linears, self.bns, self.slope = linears, bns, slope       # len(bns) == len(linears) - 1
+
+    @staticmethod
+    def from_sequential(seq):
+        """Recognise LIDVAE.make_encoder_1d (model.py:711-734): blocks Seq(Linear, BN1d, LeakyReLU) and a last block
+        Seq(Linear, BN1d, LeakyReLU, Linear).  Returns None when the module does not match (stock path is used)."""
+        nn = torch.nn
+        try:
+            blocks = list(seq)
+            lin, bns, slopes = [], [], []
+            for bi, blk in enumerate(blocks):
+                mods = list(blk)
+                last = bi == len(blocks) - 1
+                if len(mods) != (4 if last else 3):
+                    return None
+                if not (isinstance(mods[0], nn.Linear) and isinstance(mods[1], nn.BatchNorm1d) and isinstance(mods[2], nn.LeakyReLU)):
+                    return None
+                lin.append(mods[0]); bns.append(mods[1]); slopes.append(mods[2].negative_slope)
+                if last:
+                    if not isinstance(mods[3], nn.Linear):
+                        return None
+                    lin.append(mods[3])
+        except TypeError:
+            return None
+        ok_w = all(1 <= l.out_features <= 128 and (l.out_features & (l.out_features - 1)) == 0 for l in lin)
+        ok_w = ok_w and 1 <= lin[0].in_features <= 128
+        ok_bn = all(b.affine and b.track_running_stats and b.momentum is not None for b in bns)
+        if not (ok_w and ok_bn and len(set(slopes)) == 1 and all(l.bias is not None for l in lin)):
+            return None
+        return MlpPlan(lin, bns, float(slopes[0]))
+
+
+def _bn_group(bn):
+    """Process group for cross-rank statistics (train.SyncBatchNorm1d carries one), or None for local BN."""
+    import torch.distributed as dist
+    if type(bn).__name__ == "SyncBatchNorm1d" and dist.is_available() and dist.is_initialized() and dist.get_world_size(bn.group) > 1:
+        return bn.group if bn.group is not None else dist.group.WORLD
+    return None
+
+
+class FusedMlpFn(torch.autograd.Function):
+    """out = Linear_n( act(BN_{n-1}( ... act(BN_0(Linear_0(x))) ... )) ) through the fused layer kernels (csrc/mlp.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, plan, training, *params):
+        lib = _C.load()
+        x = _req(x, "x")
+        B = x.shape[0]
+        nl = len(plan.linears)
+        Ws = [_req(params[2 * i], "W") for i in range(nl)]
+        bs = [_req(params[2 * i + 1], "b") for i in range(nl)]
+        gs = [_req(params[2 * nl + 2 * i], "gamma") for i in range(nl - 1)]
+        bes = [_req(params[2 * nl + 2 * i + 1], "beta") for i in range(nl - 1)]
+        scratch = torch.empty(lib.b200vae_mlp_scratch_bytes(B), dtype=torch.uint8, device=x.device)
+        ys, stats, counts = [], [], []
+        prev = (x, None, None, None)
+        for i in range(nl):
+            wo, wi = Ws[i].shape
+            has_bn = i < nl - 1
+            y = torch.empty(B, wo, dtype=torch.float32, device=x.device)
+            st = None
+            rm = rv = None
+            mom = 0.0
+            if has_bn:
+                bn = plan.bns[i]
+                grp = _bn_group(bn) if training else None
+                st = torch.empty(4, wo, dtype=torch.float32, device=x.device)
+                if training and grp is None:
+                    rm, rv, mom = bn.running_mean, bn.running_var, float(bn.momentum)
+                    bn.num_batches_tracked.add_(1)
+            _C.check(lib.b200vae_mlp_layer_fwd(_ptr(prev[0]), _ptr(prev[1]), _ptr(prev[2]), _ptr(prev[3]), plan.slope,
+                                               _ptr(Ws[i]), _ptr(bs[i]), B, wi, wo, _ptr(y),
+                                               _ptr(st) if (has_bn and training) else None,
+                                               float(plan.bns[i].eps) if has_bn else 0.0, _ptr(rm), _ptr(rv), mom,
+                                               _ptr(scratch), _stream()), "mlp_layer_fwd")
+            n_glob = float(B)
+            if has_bn:
+                bn = plan.bns[i]
+                if not training:          # eval: running statistics are constants
+                    st[0].copy_(bn.running_mean); st[1].copy_(bn.running_var)
+                    st[2].copy_(torch.rsqrt(bn.running_var + bn.eps)); st[3].fill_(float(B))
+                elif grp is not None:     # cross-rank: one all_gather of (mean, var, count), Chan combine, no host sync
+                    import torch.distributed as dist
+                    world = dist.get_world_size(grp)
+                    pack = torch.cat([st[0], st[1], st[3, :1]])
+                    outs = [torch.empty_like(pack) for _ in range(world)]
+                    dist.all_gather(outs, pack, group=grp)
+                    allp = torch.stack(outs)
+                    means, vars_, cnt = allp[:, :wo], allp[:, wo:2 * wo], allp[:, 2 * wo:]
+                    N = cnt.sum()
+                    mean = (means * cnt).sum(0) / N
+                    var = ((vars_ + (means - mean) ** 2) * cnt).sum(0) / N
+                    st[0].copy_(mean); st[1].copy_(var); st[2].copy_(torch.rsqrt(var + bn.eps)); st[3].copy_(N.expand(wo))
+                    bn.running_mean.mul_(1 - bn.momentum).add_(mean, alpha=bn.momentum)
+                    bn.running_var.mul_(1 - bn.momentum).add_(var * (N / (N - 1)), alpha=bn.momentum)
+                    bn.num_batches_tracked.add_(1)
+                    n_glob = None         # read from st[3] in backward (device value)
+            ys.append(y); stats.append(st); counts.append(n_glob)
+            prev = (y, st, gs[i] if has_bn else None, bes[i] if has_bn else None)
+        ctx.plan, ctx.training, ctx.nl = plan, training, nl
+        ctx.save_for_backward(x, *ys, *[s for s in stats if s is not None], *Ws, *gs, *bes)
+        ctx.scratch = scratch
+        return ys[-1]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        lib = _C.load()
+        plan, training, nl = ctx.plan, ctx.training, ctx.nl
+        sv = ctx.saved_tensors
+        x = sv[0]; ys = sv[1:1 + nl]; sts = list(sv[1 + nl:nl + nl]) + [None]
+        Ws = sv[2 * nl:3 * nl]; gs = sv[3 * nl:4 * nl - 1]; bes = sv[4 * nl - 1:5 * nl - 2]
+        B = x.shape[0]
+        scratch = ctx.scratch
+        dWs, dbs, dgs, dbes = [None] * nl, [None] * nl, [None] * (nl - 1), [None] * (nl - 1)
+        da = _req(dout, "grad_out")
+        for i in range(nl - 1, -1, -1):
+            wo, wi = Ws[i].shape
+            has_bn = i < nl - 1
+            st = sts[i]
+            dyhat = torch.empty(B, wo, dtype=torch.float32, device=x.device)
+            sums = torch.empty(2, wo, dtype=torch.float32, device=x.device)
+            _C.check(lib.b200vae_mlp_layer_bwd_reduce(_ptr(da), _ptr(ys[i]), _ptr(st), _ptr(gs[i]) if has_bn else None,
+                                                      _ptr(bes[i]) if has_bn else None, plan.slope, B, wo, _ptr(dyhat),
+                                                      _ptr(sums), _ptr(scratch), _stream()), "mlp_layer_bwd_reduce")
+            inv_n = 1.0 / B
+            if has_bn:
+                dbes[i], dgs[i] = sums[0].clone(), sums[1].clone()        # local sums = parameter gradients
+                dbs[i] = torch.zeros(wo, dtype=torch.float32, device=x.device)   # bias feeding a BatchNorm: exactly 0
+                if not training:
+                    sums.zero_()                                          # eval-mode BN is affine: dy = gamma*invstd*dyhat
+                else:
+                    grp = _bn_group(plan.bns[i])
+                    if grp is not None:
+                        import torch.distributed as dist
+                        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=grp)
+                        inv_n = 1.0 / (B * dist.get_world_size(grp))      # equal shards (train.shard_rows)
+            else:
+                dbs[i] = sums[0].clone()
+            prev_y = x if i == 0 else ys[i - 1]
+            prev_st = None if i == 0 else sts[i - 1]
+            need_da = i > 0 or ctx.needs_input_grad[0]
+            da_prev = torch.empty(B, wi, dtype=torch.float32, device=x.device) if need_da else None
+            dW = torch.empty_like(Ws[i])
+            _C.check(lib.b200vae_mlp_layer_bwd(_ptr(dyhat), _ptr(ys[i]), _ptr(st), _ptr(gs[i]) if has_bn else None,
+                                               _ptr(bes[i]) if has_bn else None, _ptr(sums), inv_n, plan.slope, _ptr(Ws[i]),
+                                               _ptr(prev_y), _ptr(prev_st), _ptr(gs[i - 1]) if i > 0 else None,
+                                               _ptr(bes[i - 1]) if i > 0 else None, B, wo, wi, _ptr(da_prev), _ptr(dW),
+                                               _ptr(scratch), _stream()), "mlp_layer_bwd")
+            dWs[i] = dW
+            da = da_prev
+        flat = []
+        for i in range(nl):
+            flat += [dWs[i], dbs[i]]
+        for i in range(nl - 1):
+            flat += [dgs[i], dbes[i]]
+        return (da if ctx.needs_input_grad[0] else None, None, None, *flat)
+
+
+def fused_mlp(plan, x, training):
+    params = []
+    for l in plan.linears:
+        params += [l.weight, l.bias]
+    for b in plan.bns:
+        params += [b.weight, b.bias]
+    return FusedMlpFn.apply(x, plan, training, *params)
+
+
 # ------------------------------------------------------------------------------------------ Lipschitz
 def lipschitz_pair_ratios(X, Y, i1, i2, eps=1e-3):
     """ratio[p] = clamp(|Y[i1]-Y[i2]|,eps)/clamp(|X[i1]-X[i2]|,eps)  (utils.py:548-562)."""
