@@ -121,25 +121,40 @@ mlp_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict_
   }
 }
 
-// Chan et al. pairwise combination in CTA order; stats: [4][w] = mean, biased var, invstd, (spare)
-__global__ void mlp_stats_finalize_kernel(const float* __restrict__ part, int ncta, int w, float eps, float* __restrict__ stats,
-                                          float* __restrict__ running_mean, float* __restrict__ running_var, float momentum) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= w) return;
-  float cnt = 0.f, mean = 0.f, m2 = 0.f;
-  for (int c = 0; c < ncta; ++c) {
-    const float* p = part + ((size_t)c * 128 + n) * 3;
-    const float nb = p[0], mb = p[1], m2b = p[2];
-    const float tot = cnt + nb, dlt = mb - mean;
+// Chan et al. combination of the per-CTA (count, mean, M2): one WARP per column, lanes stride over the CTAs (independent
+// loads in flight), then a fixed-order shuffle tree -> deterministic.  stats: [4][w] = mean, biased var, invstd, count
+__device__ __forceinline__ void chan_merge(float& cnt, float& mean, float& m2, float nb, float mb, float m2b) {
+  const float tot = cnt + nb;
+  if (tot > 0.f) {
+    const float dlt = mb - mean;
     mean += dlt * (nb / tot);
     m2 += m2b + dlt * dlt * (cnt * nb / tot);
-    cnt = tot;
   }
-  const float var = m2 / cnt;
-  stats[n] = mean; stats[w + n] = var; stats[2 * w + n] = rsqrtf(var + eps); stats[3 * w + n] = cnt;
-  if (running_mean) {
-    running_mean[n] = (1.f - momentum) * running_mean[n] + momentum * mean;
-    running_var[n] = (1.f - momentum) * running_var[n] + momentum * (m2 / fmaxf(cnt - 1.f, 1.f));
+  cnt = tot;
+}
+__global__ void __launch_bounds__(256)
+mlp_stats_finalize_kernel(const float* __restrict__ part, int ncta, int w, float eps, float* __restrict__ stats,
+                          float* __restrict__ running_mean, float* __restrict__ running_var, float momentum) {
+  const int lane = threadIdx.x & 31, n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= w) return;
+  float cnt = 0.f, mean = 0.f, m2 = 0.f;
+  for (int c = lane; c < ncta; c += 32) {
+    const float* p = part + ((size_t)c * 128 + n) * 3;
+    chan_merge(cnt, mean, m2, p[0], p[1], p[2]);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const float nb = __shfl_down_sync(0xffffffffu, cnt, off), mb = __shfl_down_sync(0xffffffffu, mean, off),
+                m2b = __shfl_down_sync(0xffffffffu, m2, off);
+    chan_merge(cnt, mean, m2, nb, mb, m2b);
+  }
+  if (lane == 0) {
+    const float var = m2 / cnt;
+    stats[n] = mean; stats[w + n] = var; stats[2 * w + n] = rsqrtf(var + eps); stats[3 * w + n] = cnt;
+    if (running_mean) {
+      running_mean[n] = (1.f - momentum) * running_mean[n] + momentum * mean;
+      running_var[n] = (1.f - momentum) * running_var[n] + momentum * (m2 / fmaxf(cnt - 1.f, 1.f));
+    }
   }
 }
 
@@ -175,12 +190,14 @@ mlp_bwd_reduce_kernel(const float* __restrict__ da, ActSrc cur, int has_bn, long
     part[((size_t)blockIdx.x * 128 + threadIdx.x) * 2 + 1] = b;
   }
 }
-__global__ void mlp_sum_finalize_kernel(const float* __restrict__ part, int nblk, int w, float* __restrict__ sums /*[2][w]*/) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+mlp_sum_finalize_kernel(const float* __restrict__ part, int nblk, int w, float* __restrict__ sums /*[2][w]*/) {
+  const int lane = threadIdx.x & 31, n = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (n >= w) return;
   float a = 0.f, b = 0.f;
-  for (int c = 0; c < nblk; ++c) { a += part[((size_t)c * 128 + n) * 2]; b += part[((size_t)c * 128 + n) * 2 + 1]; }
-  sums[n] = a; sums[w + n] = b;
+  for (int c = lane; c < nblk; c += 32) { a += part[((size_t)c * 128 + n) * 2]; b += part[((size_t)c * 128 + n) * 2 + 1]; }
+  a = warp_sum(a); b = warp_sum(b);
+  if (lane == 0) { sums[n] = a; sums[w + n] = b; }
 }
 
 // dy[b][o] formed on the fly from dyhat, y, stats and the (global) sums
@@ -294,12 +311,14 @@ mlp_bwd_dw_kernel(DyCtx c, ActSrc prev, int B, int rows_per_split, float* __rest
     }
   }
 }
-__global__ void mlp_dw_finalize_kernel(const float* __restrict__ part, int nsplit, int n, float* __restrict__ dW) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+mlp_dw_finalize_kernel(const float* __restrict__ part, int nsplit, int n, float* __restrict__ dW) {
+  const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= n) return;
   float s = 0.f;
-  for (int c = 0; c < nsplit; ++c) s += part[(size_t)c * n + i];
-  dW[i] = s;
+  for (int c = lane; c < nsplit; c += 32) s += part[(size_t)c * n + i];
+  s = warp_sum(s);
+  if (lane == 0) dW[i] = s;
 }
 
 static bool pow2_le128(int w) { return w >= 1 && w <= 128 && (w & (w - 1)) == 0; }
@@ -334,7 +353,7 @@ extern "C" int b200vae_mlp_layer_fwd(const float* in_y, const float* in_stats, c
   mlp_fwd_kernel<<<ncta, kThreads, 0, st>>>(src, W, bias, B, wo, y_out, (float*)scratch, stats_out ? 1 : 0);
   int rc = check_launch();
   if (rc || !stats_out) return rc;
-  mlp_stats_finalize_kernel<<<1, 128, 0, st>>>((const float*)scratch, ncta, wo, eps, stats_out, running_mean, running_var, momentum);
+  mlp_stats_finalize_kernel<<<(wo + 7) / 8, 256, 0, st>>>((const float*)scratch, ncta, wo, eps, stats_out, running_mean, running_var, momentum);
   return check_launch();
 }
 
@@ -354,7 +373,7 @@ extern "C" int b200vae_mlp_layer_bwd_reduce(const float* da, const float* y, con
   mlp_bwd_reduce_kernel<<<nblk, 256, 0, st>>>(da, cur, stats ? 1 : 0, n, per, dyhat, (float*)scratch);
   int rc = check_launch();
   if (rc) return rc;
-  mlp_sum_finalize_kernel<<<1, 128, 0, st>>>((const float*)scratch, nblk, w, sums);
+  mlp_sum_finalize_kernel<<<(w + 7) / 8, 256, 0, st>>>((const float*)scratch, nblk, w, sums);
   return check_launch();
 }
 
@@ -385,7 +404,7 @@ extern "C" int b200vae_mlp_layer_bwd(const float* dyhat, const float* y, const f
     rc = check_launch();
     if (rc) return rc;
     const int n = wo * wi;
-    mlp_dw_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float*)scratch, nsplit, n, dW);
+    mlp_dw_finalize_kernel<<<(n + 7) / 8, 256, 0, st>>>((const float*)scratch, nsplit, n, dW);
     rc = check_launch();
   }
   return rc;
