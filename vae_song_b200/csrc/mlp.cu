@@ -43,17 +43,24 @@ struct ActSmem {
 };
 
 // A tile from activations: As[kk][m] = act(prev[m0+m][k0+kk])
+// (pre() only issues the global loads; post() -- after the FMA block of the previous K-step -- finishes and stores)
 struct AGenAct {
   ActSrc s; const ActSmem* sm; int m0, B;
-  __device__ __forceinline__ void post(int, float (*)[kBM]) {}
-  __device__ __forceinline__ void pre(int kt, float (*As)[kBM]) {
+  float r[8];
+  __device__ __forceinline__ void pre(int kt, float (*)[kBM]) {
     const int m = threadIdx.x & 127, kg = threadIdx.x >> 7, row = m0 + m;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int k = kt * kBK + kg * 8 + e;
-      float v = 0.f;
-      if (row < B && k < s.w) v = sm->act(s.mean != nullptr, s.slope, __ldg(s.y + (size_t)row * s.w + k), k);
-      As[kg * 8 + e][m] = v;
+      r[e] = (row < B && k < s.w) ? __ldg(s.y + (size_t)row * s.w + k) : 0.f;
+    }
+  }
+  __device__ __forceinline__ void post(int kt, float (*As)[kBM]) {
+    const int m = threadIdx.x & 127, kg = threadIdx.x >> 7, row = m0 + m;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kt * kBK + kg * 8 + e;
+      As[kg * 8 + e][m] = (row < B && k < s.w) ? sm->act(s.mean != nullptr, s.slope, r[e], k) : 0.f;
     }
   }
 };
@@ -203,10 +210,13 @@ mlp_sum_finalize_kernel(const float* __restrict__ part, int nblk, int w, float* 
 // dy[b][o] formed on the fly from dyhat, y, stats and the (global) sums
 struct DyCtx {
   const float* dyhat; ActSrc cur; const float* sums; float invN; int has_bn;
-  __device__ __forceinline__ float dy(const ActSmem& am, const float* s1, const float* s2, long long idx, int o) const {
-    const float g = __ldg(dyhat + idx);
+  __device__ __forceinline__ void fetch(long long idx, float& g, float& yv) const {
+    g = __ldg(dyhat + idx);
+    yv = has_bn ? __ldg(cur.y + idx) : 0.f;
+  }
+  __device__ __forceinline__ float dy(const ActSmem& am, const float* s1, const float* s2, float g, float yv, int o) const {
     if (!has_bn) return g;
-    const float xh = am.xhat(__ldg(cur.y + idx), o);
+    const float xh = am.xhat(yv, o);
     return am.gamma[o] * am.invstd[o] * (g - s1[o] * invN - xh * (s2[o] * invN));
   }
 };
@@ -214,13 +224,22 @@ struct DyCtx {
 // ----------------------------------------------------------------------------------------- backward (2a): da_prev = dy W
 struct AGenDy {
   DyCtx c; const ActSmem* am; const float* s1; const float* s2; int m0, B;
-  __device__ __forceinline__ void post(int, float (*)[kBM]) {}
-  __device__ __forceinline__ void pre(int kt, float (*As)[kBM]) {
+  float g[8], yv[8];
+  __device__ __forceinline__ void pre(int kt, float (*)[kBM]) {
     const int m = threadIdx.x & 127, kg = threadIdx.x >> 7, row = m0 + m, wo = c.cur.w;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int o = kt * kBK + kg * 8 + e;
-      As[kg * 8 + e][m] = (row < B && o < wo) ? c.dy(*am, s1, s2, (long long)row * wo + o, o) : 0.f;
+      g[e] = 0.f; yv[e] = 0.f;
+      if (row < B && o < wo) c.fetch((long long)row * wo + o, g[e], yv[e]);
+    }
+  }
+  __device__ __forceinline__ void post(int kt, float (*As)[kBM]) {
+    const int m = threadIdx.x & 127, kg = threadIdx.x >> 7, row = m0 + m, wo = c.cur.w;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int o = kt * kBK + kg * 8 + e;
+      As[kg * 8 + e][m] = (row < B && o < wo) ? c.dy(*am, s1, s2, g[e], yv[e], o) : 0.f;
     }
   }
 };
@@ -256,31 +275,46 @@ mlp_bwd_gemm_kernel(DyCtx c, const float* __restrict__ W /*[wo][wi]*/, int B, in
 // ----------------------------------------------------------------------------------------- backward (2b): dW = dy^T act(prev)
 struct AGenDyT {   // As[kk = sample][m = o]
   DyCtx c; const ActSmem* am; const float* s1; const float* s2; int b0, b1;
-  __device__ __forceinline__ void post(int, float (*)[kBM]) {}
-  __device__ __forceinline__ void pre(int kt, float (*As)[kBM]) {
+  float g[8], yv[8];
+  __device__ __forceinline__ void pre(int kt, float (*)[kBM]) {
     const int o = threadIdx.x & 127, kg = threadIdx.x >> 7, wo = c.cur.w;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int b = b0 + kt * kBK + kg * 8 + e;
-      As[kg * 8 + e][o] = (b < b1 && o < wo) ? c.dy(*am, s1, s2, (long long)b * wo + o, o) : 0.f;
+      g[e] = 0.f; yv[e] = 0.f;
+      if (b < b1 && o < wo) c.fetch((long long)b * wo + o, g[e], yv[e]);
+    }
+  }
+  __device__ __forceinline__ void post(int kt, float (*As)[kBM]) {
+    const int o = threadIdx.x & 127, kg = threadIdx.x >> 7, wo = c.cur.w;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int b = b0 + kt * kBK + kg * 8 + e;
+      As[kg * 8 + e][o] = (b < b1 && o < wo) ? c.dy(*am, s1, s2, g[e], yv[e], o) : 0.f;
     }
   }
 };
 struct BGenActT {  // Bs[kk = sample][n = i]
   ActSrc s; const ActSmem* sm; int b0, b1;
-  __device__ __forceinline__ void post(int, float (*)[kBN]) {}
-  __device__ __forceinline__ void pre(int kt, float (*Bs)[kBN]) {
+  float r[8];
+  __device__ __forceinline__ void pre(int kt, float (*)[kBN]) {
     const int i = threadIdx.x & 127, kg = threadIdx.x >> 7;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int b = b0 + kt * kBK + kg * 8 + e;
-      float v = 0.f;
-      if (b < b1 && i < s.w) v = sm->act(s.mean != nullptr, s.slope, __ldg(s.y + (size_t)b * s.w + i), i);
-      Bs[kg * 8 + e][i] = v;
+      r[e] = (b < b1 && i < s.w) ? __ldg(s.y + (size_t)b * s.w + i) : 0.f;
+    }
+  }
+  __device__ __forceinline__ void post(int kt, float (*Bs)[kBN]) {
+    const int i = threadIdx.x & 127, kg = threadIdx.x >> 7;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int b = b0 + kt * kBK + kg * 8 + e;
+      Bs[kg * 8 + e][i] = (b < b1 && i < s.w) ? sm->act(s.mean != nullptr, s.slope, r[e], i) : 0.f;
     }
   }
 };
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 mlp_bwd_dw_kernel(DyCtx c, ActSrc prev, int B, int rows_per_split, float* __restrict__ part /*[nsplit][wo][wi]*/) {
   __shared__ GemmSmem gs;
   __shared__ ActSmem am, pm;
@@ -335,7 +369,7 @@ using namespace b200vae;
 
 extern "C" size_t b200vae_mlp_scratch_bytes(int B) {
   const size_t ncta = (size_t)(B + 127) / 128;
-  const size_t a = ncta * 128 * 3, b = (size_t)296 * 128 * 2, c = (size_t)148 * 128 * 128;
+  const size_t a = ncta * 128 * 3, b = (size_t)296 * 128 * 2, c = (size_t)296 * 128 * 128;
   size_t m = a > b ? a : b;
   if (c > m) m = c;
   return m * sizeof(float);
@@ -364,7 +398,7 @@ extern "C" int b200vae_mlp_layer_bwd_reduce(const float* da, const float* y, con
   if (B <= 0 || !pow2_le128(w)) return B200VAE_EUNSUP;
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = (long long)B * w;
-  int nblk = (int)((n + 256 * 32 - 1) / (256 * 32));
+  int nblk = (int)((n + 256 * 4 - 1) / (256 * 4));
   if (nblk > 296) nblk = 296;
   if (nblk < 1) nblk = 1;
   long long per = (n + nblk - 1) / nblk;
@@ -395,8 +429,8 @@ extern "C" int b200vae_mlp_layer_bwd(const float* dyhat, const float* y, const f
     if (rc) return rc;
   }
   if (dW) {
-    int nsplit = (B + 511) / 512;
-    if (nsplit > 148) nsplit = 148;
+    int nsplit = (B + 255) / 256;
+    if (nsplit > 296) nsplit = 296;
     int rows = (B + nsplit - 1) / nsplit;
     rows = round_up(rows, kBK);
     const ActSrc prev = make_src(prev_y, prev_stats, prev_gamma, prev_beta, wi, slope);
