@@ -355,6 +355,158 @@ mlp_dw_finalize_kernel(const float* __restrict__ part, int nsplit, int n, float*
   if (lane == 0) dW[i] = s;
 }
 
+// ----------------------------------------------------------------------------------------- narrow layers (w <= 8)
+// The default LID-VAE encoder is 2-2-2-2-2-4-4 wide: a 128x128 tile per 128 rows wastes >99 % of its FMAs and is
+// latency bound.  For wi, wo <= 8 one THREAD owns a row: vector load, BN+LeakyReLU, wo x wi FMAs, vector store;
+// statistics / weight gradients are Chan- / sum-reduced warp -> block -> ordered per-block partials.
+template <int WI, int WO>
+__global__ void __launch_bounds__(256)
+mlp_narrow_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ bias, int B, int wo,
+                      float* __restrict__ y_out, float* __restrict__ part, int do_stats) {
+  __shared__ ActSmem am;
+  __shared__ float Ws[WO][WI], bs[WO];
+  __shared__ float red[8][WO][3];
+  am.load(src);
+  const int wi = src.w;
+  if (threadIdx.x < WO * WI) {
+    const int o = threadIdx.x / WI, k = threadIdx.x % WI;
+    Ws[o][k] = (o < wo && k < wi) ? W[o * wi + k] : 0.f;
+  }
+  if (threadIdx.x < WO) bs[threadIdx.x] = (threadIdx.x < wo && bias) ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const bool has_bn = src.mean != nullptr;
+  float cnt = 0.f, mean[WO], m2[WO];
+#pragma unroll
+  for (int o = 0; o < WO; ++o) { mean[o] = 0.f; m2[o] = 0.f; }
+  for (int row = blockIdx.x * 256 + threadIdx.x; row < B; row += gridDim.x * 256) {
+    float a[WI];
+#pragma unroll
+    for (int k = 0; k < WI; ++k) a[k] = (k < wi) ? am.act(has_bn, src.slope, __ldg(src.y + (size_t)row * wi + k), k) : 0.f;
+    cnt += 1.f;
+#pragma unroll
+    for (int o = 0; o < WO; ++o) {
+      float yv = bs[o];
+#pragma unroll
+      for (int k = 0; k < WI; ++k) yv = fmaf(a[k], Ws[o][k], yv);
+      if (o < wo) y_out[(size_t)row * wo + o] = yv;
+      const float dlt = yv - mean[o];                    // Welford
+      mean[o] += dlt / cnt;
+      m2[o] = fmaf(dlt, yv - mean[o], m2[o]);
+    }
+  }
+  if (!do_stats) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 0; o < WO; ++o) {
+    float c = cnt, mu = mean[o], q = m2[o];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const float nb = __shfl_down_sync(0xffffffffu, c, off), mb = __shfl_down_sync(0xffffffffu, mu, off),
+                  qb = __shfl_down_sync(0xffffffffu, q, off);
+      chan_merge(c, mu, q, nb, mb, qb);
+    }
+    if (lane == 0) { red[warp][o][0] = c; red[warp][o][1] = mu; red[warp][o][2] = q; }
+  }
+  __syncthreads();
+  if (threadIdx.x < wo) {
+    float c = 0.f, mu = 0.f, q = 0.f;
+    for (int w8 = 0; w8 < 8; ++w8) chan_merge(c, mu, q, red[w8][threadIdx.x][0], red[w8][threadIdx.x][1], red[w8][threadIdx.x][2]);
+    float* o = part + ((size_t)blockIdx.x * 128 + threadIdx.x) * 3;
+    o[0] = c; o[1] = mu; o[2] = q;
+  }
+}
+
+// da_prev = dy W and per-block partial of dW = dy^T act(prev), one row per thread
+template <int WI, int WO>
+__global__ void __launch_bounds__(256)
+mlp_narrow_bwd_kernel(DyCtx c, ActSrc prev, const float* __restrict__ W, int B, float* __restrict__ da_prev,
+                      float* __restrict__ part /*[nblk][wo*wi]*/) {
+  __shared__ ActSmem am, pm;
+  __shared__ float Ws[WO][WI], s1[WO], s2[WO];
+  __shared__ float red[8][WO * WI];
+  const int wo = c.cur.w, wi = prev.w;
+  am.load(c.cur);
+  pm.load(prev);
+  if (threadIdx.x < WO * WI) {
+    const int o = threadIdx.x / WI, k = threadIdx.x % WI;
+    Ws[o][k] = (o < wo && k < wi) ? W[o * wi + k] : 0.f;
+  }
+  if (threadIdx.x < WO) {
+    s1[threadIdx.x] = (c.has_bn && threadIdx.x < wo) ? c.sums[threadIdx.x] : 0.f;
+    s2[threadIdx.x] = (c.has_bn && threadIdx.x < wo) ? c.sums[wo + threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  const bool prev_bn = prev.mean != nullptr;
+  float acc[WO][WI];
+#pragma unroll
+  for (int o = 0; o < WO; ++o)
+#pragma unroll
+    for (int k = 0; k < WI; ++k) acc[o][k] = 0.f;
+  for (int row = blockIdx.x * 256 + threadIdx.x; row < B; row += gridDim.x * 256) {
+    float dy[WO], a[WI], dap[WI];
+#pragma unroll
+    for (int o = 0; o < WO; ++o) {
+      dy[o] = 0.f;
+      if (o < wo) {
+        float g, yv;
+        c.fetch((long long)row * wo + o, g, yv);
+        dy[o] = c.dy(am, s1, s2, g, yv, o);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < WI; ++k) {
+      a[k] = (k < wi) ? pm.act(prev_bn, prev.slope, __ldg(prev.y + (size_t)row * wi + k), k) : 0.f;
+      dap[k] = 0.f;
+    }
+#pragma unroll
+    for (int o = 0; o < WO; ++o)
+#pragma unroll
+      for (int k = 0; k < WI; ++k) { dap[k] = fmaf(dy[o], Ws[o][k], dap[k]); acc[o][k] = fmaf(dy[o], a[k], acc[o][k]); }
+    if (da_prev) {
+#pragma unroll
+      for (int k = 0; k < WI; ++k) if (k < wi) da_prev[(size_t)row * wi + k] = dap[k];
+    }
+  }
+  if (!part) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 0; o < WO; ++o)
+#pragma unroll
+    for (int k = 0; k < WI; ++k) {
+      const float v = warp_sum(acc[o][k]);
+      if (lane == 0) red[warp][o * WI + k] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < WO * WI) {
+    const int o = threadIdx.x / WI, k = threadIdx.x % WI;
+    float v = 0.f;
+    for (int w8 = 0; w8 < 8; ++w8) v += red[w8][threadIdx.x];
+    if (o < wo && k < wi) part[(size_t)blockIdx.x * wo * wi + o * wi + k] = v;
+  }
+}
+
+static int narrow_class(int w) { return w <= 2 ? 2 : (w <= 4 ? 4 : (w <= 8 ? 8 : 0)); }
+static int narrow_grid(int B) { int g = (B + 255) / 256; return g > 592 ? 592 : (g < 1 ? 1 : g); }
+
+template <int WI, int WO>
+static void narrow_fwd_launch(const ActSrc& src, const float* W, const float* bias, int B, int wo, float* y, float* part,
+                              int do_stats, int grid, cudaStream_t st) {
+  mlp_narrow_fwd_kernel<WI, WO><<<grid, 256, 0, st>>>(src, W, bias, B, wo, y, part, do_stats);
+}
+template <int WI, int WO>
+static void narrow_bwd_launch(const DyCtx& c, const ActSrc& prev, const float* W, int B, float* da_prev, float* part, int grid,
+                              cudaStream_t st) {
+  mlp_narrow_bwd_kernel<WI, WO><<<grid, 256, 0, st>>>(c, prev, W, B, da_prev, part);
+}
+#define B200VAE_NARROW_DISPATCH(FN, ci, co, ...)                                   \
+  do {                                                                              \
+    if (ci == 2 && co == 2) FN<2, 2>(__VA_ARGS__); else if (ci == 2 && co == 4) FN<2, 4>(__VA_ARGS__);   \
+    else if (ci == 2 && co == 8) FN<2, 8>(__VA_ARGS__); else if (ci == 4 && co == 2) FN<4, 2>(__VA_ARGS__); \
+    else if (ci == 4 && co == 4) FN<4, 4>(__VA_ARGS__); else if (ci == 4 && co == 8) FN<4, 8>(__VA_ARGS__); \
+    else if (ci == 8 && co == 2) FN<8, 2>(__VA_ARGS__); else if (ci == 8 && co == 4) FN<8, 4>(__VA_ARGS__); \
+    else FN<8, 8>(__VA_ARGS__);                                                     \
+  } while (0)
+
 static bool pow2_le128(int w) { return w >= 1 && w <= 128 && (w & (w - 1)) == 0; }
 static ActSrc make_src(const float* y, const float* stats, const float* gamma, const float* beta, int w, float slope) {
   ActSrc s;
@@ -369,7 +521,7 @@ using namespace b200vae;
 
 extern "C" size_t b200vae_mlp_scratch_bytes(int B) {
   const size_t ncta = (size_t)(B + 127) / 128;
-  const size_t a = ncta * 128 * 3, b = (size_t)296 * 128 * 2, c = (size_t)296 * 128 * 128;
+  const size_t a = (ncta > 592 ? ncta : 592) * 128 * 3, b = (size_t)296 * 128 * 2, c = (size_t)296 * 128 * 128;
   size_t m = a > b ? a : b;
   if (c > m) m = c;
   return m * sizeof(float);
@@ -382,9 +534,15 @@ extern "C" int b200vae_mlp_layer_fwd(const float* in_y, const float* in_stats, c
   if (!in_y || !W || !y_out || !scratch) return B200VAE_EALIGN;
   if (B <= 0 || wi < 1 || wi > 128 || wo < 1 || wo > 128) return B200VAE_ESHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  const int ncta = (B + 127) / 128;
+  int ncta = (B + 127) / 128;
   const ActSrc src = make_src(in_y, in_stats, in_gamma, in_beta, wi, slope);
-  mlp_fwd_kernel<<<ncta, kThreads, 0, st>>>(src, W, bias, B, wo, y_out, (float*)scratch, stats_out ? 1 : 0);
+  const int ci = narrow_class(wi), co = narrow_class(wo);
+  if (ci && co) {
+    ncta = narrow_grid(B);
+    B200VAE_NARROW_DISPATCH(narrow_fwd_launch, ci, co, src, W, bias, B, wo, y_out, (float*)scratch, stats_out ? 1 : 0, ncta, st);
+  } else {
+    mlp_fwd_kernel<<<ncta, kThreads, 0, st>>>(src, W, bias, B, wo, y_out, (float*)scratch, stats_out ? 1 : 0);
+  }
   int rc = check_launch();
   if (rc || !stats_out) return rc;
   mlp_stats_finalize_kernel<<<(wo + 7) / 8, 256, 0, st>>>((const float*)scratch, ncta, wo, eps, stats_out, running_mean, running_var, momentum);
@@ -423,6 +581,17 @@ extern "C" int b200vae_mlp_layer_bwd(const float* dyhat, const float* y, const f
   c.dyhat = dyhat; c.cur = make_src(y, stats, gamma, beta, wo, slope); c.sums = sums; c.invN = inv_n; c.has_bn = stats ? 1 : 0;
   if (c.has_bn && !sums) return B200VAE_EALIGN;
   int rc = B200VAE_OK;
+  const int ci = narrow_class(wi), co = narrow_class(wo);
+  if (ci && co) {
+    const int grid = narrow_grid(B);
+    const ActSrc prev = make_src(prev_y, prev_stats, prev_gamma, prev_beta, wi, slope);
+    B200VAE_NARROW_DISPATCH(narrow_bwd_launch, ci, co, c, prev, W, B, da_prev, dW ? (float*)scratch : nullptr, grid, st);
+    rc = check_launch();
+    if (rc || !dW) return rc;
+    const int n = wo * wi;
+    mlp_dw_finalize_kernel<<<(n + 7) / 8, 256, 0, st>>>((const float*)scratch, grid, n, dW);
+    return check_launch();
+  }
   if (da_prev) {
     mlp_bwd_gemm_kernel<<<(B + 127) / 128, kThreads, 0, st>>>(c, W, B, wi, da_prev);
     rc = check_launch();
