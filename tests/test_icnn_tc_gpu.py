@@ -114,5 +114,5 @@ np.savez(sys.argv[1], **out)
             env = dict(os.environ, B200VAE_TC2=flag)
             subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
             res[flag] = dict(np.load(f.name))
-    for k in res["0"]:
-        assert np.array_equal(res["0"][k], res["1"][k]), k      # same arithmetic order per row -> bit identical
+    for k in res["0"]:      # same MMA sequence per accumulator; only the order of the thin A1^T g1 partial sums differs
+        close_report(res["1"][k], res["0"][k], 2e-6, "pair vs single " + k)
