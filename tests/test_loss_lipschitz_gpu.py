@@ -160,3 +160,49 @@ def test_batched_cell_estimator_equals_per_cell_calls():
     for i, X in enumerate(cells):
         ref = utils.estimate_local_lipschitz(m.decode, X, num_pairs=500) if X.size(0) >= 2 else (0.0, 0.0, 0.0)
         np.testing.assert_allclose(got[i], ref, rtol=1e-5)
+
+
+def test_utils_reparameterize_and_kld_match_reference_formulas():
+    """utils.reparameterize draws eps exactly like utils.py:40-47 (randn_like on the expanded [B,ns,nz] std), so the
+    same seed gives the reference's samples; utils.kld is model.py:884 / utils.py:140-141."""
+    from vae_song_b200 import utils
+    g = torch.Generator(device="cuda").manual_seed(9)
+    mu = torch.randn(50, 3, device="cuda", generator=g)
+    lv = torch.randn(50, 3, device="cuda", generator=g) * 0.5
+    torch.manual_seed(123)
+    z = utils.reparameterize(mu, lv, nsamples=7)
+    torch.manual_seed(123)
+    std = lv.mul(0.5).exp().unsqueeze(1).expand(50, 7, 3)
+    ref = mu.unsqueeze(1).expand(50, 7, 3) + torch.randn_like(std) * std
+    assert z.shape == (50, 7, 3)
+    close_report(z.cpu().numpy(), ref.cpu().numpy(), 1e-6, "reparameterize")
+    ref_kl = (-0.5 * (1 + lv - mu ** 2 - lv.exp())).mean(dim=0).sum().item()
+    assert abs(utils.kld(mu, lv) - ref_kl) <= 1e-5 * abs(ref_kl)
+
+
+def test_train_model_loop_runs_and_learns():
+    """train.train_model == lipschitz.py:23-44 (same signature): a few epochs on a toy mixture reduce the loss."""
+    from vae_song_b200 import model, train
+    torch.manual_seed(0)
+    X = torch.cat([torch.randn(512, 2) * 0.3 + 2.0, torch.randn(512, 2) * 0.3 - 2.0])
+    ds = torch.utils.data.TensorDataset(X, torch.zeros(1024, dtype=torch.long))
+    loader = torch.utils.data.DataLoader(ds, batch_size=256, shuffle=True, drop_last=True,
+                                         generator=torch.Generator().manual_seed(0))
+    m = model.LIDVAE(dataset="pinwheel", icnn_channels=[64, 64], hidden_channels=[16, 8], inverse_lipschitz=0.1, beta=0.01)
+    rng = np.random.default_rng(0)
+    with torch.no_grad():
+        for ic in (m.decoder[0], m.decoder[1]):
+            ic.W[0].param.copy_(torch.tensor(rng.normal(np.log(1.0 / 64), 0.5, (64, 64)), dtype=torch.float32))
+            ic.W[1].param.copy_(torch.tensor(rng.normal(np.log(2.0 / 64), 0.5, (1, 64)), dtype=torch.float32))
+
+    def eval_loss():
+        m.eval()
+        with torch.no_grad():
+            x = X.cuda()
+            recon, mu, lv, z, _ = m(x, latent_rand_sampling=False)
+            return float(m.loss(x, recon, mu, lv, z, None)[0])
+    m.cuda()
+    before = eval_loss()
+    train.train_model(m, loader, epochs=15, lr=2e-3, device="cuda", grad_clip={"enabled": True, "clip_type": "norm", "max_norm": 5.0})
+    after = eval_loss()
+    assert np.isfinite(after) and after < 0.7 * before, (before, after)
