@@ -45,10 +45,23 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock / power / throttle reasons sampled every ~2 ms through NVML in a background thread (the timed region of
+    a 3 ms step x K steps is far shorter than nvidia-smi's sampling period); falls back to `nvidia-smi -lms 100`."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self._stop = [], None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                                           str(index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -57,13 +70,29 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        R = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+             "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.time(), [str(sm), str(self.max_sm), str(pw)] +
+                                  ["Active" if (mask & R[k]) else "Not Active" for k in
+                                   ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def window(self, t0, t1):
-        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows[-3:]]
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(rows)}
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(rows), "source": "nvml" if self.nvml else "nvidia-smi"}
         try:
             sm = sorted(float(r[0]) for r in rows)
             out["sm_mhz"] = sm[len(sm) // 2]
@@ -77,6 +106,7 @@ class ClockSampler:
         return out
 
     def stop(self):
+        self._stop = True
         if self.proc:
             self.proc.terminate()
 
