@@ -164,6 +164,16 @@ int b200vae_mlp_layer_bwd(const float* dyhat, const float* y, const float* stats
                           const float* prev_beta, int B, int wo, int wi, float* da_prev, float* dW,
                           void* scratch, void* stream);
 
+/* ---- nearest-neighbour squared distances (chamfer_distance, model.py:896-912) -------------------
+ * minv[b,i] = min_j |A[b,i,:] - Bp[b,j,:]|^2, argm[b,i] = a minimiser.  A [B,Na,dim], Bp [B,Nb,dim], dim <= 4.  The
+ * [B,Na,Nb] matrix of torch.cdist is never formed. */
+int b200vae_nn_sqdist_fwd(const float* A, const float* Bp, int B, int Na, int Nb, int dim, float* minv, int* argm,
+                          void* stream);
+/* dA[b,i,:] = gA[b,i]*2(A_i - Bp_argA(i)) + sum_{j: argB(j)=i} gB[b,j]*2(A_i - Bp_j): gradient w.r.t. A of
+ * sum gA*min_j|A_i-Bp_j|^2 + sum gB*min_i|Bp_j-A_i|^2 (argB = minimisers of the reversed query).  gA or gB may be NULL. */
+int b200vae_nn_sqdist_bwd(const float* A, const float* Bp, const int* argA, const int* argB, const float* gA,
+                          const float* gB, int B, int Na, int Nb, int dim, float* dA, void* stream);
+
 int b200vae_last_cuda_error(void);
 const char* b200vae_version(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */

@@ -262,6 +262,73 @@ def gen_lipschitz(ref_model, ref_utils):
     print("lipschitz_cases.npz:", len(out), "arrays")
 
 
+def _run_family(out, name, make, x, eps, patch_name, L=None):
+    """Reference forward/loss/backward of a FlexibleVAE / Set model with the noise draw replaced by `eps`
+    (unittest.mock on torch.randn / torch.randn_like for the duration of the call; the reference source is untouched)."""
+    from unittest import mock
+    torch.manual_seed(5)
+    m32 = make()
+    sd = sd_to_np(m32.state_dict())
+    for k, a in sd.items():
+        out[f"{name}/sd/{k}"] = a
+    out[f"{name}/x"], out[f"{name}/eps"] = x, eps
+    m = make().double()
+    m.load_state_dict({k: torch.tensor(a).double() if a.dtype.kind == "f" else torch.tensor(a) for k, a in sd.items()})
+    m.train()
+    if hasattr(m, "wu_alpha"):
+        m.wu_alpha = 0.6
+    xt = torch.tensor(x, dtype=torch.float64)
+    et = torch.tensor(eps, dtype=torch.float64)
+    with mock.patch.object(torch, patch_name, side_effect=lambda *a, **k: et.clone()):
+        res = m(xt, L=L) if L is not None else m(xt)
+    recon, mu, lv, z_in, z_rec = res
+    total, lrec, lreg, llr = m.loss(xt, recon, mu, lv, z_in, z_rec)
+    total.backward()
+    pre = f"{name}/f64/"
+    out[pre + "recon"], out[pre + "mu"], out[pre + "lv"] = (t.detach().numpy() for t in (recon, mu, lv))
+    out[pre + "z_in"] = z_in.detach().numpy()
+    if z_rec is not None:
+        out[pre + "z_rec"] = z_rec.detach().numpy()
+    out[pre + "loss"] = np.array([float(total), float(lrec), float(lreg), float(llr)])
+    for k, q in m.named_parameters():
+        out[pre + "grad/" + k] = np.zeros(q.shape) if q.grad is None else q.grad.numpy().copy()
+
+
+def gen_families(ref_model):
+    """BASELINE configs[0] (pinwheel LR-VAE), configs[3] (conv LR-VAE / beta-VAE on MNIST-shaped data), configs[4]
+    (set LR-VAE on point clouds) at reduced widths: forward tuple, loss 4-tuple, every parameter gradient."""
+    out = {}
+    rng = np.random.default_rng(41)
+    _run_family(out, "c1_lrvae_pinwheel",
+                lambda: ref_model.LRVAE(alpha=0.3, beta=0.01, dataset="pinwheel", hidden_channels=[16] * 3,
+                                        encoder_type="mlp", decoder_type="mlp"),
+                rng.normal(0, 1.5, (64, 2)).astype(np.float32), rng.normal(0, 1, (3, 64, 2)).astype(np.float32), "randn", L=3)
+    _run_family(out, "c3_lrvae_conv",
+                lambda: ref_model.LRVAE(alpha=0.1, beta=0.001, dataset="mnist", hidden_channels=[4, 8],
+                                        encoder_type="conv", decoder_type="conv"),
+                rng.uniform(0, 1, (6, 1, 28, 28)).astype(np.float32), rng.normal(0, 1, (2, 6, 28)).astype(np.float32), "randn", L=2)
+    _run_family(out, "c3_vanilla_conv_logmse",
+                lambda: ref_model.VanillaVAE(beta=0.5, dataset="mnist", hidden_channels=[4, 8], encoder_type="conv",
+                                             decoder_type="conv", is_log_mse=True),
+                rng.uniform(0, 1, (5, 1, 28, 28)).astype(np.float32), rng.normal(0, 1, (1, 5, 28)).astype(np.float32), "randn", L=1)
+    kw = dict(latent_channel=8, num_points=48, d_model=16, num_heads=2, num_encoder_layers=1, num_decoder_layers=1, ff_dim=32)
+    _run_family(out, "c4_setlrvae_attn", lambda: ref_model.SetLRVAE(alpha=0.1, beta=0.2, use_attention=True, **kw),
+                rng.normal(0, 1, (4, 48, 3)).astype(np.float32), rng.normal(0, 1, (4, 8)).astype(np.float32), "randn_like")
+    _run_family(out, "c4_setvae_deepsets",
+                lambda: ref_model.SetVAE(beta=0.2, latent_channel=8, num_points=40, encoder_hidden=[16, 32],
+                                         decoder_hidden=[32, 16], use_attention=False),
+                rng.normal(0, 1, (5, 40, 3)).astype(np.float32), rng.normal(0, 1, (5, 8)).astype(np.float32), "randn_like")
+    # chamfer_distance model.py:896-912 on ragged set sizes, values and gradients
+    a = rng.normal(0, 1, (3, 70, 3)); b = rng.normal(0, 1, (3, 300, 3))
+    at, bt = torch.tensor(a, requires_grad=True), torch.tensor(b, requires_grad=True)
+    cd = ref_model.chamfer_distance(at, bt)
+    cd.backward()
+    out["chamfer/a"], out["chamfer/b"], out["chamfer/cd"] = a, b, np.array(float(cd))
+    out["chamfer/ga"], out["chamfer/gb"] = at.grad.numpy().copy(), bt.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "family_cases.npz"), **out)
+    print("family_cases.npz:", len(out), "arrays")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref_module, ref_model, ref_utils = import_reference()
@@ -271,6 +338,7 @@ def main():
     gen_mnist_shaped(ref_model)
     gen_losses(ref_model, ref_utils)
     gen_lipschitz(ref_model, ref_utils)
+    gen_families(ref_model)
 
 
 if __name__ == "__main__":

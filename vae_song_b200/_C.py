@@ -26,7 +26,7 @@ EXPORTS = [
     "b200vae_icnn_workspace_bytes", "b200vae_icnn_prepare", "b200vae_icnn_decode_fwd", "b200vae_icnn_decode_bwd",
     "b200vae_loss_fwd", "b200vae_loss_bwd", "b200vae_lipschitz_pairs", "b200vae_lipschitz_allpairs",
     "b200vae_lipschitz_num_tiles", "b200vae_adam_step", "b200vae_adam_step_dev", "b200vae_mlp_scratch_bytes", "b200vae_mlp_layer_fwd",
-    "b200vae_mlp_layer_bwd_reduce", "b200vae_mlp_layer_bwd", "b200vae_last_cuda_error", "b200vae_version",
+    "b200vae_mlp_layer_bwd_reduce", "b200vae_mlp_layer_bwd", "b200vae_nn_sqdist_fwd", "b200vae_nn_sqdist_bwd", "b200vae_last_cuda_error", "b200vae_version",
     "b200vae_launch_count",
 ]
 
@@ -100,6 +100,10 @@ def load():
     lib.b200vae_mlp_layer_bwd_reduce.argtypes = [vp, vp, vp, vp, vp, f, i, i, vp, vp, vp, vp]
     lib.b200vae_mlp_layer_bwd.restype = i
     lib.b200vae_mlp_layer_bwd.argtypes = [vp, vp, vp, vp, vp, vp, f, f, vp, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp]
+    lib.b200vae_nn_sqdist_fwd.restype = i
+    lib.b200vae_nn_sqdist_fwd.argtypes = [vp, vp, i, i, i, i, vp, vp, vp]
+    lib.b200vae_nn_sqdist_bwd.restype = i
+    lib.b200vae_nn_sqdist_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp]
     lib.b200vae_last_cuda_error.restype = i
     lib.b200vae_version.restype = C.c_char_p
     lib.b200vae_launch_count.restype = ll

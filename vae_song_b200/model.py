@@ -386,3 +386,155 @@ class LIDVAE(VAE):
     def loss(self, input, output, mu, log_var, z_input=None, z_recon=None):
         rec, reg, _ = _vae_losses(input, output, mu, log_var, None, None, self.is_log_mse)
         return rec + reg * self.beta, rec.detach(), reg.detach(), 0.0
+
+
+# ------------------------------------------------------------------------------------------------ set models
+def chamfer_distance(points_pred, points_gt):
+    """Symmetric Chamfer distance (model.py:896-912) through the tiled nearest-neighbour kernel: the [B,Np,Ng]
+    matrix of torch.cdist is never materialised.  points_* [B, N, 3] -> scalar."""
+    m_pg, m_gp = ops.NearestSqDistFn.apply(points_pred, points_gt)
+    return (m_pg.mean(dim=1) + m_gp.mean(dim=1)).mean()
+
+
+def _lin_bn_relu(i, o):
+    return nn.Sequential(nn.Linear(i, o), nn.BatchNorm1d(o), nn.ReLU())
+
+
+class SetEncoder(nn.Module):
+    """DeepSets encoder (model.py:915-948): per-point MLP, permutation-invariant pooling, two heads."""
+
+    def __init__(self, point_dim=3, hidden_dims=[128, 256, 512], latent_dim=128, pool_type="max"):
+        super().__init__()
+        self.pool_type = pool_type
+        dims = [point_dim] + list(hidden_dims)
+        self.phi = nn.ModuleList([_lin_bn_relu(a, b) for a, b in zip(dims[:-1], dims[1:])])
+        self.fc_mu = nn.Linear(dims[-1], latent_dim)
+        self.fc_logvar = nn.Linear(dims[-1], latent_dim)
+
+    def forward(self, points):
+        B, N, D = points.shape
+        x = points.reshape(B * N, D)
+        for layer in self.phi:
+            x = layer(x)
+        x = x.view(B, N, -1)
+        s = x.mean(dim=1) if self.pool_type == "mean" else (x.sum(dim=1) if self.pool_type == "sum" else x.max(dim=1)[0])
+        return self.fc_mu(s), self.fc_logvar(s)
+
+
+class SetEncoderAttn(nn.Module):
+    """Transformer set encoder (model.py:951-971), stock nn.TransformerEncoder + max pooling."""
+
+    def __init__(self, point_dim=3, latent_dim=128, d_model=256, num_heads=4, num_layers=2, ff_dim=512, dropout=0.0):
+        super().__init__()
+        self.input_proj = nn.Linear(point_dim, d_model)
+        layer = nn.TransformerEncoderLayer(d_model=d_model, nhead=num_heads, dim_feedforward=ff_dim, dropout=dropout,
+                                           batch_first=True)
+        self.encoder = nn.TransformerEncoder(layer, num_layers=num_layers)
+        self.pool = nn.AdaptiveMaxPool1d(1)
+        self.fc_mu = nn.Linear(d_model, latent_dim)
+        self.fc_logvar = nn.Linear(d_model, latent_dim)
+
+    def forward(self, points):
+        x = self.encoder(self.input_proj(points))
+        s = self.pool(x.transpose(1, 2)).squeeze(-1)
+        return self.fc_mu(s), self.fc_logvar(s)
+
+
+class SetDecoderAttn(nn.Module):
+    """Learned point queries cross-attending to one latent token (model.py:974-994)."""
+
+    def __init__(self, latent_dim=128, num_points=2048, d_model=256, num_heads=4, num_layers=2, ff_dim=512, dropout=0.0):
+        super().__init__()
+        self.num_points = num_points
+        self.query_embed = nn.Parameter(torch.randn(num_points, d_model) * 0.02)
+        self.latent_to_token = nn.Linear(latent_dim, d_model)
+        layer = nn.TransformerDecoderLayer(d_model=d_model, nhead=num_heads, dim_feedforward=ff_dim, dropout=dropout,
+                                           batch_first=True)
+        self.decoder = nn.TransformerDecoder(layer, num_layers=num_layers)
+        self.output_proj = nn.Linear(d_model, 3)
+
+    def forward(self, z):
+        memory = self.latent_to_token(z).unsqueeze(1)
+        queries = self.query_embed.unsqueeze(0).expand(z.shape[0], -1, -1)
+        return self.output_proj(self.decoder(tgt=queries, memory=memory))
+
+
+class SetDecoder(nn.Module):
+    """MLP decoder over [z, per-point query] (model.py:996-1029)."""
+
+    def __init__(self, latent_dim=128, num_points=2048, hidden_dims=[512, 256, 128], point_dim=3):
+        super().__init__()
+        self.num_points = num_points
+        self.point_queries = nn.Parameter(torch.randn(num_points, 64) * 0.02)
+        dims = [latent_dim + 64] + list(hidden_dims)
+        self.mlp = nn.ModuleList([_lin_bn_relu(a, b) for a, b in zip(dims[:-1], dims[1:])] + [nn.Linear(dims[-1], point_dim)])
+
+    def forward(self, z):
+        B = z.shape[0]
+        q = self.point_queries.unsqueeze(0).expand(B, -1, -1)
+        x = torch.cat([z.unsqueeze(1).expand(-1, self.num_points, -1), q], dim=-1).reshape(B * self.num_points, -1)
+        for layer in self.mlp[:-1]:
+            x = layer(x)
+        return self.mlp[-1](x).view(B, self.num_points, -1)
+
+
+class SetVAE(VAE):
+    """Set VAE on point clouds (model.py:1032-1083); Chamfer reconstruction + Gaussian KL through the fused kernels."""
+
+    def __init__(self, latent_channel=128, num_points=2048, encoder_hidden=[128, 256, 512], decoder_hidden=[512, 256, 128],
+                 beta=1.0, is_log_mse=False, dataset="shapenet", pool_type="max", use_attention=True, d_model=256,
+                 num_heads=4, num_encoder_layers=2, num_decoder_layers=2, ff_dim=512, attn_dropout=0.0):
+        super().__init__()
+        self.latent_channel, self.beta, self.is_log_mse, self.num_points = latent_channel, beta, is_log_mse, num_points
+        self.data_type = "set"
+        if use_attention:
+            self.encoder = SetEncoderAttn(3, latent_channel, d_model, num_heads, num_encoder_layers, ff_dim, attn_dropout)
+            self.decoder = SetDecoderAttn(latent_channel, num_points, d_model, num_heads, num_decoder_layers, ff_dim, attn_dropout)
+        else:
+            self.encoder = SetEncoder(3, encoder_hidden, latent_channel, pool_type)
+            self.decoder = SetDecoder(latent_channel, num_points, decoder_hidden, 3)
+
+    def encode(self, input):
+        return self.encoder(input)
+
+    def decode(self, input):
+        return self.decoder(input)
+
+    def _sample(self, mu, log_var, latent_rand_sampling, eps):
+        if not latent_rand_sampling:
+            return mu
+        return ops.ReparamFn.apply(mu, log_var, torch.randn_like(mu) if eps is None else eps)
+
+    def forward(self, input, latent_rand_sampling=True, L=1, eps=None):
+        mu, log_var = self.encode(input)
+        z = self._sample(mu, log_var, latent_rand_sampling, eps)
+        return self.decode(z), mu, log_var, z, None
+
+    def loss(self, input, output, mu, log_var, z_input=None, z_recon=None):
+        rec = chamfer_distance(output, input)
+        _, reg, _ = _vae_losses(None, None, mu, log_var, None, None, False)
+        return rec + self.beta * reg, rec.detach(), reg.detach(), torch.tensor(0.0, device=input.device)
+
+
+class SetLRVAE(SetVAE):
+    """Set LR-VAE (model.py:1086-1114): decodes z.detach() and re-encodes for the latent-reconstruction term."""
+
+    def __init__(self, alpha=0.01, **kwargs):
+        super().__init__(**kwargs)
+        self.alpha = alpha
+        self.wu_alpha = 0.0
+
+    def forward(self, input, latent_rand_sampling=True, L=1, eps=None):
+        mu, log_var = self.encode(input)
+        z = self._sample(mu, log_var, latent_rand_sampling, eps)
+        recon = self.decode(z.detach())
+        z_recon, _ = self.encode(recon)
+        return recon, mu, log_var, z, z_recon
+
+    def loss(self, input, output, mu, log_var, z_input, z_recon):
+        rec = chamfer_distance(output, input)
+        # [B,D] latents: dim 0 of the latent-recon mean is the batch here (no L axis); the fused kernel's Lz = B
+        _, reg, lr = _vae_losses(None, None, mu, log_var, z_input, z_recon, False)
+        self.last_kl_loss = float(reg.detach())
+        w = self.alpha * self.wu_alpha
+        return rec + self.beta * reg + w * lr, rec.detach(), (self.beta * reg).detach(), (w * lr).detach()

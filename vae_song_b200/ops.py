@@ -526,6 +526,48 @@ def fused_mlp(plan, x, training):
     return FusedMlpFn.apply(x, plan, training, *params)
 
 
+# ------------------------------------------------------------------------------------------ chamfer
+class NearestSqDistFn(torch.autograd.Function):
+    """(min_j |a_i - b_j|^2 [B,Na],  min_i |b_j - a_i|^2 [B,Nb]) for point sets a [B,Na,dim], b [B,Nb,dim] without the
+    [B,Na,Nb] distance matrix of torch.cdist (model.py:905-912)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        lib = _C.load()
+        a, b = _req(a, "points_pred"), _req(b, "points_gt")
+        B, Na, dim = a.shape
+        Nb = b.shape[1]
+        ma = torch.empty(B, Na, dtype=torch.float32, device=a.device)
+        mb = torch.empty(B, Nb, dtype=torch.float32, device=a.device)
+        ia = torch.empty(B, Na, dtype=torch.int32, device=a.device)
+        ib = torch.empty(B, Nb, dtype=torch.int32, device=a.device)
+        _C.check(lib.b200vae_nn_sqdist_fwd(_ptr(a), _ptr(b), B, Na, Nb, dim, _ptr(ma), _ptr(ia), _stream()), "nn_sqdist_fwd")
+        _C.check(lib.b200vae_nn_sqdist_fwd(_ptr(b), _ptr(a), B, Nb, Na, dim, _ptr(mb), _ptr(ib), _stream()), "nn_sqdist_fwd")
+        ctx.save_for_backward(a, b, ia, ib)
+        ctx.set_materialize_grads(False)
+        return ma, mb
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, ga, gb):
+        lib = _C.load()
+        a, b, ia, ib = ctx.saved_tensors
+        B, Na, dim = a.shape
+        Nb = b.shape[1]
+        ga = None if ga is None else _req(ga, "grad")
+        gb = None if gb is None else _req(gb, "grad")
+        da = db = None
+        if ctx.needs_input_grad[0] and (ga is not None or gb is not None):
+            da = torch.empty_like(a)
+            _C.check(lib.b200vae_nn_sqdist_bwd(_ptr(a), _ptr(b), _ptr(ia), _ptr(ib), _ptr(ga), _ptr(gb), B, Na, Nb, dim,
+                                               _ptr(da), _stream()), "nn_sqdist_bwd")
+        if ctx.needs_input_grad[1] and (ga is not None or gb is not None):
+            db = torch.empty_like(b)
+            _C.check(lib.b200vae_nn_sqdist_bwd(_ptr(b), _ptr(a), _ptr(ib), _ptr(ia), _ptr(gb), _ptr(ga), B, Nb, Na, dim,
+                                               _ptr(db), _stream()), "nn_sqdist_bwd")
+        return da, db
+
+
 # ------------------------------------------------------------------------------------------ Lipschitz
 def lipschitz_pair_ratios(X, Y, i1, i2, eps=1e-3):
     """ratio[p] = clamp(|Y[i1]-Y[i2]|,eps)/clamp(|X[i1]-X[i2]|,eps)  (utils.py:548-562)."""
