@@ -64,8 +64,12 @@ struct Tc2Maps { CUtensorMap b1hi, b1lo, b2hi, b2lo; };   // boxes of 16 x 128 (
 
 template <bool X3>
 struct Tc2Cfg {
-  static constexpr int S = X3 ? 5 : 10;
-  static constexpr int kStageBytes = (X3 ? 4 : 2) * k2TileBytes;          // A(hi[,lo]) + B half (hi[,lo])
+  // Every stage costs one cross-SM barrier round trip (remote arrives in, multicast commit out).  With one 16-wide
+  // K-block per stage (256 tensor cycles at 1xTF32) that round trip paced the pipeline, so a stage holds KPS blocks.
+  static constexpr int KPS = 2;
+  static constexpr int S = X3 ? 2 : 5;
+  static constexpr int kSubBytes = (X3 ? 4 : 2) * k2TileBytes;            // one K-block: A(hi[,lo]) + B half (hi[,lo])
+  static constexpr int kStageBytes = KPS * kSubBytes;
   static constexpr int kOffAlo = k2TileBytes, kOffB = (X3 ? 2 : 1) * k2TileBytes, kOffBlo = 3 * k2TileBytes;
 };
 template <bool X3>
@@ -103,7 +107,7 @@ icnn_tc2_fwd_kernel(const __grid_constant__ Tc2Maps maps, const float* __restric
   const int ngemm = (xhat != nullptr) ? 2 : 1;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 8 + 1); mbar_init(empty0 + 8 * s, 1); }   // 4 generator warps x 2 CTAs + TMA
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 16 + 1); mbar_init(empty0 + 8 * s, 1); }   // 8 generator warps x 2 CTAs + TMA
     for (int b = 0; b < 2; ++b) { mbar_init(accfull0 + 8 * b, 1); mbar_init(accempty0 + 8 * b, 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -201,14 +205,14 @@ icnn_tc2_fwd_kernel(const __grid_constant__ Tc2Maps maps, const float* __restric
     for (int j = 0; j < D; ++j) zr[j] = valid ? z[(size_t)(m0 + row) * D + j] : 0.f;
     const uint32_t a_row_off = (uint32_t)row * 64u;
     uint32_t it = 0;
-    auto produce = [&](int kb, auto&& gen) {                   // group kh produces the K-blocks with kb % 2 == kh
-      if ((kb & 1) != kh) { ++it; return; }
-      const uint32_t s = it % S, ph = (it / S) & 1;
+    auto produce = [&](int kb, auto&& gen) {                   // group kh produces the K-blocks with kb % 2 == kh,
+      if ((kb & 1) != kh) { ++it; return; }                    // i.e. sub-block kh of every stage (it counts K-blocks)
+      const uint32_t stg = it / C::KPS, s = stg % S, ph = (stg / S) & 1;
       float v[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) v[e] = gen(kb * kKB + e, e);
       mbar_wait(empty0 + 8 * s, ph ^ 1);
-      unsigned char* At = stages + s * C::kStageBytes;
+      unsigned char* At = stages + s * C::kStageBytes + (it % C::KPS) * C::kSubBytes;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t off = a_row_off + ((uint32_t)(c ^ rsw) << 4);
@@ -275,17 +279,22 @@ icnn_tc2_fwd_kernel(const __grid_constant__ Tc2Maps maps, const float* __restric
     // =========================== TMA producer: this CTA's half of every B tile ===========================
     if (lane == 0) {
       uint32_t it = 0;
+      const int NST = NKB / C::KPS;
       for (int g = 0; g < ngemm; ++g) {
         const CUtensorMap* mhi = g == 0 ? &maps.b1hi : &maps.b2hi;
         const CUtensorMap* mlo = g == 0 ? &maps.b1lo : &maps.b2lo;
         for (int p = 0; p < NP; ++p)
-          for (int kb = 0; kb < NKB; ++kb, ++it) {
+          for (int st = 0; st < NST; ++st, ++it) {
             const uint32_t s = it % S, ph = (it / S) & 1;
             mbar_wait(empty0 + 8 * s, ph ^ 1);
-            const uint32_t dst = smem_u32(stages + s * C::kStageBytes);
-            if (rank == 0) mbar_arrive_expect_tx(full0 + 8 * s, 2 * (X3 ? 2 : 1) * k2TileBytes);   // both halves
-            tma_load_2d_2sm(dst + C::kOffB, mhi, lead_full0 + 8 * s, kb * kKB, p * kTN + (int)rank * k2Rows);
-            if (X3) tma_load_2d_2sm(dst + C::kOffBlo, mlo, lead_full0 + 8 * s, kb * kKB, p * kTN + (int)rank * k2Rows);
+            if (rank == 0) mbar_arrive_expect_tx(full0 + 8 * s, C::KPS * 2 * (X3 ? 2 : 1) * k2TileBytes);   // both CTAs' halves
+#pragma unroll
+            for (int j = 0; j < C::KPS; ++j) {
+              const uint32_t dst = smem_u32(stages + s * C::kStageBytes + j * C::kSubBytes);
+              const int kb = st * C::KPS + j;
+              tma_load_2d_2sm(dst + C::kOffB, mhi, lead_full0 + 8 * s, kb * kKB, p * kTN + (int)rank * k2Rows);
+              if (X3) tma_load_2d_2sm(dst + C::kOffBlo, mlo, lead_full0 + 8 * s, kb * kKB, p * kTN + (int)rank * k2Rows);
+            }
           }
       }
     }
@@ -293,29 +302,33 @@ icnn_tc2_fwd_kernel(const __grid_constant__ Tc2Maps maps, const float* __restric
     // =========================== MMA issuer (leader CTA only) ===========================
     if (lane == 0 && rank == 0) {
       uint32_t it = 0;
+      const int NST = NKB / C::KPS;
       for (int pp = 0; pp < ngemm * NP; ++pp) {
         const int buf = pp & 1;
         mbar_wait(accempty0 + 8 * buf, ((pp >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_t = tmem_base + (uint32_t)(buf * kTN);
-        for (int kb = 0; kb < NKB; ++kb, ++it) {
+        for (int st = 0; st < NST; ++st, ++it) {
           const uint32_t s = it % S, ph = (it / S) & 1;
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stages + s * C::kStageBytes);
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t a_hi = make_desc_sw64(sa + ks * 32);
-            const uint64_t b_hi = make_desc_sw64(sa + C::kOffB + ks * 32);
-            const uint32_t acc = (kb | ks) ? 1u : 0u;
-            if (X3) {
-              const uint64_t a_lo = make_desc_sw64(sa + C::kOffAlo + ks * 32);
-              const uint64_t b_lo = make_desc_sw64(sa + C::kOffBlo + ks * 32);
-              umma_tf32_2sm(d_t, a_lo, b_hi, kIdescTf32M256, acc);
-              umma_tf32_2sm(d_t, a_hi, b_lo, kIdescTf32M256, 1u);
-              umma_tf32_2sm(d_t, a_hi, b_hi, kIdescTf32M256, 1u);
-            } else {
-              umma_tf32_2sm(d_t, a_hi, b_hi, kIdescTf32M256, acc);
+          for (int j = 0; j < C::KPS; ++j) {
+            const uint32_t sa = smem_u32(stages + s * C::kStageBytes + j * C::kSubBytes);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t a_hi = make_desc_sw64(sa + ks * 32);
+              const uint64_t b_hi = make_desc_sw64(sa + C::kOffB + ks * 32);
+              const uint32_t acc = (st | j | ks) ? 1u : 0u;
+              if (X3) {
+                const uint64_t a_lo = make_desc_sw64(sa + C::kOffAlo + ks * 32);
+                const uint64_t b_lo = make_desc_sw64(sa + C::kOffBlo + ks * 32);
+                umma_tf32_2sm(d_t, a_lo, b_hi, kIdescTf32M256, acc);
+                umma_tf32_2sm(d_t, a_hi, b_lo, kIdescTf32M256, 1u);
+                umma_tf32_2sm(d_t, a_hi, b_hi, kIdescTf32M256, 1u);
+              } else {
+                umma_tf32_2sm(d_t, a_hi, b_hi, kIdescTf32M256, acc);
+              }
             }
           }
           umma_commit_2sm(empty0 + 8 * s);
