@@ -29,7 +29,10 @@ int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* 
            uint8_t* mask2, int precision, const float* ws, cudaStream_t st);
 int tc2_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1,
             uint8_t* mask2, int precision, const float* ws, cudaStream_t st);
-size_t tc_extra_ws_floats(int d, int H, int precision);
+int tc3_prepare(int d, int H, int precision, float* ws, cudaStream_t st);
+int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2,
+            int precision, float* ws, cudaStream_t st);
+size_t tc_extra_ws_floats(int B, int d, int H, int precision);
 size_t tc_bwd_ws_floats(int B, int d, int H);
 int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H,
            const b200vae_icnn_params* p, int mode, float kappa, const b200vae_icnn_grads* g, float* dz, int precision,
@@ -52,7 +55,7 @@ using namespace b200vae;
 
 extern "C" size_t b200vae_icnn_workspace_bytes(int B, int d, int H, int precision, int for_backward) {
   if (B <= 0 || d <= 0 || H <= 0) return 0;
-  const size_t extra = (precision != B200VAE_PREC_FP32) ? tc_extra_ws_floats(d, H, precision) : 0;
+  const size_t extra = (precision != B200VAE_PREC_FP32) ? tc_extra_ws_floats(B, d, H, precision) : 0;
   const WsLayout L = ws_layout(B, d, H, extra);
   const size_t fl = for_backward ? L.end + (extra ? tc_bwd_ws_floats(B, d, H) : 0) : L.fwd_end + extra + 64;
   return fl * sizeof(float) + 256;
@@ -72,7 +75,9 @@ extern "C" int b200vae_icnn_prepare(const b200vae_icnn_params* p, int d, int H, 
   if (ws_bytes < b200vae_icnn_workspace_bytes(1, d, H, precision, 0)) return B200VAE_EWS;
   rc = simt_prepare(p, d, H, weight_mode, ws_base(ws), (cudaStream_t)stream);
   if (rc || precision == B200VAE_PREC_FP32) return rc;
-  return tc_prepare(p, d, H, weight_mode, precision, ws_base(ws), (cudaStream_t)stream);
+  rc = tc_prepare(p, d, H, weight_mode, precision, ws_base(ws), (cudaStream_t)stream);
+  if (rc) return rc;
+  return tc3_prepare(d, H, precision, ws_base(ws), (cudaStream_t)stream);
 }
 
 extern "C" int b200vae_icnn_decode_fwd(const float* z, int B, int d, int H, int weight_mode, float kappa, float* psi,
@@ -86,9 +91,14 @@ extern "C" int b200vae_icnn_decode_fwd(const float* z, int B, int d, int H, int 
   if (ws_bytes < b200vae_icnn_workspace_bytes(B, d, H, precision, 0)) return B200VAE_EWS;
   if (precision == B200VAE_PREC_FP32)
     return simt_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, ws_base(ws), (cudaStream_t)stream);
-  // forward kernel variant: CTA pairs (tcgen05 cta_group::2, double-buffered TMEM) or single CTA; B200VAE_TC2=0/1
-  static const int use_pair = [] { const char* e = getenv("B200VAE_TC2"); return e ? atoi(e) : 0; }();
-  if (use_pair) return tc2_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), (cudaStream_t)stream);
+  // forward kernel variant, B200VAE_FWD = 3 (default): persistent CTA pairs (icnn_tc3.cu), falling back to 1 where it
+  // does not fit (H > 1024); 2: one-tile-per-pair kernel (icnn_tc2.cu); 1: single-CTA kernel (icnn_tc.cu)
+  static const int variant = [] { const char* e = getenv("B200VAE_FWD"); return e ? atoi(e) : 3; }();
+  if (variant == 3) {
+    rc = tc3_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), (cudaStream_t)stream);
+    if (rc != B200VAE_EUNSUP) return rc;
+  }
+  if (variant == 2) return tc2_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), (cudaStream_t)stream);
   return tc_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), (cudaStream_t)stream);
 }
 
@@ -104,7 +114,7 @@ extern "C" int b200vae_icnn_decode_bwd(const float* z, const float* v, const flo
   if (ws_bytes < b200vae_icnn_workspace_bytes(B, d, H, precision, 1)) return B200VAE_EWS;
   if (precision != B200VAE_PREC_FP32 && !gpsi)   // tensor-core backward (gpsi path stays on the FP32 kernels)
     return tc_bwd(z, v, mask1, mask2, B, d, H, p, weight_mode, kappa, grads, dz, precision, ws_base(ws), (cudaStream_t)stream);
-  const size_t extra = (precision != B200VAE_PREC_FP32) ? tc_extra_ws_floats(d, H, precision) : 0;
+  const size_t extra = (precision != B200VAE_PREC_FP32) ? tc_extra_ws_floats(B, d, H, precision) : 0;
   return simt_bwd(z, v, gpsi, mask1, mask2, B, d, H, p, weight_mode, kappa, grads, dz, ws_base(ws), extra,
                   (cudaStream_t)stream);
 }

@@ -24,9 +24,9 @@
 
 namespace b200vae {
 
-size_t tc_extra_ws_floats(int d, int H, int precision) {
+size_t tc_extra_ws_floats(int B, int d, int H, int precision) {
   (void)precision;
-  return tc_layout(d, H).end;
+  return tc_layout(d, H).end + tc3_layout(B, d, H).end;      // single-CTA operand copies, then the pair kernel's arrays
 }
 
 __global__ void tc_prepare_kernel(const float* __restrict__ P0, const float* __restrict__ P0T, const float* __restrict__ P1,
@@ -48,6 +48,7 @@ __global__ void tc_prepare_kernel(const float* __restrict__ P0, const float* __r
         for (int j = 0; j < d; ++j) { w[j] = A0p[(size_t)c * (d + 1) + j]; u[j] = A1p[(size_t)c * (d + 1) + j]; }
         w[3] = A0p[(size_t)c * (d + 1) + d]; u[3] = A1p[(size_t)c * (d + 1) + d];
       }
+      if (d <= 2) u[2] = inr ? P1[c] : 0.f;     // spare lane of the float4: P1 rides along (one LDS less per element)
       A0q[c] = make_float4(w[0], w[1], w[2], w[3]);
       A1q[c] = make_float4(u[0], u[1], u[2], u[3]);
       P1q[c] = inr ? P1[c] : 0.f;
@@ -380,9 +381,10 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
         uint32_t word = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float h1 = __uint_as_float(r[j]) + lin_of<D>(m.A1s[nb + j], zr);
+          const float4 q1 = m.A1s[nb + j];
+          const float h1 = __uint_as_float(r[j]) + lin_of<D>(q1, zr);
           const bool pos = h1 > 0.f;
-          h2 = fmaf(m.P1s[nb + j], pos ? h1 : kSlope * h1, h2);
+          h2 = fmaf(D <= 2 ? q1.z : m.P1s[nb + j], pos ? h1 : kSlope * h1, h2);
           word |= (pos ? 1u : 0u) << j;
         }
         m.maskw[(nb >> 5) * 256 + w.row] = word;
@@ -429,8 +431,8 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
               bits4[r] = m.maskw[(kb >> 1) * 256 + g.rb + 64 * r] >> ((kb & 1) * 16 + g.c * 4);
           }
           worker_produce4<X3>(m, w, g, kb, [&](int k, int e, float (&o)[4]) {
-            const float p1 = m.P1s[k];
             const float4 q = m.A1s[k];
+            const float p1 = D <= 2 ? q.z : m.P1s[k];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               const float c1 = s24[r] * p1;
@@ -1038,7 +1040,7 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
            const b200vae_icnn_params* p, int mode, float kappa, const b200vae_icnn_grads* g, float* dz, int precision,
            float* ws, cudaStream_t st) {
   if (precision == B200VAE_PREC_BF16 || d > 3 || !v) return B200VAE_EUNSUP;
-  const size_t extra = tc_extra_ws_floats(d, H, precision);
+  const size_t extra = tc_extra_ws_floats(B, d, H, precision);
   const WsLayout L = ws_layout(B, d, H, extra);
   const TcLayout T = tc_layout(d, H);
   const float* tb = tc_base(ws, d, H);

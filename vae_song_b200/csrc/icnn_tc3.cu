@@ -1,0 +1,705 @@
+// icnn_tc3.cu -- persistent CTA-pair (tcgen05 cta_group::2) fused ICNN potential + Brenier map (forward).
+//
+// Why a third forward kernel: ncu showed the single-CTA kernel (icnn_tc.cu) to be ISSUE bound, not tensor bound
+// (about 2000 warp instructions per 16-wide K-block against 512 tensor cycles), with the epilogue exposed
+// (D[256x256] fills TMEM) and 256 tiles on 148 SMs.  This kernel removes all three:
+//   * lean operand generators.  GEMM1's A = leaky(A0 z + b0)^2 is computed with packed f32x2 FMAs and rounded to
+//     tf32 with ONE integer add (the tensor core ignores the low 13 bits).  GEMM2's A operand is no longer
+//     g1 = s2*P1*s1 but the bare LeakyReLU slope pattern 1 + 4*bit (1.0 / 5.0, exact in tf32): P1 and the factor
+//     0.2 are folded into the B operand (B2g = 0.2*P1[o]*P[o][i], prepared once), s2 is a per-row scalar applied
+//     at the very end.  The affine part A1 z + b1 of h1 rides in one extra K-block of GEMM1 (z and A1 split hi/lo,
+//     so it is fp32-accurate in every precision) and xhat's A1^T g1 term is a predicated add in GEMM1's epilogue.
+//   * CTA pairs: one tcgen05.mma.cta_group::2 (M=256, N=256, K=8) drives both SMs, each SM holds 128 sample rows
+//     (A tile + accumulator) and half of every B tile: half the shared-memory operand traffic per MMA, and the
+//     512 TMEM columns hold TWO accumulators, so 8 epilogue warps drain unit i while 8 generator warps feed unit i+1.
+//   * persistent scheduling over fine units.  Unit = (256-row tile, GEMM, 256-column pass); 74 clusters walk the
+//     unit list round-robin (all GEMM1 units first).  Cross-unit data (mask bits, per-pass partial sums) goes
+//     through an L2-resident scratch; a per-(tile, rank) counter orders GEMM2 after GEMM1 and elects the last
+//     unit of a tile to combine the partials in a FIXED order (bit-reproducible, no float atomics).
+// Reference lines replaced: module.py:142-148 (ICNN.forward) and model.py:820-822 / 826-828 (grad of psi).
+#include <mutex>
+#include <unordered_map>
+
+#include "tc_common.cuh"
+
+namespace b200vae {
+
+constexpr int k3Rows = 128;                       // sample rows per CTA
+constexpr int k3Threads = 18 * 32;                // 8 epilogue warps, 8 generator warps, TMA warp, MMA warp
+constexpr int k3TileBytes = k3Rows * 64;          // 128 rows x 64 B = 8 KB (A tile, and this CTA's half of a B tile)
+constexpr int k3MaskStride = 36;                  // words per row of the shared mask buffer (16 B aligned, conflict free)
+constexpr uint32_t k3Idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_rank3() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id3() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters3() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync3() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa3(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t lead_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(lead_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(k3Idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bar_gen() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// round-to-nearest (ties away) to tf32 in one integer add: tcgen05 kind::tf32 ignores the 13 low mantissa bits
+__device__ __forceinline__ float rn_tf32_fast(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+__device__ __forceinline__ float rn_tf32_masked(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+// ------------------------------------------------------------------------------------ prepare
+// grid (ceil(K1/256), Hq): row r, column c of the four operand copies; row 0 also packs the per-unit parameter tables
+__global__ void tc3_prepare_kernel(const float* __restrict__ P0, const float* __restrict__ P0T, const float* __restrict__ P1,
+                                   const float* __restrict__ A0p, const float* __restrict__ A1p, int d, int Hp, int Hq,
+                                   int K1, int want_lo, float* __restrict__ B1ahi, float* __restrict__ B1alo,
+                                   float* __restrict__ B2ghi, float* __restrict__ B2glo, float4* __restrict__ A0g,
+                                   float4* __restrict__ E1) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= K1) return;
+  const bool rin = r < Hp;
+  if (c < Hq) {
+    const bool in = rin && c < Hp;
+    const float a = in ? P0[(size_t)r * Hp + c] : 0.f;                              // P[o=r][i=c]
+    const float b = in ? (kSlope * P1[c]) * P0T[(size_t)r * Hp + c] : 0.f;          // 0.2 * P1[o=c] * P[o=c][i=r]
+    const float ah = to_tf32(a), bh = to_tf32(b);
+    B1ahi[(size_t)r * K1 + c] = ah;
+    B2ghi[(size_t)r * Hq + c] = bh;
+    if (want_lo) {
+      B1alo[(size_t)r * K1 + c] = to_tf32(a - ah);
+      B2glo[(size_t)r * Hq + c] = to_tf32(b - bh);
+    }
+    if (r == 0) {
+      const bool inr = c < Hp;
+      float w[4] = {0.f, 0.f, 0.f, 0.f}, u[4] = {0.f, 0.f, 0.f, 0.f};
+      if (inr) {
+        const float p1 = P1[c];
+        for (int j = 0; j < d; ++j) { w[j] = A0p[(size_t)c * (d + 1) + j]; u[1 + j] = p1 * A1p[(size_t)c * (d + 1) + j]; }
+        w[3] = A0p[(size_t)c * (d + 1) + d];
+        u[0] = p1;
+      }
+      const int pos = (c & ~15) | ((c & 3) << 2) | ((c >> 2) & 3);                  // unit 16kb+4cc+e -> slot 16kb+4e+cc
+      A0g[pos] = make_float4(w[0], w[1], w[2], w[3]);
+      E1[c] = make_float4(u[0], u[1], u[2], u[3]);
+    }
+  } else {
+    // lin block, column m: m = 3j -> A1w_j hi, 3j+1 -> A1w_j hi, 3j+2 -> A1w_j lo, 3d -> b1 hi, 3d+1 -> b1 lo.
+    // The generator writes (z_j hi, z_j lo, z_j hi, ..., 1, 1): the sum is A1.z + b1 to ~2^-22 relative.
+    const int m = c - Hq;
+    float val = 0.f;
+    if (rin && m < 3 * d + 2) {
+      const int j = m < 3 * d ? m / 3 : d, t = m < 3 * d ? m % 3 : (m - 3 * d == 0 ? 0 : 2);
+      const float x = A1p[(size_t)r * (d + 1) + j];
+      const float xh = to_tf32(x);
+      val = (t == 2) ? to_tf32(x - xh) : xh;
+    }
+    B1ahi[(size_t)r * K1 + c] = val;
+    if (want_lo) B1alo[(size_t)r * K1 + c] = 0.f;
+  }
+}
+// sumV[j] = sum_o E1[o].(y,z,w)[j]  (fixed order: one warp, strided partials then a shuffle tree)
+__global__ void tc3_sumv_kernel(const float4* __restrict__ E1, int Hq, float* __restrict__ sumV) {
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int o = threadIdx.x; o < Hq; o += 32) { const float4 q = E1[o]; s[0] += q.y; s[1] += q.z; s[2] += q.w; }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) s[j] = warp_sum(s[j]);
+  if (threadIdx.x == 0) { sumV[0] = s[0]; sumV[1] = s[1]; sumV[2] = s[2]; sumV[3] = 0.f; }
+}
+
+// ------------------------------------------------------------------------------------ the kernel
+struct alignas(64) Tc3Args {
+  CUtensorMap b1hi, b1lo, b2hi, b2lo;             // boxes of 16 x 128 (this CTA's half of a 256-row B tile)
+  const float* z;
+  const float4 *A0g, *E1, *A0q;
+  const float *sumV, *A2p;
+  float *psi, *xhat;
+  uint32_t* maskg;                                // mask1 of the caller or the internal scratch (null: psi-only, no masks)
+  uint8_t* mask2;
+  float4 *scr1, *scr2;
+  uint32_t* cnt;
+  int B, Hq, T, NP, mask_stride, mask_rows, want_x;
+  float kappa;
+};
+
+template <bool X3>
+struct Tc3Cfg {
+  static constexpr int S = X3 ? 2 : 4;                                    // stages of two 16-wide K-blocks
+  static constexpr int kSubBytes = (X3 ? 4 : 2) * k3TileBytes;            // one K-block: A(hi[,lo]) + B half (hi[,lo])
+  static constexpr int kStageBytes = 2 * kSubBytes;
+  static constexpr int kOffAlo = k3TileBytes, kOffB = (X3 ? 2 : 1) * k3TileBytes, kOffBlo = 3 * k3TileBytes;
+};
+template <bool X3>
+static size_t tc3_smem_bytes(int Hq) {
+  using C = Tc3Cfg<X3>;
+  return (size_t)C::S * C::kStageBytes + (size_t)Hq * 48 + 2 * k3Rows * k3MaskStride * 4 + (2 * C::S + 4) * 8 + 64 + 1024;
+}
+
+struct Unit { int g, t, p; };
+__device__ __forceinline__ Unit decode_unit(int u, int T, int NP) {
+  Unit x;
+  const int per = T * NP;
+  x.g = u >= per ? 1 : 0;
+  const int rem = u - x.g * per;
+  x.t = rem / NP;
+  x.p = rem - x.t * NP;
+  return x;
+}
+
+template <int D, bool X3>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k3Threads, 1)
+icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
+  using C = Tc3Cfg<X3>;
+  constexpr int S = C::S;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* stages = smem;
+  const int Hq = a.Hq;
+  float4* A0gs = reinterpret_cast<float4*>(smem + S * C::kStageBytes);     // generator order
+  float4* E1s = A0gs + Hq;
+  float4* A0qs = E1s + Hq;
+  uint32_t* maskbuf = reinterpret_cast<uint32_t*>(A0qs + Hq);              // [2][128][36]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(maskbuf + 2 * k3Rows * k3MaskStride);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  volatile int* flags = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [0] finalize (epilogue), [1] prefetch ok (generators)
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull0 = smem_u32(bars + 2 * S),
+                 accempty0 = smem_u32(bars + 2 * S + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);     // provably warp-uniform role index
+  const uint32_t rank = cluster_rank3();
+  const int cid = (int)cluster_id3(), G = (int)num_clusters3();
+  const int T = a.T, NP = a.NP, NKB = Hq / kKB;
+  const int U = (a.want_x ? 2 : 1) * T * NP;
+  const uint32_t target = (uint32_t)((a.want_x ? 2 : 1) * NP);
+
+  if (tid == 0) {
+    // full: 4 generator warps x 2 K-blocks x 2 CTAs + the leader's 2 TMA arrivals (one per K-block)
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 16 + 2); mbar_init(empty0 + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(accfull0 + 8 * b, 1); mbar_init(accempty0 + 8 * b, 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 16) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  for (int i = tid; i < Hq; i += k3Threads) { A0gs[i] = a.A0g[i]; E1s[i] = a.E1[i]; A0qs[i] = a.A0q[i]; }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync3();                         // peer barriers initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lead_full0 = mapa3(full0, 0), lead_accempty0 = mapa3(accempty0, 0);
+
+  if (warp_u < 8) {
+    // =========================== epilogue warps: my row, 128 of the unit's 256 columns ===========================
+    const int row = (warp & 3) * 32 + lane, chalf = warp >> 2;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chalf * 128);
+    int i = 0;
+    for (int u = cid; u < U; u += G, ++i) {
+      const Unit un = decode_unit(u, T, NP);
+      const int buf = i & 1;
+      const int grow = un.t * 256 + (int)rank * k3Rows + row;
+      const size_t sidx = ((size_t)grow * NP + un.p) * 2 + chalf;
+      float zr[D];
+      if (un.g) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) zr[j] = grow < a.B ? a.z[(size_t)grow * D + j] : 0.f;
+      }
+      mbar_wait_parked(accfull0 + 8 * buf, (i >> 1) & 1, 2000);
+      tc_fence_after();
+      if (!un.g) {
+        float h2p = 0.f, tp[3] = {0.f, 0.f, 0.f};
+        uint32_t words[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t r[32];
+          tmem_ld32(taddr + buf * 256 + cc * 32, r);
+          tmem_ld_wait();
+          const int nb = un.p * 256 + chalf * 128 + cc * 32;
+          uint32_t word = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float4 q = E1s[nb + j];                       // (P1, P1*A1w0, P1*A1w1, P1*A1w2)
+            const float h1 = __uint_as_float(r[j]);             // affine part included by the lin K-block
+            const bool pos = h1 > 0.f;
+            h2p = fmaf(q.x, fmaxf(h1, kSlope * h1), h2p);       // leaky(h) = max(h, 0.2 h)
+            if (pos) {
+              tp[0] += q.y;
+              if (D > 1) tp[1] += q.z;
+              if (D > 2) tp[2] += q.w;
+              word |= 1u << j;
+            }
+          }
+          words[cc] = word;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(lead_accempty0 + 8 * buf);
+        a.scr1[sidx] = make_float4(h2p, tp[0], tp[1], tp[2]);
+        const int w0 = un.p * 8 + chalf * 4;
+        if (a.maskg != nullptr && grow < a.mask_rows && w0 < a.mask_stride)
+          *reinterpret_cast<uint4*>(a.maskg + (size_t)grow * a.mask_stride + w0) = make_uint4(words[0], words[1], words[2], words[3]);
+      } else {
+        float X[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t r[32];
+          tmem_ld32(taddr + buf * 256 + cc * 32, r);
+          tmem_ld_wait();
+          const int nb = un.p * 256 + chalf * 128 + cc * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float4 q = A0qs[nb + j];
+            const float h0 = lin_of<D>(q, zr);
+            const float f0 = fmaxf(h0, (kSlope * kSlope) * h0);   // a0*s0 = h0*s0^2
+            const float wv = f0 * __uint_as_float(r[j]);
+#pragma unroll
+            for (int jj = 0; jj < D; ++jj) X[jj] = fmaf(comp(q, jj), wv, X[jj]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(lead_accempty0 + 8 * buf);
+        a.scr2[sidx] = make_float4(X[0], X[1], X[2], 0.f);
+      }
+      // ---- publish the unit; the last unit of this (tile, rank) combines all partials in a fixed order ----
+      __threadfence();
+      bar_epi();
+      uint32_t* cp = a.cnt + (un.t * 2 + (int)rank);
+      if (tid == 0) flags[0] = (atomicAdd(cp, 1u) + 1u == target) ? 1 : 0;
+      bar_epi();
+      if (flags[0]) {
+        __threadfence();
+        if (tid < k3Rows) {
+          const int fr = un.t * 256 + (int)rank * k3Rows + tid;
+          if (fr < a.B) {
+            float zf[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) zf[j] = a.z[(size_t)fr * D + j];
+            float h2 = 0.f, tp[3] = {0.f, 0.f, 0.f}, X[3] = {0.f, 0.f, 0.f};
+            for (int q = 0; q < 2 * NP; ++q) {
+              const float4 s1 = __ldcg(a.scr1 + (size_t)fr * NP * 2 + q);
+              h2 += s1.x; tp[0] += s1.y; tp[1] += s1.z; tp[2] += s1.w;
+            }
+            float lin = a.A2p[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) lin = fmaf(a.A2p[j], zf[j], lin);
+            h2 += lin;
+            const bool pos2 = h2 > 0.f;
+            const float s2 = pos2 ? 1.f : kSlope;
+            if (a.psi) a.psi[fr] = pos2 ? h2 : kSlope * h2;
+            if (a.mask2) a.mask2[fr] = pos2 ? 1 : 0;
+            if (a.want_x) {
+              for (int q = 0; q < 2 * NP; ++q) {
+                const float4 s2v = __ldcg(a.scr2 + (size_t)fr * NP * 2 + q);
+                X[0] += s2v.x; X[1] += s2v.y; X[2] += s2v.z;
+              }
+#pragma unroll
+              for (int j = 0; j < D; ++j) {
+                // xhat = A0^T g0 + A1^T g1 + s2 A2 + 2 kappa z;  g1 = s2 P1 (0.2 + 0.8 bit),  A0^T g0 = 2 s2 X
+                const float a1 = fmaf(0.8f, tp[j], kSlope * a.sumV[j]);
+                const float inner = fmaf(2.f, X[j], a1) + a.A2p[j];
+                a.xhat[(size_t)fr * D + j] = fmaf(2.f * a.kappa, zf[j], s2 * inner);
+              }
+            }
+          }
+        }
+        if (tid == 0) *cp = 0u;                               // leave the counter ready for the next launch
+      }
+    }
+  } else if (warp_u < 16) {
+    // =========================== generator warps: A tiles for every K-block ===========================
+    // thread = (16-byte chunk c of 4 consecutive k, base row rb): it writes its chunk of rows rb, rb+32, rb+64, rb+96;
+    // group kh (warps 8-11 / 12-15) fills K-block kh of every stage, so each group has two block-times per block
+    const int t2 = tid - 256, kh = t2 >> 7, c = t2 & 3, rb = (t2 >> 2) & 31;
+    const uint32_t goff = (uint32_t)rb * 64u + ((uint32_t)(c ^ ((rb >> 1) & 3)) << 4);
+    uint32_t it = 0;                                           // K-blocks since kernel start (same sequence in every role)
+    int n2 = 0;                                                // GEMM2 units seen (mask buffer parity)
+    bool prefetched = false;
+    auto stage_ptr = [&](uint32_t itv) { return stages + ((itv >> 1) % S) * C::kStageBytes + (itv & 1) * C::kSubBytes + goff; };
+    auto wait_slot = [&](uint32_t itv) { mbar_wait(empty0 + 8 * ((itv >> 1) % S), (((itv >> 1) / S) & 1) ^ 1); };
+    auto publish = [&](uint32_t itv) {
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(lead_full0 + 8 * ((itv >> 1) % S));
+    };
+    auto load_masks = [&](int tile, int mb) {                  // 128 rows x Hq/32 words -> maskbuf[mb] (cp.async, 16 B chunks)
+      const int cpr = Hq / 128;                                // 16-byte chunks per row
+      uint32_t* dst0 = maskbuf + mb * (k3Rows * k3MaskStride);
+      for (int id = t2; id < k3Rows * cpr; id += 256) {
+        const int r = id / cpr, ch = id - r * cpr;
+        const int gr = tile * 256 + (int)rank * k3Rows + r;
+        uint32_t* dst = dst0 + r * k3MaskStride + ch * 4;
+        if (gr < a.mask_rows && ch * 4 < a.mask_stride) cp_async16(dst, a.maskg + (size_t)gr * a.mask_stride + ch * 4);
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      cp_async_commit();
+    };
+    for (int u = cid; u < U; u += G) {
+      const Unit un = decode_unit(u, T, NP);
+      const int m0 = un.t * 256 + (int)rank * k3Rows;
+      if (!un.g) {
+        // ---------------- GEMM1: x1 = leaky(A0 z + b0)^2, then the lin block (z hi/lo, 1, 1) ----------------
+        float z4[4][D];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int j = 0; j < D; ++j) z4[r][j] = (m0 + rb + 32 * r < a.B) ? a.z[(size_t)(m0 + rb + 32 * r) * D + j] : 0.f;
+        float2 zp[2][D];
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+          for (int j = 0; j < D; ++j) zp[pr][j] = make_float2(z4[2 * pr][j], z4[2 * pr + 1][j]);
+        for (int kb = 0; kb < NKB; ++kb, ++it) {
+          if ((int)(it & 1) != kh) continue;
+          float v[4][4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 q = A0gs[kb * kKB + e * 4 + c];
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+              float2 h = __ffma2_rn(make_float2(q.x, q.x), zp[pr][0], make_float2(q.w, q.w));
+              if (D > 1) h = __ffma2_rn(make_float2(q.y, q.y), zp[pr][D > 1 ? 1 : 0], h);
+              if (D > 2) h = __ffma2_rn(make_float2(q.z, q.z), zp[pr][D > 2 ? 2 : 0], h);
+              const float2 l = __fmul2_rn(h, make_float2(kSlope, kSlope));
+              const float2 a0 = make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y));
+              const float2 x = __fmul2_rn(a0, a0);
+              v[2 * pr][e] = x.x; v[2 * pr + 1][e] = x.y;
+            }
+          }
+          wait_slot(it);
+          unsigned char* At = stage_ptr(it);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            if (X3) {
+              const float4 hi = make_float4(rn_tf32_masked(v[r][0]), rn_tf32_masked(v[r][1]), rn_tf32_masked(v[r][2]), rn_tf32_masked(v[r][3]));
+              *reinterpret_cast<float4*>(At + r * 2048) = hi;
+              *reinterpret_cast<float4*>(At + C::kOffAlo + r * 2048) =
+                  make_float4(rn_tf32_fast(v[r][0] - hi.x), rn_tf32_fast(v[r][1] - hi.y), rn_tf32_fast(v[r][2] - hi.z), rn_tf32_fast(v[r][3] - hi.w));
+            } else {
+              *reinterpret_cast<float4*>(At + r * 2048) =
+                  make_float4(rn_tf32_fast(v[r][0]), rn_tf32_fast(v[r][1]), rn_tf32_fast(v[r][2]), rn_tf32_fast(v[r][3]));
+            }
+          }
+          publish(it);
+        }
+        // lin block (kb = NKB) and the dummy that keeps the unit's block count even (kb = NKB + 1: arrive only)
+        for (int x = 0; x < 2; ++x, ++it) {
+          if ((int)(it & 1) != kh) continue;
+          wait_slot(it);
+          if (x == 0) {
+            unsigned char* At = stage_ptr(it);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              float col[16];
+#pragma unroll
+              for (int m = 0; m < 16; ++m) col[m] = 0.f;
+#pragma unroll
+              for (int j = 0; j < D; ++j) {
+                const float zh = rn_tf32_masked(z4[r][j]);
+                col[3 * j] = zh; col[3 * j + 1] = rn_tf32_masked(z4[r][j] - zh); col[3 * j + 2] = zh;
+              }
+              col[3 * D] = 1.f; col[3 * D + 1] = 1.f;
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc)
+                if (cc == c) {
+                  *reinterpret_cast<float4*>(At + r * 2048) = make_float4(col[4 * cc], col[4 * cc + 1], col[4 * cc + 2], col[4 * cc + 3]);
+                  if (X3) *reinterpret_cast<float4*>(At + C::kOffAlo + r * 2048) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+          }
+          publish(it);
+        }
+      } else {
+        // ---------------- GEMM2: A = 1 + 4*bit (LeakyReLU slope / 0.2), exact in tf32 ----------------
+        const int mb = n2 & 1;
+        ++n2;
+        if (!prefetched) {
+          if (t2 == 0) {
+            const uint32_t* cp = a.cnt + (un.t * 2 + (int)rank);
+            while (ld_acquire_u32(cp) < (uint32_t)NP) {}       // all GEMM1 passes of this tile have published their bits
+          }
+          bar_gen();
+          load_masks(un.t, mb);
+        }
+        cp_async_wait_all();
+        if (t2 == 0) {                                         // can the next unit's bits be fetched while this one runs?
+          int ok = 0;
+          if (u + G < U) {
+            const Unit nx = decode_unit(u + G, T, NP);
+            ok = (nx.g && ld_acquire_u32(a.cnt + (nx.t * 2 + (int)rank)) >= (uint32_t)NP) ? 1 : 0;
+          }
+          flags[1] = ok;
+        }
+        bar_gen();                                             // masks of this unit visible; flags[1] valid
+        prefetched = flags[1] != 0;
+        if (prefetched) load_masks(decode_unit(u + G, T, NP).t, mb ^ 1);
+        const uint32_t* mrow = maskbuf + mb * (k3Rows * k3MaskStride) + rb * k3MaskStride;
+        for (int kb = 0; kb < NKB; ++kb, ++it) {
+          if ((int)(it & 1) != kh) continue;
+          uint32_t w4[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) w4[r] = mrow[r * 32 * k3MaskStride + (kb >> 1)] >> ((kb & 1) * 16 + c * 4);
+          wait_slot(it);
+          unsigned char* At = stage_ptr(it);
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            *reinterpret_cast<float4*>(At + r * 2048) =
+                make_float4((w4[r] & 1u) ? 5.f : 1.f, (w4[r] & 2u) ? 5.f : 1.f, (w4[r] & 4u) ? 5.f : 1.f, (w4[r] & 8u) ? 5.f : 1.f);
+          publish(it);
+        }
+        bar_gen();                                             // everybody is done with maskbuf[mb] before it is refilled
+      }
+    }
+    cp_async_wait_all();
+  } else if (warp_u == 16) {
+    // =========================== TMA producer: this CTA's half of every B tile ===========================
+    // The whole warp walks the loop converged (warp-uniform state); one elected lane issues.
+    uint32_t it = 0;
+    for (int u = cid; u < U; u += G) {
+      const Unit un = decode_unit(u, T, NP);
+      const CUtensorMap* mhi = un.g ? &a.b2hi : &a.b1hi;
+      const CUtensorMap* mlo = un.g ? &a.b2lo : &a.b1lo;
+      const int nreal = un.g ? NKB : NKB + 1, npad = (nreal + 1) & ~1;
+      const int rowc = un.p * 256 + (int)rank * k3Rows;
+      for (int kb = 0; kb < npad; kb += 2, it += 2) {                  // one stage = two K-blocks
+        const uint32_t s = (it >> 1) % S, ph = ((it >> 1) / S) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const bool real1 = kb + 1 < nreal;
+        if (elect_one()) {
+          const uint32_t bar = lead_full0 + 8 * s;
+          if (rank == 0) {                                              // expect both CTAs' halves of the stage
+            mbar_arrive_expect_tx(full0 + 8 * s, 2 * (X3 ? 2 : 1) * k3TileBytes);
+            if (real1) mbar_arrive_expect_tx(full0 + 8 * s, 2 * (X3 ? 2 : 1) * k3TileBytes);
+            else mbar_arrive(full0 + 8 * s);
+          }
+          const uint32_t dst = smem_u32(stages + s * C::kStageBytes);
+          tma_load_2d_pair(dst + C::kOffB, mhi, bar, kb * kKB, rowc);
+          if (X3) tma_load_2d_pair(dst + C::kOffBlo, mlo, bar, kb * kKB, rowc);
+          if (real1) {
+            tma_load_2d_pair(dst + C::kSubBytes + C::kOffB, mhi, bar, (kb + 1) * kKB, rowc);
+            if (X3) tma_load_2d_pair(dst + C::kSubBytes + C::kOffBlo, mlo, bar, (kb + 1) * kKB, rowc);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (rank == 0) {
+    // =========================== MMA issuer (leader CTA only) ===========================
+    // Converged warp, one elected lane issues.  Descriptors advance by constants: +2 (32 B) per K=8 step,
+    // +kSubBytes/16 per K-block, +kStageBytes/16 per stage.
+    const uint64_t descA0 = make_desc_sw64(smem_u32(stages));
+    uint32_t it = 0;
+    int i = 0;
+    for (int u = cid; u < U; u += G, ++i) {
+      const Unit un = decode_unit(u, T, NP);
+      const int buf = i & 1;
+      const int nreal = un.g ? NKB : NKB + 1, npad = (nreal + 1) & ~1;
+      mbar_wait(accempty0 + 8 * buf, ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_t = tmem_base + (uint32_t)(buf * 256);
+      for (int kb = 0; kb < npad; kb += 2, it += 2) {
+        const uint32_t s = (it >> 1) % S, ph = ((it >> 1) / S) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a0 = descA0 + (uint64_t)(s * (C::kStageBytes >> 4));
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            if (sub == 1 && kb + 1 >= nreal) break;                     // dummy block of a GEMM1 unit
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t a_hi = a0 + (uint64_t)(sub * (C::kSubBytes >> 4) + ks * 2);
+              const uint64_t b_hi = a_hi + (uint64_t)(C::kOffB >> 4);
+              const uint32_t acc = (kb | sub | ks) ? 1u : 0u;
+              if (X3) {
+                const uint64_t b_lo = a_hi + (uint64_t)(C::kOffBlo >> 4);
+                if (!un.g) {                                            // GEMM2's A operand is exact: no a_lo term
+                  umma_tf32_pair(d_t, a_hi + (uint64_t)(C::kOffAlo >> 4), b_hi, acc);
+                  umma_tf32_pair(d_t, a_hi, b_lo, 1u);
+                } else {
+                  umma_tf32_pair(d_t, a_hi, b_lo, acc);
+                }
+                umma_tf32_pair(d_t, a_hi, b_hi, 1u);
+              } else {
+                umma_tf32_pair(d_t, a_hi, b_hi, acc);
+              }
+            }
+          }
+          umma_commit_pair(empty0 + 8 * s);                             // frees the stage in both CTAs
+          if (kb + 2 >= npad) umma_commit_pair(accfull0 + 8 * buf);     // unit complete
+        }
+        __syncwarp();
+      }
+    }
+  }
+  // teardown: nobody may leave (or free TMEM) while the peer can still touch this CTA's smem / TMEM
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync3();
+  if (warp == 16) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_map3(CUtensorMap* m, const float* base, int K, int rows) {
+  static EncodeTiledFn3 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p)
+      fn = reinterpret_cast<EncodeTiledFn3>(p);
+  }
+  if (!fn) return B200VAE_ECUDA;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)k3Rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_last_cuda_error = 100000 + (int)r; return B200VAE_ECUDA; }
+  return B200VAE_OK;
+}
+
+int tc3_prepare(int d, int H, int precision, float* ws, cudaStream_t st) {
+  if (d > 3) return B200VAE_EUNSUP;
+  const WsLayout L = ws_layout(1, d, H);
+  const TcLayout T = tc_layout(d, H);
+  const Tc3Layout T3 = tc3_layout(1, d, H);
+  float* t3 = tc_base(ws, d, H) + T.end;
+  const int want_lo = precision == B200VAE_PREC_TF32X3 ? 1 : 0;
+  dim3 grid((T3.K1 + 255) / 256, T3.Hq);
+  tc3_prepare_kernel<<<grid, 256, 0, st>>>(ws + L.P0, ws + L.P0T, ws + L.P1, ws + L.A0p, ws + L.A1p, d, L.Hp, T3.Hq, T3.K1,
+                                           want_lo, t3 + T3.B1ahi, t3 + T3.B1alo, t3 + T3.B2ghi, t3 + T3.B2glo,
+                                           reinterpret_cast<float4*>(t3 + T3.A0g), reinterpret_cast<float4*>(t3 + T3.E1));
+  int rc = check_launch();
+  if (rc) return rc;
+  tc3_sumv_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const float4*>(t3 + T3.E1), T3.Hq, t3 + T3.sumV);
+  rc = check_launch();
+  if (rc) return rc;
+  if (cudaMemsetAsync(t3 + T3.cnt, 0, (size_t)2 * kTc3MaxTiles * sizeof(uint32_t), st) != cudaSuccess) return B200VAE_ECUDA;
+  return B200VAE_OK;
+}
+
+template <int D, bool X3>
+static int launch_tc3(const Tc3Args& args, int units, cudaStream_t st) {
+  const size_t smem = tc3_smem_bytes<X3>(args.Hq);
+  if (smem > 227 * 1024) return B200VAE_EUNSUP;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cudaFuncSetAttribute(icnn_tc3_fwd_kernel<D, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(k3Threads); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, icnn_tc3_fwd_kernel<D, X3>, &cfg) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      n = sm_count() / 2;
+    }
+    max_clusters = n;
+  }
+  // every cluster must be resident (GEMM2 units wait for GEMM1 units of other clusters): never exceed one wave
+  const int G = units < max_clusters ? units : max_clusters;
+  icnn_tc3_fwd_kernel<D, X3><<<2 * G, k3Threads, smem, st>>>(args);
+  return check_launch();
+}
+
+int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2,
+            int precision, float* ws, cudaStream_t st) {
+  if (precision == B200VAE_PREC_BF16 || d > 3) return B200VAE_EUNSUP;
+  const WsLayout L = ws_layout(1, d, H);
+  const TcLayout T = tc_layout(d, H);
+  const Tc3Layout T3 = tc3_layout(B, d, H);
+  if (T3.Bp / 256 > kTc3MaxTiles) return B200VAE_EUNSUP;
+  float* tb = tc_base(ws, d, H);
+  float* t3 = tb + T.end;
+  const bool x3 = (precision == B200VAE_PREC_TF32X3);
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, Tc3Args> cache;       // tensor maps only encode (address, shape)
+  Tc3Args args;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    const uint64_t key = reinterpret_cast<uint64_t>(t3) ^ ((uint64_t)T3.Hq << 48) ^ ((uint64_t)x3 << 63);
+    auto itc = cache.find(key);
+    if (itc == cache.end()) {
+      int rc = make_map3(&args.b1hi, t3 + T3.B1ahi, T3.K1, T3.Hq);
+      if (!rc) rc = make_map3(&args.b1lo, t3 + (x3 ? T3.B1alo : T3.B1ahi), T3.K1, T3.Hq);
+      if (!rc) rc = make_map3(&args.b2hi, t3 + T3.B2ghi, T3.Hq, T3.Hq);
+      if (!rc) rc = make_map3(&args.b2lo, t3 + (x3 ? T3.B2glo : T3.B2ghi), T3.Hq, T3.Hq);
+      if (rc) return rc;
+      if (cache.size() > 256) cache.clear();
+      cache.emplace(key, args);
+    } else {
+      args = itc->second;
+    }
+  }
+  args.z = z;
+  args.A0g = reinterpret_cast<const float4*>(t3 + T3.A0g);
+  args.E1 = reinterpret_cast<const float4*>(t3 + T3.E1);
+  args.A0q = reinterpret_cast<const float4*>(tb + T.A0q);
+  args.sumV = t3 + T3.sumV;
+  args.A2p = ws + L.A2p;
+  args.psi = psi; args.xhat = xhat; args.mask2 = mask2;
+  args.want_x = xhat != nullptr ? 1 : 0;
+  if (mask1) { args.maskg = mask1; args.mask_stride = L.Hp / 32; args.mask_rows = B; }
+  else if (args.want_x) { args.maskg = reinterpret_cast<uint32_t*>(t3 + T3.imask); args.mask_stride = T3.Hq / 32; args.mask_rows = T3.Bp; }
+  else { args.maskg = nullptr; args.mask_stride = 0; args.mask_rows = 0; }
+  args.scr1 = reinterpret_cast<float4*>(t3 + T3.scr1);
+  args.scr2 = reinterpret_cast<float4*>(t3 + T3.scr2);
+  args.cnt = reinterpret_cast<uint32_t*>(t3 + T3.cnt);
+  args.B = B; args.Hq = T3.Hq; args.T = T3.Bp / 256; args.NP = T3.NP; args.kappa = kappa;
+  const int units = (args.want_x ? 2 : 1) * args.T * args.NP;
+#define B200VAE_TC3(DD) return x3 ? launch_tc3<DD, true>(args, units, st) : launch_tc3<DD, false>(args, units, st)
+  switch (d) {
+    case 1: B200VAE_TC3(1);
+    case 2: B200VAE_TC3(2);
+    case 3: B200VAE_TC3(3);
+    default: return B200VAE_EUNSUP;
+  }
+#undef B200VAE_TC3
+}
+
+}  // namespace b200vae

@@ -35,6 +35,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// long waits (epilogue warps waiting for a whole accumulator pass): let the hardware park the warp for up to
+// `ns` nanoseconds per try instead of re-issuing the poll every few dozen cycles next to the MMA-issuing warp
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+  } while (!ok);
+}
+// one lane of a CONVERGED warp (CUTLASS elect_one_sync): inside `if (elect_one())` the compiler knows a single lane
+// is active, so the uniform-register operands of UTCHMMA / UTMALDG need no ELECT + R2UR.BROADCAST retry loops
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -108,6 +127,42 @@ inline float* tc_base(float* ws, int d, int H) {
   return ws + ws_layout(1, d, H).fwd_end;
 }
 
+
+// ------------------------------------------------------------------------------------ persistent pair kernel (icnn_tc3.cu)
+// Placed after the TcLayout arrays (floats from tc_base + TcLayout::end).  K1 = Hq + 16: GEMM1's B operand carries one
+// extra 16-wide K-block holding A1/b1 (split hi/lo) so that the affine part of h1 is accumulated by the tensor core.
+//   B1a hi,lo [Hq][K1]   B1a[o][i] = P[o][i] (i < Hq);  B1a[o][Hq + m] = lin-block column m (see tc3_prepare_kernel)
+//   B2g hi,lo [Hq][Hq]   B2g[i][o] = 0.2 * P1[o] * P[o][i]        (GEMM2: A operand = 1 + 4*maskbit, exact in tf32)
+//   A0g float4[Hq]       (A0w0, A0w1, A0w2, A0b) in generator order: unit 16*kb + 4*c + e sits at 16*kb + 4*e + c
+//   E1  float4[Hq]       (P1[o], P1[o]*A1w[o][0..2])
+//   sumV [4]             sum_o P1[o]*A1w[o][j]
+//   cnt  [2*kTc3MaxTiles] u32 per-(tile, cta rank) unit counters: zeroed by prepare, left zero by every launch
+//   -- B dependent --
+//   scr1 float4 [Bp][NP][2]  (h2 partial, tpos_0..2) per (row, pass, column half);  scr2 float4 same shape (X_0..2)
+//   imask u32 [Bp][Hq/32]    LeakyReLU bits of h1 when the caller does not ask for mask1
+constexpr int kTc3MaxTiles = 16384;
+struct Tc3Layout {
+  int Hq, K1, NP, Bp;
+  size_t B1ahi, B1alo, B2ghi, B2glo, A0g, E1, sumV, cnt, fixed_end, scr1, scr2, imask, end;
+};
+inline Tc3Layout tc3_layout(int B, int d, int H) {
+  (void)d;
+  Tc3Layout T;
+  T.Hq = round_up(H, 256); T.K1 = T.Hq + 16; T.NP = T.Hq / 256; T.Bp = round_up(B, 256);
+  auto up = [](size_t x) { return (x + 63) / 64 * 64; };
+  size_t o = 0;
+  T.B1ahi = o; o += up((size_t)T.Hq * T.K1); T.B1alo = o; o += up((size_t)T.Hq * T.K1);
+  T.B2ghi = o; o += up((size_t)T.Hq * T.Hq); T.B2glo = o; o += up((size_t)T.Hq * T.Hq);
+  T.A0g = o; o += (size_t)4 * T.Hq; T.E1 = o; o += (size_t)4 * T.Hq;
+  T.sumV = o; o += 64;
+  T.cnt = o; o += (size_t)2 * kTc3MaxTiles;
+  T.fixed_end = o;
+  T.scr1 = o; o += (size_t)T.Bp * T.NP * 2 * 4;
+  T.scr2 = o; o += (size_t)T.Bp * T.NP * 2 * 4;
+  T.imask = o; o += (size_t)T.Bp * (T.Hq / 32);
+  T.end = o + 64;
+  return T;
+}
 
 template <int D>
 __device__ __forceinline__ float lin_of(const float4 q, const float (&z)[D]) {
