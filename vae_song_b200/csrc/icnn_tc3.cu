@@ -207,8 +207,8 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
   const uint32_t target = (uint32_t)((a.want_x ? 2 : 1) * NP);
 
   if (tid == 0) {
-    // full: 4 generator warps x 2 K-blocks x 2 CTAs + the leader's 2 TMA arrivals (one per K-block)
-    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 16 + 2); mbar_init(empty0 + 8 * s, 1); }
+    // full: 4 generator warps (one group owns a whole stage) x 2 CTAs + the leader's 2 TMA arrivals (one per K-block)
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 8 + 2); mbar_init(empty0 + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(accfull0 + 8 * b, 1); mbar_init(accempty0 + 8 * b, 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -342,20 +342,21 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
       }
     }
   } else if (warp_u < 16) {
-    // =========================== generator warps: A tiles for every K-block ===========================
-    // thread = (16-byte chunk c of 4 consecutive k, base row rb): it writes its chunk of rows rb, rb+32, rb+64, rb+96;
-    // group kh (warps 8-11 / 12-15) fills K-block kh of every stage, so each group has two block-times per block
+    // =========================== generator warps: A tiles for every stage ===========================
+    // thread = (16-byte chunk c of 4 consecutive k, base row rb): it writes its chunk of rows rb, rb+32, rb+64, rb+96 of
+    // BOTH K-blocks of a stage; the two groups (warps 8-11 / 12-15) take alternate stages, so each has two stage-times
+    // per stage and pays one proxy fence + one barrier arrival per 32 generated elements.
     const int t2 = tid - 256, kh = t2 >> 7, c = t2 & 3, rb = (t2 >> 2) & 31;
     const uint32_t goff = (uint32_t)rb * 64u + ((uint32_t)(c ^ ((rb >> 1) & 3)) << 4);
-    uint32_t it = 0;                                           // K-blocks since kernel start (same sequence in every role)
+    uint32_t stg = 0;                                          // stages since kernel start (same sequence in every role)
     int n2 = 0;                                                // GEMM2 units seen (mask buffer parity)
     bool prefetched = false;
-    auto stage_ptr = [&](uint32_t itv) { return stages + ((itv >> 1) % S) * C::kStageBytes + (itv & 1) * C::kSubBytes + goff; };
-    auto wait_slot = [&](uint32_t itv) { mbar_wait(empty0 + 8 * ((itv >> 1) % S), (((itv >> 1) / S) & 1) ^ 1); };
-    auto publish = [&](uint32_t itv) {
+    auto stage_ptr = [&](uint32_t sg) { return stages + (sg % S) * C::kStageBytes + goff; };
+    auto wait_stage = [&](uint32_t sg) { mbar_wait(empty0 + 8 * (sg % S), ((sg / S) & 1) ^ 1); };
+    auto publish = [&](uint32_t sg) {
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(lead_full0 + 8 * ((itv >> 1) % S));
+      if (lane == 0) mbar_arrive_remote(lead_full0 + 8 * (sg % S));
     };
     auto load_masks = [&](int tile, int mb) {                  // 128 rows x Hq/32 words -> maskbuf[mb] (cp.async, 16 B chunks)
       const int cpr = Hq / 128;                                // 16-byte chunks per row
@@ -369,6 +370,7 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
       }
       cp_async_commit();
     };
+    const int NST = NKB / 2;                                   // full stages per unit
     for (int u = cid; u < U; u += G) {
       const Unit un = decode_unit(u, T, NP);
       const int m0 = un.t * 256 + (int)rank * k3Rows;
@@ -384,66 +386,71 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
         for (int pr = 0; pr < 2; ++pr)
 #pragma unroll
           for (int j = 0; j < D; ++j) zp[pr][j] = make_float2(z4[2 * pr][j], z4[2 * pr + 1][j]);
-        for (int kb = 0; kb < NKB; ++kb, ++it) {
-          if ((int)(it & 1) != kh) continue;
-          float v[4][4];
+        int st = (int)((stg ^ (uint32_t)kh) & 1u);             // my first stage of this unit
+        for (; st < NST; st += 2) {
+          float v[2][4][4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float4 q = A0gs[kb * kKB + e * 4 + c];
+          for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
-            for (int pr = 0; pr < 2; ++pr) {
-              float2 h = __ffma2_rn(make_float2(q.x, q.x), zp[pr][0], make_float2(q.w, q.w));
-              if (D > 1) h = __ffma2_rn(make_float2(q.y, q.y), zp[pr][D > 1 ? 1 : 0], h);
-              if (D > 2) h = __ffma2_rn(make_float2(q.z, q.z), zp[pr][D > 2 ? 2 : 0], h);
-              const float2 l = __fmul2_rn(h, make_float2(kSlope, kSlope));
-              const float2 a0 = make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y));
-              const float2 x = __fmul2_rn(a0, a0);
-              v[2 * pr][e] = x.x; v[2 * pr + 1][e] = x.y;
+            for (int e = 0; e < 4; ++e) {
+              const float4 q = A0gs[(2 * st + sub) * kKB + e * 4 + c];
+#pragma unroll
+              for (int pr = 0; pr < 2; ++pr) {
+                float2 h = __ffma2_rn(make_float2(q.x, q.x), zp[pr][0], make_float2(q.w, q.w));
+                if (D > 1) h = __ffma2_rn(make_float2(q.y, q.y), zp[pr][D > 1 ? 1 : 0], h);
+                if (D > 2) h = __ffma2_rn(make_float2(q.z, q.z), zp[pr][D > 2 ? 2 : 0], h);
+                const float2 l = __fmul2_rn(h, make_float2(kSlope, kSlope));
+                const float2 a0 = make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y));
+                const float2 x = __fmul2_rn(a0, a0);
+                v[sub][2 * pr][e] = x.x; v[sub][2 * pr + 1][e] = x.y;
+              }
             }
-          }
-          wait_slot(it);
-          unsigned char* At = stage_ptr(it);
+          wait_stage(stg + st);
+          unsigned char* At = stage_ptr(stg + st);
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            if (X3) {
-              const float4 hi = make_float4(rn_tf32_masked(v[r][0]), rn_tf32_masked(v[r][1]), rn_tf32_masked(v[r][2]), rn_tf32_masked(v[r][3]));
-              *reinterpret_cast<float4*>(At + r * 2048) = hi;
-              *reinterpret_cast<float4*>(At + C::kOffAlo + r * 2048) =
-                  make_float4(rn_tf32_fast(v[r][0] - hi.x), rn_tf32_fast(v[r][1] - hi.y), rn_tf32_fast(v[r][2] - hi.z), rn_tf32_fast(v[r][3] - hi.w));
-            } else {
-              *reinterpret_cast<float4*>(At + r * 2048) =
-                  make_float4(rn_tf32_fast(v[r][0]), rn_tf32_fast(v[r][1]), rn_tf32_fast(v[r][2]), rn_tf32_fast(v[r][3]));
-            }
-          }
-          publish(it);
-        }
-        // lin block (kb = NKB) and the dummy that keeps the unit's block count even (kb = NKB + 1: arrive only)
-        for (int x = 0; x < 2; ++x, ++it) {
-          if ((int)(it & 1) != kh) continue;
-          wait_slot(it);
-          if (x == 0) {
-            unsigned char* At = stage_ptr(it);
+          for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-              float col[16];
-#pragma unroll
-              for (int m = 0; m < 16; ++m) col[m] = 0.f;
-#pragma unroll
-              for (int j = 0; j < D; ++j) {
-                const float zh = rn_tf32_masked(z4[r][j]);
-                col[3 * j] = zh; col[3 * j + 1] = rn_tf32_masked(z4[r][j] - zh); col[3 * j + 2] = zh;
+              unsigned char* dst = At + sub * C::kSubBytes + r * 2048;
+              if (X3) {
+                const float4 hi = make_float4(rn_tf32_masked(v[sub][r][0]), rn_tf32_masked(v[sub][r][1]),
+                                              rn_tf32_masked(v[sub][r][2]), rn_tf32_masked(v[sub][r][3]));
+                *reinterpret_cast<float4*>(dst) = hi;
+                *reinterpret_cast<float4*>(dst + C::kOffAlo) =
+                    make_float4(rn_tf32_fast(v[sub][r][0] - hi.x), rn_tf32_fast(v[sub][r][1] - hi.y),
+                                rn_tf32_fast(v[sub][r][2] - hi.z), rn_tf32_fast(v[sub][r][3] - hi.w));
+              } else {
+                *reinterpret_cast<float4*>(dst) = make_float4(rn_tf32_fast(v[sub][r][0]), rn_tf32_fast(v[sub][r][1]),
+                                                              rn_tf32_fast(v[sub][r][2]), rn_tf32_fast(v[sub][r][3]));
               }
-              col[3 * D] = 1.f; col[3 * D + 1] = 1.f;
-#pragma unroll
-              for (int cc = 0; cc < 4; ++cc)
-                if (cc == c) {
-                  *reinterpret_cast<float4*>(At + r * 2048) = make_float4(col[4 * cc], col[4 * cc + 1], col[4 * cc + 2], col[4 * cc + 3]);
-                  if (X3) *reinterpret_cast<float4*>(At + C::kOffAlo + r * 2048) = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
             }
-          }
-          publish(it);
+          publish(stg + st);
         }
+        if (st == NST) {
+          // last stage of the unit: the lin block in K-block 0; K-block 1 is a dummy the MMA warp skips
+          wait_stage(stg + st);
+          unsigned char* At = stage_ptr(stg + st);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            float col[16];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) col[m] = 0.f;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+              const float zh = rn_tf32_masked(z4[r][j]);
+              col[3 * j] = zh; col[3 * j + 1] = rn_tf32_masked(z4[r][j] - zh); col[3 * j + 2] = zh;
+            }
+            col[3 * D] = 1.f; col[3 * D + 1] = 1.f;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              if (cc == c) {
+                *reinterpret_cast<float4*>(At + r * 2048) = make_float4(col[4 * cc], col[4 * cc + 1], col[4 * cc + 2], col[4 * cc + 3]);
+                if (X3) *reinterpret_cast<float4*>(At + C::kOffAlo + r * 2048) = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+          }
+          publish(stg + st);
+        }
+        stg += NST + 1;
       } else {
         // ---------------- GEMM2: A = 1 + 4*bit (LeakyReLU slope / 0.2), exact in tf32 ----------------
         const int mb = n2 & 1;
@@ -469,19 +476,23 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
         prefetched = flags[1] != 0;
         if (prefetched) load_masks(decode_unit(u + G, T, NP).t, mb ^ 1);
         const uint32_t* mrow = maskbuf + mb * (k3Rows * k3MaskStride) + rb * k3MaskStride;
-        for (int kb = 0; kb < NKB; ++kb, ++it) {
-          if ((int)(it & 1) != kh) continue;
-          uint32_t w4[4];
+        for (int st = (int)((stg ^ (uint32_t)kh) & 1u); st < NST; st += 2) {
+          uint32_t w4[4];                                      // word st of my 4 rows: bits of K-blocks 2st (low half), 2st+1
 #pragma unroll
-          for (int r = 0; r < 4; ++r) w4[r] = mrow[r * 32 * k3MaskStride + (kb >> 1)] >> ((kb & 1) * 16 + c * 4);
-          wait_slot(it);
-          unsigned char* At = stage_ptr(it);
+          for (int r = 0; r < 4; ++r) w4[r] = mrow[r * 32 * k3MaskStride + st] >> (c * 4);
+          wait_stage(stg + st);
+          unsigned char* At = stage_ptr(stg + st);
 #pragma unroll
-          for (int r = 0; r < 4; ++r)
-            *reinterpret_cast<float4*>(At + r * 2048) =
-                make_float4((w4[r] & 1u) ? 5.f : 1.f, (w4[r] & 2u) ? 5.f : 1.f, (w4[r] & 4u) ? 5.f : 1.f, (w4[r] & 8u) ? 5.f : 1.f);
-          publish(it);
+          for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const uint32_t w = w4[r] >> (16 * sub);
+              *reinterpret_cast<float4*>(At + sub * C::kSubBytes + r * 2048) =
+                  make_float4((w & 1u) ? 5.f : 1.f, (w & 2u) ? 5.f : 1.f, (w & 4u) ? 5.f : 1.f, (w & 8u) ? 5.f : 1.f);
+            }
+          publish(stg + st);
         }
+        stg += NST;
         bar_gen();                                             // everybody is done with maskbuf[mb] before it is refilled
       }
     }
