@@ -15,6 +15,7 @@
 // warp 8 TMA producer + TMEM allocator, warp 9 MMA issuer (one elected lane).
 // Precisions: TF32 (kind::tf32, operands rounded-to-nearest to tf32) and 3xTF32
 // (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulate in TMEM: fp32-grade accuracy).
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -140,7 +141,8 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
   }
 }
 
-// TMA producer: for each GEMM g (maps hi[g]/lo[g]) stream NP x NKB B tiles through the stage ring
+// TMA producer: for each GEMM g (maps hi[g]/lo[g]) stream NP x NKB B tiles through the stage ring.
+// Called by the WHOLE (converged) warp; one elected lane issues (see elect_one()).
 template <bool X3>
 __device__ __forceinline__ void tc_tma_role(const TcSmem& m, const CUtensorMap* const* hi, const CUtensorMap* const* lo,
                                             int ngemm, int NP, int NKB) {
@@ -152,23 +154,28 @@ __device__ __forceinline__ void tc_tma_role(const TcSmem& m, const CUtensorMap* 
       for (int st = 0; st < NST; ++st, ++it) {
         const uint32_t s = it % C::S, ph = (it / C::S) & 1;
         mbar_wait(m.empty0 + 8 * s, ph ^ 1);
-        const uint32_t bar = m.full0 + 8 * s;
-        mbar_arrive_expect_tx(bar, C::KPS * (X3 ? 2 : 1) * kTileBytes);
+        if (elect_one()) {
+          const uint32_t bar = m.full0 + 8 * s;
+          mbar_arrive_expect_tx(bar, C::KPS * (X3 ? 2 : 1) * kTileBytes);
 #pragma unroll
-        for (int j = 0; j < C::KPS; ++j) {
-          const uint32_t dst = smem_u32(m.stages + s * C::kStageBytes + j * C::kSubBytes);
-          const int kb = st * C::KPS + j;
-          tma_load_2d(dst + C::kOffB, hi[g], bar, kb * kKB, p * kTN);
-          if (X3) tma_load_2d(dst + C::kOffBlo, lo[g], bar, kb * kKB, p * kTN);
+          for (int j = 0; j < C::KPS; ++j) {
+            const uint32_t dst = smem_u32(m.stages + s * C::kStageBytes + j * C::kSubBytes);
+            const int kb = st * C::KPS + j;
+            tma_load_2d(dst + C::kOffB, hi[g], bar, kb * kKB, p * kTN);
+            if (X3) tma_load_2d(dst + C::kOffBlo, lo[g], bar, kb * kKB, p * kTN);
+          }
         }
+        __syncwarp();
       }
 }
-// MMA issuer: npass accumulator passes of NKB K-blocks; D[256 x 256] = two M=128 blocks sharing B
+// MMA issuer: npass accumulator passes of NKB K-blocks; D[256 x 256] = two M=128 blocks sharing B.
+// Whole converged warp; one elected lane issues; descriptors advance by constants from one base.
 template <bool X3>
 __device__ __forceinline__ void tc_mma_role(const TcSmem& m, uint32_t tmem_base, int npass, int NKB) {
   using C = TcCfg<X3>;
   uint32_t it = 0;
   const int NST = NKB / C::KPS;
+  const uint64_t desc0 = make_desc_sw64(smem_u32(m.stages));
   for (int pp = 0; pp < npass; ++pp) {
     mbar_wait(m.accempty, (pp & 1) ^ 1);
     tc_fence_after();
@@ -176,32 +183,35 @@ __device__ __forceinline__ void tc_mma_role(const TcSmem& m, uint32_t tmem_base,
       const uint32_t s = it % C::S, ph = (it / C::S) & 1;
       mbar_wait(m.full0 + 8 * s, ph);
       tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-      for (int j = 0; j < C::KPS; ++j) {
-        const uint32_t sa = smem_u32(m.stages + s * C::kStageBytes + j * C::kSubBytes);
+        for (int j = 0; j < C::KPS; ++j) {
+          const uint64_t sa = desc0 + (uint64_t)((s * C::kStageBytes + j * C::kSubBytes) >> 4);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t d_t = tmem_base + (uint32_t)(half * kTN);
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t d_t = tmem_base + (uint32_t)(half * kTN);
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {                         // two K=8 steps per 64-byte row
-            const uint64_t a_hi = make_desc_sw64(sa + half * (kTileBytes / 2) + ks * 32);
-            const uint64_t b_hi = make_desc_sw64(sa + C::kOffB + ks * 32);
-            const uint32_t acc = (st | j | ks) ? 1u : 0u;
-            if (X3) {
-              const uint64_t a_lo = make_desc_sw64(sa + C::kOffAlo + half * (kTileBytes / 2) + ks * 32);
-              const uint64_t b_lo = make_desc_sw64(sa + C::kOffBlo + ks * 32);
-              umma_tf32(d_t, a_lo, b_hi, kIdescTf32, acc);
-              umma_tf32(d_t, a_hi, b_lo, kIdescTf32, 1u);
-              umma_tf32(d_t, a_hi, b_hi, kIdescTf32, 1u);
-            } else {
-              umma_tf32(d_t, a_hi, b_hi, kIdescTf32, acc);
+            for (int ks = 0; ks < 2; ++ks) {                         // two K=8 steps per 64-byte row
+              const uint64_t a_hi = sa + (uint64_t)((half * (kTileBytes / 2) + ks * 32) >> 4);
+              const uint64_t b_hi = sa + (uint64_t)((C::kOffB + ks * 32) >> 4);
+              const uint32_t acc = (st | j | ks) ? 1u : 0u;
+              if (X3) {
+                const uint64_t a_lo = a_hi + (uint64_t)(C::kOffAlo >> 4);
+                const uint64_t b_lo = sa + (uint64_t)((C::kOffBlo + ks * 32) >> 4);
+                umma_tf32(d_t, a_lo, b_hi, kIdescTf32, acc);
+                umma_tf32(d_t, a_hi, b_lo, kIdescTf32, 1u);
+                umma_tf32(d_t, a_hi, b_hi, kIdescTf32, 1u);
+              } else {
+                umma_tf32(d_t, a_hi, b_hi, kIdescTf32, acc);
+              }
             }
           }
         }
+        umma_commit(m.empty0 + 8 * s);       // frees the smem stage when these MMAs have read it
+        if (st == NST - 1) umma_commit(m.accfull);   // accumulator pass complete
       }
-      umma_commit(m.empty0 + 8 * s);       // frees the smem stage when these MMAs have read it
+      __syncwarp();
     }
-    umma_commit(m.accfull);                // accumulator pass complete
   }
 }
 
@@ -345,11 +355,13 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
   const TcSmem m = carve<X3>(smem_raw, Hq);
   const uint32_t tmem_base = tc_setup<X3>(m, Hq, A0q_g, A1q_g, P1q_g);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform role index
   const int m0 = blockIdx.x * kTM;
   const int NP = Hq / kTN, NKB = Hq / kKB;
   const int ngemm = (xhat != nullptr) ? 2 : 1;
+  (void)lane;
 
-  if (warp < kNW) {
+  if (warp_u < kNW) {
     Worker w = make_worker(tmem_base);
     const Gen4 g = make_gen4();
     const bool valid = (m0 + w.row) < B;
@@ -487,14 +499,12 @@ icnn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
         }
       }
     }
-  } else if (warp == kNW) {
-    if (lane == 0) {
-      const CUtensorMap* hi[2] = {&maps.b1hi, &maps.b2hi};
-      const CUtensorMap* lo[2] = {&maps.b1lo, &maps.b2lo};
-      tc_tma_role<X3>(m, hi, lo, ngemm, NP, NKB);
-    }
+  } else if (warp_u == kNW) {
+    const CUtensorMap* hi[2] = {&maps.b1hi, &maps.b2hi};
+    const CUtensorMap* lo[2] = {&maps.b1lo, &maps.b2lo};
+    tc_tma_role<X3>(m, hi, lo, ngemm, NP, NKB);
   } else {
-    if (lane == 0) tc_mma_role<X3>(m, tmem_base, ngemm * NP, NKB);
+    tc_mma_role<X3>(m, tmem_base, ngemm * NP, NKB);
   }
   tc_teardown(tmem_base);
 }
@@ -515,11 +525,12 @@ icnn_tc_bwd_rows_kernel(const __grid_constant__ TcMaps maps, const float* __rest
   const TcSmem m = carve<X3>(smem_raw, Hq);
   const uint32_t tmem_base = tc_setup<X3>(m, Hq, A0q_g, A1q_g, P1q_g);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform role index
   const int m0 = blockIdx.x * kTM;
   const int NP = Hq / kTN, NKB = Hq / kKB;
   constexpr int NF = D + 1;
 
-  if (warp < kNW) {
+  if (warp_u < kNW) {
     Worker w = make_worker(tmem_base);
     const bool valid = (m0 + w.row) < B;
     float zr[D], vr[D];
@@ -634,14 +645,12 @@ icnn_tc_bwd_rows_kernel(const __grid_constant__ TcMaps maps, const float* __rest
       for (int q = 0; q < 8; ++q) sred += m.xch[q * 4 + threadIdx.x];
       a2part[(size_t)blockIdx.x * D + threadIdx.x] = sred;
     }
-  } else if (warp == kNW) {
-    if (lane == 0) {
-      const CUtensorMap* hi[2] = {&maps.b2hi, &maps.b1hi};
-      const CUtensorMap* lo[2] = {&maps.b2lo, &maps.b1lo};
-      tc_tma_role<X3>(m, hi, lo, 2, NP, NKB);
-    }
+  } else if (warp_u == kNW) {
+    const CUtensorMap* hi[2] = {&maps.b2hi, &maps.b1hi};
+    const CUtensorMap* lo[2] = {&maps.b2lo, &maps.b1lo};
+    tc_tma_role<X3>(m, hi, lo, 2, NP, NKB);
   } else {
-    if (lane == 0) tc_mma_role<X3>(m, tmem_base, 2 * NP, NKB);
+    tc_mma_role<X3>(m, tmem_base, 2 * NP, NKB);
   }
   tc_teardown(tmem_base);
 }
@@ -676,6 +685,7 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform role index
   const int n0 = blockIdx.x * kTN, o0 = blockIdx.y * kTM, split = blockIdx.z;
   const int b0 = split * rows_per_split;
   const int b1 = min(B, b0 + rows_per_split);
@@ -695,7 +705,7 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kNW) {
+  if (warp_u < kNW) {
     const int ks = tid & 15, u = tid >> 4, blk = u >> 2, qd = u & 3;     // sample-in-stage, MN block, 8-wide quarter
     const int g4 = ks >> 2, kr = ks & 3;                                 // group of 4 k, k-row inside the atom
     float4 q[8];
@@ -799,34 +809,39 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
     } else {
       for (int j = 0; j < 128; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  } else if (lane == 0) {
+  } else {
+    // MMA issuer: whole converged warp, one elected lane issues; descriptors advance by constants
+    const uint64_t desc0 = make_desc_mn_sw128(smem_u32(stages));
     for (int kb = 0; kb < NKB; ++kb) {
       const uint32_t s = kb % S, ph = (kb / S) & 1;
       mbar_wait(full0 + 8 * s, ph);
       tc_fence_after();
-      const uint32_t sa = smem_u32(stages + s * kStage);
+      if (elect_one()) {
+        const uint64_t sa = desc0 + (uint64_t)((s * kStage) >> 4);
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
+        for (int g = 0; g < 2; ++g) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t d_t = tmem_base + (uint32_t)(half * kTN);
-          const uint64_t a_hi = make_desc_mn_sw128(sa + g * 8192 + half * 2048);     // K=8 = two 4-k groups
-          const uint64_t b_hi = make_desc_mn_sw128(sa + kOffB + g * 8192);
-          const uint32_t acc = (kb | g) ? 1u : 0u;
-          if (X3) {
-            const uint64_t a_lo = make_desc_mn_sw128(sa + kOffAlo + g * 8192 + half * 2048);
-            const uint64_t b_lo = make_desc_mn_sw128(sa + kOffBlo + g * 8192);
-            umma_tf32(d_t, a_lo, b_hi, kIdescTf32MN, acc);
-            umma_tf32(d_t, a_hi, b_lo, kIdescTf32MN, 1u);
-            umma_tf32(d_t, a_hi, b_hi, kIdescTf32MN, 1u);
-          } else {
-            umma_tf32(d_t, a_hi, b_hi, kIdescTf32MN, acc);
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t d_t = tmem_base + (uint32_t)(half * kTN);
+            const uint64_t a_hi = sa + (uint64_t)((g * 8192 + half * 2048) >> 4);     // K=8 = two 4-k groups
+            const uint64_t b_hi = sa + (uint64_t)((kOffB + g * 8192) >> 4);
+            const uint32_t acc = (kb | g) ? 1u : 0u;
+            if (X3) {
+              const uint64_t a_lo = a_hi + (uint64_t)(kOffAlo >> 4);
+              const uint64_t b_lo = sa + (uint64_t)((kOffBlo + g * 8192) >> 4);
+              umma_tf32(d_t, a_lo, b_hi, kIdescTf32MN, acc);
+              umma_tf32(d_t, a_hi, b_lo, kIdescTf32MN, 1u);
+              umma_tf32(d_t, a_hi, b_hi, kIdescTf32MN, 1u);
+            } else {
+              umma_tf32(d_t, a_hi, b_hi, kIdescTf32MN, acc);
+            }
           }
         }
+        umma_commit(empty0 + 8 * s);
+        if (kb == NKB - 1) umma_commit(accfull);
       }
-      umma_commit(empty0 + 8 * s);
+      __syncwarp();
     }
-    if (NKB > 0) umma_commit(accfull);
   }
   tc_teardown(tmem_base);
 }
@@ -990,10 +1005,15 @@ static int tc_dp0_splits(int B, int Hq) {
   return s;
 }
 
+int tc3_bwd_rows(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H, float kappa,
+                 float* dz, float* partA, float* partB, float* a2part, float* dzpart, int precision, float* ws, cudaStream_t st);
+size_t tc3_bwd_ws_floats(int B, int d, int H);
+
 size_t tc_bwd_ws_floats(int B, int d, int H) {
   const TcLayout T = tc_layout(d, H);
   const size_t nmt = (size_t)(B + kTM - 1) / kTM;
-  return 2 * nmt * 8 * (d + 1) * T.Hq + nmt * 4 + 64 + 16 + (size_t)tc_dp0_splits(B, T.Hq) * T.Hq * T.Hq;
+  return 2 * nmt * 8 * (d + 1) * T.Hq + nmt * 4 + 64 + 16 + (size_t)tc_dp0_splits(B, T.Hq) * T.Hq * T.Hq + 64 +
+         tc3_bwd_ws_floats(B, d, H);
 }
 
 template <int D, bool X3>
@@ -1053,6 +1073,17 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
   float* a2part = partB + nmt * 8 * (d + 1) * T.Hq;
   const bool x3 = (precision == B200VAE_PREC_TF32X3);
   const int Hw_in = L.Hp / 32;
+  // rows part: persistent pair kernel (icnn_tc3.cu) unless B200VAE_BWD=1 or it does not fit (H > 1024)
+  static const int variant = [] { const char* e = getenv("B200VAE_BWD"); return e ? atoi(e) : 3; }();
+  float* dp0part = a2part + nmt * 4 + 64;
+  dp0part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dp0part) + 15) & ~(uintptr_t)15);
+  rc = B200VAE_EUNSUP;
+  if (variant == 3) {
+    float* dzpart = dp0part + (size_t)tc_dp0_splits(B, T.Hq) * T.Hq * T.Hq;
+    dzpart = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dzpart) + 15) & ~(uintptr_t)15);
+    rc = tc3_bwd_rows(z, v, mask1, mask2, B, d, H, kappa, dz, partA, partB, a2part, dzpart, precision, ws, st);
+  }
+  if (rc == B200VAE_EUNSUP) {
 #define B200VAE_TCB(DD)                                                                                                 \
   rc = x3 ? launch_tc_bwd<DD, true>(maps, z, v, mask1, mask2, B, T, tb, Hw_in, kappa, dz, partA, partB, a2part, st)    \
           : launch_tc_bwd<DD, false>(maps, z, v, mask1, mask2, B, T, tb, Hw_in, kappa, dz, partA, partB, a2part, st)
@@ -1063,10 +1094,10 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
     default: return B200VAE_EUNSUP;
   }
 #undef B200VAE_TCB
+  }
   if (rc || !g) return rc;
   if (g->W0) {
-    float* part = a2part + nmt * 4 + 64;
-    part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(part) + 15) & ~(uintptr_t)15);
+    float* part = dp0part;
     const int splits = tc_dp0_splits(B, T.Hq);
 #define B200VAE_TCD(DD)                                                                                       \
   rc = x3 ? launch_tc_dp0<DD, true>(z, v, mask1, mask2, B, T, tb, Hw_in, splits, part, st)                    \

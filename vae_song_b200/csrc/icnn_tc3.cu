@@ -588,6 +588,483 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
   }
 }
 
+// =====================================================================================================
+// Backward (double-backward of the Brenier map), sample-stationary part, same persistent pair framework.
+//   A-units: acc = (1 + 4 bit) . B2g  (= gx1 / s2, the forward's GEMM2 recomputed from the saved mask bits)
+//            epilogue: t0, g0 -> row-local dz partials; column sums dA0w_j = sum_b (g0 v_j + t0 z_j), db0 = sum_b t0
+//   B-units: w1 = A1 v + P q1  (q1 = 2 (A0 v) a0 s0 generated; A1 v rides in the lin K-block with v instead of z)
+//            epilogue: column sums dP1 = sum_b s2 s1 w1, dA1w_j = P1 sum_b s2 s1 v_j
+// All units are independent.  The epilogue reads TMEM with the 16x256b shape: a thread then owns 4 rows x 8 columns
+// of every 32-column chunk, so per-column parameters are loaded once per 4 rows and a column sum needs 3 in-thread
+// adds plus a 3-step transposing shuffle reduction over the 8 lanes that share the columns (instead of 5 steps over
+// 32 lanes).  Column partials go to ordered slots part[(tile*8 + rank*4 + quarter)][f][Hq] (summed in fixed order by
+// tc_finalize_small_kernel, icnn_tc.cu); dz partials per (row, pass, column half) are combined by tc3_bwd_dz_kernel.
+struct alignas(64) Tc3BwdArgs {
+  CUtensorMap b1hi, b1lo, b2hi, b2lo;
+  const float *z, *v;
+  const uint32_t* mask1;
+  const uint8_t* mask2;
+  const float4 *A0g, *E1, *A0q;
+  float *partA, *partB;
+  float4* dzpart;
+  int B, Hq, T, NP, Hw_in;
+};
+
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// vals[c*NF + f] (c = 0..7 column slots) summed over the 8 lanes with equal (lane & 3): afterwards vals[0..NF) of a
+// lane hold the sums for column slot (lane >> 2) & 7.  NV = 8*NF values, 7*NF shuffles.
+template <int NV>
+__device__ __forceinline__ void fold8(float (&vals)[NV], int lane) {
+#pragma unroll
+  for (int step = 0; step < 3; ++step) {
+    const int off = 16 >> step, n = NV >> step, half = n / 2;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? vals[i] : vals[i + half];
+      const float keep = up ? vals[i + half] : vals[i];
+      vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+template <int D, bool X3>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k3Threads, 1)
+icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
+  using C = Tc3Cfg<X3>;
+  constexpr int S = C::S;
+  constexpr int NF = D + 1;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* stages = smem;
+  const int Hq = a.Hq;
+  float4* A0gs = reinterpret_cast<float4*>(smem + S * C::kStageBytes);     // generator order
+  float4* E1s = A0gs + Hq;
+  float4* A0qs = E1s + Hq;
+  uint32_t* maskbuf = reinterpret_cast<uint32_t*>(A0qs + Hq);              // [2][128][36]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(maskbuf + 2 * k3Rows * k3MaskStride);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull0 = smem_u32(bars + 2 * S),
+                 accempty0 = smem_u32(bars + 2 * S + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t rank = cluster_rank3();
+  const int cid = (int)cluster_id3(), G = (int)num_clusters3();
+  const int T = a.T, NP = a.NP, NKB = Hq / kKB;
+  const int U = 2 * T * NP;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 8 + 2); mbar_init(empty0 + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(accfull0 + 8 * b, 1); mbar_init(accempty0 + 8 * b, 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 16) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  for (int i = tid; i < Hq; i += k3Threads) { A0gs[i] = a.A0g[i]; E1s[i] = a.E1[i]; A0qs[i] = a.A0q[i]; }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync3();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lead_full0 = mapa3(full0, 0), lead_accempty0 = mapa3(accempty0, 0);
+
+  if (warp_u < 8) {
+    // =========================== epilogue warps ===========================
+    // warp -> TMEM lane quarter q (32 rows) and column half; lane -> rows (lane>>2) + 8r, columns 8n + 2(lane&3) + e
+    const int q4 = warp & 3, chalf = warp >> 2;
+    const int r0 = q4 * 32 + (lane >> 2), cp2 = 2 * (lane & 3);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(chalf * 128);
+    int i = 0;
+    for (int u = cid; u < U; u += G, ++i) {
+      const Unit un = decode_unit(u, T, NP);
+      const int buf = i & 1;
+      const int m0 = un.t * 256 + (int)rank * k3Rows;
+      float zr[4][D], vr[4][D], s2r[4];
+      uint4 mw[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int gr = m0 + r0 + 8 * r;
+        const bool in = gr < a.B;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          zr[r][j] = in ? a.z[(size_t)gr * D + j] : 0.f;
+          vr[r][j] = in ? a.v[(size_t)gr * D + j] : 0.f;
+        }
+        s2r[r] = in ? (a.mask2[gr] ? 1.f : kSlope) : 0.f;      // 0 kills every term of padded rows
+        const int w0 = un.p * 8 + chalf * 4;
+        mw[r] = (un.g && in && w0 < a.Hw_in) ? *reinterpret_cast<const uint4*>(a.mask1 + (size_t)gr * a.Hw_in + w0)
+                                              : make_uint4(0u, 0u, 0u, 0u);
+      }
+      float* part = (un.g ? a.partB : a.partA) + (size_t)((un.t * 8 + (int)rank * 4 + q4) * NF) * Hq;
+      float dz4[4][D];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < D; ++j) dz4[r][j] = 0.f;
+      mbar_wait_parked(accfull0 + 8 * buf, (i >> 1) & 1, 2000);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t ra[16], rb[16];
+        tmem_ld_16x256b_x4(taddr + buf * 256 + cc * 32, ra);
+        tmem_ld_16x256b_x4(taddr + (16u << 16) + buf * 256 + cc * 32, rb);
+        tmem_ld_wait();
+        const int nb = un.p * 256 + chalf * 128 + cc * 32;
+        float vals[8 * NF];
+        if (!un.g) {
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float4 q = A0qs[nb + 8 * n + cp2 + e];
+              float ef[NF];
+#pragma unroll
+              for (int f = 0; f < NF; ++f) ef[f] = 0.f;
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const float acc = __uint_as_float((r < 2 ? ra : rb)[4 * n + 2 * (r & 1) + e]);
+                const float h0 = lin_of<D>(q, zr[r]), u0 = dot_of<D>(q, vr[r]);
+                const float s2x2 = 2.f * s2r[r];
+                const float mc = acc * (h0 > 0.f ? s2x2 : (kSlope * kSlope) * s2x2);   // 2 s2 s0^2 acc
+                const float t0 = mc * u0;                                               // u0 2 gx1 s0^2
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                  dz4[r][j] = fmaf(comp(q, j), t0, dz4[r][j]);
+                  ef[j] = fmaf(mc, fmaf(h0, vr[r][j], u0 * zr[r][j]), ef[j]);           // g0 v_j + t0 z_j
+                }
+                ef[D] += t0;
+              }
+#pragma unroll
+              for (int f = 0; f < NF; ++f) vals[(2 * n + e) * NF + f] = ef[f];
+            }
+        } else {
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int bitpos = 8 * n + cp2 + e;
+              float ef[NF];
+#pragma unroll
+              for (int f = 0; f < NF; ++f) ef[f] = 0.f;
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const uint32_t wd = cc == 0 ? mw[r].x : (cc == 1 ? mw[r].y : (cc == 2 ? mw[r].z : mw[r].w));
+                const float w1 = __uint_as_float((r < 2 ? ra : rb)[4 * n + 2 * (r & 1) + e]);
+                const float c1 = ((wd >> bitpos) & 1u) ? s2r[r] : kSlope * s2r[r];      // s2 s1
+#pragma unroll
+                for (int j = 0; j < D; ++j) ef[j] = fmaf(c1, vr[r][j], ef[j]);
+                ef[D] = fmaf(c1, w1, ef[D]);
+              }
+#pragma unroll
+              for (int f = 0; f < NF; ++f) vals[(2 * n + e) * NF + f] = ef[f];
+            }
+        }
+        fold8<8 * NF>(vals, lane);
+        const int cs = (lane >> 2) & 7;                          // my column slot after the fold
+        const int col = nb + 8 * (cs >> 1) + cp2 + (cs & 1);
+        const float p1 = un.g ? E1s[col].x : 1.f;                // dA1w carries P1 (g1 = s2 P1 s1)
+#pragma unroll
+        for (int f = 0; f < NF; ++f) part[(size_t)f * Hq + col] = (f < D) ? vals[f] * p1 : vals[f];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(lead_accempty0 + 8 * buf);
+      if (!un.g) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            float t = dz4[r][j];
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            o[j] = t;
+          }
+          if ((lane & 3) == 0)
+            a.dzpart[((size_t)(m0 + r0 + 8 * r) * NP + un.p) * 2 + chalf] = make_float4(o[0], o[1], o[2], 0.f);
+        }
+      }
+    }
+  } else if (warp_u < 16) {
+    // =========================== generator warps ===========================
+    const int t2 = tid - 256, kh = t2 >> 7, c = t2 & 3, rb = (t2 >> 2) & 31;
+    const uint32_t goff = (uint32_t)rb * 64u + ((uint32_t)(c ^ ((rb >> 1) & 3)) << 4);
+    uint32_t stg = 0;
+    int n2 = 0;
+    bool prefetched = false;
+    auto stage_ptr = [&](uint32_t sg) { return stages + (sg % S) * C::kStageBytes + goff; };
+    auto wait_stage = [&](uint32_t sg) { mbar_wait(empty0 + 8 * (sg % S), ((sg / S) & 1) ^ 1); };
+    auto publish = [&](uint32_t sg) {
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(lead_full0 + 8 * (sg % S));
+    };
+    auto load_masks = [&](int tile, int mb) {
+      const int cpr = Hq / 128;
+      uint32_t* dst0 = maskbuf + mb * (k3Rows * k3MaskStride);
+      for (int id = t2; id < k3Rows * cpr; id += 256) {
+        const int r = id / cpr, ch = id - r * cpr;
+        const int gr = tile * 256 + (int)rank * k3Rows + r;
+        uint32_t* dst = dst0 + r * k3MaskStride + ch * 4;
+        if (gr < a.B && ch * 4 < a.Hw_in) cp_async16(dst, a.mask1 + (size_t)gr * a.Hw_in + ch * 4);
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      cp_async_commit();
+    };
+    const int NST = NKB / 2;
+    for (int u = cid; u < U; u += G) {
+      const Unit un = decode_unit(u, T, NP);
+      const int m0 = un.t * 256 + (int)rank * k3Rows;
+      if (!un.g) {
+        // ---------------- A-units: bits -> 1 + 4*bit ----------------
+        const int mb = n2 & 1;
+        ++n2;
+        if (!prefetched) load_masks(un.t, mb);
+        cp_async_wait_all();
+        bar_gen();
+        prefetched = (u + G < U) && (decode_unit(u + G, T, NP).g == 0);
+        if (prefetched) load_masks(decode_unit(u + G, T, NP).t, mb ^ 1);
+        const uint32_t* mrow = maskbuf + mb * (k3Rows * k3MaskStride) + rb * k3MaskStride;
+        for (int st = (int)((stg ^ (uint32_t)kh) & 1u); st < NST; st += 2) {
+          uint32_t w4[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) w4[r] = mrow[r * 32 * k3MaskStride + st] >> (c * 4);
+          wait_stage(stg + st);
+          unsigned char* At = stage_ptr(stg + st);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const uint32_t w = w4[r] >> (16 * sub);
+              *reinterpret_cast<float4*>(At + sub * C::kSubBytes + r * 2048) =
+                  make_float4((w & 1u) ? 5.f : 1.f, (w & 2u) ? 5.f : 1.f, (w & 4u) ? 5.f : 1.f, (w & 8u) ? 5.f : 1.f);
+            }
+          publish(stg + st);
+        }
+        stg += NST;
+        bar_gen();
+      } else {
+        // ---------------- B-units: q1 = 2 (A0 v) a0 s0, then the lin block (v hi/lo, bias columns off) ----------------
+        float z4[4][D], v4[4][D];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            const bool in = m0 + rb + 32 * r < a.B;
+            z4[r][j] = in ? a.z[(size_t)(m0 + rb + 32 * r) * D + j] : 0.f;
+            v4[r][j] = in ? a.v[(size_t)(m0 + rb + 32 * r) * D + j] : 0.f;
+          }
+        float2 zp[2][D], vp[2][D];
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            zp[pr][j] = make_float2(z4[2 * pr][j], z4[2 * pr + 1][j]);
+            vp[pr][j] = make_float2(2.f * v4[2 * pr][j], 2.f * v4[2 * pr + 1][j]);
+          }
+        int st = (int)((stg ^ (uint32_t)kh) & 1u);
+        for (; st < NST; st += 2) {
+          float vv[2][4][4];
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 q = A0gs[(2 * st + sub) * kKB + e * 4 + c];
+#pragma unroll
+              for (int pr = 0; pr < 2; ++pr) {
+                float2 h = __ffma2_rn(make_float2(q.x, q.x), zp[pr][0], make_float2(q.w, q.w));
+                float2 uu = __fmul2_rn(make_float2(q.x, q.x), vp[pr][0]);
+                if (D > 1) {
+                  h = __ffma2_rn(make_float2(q.y, q.y), zp[pr][D > 1 ? 1 : 0], h);
+                  uu = __ffma2_rn(make_float2(q.y, q.y), vp[pr][D > 1 ? 1 : 0], uu);
+                }
+                if (D > 2) {
+                  h = __ffma2_rn(make_float2(q.z, q.z), zp[pr][D > 2 ? 2 : 0], h);
+                  uu = __ffma2_rn(make_float2(q.z, q.z), vp[pr][D > 2 ? 2 : 0], uu);
+                }
+                const float2 l = __fmul2_rn(h, make_float2(kSlope * kSlope, kSlope * kSlope));
+                const float2 f0 = make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y));        // a0 s0 = h0 s0^2
+                const float2 x = __fmul2_rn(uu, f0);
+                vv[sub][2 * pr][e] = x.x; vv[sub][2 * pr + 1][e] = x.y;
+              }
+            }
+          wait_stage(stg + st);
+          unsigned char* At = stage_ptr(stg + st);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              unsigned char* dst = At + sub * C::kSubBytes + r * 2048;
+              if (X3) {
+                const float4 hi = make_float4(rn_tf32_masked(vv[sub][r][0]), rn_tf32_masked(vv[sub][r][1]),
+                                              rn_tf32_masked(vv[sub][r][2]), rn_tf32_masked(vv[sub][r][3]));
+                *reinterpret_cast<float4*>(dst) = hi;
+                *reinterpret_cast<float4*>(dst + C::kOffAlo) =
+                    make_float4(rn_tf32_fast(vv[sub][r][0] - hi.x), rn_tf32_fast(vv[sub][r][1] - hi.y),
+                                rn_tf32_fast(vv[sub][r][2] - hi.z), rn_tf32_fast(vv[sub][r][3] - hi.w));
+              } else {
+                *reinterpret_cast<float4*>(dst) = make_float4(rn_tf32_fast(vv[sub][r][0]), rn_tf32_fast(vv[sub][r][1]),
+                                                              rn_tf32_fast(vv[sub][r][2]), rn_tf32_fast(vv[sub][r][3]));
+              }
+            }
+          publish(stg + st);
+        }
+        if (st == NST) {
+          wait_stage(stg + st);
+          unsigned char* At = stage_ptr(stg + st);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            float col[16];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) col[m] = 0.f;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+              const float vh = rn_tf32_masked(v4[r][j]);
+              col[3 * j] = vh; col[3 * j + 1] = rn_tf32_masked(v4[r][j] - vh); col[3 * j + 2] = vh;
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              if (cc == c) {
+                *reinterpret_cast<float4*>(At + r * 2048) = make_float4(col[4 * cc], col[4 * cc + 1], col[4 * cc + 2], col[4 * cc + 3]);
+                if (X3) *reinterpret_cast<float4*>(At + C::kOffAlo + r * 2048) = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+          }
+          publish(stg + st);
+        }
+        stg += NST + 1;
+      }
+    }
+    cp_async_wait_all();
+  } else if (warp_u == 16) {
+    // =========================== TMA producer ===========================
+    uint32_t it = 0;
+    for (int u = cid; u < U; u += G) {
+      const Unit un = decode_unit(u, T, NP);
+      const CUtensorMap* mhi = un.g ? &a.b1hi : &a.b2hi;
+      const CUtensorMap* mlo = un.g ? &a.b1lo : &a.b2lo;
+      const int nreal = un.g ? NKB + 1 : NKB, npad = (nreal + 1) & ~1;
+      const int rowc = un.p * 256 + (int)rank * k3Rows;
+      for (int kb = 0; kb < npad; kb += 2, it += 2) {
+        const uint32_t s = (it >> 1) % S, ph = ((it >> 1) / S) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const bool real1 = kb + 1 < nreal;
+        if (elect_one()) {
+          const uint32_t bar = lead_full0 + 8 * s;
+          if (rank == 0) {
+            mbar_arrive_expect_tx(full0 + 8 * s, 2 * (X3 ? 2 : 1) * k3TileBytes);
+            if (real1) mbar_arrive_expect_tx(full0 + 8 * s, 2 * (X3 ? 2 : 1) * k3TileBytes);
+            else mbar_arrive(full0 + 8 * s);
+          }
+          const uint32_t dst = smem_u32(stages + s * C::kStageBytes);
+          tma_load_2d_pair(dst + C::kOffB, mhi, bar, kb * kKB, rowc);
+          if (X3) tma_load_2d_pair(dst + C::kOffBlo, mlo, bar, kb * kKB, rowc);
+          if (real1) {
+            tma_load_2d_pair(dst + C::kSubBytes + C::kOffB, mhi, bar, (kb + 1) * kKB, rowc);
+            if (X3) tma_load_2d_pair(dst + C::kSubBytes + C::kOffBlo, mlo, bar, (kb + 1) * kKB, rowc);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (rank == 0) {
+    // =========================== MMA issuer (leader CTA only) ===========================
+    const uint64_t descA0 = make_desc_sw64(smem_u32(stages));
+    uint32_t it = 0;
+    int i = 0;
+    for (int u = cid; u < U; u += G, ++i) {
+      const Unit un = decode_unit(u, T, NP);
+      const int buf = i & 1;
+      const int nreal = un.g ? NKB + 1 : NKB, npad = (nreal + 1) & ~1;
+      mbar_wait(accempty0 + 8 * buf, ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_t = tmem_base + (uint32_t)(buf * 256);
+      for (int kb = 0; kb < npad; kb += 2, it += 2) {
+        const uint32_t s = (it >> 1) % S, ph = ((it >> 1) / S) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a0 = descA0 + (uint64_t)(s * (C::kStageBytes >> 4));
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            if (sub == 1 && kb + 1 >= nreal) break;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t a_hi = a0 + (uint64_t)(sub * (C::kSubBytes >> 4) + ks * 2);
+              const uint64_t b_hi = a_hi + (uint64_t)(C::kOffB >> 4);
+              const uint32_t acc = (kb | sub | ks) ? 1u : 0u;
+              if (X3) {
+                const uint64_t b_lo = a_hi + (uint64_t)(C::kOffBlo >> 4);
+                if (un.g) {                                             // A-units' operand is exact: no a_lo term
+                  umma_tf32_pair(d_t, a_hi + (uint64_t)(C::kOffAlo >> 4), b_hi, acc);
+                  umma_tf32_pair(d_t, a_hi, b_lo, 1u);
+                } else {
+                  umma_tf32_pair(d_t, a_hi, b_lo, acc);
+                }
+                umma_tf32_pair(d_t, a_hi, b_hi, 1u);
+              } else {
+                umma_tf32_pair(d_t, a_hi, b_hi, acc);
+              }
+            }
+          }
+          umma_commit_pair(empty0 + 8 * s);
+          if (kb + 2 >= npad) umma_commit_pair(accfull0 + 8 * buf);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync3();
+  if (warp == 16) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// dz[b] = sum of the A-units' partials + 2 kappa v;  a2part[tile][j] = sum_{b in tile} s2 v_j (fixed order).  One block per
+// 256-row tile.
+__global__ void __launch_bounds__(256)
+tc3_bwd_dz_kernel(const float4* __restrict__ dzpart, const float* __restrict__ v, const uint8_t* __restrict__ mask2, int B,
+                  int NP, int d, float kappa, float* __restrict__ dz, float* __restrict__ a2part) {
+  __shared__ float red[8][4];
+  const int row = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const bool in = row < B;
+  float acc[3] = {0.f, 0.f, 0.f}, sv[3] = {0.f, 0.f, 0.f};
+  if (in) {
+    for (int q = 0; q < 2 * NP; ++q) {
+      const float4 t = dzpart[(size_t)row * NP * 2 + q];
+      acc[0] += t.x; acc[1] += t.y; acc[2] += t.z;
+    }
+    const float s2 = mask2[row] ? 1.f : kSlope;
+    for (int j = 0; j < d; ++j) {
+      const float vj = v[(size_t)row * d + j];
+      if (dz) dz[(size_t)row * d + j] = fmaf(2.f * kappa, vj, acc[j]);
+      sv[j] = s2 * vj;
+    }
+  }
+  for (int j = 0; j < 3; ++j) {
+    const float t = warp_sum(sv[j]);
+    if (lane == 0) red[wp][j] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < d) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    a2part[(size_t)blockIdx.x * d + threadIdx.x] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -632,26 +1109,99 @@ int tc3_prepare(int d, int H, int precision, float* ws, cudaStream_t st) {
   return B200VAE_OK;
 }
 
+struct Tc3Maps { CUtensorMap b1hi, b1lo, b2hi, b2lo; };
+static int get_maps3(const float* t3, const Tc3Layout& T3, bool x3, Tc3Maps* out) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, Tc3Maps> cache;       // tensor maps only encode (address, shape)
+  std::lock_guard<std::mutex> lk(mu);
+  const uint64_t key = reinterpret_cast<uint64_t>(t3) ^ ((uint64_t)T3.Hq << 48) ^ ((uint64_t)x3 << 63);
+  auto itc = cache.find(key);
+  if (itc != cache.end()) { *out = itc->second; return B200VAE_OK; }
+  Tc3Maps mp;
+  int rc = make_map3(&mp.b1hi, t3 + T3.B1ahi, T3.K1, T3.Hq);
+  if (!rc) rc = make_map3(&mp.b1lo, t3 + (x3 ? T3.B1alo : T3.B1ahi), T3.K1, T3.Hq);
+  if (!rc) rc = make_map3(&mp.b2hi, t3 + T3.B2ghi, T3.Hq, T3.Hq);
+  if (!rc) rc = make_map3(&mp.b2lo, t3 + (x3 ? T3.B2glo : T3.B2ghi), T3.Hq, T3.Hq);
+  if (rc) return rc;
+  if (cache.size() > 256) cache.clear();
+  cache.emplace(key, mp);
+  *out = mp;
+  return B200VAE_OK;
+}
+
+static int max_clusters_for(const void* fn, size_t smem) {
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(k3Threads); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    n = sm_count() / 2;
+  }
+  return n;
+}
+
+template <int D, bool X3>
+static int launch_tc3_bwd(const Tc3BwdArgs& args, cudaStream_t st) {
+  const size_t smem = tc3_smem_bytes<X3>(args.Hq);
+  if (smem > 227 * 1024) return B200VAE_EUNSUP;
+  static int max_clusters = 0;
+  if (max_clusters == 0) max_clusters = max_clusters_for(reinterpret_cast<const void*>(icnn_tc3_bwd_kernel<D, X3>), smem);
+  const int units = 2 * args.T * args.NP;
+  const int G = units < max_clusters ? units : max_clusters;
+  icnn_tc3_bwd_kernel<D, X3><<<2 * G, k3Threads, smem, st>>>(args);
+  return check_launch();
+}
+
+// rows part of the backward: fills partA/partB [T*8][d+1][Hq], a2part [T][d], dz [B,d] (layouts of icnn_tc.cu's tc_bwd)
+int tc3_bwd_rows(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H, float kappa,
+                 float* dz, float* partA, float* partB, float* a2part, float* dzpart, int precision, float* ws, cudaStream_t st) {
+  if (precision == B200VAE_PREC_BF16 || d > 3) return B200VAE_EUNSUP;
+  const WsLayout L = ws_layout(1, d, H);
+  const TcLayout T = tc_layout(d, H);
+  const Tc3Layout T3 = tc3_layout(B, d, H);
+  float* tb = tc_base(ws, d, H);
+  float* t3 = tb + T.end;
+  const bool x3 = (precision == B200VAE_PREC_TF32X3);
+  Tc3Maps mp;
+  int rc = get_maps3(t3, T3, x3, &mp);
+  if (rc) return rc;
+  Tc3BwdArgs args;
+  args.b1hi = mp.b1hi; args.b1lo = mp.b1lo; args.b2hi = mp.b2hi; args.b2lo = mp.b2lo;
+  args.z = z; args.v = v; args.mask1 = mask1; args.mask2 = mask2;
+  args.A0g = reinterpret_cast<const float4*>(t3 + T3.A0g);
+  args.E1 = reinterpret_cast<const float4*>(t3 + T3.E1);
+  args.A0q = reinterpret_cast<const float4*>(tb + T.A0q);
+  args.partA = partA; args.partB = partB;
+  args.dzpart = reinterpret_cast<float4*>(dzpart);
+  args.B = B; args.Hq = T3.Hq; args.T = T3.Bp / 256; args.NP = T3.NP; args.Hw_in = L.Hp / 32;
+#define B200VAE_TC3B(DD) rc = x3 ? launch_tc3_bwd<DD, true>(args, st) : launch_tc3_bwd<DD, false>(args, st)
+  switch (d) {
+    case 1: B200VAE_TC3B(1); break;
+    case 2: B200VAE_TC3B(2); break;
+    case 3: B200VAE_TC3B(3); break;
+    default: return B200VAE_EUNSUP;
+  }
+#undef B200VAE_TC3B
+  if (rc) return rc;
+  tc3_bwd_dz_kernel<<<args.T, 256, 0, st>>>(reinterpret_cast<const float4*>(dzpart), v, mask2, B, args.NP, d, kappa, dz, a2part);
+  return check_launch();
+}
+size_t tc3_bwd_ws_floats(int B, int d, int H) {
+  const Tc3Layout T3 = tc3_layout(B, d, H);
+  return (size_t)T3.Bp * T3.NP * 2 * 4 + 64;
+}
+
 template <int D, bool X3>
 static int launch_tc3(const Tc3Args& args, int units, cudaStream_t st) {
   const size_t smem = tc3_smem_bytes<X3>(args.Hq);
   if (smem > 227 * 1024) return B200VAE_EUNSUP;
   static int max_clusters = 0;
-  if (max_clusters == 0) {
-    cudaFuncSetAttribute(icnn_tc3_fwd_kernel<D, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(k3Threads); cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute at;
-    at.id = cudaLaunchAttributeClusterDimension;
-    at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-    cfg.attrs = &at; cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, icnn_tc3_fwd_kernel<D, X3>, &cfg) != cudaSuccess || n <= 0) {
-      (void)cudaGetLastError();
-      n = sm_count() / 2;
-    }
-    max_clusters = n;
-  }
+  if (max_clusters == 0) max_clusters = max_clusters_for(reinterpret_cast<const void*>(icnn_tc3_fwd_kernel<D, X3>), smem);
   // every cluster must be resident (GEMM2 units wait for GEMM1 units of other clusters): never exceed one wave
   const int G = units < max_clusters ? units : max_clusters;
   icnn_tc3_fwd_kernel<D, X3><<<2 * G, k3Threads, smem, st>>>(args);
@@ -668,24 +1218,12 @@ int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float*
   float* tb = tc_base(ws, d, H);
   float* t3 = tb + T.end;
   const bool x3 = (precision == B200VAE_PREC_TF32X3);
-  static std::mutex mu;
-  static std::unordered_map<uint64_t, Tc3Args> cache;       // tensor maps only encode (address, shape)
   Tc3Args args;
   {
-    std::lock_guard<std::mutex> lk(mu);
-    const uint64_t key = reinterpret_cast<uint64_t>(t3) ^ ((uint64_t)T3.Hq << 48) ^ ((uint64_t)x3 << 63);
-    auto itc = cache.find(key);
-    if (itc == cache.end()) {
-      int rc = make_map3(&args.b1hi, t3 + T3.B1ahi, T3.K1, T3.Hq);
-      if (!rc) rc = make_map3(&args.b1lo, t3 + (x3 ? T3.B1alo : T3.B1ahi), T3.K1, T3.Hq);
-      if (!rc) rc = make_map3(&args.b2hi, t3 + T3.B2ghi, T3.Hq, T3.Hq);
-      if (!rc) rc = make_map3(&args.b2lo, t3 + (x3 ? T3.B2glo : T3.B2ghi), T3.Hq, T3.Hq);
-      if (rc) return rc;
-      if (cache.size() > 256) cache.clear();
-      cache.emplace(key, args);
-    } else {
-      args = itc->second;
-    }
+    Tc3Maps mp;
+    int rc = get_maps3(t3, T3, x3, &mp);
+    if (rc) return rc;
+    args.b1hi = mp.b1hi; args.b1lo = mp.b1lo; args.b2hi = mp.b2hi; args.b2lo = mp.b2lo;
   }
   args.z = z;
   args.A0g = reinterpret_cast<const float4*>(t3 + T3.A0g);
