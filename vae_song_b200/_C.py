@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200vae.so")
+LIB_PATH = os.environ.get("B200VAE_LIB", os.path.join(_HERE, "libb200vae.so"))   # override: A/B builds of the library
 CSRC = os.path.join(_HERE, "csrc")
 
 WEIGHT_EXP, WEIGHT_CLAMP = 0, 1

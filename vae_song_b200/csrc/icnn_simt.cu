@@ -641,13 +641,13 @@ icnn_bwd_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, co
 // ------------------------------------------------------------------------------------- finalize
 __global__ void finalize_W0_kernel(const float* __restrict__ part, int splits, int H, int Hp, int ldp,
                                    const float* __restrict__ P0, const float* __restrict__ P1,
-                                   const float* __restrict__ W0raw, int mode, float* __restrict__ dW0) {
-  // part: [splits][ldp][ldp] ordered split-K partials of sum_b s2*s1[b,k] * q1[b,n]; P1[k] is applied here
+                                   const float* __restrict__ W0raw, int mode, float scale, float* __restrict__ dW0) {
+  // part: [splits][ldp][ldp] ordered split-K partials of sum_b s2*s1[b,k] * q1[b,n] / scale; scale*P1[k] is applied here
   const int n = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
   if (n >= H) return;
   float s = 0.f;
   for (int sp = 0; sp < splits; ++sp) s += part[((size_t)sp * ldp + k) * ldp + n];
-  const float dP = P1[k] * s;
+  const float dP = (scale * P1[k]) * s;
   float g;
   if (mode == B200VAE_WEIGHT_EXP) g = dP * P0[(size_t)k * Hp + n];
   else g = (W0raw[(size_t)k * H + n] >= kClampMin) ? dP : 0.f;
@@ -747,14 +747,14 @@ int simt_bwd_W0(const float* z, const float* v, const uint32_t* mask1, const uin
   }
   if (rc) return rc;
   dim3 grid((H + 255) / 256, H);
-  finalize_W0_kernel<<<grid, 256, 0, st>>>(ws + L.dP0part, L.splits, H, L.Hp, L.Hp, ws + L.P0, ws + L.P1, p->W0, mode, gW0);
+  finalize_W0_kernel<<<grid, 256, 0, st>>>(ws + L.dP0part, L.splits, H, L.Hp, L.Hp, ws + L.P0, ws + L.P1, p->W0, mode, 1.f, gW0);
   return check_launch();
 }
 
 int finalize_W0_launch(const float* part, int splits, int H, int Hp, int ldp, const float* P0, const float* P1,
-                       const float* W0raw, int mode, float* dW0, cudaStream_t st) {
+                       const float* W0raw, int mode, float scale, float* dW0, cudaStream_t st) {
   dim3 grid((H + 255) / 256, H);
-  finalize_W0_kernel<<<grid, 256, 0, st>>>(part, splits, H, Hp, ldp, P0, P1, W0raw, mode, dW0);
+  finalize_W0_kernel<<<grid, 256, 0, st>>>(part, splits, H, Hp, ldp, P0, P1, W0raw, mode, scale, dW0);
   return check_launch();
 }
 
@@ -799,7 +799,7 @@ int simt_bwd(const float* z, const float* v, const float* gpsi, const uint32_t* 
   if (!g) return B200VAE_OK;
   if (need_W0) {
     dim3 grid((H + 255) / 256, H);
-    finalize_W0_kernel<<<grid, 256, 0, st>>>(ws + L.dP0part, L.splits, H, L.Hp, L.Hp, ws + L.P0, ws + L.P1, p->W0, mode, g->W0);
+    finalize_W0_kernel<<<grid, 256, 0, st>>>(ws + L.dP0part, L.splits, H, L.Hp, L.Hp, ws + L.P0, ws + L.P1, p->W0, mode, 1.f, g->W0);
     rc = check_launch();
     if (rc) return rc;
   }

@@ -656,7 +656,7 @@ icnn_tc_bwd_rows_kernel(const __grid_constant__ TcMaps maps, const float* __rest
 }
 
 // ====================================== backward, dP0 (batch-reduced) ===================================
-// dP0part[split][o][n] = sum_{m in split} s2[m] s1[m,o] * q1[m,n]      (P1[o] and the exp/clamp chain: finalize)
+// dP0part[split][o][n] = sum_{m in split} (1 + 4 bit[m,o]) * s2[m] q1[m,n]   (0.2 P1[o] and the exp/clamp chain: finalize)
 // Output-stationary 256 x 256 tile in TMEM, K = the CTA's batch slice.  BOTH operands are generated: a sample
 // (= K index) is owned by a thread, which emits 8 consecutive o's / n's as 16-byte chunks -> MN-major UMMA
 // layout.  For 32-bit MN-major operands the only legal UMMA layout is SWIZZLE_128B_BASE32B (cute
@@ -708,9 +708,14 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
   if (warp_u < kNW) {
     const int ks = tid & 15, u = tid >> 4, blk = u >> 2, qd = u & 3;     // sample-in-stage, MN block, 8-wide quarter
     const int g4 = ks >> 2, kr = ks & 3;                                 // group of 4 k, k-row inside the atom
-    float4 q[8];
+    // my 8 n's as 4 pairs (packed f32x2 math): component arrays (w0, w1, w2, bias)
+    float2 qx2[4], qy2[4], qz2[4], qw2[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) q[e] = A0q_g[n0 + blk * 32 + qd * 8 + e];
+    for (int i = 0; i < 4; ++i) {
+      const float4 qa = A0q_g[n0 + blk * 32 + qd * 8 + 2 * i], qb = A0q_g[n0 + blk * 32 + qd * 8 + 2 * i + 1];
+      qx2[i] = make_float2(qa.x, qb.x); qy2[i] = make_float2(qa.y, qb.y);
+      qz2[i] = make_float2(qa.z, qb.z); qw2[i] = make_float2(qa.w, qb.w);
+    }
     const uint32_t off0 = (uint32_t)((g4 * 8 + blk) * 512 + kr * 128) + ((uint32_t)(qd ^ kr) << 5), off1 = off0 + 16;
     // per-sample inputs (z, v, s2, the 8 mask words of this o-tile) are staged through shared memory in
     // chunks of 256 samples, fetched one chunk ahead (register staged) so no global latency is exposed
@@ -754,13 +759,29 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
       for (int j = 0; j < D; ++j) { zr[j] = zf[j * CH + sl]; vr[j] = zf[(D + j) * CH + sl]; }
       const float s2f = zf[2 * D * CH + sl];
       const uint32_t bits = sampw[buf * (CH * 8) + blk * CH + sl] >> (qd * 8);
+      // A = 1 + 4*bit (the LeakyReLU slope / 0.2, exact in tf32; 0.2 and P1 are applied by finalize_W0);
+      // B = s2 q1 = (2 s2 A0 v) . max(h0, 0.04 h0), two n's per packed instruction
       float av[8], bv[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        av[e] = ((bits >> e) & 1u) ? s2f : kSlope * s2f;
-        const float h = lin_of<D>(q[e], zr), u0 = dot_of<D>(q[e], vr);
-        const float s0 = slope_of(h), a0 = h * s0;
-        bv[e] = u0 * (2.f * a0) * s0;
+      for (int e = 0; e < 8; ++e) av[e] = ((bits >> e) & 1u) ? 5.f : 1.f;
+      float sv[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) sv[j] = (2.f * s2f) * vr[j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 h = __ffma2_rn(qx2[i], make_float2(zr[0], zr[0]), qw2[i]);
+        float2 uu = __fmul2_rn(qx2[i], make_float2(sv[0], sv[0]));
+        if (D > 1) {
+          h = __ffma2_rn(qy2[i], make_float2(zr[D > 1 ? 1 : 0], zr[D > 1 ? 1 : 0]), h);
+          uu = __ffma2_rn(qy2[i], make_float2(sv[D > 1 ? 1 : 0], sv[D > 1 ? 1 : 0]), uu);
+        }
+        if (D > 2) {
+          h = __ffma2_rn(qz2[i], make_float2(zr[D > 2 ? 2 : 0], zr[D > 2 ? 2 : 0]), h);
+          uu = __ffma2_rn(qz2[i], make_float2(sv[D > 2 ? 2 : 0], sv[D > 2 ? 2 : 0]), uu);
+        }
+        const float2 l = __fmul2_rn(h, make_float2(kSlope * kSlope, kSlope * kSlope));
+        const float2 x = __fmul2_rn(uu, make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y)));
+        bv[2 * i] = x.x; bv[2 * i + 1] = x.y;
       }
       if ((kb & 15) == 15 && c + 1 < nchunk) {               // next chunk's buffer was last read 16 stages ago
         worker_bar();
@@ -770,20 +791,21 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
       const uint32_t s = kb % S, ph = (kb / S) & 1;
       mbar_wait(empty0 + 8 * s, ph ^ 1);
       unsigned char* st = stages + s * kStage;
-      auto put = [&](unsigned char* base, const float (&x)[8]) {
-        const float4 h0 = make_float4(to_tf32(x[0]), to_tf32(x[1]), to_tf32(x[2]), to_tf32(x[3]));
-        const float4 h1 = make_float4(to_tf32(x[4]), to_tf32(x[5]), to_tf32(x[6]), to_tf32(x[7]));
-        *reinterpret_cast<float4*>(base + off0) = h0;
-        *reinterpret_cast<float4*>(base + off1) = h1;
-        if (X3) {
-          *reinterpret_cast<float4*>(base + kTileBytes + off0) =
-              make_float4(to_tf32(x[0] - h0.x), to_tf32(x[1] - h0.y), to_tf32(x[2] - h0.z), to_tf32(x[3] - h0.w));
-          *reinterpret_cast<float4*>(base + kTileBytes + off1) =
-              make_float4(to_tf32(x[4] - h1.x), to_tf32(x[5] - h1.y), to_tf32(x[6] - h1.z), to_tf32(x[7] - h1.w));
-        }
-      };
-      put(st, av);
-      put(st + kOffB, bv);
+      *reinterpret_cast<float4*>(st + off0) = make_float4(av[0], av[1], av[2], av[3]);       // exact: no lo part
+      *reinterpret_cast<float4*>(st + off1) = make_float4(av[4], av[5], av[6], av[7]);
+      if (X3) {
+        const float4 h0 = make_float4(rn_tf32_masked(bv[0]), rn_tf32_masked(bv[1]), rn_tf32_masked(bv[2]), rn_tf32_masked(bv[3]));
+        const float4 h1 = make_float4(rn_tf32_masked(bv[4]), rn_tf32_masked(bv[5]), rn_tf32_masked(bv[6]), rn_tf32_masked(bv[7]));
+        *reinterpret_cast<float4*>(st + kOffB + off0) = h0;
+        *reinterpret_cast<float4*>(st + kOffB + off1) = h1;
+        *reinterpret_cast<float4*>(st + kOffBlo + off0) =
+            make_float4(rn_tf32_fast(bv[0] - h0.x), rn_tf32_fast(bv[1] - h0.y), rn_tf32_fast(bv[2] - h0.z), rn_tf32_fast(bv[3] - h0.w));
+        *reinterpret_cast<float4*>(st + kOffBlo + off1) =
+            make_float4(rn_tf32_fast(bv[4] - h1.x), rn_tf32_fast(bv[5] - h1.y), rn_tf32_fast(bv[6] - h1.z), rn_tf32_fast(bv[7] - h1.w));
+      } else {
+        *reinterpret_cast<float4*>(st + kOffB + off0) = make_float4(rn_tf32_masked(bv[0]), rn_tf32_masked(bv[1]), rn_tf32_masked(bv[2]), rn_tf32_masked(bv[3]));
+        *reinterpret_cast<float4*>(st + kOffB + off1) = make_float4(rn_tf32_masked(bv[4]), rn_tf32_masked(bv[5]), rn_tf32_masked(bv[6]), rn_tf32_masked(bv[7]));
+      }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(full0 + 8 * s);
@@ -826,11 +848,9 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
             const uint64_t a_hi = sa + (uint64_t)((g * 8192 + half * 2048) >> 4);     // K=8 = two 4-k groups
             const uint64_t b_hi = sa + (uint64_t)((kOffB + g * 8192) >> 4);
             const uint32_t acc = (kb | g) ? 1u : 0u;
-            if (X3) {
-              const uint64_t a_lo = a_hi + (uint64_t)(kOffAlo >> 4);
+            if (X3) {                                                        // A is exact: a_hi.b_lo + a_hi.b_hi
               const uint64_t b_lo = sa + (uint64_t)((kOffBlo + g * 8192) >> 4);
-              umma_tf32(d_t, a_lo, b_hi, kIdescTf32MN, acc);
-              umma_tf32(d_t, a_hi, b_lo, kIdescTf32MN, 1u);
+              umma_tf32(d_t, a_hi, b_lo, kIdescTf32MN, acc);
               umma_tf32(d_t, a_hi, b_hi, kIdescTf32MN, 1u);
             } else {
               umma_tf32(d_t, a_hi, b_hi, kIdescTf32MN, acc);
@@ -1035,7 +1055,7 @@ static int launch_tc_bwd(const TcMaps& maps, const float* z, const float* v, con
 }
 
 int finalize_W0_launch(const float* part, int splits, int H, int Hp, int ldp, const float* P0, const float* P1,
-                       const float* W0raw, int mode, float* dW0, cudaStream_t st);
+                       const float* W0raw, int mode, float scale, float* dW0, cudaStream_t st);
 
 template <int D, bool X3>
 static int launch_tc_dp0(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B,
@@ -1109,7 +1129,7 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
     }
 #undef B200VAE_TCD
     if (rc) return rc;
-    rc = finalize_W0_launch(part, splits, H, L.Hp, T.Hq, ws + L.P0, ws + L.P1, p->W0, mode, g->W0, st);
+    rc = finalize_W0_launch(part, splits, H, L.Hp, T.Hq, ws + L.P0, ws + L.P1, p->W0, mode, kSlope, g->W0, st);
     if (rc) return rc;
   }
   dim3 fgrid(T.Hq / 32, d + 1, 2);

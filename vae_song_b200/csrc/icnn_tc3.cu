@@ -78,9 +78,6 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// round-to-nearest (ties away) to tf32 in one integer add: tcgen05 kind::tf32 ignores the 13 low mantissa bits
-__device__ __forceinline__ float rn_tf32_fast(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
-__device__ __forceinline__ float rn_tf32_masked(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 // ------------------------------------------------------------------------------------ prepare
 // grid (ceil(K1/256), Hq): row r, column c of the four operand copies; row 0 also packs the per-unit parameter tables

@@ -89,6 +89,14 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(u);
 }
 
+// round-to-nearest (ties away) to tf32 in one integer add: tcgen05 kind::tf32 ignores the 13 low mantissa bits
+#ifdef B200VAE_MASKED_RN
+__device__ __forceinline__ float rn_tf32_fast(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+#else
+__device__ __forceinline__ float rn_tf32_fast(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+#endif
+__device__ __forceinline__ float rn_tf32_masked(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
 // K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 |
 // SBO(512 B >> 4)<<32 | version(1)<<46 | layout SWIZZLE_64B(4)<<61.  8-row atoms of 64-byte rows.
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
