@@ -27,8 +27,6 @@ int simt_bwd(const float* z, const float* v, const float* gpsi, const uint32_t* 
 int tc_prepare(const b200vae_icnn_params* p, int d, int H, int mode, int precision, float* ws, cudaStream_t st);
 int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1,
            uint8_t* mask2, int precision, const float* ws, cudaStream_t st);
-int tc2_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1,
-            uint8_t* mask2, int precision, const float* ws, cudaStream_t st);
 int tc3_prepare(int d, int H, int precision, float* ws, cudaStream_t st);
 int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2,
             int precision, float* ws, cudaStream_t st);
@@ -92,13 +90,12 @@ extern "C" int b200vae_icnn_decode_fwd(const float* z, int B, int d, int H, int 
   if (precision == B200VAE_PREC_FP32)
     return simt_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, ws_base(ws), (cudaStream_t)stream);
   // forward kernel variant, B200VAE_FWD = 3 (default): persistent CTA pairs (icnn_tc3.cu), falling back to 1 where it
-  // does not fit (H > 1024); 2: one-tile-per-pair kernel (icnn_tc2.cu); 1: single-CTA kernel (icnn_tc.cu)
+  // does not fit (H > 1024); 1: single-CTA kernel (icnn_tc.cu)
   static const int variant = [] { const char* e = getenv("B200VAE_FWD"); return e ? atoi(e) : 3; }();
   if (variant == 3) {
     rc = tc3_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), (cudaStream_t)stream);
     if (rc != B200VAE_EUNSUP) return rc;
   }
-  if (variant == 2) return tc2_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), (cudaStream_t)stream);
   return tc_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), (cudaStream_t)stream);
 }
 
