@@ -194,7 +194,11 @@ def run_ours(args, rank, local_rank, world):
             ic.W[0].param.copy_(torch.tensor(wr.normal(np.log(1.0 / H), 1.0, (H, H)), dtype=torch.float32))
             ic.W[1].param.copy_(torch.tensor(wr.normal(np.log(2.0 / H), 1.0, (1, H)), dtype=torch.float32))
             ic.A[0].bias.copy_(torch.tensor(wr.normal(-0.3, 1.0, (H,)), dtype=torch.float32))
-    tr = train.DataParallelTrainer(m, lr=1e-3)
+    tr = train.DataParallelTrainer(m, lr=1e-3, comm=args.comm)
+    exchange = "none (1 GPU)" if world == 1 else (
+        "peer-memory kernels over NVLink: BatchNorm statistics inside the encoder finalize kernels, two-shot gradient "
+        "all-reduce fused with Adam (no NCCL call in the step)" if tr.peer is not None else
+        "NCCL: all_gather/all_reduce per BatchNorm layer + one flat gradient all-reduce")
     rng = np.random.default_rng(100 + rank)
     n_pool = 4
     host_pool = [torch.from_numpy(chessboard(B, rng)).pin_memory() for _ in range(n_pool)]
@@ -343,7 +347,7 @@ def run_ours(args, rank, local_rank, world):
                 "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
                 "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "precision": args.precision,
                            "parallelism": f"dp{world}", "l2": "flushed between timed iterations (256 MB write)",
-                           "optimizer": "fused Adam lr 1e-3 over flat buffer",
+                           "optimizer": "fused Adam lr 1e-3 over flat buffer", "exchange": exchange,
                            "cuda_graph": bool(use_graph), "own_kernel_launches_per_step": int(launches_per_step)},
                 "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 2 * 4 * world,
                         "d2h_bytes_per_step": 4 * world},
@@ -370,6 +374,8 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="per-GPU batch")
     ap.add_argument("--precision", default=os.environ.get("B200VAE_PRECISION", "tf32x3"), choices=["fp32", "tf32", "tf32x3"],
                     help="arithmetic of the H x H contractions in the train step (fp32 = SIMT parity path)")
+    ap.add_argument("--comm", default="auto", choices=["auto", "peer", "nccl"],
+                    help="multi-GPU exchange back-end (train.DataParallelTrainer): peer-memory kernels or NCCL")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--roofline-precision", default="tf32", choices=["fp32", "tf32", "tf32x3"])
     args = ap.parse_args()

@@ -174,6 +174,59 @@ int b200vae_nn_sqdist_fwd(const float* A, const float* Bp, int B, int Na, int Nb
 int b200vae_nn_sqdist_bwd(const float* A, const float* Bp, const int* argA, const int* argB, const float* gA,
                           const float* gB, int B, int Na, int Nb, int dim, float* dA, void* stream);
 
+/* ---- peer-memory exchange between the GPUs of one node (the data-parallel exchange steps) ---------------
+ * The reference has no multi-GPU path; these replace what torch.distributed/NCCL would do for the LATENCY-bound
+ * collectives of the sharded train step (BatchNorm statistics of model.py:711-734's encoder, 1 KB each, ten per step)
+ * and for the gradient all-reduce + Adam of lipschitz.py:41-43, as kernels that read/write the other GPUs' memory
+ * directly over NVLink / NVSwitch.
+ *
+ * Set-up (host, once): every rank calls b200vae_peer_alloc (cudaMalloc + zero fill + CUDA IPC handle), exchanges the
+ * 64-byte handles out of band (torch.distributed.all_gather_object), maps the others with b200vae_peer_open and
+ * fills a b200vae_peer_t with buf[r] = rank r's buffer as addressable from THIS process (own buffer at buf[rank]).
+ * A host barrier must separate set-up from the first exchange.  Every rank must issue the same sequence of
+ * exchanges per slot (they are collective).  A peer that never arrives times out after 4 s (no GPU hang) and sets a
+ * sticky flag readable with b200vae_peer_timed_out. */
+#define B200VAE_PEER_MAX_WORLD 16
+#define B200VAE_PEER_HANDLE_BYTES 64
+typedef struct b200vae_peer {
+  int world, rank;
+  void* buf[B200VAE_PEER_MAX_WORLD];
+} b200vae_peer_t;
+size_t b200vae_peer_exchange_bytes(void);  /* size of the exchange buffer (b200vae_peer_num_slots() slots)          */
+int b200vae_peer_num_slots(void);
+int b200vae_peer_max_payload(void);        /* floats per rank per exchange                                         */
+int b200vae_peer_alloc(size_t bytes, void** buf, unsigned char* handle /*[64]*/);
+int b200vae_peer_open(const unsigned char* handle /*[64]*/, void** mapped);
+int b200vae_peer_close(void* mapped);
+int b200vae_peer_free(void* buf);
+int b200vae_peer_timed_out(const b200vae_peer_t* comm, int* out /*host*/);
+/* out [world][n] = every rank's `in` [n] (n <= b200vae_peer_max_payload()); one CTA, a few microseconds. */
+int b200vae_peer_allgather(const b200vae_peer_t* comm, int slot, const float* in, int n, float* out, void* stream);
+
+/* b200vae_mlp_layer_fwd with CROSS-RANK BatchNorm statistics: the kernel that finalises this rank's (count, mean, M2)
+ * publishes them to every peer, waits for theirs and Chan-combines in rank order, so stats_out / running stats are the
+ * global-batch values, bit-identical on every rank.  stats_out must be non-NULL. */
+int b200vae_mlp_layer_fwd_peer(const float* in_y, const float* in_stats, const float* in_gamma, const float* in_beta,
+                               float slope, const float* W, const float* bias, int B, int wi, int wo, float* y_out,
+                               float* stats_out, float eps, float* running_mean, float* running_var, float momentum,
+                               void* scratch, const b200vae_peer_t* comm, int slot, void* stream);
+/* b200vae_mlp_layer_bwd_reduce that also all-reduces the two sums over the ranks: sums_local [2][w] (this rank's
+ * dbeta, dgamma contribution) and sums_global [2][w] (what b200vae_mlp_layer_bwd needs, with inv_n = 1/global batch). */
+int b200vae_mlp_layer_bwd_reduce_peer(const float* da, const float* y, const float* stats, const float* gamma,
+                                      const float* beta, float slope, int B, int w, float* dyhat, float* sums_local,
+                                      float* sums_global, void* scratch, const b200vae_peer_t* comm, int slot,
+                                      void* stream);
+
+/* Gradient all-reduce FUSED with Adam (lipschitz.py:41-43 across ranks), two-shot over peer memory: rank r sums chunk r
+ * of every rank's gradient buffer (peer loads, rank order => deterministic), applies Adam to chunk r of the parameters
+ * (moments m, v: only chunk r is touched on rank r) and stores the updated chunk into EVERY rank's parameter buffer.
+ * grads[r] / params[r]: rank r's flat fp32 buffers (n floats, b200vae_peer_alloc'ed and opened like the exchange
+ * buffer; n % 4 == 0).  Bracketed by two exchanges on `slot`, `slot`+1 (gradients complete / parameters written).
+ * grad_scale multiplies the summed gradient (1/world for a batch mean). */
+int b200vae_peer_allreduce_adam(const b200vae_peer_t* comm, int slot, void* const* grads, void* const* params,
+                                float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                                float weight_decay, long long* step_dev, float grad_scale, void* stream);
+
 int b200vae_last_cuda_error(void);
 const char* b200vae_version(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */

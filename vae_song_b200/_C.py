@@ -28,7 +28,11 @@ EXPORTS = [
     "b200vae_lipschitz_num_tiles", "b200vae_adam_step", "b200vae_adam_step_dev", "b200vae_mlp_scratch_bytes", "b200vae_mlp_layer_fwd",
     "b200vae_mlp_layer_bwd_reduce", "b200vae_mlp_layer_bwd", "b200vae_nn_sqdist_fwd", "b200vae_nn_sqdist_bwd", "b200vae_last_cuda_error", "b200vae_version",
     "b200vae_launch_count",
+    "b200vae_peer_exchange_bytes", "b200vae_peer_num_slots", "b200vae_peer_max_payload", "b200vae_peer_alloc", "b200vae_peer_open",
+    "b200vae_peer_close", "b200vae_peer_free", "b200vae_peer_timed_out", "b200vae_peer_allgather", "b200vae_mlp_layer_fwd_peer",
+    "b200vae_mlp_layer_bwd_reduce_peer", "b200vae_peer_allreduce_adam",
 ]
+PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 64
 
 
 class B200VaeError(RuntimeError):
@@ -41,6 +45,11 @@ class IcnnParams(C.Structure):
 
 class IcnnGrads(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("A0w", "A0b", "A1w", "A1b", "A2w", "A2b", "W0", "W1")]
+
+
+class PeerStruct(C.Structure):
+    """b200vae_peer_t"""
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("buf", C.c_void_p * 16)]
 
 
 PARAM_FIELDS = ("A0w", "A0b", "A1w", "A1b", "A2w", "A2b", "W0", "W1")
@@ -104,6 +113,29 @@ def load():
     lib.b200vae_nn_sqdist_fwd.argtypes = [vp, vp, i, i, i, i, vp, vp, vp]
     lib.b200vae_nn_sqdist_bwd.restype = i
     lib.b200vae_nn_sqdist_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp]
+    pp = C.POINTER(PeerStruct)
+    lib.b200vae_peer_exchange_bytes.restype = sz
+    lib.b200vae_peer_exchange_bytes.argtypes = []
+    lib.b200vae_peer_num_slots.restype = i
+    lib.b200vae_peer_max_payload.restype = i
+    lib.b200vae_peer_alloc.restype = i
+    lib.b200vae_peer_alloc.argtypes = [sz, C.POINTER(vp), C.c_char_p]
+    lib.b200vae_peer_open.restype = i
+    lib.b200vae_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.b200vae_peer_close.restype = i
+    lib.b200vae_peer_close.argtypes = [vp]
+    lib.b200vae_peer_free.restype = i
+    lib.b200vae_peer_free.argtypes = [vp]
+    lib.b200vae_peer_timed_out.restype = i
+    lib.b200vae_peer_timed_out.argtypes = [pp, C.POINTER(i)]
+    lib.b200vae_peer_allgather.restype = i
+    lib.b200vae_peer_allgather.argtypes = [pp, i, vp, i, vp, vp]
+    lib.b200vae_mlp_layer_fwd_peer.restype = i
+    lib.b200vae_mlp_layer_fwd_peer.argtypes = [vp, vp, vp, vp, f, vp, vp, i, i, i, vp, vp, f, vp, vp, f, vp, pp, i, vp]
+    lib.b200vae_mlp_layer_bwd_reduce_peer.restype = i
+    lib.b200vae_mlp_layer_bwd_reduce_peer.argtypes = [vp, vp, vp, vp, vp, f, i, i, vp, vp, vp, vp, pp, i, vp]
+    lib.b200vae_peer_allreduce_adam.restype = i
+    lib.b200vae_peer_allreduce_adam.argtypes = [pp, i, C.POINTER(vp), C.POINTER(vp), vp, vp, ll, f, f, f, f, f, vp, f, vp]
     lib.b200vae_last_cuda_error.restype = i
     lib.b200vae_version.restype = C.c_char_p
     lib.b200vae_launch_count.restype = ll

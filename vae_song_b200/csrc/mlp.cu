@@ -8,9 +8,11 @@
 //   backward: (1) dyhat = da * lrelu'(.) + per-column sums S1 = sum dyhat, S2 = sum dyhat*xhat,
 //             (2) da_prev = dy W  and  dW = dy^T act(prev)  with dy = gamma*invstd*(dyhat - S1/N - xhat*S2/N) formed on
 //                 the fly, both on the 128x128x16 FP32 tile core (gemm_simt.cuh).
-// Everything but y / dyhat / da stays on chip; cross-rank BatchNorm only needs the tiny (mean,var) / (S1,S2) vectors
-// exchanged between launches (done by the host side, train.py).
+// Everything but y / dyhat / da stays on chip; cross-rank BatchNorm only needs the tiny (count,mean,M2) / (S1,S2)
+// vectors exchanged: the *_peer finalize kernels publish them straight into the other GPUs' memory over NVLink and
+// combine in rank order (peer.cuh), so a sharded step has no NCCL call and no torch glue per BatchNorm layer.
 #include "gemm_simt.cuh"
+#include "peer.cuh"
 
 namespace b200vae {
 
@@ -165,6 +167,47 @@ mlp_stats_finalize_kernel(const float* __restrict__ part, int ncta, int w, float
   }
 }
 
+// Cross-rank variant: ONE CTA of 32 warps.  Local (count, mean, M2) per column -> peer exchange -> Chan merge of the
+// ranks' triples in rank order (identical on every rank).
+__global__ void __launch_bounds__(1024)
+mlp_stats_finalize_peer_kernel(const float* __restrict__ part, int ncta, int w, float eps, float* __restrict__ stats,
+                               float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                               PeerComm comm, int slot) {
+  __shared__ float mine[3 * 128];
+  __shared__ float all[kPeerMaxWorld * 3 * 128];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int n = wp; n < w; n += 32) {
+    float cnt = 0.f, mean = 0.f, m2 = 0.f;
+    for (int c = lane; c < ncta; c += 32) {
+      const float* p = part + ((size_t)c * 128 + n) * 3;
+      chan_merge(cnt, mean, m2, p[0], p[1], p[2]);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const float nb = __shfl_down_sync(0xffffffffu, cnt, off), mb = __shfl_down_sync(0xffffffffu, mean, off),
+                  m2b = __shfl_down_sync(0xffffffffu, m2, off);
+      chan_merge(cnt, mean, m2, nb, mb, m2b);
+    }
+    if (lane == 0) { mine[n] = cnt; mine[w + n] = mean; mine[2 * w + n] = m2; }
+  }
+  __syncthreads();
+  peer_exchange(comm, slot, mine, 3 * w, all);
+  const int n = threadIdx.x;
+  if (n < w) {
+    float cnt = 0.f, mean = 0.f, m2 = 0.f;
+    for (int r = 0; r < comm.world; ++r) {
+      const float* a = all + (size_t)r * 3 * w;
+      chan_merge(cnt, mean, m2, a[n], a[w + n], a[2 * w + n]);
+    }
+    const float var = m2 / cnt;
+    stats[n] = mean; stats[w + n] = var; stats[2 * w + n] = rsqrtf(var + eps); stats[3 * w + n] = cnt;
+    if (running_mean) {
+      running_mean[n] = (1.f - momentum) * running_mean[n] + momentum * mean;
+      running_var[n] = (1.f - momentum) * running_var[n] + momentum * (m2 / fmaxf(cnt - 1.f, 1.f));
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------- backward (1): reduce
 // dyhat = da * lrelu'(gamma*xhat+beta) ; S1 = sum dyhat ; S2 = sum dyhat*xhat.  w must divide 256 (power of two <= 128).
 __global__ void __launch_bounds__(256)
@@ -205,6 +248,30 @@ mlp_sum_finalize_kernel(const float* __restrict__ part, int nblk, int w, float* 
   for (int c = lane; c < nblk; c += 32) { a += part[((size_t)c * 128 + n) * 2]; b += part[((size_t)c * 128 + n) * 2 + 1]; }
   a = warp_sum(a); b = warp_sum(b);
   if (lane == 0) { sums[n] = a; sums[w + n] = b; }
+}
+
+// Cross-rank variant: local sums (parameter gradients of gamma/beta) and the rank-ordered global sums (for dy).
+__global__ void __launch_bounds__(1024)
+mlp_sum_finalize_peer_kernel(const float* __restrict__ part, int nblk, int w, float* __restrict__ sums_local,
+                             float* __restrict__ sums_global, PeerComm comm, int slot) {
+  __shared__ float mine[2 * 128];
+  __shared__ float all[kPeerMaxWorld * 2 * 128];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int n = wp; n < w; n += 32) {
+    float a = 0.f, b = 0.f;
+    for (int c = lane; c < nblk; c += 32) { a += part[((size_t)c * 128 + n) * 2]; b += part[((size_t)c * 128 + n) * 2 + 1]; }
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) { mine[n] = a; mine[w + n] = b; }
+  }
+  __syncthreads();
+  peer_exchange(comm, slot, mine, 2 * w, all);
+  const int i = threadIdx.x;
+  if (i < 2 * w) {
+    float s = 0.f;
+    for (int r = 0; r < comm.world; ++r) s += all[(size_t)r * 2 * w + i];
+    sums_global[i] = s;
+    if (sums_local) sums_local[i] = mine[i];
+  }
 }
 
 // dy[b][o] formed on the fly from dyhat, y, stats and the (global) sums
@@ -527,10 +594,10 @@ extern "C" size_t b200vae_mlp_scratch_bytes(int B) {
   return m * sizeof(float);
 }
 
-extern "C" int b200vae_mlp_layer_fwd(const float* in_y, const float* in_stats, const float* in_gamma, const float* in_beta,
-                                     float slope, const float* W, const float* bias, int B, int wi, int wo, float* y_out,
-                                     float* stats_out, float eps, float* running_mean, float* running_var, float momentum,
-                                     void* scratch, void* stream) {
+static int mlp_layer_fwd_impl(const float* in_y, const float* in_stats, const float* in_gamma, const float* in_beta,
+                              float slope, const float* W, const float* bias, int B, int wi, int wo, float* y_out,
+                              float* stats_out, float eps, float* running_mean, float* running_var, float momentum,
+                              void* scratch, const b200vae_peer_t* comm, int slot, void* stream) {
   if (!in_y || !W || !y_out || !scratch) return B200VAE_EALIGN;
   if (B <= 0 || wi < 1 || wi > 128 || wo < 1 || wo > 128) return B200VAE_ESHAPE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -545,14 +612,35 @@ extern "C" int b200vae_mlp_layer_fwd(const float* in_y, const float* in_stats, c
   }
   int rc = check_launch();
   if (rc || !stats_out) return rc;
-  mlp_stats_finalize_kernel<<<(wo + 7) / 8, 256, 0, st>>>((const float*)scratch, ncta, wo, eps, stats_out, running_mean, running_var, momentum);
+  if (comm)
+    mlp_stats_finalize_peer_kernel<<<1, 1024, 0, st>>>((const float*)scratch, ncta, wo, eps, stats_out, running_mean,
+                                                      running_var, momentum, make_peer(comm), slot);
+  else
+    mlp_stats_finalize_kernel<<<(wo + 7) / 8, 256, 0, st>>>((const float*)scratch, ncta, wo, eps, stats_out, running_mean, running_var, momentum);
   return check_launch();
 }
+extern "C" int b200vae_mlp_layer_fwd(const float* in_y, const float* in_stats, const float* in_gamma, const float* in_beta,
+                                     float slope, const float* W, const float* bias, int B, int wi, int wo, float* y_out,
+                                     float* stats_out, float eps, float* running_mean, float* running_var, float momentum,
+                                     void* scratch, void* stream) {
+  return mlp_layer_fwd_impl(in_y, in_stats, in_gamma, in_beta, slope, W, bias, B, wi, wo, y_out, stats_out, eps,
+                            running_mean, running_var, momentum, scratch, nullptr, 0, stream);
+}
+extern "C" int b200vae_mlp_layer_fwd_peer(const float* in_y, const float* in_stats, const float* in_gamma,
+                                          const float* in_beta, float slope, const float* W, const float* bias, int B,
+                                          int wi, int wo, float* y_out, float* stats_out, float eps, float* running_mean,
+                                          float* running_var, float momentum, void* scratch, const b200vae_peer_t* comm,
+                                          int slot, void* stream) {
+  if (!peer_ok(comm, slot) || !stats_out) return B200VAE_EALIGN;
+  return mlp_layer_fwd_impl(in_y, in_stats, in_gamma, in_beta, slope, W, bias, B, wi, wo, y_out, stats_out, eps,
+                            running_mean, running_var, momentum, scratch, comm, slot, stream);
+}
 
-extern "C" int b200vae_mlp_layer_bwd_reduce(const float* da, const float* y, const float* stats, const float* gamma,
-                                            const float* beta, float slope, int B, int w, float* dyhat, float* sums,
-                                            void* scratch, void* stream) {
-  if (!da || !dyhat || !sums || !scratch) return B200VAE_EALIGN;
+static int mlp_layer_bwd_reduce_impl(const float* da, const float* y, const float* stats, const float* gamma,
+                                     const float* beta, float slope, int B, int w, float* dyhat, float* sums,
+                                     float* sums_global, void* scratch, const b200vae_peer_t* comm, int slot,
+                                     void* stream) {
+  if (!da || !dyhat || !(sums || sums_global) || !scratch) return B200VAE_EALIGN;
   if (B <= 0 || !pow2_le128(w)) return B200VAE_EUNSUP;
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = (long long)B * w;
@@ -565,8 +653,25 @@ extern "C" int b200vae_mlp_layer_bwd_reduce(const float* da, const float* y, con
   mlp_bwd_reduce_kernel<<<nblk, 256, 0, st>>>(da, cur, stats ? 1 : 0, n, per, dyhat, (float*)scratch);
   int rc = check_launch();
   if (rc) return rc;
-  mlp_sum_finalize_kernel<<<(w + 7) / 8, 256, 0, st>>>((const float*)scratch, nblk, w, sums);
+  if (comm)
+    mlp_sum_finalize_peer_kernel<<<1, 1024, 0, st>>>((const float*)scratch, nblk, w, sums, sums_global, make_peer(comm), slot);
+  else
+    mlp_sum_finalize_kernel<<<(w + 7) / 8, 256, 0, st>>>((const float*)scratch, nblk, w, sums);
   return check_launch();
+}
+extern "C" int b200vae_mlp_layer_bwd_reduce(const float* da, const float* y, const float* stats, const float* gamma,
+                                            const float* beta, float slope, int B, int w, float* dyhat, float* sums,
+                                            void* scratch, void* stream) {
+  if (!sums) return B200VAE_EALIGN;
+  return mlp_layer_bwd_reduce_impl(da, y, stats, gamma, beta, slope, B, w, dyhat, sums, nullptr, scratch, nullptr, 0, stream);
+}
+extern "C" int b200vae_mlp_layer_bwd_reduce_peer(const float* da, const float* y, const float* stats, const float* gamma,
+                                                 const float* beta, float slope, int B, int w, float* dyhat,
+                                                 float* sums_local, float* sums_global, void* scratch,
+                                                 const b200vae_peer_t* comm, int slot, void* stream) {
+  if (!peer_ok(comm, slot) || !sums_global) return B200VAE_EALIGN;
+  return mlp_layer_bwd_reduce_impl(da, y, stats, gamma, beta, slope, B, w, dyhat, sums_local, sums_global, scratch, comm,
+                                   slot, stream);
 }
 
 extern "C" int b200vae_mlp_layer_bwd(const float* dyhat, const float* y, const float* stats, const float* gamma,

@@ -1,0 +1,101 @@
+// peer.cuh -- small-message exchange between the GPUs of one node over NVLink / NVSwitch peer memory.
+//
+// Every rank owns one "exchange buffer" (cudaMalloc + CUDA IPC, mapped into every other rank's address space by
+// b200vae_peer_open).  It is an array of PeerSlot.  An exchange on slot s, executed by ONE CTA per rank:
+//   1. read the slot's local epoch counter e-1, use e (all ranks execute the same sequence of exchanges, so the
+//      counters agree without communication; they live on the device so that a CUDA-graph replay advances them);
+//   2. store this rank's payload into data[e&1][rank] of EVERY rank's slot (plain stores through the peer mapping),
+//      __threadfence_system, then release-store flag[e&1][rank] = e on every rank;
+//   3. spin (acquire loads, bounded by a timeout) until the local flag[e&1][q] == e for every q, then read the payloads
+//      from local memory.  Results are combined in rank order, so every rank computes bit-identical values.
+// The parity double-buffer makes slot reuse safe without a trailing barrier: a rank can only publish epoch e+2 into the
+// buffers of epoch e after it passed exchange e+1, i.e. after every rank published e+1, which each does (stream order)
+// only after it finished reading epoch e.
+#pragma once
+#include "common.cuh"
+
+namespace b200vae {
+
+constexpr int kPeerMaxWorld = B200VAE_PEER_MAX_WORLD;   // 16
+constexpr int kPeerPay = 400;                           // floats per rank per exchange (>= 3*128 + 1)
+constexpr int kPeerSlots = 64;
+constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;   // 4 s: a missing peer must not hang the GPU
+
+struct PeerSlot {
+  float data[2][kPeerMaxWorld][kPeerPay];
+  unsigned flag[2][kPeerMaxWorld];
+  unsigned epoch;
+  unsigned timed_out;
+  unsigned pad[30];
+};
+
+struct PeerComm {   // kernel-parameter copy of b200vae_peer_t
+  int world, rank;
+  PeerSlot* buf[kPeerMaxWorld];
+};
+
+inline PeerComm make_peer(const b200vae_peer_t* c) {
+  PeerComm p;
+  p.world = c->world; p.rank = c->rank;
+  for (int r = 0; r < kPeerMaxWorld; ++r) p.buf[r] = r < c->world ? (PeerSlot*)c->buf[r] : nullptr;
+  return p;
+}
+inline bool peer_ok(const b200vae_peer_t* c, int slot) {
+  if (!c || c->world < 1 || c->world > kPeerMaxWorld || c->rank < 0 || c->rank >= c->world) return false;
+  if (slot < 0 || slot >= kPeerSlots) return false;
+  for (int r = 0; r < c->world; ++r)
+    if (!c->buf[r]) return false;
+  return true;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];\n" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Called by all threads of one CTA (blockDim.x >= world).  `mine`: n floats in shared memory; `all`: [world][n] floats
+// in shared memory, filled with every rank's payload (rank-major).  n <= kPeerPay.
+__device__ __forceinline__ void peer_exchange(const PeerComm& c, int slot, const float* mine, int n, float* all) {
+  __shared__ unsigned s_epoch;
+  PeerSlot* local = c.buf[c.rank] + slot;
+  if (threadIdx.x == 0) s_epoch = local->epoch + 1u;
+  __syncthreads();
+  const unsigned e = s_epoch;
+  const int par = (int)(e & 1u);
+  for (int i = threadIdx.x; i < c.world * n; i += blockDim.x) {
+    const int p = i / n, j = i - p * n;
+    (c.buf[p] + slot)->data[par][c.rank][j] = mine[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < c.world) {
+    st_release_sys(&(c.buf[threadIdx.x] + slot)->flag[par][c.rank], e);
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(&local->flag[par][threadIdx.x]) != e) {
+      if (global_timer_ns() - t0 > kPeerTimeoutNs) { local->timed_out = 1u; break; }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c.world * n; i += blockDim.x) {
+    const int p = i / n, j = i - p * n;
+    all[i] = ld_relaxed_sys_f32(&local->data[par][p][j]);
+  }
+  if (threadIdx.x == 0) local->epoch = e;
+  __syncthreads();
+}
+
+}  // namespace b200vae

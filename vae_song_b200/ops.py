@@ -421,24 +421,34 @@ class FusedMlpFn(torch.autograd.Function):
             st = None
             rm = rv = None
             mom = 0.0
+            grp = peer = None
             if has_bn:
                 bn = plan.bns[i]
                 grp = _bn_group(bn) if training else None
+                peer = getattr(bn, "peer", None) if grp is not None else None
                 st = torch.empty(4, wo, dtype=torch.float32, device=x.device)
-                if training and grp is None:
+                if training and (grp is None or peer is not None):
                     rm, rv, mom = bn.running_mean, bn.running_var, float(bn.momentum)
                     bn.num_batches_tracked.add_(1)
-            _C.check(lib.b200vae_mlp_layer_fwd(_ptr(prev[0]), _ptr(prev[1]), _ptr(prev[2]), _ptr(prev[3]), plan.slope,
-                                               _ptr(Ws[i]), _ptr(bs[i]), B, wi, wo, _ptr(y),
-                                               _ptr(st) if (has_bn and training) else None,
-                                               float(plan.bns[i].eps) if has_bn else 0.0, _ptr(rm), _ptr(rv), mom,
-                                               _ptr(scratch), _stream()), "mlp_layer_fwd")
+            if peer is not None:          # cross-rank statistics exchanged by the finalize kernel itself (peer memory)
+                _C.check(lib.b200vae_mlp_layer_fwd_peer(_ptr(prev[0]), _ptr(prev[1]), _ptr(prev[2]), _ptr(prev[3]), plan.slope,
+                                                        _ptr(Ws[i]), _ptr(bs[i]), B, wi, wo, _ptr(y), _ptr(st),
+                                                        float(bn.eps), _ptr(rm), _ptr(rv), mom, _ptr(scratch), peer.ref,
+                                                        bn.peer_slots[0], _stream()), "mlp_layer_fwd_peer")
+            else:
+                _C.check(lib.b200vae_mlp_layer_fwd(_ptr(prev[0]), _ptr(prev[1]), _ptr(prev[2]), _ptr(prev[3]), plan.slope,
+                                                   _ptr(Ws[i]), _ptr(bs[i]), B, wi, wo, _ptr(y),
+                                                   _ptr(st) if (has_bn and training) else None,
+                                                   float(plan.bns[i].eps) if has_bn else 0.0, _ptr(rm), _ptr(rv), mom,
+                                                   _ptr(scratch), _stream()), "mlp_layer_fwd")
             n_glob = float(B)
             if has_bn:
                 bn = plan.bns[i]
                 if not training:          # eval: running statistics are constants
                     st[0].copy_(bn.running_mean); st[1].copy_(bn.running_var)
                     st[2].copy_(torch.rsqrt(bn.running_var + bn.eps)); st[3].fill_(float(B))
+                elif peer is not None:
+                    n_glob = None
                 elif grp is not None:     # cross-rank: one all_gather of (mean, var, count), Chan combine, no host sync
                     import torch.distributed as dist
                     world = dist.get_world_size(grp)
@@ -480,17 +490,30 @@ class FusedMlpFn(torch.autograd.Function):
             st = sts[i]
             dyhat = torch.empty(B, wo, dtype=torch.float32, device=x.device)
             sums = torch.empty(2, wo, dtype=torch.float32, device=x.device)
-            _C.check(lib.b200vae_mlp_layer_bwd_reduce(_ptr(da), _ptr(ys[i]), _ptr(st), _ptr(gs[i]) if has_bn else None,
-                                                      _ptr(bes[i]) if has_bn else None, plan.slope, B, wo, _ptr(dyhat),
-                                                      _ptr(sums), _ptr(scratch), _stream()), "mlp_layer_bwd_reduce")
+            grp = _bn_group(plan.bns[i]) if (has_bn and training) else None
+            peer = getattr(plan.bns[i], "peer", None) if grp is not None else None
             inv_n = 1.0 / B
-            if has_bn:
+            if peer is not None:          # local sums (dbeta, dgamma) + rank-ordered global sums in one kernel
+                loc = torch.empty(2, wo, dtype=torch.float32, device=x.device)
+                _C.check(lib.b200vae_mlp_layer_bwd_reduce_peer(_ptr(da), _ptr(ys[i]), _ptr(st), _ptr(gs[i]), _ptr(bes[i]),
+                                                               plan.slope, B, wo, _ptr(dyhat), _ptr(loc), _ptr(sums),
+                                                               _ptr(scratch), peer.ref, plan.bns[i].peer_slots[1],
+                                                               _stream()), "mlp_layer_bwd_reduce_peer")
+                dbes[i], dgs[i] = loc[0], loc[1]
+                dbs[i] = torch.zeros(wo, dtype=torch.float32, device=x.device)
+                inv_n = 1.0 / (B * peer.world)                            # equal shards (train.shard_rows)
+            else:
+                _C.check(lib.b200vae_mlp_layer_bwd_reduce(_ptr(da), _ptr(ys[i]), _ptr(st), _ptr(gs[i]) if has_bn else None,
+                                                          _ptr(bes[i]) if has_bn else None, plan.slope, B, wo, _ptr(dyhat),
+                                                          _ptr(sums), _ptr(scratch), _stream()), "mlp_layer_bwd_reduce")
+            if peer is not None:
+                pass
+            elif has_bn:
                 dbes[i], dgs[i] = sums[0].clone(), sums[1].clone()        # local sums = parameter gradients
                 dbs[i] = torch.zeros(wo, dtype=torch.float32, device=x.device)   # bias feeding a BatchNorm: exactly 0
                 if not training:
                     sums.zero_()                                          # eval-mode BN is affine: dy = gamma*invstd*dyhat
                 else:
-                    grp = _bn_group(plan.bns[i])
                     if grp is not None:
                         import torch.distributed as dist
                         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=grp)
@@ -616,3 +639,13 @@ def adam_step_dev_(param, grad, m, v, step_dev, lr=1e-3, betas=(0.9, 0.999), eps
     _C.check(_C.load().b200vae_adam_step_dev(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), float(lr),
                                              float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
                                              _ptr(step_dev), float(grad_scale), _stream()), "adam_step_dev")
+
+
+def peer_allreduce_adam_(comm, slot, grad_buf, param_buf, m, v, n, step_dev, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                         weight_decay=0.0, grad_scale=1.0):
+    """Gradient all-reduce fused with Adam over peer memory (include/b200vae.h b200vae_peer_allreduce_adam).
+    grad_buf / param_buf: peer.PeerBuffer holding the flat gradient / parameter buffers of every rank."""
+    lib = _C.load()
+    _C.check(lib.b200vae_peer_allreduce_adam(comm.ref, slot, grad_buf.ptr_array(), param_buf.ptr_array(), _ptr(_req(m, "m")),
+                                             _ptr(_req(v, "v")), n, lr, betas[0], betas[1], eps, weight_decay,
+                                             _ptr(step_dev), grad_scale, _stream()), "peer_allreduce_adam")

@@ -118,14 +118,20 @@ def convert_sync_batchnorm(model, group=None):
 class FlatParams:
     """Re-homes every parameter (and its .grad) of `model` as a view into one flat fp32 buffer."""
 
-    def __init__(self, model: nn.Module):
+    def __init__(self, model: nn.Module, alloc=None):
+        """`alloc(numel) -> fp32 tensor` supplies the two flat buffers (peer-mapped memory for the fused all-reduce +
+        Adam kernel); it may return more elements than asked for (padding stays zero)."""
         params = [p for p in model.parameters() if p.requires_grad]
         if not params:
             raise ValueError("model has no trainable parameters")
         dev, n = params[0].device, sum(p.numel() for p in params)
         self.params = params
-        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        if alloc is None:
+            self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+            self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        else:
+            self.flat, self.grad = alloc(n), alloc(n)
+            self.flat.zero_(); self.grad.zero_()
         off = 0
         for p in params:
             k = p.numel()
@@ -162,14 +168,39 @@ class DataParallelTrainer:
     kernel is used and there is no fallback)."""
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None,
-                 grad_clip=None, sync_bn=True, optimizer_step=None):
+                 grad_clip=None, sync_bn=True, optimizer_step=None, comm="auto"):
+        """comm: "peer" = exchanges as kernels over NVLink peer memory (csrc/peer.cuh): BatchNorm statistics inside
+        the fused encoder's finalize kernels, gradient all-reduce fused with Adam; "nccl" = torch.distributed
+        collectives; "auto" = peer when CUDA IPC mapping works between all ranks, else nccl."""
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
         self.pg = process_group
         if self.world > 1 and sync_bn:
             model = convert_sync_batchnorm(model, process_group)
         self.model = model
-        self.fp = FlatParams(model)
+        self.peer = None
+        on_cuda = next(model.parameters()).is_cuda
+        if comm not in ("auto", "peer", "nccl"):
+            raise ValueError(f"comm must be auto|peer|nccl, got {comm!r}")
+        if self.world > 1 and on_cuda and comm != "nccl" and optimizer_step is None:
+            from . import peer as _peer
+            self.peer = _peer.PeerComm(process_group) if comm == "peer" else _peer.try_create(process_group)
+        self._peer_bufs = None
+        if self.peer is not None:
+            for mod in model.modules():          # same traversal order on every rank -> same slots
+                if isinstance(mod, SyncBatchNorm1d):
+                    mod.peer, mod.peer_slots = self.peer, (self.peer.new_slot(), self.peer.new_slot())
+            self._adam_slot = self.peer.new_slot(2)
+            bufs = []
+
+            def alloc(n):
+                b = self.peer.alloc_flat(n)
+                bufs.append(b)
+                return b.tensor()
+            self.fp = FlatParams(model, alloc)
+            self._peer_bufs = (bufs[0], bufs[1])          # (parameters, gradients)
+        else:
+            self.fp = FlatParams(model)
         self.m = torch.zeros_like(self.fp.flat)
         self.v = torch.zeros_like(self.fp.flat)
         self.t = 0
@@ -234,6 +265,15 @@ class DataParallelTrainer:
             # every other term is a batch mean -> compensate before the 1/W gradient averaging
             total = total + (W - 1) * lr_term
         total.backward()
+        clip = bool(self.grad_clip and self.grad_clip.get("enabled", False))
+        if self.peer is not None and not clip:
+            # two-shot all-reduce over peer memory fused with Adam: rank r reduces + updates chunk r and stores it
+            # into every replica (csrc/peer.cu); no NCCL call in the step
+            self.t += 1
+            ops.peer_allreduce_adam_(self.peer, self._adam_slot, self._peer_bufs[1], self._peer_bufs[0], self.m, self.v,
+                                     self.fp.flat.numel(), self.t_dev, self.hp["lr"], self.hp["betas"], self.hp["eps"],
+                                     self.hp["weight_decay"], 1.0 / W)
+            return total.detach(), rec, reg
         if W > 1:
             dist.all_reduce(self.fp.grad, op=dist.ReduceOp.SUM, group=self.pg)
         scale = 1.0 / W
