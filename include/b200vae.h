@@ -174,6 +174,21 @@ int b200vae_nn_sqdist_fwd(const float* A, const float* Bp, int B, int Na, int Nb
 int b200vae_nn_sqdist_bwd(const float* A, const float* Bp, const int* argA, const int* argB, const float* gA,
                           const float* gB, int B, int Na, int Nb, int dim, float* dA, void* stream);
 
+/* ---- wide-input ICNN (d > 4): MNIST-shaped LIDVAE decoder, ICNN(32,512) + ICNN(784,1024) (model.py:766-805) ----------
+ * Same mathematics as b200vae_icnn_decode_fwd/bwd (module.py:142-148 + the autograd.grad of model.py:822,828 and its
+ * double-backward), FP32, as a chain of fused tile GEMMs whose operands are generated while loading (csrc/icnn_wide.cu).
+ * Caller-owned activations: h0 [B,H] fp32, mask1 [B,H] uint8 (h1 > 0), s2 [B] fp32 (1 or 0.2) are SAVED by the forward
+ * for the backward; g0 (fwd) and u0,q1,g0,t0 (bwd) are [B,H] fp32 scratch.  psi may be NULL; xhat NULL = psi only.
+ * The backward takes v = dL/dxhat only (no psi-gradient) and OVERWRITES every non-null field of `g` and dz. */
+size_t b200vae_icnn_wide_workspace_bytes(int B, int d, int H, int for_backward);
+int b200vae_icnn_wide_fwd(const float* z, int B, int d, int H, const b200vae_icnn_params* p, int weight_mode, float kappa,
+                          float* psi, float* xhat, float* h0, uint8_t* mask1, float* s2, float* g0, void* workspace,
+                          size_t ws_bytes, void* stream);
+int b200vae_icnn_wide_bwd(const float* z, const float* v, const float* h0, const uint8_t* mask1, const float* s2, int B,
+                          int d, int H, const b200vae_icnn_params* p, int weight_mode, float kappa,
+                          const b200vae_icnn_grads* g, float* dz, float* u0, float* q1, float* g0, float* t0,
+                          void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- peer-memory exchange between the GPUs of one node (the data-parallel exchange steps) ---------------
  * The reference has no multi-GPU path; these replace what torch.distributed/NCCL would do for the LATENCY-bound
  * collectives of the sharded train step (BatchNorm statistics of model.py:711-734's encoder, 1 KB each, ten per step)

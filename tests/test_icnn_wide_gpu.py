@@ -1,0 +1,114 @@
+"""Parity of the fused wide-input ICNN kernels (csrc/icnn_wide.cu, d > 4: the MNIST-shaped decoder of BASELINE
+configs[3]) against the fp64 oracle and the reference-generated goldens.  FP32 bounds of the north_star: rtol 1e-5 for
+psi / xhat, 1e-4 for gradients (|a-b| <= rtol*|b| + rtol*max|b|, helpers.close_report)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import icnn_oracle as io
+from oracle.make_golden import ICNN_CASES, case_inputs
+
+from conftest import GOLDEN
+from helpers import KEYS, close_report, f32_as_f64, params_f32_as_f64, params_to_torch
+
+pytestmark = pytest.mark.gpu
+WIDE_GOLDEN = [c for c in ICNN_CASES if c[1] > 4]
+# (d, H, B, regime, mode, kappa, seed): ragged sizes (d, H not multiples of 4 / 16 / 128; B across several row tiles),
+# both weight modes, and the two shapes of the MNIST-shaped decoder at reduced batch
+SHAPES = [
+    (5, 40, 37, "mixed", 0, 0.1, 201),
+    (7, 130, 300, "mixed", 1, 0.0, 202),
+    (32, 512, 129, "mixed", 0, 0.1, 203),
+    (784, 256, 40, "mixed", 0, 0.05, 204),
+    (36, 96, 1000, "clampy", 1, 0.2, 205),
+]
+
+
+def run_wide(p, z, v, mode, kappa):
+    from vae_song_b200 import ops
+    dev = "cuda"
+    params = [t.requires_grad_(True) for t in params_to_torch(p, dev)]
+    zt = torch.tensor(z, dtype=torch.float32, device=dev, requires_grad=True)
+    psi, xhat = ops.IcnnBrenierWideFn.apply(zt, kappa, mode, 0, *params)
+    (xhat * torch.tensor(v, dtype=torch.float32, device=dev)).sum().backward()
+    g = {k: t.grad.cpu().numpy() for k, t in zip(KEYS, params)}
+    return psi.detach().cpu().numpy(), xhat.detach().cpu().numpy(), zt.grad.cpu().numpy(), g
+
+
+def check_against_oracle(p, z, v, mode, kappa, out):
+    psi, xhat, dz, g = out
+    p64, z64, v64 = params_f32_as_f64(p), f32_as_f64(z), f32_as_f64(v)
+    rpsi, rxhat, _ = io.icnn_brenier(z64, p64, mode, kappa)
+    rdz, rg = io.icnn_brenier_backward(z64, v64, p64, mode, kappa, None)
+    close_report(psi, rpsi, 1e-5, "psi")
+    close_report(xhat, rxhat, 1e-5, "xhat", bad_frac=0.01)
+    close_report(dz, rdz, 1e-4, "dz", bad_frac=0.01)
+    for k in KEYS:
+        if np.abs(rg[k]).max() == 0:
+            assert np.abs(g[k]).max() == 0, k          # A1b / A2b exact zeros (not None)
+        else:
+            close_report(g[k], rg[k], 1e-4, "grad " + k)
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"d{s[0]}_h{s[1]}_b{s[2]}" for s in SHAPES])
+def test_wide_fwd_bwd_vs_oracle(shape):
+    d, H, B, regime, mode, kappa, seed = shape
+    p, z, v, _ = case_inputs(d, H, B, regime, seed)
+    check_against_oracle(p, z, v, mode, kappa, run_wide(p, z, v, mode, kappa))
+
+
+@pytest.mark.parametrize("case", WIDE_GOLDEN, ids=[c[0] for c in WIDE_GOLDEN])
+def test_wide_vs_reference_golden(case):
+    """Against what the unmodified reference produced (fp64 golden; oracle/make_golden.py)."""
+    name, d, H, B, regime, mode, kappa, seed, with_gpsi = case
+    assert not with_gpsi
+    G = np.load(os.path.join(GOLDEN, "icnn_cases.npz"))
+    p, z, v, _ = case_inputs(d, H, B, regime, seed)
+    psi, xhat, dz, g = run_wide(p, z, v, mode, kappa)
+    pre = f"{name}/f64/"
+    close_report(psi, G[pre + "psi"], 2e-5, "psi")
+    close_report(xhat, G[pre + "xhat"], 2e-5, "xhat", bad_frac=0.01)
+    close_report(dz, G[pre + "dz"], 1e-4, "dz", bad_frac=0.01)
+    for k in KEYS:
+        key = pre + "g_" + k
+        if key in G.files and np.abs(G[key]).max() > 0:
+            close_report(g[k], G[key], 1e-4, "grad " + k)
+
+
+def test_wide_is_deterministic_and_psi_only_inference():
+    from vae_song_b200 import module, ops
+    d, H, B = 32, 128, 70
+    p, z, v, _ = case_inputs(d, H, B, "mixed", 77)
+    a = run_wide(p, z, v, 0, 0.1)
+    b = run_wide(p, z, v, 0, 0.1)
+    for x, y in zip(a[:3], b[:3]):
+        assert np.array_equal(x, y)                      # ordered reductions: bit-reproducible
+    for k in KEYS:
+        assert np.array_equal(a[3][k], b[3][k]), k
+    ic = module.ICNN(d, H).cuda()
+    with torch.no_grad():
+        for t, src in zip(ic._flat_params(), params_to_torch(p, "cuda")):
+            t.copy_(src)
+        zt = torch.tensor(z, dtype=torch.float32, device="cuda")
+        psi_inf = ic(zt)                                 # no_grad: fused psi-only kernels
+    assert psi_inf.shape == (B, 1)
+    close_report(psi_inf[:, 0].cpu().numpy(), a[0], 1e-6, "psi-only == psi of the Brenier call")
+    zt2 = torch.tensor(z, dtype=torch.float32, device="cuda", requires_grad=True)
+    psi_ad = ic(zt2)                                     # autograd idiom of the reference stays available
+    xh = torch.autograd.grad(psi_ad, [zt2], torch.ones_like(psi_ad), create_graph=True)[0] + 2 * 0.1 * zt2
+    close_report(xh.detach().cpu().numpy(), a[1], 1e-5, "autograd Brenier == fused", bad_frac=0.01)
+
+
+def test_wide_rejects_cpu_and_psi_gradient():
+    from vae_song_b200 import _C, ops
+    p, z, v, _ = case_inputs(8, 16, 4, "mixed", 5)
+    params = params_to_torch(p, "cpu")
+    with pytest.raises(_C.B200VaeError):
+        ops.IcnnBrenierWideFn.apply(torch.tensor(z, dtype=torch.float32), 0.0, 0, 0, *params)
+    params = [t.requires_grad_(True) for t in params_to_torch(p, "cuda")]
+    zt = torch.tensor(z, dtype=torch.float32, device="cuda", requires_grad=True)
+    psi, xhat = ops.IcnnBrenierWideFn.apply(zt, 0.0, 0, 0, *params)
+    with pytest.raises(NotImplementedError):
+        psi.sum().backward()

@@ -31,6 +31,7 @@ EXPORTS = [
     "b200vae_peer_exchange_bytes", "b200vae_peer_num_slots", "b200vae_peer_max_payload", "b200vae_peer_alloc", "b200vae_peer_open",
     "b200vae_peer_close", "b200vae_peer_free", "b200vae_peer_timed_out", "b200vae_peer_allgather", "b200vae_mlp_layer_fwd_peer",
     "b200vae_mlp_layer_bwd_reduce_peer", "b200vae_peer_allreduce_adam",
+    "b200vae_icnn_wide_workspace_bytes", "b200vae_icnn_wide_fwd", "b200vae_icnn_wide_bwd",
 ]
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 64
 
@@ -113,6 +114,13 @@ def load():
     lib.b200vae_nn_sqdist_fwd.argtypes = [vp, vp, i, i, i, i, vp, vp, vp]
     lib.b200vae_nn_sqdist_bwd.restype = i
     lib.b200vae_nn_sqdist_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp]
+    lib.b200vae_icnn_wide_workspace_bytes.restype = sz
+    lib.b200vae_icnn_wide_workspace_bytes.argtypes = [i, i, i, i]
+    lib.b200vae_icnn_wide_fwd.restype = i
+    lib.b200vae_icnn_wide_fwd.argtypes = [vp, i, i, i, C.POINTER(IcnnParams), i, f, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.b200vae_icnn_wide_bwd.restype = i
+    lib.b200vae_icnn_wide_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, C.POINTER(IcnnParams), i, f, C.POINTER(IcnnGrads), vp,
+                                          vp, vp, vp, vp, vp, sz, vp]
     pp = C.POINTER(PeerStruct)
     lib.b200vae_peer_exchange_bytes.restype = sz
     lib.b200vae_peer_exchange_bytes.argtypes = []

@@ -161,33 +161,51 @@ def _pos(W, mode):
     return W.exp() if mode == _C.WEIGHT_EXP else W.clamp(min=1e-2)
 
 
+def _grads_struct(tensors):
+    g = _C.IcnnGrads()
+    for k, t in zip(PARAM_FIELDS, tensors):
+        setattr(g, k, None if t is None else t.data_ptr())
+    return g
+
+
+def icnn_wide_fwd(z, params, mode, kappa, want_xhat=True):
+    """Fused FP32 forward of a wide-input ICNN (csrc/icnn_wide.cu).  Returns (psi [B], xhat [B,d] | None, saved) with
+    saved = (h0 [B,H], mask1 [B,H] uint8, s2 [B]) -- what the backward needs besides z."""
+    lib = _C.load()
+    B, d = z.shape
+    H = params[0].shape[0]
+    dev = z.device
+    ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, 0), dtype=torch.uint8, device=dev)
+    psi = torch.empty(B, dtype=torch.float32, device=dev)
+    h0 = torch.empty(B, H, dtype=torch.float32, device=dev)
+    mask1 = torch.empty(B, H, dtype=torch.uint8, device=dev)
+    s2 = torch.empty(B, dtype=torch.float32, device=dev)
+    xhat = torch.empty(B, d, dtype=torch.float32, device=dev) if want_xhat else None
+    g0 = torch.empty(B, H, dtype=torch.float32, device=dev) if want_xhat else None
+    ps = _params_struct(params)
+    _C.check(lib.b200vae_icnn_wide_fwd(_ptr(z), B, d, H, C.byref(ps), mode, float(kappa), _ptr(psi), _ptr(xhat), _ptr(h0),
+                                       _ptr(mask1), _ptr(s2), _ptr(g0), _ptr(ws), ws.numel(), _stream()), "icnn_wide_fwd")
+    return psi, xhat, (h0, mask1, s2)
+
+
 class IcnnBrenierWideFn(torch.autograd.Function):
-    """Same contract as IcnnBrenierFn for input widths the fused kernels do not cover yet (d > 4, e.g. the
-    MNIST-shaped ICNN(32,512) / ICNN(784,1024)).  Here the thin products A.z are dense [B,d]x[d,H] GEMMs as well,
-    so this path composes plain library GEMMs (cuBLAS through torch.mm, FP32, no TF32) with the same ANALYTIC
-    forward-then-reverse sweep and double-backward: no autograd graph, ~3x fewer launches
-    than the reference's autograd.grad formulation, masks instead of saved activations.  CUDA only."""
+    """Same contract as IcnnBrenierFn for input widths the register-resident kernels do not cover (d > 4, e.g. the
+    MNIST-shaped ICNN(32,512) / ICNN(784,1024) of BASELINE configs[3]).  Here the thin products A.z are dense
+    [B,d]x[d,H] contractions as well; the path is a chain of fused FP32 tile-GEMM kernels with generated operands and
+    elementwise epilogues (csrc/icnn_wide.cu): the ANALYTIC forward-then-reverse sweep and double-backward of SURVEY
+    Appendix A, no autograd graph, h0 + a byte mask saved instead of ~20 activations.  `precision` is ignored: this path
+    always computes in FP32 (the parity arithmetic)."""
 
     @staticmethod
     def forward(ctx, z, kappa, mode, precision, *params):
-        _C.load()                                   # fail loudly without the extension, like every other op
         z = _req(z, "z")
-        A0w, A0b, A1w, A1b, A2w, A2b, W0, W1 = [_req(p, k) for p, k in zip(params, PARAM_FIELDS)]
-        P0, P1 = _pos(W0, mode), _pos(W1, mode)
-        h0 = torch.addmm(A0b, z, A0w.t())
-        m0 = h0 > 0
-        a0 = torch.where(m0, h0, 0.2 * h0)
-        h1 = torch.addmm(A1b, z, A1w.t()).addmm_(a0 * a0, P0.t())
-        m1 = h1 > 0
-        h2 = torch.addmv(torch.addmv(A2b.expand(z.shape[0]), z, A2w[0]), torch.where(m1, h1, 0.2 * h1), P1[0])
-        m2 = h2 > 0
-        s2 = torch.where(m2, 1.0, 0.2).to(z.dtype)
-        psi = h2 * s2
-        g1 = (s2[:, None] * P1) * torch.where(m1, 1.0, 0.2).to(z.dtype)
-        g0 = (g1 @ P0) * (2.0 * a0) * torch.where(m0, 1.0, 0.2).to(z.dtype)
-        xhat = torch.addmm(s2[:, None] * A2w + (2.0 * kappa) * z, g0, A0w).addmm_(g1, A1w)
+        params = [_req(p, k) for p, k in zip(params, PARAM_FIELDS)]
+        H, d = params[0].shape
+        if z.dim() != 2 or z.shape[1] != d:
+            raise _C.B200VaeError(f"z must be [B,{d}], got {tuple(z.shape)}")
+        psi, xhat, saved = icnn_wide_fwd(z, params, mode, kappa, True)
         if any(ctx.needs_input_grad):
-            ctx.save_for_backward(z, m1, m2, A0w, A0b, A1w, A2w, W0, W1)
+            ctx.save_for_backward(z, *saved, *params)
             ctx.cfg = (float(kappa), mode)
         ctx.set_materialize_grads(False)
         return psi, xhat
@@ -195,53 +213,38 @@ class IcnnBrenierWideFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gpsi, v):
-        z, m1, m2, A0w, A0b, A1w, A2w, W0, W1 = ctx.saved_tensors
+        z, h0, mask1, s2, *params = ctx.saved_tensors
         kappa, mode = ctx.cfg
         if gpsi is None and v is None:
             return (None,) * 12
-        dt = z.dtype
-        P0, P1 = _pos(W0, mode), _pos(W1, mode)
-        h0 = torch.addmm(A0b, z, A0w.t())
-        s0 = torch.where(h0 > 0, 1.0, 0.2).to(dt)
-        a0 = h0 * s0
-        s1 = torch.where(m1, 1.0, 0.2).to(dt)
-        s2 = torch.where(m2, 1.0, 0.2).to(dt)
-        g1 = (s2[:, None] * P1) * s1
-        gx1 = g1 @ P0
-        c0 = 2.0 * a0 * s0
-        g0 = gx1 * c0
-        B = z.shape[0]
-        zero = lambda t: torch.zeros_like(t)
-        dA0w, dA0b, dA1w, dA1b, dA2w, dA2b = zero(A0w), zero(A0b), zero(A1w), torch.zeros(A1w.shape[0], device=z.device, dtype=dt), zero(A2w), torch.zeros(1, device=z.device, dtype=dt)
-        dP0 = torch.zeros_like(P0)
-        dP1 = torch.zeros_like(P1[0])
-        dz = torch.zeros_like(z)
-        if v is not None:
-            v = _req(v, "grad_xhat")
-            u0, u1 = v @ A0w.t(), v @ A1w.t()
-            q1 = u0 * c0
-            t0 = u0 * (2.0 * gx1) * s0 * s0
-            w1 = u1 + q1 @ P0.t()
-            dA0w = g0.t() @ v + t0.t() @ z
-            dA0b = t0.sum(0)
-            dA1w = g1.t() @ v
-            dA2w = (s2[:, None] * v).sum(0, keepdim=True)
-            dP0 = g1.t() @ q1
-            dP1 = (s2[:, None] * s1 * w1).sum(0)
-            dz = t0 @ A0w + (2.0 * kappa) * v
         if gpsi is not None:                       # first-order backward of psi (Appendix A, last line)
             raise NotImplementedError("psi-gradient of the wide-input ICNN: use ICNN.forward (plain autograd) instead")
-        gW0 = dP0 * P0 if mode == _C.WEIGHT_EXP else dP0 * (W0 >= 1e-2)
-        gW1 = (dP1 * P1[0] if mode == _C.WEIGHT_EXP else dP1 * (W1[0] >= 1e-2))[None, :]
+        lib = _C.load()
+        v = _req(v, "grad_xhat")
+        B, d = z.shape
+        H = params[0].shape[0]
+        dev = z.device
         need = ctx.needs_input_grad
-        grads = [dA0w, dA0b, dA1w, dA1b, dA2w, dA2b, gW0, gW1]
-        return (dz if need[0] else None, None, None, None, *[g if n else None for g, n in zip(grads, need[4:])])
+        ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, 1), dtype=torch.uint8, device=dev)
+        scratch = torch.empty(4, B, H, dtype=torch.float32, device=dev)          # u0, q1, g0, t0
+        grads = [torch.empty_like(p) if n else None for p, n in zip(params, need[4:])]
+        dz = torch.empty_like(z) if need[0] else None
+        ps, gs = _params_struct(params), _grads_struct(grads)
+        _C.check(lib.b200vae_icnn_wide_bwd(_ptr(z), _ptr(v), _ptr(h0), _ptr(mask1), _ptr(s2), B, d, H, C.byref(ps), mode,
+                                           float(kappa), C.byref(gs), _ptr(dz), _ptr(scratch[0]), _ptr(scratch[1]),
+                                           _ptr(scratch[2]), _ptr(scratch[3]), _ptr(ws), ws.numel(), _stream()),
+                 "icnn_wide_bwd")
+        return (dz, None, None, None, *grads)
 
 
 def icnn_potential_wide(z, mode, A0w, A0b, A1w, A1b, A2w, A2b, W0, W1):
     """psi [B,1] of a wide-input ICNN with ordinary differentiable torch ops (module.py:142-148 verbatim
     semantics), so first- and second-order autograd through psi keep working for d > 4."""
     _C.load()
+    ps = (A0w, A0b, A1w, A1b, A2w, A2b, W0, W1)
+    if not (torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in ps))):
+        psi, _, _ = icnn_wide_fwd(_req(z, "z"), [_req(p, k) for p, k in zip(ps, PARAM_FIELDS)], mode, 0.0, False)
+        return psi.unsqueeze(1)                     # inference: fused kernels, psi only
     act = torch.nn.functional.leaky_relu
     x = act(torch.nn.functional.linear(z, A0w, A0b), 0.2).pow(2)
     x = act(torch.nn.functional.linear(x, _pos(W0, mode)) + torch.nn.functional.linear(z, A1w, A1b), 0.2)
