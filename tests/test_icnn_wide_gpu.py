@@ -112,3 +112,27 @@ def test_wide_rejects_cpu_and_psi_gradient():
     psi, xhat = ops.IcnnBrenierWideFn.apply(zt, 0.0, 0, 0, *params)
     with pytest.raises(NotImplementedError):
         psi.sum().backward()
+
+
+def test_wide_implicit_zero_pad_equals_explicit_pad():
+    """model.py:824 x = x1 B^T with B = eye(Dx, D) is a zero-pad: feeding [B,nz] to an ICNN(d) must equal feeding the
+    explicitly padded [B,d] input -- outputs, dz (first nz columns) and every parameter gradient."""
+    from vae_song_b200 import ops
+    d, nz, H, B = 784, 32, 128, 50
+    p, z, v, _ = case_inputs(d, H, B, "mixed", 31)
+    z[:, nz:] = 0.0
+    full = run_wide(p, z, v, 0, 0.1)
+    params = [t.requires_grad_(True) for t in params_to_torch(p, "cuda")]
+    zt = torch.tensor(z[:, :nz].copy(), dtype=torch.float32, device="cuda", requires_grad=True)
+    psi, xhat = ops.IcnnBrenierWideFn.apply(zt, 0.1, 0, 0, *params)
+    (xhat * torch.tensor(v, dtype=torch.float32, device="cuda")).sum().backward()
+    assert xhat.shape == (B, d) and zt.grad.shape == (B, nz)
+    close_report(psi.detach().cpu().numpy(), full[0], 1e-6, "psi")
+    close_report(xhat.detach().cpu().numpy(), full[1], 1e-6, "xhat")
+    close_report(zt.grad.cpu().numpy(), full[2][:, :nz], 1e-6, "dz")
+    for k, t in zip(KEYS, params):
+        if np.abs(full[3][k]).max() == 0:
+            assert float(t.grad.abs().max()) == 0.0
+        else:
+            close_report(t.grad.cpu().numpy(), full[3][k], 1e-6, "grad " + k)
+    check_against_oracle(p, z, v, 0, 0.1, full)

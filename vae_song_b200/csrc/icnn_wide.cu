@@ -327,7 +327,8 @@ wide_hid_kernel(const float* __restrict__ src1, int xf1, const float* __restrict
 // ---- row: h2 = sum_nt part + A2.z + b2 -> psi, s2 ----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 wide_row_kernel(const float* __restrict__ part, int nt, const float* __restrict__ z, const float* __restrict__ A2w,
-                const float* __restrict__ A2b, int B, int d, float* __restrict__ psi, float* __restrict__ s2) {
+                const float* __restrict__ A2b, int B, int d /* = nz: columns of z */, float* __restrict__ psi,
+                float* __restrict__ s2) {
   const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B) return;
   float s = 0.f;
@@ -390,8 +391,8 @@ wide_gx1_kernel(const uint8_t* __restrict__ mask1, const float* __restrict__ s2,
 __global__ void __launch_bounds__(kThreads, 2)
 wide_out_kernel(const float* __restrict__ srcA, const float* __restrict__ A0w, int with_g1, const uint8_t* __restrict__ mask1,
                 const float* __restrict__ s2, const float* __restrict__ P1, const float* __restrict__ A1w,
-                const float* __restrict__ A2w, const float* __restrict__ zv, float kappa2, int B, int d, int H,
-                float* __restrict__ out) {
+                const float* __restrict__ A2w, const float* __restrict__ zv, int zv_ld, int zv_cols, float kappa2, int B,
+                int d, int N /* output columns computed (<= d) */, int H, float* __restrict__ out) {
   __shared__ GemmSmem sm;
   const TileCoord tc;
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
@@ -399,12 +400,12 @@ wide_out_kernel(const float* __restrict__ srcA, const float* __restrict__ A0w, i
   zero_acc(acc);
   {
     ARow a; a.init(srcA, H, B, H, m0, XF_ID);
-    BMat b = make_bmat(A0w, d, 0, H, d, n0);
+    BMat b = make_bmat(A0w, d, 0, H, N, n0);
     gemm_tile_acc(acc, sm, ktiles(H), a, b, tc);
   }
   if (with_g1) {
     ARow a; a.init(nullptr, H, B, H, m0, XF_G1, mask1, P1, s2);
-    BMat b = make_bmat(A1w, d, 0, H, d, n0);
+    BMat b = make_bmat(A1w, d, 0, H, N, n0);
     gemm_tile_acc(acc, sm, ktiles(H), a, b, tc);
   }
 #pragma unroll
@@ -415,11 +416,11 @@ wide_out_kernel(const float* __restrict__ srcA, const float* __restrict__ A0w, i
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int col = n0 + tc.col(j);
-      if (col >= d) continue;
-      const size_t idx = (size_t)row * d + col;
-      float o = acc[i][j] + kappa2 * zv[idx];
+      if (col >= N) continue;
+      float o = acc[i][j];
+      if (col < zv_cols) o = fmaf(kappa2, zv[(size_t)row * zv_ld + col], o);
       if (with_g1) o = fmaf(sr, A2w[col], o);
-      out[idx] = o;
+      out[(size_t)row * N + col] = o;
     }
   }
 }
@@ -427,7 +428,7 @@ wide_out_kernel(const float* __restrict__ srcA, const float* __restrict__ A0w, i
 // ---- tn: slab[split][m][n] = sum_{b in split} xfA(srcA)[b][m] * B1[b][n]  (+ second pair) -----------------------------------------
 struct TnArgs {
   const float* a1; int xf1; const float* b1;     // first product  (a1 unused for XF_G1)
-  const float* a2; const float* b2;              // optional second product (identity A), may be null
+  const float* a2; const float* b2; int N2;      // optional second product (identity A), b2 [B,N2], N2 <= N; may be null
   const uint8_t* mask1; const float* s2; const float* P1;
   int B, Mdim, N, rows_per_split;
 };
@@ -449,7 +450,7 @@ wide_tn_kernel(TnArgs p, float* __restrict__ slabs) {
   if (p.a2) {
     ACol a; a.src = p.a2; a.mask = nullptr; a.P1 = nullptr; a.s2 = nullptr; a.ld = p.Mdim; a.Mdim = p.Mdim; a.kbeg = kbeg; a.kend = kend;
     a.m0 = m0; a.xf = XF_ID;
-    BMat b = make_bmat(p.b2, p.N, kbeg, kend, p.N, n0);
+    BMat b = make_bmat(p.b2, p.N2, kbeg, kend, p.N2, n0);
     gemm_tile_acc(acc, sm, KT, a, b, tc);
   }
   float* out = slabs + (size_t)blockIdx.z * p.Mdim * p.N;
@@ -521,11 +522,11 @@ extern "C" size_t b200vae_icnn_wide_workspace_bytes(int B, int d, int H, int for
 
 #define WIDE_CHECK() do { rc = check_launch(); if (rc) return rc; } while (0)
 
-extern "C" int b200vae_icnn_wide_fwd(const float* z, int B, int d, int H, const b200vae_icnn_params* p, int weight_mode,
+extern "C" int b200vae_icnn_wide_fwd(const float* z, int B, int d, int nz, int H, const b200vae_icnn_params* p, int weight_mode,
                                      float kappa, float* psi, float* xhat, float* h0, uint8_t* mask1, float* s2, float* g0,
                                      void* workspace, size_t ws_bytes, void* stream) {
   if (!z || !wide_params_ok(p) || !h0 || !mask1 || !s2 || !workspace || (xhat && !g0)) return B200VAE_EALIGN;
-  if (B <= 0 || d <= 0 || H <= 0) return B200VAE_ESHAPE;
+  if (B <= 0 || d <= 0 || H <= 0 || nz <= 0 || nz > d) return B200VAE_ESHAPE;
   if (weight_mode != B200VAE_WEIGHT_EXP && weight_mode != B200VAE_WEIGHT_CLAMP) return B200VAE_EUNSUP;
   const WideWs L = wide_layout(B, d, H, false);
   if (ws_bytes < L.end * sizeof(float)) return B200VAE_EWS;
@@ -535,28 +536,30 @@ extern "C" int b200vae_icnn_wide_fwd(const float* z, int B, int d, int H, const 
   int rc = wide_prepare(p, d, H, weight_mode, ws, L, st);
   if (rc) return rc;
   const dim3 gH(L.mt, L.nt), gD(L.mt, (d + 127) / 128);
-  wide_lin_kernel<<<gH, kThreads, 0, st>>>(z, ws + L.A0T, p->A0b, B, d, H, 0, nullptr, h0, nullptr);
+  // z is [B,nz]: the input is z zero-padded to d columns, so every product with z runs over nz only
+  wide_lin_kernel<<<gH, kThreads, 0, st>>>(z, ws + L.A0T, p->A0b, B, nz, H, 0, nullptr, h0, nullptr);
   WIDE_CHECK();
-  wide_hid_kernel<<<gH, kThreads, 0, st>>>(h0, XF_X1, ws + L.P0T, z, ws + L.A1T, p->A1b, ws + L.P1, B, d, H, 0, mask1, nullptr,
+  wide_hid_kernel<<<gH, kThreads, 0, st>>>(h0, XF_X1, ws + L.P0T, z, ws + L.A1T, p->A1b, ws + L.P1, B, nz, H, 0, mask1, nullptr,
                                           ws + L.part, nullptr);
   WIDE_CHECK();
-  wide_row_kernel<<<(B + 7) / 8, 256, 0, st>>>(ws + L.part, L.nt, z, p->A2w, p->A2b, B, d, psi, s2);
+  wide_row_kernel<<<(B + 7) / 8, 256, 0, st>>>(ws + L.part, L.nt, z, p->A2w, p->A2b, B, nz, psi, s2);
   WIDE_CHECK();
   if (xhat) {
     wide_gx1_kernel<<<gH, kThreads, 0, st>>>(mask1, s2, ws + L.P1, ws + L.P0, h0, nullptr, B, H, g0, nullptr, nullptr);
     WIDE_CHECK();
-    wide_out_kernel<<<gD, kThreads, 0, st>>>(g0, p->A0w, 1, mask1, s2, ws + L.P1, p->A1w, p->A2w, z, 2.f * kappa, B, d, H, xhat);
+    wide_out_kernel<<<gD, kThreads, 0, st>>>(g0, p->A0w, 1, mask1, s2, ws + L.P1, p->A1w, p->A2w, z, nz, nz, 2.f * kappa, B, d, d, H,
+                                            xhat);
     WIDE_CHECK();
   }
   return B200VAE_OK;
 }
 
 extern "C" int b200vae_icnn_wide_bwd(const float* z, const float* v, const float* h0, const uint8_t* mask1, const float* s2,
-                                     int B, int d, int H, const b200vae_icnn_params* p, int weight_mode, float kappa,
+                                     int B, int d, int nz, int H, const b200vae_icnn_params* p, int weight_mode, float kappa,
                                      const b200vae_icnn_grads* g, float* dz, float* u0, float* q1, float* g0, float* t0,
                                      void* workspace, size_t ws_bytes, void* stream) {
   if (!z || !v || !h0 || !mask1 || !s2 || !wide_params_ok(p) || !u0 || !q1 || !g0 || !t0 || !workspace) return B200VAE_EALIGN;
-  if (B <= 0 || d <= 0 || H <= 0) return B200VAE_ESHAPE;
+  if (B <= 0 || d <= 0 || H <= 0 || nz <= 0 || nz > d) return B200VAE_ESHAPE;
   if (weight_mode != B200VAE_WEIGHT_EXP && weight_mode != B200VAE_WEIGHT_CLAMP) return B200VAE_EUNSUP;
   const WideWs L = wide_layout(B, d, H, true);
   if (ws_bytes < L.end * sizeof(float)) return B200VAE_EWS;
@@ -588,7 +591,9 @@ extern "C" int b200vae_icnn_wide_bwd(const float* z, const float* v, const float
     WIDE_CHECK();
   }
   if (dz) {
-    wide_out_kernel<<<gD, kThreads, 0, st>>>(t0, p->A0w, 0, nullptr, nullptr, nullptr, nullptr, nullptr, v, 2.f * kappa, B, d, H, dz);
+    // dz [B,nz]: only the gradient w.r.t. the real (unpadded) input columns is formed
+    wide_out_kernel<<<dim3(L.mt, (nz + 127) / 128), kThreads, 0, st>>>(t0, p->A0w, 0, nullptr, nullptr, nullptr, nullptr, nullptr, v,
+                                                                      d, nz, 2.f * kappa, B, d, nz, H, dz);
     WIDE_CHECK();
   }
   if (g) {
@@ -606,21 +611,21 @@ extern "C" int b200vae_icnn_wide_bwd(const float* z, const float* v, const float
     t.rows_per_split = round_up((B + splits - 1) / splits, kBK);
     const int fin_blocks = 148 * 4;
     if (g->A0w) {   // dA0 = g0^T v + t0^T z
-      t.a1 = g0; t.xf1 = XF_ID; t.b1 = v; t.a2 = t0; t.b2 = z; t.N = d;
+      t.a1 = g0; t.xf1 = XF_ID; t.b1 = v; t.a2 = t0; t.b2 = z; t.N2 = nz; t.N = d;
       wide_tn_kernel<<<dim3(L.nt, (d + 127) / 128, splits), kThreads, 0, st>>>(t, ws + L.slabs);
       WIDE_CHECK();
       wide_slab_finalize_kernel<<<fin_blocks, 256, 0, st>>>(ws + L.slabs, splits, (size_t)H * d, 0, nullptr, nullptr, g->A0w);
       WIDE_CHECK();
     }
     if (g->A1w) {   // dA1 = g1^T v
-      t.a1 = nullptr; t.xf1 = XF_G1; t.b1 = v; t.a2 = nullptr; t.b2 = nullptr; t.N = d;
+      t.a1 = nullptr; t.xf1 = XF_G1; t.b1 = v; t.a2 = nullptr; t.b2 = nullptr; t.N2 = 0; t.N = d;
       wide_tn_kernel<<<dim3(L.nt, (d + 127) / 128, splits), kThreads, 0, st>>>(t, ws + L.slabs);
       WIDE_CHECK();
       wide_slab_finalize_kernel<<<fin_blocks, 256, 0, st>>>(ws + L.slabs, splits, (size_t)H * d, 0, nullptr, nullptr, g->A1w);
       WIDE_CHECK();
     }
     if (g->W0) {    // dP0 = g1^T q1 -> dW0
-      t.a1 = nullptr; t.xf1 = XF_G1; t.b1 = q1; t.a2 = nullptr; t.b2 = nullptr; t.N = H;
+      t.a1 = nullptr; t.xf1 = XF_G1; t.b1 = q1; t.a2 = nullptr; t.b2 = nullptr; t.N2 = 0; t.N = H;
       wide_tn_kernel<<<dim3(L.nt, L.nt, splits), kThreads, 0, st>>>(t, ws + L.slabs);
       WIDE_CHECK();
       wide_slab_finalize_kernel<<<fin_blocks, 256, 0, st>>>(ws + L.slabs, splits, (size_t)H * H, chain, ws + L.P0, p->W0, g->W0);

@@ -349,7 +349,12 @@ class LIDVAE(VAE):
             ic.precision = self.precision
         _, x = self.decoder[0].brenier(input, self.il_factor)
         Dx, D = self.B.shape
-        x = x if Dx == D and self._B_is_eye() else F.linear(x, self.B)
+        # x = x1 B^T (model.py:824): with B = eye(Dx, D) this is a zero-pad, which the wide kernels take implicitly
+        # (input [B,D] of an ICNN(Dx,.)); a user-modified B falls back to the literal product
+        if not self._B_is_eye():
+            x = F.linear(x, self.B)
+        elif Dx != D and Dx <= module.ICNN.FUSED_MAX_D:
+            x = F.pad(x, (0, Dx - D))
         _, y = self.decoder[1].brenier(x, self.il_factor)
         return self.decoder[2](y)
 

@@ -85,6 +85,7 @@ class ICNN(nn.Module):
         return ops.IcnnPotentialFn.apply(input, self._mode(), self._prec(), *self._flat_params())
 
     def brenier(self, input, kappa=0.0):
+        """(psi [B], xhat [B,d]).  For wide ICNNs `input` may be [B,nz] with nz < d: zero-padded to d inside the kernels."""
         fn = ops.IcnnBrenierWideFn if self.in_channel > self.FUSED_MAX_D else ops.IcnnBrenierFn
         return fn.apply(input, float(kappa), self._mode(), self._prec(), *self._flat_params())
 

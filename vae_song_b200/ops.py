@@ -172,8 +172,8 @@ def icnn_wide_fwd(z, params, mode, kappa, want_xhat=True):
     """Fused FP32 forward of a wide-input ICNN (csrc/icnn_wide.cu).  Returns (psi [B], xhat [B,d] | None, saved) with
     saved = (h0 [B,H], mask1 [B,H] uint8, s2 [B]) -- what the backward needs besides z."""
     lib = _C.load()
-    B, d = z.shape
-    H = params[0].shape[0]
+    B, nz = z.shape
+    H, d = params[0].shape
     dev = z.device
     ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, 0), dtype=torch.uint8, device=dev)
     psi = torch.empty(B, dtype=torch.float32, device=dev)
@@ -183,7 +183,7 @@ def icnn_wide_fwd(z, params, mode, kappa, want_xhat=True):
     xhat = torch.empty(B, d, dtype=torch.float32, device=dev) if want_xhat else None
     g0 = torch.empty(B, H, dtype=torch.float32, device=dev) if want_xhat else None
     ps = _params_struct(params)
-    _C.check(lib.b200vae_icnn_wide_fwd(_ptr(z), B, d, H, C.byref(ps), mode, float(kappa), _ptr(psi), _ptr(xhat), _ptr(h0),
+    _C.check(lib.b200vae_icnn_wide_fwd(_ptr(z), B, d, nz, H, C.byref(ps), mode, float(kappa), _ptr(psi), _ptr(xhat), _ptr(h0),
                                        _ptr(mask1), _ptr(s2), _ptr(g0), _ptr(ws), ws.numel(), _stream()), "icnn_wide_fwd")
     return psi, xhat, (h0, mask1, s2)
 
@@ -194,15 +194,16 @@ class IcnnBrenierWideFn(torch.autograd.Function):
     [B,d]x[d,H] contractions as well; the path is a chain of fused FP32 tile-GEMM kernels with generated operands and
     elementwise epilogues (csrc/icnn_wide.cu): the ANALYTIC forward-then-reverse sweep and double-backward of SURVEY
     Appendix A, no autograd graph, h0 + a byte mask saved instead of ~20 activations.  `precision` is ignored: this path
-    always computes in FP32 (the parity arithmetic)."""
+    always computes in FP32 (the parity arithmetic).  z may be NARROWER than the ICNN input ([B,nz], nz <= d): it is then
+    taken as zero-padded to d columns -- the eye(Dx,D) pad of model.py:824 fused away -- and dz is [B,nz]."""
 
     @staticmethod
     def forward(ctx, z, kappa, mode, precision, *params):
         z = _req(z, "z")
         params = [_req(p, k) for p, k in zip(params, PARAM_FIELDS)]
         H, d = params[0].shape
-        if z.dim() != 2 or z.shape[1] != d:
-            raise _C.B200VaeError(f"z must be [B,{d}], got {tuple(z.shape)}")
+        if z.dim() != 2 or not (1 <= z.shape[1] <= d):
+            raise _C.B200VaeError(f"z must be [B,nz] with nz <= {d}, got {tuple(z.shape)}")
         psi, xhat, saved = icnn_wide_fwd(z, params, mode, kappa, True)
         if any(ctx.needs_input_grad):
             ctx.save_for_backward(z, *saved, *params)
@@ -221,8 +222,8 @@ class IcnnBrenierWideFn(torch.autograd.Function):
             raise NotImplementedError("psi-gradient of the wide-input ICNN: use ICNN.forward (plain autograd) instead")
         lib = _C.load()
         v = _req(v, "grad_xhat")
-        B, d = z.shape
-        H = params[0].shape[0]
+        B, nz = z.shape
+        H, d = params[0].shape
         dev = z.device
         need = ctx.needs_input_grad
         ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, 1), dtype=torch.uint8, device=dev)
@@ -230,7 +231,7 @@ class IcnnBrenierWideFn(torch.autograd.Function):
         grads = [torch.empty_like(p) if n else None for p, n in zip(params, need[4:])]
         dz = torch.empty_like(z) if need[0] else None
         ps, gs = _params_struct(params), _grads_struct(grads)
-        _C.check(lib.b200vae_icnn_wide_bwd(_ptr(z), _ptr(v), _ptr(h0), _ptr(mask1), _ptr(s2), B, d, H, C.byref(ps), mode,
+        _C.check(lib.b200vae_icnn_wide_bwd(_ptr(z), _ptr(v), _ptr(h0), _ptr(mask1), _ptr(s2), B, d, nz, H, C.byref(ps), mode,
                                            float(kappa), C.byref(gs), _ptr(dz), _ptr(scratch[0]), _ptr(scratch[1]),
                                            _ptr(scratch[2]), _ptr(scratch[3]), _ptr(ws), ws.numel(), _stream()),
                  "icnn_wide_bwd")
