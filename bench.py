@@ -228,6 +228,7 @@ def run_ours(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t) / K
 
+    barrier()
     n_before = _C.launch_count()
     tr.step(dev_pool[0])                                   # one eager step: counts this library's launches per step
     torch.cuda.synchronize()
@@ -272,6 +273,7 @@ def run_ours(args, rank, local_rank, world):
                 clocks = sampler.window(t0c + 0.1, time.time())
                 clocks["note"] = "sampled during an untimed ~1 s continuation of the timed loop (timed region < sampling period)"
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    tr.check()                                             # a peer exchange that timed out would have produced garbage
     value = world * B / (ms * 1e-3)
     e2e = world * B / (ms_e2e * 1e-3)
 

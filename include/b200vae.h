@@ -202,8 +202,8 @@ int b200vae_icnn_wide_bwd(const float* z, const float* v, const float* h0, const
  * 64-byte handles out of band (torch.distributed.all_gather_object), maps the others with b200vae_peer_open and
  * fills a b200vae_peer_t with buf[r] = rank r's buffer as addressable from THIS process (own buffer at buf[rank]).
  * A host barrier must separate set-up from the first exchange.  Every rank must issue the same sequence of
- * exchanges per slot (they are collective).  A peer that never arrives times out after 4 s (no GPU hang) and sets a
- * sticky flag readable with b200vae_peer_timed_out. */
+ * exchanges per slot (they are collective).  A peer that never arrives times out after 20 s (no GPU hang) and sets a
+ * sticky per-rank flag readable with b200vae_peer_timed_out; later exchanges on that rank then no longer wait. */
 #define B200VAE_PEER_MAX_WORLD 16
 #define B200VAE_PEER_HANDLE_BYTES 64
 typedef struct b200vae_peer {

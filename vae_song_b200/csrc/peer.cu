@@ -111,14 +111,10 @@ extern "C" int b200vae_peer_free(void* buf) { return buf ? cuda_rc(cudaFree(buf)
 
 extern "C" int b200vae_peer_timed_out(const b200vae_peer_t* comm, int* out) {
   if (!peer_ok(comm, 0) || !out) return B200VAE_EALIGN;
-  int any = 0;
-  for (int s = 0; s < kPeerSlots; ++s) {
-    unsigned flag = 0;
-    int rc = cuda_rc(cudaMemcpy(&flag, &((PeerSlot*)comm->buf[comm->rank] + s)->timed_out, sizeof(flag), cudaMemcpyDeviceToHost));
-    if (rc) return rc;
-    any |= flag != 0;
-  }
-  *out = any;
+  unsigned flag = 0;     // sticky flag of this rank: slot 0 (peer.cuh)
+  int rc = cuda_rc(cudaMemcpy(&flag, &((PeerSlot*)comm->buf[comm->rank])->timed_out, sizeof(flag), cudaMemcpyDeviceToHost));
+  if (rc) return rc;
+  *out = flag != 0;
   return B200VAE_OK;
 }
 

@@ -6,8 +6,9 @@
 //      counters agree without communication; they live on the device so that a CUDA-graph replay advances them);
 //   2. store this rank's payload into data[e&1][rank] of EVERY rank's slot (plain stores through the peer mapping),
 //      __threadfence_system, then release-store flag[e&1][rank] = e on every rank;
-//   3. spin (acquire loads, bounded by a timeout) until the local flag[e&1][q] == e for every q, then read the payloads
-//      from local memory.  Results are combined in rank order, so every rank computes bit-identical values.
+//   3. spin (acquire loads, bounded by a 20 s timeout that sets a sticky per-rank flag) until the local
+//      flag[e&1][q] == e for every q, then read the payloads from local memory.  Results are combined in rank order,
+//      so every rank computes bit-identical values.
 // The parity double-buffer makes slot reuse safe without a trailing barrier: a rank can only publish epoch e+2 into the
 // buffers of epoch e after it passed exchange e+1, i.e. after every rank published e+1, which each does (stream order)
 // only after it finished reading epoch e.
@@ -19,7 +20,7 @@ namespace b200vae {
 constexpr int kPeerMaxWorld = B200VAE_PEER_MAX_WORLD;   // 16
 constexpr int kPeerPay = 400;                           // floats per rank per exchange (>= 3*128 + 1)
 constexpr int kPeerSlots = 64;
-constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;   // 4 s: a missing peer must not hang the GPU
+constexpr unsigned long long kPeerTimeoutNs = 20000000000ull;  // 20 s: a missing peer must not hang the GPU
 
 struct PeerSlot {
   float data[2][kPeerMaxWorld][kPeerPay];
@@ -84,9 +85,13 @@ __device__ __forceinline__ void peer_exchange(const PeerComm& c, int slot, const
   __syncthreads();
   if ((int)threadIdx.x < c.world) {
     st_release_sys(&(c.buf[threadIdx.x] + slot)->flag[par][c.rank], e);
+    // Once any exchange on this rank has timed out (sticky flag in slot 0) later ones do not wait again: a dead peer
+    // costs ONE timeout, not one per exchange, and the host sees the flag through b200vae_peer_timed_out.
+    unsigned* dead = &c.buf[c.rank]->timed_out;
     const unsigned long long t0 = global_timer_ns();
     while (ld_acquire_sys(&local->flag[par][threadIdx.x]) != e) {
-      if (global_timer_ns() - t0 > kPeerTimeoutNs) { local->timed_out = 1u; break; }
+      if (*reinterpret_cast<volatile unsigned*>(dead) != 0u) break;
+      if (global_timer_ns() - t0 > kPeerTimeoutNs) { *reinterpret_cast<volatile unsigned*>(dead) = 1u; break; }
     }
   }
   __syncthreads();

@@ -417,6 +417,7 @@ class FusedMlpFn(torch.autograd.Function):
         bes = [_req(params[2 * nl + 2 * i + 1], "beta") for i in range(nl - 1)]
         scratch = torch.empty(lib.b200vae_mlp_scratch_bytes(B), dtype=torch.uint8, device=x.device)
         ys, stats, counts = [], [], []
+        ticks = []                # num_batches_tracked counters, advanced by one multi-tensor launch at the end
         prev = (x, None, None, None)
         for i in range(nl):
             wo, wi = Ws[i].shape
@@ -433,7 +434,7 @@ class FusedMlpFn(torch.autograd.Function):
                 st = torch.empty(4, wo, dtype=torch.float32, device=x.device)
                 if training and (grp is None or peer is not None):
                     rm, rv, mom = bn.running_mean, bn.running_var, float(bn.momentum)
-                    bn.num_batches_tracked.add_(1)
+                    ticks.append(bn.num_batches_tracked)
             if peer is not None:          # cross-rank statistics exchanged by the finalize kernel itself (peer memory)
                 _C.check(lib.b200vae_mlp_layer_fwd_peer(_ptr(prev[0]), _ptr(prev[1]), _ptr(prev[2]), _ptr(prev[3]), plan.slope,
                                                         _ptr(Ws[i]), _ptr(bs[i]), B, wi, wo, _ptr(y), _ptr(st),
@@ -471,6 +472,8 @@ class FusedMlpFn(torch.autograd.Function):
                     n_glob = None         # read from st[3] in backward (device value)
             ys.append(y); stats.append(st); counts.append(n_glob)
             prev = (y, st, gs[i] if has_bn else None, bes[i] if has_bn else None)
+        if ticks:
+            torch._foreach_add_(ticks, 1)
         ctx.plan, ctx.training, ctx.nl = plan, training, nl
         ctx.save_for_backward(x, *ys, *[s for s in stats if s is not None], *Ws, *gs, *bes)
         ctx.scratch = scratch

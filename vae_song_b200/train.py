@@ -133,13 +133,39 @@ class FlatParams:
             self.flat, self.grad = alloc(n), alloc(n)
             self.flat.zero_(); self.grad.zero_()
         off = 0
+        self.views = []
         for p in params:
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p.data)
             p.grad = self.grad[off:off + k].view_as(p.data)
+            self.views.append(p.grad)
             off += k
         self.numel = n
+        self._had = [False] * len(params)
+
+    def begin_step(self):
+        """Detach every .grad: autograd then hands over each gradient tensor as produced (no zero fill of the flat
+        buffer and no accumulate-add launch per parameter); `gather()` moves them into the flat buffer in one launch."""
+        for p in self.params:
+            p.grad = None
+
+    def gather(self):
+        """Copy the step's gradients into the flat buffer with ONE multi-tensor launch and re-attach the views.
+        Parameters that received no gradient keep a zero segment."""
+        dst, src = [], []
+        for i, (p, view) in enumerate(zip(self.params, self.views)):
+            g = p.grad
+            if g is None:
+                if self._had[i]:
+                    view.zero_()
+                    self._had[i] = False
+            elif g.data_ptr() != view.data_ptr():
+                dst.append(view); src.append(g)
+                self._had[i] = True
+            p.grad = view
+        if dst:
+            torch._foreach_copy_(dst, src)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -211,6 +237,11 @@ class DataParallelTrainer:
         self._opt = optimizer_step or self._fused_adam
         if self.world > 1:   # identical replicas to start from
             dist.broadcast(self.fp.flat, src=0, group=self.pg)
+        if self.peer is not None:
+            # first peer kernel here, not in the first step: module loading skews the ranks by up to seconds at start-up
+            self.peer.barrier()
+            torch.cuda.synchronize()
+            dist.barrier(group=self.pg)
 
     def _fused_adam(self, flat, grad, m, v, t, scale, hp):
         # step count kept on the device so that the call is identical every step (CUDA-graph capturable)
@@ -256,7 +287,7 @@ class DataParallelTrainer:
 
     def step(self, x_local, eps_local=None):
         model, W = self.model, self.world
-        self.fp.zero_grad()
+        self.fp.begin_step()
         kw = {} if eps_local is None else {"eps": eps_local}
         out = model(x_local, **kw)
         total, rec, reg, lr_term = model.loss(x_local, *out)
@@ -265,6 +296,7 @@ class DataParallelTrainer:
             # every other term is a batch mean -> compensate before the 1/W gradient averaging
             total = total + (W - 1) * lr_term
         total.backward()
+        self.fp.gather()
         clip = bool(self.grad_clip and self.grad_clip.get("enabled", False))
         if self.peer is not None and not clip:
             # two-shot all-reduce over peer memory fused with Adam: rank r reduces + updates chunk r and stores it
@@ -284,6 +316,11 @@ class DataParallelTrainer:
         self.t += 1
         self._opt(self.fp.flat, self.fp.grad, self.m, self.v, self.t, scale, self.hp)
         return total.detach(), rec, reg
+
+    def check(self):
+        """Raise if a peer-memory exchange on this rank ever timed out (synchronises; call outside timed regions)."""
+        if self.peer is not None:
+            self.peer.check()
 
     @torch.no_grad()
     def global_losses(self, *local_scalars):
