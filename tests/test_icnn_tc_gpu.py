@@ -177,3 +177,38 @@ def test_tc_forward_workspace_reuse_and_mask_paths():
         assert torch.equal(xhat_a, xhat_b) and torch.equal(xhat_a, xhat_d)
         assert torch.equal(m1, m1d) and torch.equal(m2, m2d)
         assert torch.equal(m2.bool(), psi_a > 0)
+
+
+@pytest.mark.parametrize("shape", [(2, 512, 700), (3, 1024, 300), (1, 256, 1000)], ids=["d2_h512", "d3_h1024", "d1_h256"])
+def test_saved_accumulator_backward_equals_recompute(shape):
+    """3xTF32 training: the pair forward keeps its GEMM2 accumulators in the for_backward workspace and the backward reads
+    them back (icnn_tc3.cu SV kernels) instead of redoing that GEMM.  Re-running prepare on the workspace invalidates the
+    save (host bookkeeping, api.cu), so the same backward then RECOMPUTES -- both must give identical results."""
+    from vae_song_b200 import _C, ops
+    import ctypes as C
+    d, H, B = shape
+    rng = np.random.default_rng(5 + H)
+    p = io.random_params(rng, d, H, np.float64, "mixed")
+    params = params_to_torch(p)
+    z = torch.tensor(rng.normal(0, 1, (B, d)), dtype=torch.float32, device="cuda")
+    v = torch.tensor(rng.normal(0, 1, (B, d)), dtype=torch.float32, device="cuda")
+    res = []
+    for invalidate in (False, True):
+        ws = ops.icnn_prepare(params, d, H, 0, 3, B, True)
+        psi, xhat, m1, m2 = ops.icnn_decode_fwd(z, ws, d, H, 0, 0.1, 3, True, True, True)
+        if invalidate:      # same parameters, so nothing changes numerically -- but the saved accumulators are forgotten
+            ps = ops._params_struct(params)
+            _C.check(_C.load().b200vae_icnn_prepare(C.byref(ps), d, H, 0, 3, ops._ptr(ws), ws.numel(), ops._stream()), "prepare")
+        dz, grads = ops.icnn_decode_bwd(z, v, None, m1, m2, params, ws, d, H, 0, 0.1, 3)
+        torch.cuda.synchronize()
+        res.append((xhat.clone(), dz.clone(), [g.clone() for g in grads]))
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1]), float((res[0][1] - res[1][1]).abs().max())
+    for k, a, b in zip(KEYS, res[0][2], res[1][2]):
+        assert torch.equal(a, b), (k, float((a - b).abs().max()))
+    # and against the fp64 oracle (3xTF32 bounds)
+    rdz, rg = io.icnn_brenier_backward(f32_as_f64(z.cpu().numpy()), f32_as_f64(v.cpu().numpy()), params_f32_as_f64(p), 0, 0.1, None)
+    close_report(res[0][1].cpu().numpy(), rdz, 3e-4, "dz", bad_frac=0.02)
+    for k, g in zip(KEYS, res[0][2]):
+        if np.abs(rg[k]).max() > 0:
+            close_report(g.cpu().numpy(), rg[k], 3e-4, "grad " + k, bad_frac=0.01)

@@ -1,7 +1,10 @@
 // api.cu -- extern "C" entry points of libb200vae.so for the ICNN path (validation + dispatch).
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace b200vae {
 int g_last_cuda_error = 0;
@@ -29,12 +32,50 @@ int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* 
            uint8_t* mask2, int precision, const float* ws, cudaStream_t st);
 int tc3_prepare(int d, int H, int precision, float* ws, cudaStream_t st);
 int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2,
-            int precision, float* ws, cudaStream_t st);
+            int precision, float* ws, float* accsave, cudaStream_t st);
 size_t tc_extra_ws_floats(int B, int d, int H, int precision);
 size_t tc_bwd_ws_floats(int B, int d, int H);
 int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H,
            const b200vae_icnn_params* p, int mode, float kappa, const b200vae_icnn_grads* g, float* dz, int precision,
-           float* ws, cudaStream_t st);
+           float* ws, const float* accsave, cudaStream_t st);
+
+// ---- saved GEMM2 accumulators (training, 3xTF32) ------------------------------------------------------------------------
+// With a for_backward workspace and both masks requested, the pair forward kernel also stores its GEMM2 accumulators
+// (gx1 / s2, [Bp][Hq] fp32) at the end of the workspace; the backward then skips recomputing that GEMM (icnn_tc3.cu, SV
+// kernels).  Which workspace holds a valid save -- and for which (z, B, d, H) -- is tracked HERE on the host, in call
+// order (= stream order for one stream; a CUDA-graph capture records the same decision it replays): prepare invalidates,
+// a saving forward validates, the backward uses the save only on an exact match and otherwise recomputes.
+struct SavedAcc { const void* z; int B, d, H; };
+static std::mutex g_save_mu;
+static std::unordered_map<const void*, SavedAcc> g_saved;
+static bool save_enabled() {
+  static const bool on = [] { const char* e = getenv("B200VAE_SAVE_GX1"); return !e || atoi(e) != 0; }();
+  return on;
+}
+static void save_forget(const void* ws) {
+  std::lock_guard<std::mutex> lk(g_save_mu);
+  g_saved.erase(ws);
+}
+static void save_record(const void* ws, const void* z, int B, int d, int H) {
+  std::lock_guard<std::mutex> lk(g_save_mu);
+  if (g_saved.size() > 1024) g_saved.clear();
+  g_saved[ws] = SavedAcc{z, B, d, H};
+}
+static bool save_matches(const void* ws, const void* z, int B, int d, int H) {
+  std::lock_guard<std::mutex> lk(g_save_mu);
+  auto it = g_saved.find(ws);
+  return it != g_saved.end() && it->second.z == z && it->second.B == B && it->second.d == d && it->second.H == H;
+}
+static size_t bwd_floats_without_save(int B, int d, int H, int precision) {
+  const size_t extra = (precision != B200VAE_PREC_FP32) ? tc_extra_ws_floats(B, d, H, precision) : 0;
+  const WsLayout L = ws_layout(B, d, H, extra);
+  return (L.end + (extra ? tc_bwd_ws_floats(B, d, H) : 0) + 63) / 64 * 64;
+}
+static size_t accsave_floats(int B, int d, int H, int precision) {
+  if (precision != B200VAE_PREC_TF32X3 || d > 3 || !save_enabled()) return 0;
+  const Tc3Layout T3 = tc3_layout(B, d, H);
+  return (size_t)T3.Bp * T3.Hq + 64;
+}
 
 static bool params_ok(const b200vae_icnn_params* p) {
   return p && p->A0w && p->A0b && p->A1w && p->A1b && p->A2w && p->A2b && p->W0 && p->W1 && aligned4(p->A0w) &&
@@ -55,7 +96,8 @@ extern "C" size_t b200vae_icnn_workspace_bytes(int B, int d, int H, int precisio
   if (B <= 0 || d <= 0 || H <= 0) return 0;
   const size_t extra = (precision != B200VAE_PREC_FP32) ? tc_extra_ws_floats(B, d, H, precision) : 0;
   const WsLayout L = ws_layout(B, d, H, extra);
-  const size_t fl = for_backward ? L.end + (extra ? tc_bwd_ws_floats(B, d, H) : 0) : L.fwd_end + extra + 64;
+  const size_t fl = for_backward ? bwd_floats_without_save(B, d, H, precision) + accsave_floats(B, d, H, precision)
+                                 : L.fwd_end + extra + 64;
   return fl * sizeof(float) + 256;
 }
 
@@ -71,6 +113,7 @@ extern "C" int b200vae_icnn_prepare(const b200vae_icnn_params* p, int d, int H, 
   if (weight_mode != B200VAE_WEIGHT_EXP && weight_mode != B200VAE_WEIGHT_CLAMP) return B200VAE_EUNSUP;
   if (!prec_ok(precision)) return B200VAE_EUNSUP;
   if (ws_bytes < b200vae_icnn_workspace_bytes(1, d, H, precision, 0)) return B200VAE_EWS;
+  save_forget(ws_base(ws));
   rc = simt_prepare(p, d, H, weight_mode, ws_base(ws), (cudaStream_t)stream);
   if (rc || precision == B200VAE_PREC_FP32) return rc;
   rc = tc_prepare(p, d, H, weight_mode, precision, ws_base(ws), (cudaStream_t)stream);
@@ -93,7 +136,13 @@ extern "C" int b200vae_icnn_decode_fwd(const float* z, int B, int d, int H, int 
   // does not fit (H > 1024); 1: single-CTA kernel (icnn_tc.cu)
   static const int variant = [] { const char* e = getenv("B200VAE_FWD"); return e ? atoi(e) : 3; }();
   if (variant == 3) {
-    rc = tc3_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), (cudaStream_t)stream);
+    float* accsave = nullptr;
+    if (mask1 && mask2 && xhat && accsave_floats(B, d, H, precision) &&
+        ws_bytes >= b200vae_icnn_workspace_bytes(B, d, H, precision, 1))
+      accsave = ws_base(ws) + bwd_floats_without_save(B, d, H, precision);
+    save_forget(ws_base(ws));
+    rc = tc3_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), accsave, (cudaStream_t)stream);
+    if (rc == B200VAE_OK && accsave) save_record(ws_base(ws), z, B, d, H);
     if (rc != B200VAE_EUNSUP) return rc;
   }
   return tc_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), (cudaStream_t)stream);
@@ -109,8 +158,13 @@ extern "C" int b200vae_icnn_decode_bwd(const float* z, const float* v, const flo
   if (rc) return rc;
   if (!prec_ok(precision)) return B200VAE_EUNSUP;
   if (ws_bytes < b200vae_icnn_workspace_bytes(B, d, H, precision, 1)) return B200VAE_EWS;
-  if (precision != B200VAE_PREC_FP32 && !gpsi)   // tensor-core backward (gpsi path stays on the FP32 kernels)
-    return tc_bwd(z, v, mask1, mask2, B, d, H, p, weight_mode, kappa, grads, dz, precision, ws_base(ws), (cudaStream_t)stream);
+  if (precision != B200VAE_PREC_FP32 && !gpsi) { // tensor-core backward (gpsi path stays on the FP32 kernels)
+    const float* accsave = nullptr;
+    if (accsave_floats(B, d, H, precision) && save_matches(ws_base(ws), z, B, d, H))
+      accsave = ws_base(ws) + bwd_floats_without_save(B, d, H, precision);
+    return tc_bwd(z, v, mask1, mask2, B, d, H, p, weight_mode, kappa, grads, dz, precision, ws_base(ws), accsave,
+                  (cudaStream_t)stream);
+  }
   const size_t extra = (precision != B200VAE_PREC_FP32) ? tc_extra_ws_floats(B, d, H, precision) : 0;
   return simt_bwd(z, v, gpsi, mask1, mask2, B, d, H, p, weight_mode, kappa, grads, dz, ws_base(ws), extra,
                   (cudaStream_t)stream);

@@ -1026,7 +1026,8 @@ static int tc_dp0_splits(int B, int Hq) {
 }
 
 int tc3_bwd_rows(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H, float kappa,
-                 float* dz, float* partA, float* partB, float* a2part, float* dzpart, int precision, float* ws, cudaStream_t st);
+                 float* dz, float* partA, float* partB, float* a2part, float* dzpart, int precision, float* ws,
+                 const float* accsave, cudaStream_t st);
 size_t tc3_bwd_ws_floats(int B, int d, int H);
 
 size_t tc_bwd_ws_floats(int B, int d, int H) {
@@ -1078,7 +1079,7 @@ static int launch_tc_dp0(const float* z, const float* v, const uint32_t* mask1, 
 
 int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H,
            const b200vae_icnn_params* p, int mode, float kappa, const b200vae_icnn_grads* g, float* dz, int precision,
-           float* ws, cudaStream_t st) {
+           float* ws, const float* accsave, cudaStream_t st) {
   if (precision == B200VAE_PREC_BF16 || d > 3 || !v) return B200VAE_EUNSUP;
   const size_t extra = tc_extra_ws_floats(B, d, H, precision);
   const WsLayout L = ws_layout(B, d, H, extra);
@@ -1101,7 +1102,7 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
   if (variant == 3) {
     float* dzpart = dp0part + (size_t)tc_dp0_splits(B, T.Hq) * T.Hq * T.Hq;
     dzpart = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dzpart) + 15) & ~(uintptr_t)15);
-    rc = tc3_bwd_rows(z, v, mask1, mask2, B, d, H, kappa, dz, partA, partB, a2part, dzpart, precision, ws, st);
+    rc = tc3_bwd_rows(z, v, mask1, mask2, B, d, H, kappa, dz, partA, partB, a2part, dzpart, precision, ws, accsave, st);
   }
   if (rc == B200VAE_EUNSUP) {
 #define B200VAE_TCB(DD)                                                                                                 \

@@ -148,6 +148,7 @@ struct alignas(64) Tc3Args {
   uint8_t* mask2;
   float4 *scr1, *scr2;
   uint32_t* cnt;
+  float* accsave;                                 // [T*256][Hq] GEMM2 accumulators (gx1 / s2) kept for the backward, or null
   int B, Hq, T, NP, mask_stride, mask_rows, want_x;
   float kappa;
 };
@@ -278,6 +279,11 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
           tmem_ld32(taddr + buf * 256 + cc * 32, r);
           tmem_ld_wait();
           const int nb = un.p * 256 + chalf * 128 + cc * 32;
+          if (a.accsave != nullptr) {            // training: the backward reads this back instead of redoing GEMM2
+            uint4* dst = reinterpret_cast<uint4*>(a.accsave + (size_t)grow * Hq + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) __stcs(dst + j, make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float4 q = A0qs[nb + j];
@@ -604,6 +610,7 @@ struct alignas(64) Tc3BwdArgs {
   const float4 *A0g, *E1, *A0q;
   float *partA, *partB;
   float4* dzpart;
+  const float* accsave;                           // SV kernels: the forward's GEMM2 accumulators [T*256][Hq]
   int B, Hq, T, NP, Hw_in;
 };
 
@@ -632,7 +639,11 @@ __device__ __forceinline__ void fold8(float (&vals)[NV], int lane) {
   }
 }
 
-template <int D, bool X3>
+// SV ("saved") variant: the forward kept its GEMM2 accumulators (Tc3Args::accsave), so the A-units need no tensor work at
+// all.  The unit list is then the B-units only; for each one the epilogue warps FIRST do the A-part of the same
+// (tile, pass) from global memory -- while the B-unit's MMAs are in flight -- and then drain the B accumulator.  At 3xTF32
+// the kernel is tensor bound, so dropping 2 of the 5 MMAs per element pair shortens it by ~40 %; HBM is idle anyway.
+template <int D, bool X3, bool SV>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k3Threads, 1)
 icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
   using C = Tc3Cfg<X3>;
@@ -656,7 +667,11 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
   const uint32_t rank = cluster_rank3();
   const int cid = (int)cluster_id3(), G = (int)num_clusters3();
   const int T = a.T, NP = a.NP, NKB = Hq / kKB;
-  const int U = 2 * T * NP;
+  const int U = (SV ? 1 : 2) * T * NP;
+  auto unit_of = [&](int u) {
+    if (SV) { Unit x; x.g = 1; x.t = u / NP; x.p = u - x.t * NP; return x; }
+    return decode_unit(u, T, NP);
+  };
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 8 + 2); mbar_init(empty0 + 8 * s, 1); }
@@ -683,7 +698,7 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
     const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(chalf * 128);
     int i = 0;
     for (int u = cid; u < U; u += G, ++i) {
-      const Unit un = decode_unit(u, T, NP);
+      const Unit un = unit_of(u);
       const int buf = i & 1;
       const int m0 = un.t * 256 + (int)rank * k3Rows;
       float zr[4][D], vr[4][D], s2r[4];
@@ -702,94 +717,121 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
         mw[r] = (un.g && in && w0 < a.Hw_in) ? *reinterpret_cast<const uint4*>(a.mask1 + (size_t)gr * a.Hw_in + w0)
                                               : make_uint4(0u, 0u, 0u, 0u);
       }
-      float* part = (un.g ? a.partB : a.partA) + (size_t)((un.t * 8 + (int)rank * 4 + q4) * NF) * Hq;
-      float dz4[4][D];
+      // one part of the unit: isB = B-unit maths (w1 column sums) else A-unit maths (t0, g0, dz);  from_global = the
+      // accumulator comes from the forward's saved GEMM2 output instead of TMEM (SV kernels, A-part only)
+      auto do_part = [&](const bool isB, const bool from_global) {
+        float* part = (isB ? a.partB : a.partA) + (size_t)((un.t * 8 + (int)rank * 4 + q4) * NF) * Hq;
+        float dz4[4][D];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int j = 0; j < D; ++j) dz4[r][j] = 0.f;
-      mbar_wait_parked(accfull0 + 8 * buf, (i >> 1) & 1, 2000);
-      tc_fence_after();
+          for (int j = 0; j < D; ++j) dz4[r][j] = 0.f;
+        if (!from_global) {
+          mbar_wait_parked(accfull0 + 8 * buf, (i >> 1) & 1, 2000);
+          tc_fence_after();
+        }
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t ra[16], rb[16];
-        tmem_ld_16x256b_x4(taddr + buf * 256 + cc * 32, ra);
-        tmem_ld_16x256b_x4(taddr + (16u << 16) + buf * 256 + cc * 32, rb);
-        tmem_ld_wait();
-        const int nb = un.p * 256 + chalf * 128 + cc * 32;
-        float vals[8 * NF];
-        if (!un.g) {
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t ra[16], rb[16];
+          const int nb = un.p * 256 + chalf * 128 + cc * 32;
+          if (from_global) {
 #pragma unroll
-          for (int n = 0; n < 4; ++n)
+            for (int r = 0; r < 4; ++r) {
+              const float* src = a.accsave + (size_t)(m0 + r0 + 8 * r) * Hq + nb + cp2;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float4 q = A0qs[nb + 8 * n + cp2 + e];
-              float ef[NF];
-#pragma unroll
-              for (int f = 0; f < NF; ++f) ef[f] = 0.f;
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const float acc = __uint_as_float((r < 2 ? ra : rb)[4 * n + 2 * (r & 1) + e]);
-                const float h0 = lin_of<D>(q, zr[r]), u0 = dot_of<D>(q, vr[r]);
-                const float s2x2 = 2.f * s2r[r];
-                const float mc = acc * (h0 > 0.f ? s2x2 : (kSlope * kSlope) * s2x2);   // 2 s2 s0^2 acc
-                const float t0 = mc * u0;                                               // u0 2 gx1 s0^2
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                  dz4[r][j] = fmaf(comp(q, j), t0, dz4[r][j]);
-                  ef[j] = fmaf(mc, fmaf(h0, vr[r][j], u0 * zr[r][j]), ef[j]);           // g0 v_j + t0 z_j
-                }
-                ef[D] += t0;
+              for (int n = 0; n < 4; ++n) {
+                const float2 t = __ldcs(reinterpret_cast<const float2*>(src + 8 * n));
+                (r < 2 ? ra : rb)[4 * n + 2 * (r & 1)] = __float_as_uint(t.x);
+                (r < 2 ? ra : rb)[4 * n + 2 * (r & 1) + 1] = __float_as_uint(t.y);
               }
-#pragma unroll
-              for (int f = 0; f < NF; ++f) vals[(2 * n + e) * NF + f] = ef[f];
             }
-        } else {
-#pragma unroll
-          for (int n = 0; n < 4; ++n)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int bitpos = 8 * n + cp2 + e;
-              float ef[NF];
-#pragma unroll
-              for (int f = 0; f < NF; ++f) ef[f] = 0.f;
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const uint32_t wd = cc == 0 ? mw[r].x : (cc == 1 ? mw[r].y : (cc == 2 ? mw[r].z : mw[r].w));
-                const float w1 = __uint_as_float((r < 2 ? ra : rb)[4 * n + 2 * (r & 1) + e]);
-                const float c1 = ((wd >> bitpos) & 1u) ? s2r[r] : kSlope * s2r[r];      // s2 s1
-#pragma unroll
-                for (int j = 0; j < D; ++j) ef[j] = fmaf(c1, vr[r][j], ef[j]);
-                ef[D] = fmaf(c1, w1, ef[D]);
-              }
-#pragma unroll
-              for (int f = 0; f < NF; ++f) vals[(2 * n + e) * NF + f] = ef[f];
-            }
-        }
-        fold8<8 * NF>(vals, lane);
-        const int cs = (lane >> 2) & 7;                          // my column slot after the fold
-        const int col = nb + 8 * (cs >> 1) + cp2 + (cs & 1);
-        const float p1 = un.g ? E1s[col].x : 1.f;                // dA1w carries P1 (g1 = s2 P1 s1)
-#pragma unroll
-        for (int f = 0; f < NF; ++f) part[(size_t)f * Hq + col] = (f < D) ? vals[f] * p1 : vals[f];
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(lead_accempty0 + 8 * buf);
-      if (!un.g) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          float o[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-          for (int j = 0; j < D; ++j) {
-            float t = dz4[r][j];
-            t += __shfl_xor_sync(0xffffffffu, t, 1);
-            t += __shfl_xor_sync(0xffffffffu, t, 2);
-            o[j] = t;
+          } else {
+            tmem_ld_16x256b_x4(taddr + buf * 256 + cc * 32, ra);
+            tmem_ld_16x256b_x4(taddr + (16u << 16) + buf * 256 + cc * 32, rb);
+            tmem_ld_wait();
           }
-          if ((lane & 3) == 0)
-            a.dzpart[((size_t)(m0 + r0 + 8 * r) * NP + un.p) * 2 + chalf] = make_float4(o[0], o[1], o[2], 0.f);
+          float vals[8 * NF];
+          if (!isB) {
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float4 q = A0qs[nb + 8 * n + cp2 + e];
+                float ef[NF];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) ef[f] = 0.f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const float acc = __uint_as_float((r < 2 ? ra : rb)[4 * n + 2 * (r & 1) + e]);
+                  const float h0 = lin_of<D>(q, zr[r]), u0 = dot_of<D>(q, vr[r]);
+                  const float s2x2 = 2.f * s2r[r];
+                  const float mc = acc * (h0 > 0.f ? s2x2 : (kSlope * kSlope) * s2x2);   // 2 s2 s0^2 acc
+                  const float t0 = mc * u0;                                               // u0 2 gx1 s0^2
+#pragma unroll
+                  for (int j = 0; j < D; ++j) {
+                    dz4[r][j] = fmaf(comp(q, j), t0, dz4[r][j]);
+                    ef[j] = fmaf(mc, fmaf(h0, vr[r][j], u0 * zr[r][j]), ef[j]);           // g0 v_j + t0 z_j
+                  }
+                  ef[D] += t0;
+                }
+#pragma unroll
+                for (int f = 0; f < NF; ++f) vals[(2 * n + e) * NF + f] = ef[f];
+              }
+          } else {
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int bitpos = 8 * n + cp2 + e;
+                float ef[NF];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) ef[f] = 0.f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const uint32_t wd = cc == 0 ? mw[r].x : (cc == 1 ? mw[r].y : (cc == 2 ? mw[r].z : mw[r].w));
+                  const float w1 = __uint_as_float((r < 2 ? ra : rb)[4 * n + 2 * (r & 1) + e]);
+                  const float c1 = ((wd >> bitpos) & 1u) ? s2r[r] : kSlope * s2r[r];      // s2 s1
+#pragma unroll
+                  for (int j = 0; j < D; ++j) ef[j] = fmaf(c1, vr[r][j], ef[j]);
+                  ef[D] = fmaf(c1, w1, ef[D]);
+                }
+#pragma unroll
+                for (int f = 0; f < NF; ++f) vals[(2 * n + e) * NF + f] = ef[f];
+              }
+          }
+          fold8<8 * NF>(vals, lane);
+          const int cs = (lane >> 2) & 7;                          // my column slot after the fold
+          const int col = nb + 8 * (cs >> 1) + cp2 + (cs & 1);
+          const float p1 = isB ? E1s[col].x : 1.f;                 // dA1w carries P1 (g1 = s2 P1 s1)
+#pragma unroll
+          for (int f = 0; f < NF; ++f) part[(size_t)f * Hq + col] = (f < D) ? vals[f] * p1 : vals[f];
         }
+        if (!from_global) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(lead_accempty0 + 8 * buf);
+        }
+        if (!isB) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+              float t = dz4[r][j];
+              t += __shfl_xor_sync(0xffffffffu, t, 1);
+              t += __shfl_xor_sync(0xffffffffu, t, 2);
+              o[j] = t;
+            }
+            if ((lane & 3) == 0)
+              a.dzpart[((size_t)(m0 + r0 + 8 * r) * NP + un.p) * 2 + chalf] = make_float4(o[0], o[1], o[2], 0.f);
+          }
+        }
+      };
+      if (SV) {
+        do_part(false, true);       // A-part from the saved accumulators, overlapping this unit's MMAs
+        do_part(true, false);
+      } else {
+        do_part(un.g != 0, false);
       }
     }
   } else if (warp_u < 16) {
@@ -820,7 +862,7 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
     };
     const int NST = NKB / 2;
     for (int u = cid; u < U; u += G) {
-      const Unit un = decode_unit(u, T, NP);
+      const Unit un = unit_of(u);
       const int m0 = un.t * 256 + (int)rank * k3Rows;
       if (!un.g) {
         // ---------------- A-units: bits -> 1 + 4*bit ----------------
@@ -946,7 +988,7 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
     // =========================== TMA producer ===========================
     uint32_t it = 0;
     for (int u = cid; u < U; u += G) {
-      const Unit un = decode_unit(u, T, NP);
+      const Unit un = unit_of(u);
       const CUtensorMap* mhi = un.g ? &a.b1hi : &a.b2hi;
       const CUtensorMap* mlo = un.g ? &a.b1lo : &a.b2lo;
       const int nreal = un.g ? NKB + 1 : NKB, npad = (nreal + 1) & ~1;
@@ -979,7 +1021,7 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
     uint32_t it = 0;
     int i = 0;
     for (int u = cid; u < U; u += G, ++i) {
-      const Unit un = decode_unit(u, T, NP);
+      const Unit un = unit_of(u);
       const int buf = i & 1;
       const int nreal = un.g ? NKB + 1 : NKB, npad = (nreal + 1) & ~1;
       mbar_wait(accempty0 + 8 * buf, ((i >> 1) & 1) ^ 1);
@@ -1142,21 +1184,22 @@ static int max_clusters_for(const void* fn, size_t smem) {
   return n;
 }
 
-template <int D, bool X3>
+template <int D, bool X3, bool SV>
 static int launch_tc3_bwd(const Tc3BwdArgs& args, cudaStream_t st) {
   const size_t smem = tc3_smem_bytes<X3>(args.Hq);
   if (smem > 227 * 1024) return B200VAE_EUNSUP;
   static int max_clusters = 0;
-  if (max_clusters == 0) max_clusters = max_clusters_for(reinterpret_cast<const void*>(icnn_tc3_bwd_kernel<D, X3>), smem);
-  const int units = 2 * args.T * args.NP;
+  if (max_clusters == 0) max_clusters = max_clusters_for(reinterpret_cast<const void*>(icnn_tc3_bwd_kernel<D, X3, SV>), smem);
+  const int units = (SV ? 1 : 2) * args.T * args.NP;
   const int G = units < max_clusters ? units : max_clusters;
-  icnn_tc3_bwd_kernel<D, X3><<<2 * G, k3Threads, smem, st>>>(args);
+  icnn_tc3_bwd_kernel<D, X3, SV><<<2 * G, k3Threads, smem, st>>>(args);
   return check_launch();
 }
 
 // rows part of the backward: fills partA/partB [T*8][d+1][Hq], a2part [T][d], dz [B,d] (layouts of icnn_tc.cu's tc_bwd)
 int tc3_bwd_rows(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H, float kappa,
-                 float* dz, float* partA, float* partB, float* a2part, float* dzpart, int precision, float* ws, cudaStream_t st) {
+                 float* dz, float* partA, float* partB, float* a2part, float* dzpart, int precision, float* ws,
+                 const float* accsave, cudaStream_t st) {
   if (precision == B200VAE_PREC_BF16 || d > 3) return B200VAE_EUNSUP;
   const WsLayout L = ws_layout(1, d, H);
   const TcLayout T = tc_layout(d, H);
@@ -1175,8 +1218,13 @@ int tc3_bwd_rows(const float* z, const float* v, const uint32_t* mask1, const ui
   args.A0q = reinterpret_cast<const float4*>(tb + T.A0q);
   args.partA = partA; args.partB = partB;
   args.dzpart = reinterpret_cast<float4*>(dzpart);
+  args.accsave = accsave;
   args.B = B; args.Hq = T3.Hq; args.T = T3.Bp / 256; args.NP = T3.NP; args.Hw_in = L.Hp / 32;
-#define B200VAE_TC3B(DD) rc = x3 ? launch_tc3_bwd<DD, true>(args, st) : launch_tc3_bwd<DD, false>(args, st)
+  // the saved-accumulator kernels pay off where the kernel is tensor bound (3xTF32); at 1xTF32 the epilogue warps are the
+  // bottleneck either way and recomputing GEMM2 is free
+#define B200VAE_TC3B(DD)                                                                                      \
+  rc = x3 ? (accsave ? launch_tc3_bwd<DD, true, true>(args, st) : launch_tc3_bwd<DD, true, false>(args, st)) \
+          : launch_tc3_bwd<DD, false, false>(args, st)
   switch (d) {
     case 1: B200VAE_TC3B(1); break;
     case 2: B200VAE_TC3B(2); break;
@@ -1206,7 +1254,7 @@ static int launch_tc3(const Tc3Args& args, int units, cudaStream_t st) {
 }
 
 int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2,
-            int precision, float* ws, cudaStream_t st) {
+            int precision, float* ws, float* accsave, cudaStream_t st) {
   if (precision == B200VAE_PREC_BF16 || d > 3) return B200VAE_EUNSUP;
   const WsLayout L = ws_layout(1, d, H);
   const TcLayout T = tc_layout(d, H);
@@ -1236,6 +1284,7 @@ int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float*
   args.scr1 = reinterpret_cast<float4*>(t3 + T3.scr1);
   args.scr2 = reinterpret_cast<float4*>(t3 + T3.scr2);
   args.cnt = reinterpret_cast<uint32_t*>(t3 + T3.cnt);
+  args.accsave = args.want_x ? accsave : nullptr;
   args.B = B; args.Hq = T3.Hq; args.T = T3.Bp / 256; args.NP = T3.NP; args.kappa = kappa;
   const int units = (args.want_x ? 2 : 1) * args.T * args.NP;
 #define B200VAE_TC3(DD) return x3 ? launch_tc3<DD, true>(args, units, st) : launch_tc3<DD, false>(args, units, st)
