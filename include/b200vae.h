@@ -180,13 +180,16 @@ int b200vae_nn_sqdist_bwd(const float* A, const float* Bp, const int* argA, cons
  * Caller-owned activations: h0 [B,H] fp32, mask1 [B,H] uint8 (h1 > 0), s2 [B] fp32 (1 or 0.2) are SAVED by the forward
  * for the backward; g0 (fwd) and u0,q1,g0,t0 (bwd) are [B,H] fp32 scratch.  psi may be NULL; xhat NULL = psi only.
  * The backward takes v = dL/dxhat only (no psi-gradient) and OVERWRITES every non-null field of `g` and dz.
+ * `precision` (forward): FP32 = the tile-GEMM chain above; TF32 / TF32X3 = the same chain on tcgen05 (csrc/icnn_wide_tc.cu:
+ * TMA-fed 128x256 tiles, transform + hi/lo split of the A tile in shared memory, accumulators in TMEM) when d, nz, H are
+ * multiples of 4, else FP32.  The backward is FP32 in every mode and runs on whatever forward produced h0 / mask1 / s2.
  * `nz` (1 <= nz <= d): z is [B,nz] and the ICNN input is z ZERO-PADDED to d columns -- the x = x1 B^T step of
  * model.py:824 with B = eye(Dx, D) fused away (nz = D = 32, d = Dx = 784): products with z run over nz columns only,
  * xhat is [B,d], v is [B,d], dz is [B,nz].  nz = d is the plain case. */
-size_t b200vae_icnn_wide_workspace_bytes(int B, int d, int H, int for_backward);
+size_t b200vae_icnn_wide_workspace_bytes(int B, int d, int H, int precision, int for_backward);
 int b200vae_icnn_wide_fwd(const float* z, int B, int d, int nz, int H, const b200vae_icnn_params* p, int weight_mode, float kappa,
-                          float* psi, float* xhat, float* h0, uint8_t* mask1, float* s2, float* g0, void* workspace,
-                          size_t ws_bytes, void* stream);
+                          float* psi, float* xhat, float* h0, uint8_t* mask1, float* s2, float* g0, int precision,
+                          void* workspace, size_t ws_bytes, void* stream);
 int b200vae_icnn_wide_bwd(const float* z, const float* v, const float* h0, const uint8_t* mask1, const float* s2, int B,
                           int d, int nz, int H, const b200vae_icnn_params* p, int weight_mode, float kappa,
                           const b200vae_icnn_grads* g, float* dz, float* u0, float* q1, float* g0, float* t0,

@@ -10,6 +10,7 @@ from vae_song_b200 import module, ops
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device("cuda")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+PRECS = sys.argv[2].split(",") if len(sys.argv) > 2 else ["fp32", "tf32x3", "tf32"]
 kappa = 0.1
 rng = np.random.default_rng(0)
 ics = []
@@ -61,11 +62,17 @@ def timeit(fn, train, n=10):
     return e0.elapsed_time(e1) / n
 
 
-ya, yb = fused(False), eager(False)
-print(f"B={B}: max rel diff fused vs eager {float((ya - yb).abs().max() / yb.abs().max()):.2e}")
 fl_dec = io.flops_decode(32, 512) + io.flops_decode(784, 1024)
-for train in (False, True):
-    tf, te = timeit(fused, train), timeit(eager, train)
-    what = "decode+backward" if train else "decode"
-    extra = f"  fused decode = {fl_dec * B / (tf * 1e-3) / 1e12:.1f} TFLOP/s dense-algorithmic (FP32 SIMT peak 74.4)" if not train else ""
-    print(f"{what}: fused {tf:.3f} ms ({B / tf * 1e3 / 1e6:.2f} M samples/s), PyTorch eager cuBLAS-FP32 {te:.3f} ms -> {te / tf:.2f}x{extra}")
+yb = eager(False).detach()
+te = {False: timeit(eager, False), True: timeit(eager, True)}
+for prec in PRECS:
+    for ic in ics:
+        ic.precision = prec
+    ya = fused(False).detach()
+    diff = (ya - yb).abs()
+    print(f"B={B} {prec}: fused vs eager max rel diff {float(diff.max() / yb.abs().max()):.2e}, median {float(diff.median() / yb.abs().max()):.2e}")
+    for train in (False, True):
+        tf = timeit(fused, train)
+        what = "decode+backward" if train else "decode"
+        extra = f"  = {fl_dec * B / (tf * 1e-3) / 1e12:.1f} TFLOP/s dense-algorithmic" if not train else ""
+        print(f"  {what}: fused {tf:.3f} ms ({B / tf * 1e3 / 1e6:.2f} M samples/s), PyTorch eager cuBLAS-FP32 {te[train]:.3f} ms -> {te[train] / tf:.2f}x{extra}")

@@ -136,3 +136,49 @@ def test_wide_implicit_zero_pad_equals_explicit_pad():
         else:
             close_report(t.grad.cpu().numpy(), full[3][k], 1e-6, "grad " + k)
     check_against_oracle(p, z, v, 0, 0.1, full)
+
+
+# ---- tcgen05 forward (csrc/icnn_wide_tc.cu): stated looser bounds, like the d <= 3 tensor-core kernels ----------------------
+TC_BOUNDS = {3: (3e-5, 1e-4, 3e-4), 1: (2e-4, 5e-3, 5e-3)}      # precision -> (psi, xhat, gradients)
+TC_SHAPES = [(32, 512, 129, "mixed", 0, 0.1, 203), (784, 256, 40, "mixed", 0, 0.05, 204), (36, 96, 1000, "clampy", 1, 0.2, 205),
+             (8, 1024, 300, "mixed", 0, 0.0, 206)]
+
+
+@pytest.mark.parametrize("prec", [3, 1], ids=["tf32x3", "tf32"])
+@pytest.mark.parametrize("shape", TC_SHAPES, ids=[f"d{s[0]}_h{s[1]}_b{s[2]}" for s in TC_SHAPES])
+def test_wide_tc_forward_and_fp32_backward_vs_oracle(shape, prec):
+    from vae_song_b200 import ops
+    d, H, B, regime, mode, kappa, seed = shape
+    p, z, v, _ = case_inputs(d, H, B, regime, seed)
+    params = [t.requires_grad_(True) for t in params_to_torch(p, "cuda")]
+    zt = torch.tensor(z, dtype=torch.float32, device="cuda", requires_grad=True)
+    psi, xhat = ops.IcnnBrenierWideFn.apply(zt, kappa, mode, prec, *params)
+    (xhat * torch.tensor(v, dtype=torch.float32, device="cuda")).sum().backward()
+    p64, z64, v64 = params_f32_as_f64(p), f32_as_f64(z), f32_as_f64(v)
+    rpsi, rxhat, _ = io.icnn_brenier(z64, p64, mode, kappa)
+    rdz, rg = io.icnn_brenier_backward(z64, v64, p64, mode, kappa, None)
+    bp, bx, bg = TC_BOUNDS[prec]
+    close_report(psi.detach().cpu().numpy(), rpsi, bp, "psi")
+    close_report(xhat.detach().cpu().numpy(), rxhat, bx, "xhat", bad_frac=0.02)
+    close_report(zt.grad.cpu().numpy(), rdz, bg, "dz", bad_frac=0.02)
+    for k, t in zip(KEYS, params):
+        if np.abs(rg[k]).max() == 0:
+            assert float(t.grad.abs().max()) == 0.0, k
+        else:
+            # 1xTF32 flips more LeakyReLU masks near 0 (the FP32 backward then follows the flipped masks)
+            close_report(t.grad.cpu().numpy(), rg[k], bg, "grad " + k, bad_frac=0.01 if prec == 3 else 0.05)
+
+
+def test_wide_tc_matches_fp32_kernels_with_implicit_pad():
+    from vae_song_b200 import ops
+    d, nz, H, B = 784, 32, 512, 200
+    p, z, v, _ = case_inputs(d, H, B, "mixed", 41)
+    params = params_to_torch(p, "cuda")
+    zt = torch.tensor(z[:, :nz].copy(), dtype=torch.float32, device="cuda")
+    ref = ops.IcnnBrenierWideFn.apply(zt, 0.1, 0, 0, *params)
+    for prec in (3, 1):
+        bp, bx, _ = TC_BOUNDS[prec]
+        got = ops.IcnnBrenierWideFn.apply(zt, 0.1, 0, prec, *params)
+        assert got[1].shape == (B, d)
+        close_report(got[0].cpu().numpy(), ref[0].cpu().numpy(), bp, "psi vs fp32 kernels")
+        close_report(got[1].cpu().numpy(), ref[1].cpu().numpy(), bx, "xhat vs fp32 kernels", bad_frac=0.02)

@@ -115,9 +115,9 @@ def load():
     lib.b200vae_nn_sqdist_bwd.restype = i
     lib.b200vae_nn_sqdist_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp]
     lib.b200vae_icnn_wide_workspace_bytes.restype = sz
-    lib.b200vae_icnn_wide_workspace_bytes.argtypes = [i, i, i, i]
+    lib.b200vae_icnn_wide_workspace_bytes.argtypes = [i, i, i, i, i]
     lib.b200vae_icnn_wide_fwd.restype = i
-    lib.b200vae_icnn_wide_fwd.argtypes = [vp, i, i, i, i, C.POINTER(IcnnParams), i, f, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.b200vae_icnn_wide_fwd.argtypes = [vp, i, i, i, i, C.POINTER(IcnnParams), i, f, vp, vp, vp, vp, vp, vp, i, vp, sz, vp]
     lib.b200vae_icnn_wide_bwd.restype = i
     lib.b200vae_icnn_wide_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, C.POINTER(IcnnParams), i, f, C.POINTER(IcnnGrads), vp,
                                           vp, vp, vp, vp, vp, sz, vp]

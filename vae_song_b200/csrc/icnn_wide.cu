@@ -16,6 +16,8 @@
 //             out : dz = t0 A0 + 2 kappa v
 //             tn  : dA0 = g0^T v + t0^T z,  dA1 = g1^T v,  dP0 = g1^T q1     (split over the batch, ordered slabs)
 // Algebra: SURVEY.md Appendix A (oracle/icnn_oracle.py).  All reductions are ordered: bit-reproducible.
+#include <cstdlib>
+
 #include "gemm_simt.cuh"
 
 namespace b200vae {
@@ -515,24 +517,44 @@ static bool wide_params_ok(const b200vae_icnn_params* p) {
 
 using namespace b200vae;
 
-extern "C" size_t b200vae_icnn_wide_workspace_bytes(int B, int d, int H, int for_backward) {
+namespace b200vae {   // tcgen05 forward, icnn_wide_tc.cu
+size_t wide_tc_ws_floats(int B, int d, int H);
+bool wide_tc_supported(int d, int nz, int H, int precision);
+int wide_tc_fwd(const float* z, int B, int d, int nz, int H, const b200vae_icnn_params* p, int mode, float kappa, float* psi,
+                float* xhat, float* h0, uint8_t* mask1, float* s2, float* g0, float* ws, int precision, cudaStream_t st);
+}
+
+extern "C" size_t b200vae_icnn_wide_workspace_bytes(int B, int d, int H, int precision, int for_backward) {
   if (B <= 0 || d <= 0 || H <= 0) return 0;
-  return wide_layout(B, d, H, for_backward != 0).end * sizeof(float);
+  size_t fl = wide_layout(B, d, H, for_backward != 0).end;
+  if (!for_backward && precision != B200VAE_PREC_FP32) {
+    const size_t t = wide_tc_ws_floats(B, d, H);
+    if (t > fl) fl = t;
+  }
+  return fl * sizeof(float);
 }
 
 #define WIDE_CHECK() do { rc = check_launch(); if (rc) return rc; } while (0)
 
 extern "C" int b200vae_icnn_wide_fwd(const float* z, int B, int d, int nz, int H, const b200vae_icnn_params* p, int weight_mode,
                                      float kappa, float* psi, float* xhat, float* h0, uint8_t* mask1, float* s2, float* g0,
-                                     void* workspace, size_t ws_bytes, void* stream) {
+                                     int precision, void* workspace, size_t ws_bytes, void* stream) {
   if (!z || !wide_params_ok(p) || !h0 || !mask1 || !s2 || !workspace || (xhat && !g0)) return B200VAE_EALIGN;
   if (B <= 0 || d <= 0 || H <= 0 || nz <= 0 || nz > d) return B200VAE_ESHAPE;
   if (weight_mode != B200VAE_WEIGHT_EXP && weight_mode != B200VAE_WEIGHT_CLAMP) return B200VAE_EUNSUP;
+  if (precision < B200VAE_PREC_FP32 || precision > B200VAE_PREC_TF32X3 || precision == B200VAE_PREC_BF16) return B200VAE_EUNSUP;
   const WideWs L = wide_layout(B, d, H, false);
-  if (ws_bytes < L.end * sizeof(float)) return B200VAE_EWS;
-  if (!aligned16(workspace) || !aligned16(z) || !aligned16(h0) || !aligned16(p->A0w) || !aligned16(p->A1w)) return B200VAE_EALIGN;
+  if (ws_bytes < b200vae_icnn_wide_workspace_bytes(B, d, H, precision, 0)) return B200VAE_EWS;
+  if (!aligned16(workspace) || !aligned16(z) || !aligned16(h0) || !aligned16(p->A0w) || !aligned16(p->A1w) ||
+      (g0 && !aligned16(g0)) || (xhat && !aligned16(xhat)) || !aligned16(p->A0b) || !aligned16(p->A1b) || !aligned16(p->A2w))
+    return B200VAE_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
+  static const bool tc_on = [] { const char* e = getenv("B200VAE_WIDE_TC"); return !e || atoi(e) != 0; }();
+  if (precision != B200VAE_PREC_FP32 && tc_on && wide_tc_supported(d, nz, H, precision)) {   // tcgen05 forward
+    const int rc_tc = wide_tc_fwd(z, B, d, nz, H, p, weight_mode, kappa, psi, xhat, h0, mask1, s2, g0, ws, precision, st);
+    if (rc_tc != B200VAE_EUNSUP) return rc_tc;
+  }
   int rc = wide_prepare(p, d, H, weight_mode, ws, L, st);
   if (rc) return rc;
   const dim3 gH(L.mt, L.nt), gD(L.mt, (d + 127) / 128);

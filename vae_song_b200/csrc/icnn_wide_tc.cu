@@ -1,0 +1,415 @@
+// icnn_wide_tc.cu -- tcgen05 FORWARD (decode: psi + Brenier map) for wide-input ICNNs (d > 4): the MNIST-shaped decoder
+// ICNN(32,512) + ICNN(784,1024) of BASELINE configs[3] (model.py:766-805, module.py:142-148, model.py:820-828).
+//
+// For wide inputs every product of the sweep is a dense contraction, so the forward is four launches of ONE generic
+// tensor-core GEMM kernel  C[M,N] = xf(A1)[M,K1] . B1[N,K1]^T (+ A2[M,K2] . B2[N,K2]^T)  with different epilogues:
+//   lin : h0 = z A0^T + b0                                   (store h0)
+//   hid : h1 = sigma(h0)^2 P0^T + z A1^T + b1 -> byte mask, g1b = P1*sigma'(h1) (fp32), row partials of P1.sigma(h1)
+//   row : h2 = sum partials + A2 z + b2 -> psi, s2            (small SIMT kernel)
+//   gx1 : g0' = (g1b P0) * 2 a0 s0                            (s2 factored out: it is a per-row scalar)
+//   out : xhat = s2 * (g0' A0 + g1b A1 + A2) + 2 kappa z
+// Kernel: CTA tile 128 x 256, K in 16-float blocks (64-byte rows, SWIZZLE_64B), 4-stage ring.  Warp 8 streams BOTH
+// operands with TMA (out-of-bounds rows/columns are zero filled: ragged B, d, H need no special cases); warps 0-7 apply
+// the elementwise transform to the raw A tile IN PLACE in shared memory (the swizzle does not matter for an elementwise
+// pass) and split it into tf32 hi / lo; warp 9 issues tcgen05.mma.kind::tf32 (3 MMAs per product at 3xTF32, B hi/lo
+// prepared once per forward); the accumulator (128 lanes x 256 columns of TMEM) is drained by warps 0-7 with
+// tcgen05.ld.32x32b: one thread = one sample row x 128 columns, so row partials need no shuffles and stores are
+// row-contiguous.  The saved activations (h0, byte mask, s2) have the SIMT layout: the FP32 backward (icnn_wide.cu)
+// runs unchanged on them.
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace b200vae {
+
+constexpr int kWtThreads = 10 * 32;
+constexpr int kWtStages = 4;
+constexpr int kWtATile = 128 * 64, kWtBTile = 256 * 64;
+
+enum { WT_XF_ID = 0, WT_XF_X1 = 1 };
+enum { WT_EPI_LIN = 0, WT_EPI_HID = 1, WT_EPI_GX1 = 2, WT_EPI_OUT = 3 };
+
+struct alignas(64) WtArgs {
+  CUtensorMap a1, b1hi, b1lo, a2, b2hi, b2lo;
+  int nkb1, nkb2, xf1, M, N, epi;
+  const float* bias;     // LIN: b0, HID: b1
+  const float* P1;       // HID
+  const float* h0;       // GX1
+  const float* s2;       // OUT
+  const float* A2w;      // OUT
+  const float* z;        // OUT: [M, nz]
+  int nz;
+  float kappa2;
+  float* out0;           // LIN: h0, HID: g1b, GX1: g0', OUT: xhat   (row stride N)
+  uint8_t* mask;         // HID
+  float* part;           // HID: [M][npart]
+  int npart;
+};
+
+template <bool X3>
+struct WtCfg {
+  static constexpr int kStage = kWtATile * (X3 ? 2 : 1) + kWtBTile * (X3 ? 2 : 1);
+  static constexpr int kOffAlo = kWtATile, kOffB = kWtATile * (X3 ? 2 : 1), kOffBlo = kOffB + kWtBTile;
+};
+template <bool X3>
+static size_t wt_smem_bytes() { return (size_t)kWtStages * WtCfg<X3>::kStage + (3 * kWtStages + 1) * 8 + 16 + 1024; }
+
+template <bool X3>
+__global__ void __launch_bounds__(kWtThreads, 1)
+wide_tc_gemm_kernel(const __grid_constant__ WtArgs a) {
+  using C = WtCfg<X3>;
+  constexpr int S = kWtStages;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* stages = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * C::kStage);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
+  const uint32_t full0 = smem_u32(bars), ready0 = smem_u32(bars + S), empty0 = smem_u32(bars + 2 * S),
+                 accfull = smem_u32(bars + 3 * S);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 256;
+  const int nkb = a.nkb1 + a.nkb2;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(ready0 + 8 * s, 8); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(accfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_u < 8) {
+    // =========================== transform warps, then epilogue ===========================
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S;
+      mbar_wait(full0 + 8 * s, (kb / S) & 1);
+      const bool x1 = (kb < a.nkb1) && (a.xf1 == WT_XF_X1);
+      unsigned char* At = stages + s * C::kStage;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float4* p = reinterpret_cast<float4*>(At + (tid + 256 * h) * 16);
+        float4 v = *p;
+        if (x1) {
+          float t;
+          t = fmaxf(v.x, kSlope * v.x); v.x = t * t;
+          t = fmaxf(v.y, kSlope * v.y); v.y = t * t;
+          t = fmaxf(v.z, kSlope * v.z); v.z = t * t;
+          t = fmaxf(v.w, kSlope * v.w); v.w = t * t;
+        }
+        if (X3) {
+          const float4 hi = make_float4(rn_tf32_masked(v.x), rn_tf32_masked(v.y), rn_tf32_masked(v.z), rn_tf32_masked(v.w));
+          *p = hi;
+          *reinterpret_cast<float4*>(At + C::kOffAlo + (tid + 256 * h) * 16) =
+              make_float4(rn_tf32_fast(v.x - hi.x), rn_tf32_fast(v.y - hi.y), rn_tf32_fast(v.z - hi.z), rn_tf32_fast(v.w - hi.w));
+        } else {
+          *p = make_float4(rn_tf32_fast(v.x), rn_tf32_fast(v.y), rn_tf32_fast(v.z), rn_tf32_fast(v.w));
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ready0 + 8 * s);
+    }
+    // ---- epilogue: my row, 128 of the tile's 256 columns ----
+    const int q4 = warp & 3, chalf = warp >> 2;
+    const int row = m0 + q4 * 32 + lane;
+    const bool rin = row < a.M;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(chalf * 128);
+    mbar_wait_parked(accfull, 0, 1000);
+    tc_fence_after();
+    float rowsum = 0.f;
+    const float s2r = (a.epi == WT_EPI_OUT && rin) ? a.s2[row] : 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t r[32];
+      tmem_ld32(taddr + cc * 32, r);
+      tmem_ld_wait();
+      const int c0 = n0 + chalf * 128 + cc * 32;
+      if (!rin || c0 >= a.N) continue;
+      const int nv = min(32, a.N - c0);                    // N % 4 == 0: whole float4 groups
+      float* orow = a.out0 + (size_t)row * a.N + c0;
+      if (a.epi == WT_EPI_LIN) {
+        for (int j = 0; j < nv; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(a.bias + c0 + j);
+          *reinterpret_cast<float4*>(orow + j) = make_float4(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y,
+                                                             __uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w);
+        }
+      } else if (a.epi == WT_EPI_HID) {
+        uint8_t* mrow = a.mask + (size_t)row * a.N + c0;
+        for (int j = 0; j < nv; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(a.bias + c0 + j);
+          const float4 p1 = *reinterpret_cast<const float4*>(a.P1 + c0 + j);
+          const float h[4] = {__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y, __uint_as_float(r[j + 2]) + b.z,
+                              __uint_as_float(r[j + 3]) + b.w};
+          const float pp[4] = {p1.x, p1.y, p1.z, p1.w};
+          float g[4];
+          uint32_t mb = 0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const bool pos = h[e] > 0.f;
+            rowsum = fmaf(pp[e], pos ? h[e] : kSlope * h[e], rowsum);
+            g[e] = pos ? pp[e] : kSlope * pp[e];
+            mb |= (pos ? 1u : 0u) << (8 * e);
+          }
+          *reinterpret_cast<float4*>(orow + j) = make_float4(g[0], g[1], g[2], g[3]);
+          *reinterpret_cast<uint32_t*>(mrow + j) = mb;
+        }
+      } else if (a.epi == WT_EPI_GX1) {
+        const float* hrow = a.h0 + (size_t)row * a.N + c0;
+        for (int j = 0; j < nv; j += 4) {
+          const float4 hv = *reinterpret_cast<const float4*>(hrow + j);
+          const float h[4] = {hv.x, hv.y, hv.z, hv.w};
+          float g[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float sl = h[e] > 0.f ? 1.f : kSlope;
+            g[e] = __uint_as_float(r[j + e]) * (2.f * h[e] * sl * sl);
+          }
+          *reinterpret_cast<float4*>(orow + j) = make_float4(g[0], g[1], g[2], g[3]);
+        }
+      } else {   // WT_EPI_OUT
+        for (int j = 0; j < nv; j += 4) {
+          const float4 a2 = *reinterpret_cast<const float4*>(a.A2w + c0 + j);
+          float o[4] = {s2r * (__uint_as_float(r[j]) + a2.x), s2r * (__uint_as_float(r[j + 1]) + a2.y),
+                        s2r * (__uint_as_float(r[j + 2]) + a2.z), s2r * (__uint_as_float(r[j + 3]) + a2.w)};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (c0 + j + e < a.nz) o[e] = fmaf(a.kappa2, a.z[(size_t)row * a.nz + c0 + j + e], o[e]);
+          *reinterpret_cast<float4*>(orow + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    if (a.epi == WT_EPI_HID && rin) a.part[(size_t)row * a.npart + blockIdx.y * 2 + chalf] = rowsum;
+    tc_fence_before();
+  } else if (warp_u == 8) {
+    // =========================== TMA producer: A (raw) and B (hi, lo) tiles ===========================
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S;
+      mbar_wait(empty0 + 8 * s, ((kb / S) & 1) ^ 1);
+      if (elect_one()) {
+        const bool p2 = kb >= a.nkb1;
+        const int k0 = (p2 ? kb - a.nkb1 : kb) * kKB;
+        const uint32_t bar = full0 + 8 * s;
+        const uint32_t dst = smem_u32(stages + s * C::kStage);
+        mbar_arrive_expect_tx(bar, kWtATile + kWtBTile * (X3 ? 2 : 1));
+        tma_load_2d(dst, p2 ? &a.a2 : &a.a1, bar, k0, m0);
+        tma_load_2d(dst + C::kOffB, p2 ? &a.b2hi : &a.b1hi, bar, k0, n0);
+        if (X3) tma_load_2d(dst + C::kOffBlo, p2 ? &a.b2lo : &a.b1lo, bar, k0, n0);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    const uint64_t desc0 = make_desc_sw64(smem_u32(stages));
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S;
+      mbar_wait(ready0 + 8 * s, (kb / S) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t a0 = desc0 + (uint64_t)(s * (C::kStage >> 4));
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t a_hi = a0 + (uint64_t)(ks * 2);
+          const uint64_t b_hi = a_hi + (uint64_t)(C::kOffB >> 4);
+          const uint32_t acc = (kb | ks) ? 1u : 0u;
+          if (X3) {
+            umma_tf32(tmem_base, a_hi + (uint64_t)(C::kOffAlo >> 4), b_hi, kIdescTf32, acc);
+            umma_tf32(tmem_base, a_hi, a_hi + (uint64_t)(C::kOffBlo >> 4), kIdescTf32, 1u);
+            umma_tf32(tmem_base, a_hi, b_hi, kIdescTf32, 1u);
+          } else {
+            umma_tf32(tmem_base, a_hi, b_hi, kIdescTf32, acc);
+          }
+        }
+        umma_commit(empty0 + 8 * s);
+        if (kb + 1 == nkb) umma_commit(accfull);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+
+// ---- prepare: positive weights and all operand copies, split into tf32 hi / lo ------------------------------------------------
+struct WtLayout {
+  size_t P0hi, P0lo, P0Thi, P0Tlo, A0hi, A0lo, A1hi, A1lo, A0Thi, A0Tlo, A1Thi, A1Tlo, P1, g1b, part, end;
+  int mt, nt;
+};
+static inline size_t wt_up(size_t x) { return (x + 63) / 64 * 64; }
+static WtLayout wt_layout(int B, int d, int H) {
+  WtLayout L;
+  size_t o = 0;
+  const size_t HH = wt_up((size_t)H * H), dH = wt_up((size_t)d * H);
+  L.mt = (B + 127) / 128; L.nt = (H + 255) / 256;
+  L.P0hi = o; o += HH; L.P0lo = o; o += HH; L.P0Thi = o; o += HH; L.P0Tlo = o; o += HH;
+  L.A0hi = o; o += dH; L.A0lo = o; o += dH; L.A1hi = o; o += dH; L.A1lo = o; o += dH;
+  L.A0Thi = o; o += dH; L.A0Tlo = o; o += dH; L.A1Thi = o; o += dH; L.A1Tlo = o; o += dH;
+  L.P1 = o; o += wt_up(H);
+  L.g1b = o; o += wt_up((size_t)B * H);
+  L.part = o; o += wt_up((size_t)B * L.nt * 2);
+  L.end = o;
+  return L;
+}
+__device__ __forceinline__ void split_store(float x, float* hi, float* lo, size_t i) {
+  const float h = rn_tf32_masked(x);
+  hi[i] = h; lo[i] = rn_tf32_masked(x - h);
+}
+__global__ void wide_tc_prepare_kernel(const float* __restrict__ W0, const float* __restrict__ W1, const float* __restrict__ A0w,
+                                       const float* __restrict__ A1w, int d, int H, int mode, float* __restrict__ ws, WtLayout L) {
+  const size_t HH = (size_t)H * H, dH = (size_t)d * H, tot = HH + H + dH, gstride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gstride) {
+    if (i < HH) {
+      const float w = W0[i];
+      const float p = (mode == B200VAE_WEIGHT_EXP) ? expf(w) : fmaxf(w, kClampMin);
+      const size_t n = i / H, k = i - n * H;
+      split_store(p, ws + L.P0hi, ws + L.P0lo, i);
+      split_store(p, ws + L.P0Thi, ws + L.P0Tlo, k * H + n);
+    } else if (i < HH + H) {
+      const float w = W1[i - HH];
+      ws[L.P1 + i - HH] = (mode == B200VAE_WEIGHT_EXP) ? expf(w) : fmaxf(w, kClampMin);
+    } else {
+      const size_t j = i - HH - H, n = j / d, c = j - n * d;    // A*w[n][c]
+      split_store(A0w[j], ws + L.A0hi, ws + L.A0lo, j);
+      split_store(A1w[j], ws + L.A1hi, ws + L.A1lo, j);
+      split_store(A0w[j], ws + L.A0Thi, ws + L.A0Tlo, c * H + n);
+      split_store(A1w[j], ws + L.A1Thi, ws + L.A1Tlo, c * H + n);
+    }
+  }
+}
+// h2 = sum_t part[row][t] + A2.z + b2 -> psi, s2   (z is [B, nz])
+__global__ void __launch_bounds__(256)
+wide_tc_row_kernel(const float* __restrict__ part, int npart, const float* __restrict__ z, const float* __restrict__ A2w,
+                   const float* __restrict__ A2b, int B, int nz, float* __restrict__ psi, float* __restrict__ s2) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= B) return;
+  float s = 0.f;
+  for (int c = lane; c < nz; c += 32) s = fmaf(__ldg(A2w + c), z[(size_t)row * nz + c], s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    float h2 = s + A2b[0];
+    for (int t = 0; t < npart; ++t) h2 += part[(size_t)row * npart + t];
+    const float sl = h2 > 0.f ? 1.f : kSlope;
+    if (psi) psi[row] = h2 * sl;
+    s2[row] = sl;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFnW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// 2-D fp32 tensor [rows][K] (row stride ld floats), boxes of 16 x box_rows, 64-byte swizzle, zero fill outside
+static int wt_map(CUtensorMap* m, const float* base, int K, int rows, int ld, int box_rows) {
+  static EncodeTiledFnW fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p)
+      fn = reinterpret_cast<EncodeTiledFnW>(p);
+  }
+  if (!fn) return B200VAE_ECUDA;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_last_cuda_error = 100000 + (int)r; return B200VAE_ECUDA; }
+  return B200VAE_OK;
+}
+
+template <bool X3>
+static int wt_launch(const WtArgs& args, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(wide_tc_gemm_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_done = true;
+  }
+  dim3 grid((args.M + 127) / 128, (args.N + 255) / 256);
+  wide_tc_gemm_kernel<X3><<<grid, kWtThreads, wt_smem_bytes<X3>(), st>>>(args);
+  return check_launch();
+}
+static int wt_run(const WtArgs& args, bool x3, cudaStream_t st) { return x3 ? wt_launch<true>(args, st) : wt_launch<false>(args, st); }
+
+size_t wide_tc_ws_floats(int B, int d, int H) { return wt_layout(B, d, H).end; }
+bool wide_tc_supported(int d, int nz, int H, int precision) {
+  return (precision == B200VAE_PREC_TF32 || precision == B200VAE_PREC_TF32X3) && d % 4 == 0 && nz % 4 == 0 && H % 4 == 0;
+}
+
+// same contract as b200vae_icnn_wide_fwd (h0, mask1, s2 saved for the FP32 backward); g0 is [B,H] scratch
+int wide_tc_fwd(const float* z, int B, int d, int nz, int H, const b200vae_icnn_params* p, int mode, float kappa, float* psi,
+                float* xhat, float* h0, uint8_t* mask1, float* s2, float* g0, float* ws, int precision, cudaStream_t st) {
+  if (!wide_tc_supported(d, nz, H, precision)) return B200VAE_EUNSUP;
+  const bool x3 = precision == B200VAE_PREC_TF32X3;
+  const WtLayout L = wt_layout(B, d, H);
+  wide_tc_prepare_kernel<<<148 * 4, 256, 0, st>>>(p->W0, p->W1, p->A0w, p->A1w, d, H, mode, ws, L);
+  int rc = check_launch();
+  if (rc) return rc;
+  const int kb = kKB;
+  auto nkb = [&](int K) { return (K + kb - 1) / kb; };
+  WtArgs a;
+  memset(&a, 0, sizeof(a));
+  // ---- lin: h0 = z A0^T + b0   (A0w is [H][d]; only its first nz columns meet non-zero inputs)
+  rc = wt_map(&a.a1, z, nz, B, nz, 128);
+  if (!rc) rc = wt_map(&a.b1hi, ws + L.A0hi, nz, H, d, 256);
+  if (!rc) rc = wt_map(&a.b1lo, ws + L.A0lo, nz, H, d, 256);
+  if (rc) return rc;
+  a.a2 = a.a1; a.b2hi = a.b1hi; a.b2lo = a.b1lo;
+  a.nkb1 = nkb(nz); a.nkb2 = 0; a.xf1 = WT_XF_ID; a.M = B; a.N = H; a.epi = WT_EPI_LIN; a.bias = p->A0b; a.out0 = h0;
+  rc = wt_run(a, true, st);     // always 3xTF32: K = nz is tiny, and h0 feeds a square (its error would be amplified)
+  if (rc) return rc;
+  // ---- hid: h1 = x1 P0^T + z A1^T + b1
+  WtArgs b;
+  memset(&b, 0, sizeof(b));
+  rc = wt_map(&b.a1, h0, H, B, H, 128);
+  if (!rc) rc = wt_map(&b.b1hi, ws + L.P0hi, H, H, H, 256);
+  if (!rc) rc = wt_map(&b.b1lo, ws + (x3 ? L.P0lo : L.P0hi), H, H, H, 256);
+  if (!rc) rc = wt_map(&b.b2hi, ws + L.A1hi, nz, H, d, 256);
+  if (!rc) rc = wt_map(&b.b2lo, ws + (x3 ? L.A1lo : L.A1hi), nz, H, d, 256);
+  if (rc) return rc;
+  b.a2 = a.a1;
+  b.nkb1 = nkb(H); b.nkb2 = nkb(nz); b.xf1 = WT_XF_X1; b.M = B; b.N = H; b.epi = WT_EPI_HID; b.bias = p->A1b; b.P1 = ws + L.P1;
+  b.out0 = ws + L.g1b; b.mask = mask1; b.part = ws + L.part; b.npart = L.nt * 2;
+  rc = wt_run(b, x3, st);
+  if (rc) return rc;
+  wide_tc_row_kernel<<<(B + 7) / 8, 256, 0, st>>>(ws + L.part, L.nt * 2, z, p->A2w, p->A2b, B, nz, psi, s2);
+  rc = check_launch();
+  if (rc || !xhat) return rc;
+  // ---- gx1: g0' = (g1b P0) * c0(h0)      B^T[k'][n] = P0[n][k'] = P0T
+  WtArgs c;
+  memset(&c, 0, sizeof(c));
+  rc = wt_map(&c.a1, ws + L.g1b, H, B, H, 128);
+  if (!rc) rc = wt_map(&c.b1hi, ws + L.P0Thi, H, H, H, 256);
+  if (!rc) rc = wt_map(&c.b1lo, ws + (x3 ? L.P0Tlo : L.P0Thi), H, H, H, 256);
+  if (rc) return rc;
+  c.a2 = c.a1; c.b2hi = c.b1hi; c.b2lo = c.b1lo;
+  c.nkb1 = nkb(H); c.nkb2 = 0; c.xf1 = WT_XF_ID; c.M = B; c.N = H; c.epi = WT_EPI_GX1; c.h0 = h0; c.out0 = g0;
+  rc = wt_run(c, x3, st);
+  if (rc) return rc;
+  // ---- out: xhat = s2 (g0' A0 + g1b A1 + A2) + 2 kappa z      B^T[c][n] = A*w[n][c] = A*wT  ([d][H])
+  WtArgs e;
+  memset(&e, 0, sizeof(e));
+  rc = wt_map(&e.a1, g0, H, B, H, 128);
+  if (!rc) rc = wt_map(&e.b1hi, ws + L.A0Thi, H, d, H, 256);
+  if (!rc) rc = wt_map(&e.b1lo, ws + (x3 ? L.A0Tlo : L.A0Thi), H, d, H, 256);
+  if (!rc) rc = wt_map(&e.b2hi, ws + L.A1Thi, H, d, H, 256);
+  if (!rc) rc = wt_map(&e.b2lo, ws + (x3 ? L.A1Tlo : L.A1Thi), H, d, H, 256);
+  if (rc) return rc;
+  e.a2 = c.a1;
+  e.nkb1 = nkb(H); e.nkb2 = nkb(H); e.xf1 = WT_XF_ID; e.M = B; e.N = d; e.epi = WT_EPI_OUT; e.s2 = s2; e.A2w = p->A2w; e.z = z;
+  e.nz = nz; e.kappa2 = 2.f * kappa; e.out0 = xhat;
+  return wt_run(e, x3, st);
+}
+
+}  // namespace b200vae

@@ -168,14 +168,16 @@ def _grads_struct(tensors):
     return g
 
 
-def icnn_wide_fwd(z, params, mode, kappa, want_xhat=True):
+def icnn_wide_fwd(z, params, mode, kappa, want_xhat=True, precision=0):
     """Fused FP32 forward of a wide-input ICNN (csrc/icnn_wide.cu).  Returns (psi [B], xhat [B,d] | None, saved) with
     saved = (h0 [B,H], mask1 [B,H] uint8, s2 [B]) -- what the backward needs besides z."""
     lib = _C.load()
     B, nz = z.shape
     H, d = params[0].shape
     dev = z.device
-    ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, 0), dtype=torch.uint8, device=dev)
+    if precision == _C.PREC_BF16:
+        raise _C.B200VaeError("bf16 is not built; use fp32, tf32x3 or tf32")
+    ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, precision, 0), dtype=torch.uint8, device=dev)
     psi = torch.empty(B, dtype=torch.float32, device=dev)
     h0 = torch.empty(B, H, dtype=torch.float32, device=dev)
     mask1 = torch.empty(B, H, dtype=torch.uint8, device=dev)
@@ -184,7 +186,8 @@ def icnn_wide_fwd(z, params, mode, kappa, want_xhat=True):
     g0 = torch.empty(B, H, dtype=torch.float32, device=dev) if want_xhat else None
     ps = _params_struct(params)
     _C.check(lib.b200vae_icnn_wide_fwd(_ptr(z), B, d, nz, H, C.byref(ps), mode, float(kappa), _ptr(psi), _ptr(xhat), _ptr(h0),
-                                       _ptr(mask1), _ptr(s2), _ptr(g0), _ptr(ws), ws.numel(), _stream()), "icnn_wide_fwd")
+                                       _ptr(mask1), _ptr(s2), _ptr(g0), precision, _ptr(ws), ws.numel(), _stream()),
+             "icnn_wide_fwd")
     return psi, xhat, (h0, mask1, s2)
 
 
@@ -193,8 +196,8 @@ class IcnnBrenierWideFn(torch.autograd.Function):
     MNIST-shaped ICNN(32,512) / ICNN(784,1024) of BASELINE configs[3]).  Here the thin products A.z are dense
     [B,d]x[d,H] contractions as well; the path is a chain of fused FP32 tile-GEMM kernels with generated operands and
     elementwise epilogues (csrc/icnn_wide.cu): the ANALYTIC forward-then-reverse sweep and double-backward of SURVEY
-    Appendix A, no autograd graph, h0 + a byte mask saved instead of ~20 activations.  `precision` is ignored: this path
-    always computes in FP32 (the parity arithmetic).  z may be NARROWER than the ICNN input ([B,nz], nz <= d): it is then
+    Appendix A, no autograd graph, h0 + a byte mask saved instead of ~20 activations.  `precision`: fp32 = those kernels;
+    tf32 / tf32x3 = the forward on tcgen05 (csrc/icnn_wide_tc.cu), the backward stays FP32.  z may be NARROWER than the ICNN input ([B,nz], nz <= d): it is then
     taken as zero-padded to d columns -- the eye(Dx,D) pad of model.py:824 fused away -- and dz is [B,nz]."""
 
     @staticmethod
@@ -204,7 +207,7 @@ class IcnnBrenierWideFn(torch.autograd.Function):
         H, d = params[0].shape
         if z.dim() != 2 or not (1 <= z.shape[1] <= d):
             raise _C.B200VaeError(f"z must be [B,nz] with nz <= {d}, got {tuple(z.shape)}")
-        psi, xhat, saved = icnn_wide_fwd(z, params, mode, kappa, True)
+        psi, xhat, saved = icnn_wide_fwd(z, params, mode, kappa, True, precision)
         if any(ctx.needs_input_grad):
             ctx.save_for_backward(z, *saved, *params)
             ctx.cfg = (float(kappa), mode)
@@ -226,7 +229,7 @@ class IcnnBrenierWideFn(torch.autograd.Function):
         H, d = params[0].shape
         dev = z.device
         need = ctx.needs_input_grad
-        ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, 1), dtype=torch.uint8, device=dev)
+        ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, 0, 1), dtype=torch.uint8, device=dev)
         scratch = torch.empty(4, B, H, dtype=torch.float32, device=dev)          # u0, q1, g0, t0
         grads = [torch.empty_like(p) if n else None for p, n in zip(params, need[4:])]
         dz = torch.empty_like(z) if need[0] else None
