@@ -182,7 +182,8 @@ int b200vae_nn_sqdist_bwd(const float* A, const float* Bp, const int* argA, cons
  * The backward takes v = dL/dxhat only (no psi-gradient) and OVERWRITES every non-null field of `g` and dz.
  * `precision` (forward): FP32 = the tile-GEMM chain above; TF32 / TF32X3 = the same chain on tcgen05 (csrc/icnn_wide_tc.cu:
  * TMA-fed 128x256 tiles, transform + hi/lo split of the A tile in shared memory, accumulators in TMEM) when d, nz, H are
- * multiples of 4, else FP32.  The backward is FP32 in every mode and runs on whatever forward produced h0 / mask1 / s2.
+ * multiples of 4, else FP32.  Backward with TF32 / TF32X3: the sample-stationary GEMMs (u0, w1, gx1, dz) run on the same
+ * tcgen05 kernel, the batch-reduction GEMMs (dA0, dA1, dP0) stay FP32; it works on whatever forward produced h0/mask1/s2.
  * `nz` (1 <= nz <= d): z is [B,nz] and the ICNN input is z ZERO-PADDED to d columns -- the x = x1 B^T step of
  * model.py:824 with B = eye(Dx, D) fused away (nz = D = 32, d = Dx = 784): products with z run over nz columns only,
  * xhat is [B,d], v is [B,d], dz is [B,nz].  nz = d is the plain case. */
@@ -192,7 +193,7 @@ int b200vae_icnn_wide_fwd(const float* z, int B, int d, int nz, int H, const b20
                           void* workspace, size_t ws_bytes, void* stream);
 int b200vae_icnn_wide_bwd(const float* z, const float* v, const float* h0, const uint8_t* mask1, const float* s2, int B,
                           int d, int nz, int H, const b200vae_icnn_params* p, int weight_mode, float kappa,
-                          const b200vae_icnn_grads* g, float* dz, float* u0, float* q1, float* g0, float* t0,
+                          const b200vae_icnn_grads* g, float* dz, float* u0, float* q1, float* g0, float* t0, int precision,
                           void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- peer-memory exchange between the GPUs of one node (the data-parallel exchange steps) ---------------

@@ -120,7 +120,7 @@ def load():
     lib.b200vae_icnn_wide_fwd.argtypes = [vp, i, i, i, i, C.POINTER(IcnnParams), i, f, vp, vp, vp, vp, vp, vp, i, vp, sz, vp]
     lib.b200vae_icnn_wide_bwd.restype = i
     lib.b200vae_icnn_wide_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, C.POINTER(IcnnParams), i, f, C.POINTER(IcnnGrads), vp,
-                                          vp, vp, vp, vp, vp, sz, vp]
+                                          vp, vp, vp, vp, i, vp, sz, vp]
     pp = C.POINTER(PeerStruct)
     lib.b200vae_peer_exchange_bytes.restype = sz
     lib.b200vae_peer_exchange_bytes.argtypes = []

@@ -522,14 +522,18 @@ size_t wide_tc_ws_floats(int B, int d, int H);
 bool wide_tc_supported(int d, int nz, int H, int precision);
 int wide_tc_fwd(const float* z, int B, int d, int nz, int H, const b200vae_icnn_params* p, int mode, float kappa, float* psi,
                 float* xhat, float* h0, uint8_t* mask1, float* s2, float* g0, float* ws, int precision, cudaStream_t st);
+int wide_tc_bwd_rows(const float* v, const float* h0, const uint8_t* mask1, const float* s2, int B, int d, int nz, int H,
+                     const b200vae_icnn_params* p, int mode, float kappa, float* dz, float* u0, float* q1, float* g0, float* t0,
+                     float* dW1, float* db0, float* ws, float* colpart, int precision, cudaStream_t st);
 }
 
 extern "C" size_t b200vae_icnn_wide_workspace_bytes(int B, int d, int H, int precision, int for_backward) {
   if (B <= 0 || d <= 0 || H <= 0) return 0;
   size_t fl = wide_layout(B, d, H, for_backward != 0).end;
-  if (!for_backward && precision != B200VAE_PREC_FP32) {
+  if (precision != B200VAE_PREC_FP32) {
     const size_t t = wide_tc_ws_floats(B, d, H);
-    if (t > fl) fl = t;
+    if (for_backward) fl += t;              // FP32 layout (batch-reduction GEMMs) followed by the tensor-core layout
+    else if (t > fl) fl = t;
   }
   return fl * sizeof(float);
 }
@@ -579,14 +583,15 @@ extern "C" int b200vae_icnn_wide_fwd(const float* z, int B, int d, int nz, int H
 extern "C" int b200vae_icnn_wide_bwd(const float* z, const float* v, const float* h0, const uint8_t* mask1, const float* s2,
                                      int B, int d, int nz, int H, const b200vae_icnn_params* p, int weight_mode, float kappa,
                                      const b200vae_icnn_grads* g, float* dz, float* u0, float* q1, float* g0, float* t0,
-                                     void* workspace, size_t ws_bytes, void* stream) {
+                                     int precision, void* workspace, size_t ws_bytes, void* stream) {
   if (!z || !v || !h0 || !mask1 || !s2 || !wide_params_ok(p) || !u0 || !q1 || !g0 || !t0 || !workspace) return B200VAE_EALIGN;
   if (B <= 0 || d <= 0 || H <= 0 || nz <= 0 || nz > d) return B200VAE_ESHAPE;
   if (weight_mode != B200VAE_WEIGHT_EXP && weight_mode != B200VAE_WEIGHT_CLAMP) return B200VAE_EUNSUP;
+  if (precision < B200VAE_PREC_FP32 || precision > B200VAE_PREC_TF32X3 || precision == B200VAE_PREC_BF16) return B200VAE_EUNSUP;
   const WideWs L = wide_layout(B, d, H, true);
-  if (ws_bytes < L.end * sizeof(float)) return B200VAE_EWS;
+  if (ws_bytes < b200vae_icnn_wide_workspace_bytes(B, d, H, precision, 1)) return B200VAE_EWS;
   if (!aligned16(workspace) || !aligned16(z) || !aligned16(v) || !aligned16(h0) || !aligned16(u0) || !aligned16(q1) ||
-      !aligned16(g0) || !aligned16(t0) || !aligned16(p->A0w) || !aligned16(p->A1w))
+      !aligned16(g0) || !aligned16(t0) || !aligned16(p->A0w) || !aligned16(p->A1w) || (dz && !aligned16(dz)))
     return B200VAE_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
@@ -594,6 +599,16 @@ extern "C" int b200vae_icnn_wide_bwd(const float* z, const float* v, const float
   int rc = wide_prepare(p, d, H, weight_mode, ws, L, st);
   if (rc) return rc;
   const dim3 gH(L.mt, L.nt), gD(L.mt, (d + 127) / 128);
+  static const bool tc_on = [] { const char* e = getenv("B200VAE_WIDE_TC"); return !e || atoi(e) != 0; }();
+  bool rows_done = false;
+  if (precision != B200VAE_PREC_FP32 && tc_on && wide_tc_supported(d, nz, H, precision)) {
+    // sample-stationary GEMMs on tcgen05 (icnn_wide_tc.cu); the batch-reduction GEMMs below stay FP32
+    rc = wide_tc_bwd_rows(v, h0, mask1, s2, B, d, nz, H, p, weight_mode, kappa, dz, u0, q1, g0, t0, g ? g->W1 : nullptr,
+                          g ? g->A0b : nullptr, ws + L.end, ws + L.colpart, precision, st);
+    if (rc == B200VAE_OK) rows_done = true;
+    else if (rc != B200VAE_EUNSUP) return rc;
+  }
+  if (!rows_done) {
   // u0 = v A0^T, q1 = u0 * c0
   wide_lin_kernel<<<gH, kThreads, 0, st>>>(v, ws + L.A0T, nullptr, B, d, H, 1, h0, u0, q1);
   WIDE_CHECK();
@@ -618,6 +633,7 @@ extern "C" int b200vae_icnn_wide_bwd(const float* z, const float* v, const float
                                                                       d, nz, 2.f * kappa, B, d, nz, H, dz);
     WIDE_CHECK();
   }
+  }   // !rows_done
   if (g) {
     if (g->A2w) {
       wide_a2_kernel<<<L.mt, 256, 0, st>>>(v, s2, B, d, ws + L.colpart);

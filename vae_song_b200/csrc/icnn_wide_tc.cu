@@ -27,7 +27,7 @@ constexpr int kWtStages = 4;
 constexpr int kWtATile = 128 * 64, kWtBTile = 256 * 64;
 
 enum { WT_XF_ID = 0, WT_XF_X1 = 1 };
-enum { WT_EPI_LIN = 0, WT_EPI_HID = 1, WT_EPI_GX1 = 2, WT_EPI_OUT = 3 };
+enum { WT_EPI_LIN = 0, WT_EPI_HID = 1, WT_EPI_GX1 = 2, WT_EPI_OUT = 3, WT_EPI_U = 4, WT_EPI_W1 = 5, WT_EPI_GXB = 6, WT_EPI_DZ = 7 };
 
 struct alignas(64) WtArgs {
   CUtensorMap a1, b1hi, b1lo, a2, b2hi, b2lo;
@@ -41,9 +41,14 @@ struct alignas(64) WtArgs {
   int nz;
   float kappa2;
   float* out0;           // LIN: h0, HID: g1b, GX1: g0', OUT: xhat   (row stride N)
-  uint8_t* mask;         // HID
+  uint8_t* mask;         // HID (written); W1 (read)
   float* part;           // HID: [M][npart]
   int npart;
+  // backward epilogues
+  float* out1;           // U: q1, GXB: t0
+  const float* u0;       // GXB
+  const float* v;        // DZ: [M, ldv]
+  int ldv;
 };
 
 template <bool X3>
@@ -124,7 +129,7 @@ wide_tc_gemm_kernel(const __grid_constant__ WtArgs a) {
     mbar_wait_parked(accfull, 0, 1000);
     tc_fence_after();
     float rowsum = 0.f;
-    const float s2r = (a.epi == WT_EPI_OUT && rin) ? a.s2[row] : 0.f;
+    const float s2r = ((a.epi == WT_EPI_OUT || a.epi == WT_EPI_W1 || a.epi == WT_EPI_GXB) && rin) ? a.s2[row] : 0.f;
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
       uint32_t r[32];
@@ -172,6 +177,55 @@ wide_tc_gemm_kernel(const __grid_constant__ WtArgs a) {
             g[e] = __uint_as_float(r[j + e]) * (2.f * h[e] * sl * sl);
           }
           *reinterpret_cast<float4*>(orow + j) = make_float4(g[0], g[1], g[2], g[3]);
+        }
+      } else if (a.epi == WT_EPI_U) {          // u0 = acc, q1 = u0 * 2 a0 s0
+        const float* hrow = a.h0 + (size_t)row * a.N + c0;
+        float* qrow = a.out1 + (size_t)row * a.N + c0;
+        for (int j = 0; j < nv; j += 4) {
+          const float4 hv = *reinterpret_cast<const float4*>(hrow + j);
+          const float h[4] = {hv.x, hv.y, hv.z, hv.w};
+          float u[4], q[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float sl = h[e] > 0.f ? 1.f : kSlope;
+            u[e] = __uint_as_float(r[j + e]);
+            q[e] = u[e] * (2.f * h[e] * sl * sl);
+          }
+          *reinterpret_cast<float4*>(orow + j) = make_float4(u[0], u[1], u[2], u[3]);
+          *reinterpret_cast<float4*>(qrow + j) = make_float4(q[0], q[1], q[2], q[3]);
+        }
+      } else if (a.epi == WT_EPI_W1) {         // e1 = s2 s1 w1 (its column sums are dP1)
+        const uint8_t* mrow = a.mask + (size_t)row * a.N + c0;
+        for (int j = 0; j < nv; j += 4) {
+          const uint32_t mb = *reinterpret_cast<const uint32_t*>(mrow + j);
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = __uint_as_float(r[j + e]) * (((mb >> (8 * e)) & 0xffu) ? s2r : kSlope * s2r);
+          *reinterpret_cast<float4*>(orow + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      } else if (a.epi == WT_EPI_GXB) {        // gx1 = s2 acc;  g0 = gx1 2 a0 s0;  t0 = u0 2 gx1 s0^2
+        const float* hrow = a.h0 + (size_t)row * a.N + c0;
+        const float* urow = a.u0 + (size_t)row * a.N + c0;
+        float* trow = a.out1 + (size_t)row * a.N + c0;
+        for (int j = 0; j < nv; j += 4) {
+          const float4 hv = *reinterpret_cast<const float4*>(hrow + j);
+          const float4 uv = *reinterpret_cast<const float4*>(urow + j);
+          const float h[4] = {hv.x, hv.y, hv.z, hv.w}, u[4] = {uv.x, uv.y, uv.z, uv.w};
+          float g[4], t[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float sl = h[e] > 0.f ? 1.f : kSlope, gx = s2r * __uint_as_float(r[j + e]);
+            g[e] = gx * (2.f * h[e] * sl * sl);
+            t[e] = u[e] * (2.f * gx) * sl * sl;
+          }
+          *reinterpret_cast<float4*>(orow + j) = make_float4(g[0], g[1], g[2], g[3]);
+          *reinterpret_cast<float4*>(trow + j) = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      } else if (a.epi == WT_EPI_DZ) {         // dz = acc + 2 kappa v
+        for (int j = 0; j < nv; j += 4) {
+          const float4 vv = *reinterpret_cast<const float4*>(a.v + (size_t)row * a.ldv + c0 + j);
+          *reinterpret_cast<float4*>(orow + j) = make_float4(fmaf(a.kappa2, vv.x, __uint_as_float(r[j])), fmaf(a.kappa2, vv.y, __uint_as_float(r[j + 1])),
+                                                             fmaf(a.kappa2, vv.z, __uint_as_float(r[j + 2])), fmaf(a.kappa2, vv.w, __uint_as_float(r[j + 3])));
         }
       } else {   // WT_EPI_OUT
         for (int j = 0; j < nv; j += 4) {
@@ -304,6 +358,33 @@ wide_tc_row_kernel(const float* __restrict__ part, int npart, const float* __res
   }
 }
 
+// g1b[b][n] = P1[n] * sigma'(h1[b][n]) from the saved byte mask (A operand of the backward's gx1 GEMM)
+__global__ void wide_tc_g1b_kernel(const uint8_t* __restrict__ mask, const float* __restrict__ P1, size_t n, int H,
+                                   float* __restrict__ g1b) {
+  const size_t gstride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride)
+    g1b[i] = P1[i % H] * (mask[i] ? 1.f : kSlope);
+}
+// ordered column sums of a [B][H] matrix: colpart[mt][H] over 128-row blocks, then a fixed-order finalize (+ chain)
+__global__ void __launch_bounds__(256)
+wide_tc_colsum_kernel(const float* __restrict__ x, int B, int H, float* __restrict__ colpart) {
+  const int c = blockIdx.y * 256 + threadIdx.x, r0 = blockIdx.x * 128, r1 = min(B, r0 + 128);
+  if (c >= H) return;
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += x[(size_t)r * H + c];
+  colpart[(size_t)blockIdx.x * H + c] = s;
+}
+__global__ void wide_tc_colfin_kernel(const float* __restrict__ colpart, int mt, int H, int chain, const float* __restrict__ P,
+                                      const float* __restrict__ W, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  float s = 0.f;
+  for (int t = 0; t < mt; ++t) s += colpart[(size_t)t * H + c];
+  if (chain == 1) s *= P[c];
+  else if (chain == 2) s = W[c] >= kClampMin ? s : 0.f;
+  out[c] = s;
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFnW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -409,6 +490,92 @@ int wide_tc_fwd(const float* z, int B, int d, int nz, int H, const b200vae_icnn_
   e.a2 = c.a1;
   e.nkb1 = nkb(H); e.nkb2 = nkb(H); e.xf1 = WT_XF_ID; e.M = B; e.N = d; e.epi = WT_EPI_OUT; e.s2 = s2; e.A2w = p->A2w; e.z = z;
   e.nz = nz; e.kappa2 = 2.f * kappa; e.out0 = xhat;
+  return wt_run(e, x3, st);
+}
+
+// Sample-stationary part of the backward on tcgen05: u0, q1 -> w1 -> dP1;  gx1 -> g0, t0 -> db0;  dz.
+// Leaves u0, q1, g0, t0 [B,H] filled for the batch-reduction GEMMs (dA0, dA1, dP0: FP32 kernels of icnn_wide.cu).
+// `colpart`: [ceil(B/128)][H] floats of scratch.  dW1 / db0 may be null.
+int wide_tc_bwd_rows(const float* v, const float* h0, const uint8_t* mask1, const float* s2, int B, int d, int nz, int H,
+                     const b200vae_icnn_params* p, int mode, float kappa, float* dz, float* u0, float* q1, float* g0, float* t0,
+                     float* dW1, float* db0, float* ws, float* colpart, int precision, cudaStream_t st) {
+  if (!wide_tc_supported(d, nz, H, precision)) return B200VAE_EUNSUP;
+  const bool x3 = precision == B200VAE_PREC_TF32X3;
+  const WtLayout L = wt_layout(B, d, H);
+  wide_tc_prepare_kernel<<<148 * 4, 256, 0, st>>>(p->W0, p->W1, p->A0w, p->A1w, d, H, mode, ws, L);
+  int rc = check_launch();
+  if (rc) return rc;
+  wide_tc_g1b_kernel<<<148 * 8, 256, 0, st>>>(mask1, ws + L.P1, (size_t)B * H, H, ws + L.g1b);
+  rc = check_launch();
+  if (rc) return rc;
+  auto nkb = [&](int K) { return (K + kKB - 1) / kKB; };
+  const int mt = (B + 127) / 128;
+  const dim3 cgrid(mt, (H + 255) / 256);
+  const int chain = mode == B200VAE_WEIGHT_EXP ? 1 : 2;
+  // ---- u0 = v A0^T, q1 = u0 * c0
+  WtArgs a;
+  memset(&a, 0, sizeof(a));
+  rc = wt_map(&a.a1, v, d, B, d, 128);
+  if (!rc) rc = wt_map(&a.b1hi, ws + L.A0hi, d, H, d, 256);
+  if (!rc) rc = wt_map(&a.b1lo, ws + (x3 ? L.A0lo : L.A0hi), d, H, d, 256);
+  if (rc) return rc;
+  a.a2 = a.a1; a.b2hi = a.b1hi; a.b2lo = a.b1lo;
+  a.nkb1 = nkb(d); a.nkb2 = 0; a.xf1 = WT_XF_ID; a.M = B; a.N = H; a.epi = WT_EPI_U; a.h0 = h0; a.out0 = u0; a.out1 = q1;
+  rc = wt_run(a, x3, st);
+  if (rc) return rc;
+  // ---- e1 = s2 s1 (q1 P0^T + v A1^T)  -> column sums = dP1   (e1 parked in the g0 buffer)
+  WtArgs b;
+  memset(&b, 0, sizeof(b));
+  rc = wt_map(&b.a1, q1, H, B, H, 128);
+  if (!rc) rc = wt_map(&b.b1hi, ws + L.P0hi, H, H, H, 256);
+  if (!rc) rc = wt_map(&b.b1lo, ws + (x3 ? L.P0lo : L.P0hi), H, H, H, 256);
+  if (!rc) rc = wt_map(&b.b2hi, ws + L.A1hi, d, H, d, 256);
+  if (!rc) rc = wt_map(&b.b2lo, ws + (x3 ? L.A1lo : L.A1hi), d, H, d, 256);
+  if (rc) return rc;
+  b.a2 = a.a1;
+  b.nkb1 = nkb(H); b.nkb2 = nkb(d); b.xf1 = WT_XF_ID; b.M = B; b.N = H; b.epi = WT_EPI_W1; b.s2 = s2;
+  b.mask = const_cast<uint8_t*>(mask1); b.out0 = g0;
+  rc = wt_run(b, x3, st);
+  if (rc) return rc;
+  if (dW1) {
+    wide_tc_colsum_kernel<<<cgrid, 256, 0, st>>>(g0, B, H, colpart);
+    rc = check_launch();
+    if (rc) return rc;
+    wide_tc_colfin_kernel<<<(H + 255) / 256, 256, 0, st>>>(colpart, mt, H, chain, ws + L.P1, p->W1, dW1);
+    rc = check_launch();
+    if (rc) return rc;
+  }
+  // ---- gx1 = s2 (g1b P0) -> g0, t0
+  WtArgs c;
+  memset(&c, 0, sizeof(c));
+  rc = wt_map(&c.a1, ws + L.g1b, H, B, H, 128);
+  if (!rc) rc = wt_map(&c.b1hi, ws + L.P0Thi, H, H, H, 256);
+  if (!rc) rc = wt_map(&c.b1lo, ws + (x3 ? L.P0Tlo : L.P0Thi), H, H, H, 256);
+  if (rc) return rc;
+  c.a2 = c.a1; c.b2hi = c.b1hi; c.b2lo = c.b1lo;
+  c.nkb1 = nkb(H); c.nkb2 = 0; c.xf1 = WT_XF_ID; c.M = B; c.N = H; c.epi = WT_EPI_GXB; c.h0 = h0; c.u0 = u0; c.s2 = s2;
+  c.out0 = g0; c.out1 = t0;
+  rc = wt_run(c, x3, st);
+  if (rc) return rc;
+  if (db0) {
+    wide_tc_colsum_kernel<<<cgrid, 256, 0, st>>>(t0, B, H, colpart);
+    rc = check_launch();
+    if (rc) return rc;
+    wide_tc_colfin_kernel<<<(H + 255) / 256, 256, 0, st>>>(colpart, mt, H, 0, nullptr, nullptr, db0);
+    rc = check_launch();
+    if (rc) return rc;
+  }
+  if (!dz) return B200VAE_OK;
+  // ---- dz [B,nz] = t0 A0[:, :nz] + 2 kappa v[:, :nz]
+  WtArgs e;
+  memset(&e, 0, sizeof(e));
+  rc = wt_map(&e.a1, t0, H, B, H, 128);
+  if (!rc) rc = wt_map(&e.b1hi, ws + L.A0Thi, H, nz, H, 256);
+  if (!rc) rc = wt_map(&e.b1lo, ws + (x3 ? L.A0Tlo : L.A0Thi), H, nz, H, 256);
+  if (rc) return rc;
+  e.a2 = e.a1; e.b2hi = e.b1hi; e.b2lo = e.b1lo;
+  e.nkb1 = nkb(H); e.nkb2 = 0; e.xf1 = WT_XF_ID; e.M = B; e.N = nz; e.epi = WT_EPI_DZ; e.v = v; e.ldv = d; e.kappa2 = 2.f * kappa;
+  e.out0 = dz;
   return wt_run(e, x3, st);
 }
 

@@ -197,7 +197,8 @@ class IcnnBrenierWideFn(torch.autograd.Function):
     [B,d]x[d,H] contractions as well; the path is a chain of fused FP32 tile-GEMM kernels with generated operands and
     elementwise epilogues (csrc/icnn_wide.cu): the ANALYTIC forward-then-reverse sweep and double-backward of SURVEY
     Appendix A, no autograd graph, h0 + a byte mask saved instead of ~20 activations.  `precision`: fp32 = those kernels;
-    tf32 / tf32x3 = the forward on tcgen05 (csrc/icnn_wide_tc.cu), the backward stays FP32.  z may be NARROWER than the ICNN input ([B,nz], nz <= d): it is then
+    tf32 / tf32x3 = forward and the sample-stationary GEMMs of the backward on tcgen05 (csrc/icnn_wide_tc.cu), the
+    batch-reduction GEMMs (dA0, dA1, dP0) stay FP32.  z may be NARROWER than the ICNN input ([B,nz], nz <= d): it is then
     taken as zero-padded to d columns -- the eye(Dx,D) pad of model.py:824 fused away -- and dz is [B,nz]."""
 
     @staticmethod
@@ -210,7 +211,7 @@ class IcnnBrenierWideFn(torch.autograd.Function):
         psi, xhat, saved = icnn_wide_fwd(z, params, mode, kappa, True, precision)
         if any(ctx.needs_input_grad):
             ctx.save_for_backward(z, *saved, *params)
-            ctx.cfg = (float(kappa), mode)
+            ctx.cfg = (float(kappa), mode, precision)
         ctx.set_materialize_grads(False)
         return psi, xhat
 
@@ -218,7 +219,7 @@ class IcnnBrenierWideFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, gpsi, v):
         z, h0, mask1, s2, *params = ctx.saved_tensors
-        kappa, mode = ctx.cfg
+        kappa, mode, precision = ctx.cfg
         if gpsi is None and v is None:
             return (None,) * 12
         if gpsi is not None:                       # first-order backward of psi (Appendix A, last line)
@@ -229,14 +230,14 @@ class IcnnBrenierWideFn(torch.autograd.Function):
         H, d = params[0].shape
         dev = z.device
         need = ctx.needs_input_grad
-        ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, 0, 1), dtype=torch.uint8, device=dev)
+        ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, precision, 1), dtype=torch.uint8, device=dev)
         scratch = torch.empty(4, B, H, dtype=torch.float32, device=dev)          # u0, q1, g0, t0
         grads = [torch.empty_like(p) if n else None for p, n in zip(params, need[4:])]
         dz = torch.empty_like(z) if need[0] else None
         ps, gs = _params_struct(params), _grads_struct(grads)
         _C.check(lib.b200vae_icnn_wide_bwd(_ptr(z), _ptr(v), _ptr(h0), _ptr(mask1), _ptr(s2), B, d, nz, H, C.byref(ps), mode,
                                            float(kappa), C.byref(gs), _ptr(dz), _ptr(scratch[0]), _ptr(scratch[1]),
-                                           _ptr(scratch[2]), _ptr(scratch[3]), _ptr(ws), ws.numel(), _stream()),
+                                           _ptr(scratch[2]), _ptr(scratch[3]), precision, _ptr(ws), ws.numel(), _stream()),
                  "icnn_wide_bwd")
         return (dz, None, None, None, *grads)
 
