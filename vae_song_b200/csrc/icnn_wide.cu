@@ -525,6 +525,10 @@ int wide_tc_fwd(const float* z, int B, int d, int nz, int H, const b200vae_icnn_
 int wide_tc_bwd_rows(const float* v, const float* h0, const uint8_t* mask1, const float* s2, int B, int d, int nz, int H,
                      const b200vae_icnn_params* p, int mode, float kappa, float* dz, float* u0, float* q1, float* g0, float* t0,
                      float* dW1, float* db0, float* ws, float* colpart, int precision, cudaStream_t st);
+size_t wide_tc_tn_ws_floats(int B, int d, int H);
+int wide_tc_bwd_tn(const float* z, const float* v, const uint8_t* mask1, const float* s2, const float* q1, const float* g0,
+                   const float* t0, int B, int d, int nz, int H, const b200vae_icnn_params* p, int mode, const float* P1,
+                   float* dA0w, float* dA1w, float* dW0, float* ws, int precision, cudaStream_t st);
 }
 
 extern "C" size_t b200vae_icnn_wide_workspace_bytes(int B, int d, int H, int precision, int for_backward) {
@@ -532,7 +536,7 @@ extern "C" size_t b200vae_icnn_wide_workspace_bytes(int B, int d, int H, int pre
   size_t fl = wide_layout(B, d, H, for_backward != 0).end;
   if (precision != B200VAE_PREC_FP32) {
     const size_t t = wide_tc_ws_floats(B, d, H);
-    if (for_backward) fl += t;              // FP32 layout (batch-reduction GEMMs) followed by the tensor-core layout
+    if (for_backward) fl += t + wide_tc_tn_ws_floats(B, d, H);   // FP32 layout, then the tensor-core layouts (rows, batch-reduction)
     else if (t > fl) fl = t;
   }
   return fl * sizeof(float);
@@ -643,6 +647,14 @@ extern "C" int b200vae_icnn_wide_bwd(const float* z, const float* v, const float
     }
     if (g->A1b) { wide_zero_kernel<<<(H + 255) / 256, 256, 0, st>>>(g->A1b, H); WIDE_CHECK(); }   // sigma'' = 0: exact zeros
     if (g->A2b) { wide_zero_kernel<<<1, 32, 0, st>>>(g->A2b, 1); WIDE_CHECK(); }
+    bool tn_done = false;
+    if (rows_done) {                 // batch-reduction GEMMs on tcgen05 as well (transposed operands, split-K slabs)
+      rc = wide_tc_bwd_tn(z, v, mask1, s2, q1, g0, t0, B, d, nz, H, p, weight_mode, ws + L.P1, g->A0w, g->A1w, g->W0,
+                          ws + L.end + wide_tc_ws_floats(B, d, H), precision, st);
+      if (rc == B200VAE_OK) tn_done = true;
+      else if (rc != B200VAE_EUNSUP) return rc;
+    }
+    if (tn_done) return B200VAE_OK;
     TnArgs t;
     t.mask1 = mask1; t.s2 = s2; t.P1 = ws + L.P1; t.B = B; t.Mdim = H;
     const int splits = L.splits;

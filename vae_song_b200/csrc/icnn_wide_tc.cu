@@ -27,7 +27,7 @@ constexpr int kWtStages = 4;
 constexpr int kWtATile = 128 * 64, kWtBTile = 256 * 64;
 
 enum { WT_XF_ID = 0, WT_XF_X1 = 1 };
-enum { WT_EPI_LIN = 0, WT_EPI_HID = 1, WT_EPI_GX1 = 2, WT_EPI_OUT = 3, WT_EPI_U = 4, WT_EPI_W1 = 5, WT_EPI_GXB = 6, WT_EPI_DZ = 7 };
+enum { WT_EPI_LIN = 0, WT_EPI_HID = 1, WT_EPI_GX1 = 2, WT_EPI_OUT = 3, WT_EPI_U = 4, WT_EPI_W1 = 5, WT_EPI_GXB = 6, WT_EPI_DZ = 7, WT_EPI_SLAB = 8 };
 
 struct alignas(64) WtArgs {
   CUtensorMap a1, b1hi, b1lo, a2, b2hi, b2lo;
@@ -49,6 +49,7 @@ struct alignas(64) WtArgs {
   const float* u0;       // GXB
   const float* v;        // DZ: [M, ldv]
   int ldv;
+  int kb_per_split;      // > 0: split-K over blockIdx.z (both phases share the K range); SLAB epilogue stores partial tiles
 };
 
 template <bool X3>
@@ -75,6 +76,7 @@ wide_tc_gemm_kernel(const __grid_constant__ WtArgs a) {
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 256;
   const int nkb = a.nkb1 + a.nkb2;
+  const int kb_off = a.kb_per_split > 0 ? (int)blockIdx.z * a.kb_per_split : 0;   // split-K: first K-block of this CTA
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(ready0 + 8 * s, 8); mbar_init(empty0 + 8 * s, 1); }
@@ -139,7 +141,11 @@ wide_tc_gemm_kernel(const __grid_constant__ WtArgs a) {
       if (!rin || c0 >= a.N) continue;
       const int nv = min(32, a.N - c0);                    // N % 4 == 0: whole float4 groups
       float* orow = a.out0 + (size_t)row * a.N + c0;
-      if (a.epi == WT_EPI_LIN) {
+      if (a.epi == WT_EPI_SLAB) {              // split-K partial tile -> slab[blockIdx.z]
+        float* srow = orow + (size_t)blockIdx.z * a.M * a.N;
+        for (int j = 0; j < nv; j += 4)
+          *reinterpret_cast<uint4*>(srow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      } else if (a.epi == WT_EPI_LIN) {
         for (int j = 0; j < nv; j += 4) {
           const float4 b = *reinterpret_cast<const float4*>(a.bias + c0 + j);
           *reinterpret_cast<float4*>(orow + j) = make_float4(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y,
@@ -248,7 +254,7 @@ wide_tc_gemm_kernel(const __grid_constant__ WtArgs a) {
       mbar_wait(empty0 + 8 * s, ((kb / S) & 1) ^ 1);
       if (elect_one()) {
         const bool p2 = kb >= a.nkb1;
-        const int k0 = (p2 ? kb - a.nkb1 : kb) * kKB;
+        const int k0 = (kb_off + (p2 ? kb - a.nkb1 : kb)) * kKB;
         const uint32_t bar = full0 + 8 * s;
         const uint32_t dst = smem_u32(stages + s * C::kStage);
         mbar_arrive_expect_tx(bar, kWtATile + kWtBTile * (X3 ? 2 : 1));
@@ -385,6 +391,49 @@ __global__ void wide_tc_colfin_kernel(const float* __restrict__ colpart, int mt,
   out[c] = s;
 }
 
+// Transpose [B][C] -> [C][ldo] (ldo >= B) so that the BATCH index becomes the contiguous K dimension of the batch-reduction
+// GEMMs.  mode 0: plain; mode 1: g1 = s2[b]*P1[c]*sigma'(h1) from the byte mask.  `lo` != null: also the tf32 residual.
+__global__ void __launch_bounds__(256)
+wide_tc_transpose_kernel(const float* __restrict__ src, const uint8_t* __restrict__ mask, const float* __restrict__ s2,
+                         const float* __restrict__ P1, int mode, int B, int Ccols, int ldo, float* __restrict__ hi,
+                         float* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int b0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int b = b0 + r, c = c0 + tx;
+    float x = 0.f;
+    if (b < B && c < Ccols) {
+      const size_t i = (size_t)b * Ccols + c;
+      x = mode == 1 ? s2[b] * P1[c] * (mask[i] ? 1.f : kSlope) : src[i];
+    }
+    tile[r][tx] = x;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, b = b0 + tx;
+    if (c < Ccols && b < B) {
+      const float x = tile[tx][r];
+      const size_t o = (size_t)c * ldo + b;
+      if (lo) { const float h = rn_tf32_masked(x); hi[o] = h; lo[o] = rn_tf32_masked(x - h); }
+      else hi[o] = x;
+    }
+  }
+}
+// out[i] = chain( sum_s slabs[s][i] ):  chain 0 none, 1 * exp(W) (dW = dP * P), 2 * [W >= 1e-2]
+__global__ void wide_tc_slabfin_kernel(const float* __restrict__ slabs, int splits, size_t n, int chain, const float* __restrict__ W,
+                                       float* __restrict__ out) {
+  const size_t gstride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += slabs[(size_t)k * n + i];
+    if (chain == 1) s *= expf(W[i]);
+    else if (chain == 2) s = W[i] >= kClampMin ? s : 0.f;
+    out[i] = s;
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFnW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -411,17 +460,19 @@ static int wt_map(CUtensorMap* m, const float* base, int K, int rows, int ld, in
 }
 
 template <bool X3>
-static int wt_launch(const WtArgs& args, cudaStream_t st) {
+static int wt_launch(const WtArgs& args, int splits, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(wide_tc_gemm_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_done = true;
   }
-  dim3 grid((args.M + 127) / 128, (args.N + 255) / 256);
+  dim3 grid((args.M + 127) / 128, (args.N + 255) / 256, splits);
   wide_tc_gemm_kernel<X3><<<grid, kWtThreads, wt_smem_bytes<X3>(), st>>>(args);
   return check_launch();
 }
-static int wt_run(const WtArgs& args, bool x3, cudaStream_t st) { return x3 ? wt_launch<true>(args, st) : wt_launch<false>(args, st); }
+static int wt_run(const WtArgs& args, bool x3, cudaStream_t st, int splits = 1) {
+  return x3 ? wt_launch<true>(args, splits, st) : wt_launch<false>(args, splits, st);
+}
 
 size_t wide_tc_ws_floats(int B, int d, int H) { return wt_layout(B, d, H).end; }
 bool wide_tc_supported(int d, int nz, int H, int precision) {
@@ -577,6 +628,87 @@ int wide_tc_bwd_rows(const float* v, const float* h0, const uint8_t* mask1, cons
   e.nkb1 = nkb(H); e.nkb2 = 0; e.xf1 = WT_XF_ID; e.M = B; e.N = nz; e.epi = WT_EPI_DZ; e.v = v; e.ldv = d; e.kappa2 = 2.f * kappa;
   e.out0 = dz;
   return wt_run(e, x3, st);
+}
+
+// Batch-reduction GEMMs of the backward on tcgen05:  dA0 = g0^T v + t0^T z,  dA1 = g1^T v,  dP0 = g1^T q1 (-> dW0).
+// The operands are transposed first (batch -> contiguous K; B operands split hi/lo on the way), then each product is the
+// generic GEMM with M = H, K = B, split over K into `splits` slabs that are summed in fixed order.
+struct WtTnLayout { size_t g0T, t0T, g1T, vThi, vTlo, zThi, zTlo, q1Thi, q1Tlo, slabs, end; int ldb, splits; };
+static WtTnLayout wt_tn_layout(int B, int d, int nz, int H) {
+  WtTnLayout T;
+  T.ldb = (B + 3) / 4 * 4;
+  const size_t HB = wt_up((size_t)H * T.ldb), dB = wt_up((size_t)d * T.ldb), zB = wt_up((size_t)nz * T.ldb);
+  const int tiles = ((H + 127) / 128) * ((H + 255) / 256);
+  int s = (148 + tiles - 1) / tiles, maxs = (B + 255) / 256;
+  T.splits = s < maxs ? s : maxs;
+  if (T.splits < 1) T.splits = 1;
+  if (T.splits > 16) T.splits = 16;
+  size_t o = 0;
+  T.g0T = o; o += HB; T.t0T = o; o += HB; T.g1T = o; o += HB;
+  T.vThi = o; o += dB; T.vTlo = o; o += dB; T.zThi = o; o += zB; T.zTlo = o; o += zB; T.q1Thi = o; o += HB; T.q1Tlo = o; o += HB;
+  T.slabs = o; o += wt_up((size_t)T.splits * H * (H > d ? H : d));
+  T.end = o;
+  return T;
+}
+size_t wide_tc_tn_ws_floats(int B, int d, int H) { return wt_tn_layout(B, d, d, H).end; }
+
+int wide_tc_bwd_tn(const float* z, const float* v, const uint8_t* mask1, const float* s2, const float* q1, const float* g0,
+                   const float* t0, int B, int d, int nz, int H, const b200vae_icnn_params* p, int mode, const float* P1,
+                   float* dA0w, float* dA1w, float* dW0, float* ws, int precision, cudaStream_t st) {
+  if (!wide_tc_supported(d, nz, H, precision)) return B200VAE_EUNSUP;
+  const bool x3 = precision == B200VAE_PREC_TF32X3;
+  const WtTnLayout T = wt_tn_layout(B, d, nz, H);
+  const int ldb = T.ldb;
+  int rc;
+  auto transpose = [&](const float* src, int md, int C, float* hi, float* lo) {
+    dim3 grid((B + 31) / 32, (C + 31) / 32);
+    wide_tc_transpose_kernel<<<grid, 256, 0, st>>>(src, mask1, s2, P1, md, B, C, ldb, hi, lo);
+    return check_launch();
+  };
+  const int nkb_all = (B + kKB - 1) / kKB, per = (nkb_all + T.splits - 1) / T.splits;
+  const int chain = mode == B200VAE_WEIGHT_EXP ? 1 : 2;
+  auto gemm = [&](const float* At, const float* Bhi, const float* Blo, int N, const float* At2, const float* B2hi,
+                  const float* B2lo, int N2) {
+    WtArgs a;
+    memset(&a, 0, sizeof(a));
+    int r = wt_map(&a.a1, At, B, H, ldb, 128);
+    if (!r) r = wt_map(&a.b1hi, Bhi, B, N, ldb, 256);
+    if (!r) r = wt_map(&a.b1lo, x3 ? Blo : Bhi, B, N, ldb, 256);
+    if (!r && At2) {
+      r = wt_map(&a.a2, At2, B, H, ldb, 128);
+      if (!r) r = wt_map(&a.b2hi, B2hi, B, N2, ldb, 256);
+      if (!r) r = wt_map(&a.b2lo, x3 ? B2lo : B2hi, B, N2, ldb, 256);
+    } else if (!r) {
+      a.a2 = a.a1; a.b2hi = a.b1hi; a.b2lo = a.b1lo;
+    }
+    if (r) return r;
+    a.nkb1 = per; a.nkb2 = At2 ? per : 0; a.xf1 = WT_XF_ID; a.M = H; a.N = N; a.epi = WT_EPI_SLAB; a.out0 = ws + T.slabs;
+    a.kb_per_split = per;
+    return wt_run(a, x3, st, T.splits);
+  };
+  auto finalize = [&](size_t n, int ch, const float* W, float* out) {
+    wide_tc_slabfin_kernel<<<148 * 4, 256, 0, st>>>(ws + T.slabs, T.splits, n, ch, W, out);
+    return check_launch();
+  };
+  if (dA0w || dA1w) { rc = transpose(v, 0, d, ws + T.vThi, x3 ? ws + T.vTlo : nullptr); if (rc) return rc; }
+  if (dA1w || dW0) { rc = transpose(nullptr, 1, H, ws + T.g1T, nullptr); if (rc) return rc; }
+  if (dA0w) {
+    rc = transpose(g0, 0, H, ws + T.g0T, nullptr); if (rc) return rc;
+    rc = transpose(t0, 0, H, ws + T.t0T, nullptr); if (rc) return rc;
+    rc = transpose(z, 0, nz, ws + T.zThi, x3 ? ws + T.zTlo : nullptr); if (rc) return rc;
+    rc = gemm(ws + T.g0T, ws + T.vThi, ws + T.vTlo, d, ws + T.t0T, ws + T.zThi, ws + T.zTlo, nz); if (rc) return rc;
+    rc = finalize((size_t)H * d, 0, nullptr, dA0w); if (rc) return rc;
+  }
+  if (dA1w) {
+    rc = gemm(ws + T.g1T, ws + T.vThi, ws + T.vTlo, d, nullptr, nullptr, nullptr, 0); if (rc) return rc;
+    rc = finalize((size_t)H * d, 0, nullptr, dA1w); if (rc) return rc;
+  }
+  if (dW0) {
+    rc = transpose(q1, 0, H, ws + T.q1Thi, x3 ? ws + T.q1Tlo : nullptr); if (rc) return rc;
+    rc = gemm(ws + T.g1T, ws + T.q1Thi, ws + T.q1Tlo, H, nullptr, nullptr, nullptr, 0); if (rc) return rc;
+    rc = finalize((size_t)H * H, chain, p->W0, dW0); if (rc) return rc;
+  }
+  return B200VAE_OK;
 }
 
 }  // namespace b200vae
