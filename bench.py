@@ -169,6 +169,60 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def mnist_shaped_times(dev, flush, precision):
+    """BASELINE configs[3] (parity-test config, reported for reference): the MNIST-shaped LIDVAE decoder ICNN(32,512) ->
+    implicit eye(784,32) pad -> ICNN(784,1024) through the wide-input tcgen05 kernels, against the reference's own
+    formulation (module.py:142-148 + autograd.grad(create_graph=True)) run by stock PyTorch (cuBLAS FP32) on this GPU."""
+    import torch
+    from vae_song_b200 import module, ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rng = np.random.default_rng(0)
+    ics = []
+    for d, H in ((32, 512), (784, 1024)):
+        ic = module.ICNN(d, H, precision=precision).to(dev)
+        with torch.no_grad():
+            ic.W[0].param.copy_(torch.tensor(rng.normal(np.log(1.0 / H), 1.0, (H, H)), dtype=torch.float32))
+            ic.W[1].param.copy_(torch.tensor(rng.normal(np.log(2.0 / H), 1.0, (1, H)), dtype=torch.float32))
+            ic.A[0].bias.copy_(torch.tensor(rng.normal(-0.3, 1.0, (H,)), dtype=torch.float32))
+        ics.append(ic)
+    out = {"precision": precision}
+    for B in (256, 8192):
+        z = torch.randn(B, 32, device=dev, requires_grad=True)
+        vy = torch.randn(B, 784, device=dev)
+
+        def fused(train):
+            _, x1 = ics[0].brenier(z, 0.1)
+            _, y = ics[1].brenier(x1, 0.1)
+            if train:
+                (y * vy).sum().backward()
+
+        def eager(train):
+            def br(ic, x):
+                psi = ops.icnn_potential_wide(x, ic._mode(), *ic._flat_params()) + 0.1 * x.pow(2).sum(1, keepdim=True)
+                return torch.autograd.grad(psi, [x], torch.ones_like(psi), create_graph=True)[0]
+            y = br(ics[1], torch.nn.functional.linear(br(ics[0], z), torch.eye(784, 32, device=dev)))
+            if train:
+                (y * vy).sum().backward()
+
+        def t(fn, train):
+            for _ in range(3):
+                fn(train)
+            ts = []
+            for _ in range(8):
+                for ic in ics:
+                    ic.zero_grad(set_to_none=True)
+                z.grad = None
+                flush.fill_(1.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(train); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return float(np.mean(ts))
+        out[f"B{B}"] = {"decode_ms": t(fused, False), "train_ms": t(fused, True),
+                        "pytorch_eager_fp32_decode_ms": t(eager, False), "pytorch_eager_fp32_train_ms": t(eager, True)}
+    return out
+
+
 WORKLOAD = "configs[1]: LIDVAE(pinwheel/chessboard 2-D, latent 2, encoder [2,2,2,2], ICNN(2,512)+ICNN(2,1024)) train step"
 
 
@@ -339,7 +393,8 @@ def run_ours(args, rank, local_rank, world):
                 "algorithmic_flop_per_sample": io.flops_decode(2, 1024),
                 "note": "achieved = algorithmic flops / CUDA-event time; tf32x3 executes 3 MMAs per algorithmic MAC, "
                         "fp32 is the SIMT parity path (FP32 FMA peak 74.4 TFLOP/s at 1965 MHz)"}
-        extra = {"decode_by_precision": byp, "train_step_by_precision": by_prec_train}
+        extra = {"decode_by_precision": byp, "train_step_by_precision": by_prec_train,
+                 "mnist_shaped_decoder": mnist_shaped_times(dev, flush, args.precision)}
         sample = 8192
         cpu_val, cpu_s = time_oracle(sample, 3)
         cpu = {"value": cpu_val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
