@@ -280,9 +280,12 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
           tmem_ld_wait();
           const int nb = un.p * 256 + chalf * 128 + cc * 32;
           if (a.accsave != nullptr) {            // training: the backward reads this back instead of redoing GEMM2
-            uint4* dst = reinterpret_cast<uint4*>(a.accsave + (size_t)grow * Hq + nb);
+            float* dst = a.accsave + (size_t)grow * Hq + nb;      // 128 contiguous bytes per thread: 4 x 256-bit stores
 #pragma unroll
-            for (int j = 0; j < 8; ++j) __stcs(dst + j, make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+            for (int j = 0; j < 4; ++j)
+              asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * j), "r"(r[8 * j]),
+                           "r"(r[8 * j + 1]), "r"(r[8 * j + 2]), "r"(r[8 * j + 3]), "r"(r[8 * j + 4]), "r"(r[8 * j + 5]),
+                           "r"(r[8 * j + 6]), "r"(r[8 * j + 7]) : "memory");
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
