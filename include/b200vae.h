@@ -196,6 +196,11 @@ int b200vae_icnn_wide_bwd(const float* z, const float* v, const float* h0, const
                           const b200vae_icnn_grads* g, float* dz, float* u0, float* q1, float* g0, float* t0, int precision,
                           void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- aggregate-posterior log-density for calc_mi (utils.py:87-107) ------------------------------------
+ * logqz[i] = logsumexp_j log N(z[i]; mu[j], diag exp(lv[j])) - log B for z, mu, lv [B,nz]: tiled all-pairs with an online
+ * logsumexp; the [B,B,nz] tensor of the reference is never formed. */
+int b200vae_mi_logqz(const float* z, const float* mu, const float* lv, int B, int nz, float* logqz, void* stream);
+
 /* ---- peer-memory exchange between the GPUs of one node (the data-parallel exchange steps) ---------------
  * The reference has no multi-GPU path; these replace what torch.distributed/NCCL would do for the LATENCY-bound
  * collectives of the sharded train step (BatchNorm statistics of model.py:711-734's encoder, 1 KB each, ten per step)

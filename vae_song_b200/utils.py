@@ -35,6 +35,73 @@ def kld(mu, log_var):
     return kl.item()
 
 
+# ---- end-of-run latent metrics (utils.py:49-164) ------------------------------------------------------
+def calc_au_per_batch(z, eps=0.01):
+    """utils.py:49-50: fraction of latent dimensions whose batch variance (biased) is >= eps."""
+    return (torch.mean((z - z.mean(dim=0, keepdim=True)) ** 2, dim=0) >= eps).float().mean().item()
+
+
+def log_sum_exp(value, dim=None, keepdim=False):
+    """utils.py:74-85."""
+    return torch.logsumexp(value, dim=dim, keepdim=keepdim) if dim is not None else torch.logsumexp(value.reshape(-1), 0)
+
+
+def calc_mi(mu, logvar, eps=None):
+    """utils.py:87-107 (Wang et al.): I(x,z) ~= E log q(z|x) - E log q(z).  The aggregate-posterior term is the tiled
+    all-pairs kernel b200vae_mi_logqz (online logsumexp; no [B,B,nz] tensor).  `eps` may be injected for tests."""
+    import math
+    from . import _C
+    B, nz = mu.size()
+    mu, logvar = ops._req(mu.detach(), "mu"), ops._req(logvar.detach(), "logvar")
+    neg_entropy = (-0.5 * nz * math.log(2 * math.pi) - 0.5 * (1 + logvar).sum(-1)).mean()
+    if eps is None:
+        z = reparameterize(mu, logvar, 1).reshape(B, nz).contiguous()
+    else:
+        z = (mu + eps * (0.5 * logvar).exp()).contiguous()
+    log_qz = torch.empty(B, dtype=torch.float32, device=mu.device)
+    _C.check(_C.load().b200vae_mi_logqz(ops._ptr(z), ops._ptr(mu), ops._ptr(logvar), B, nz, ops._ptr(log_qz), ops._stream()),
+             "mi_logqz")
+    return (neg_entropy - log_qz.mean()).item()
+
+
+def eval_inference_dist(mu, logvar, z):
+    """utils.py:128-138: log q(z|x) for z [B,ns,nz]."""
+    import math
+    nz = z.size(2)
+    mu, logvar = mu.unsqueeze(1), logvar.unsqueeze(1)
+    return -0.5 * (((z - mu) ** 2) / logvar.exp()).sum(dim=-1) - 0.5 * (nz * math.log(2 * math.pi) + logvar.sum(-1))
+
+
+def nll_iw(mu, log_var, loss_rec, nsamples=100):
+    """utils.py:109-120: importance-weighted NLL estimate (a scalar over the whole batch, like the reference)."""
+    import math
+    z = reparameterize(mu.detach(), log_var.detach(), nsamples)
+    log_pz = (-0.5 * z ** 2 - 0.5 * math.log(2 * math.pi)).sum(dim=-1)
+    tmp = log_pz - loss_rec - eval_inference_dist(mu.detach(), log_var.detach(), z)
+    return -(log_sum_exp(tmp) - math.log(nsamples)).item()
+
+
+def measure_pc_runmodel(model, loader, device):
+    """utils.py:144-164: (AU, KL, MI, NLL, sum of variances) on the FIRST batch of the loader."""
+    au_sum = kl_sum = mi_sum = nll_sum = var_sum = 0
+    for i, data in enumerate(loader):
+        if i > 0:
+            break
+        x = data[0].to(device)
+        res = model(x)
+        recon, mu, log_var = res[0], res[1], res[2]
+        z_in = res[3] if len(res) > 3 else None
+        z_rec = res[4] if len(res) > 4 else None
+        _, loss_rec, _, _ = model.loss(x, recon, mu, log_var, z_input=z_in, z_recon=z_rec)
+        au_sum += calc_au_per_batch(mu.detach())
+        kl_sum += kld(mu, log_var)
+        mi_sum += calc_mi(mu, log_var)
+        nll_sum += nll_iw(mu, log_var, loss_rec.detach() if torch.is_tensor(loss_rec) else loss_rec)
+        if torch.is_tensor(log_var):
+            var_sum += log_var.detach().exp().sum().item()
+    return au_sum, kl_sum, mi_sum, nll_sum, var_sum
+
+
 def estimate_local_lipschitz(func, X, num_pairs=2000, metric=2, quantile=0.05, eps=1e-3, generator=None,
                              use_grad=False):
     """Random-pair local Lipschitz estimate, reference semantics (utils.py:532-567):
