@@ -231,8 +231,8 @@ def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
 
-    from oracle import icnn_oracle as io
     from vae_song_b200 import _C, model, ops, train
+    from vae_song_b200 import utils as vutils
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -377,8 +377,8 @@ def run_ours(args, rank, local_rank, world):
                 res[H] = float(np.mean(ts))
             both = Bk / ((res[512] + res[1024]) * 1e-3)
             byp[pname] = {"decode_ms_H512": res[512], "decode_ms_H1024": res[1024], "decode_samples_per_s": both,
-                          "tflops_H1024": io.flops_decode(2, 1024) * Bk / (res[1024] * 1e-3) / 1e12,
-                          "tflops_2icnn": both * (io.flops_decode(2, 512) + io.flops_decode(2, 1024)) / 1e12}
+                          "tflops_H1024": vutils.flops_decode(2, 1024) * Bk / (res[1024] * 1e-3) / 1e12,
+                          "tflops_2icnn": both * (vutils.flops_decode(2, 512) + vutils.flops_decode(2, 1024)) / 1e12}
         rp = args.roofline_precision
         ach = byp[rp]["tflops_H1024"]
         try:      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture (profiles/)
@@ -390,7 +390,7 @@ def run_ours(args, rank, local_rank, world):
                 "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak, "traffic": traffic,
                 "peak_kind": f"{pk_kind} cuBLAS bf16 burst" + (" / 2 (TF32 runs at half the bf16 rate)" if rp.startswith("tf32") else ""),
                 "precision": rp, "kernel_ms": byp[rp]["decode_ms_H1024"],
-                "algorithmic_flop_per_sample": io.flops_decode(2, 1024),
+                "algorithmic_flop_per_sample": vutils.flops_decode(2, 1024),
                 "note": "achieved = algorithmic flops / CUDA-event time; tf32x3 executes 3 MMAs per algorithmic MAC, "
                         "fp32 is the SIMT parity path (FP32 FMA peak 74.4 TFLOP/s at 1965 MHz)"}
         extra = {"decode_by_precision": byp, "train_step_by_precision": by_prec_train,

@@ -2,8 +2,7 @@
 import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from oracle import icnn_oracle as io
-from vae_song_b200 import ops, _C
+from vae_song_b200 import module, ops, utils as vutils, _C
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--precision", default="tf32")
@@ -13,8 +12,8 @@ ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--bwd", action="store_true")
 a = ap.parse_args()
 rng = np.random.default_rng(0)
-p = io.random_params(rng, 2, a.H, np.float64, "mixed")
-P = [torch.tensor(np.asarray(p[k], np.float32), device="cuda") for k in io.PARAM_KEYS]
+ic = vutils.trained_like_icnn_(module.ICNN(2, a.H).cuda(), rng)
+P = [t.detach() for t in ic._flat_params()]
 z = torch.randn(a.B, 2, device="cuda")
 v = torch.randn(a.B, 2, device="cuda")
 prec = _C.PRECISIONS[a.precision]

@@ -2,14 +2,13 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from oracle import icnn_oracle as io
-from vae_song_b200 import ops
+from vae_song_b200 import module, ops, utils as vutils
 B = 65536
 flush = torch.empty(64 * 1024 * 1024, device="cuda")
 for H in (512, 1024):
     rng = np.random.default_rng(0)
-    p = io.random_params(rng, 2, H, np.float64, "mixed")
-    P = [torch.tensor(np.asarray(p[k], np.float32), device="cuda") for k in io.PARAM_KEYS]
+    ic = vutils.trained_like_icnn_(module.ICNN(2, H).cuda(), rng)
+    P = [t.detach() for t in ic._flat_params()]
     z = torch.randn(B, 2, device="cuda"); v = torch.randn(B, 2, device="cuda")
     ws = ops.icnn_prepare(P, 2, H, 0, 3, B, True)
     def t(fn):

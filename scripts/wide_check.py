@@ -4,8 +4,7 @@ formulation (module.py:142-148 + autograd.grad(create_graph=True), model.py:818-
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from oracle import icnn_oracle as io
-from vae_song_b200 import module, ops
+from vae_song_b200 import module, ops, utils as vutils
 
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device("cuda")
@@ -62,7 +61,7 @@ def timeit(fn, train, n=10):
     return e0.elapsed_time(e1) / n
 
 
-fl_dec = io.flops_decode(32, 512) + io.flops_decode(784, 1024)
+fl_dec = vutils.flops_decode(32, 512) + vutils.flops_decode(784, 1024)
 yb = eager(False).detach()
 te = {False: timeit(eager, False), True: timeit(eager, True)}
 for prec in PRECS:

@@ -8,6 +8,29 @@ import torch
 from . import ops
 
 
+def flops_decode(d, H):
+    """Algorithmic flops per sample of one ICNN decode (psi + grad psi), multiply-add = 2:
+    forward P0 x1 (2H^2) + reverse P0^T g1 (2H^2) + four [d,H] products + the P1 dot + A2."""
+    return 4 * H * H + 8 * d * H + 2 * H + 4 * d
+
+
+def flops_train(d, H):
+    """Decode + double-backward per sample: adds P0 q1, g1^T q1, A0 v, A1 v, three [H,d] outer products."""
+    return 8 * H * H + 22 * d * H
+
+
+def trained_like_icnn_(icnn, rng):
+    """O(1)-scale, mixed-sign weights for synthetic benchmarks (the default exp(W) ~ 1 init gives ~1e10 outputs,
+    SURVEY Appendix B.8).  `rng`: numpy Generator."""
+    import numpy as np
+    H = icnn.hidden_channel
+    with torch.no_grad():
+        icnn.W[0].param.copy_(torch.tensor(rng.normal(np.log(1.0 / H), 1.0, (H, H)), dtype=torch.float32))
+        icnn.W[1].param.copy_(torch.tensor(rng.normal(np.log(2.0 / H), 1.0, (1, H)), dtype=torch.float32))
+        icnn.A[0].bias.copy_(torch.tensor(rng.normal(-0.3, 1.0, (H,)), dtype=torch.float32))
+    return icnn
+
+
 def apply_grad_clip(model, grad_clip_cfg):
     """Same config contract as the reference: {'enabled', 'clip_type': 'norm'|'value', 'max_norm',
     'norm_type', 'clip_value'}; anything else is a no-op."""
