@@ -3,11 +3,10 @@ forward with the library given by B200VAE_LIB and dumps psi/xhat; compare the tw
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from oracle import icnn_oracle as io
-from vae_song_b200 import ops
+from vae_song_b200 import module, ops, utils as vutils
 rng = np.random.default_rng(0)
-p = io.random_params(rng, 2, 1024, np.float64, "mixed")
-P = [torch.tensor(np.asarray(p[k], np.float32), device="cuda") for k in io.PARAM_KEYS]
+ic = vutils.trained_like_icnn_(module.ICNN(2, 1024).cuda(), rng)
+P = [t.detach() for t in ic._flat_params()]
 z = torch.tensor(rng.normal(0, 1, (4096, 2)), dtype=torch.float32, device="cuda")
 v = torch.tensor(rng.normal(0, 1, (4096, 2)), dtype=torch.float32, device="cuda")
 ws = ops.icnn_prepare(P, 2, 1024, 0, 1, 4096, True)
