@@ -1,6 +1,6 @@
 """Diagnostic: tcgen05 ICNN forward vs fp64 oracle and vs the SIMT path, with timings (run on the GPU box)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import icnn_oracle as io
 from vae_song_b200 import ops, _C
