@@ -179,7 +179,8 @@ def test_tc_forward_workspace_reuse_and_mask_paths():
         assert torch.equal(m2.bool(), psi_a > 0)
 
 
-@pytest.mark.parametrize("shape", [(2, 512, 700), (3, 1024, 300), (1, 256, 1000)], ids=["d2_h512", "d3_h1024", "d1_h256"])
+@pytest.mark.parametrize("shape", [(2, 512, 700), (3, 1024, 300), (1, 256, 1000), (2, 1024, 65536)],
+                         ids=["d2_h512", "d3_h1024", "d1_h256", "d2_h1024_b65536"])
 def test_saved_accumulator_backward_equals_recompute(shape):
     """3xTF32 training: the pair forward keeps its GEMM2 accumulators in the for_backward workspace and the backward reads
     them back (icnn_tc3.cu SV kernels) instead of redoing that GEMM.  Re-running prepare on the workspace invalidates the
@@ -206,6 +207,8 @@ def test_saved_accumulator_backward_equals_recompute(shape):
     assert torch.equal(res[0][1], res[1][1]), float((res[0][1] - res[1][1]).abs().max())
     for k, a, b in zip(KEYS, res[0][2], res[1][2]):
         assert torch.equal(a, b), (k, float((a - b).abs().max()))
+    if B > 2000:        # BASELINE batch: the bit-identity above is the size-independent check
+        return
     # and against the fp64 oracle (3xTF32 bounds)
     rdz, rg = io.icnn_brenier_backward(f32_as_f64(z.cpu().numpy()), f32_as_f64(v.cpu().numpy()), params_f32_as_f64(p), 0, 0.1, None)
     close_report(res[0][1].cpu().numpy(), rdz, 3e-4, "dz", bad_frac=0.02)
