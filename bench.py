@@ -169,6 +169,54 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def eager_same_gpu(m, x, flush, steps=5):
+    """The reference's own formulation of this train step (lipschitz.py:36-43 over model.py:818-886: stock nn.Modules for
+    the encoder, ICNN.forward as torch ops, two autograd.grad(create_graph=True) calls, autograd double-backward,
+    torch.optim.Adam) run by stock PyTorch eager in FP32 (TF32 off, the reference's default) on THIS GPU -- the number the
+    fused path has to beat.  Same weights, same batch."""
+    import copy
+    import torch
+    import torch.nn.functional as F
+    from vae_song_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ref = copy.deepcopy(m).train()
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    kappa = ref.il_factor
+
+    def brenier(ic, zz):
+        psi = ops.icnn_potential_wide(zz, ic._mode(), *ic._flat_params()) + kappa * zz.pow(2).sum(1, keepdim=True)
+        return torch.autograd.grad(psi, [zz], torch.ones_like(psi), create_graph=True)[0]
+
+    def step():
+        opt.zero_grad()
+        ret = ref.encoder(x)                                    # stock Linear / BatchNorm1d / LeakyReLU modules
+        mu, var = ret.split(ret.shape[1] // 2, 1)
+        lv = F.softplus(var)
+        z = mu + torch.randn_like(mu) * torch.exp(0.5 * lv)
+        y = brenier(ref.decoder[1], F.linear(brenier(ref.decoder[0], z), ref.B))
+        rec = ((x - y) ** 2).mean(0).sum()
+        kl = (-0.5 * (1 + lv - mu ** 2 - lv.exp())).mean(0).sum()
+        (rec + ref.beta * kl).backward()
+        opt.step()
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(steps):
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); step(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.mean(ts))
+    del ref, opt
+    torch.cuda.empty_cache()
+    return {"train_ms": ms, "samples_per_s": x.shape[0] / (ms * 1e-3), "batch": int(x.shape[0]),
+            "what": "reference formulation (torch ops + autograd.grad(create_graph=True) + autograd double-backward + "
+                    "torch.optim.Adam), stock PyTorch eager, FP32 with TF32 off, same weights and batch, this GPU"}
+
+
 def mnist_shaped_times(dev, flush, precision):
     """BASELINE configs[3] (parity-test config, reported for reference): the MNIST-shaped LIDVAE decoder ICNN(32,512) ->
     implicit eye(784,32) pad -> ICNN(784,1024) through the wide-input tcgen05 kernels, against the reference's own
@@ -394,6 +442,7 @@ def run_ours(args, rank, local_rank, world):
                 "note": "achieved = algorithmic flops / CUDA-event time; tf32x3 executes 3 MMAs per algorithmic MAC, "
                         "fp32 is the SIMT parity path (FP32 FMA peak 74.4 TFLOP/s at 1965 MHz)"}
         extra = {"decode_by_precision": byp, "train_step_by_precision": by_prec_train,
+                 "pytorch_eager_same_gpu": eager_same_gpu(m, dev_pool[0], flush) if world == 1 else None,
                  "mnist_shaped_decoder": mnist_shaped_times(dev, flush, args.precision)}
         sample = 8192
         cpu_val, cpu_s = time_oracle(sample, 3)
