@@ -375,7 +375,12 @@ def run_ours(args, rank, local_rank, world):
                 clocks = sampler.window(t0c + 0.1, time.time())
                 clocks["note"] = "sampled during an untimed ~1 s continuation of the timed loop (timed region < sampling period)"
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
-    tr.check()                                             # a peer exchange that timed out would have produced garbage
+    exchange_ok = True
+    try:
+        tr.check()                                         # a peer exchange that timed out would have produced garbage
+    except Exception as exc:                               # noqa: BLE001 - report it in the line instead of losing the run
+        exchange_ok = False
+        print(f"[bench] rank {rank}: {exc}", file=sys.stderr, flush=True)
     value = world * B / (ms * 1e-3)
     e2e = world * B / (ms_e2e * 1e-3)
 
@@ -454,6 +459,7 @@ def run_ours(args, rank, local_rank, world):
                 "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "precision": args.precision,
                            "parallelism": f"dp{world}", "l2": "flushed between timed iterations (256 MB write)",
                            "optimizer": "fused Adam lr 1e-3 over flat buffer", "exchange": exchange,
+                           "exchange_ok": exchange_ok,
                            "cuda_graph": bool(use_graph), "own_kernel_launches_per_step": int(launches_per_step)},
                 "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 2 * 4 * world,
                         "d2h_bytes_per_step": 4 * world},
