@@ -217,6 +217,34 @@ def eager_same_gpu(m, x, flush, steps=5):
                     "torch.optim.Adam), stock PyTorch eager, FP32 with TF32 off, same weights and batch, this GPU"}
 
 
+def lipschitz_times(m, dev):
+    """north_star kernel (4): the tiled all-pairs estimator and the reference-semantics random-pair estimator
+    (utils.py:532-567) on N = 5000 latent samples of this model (lipschitz.py:157-194 sizes)."""
+    import torch
+    from vae_song_b200 import ops, utils
+    N = 5000
+    X = torch.randn(N, 2, device=dev)
+    with torch.no_grad():
+        Y = m.decode(X)
+
+    def t(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    k_ms = t(lambda: ops.lipschitz_allpairs(X, Y, 1e-3))
+    e_ms = t(lambda: utils.estimate_local_lipschitz(m.decode, X, num_pairs=5000), 5)
+    pairs = N * (N - 1) // 2
+    return {"N": N, "allpairs_kernel_ms": k_ms, "allpairs_pairs_per_s": pairs / (k_ms * 1e-3),
+            "random_pairs_estimate_ms": e_ms, "note": "all-pairs: 64x64 tiles of the upper triangle, max/min/sum by warp shuffles; "
+            "random pairs: 2 decodes of 5000 rows + ratio kernel + 2 quantiles + one host sync"}
+
+
 def mnist_shaped_times(dev, flush, precision):
     """BASELINE configs[3] (parity-test config, reported for reference): the MNIST-shaped LIDVAE decoder ICNN(32,512) ->
     implicit eye(784,32) pad -> ICNN(784,1024) through the wide-input tcgen05 kernels, against the reference's own
@@ -448,6 +476,7 @@ def run_ours(args, rank, local_rank, world):
                         "fp32 is the SIMT parity path (FP32 FMA peak 74.4 TFLOP/s at 1965 MHz)"}
         extra = {"decode_by_precision": byp, "train_step_by_precision": by_prec_train,
                  "pytorch_eager_same_gpu": eager_same_gpu(m, dev_pool[0], flush) if world == 1 else None,
+                 "lipschitz_estimator": lipschitz_times(m, dev),
                  "mnist_shaped_decoder": mnist_shaped_times(dev, flush, args.precision)}
         sample = 8192
         cpu_val, cpu_s = time_oracle(sample, 3)

@@ -99,6 +99,21 @@ for mode, graphed in (("nccl", False), ("peer", False), ("peer", True)):
     del tr
 say("DP_CHECK", "PASS" if ok else "FAIL")
 
+# ---- 2b. all-pairs Lipschitz estimator: pair tiles sharded over the ranks == single rank -----------------------------------
+from vae_song_b200 import utils as vutils
+mm = make().eval()
+torch.manual_seed(9)
+Xl = torch.randn(3000, 2, device=dev)
+dist.broadcast(Xl, src=0)
+sharded = vutils.estimate_lipschitz_allpairs(mm.decode, Xl)                      # default group: tiles split by range
+single = vutils.estimate_lipschitz_allpairs(mm.decode, Xl, process_group=solo) if rank == 0 else None
+if rank == 0:
+    good = (sharded["count"] == single["count"] == 3000 * 2999 // 2 and sharded["max"] == single["max"]
+            and sharded["min"] == single["min"] and abs(sharded["mean"] - single["mean"]) <= 1e-9 * abs(single["mean"]))
+    ok = ok and good
+    print(f"all-pairs Lipschitz sharded over {world} ranks: max {sharded['max']:.6g} min {sharded['min']:.6g} mean "
+          f"{sharded['mean']:.9g} (single {single['mean']:.9g}) -> {'PASS' if good else 'FAIL'}", flush=True)
+
 # ---- 3. timing on the bench workload --------------------------------------------------------------------------------------
 if "--time" in sys.argv:
     B = 65536
