@@ -109,7 +109,7 @@ sharded = vutils.estimate_lipschitz_allpairs(mm.decode, Xl)                     
 single = vutils.estimate_lipschitz_allpairs(mm.decode, Xl, process_group=solo) if rank == 0 else None
 if rank == 0:
     good = (sharded["count"] == single["count"] == 3000 * 2999 // 2 and sharded["max"] == single["max"]
-            and sharded["min"] == single["min"] and abs(sharded["mean"] - single["mean"]) <= 1e-9 * abs(single["mean"]))
+            and sharded["min"] == single["min"] and abs(sharded["mean"] - single["mean"]) <= 1e-6 * abs(single["mean"]))   # fp32 per-CTA partial sums: order differs
     ok = ok and good
     print(f"all-pairs Lipschitz sharded over {world} ranks: max {sharded['max']:.6g} min {sharded['min']:.6g} mean "
           f"{sharded['mean']:.9g} (single {single['mean']:.9g}) -> {'PASS' if good else 'FAIL'}", flush=True)
