@@ -329,6 +329,53 @@ def gen_families(ref_model):
     print("family_cases.npz:", len(out), "arrays")
 
 
+def gen_train_trajectory(ref_model):
+    """Training TRAJECTORY of the unmodified reference loop: lipschitz.train_model (lipschitz.py:23-44: Adam, forward,
+    loss, backward, step) on a small LIDVAE for 2 epochs x 6 batches in fp32 on CPU.  The only intervention is the
+    ENVIRONMENT: torch.randn_like is wrapped so that the eps draws of model.py:843 come from a recorded list (the CPU and
+    CUDA generators produce different streams), and the loader is a plain list of batches.  Stored: per-step total /
+    recon / KL losses (captured by wrapping model.loss), the initial state_dict, the final parameters and BatchNorm buffers."""
+    import lipschitz as ref_lipschitz        # the reference's own training loop
+    rng = np.random.default_rng(21)
+    kw = dict(dataset="pinwheel", icnn_channels=[32, 64], hidden_channels=[16, 8], inverse_lipschitz=0.2, beta=0.3)
+    torch.manual_seed(3)
+    m = ref_model.LIDVAE(**kw)
+    with torch.no_grad():
+        for ic in (m.decoder[0], m.decoder[1]):
+            H = ic.A0.weight.shape[0]
+            ic.W[0].param.copy_(torch.tensor(rng.normal(np.log(1.0 / H), 1.0, ic.W[0].param.shape), dtype=torch.float32))
+            ic.W[1].param.copy_(torch.tensor(rng.normal(np.log(2.0 / H), 1.0, ic.W[1].param.shape), dtype=torch.float32))
+            ic.A[0].bias.copy_(torch.tensor(rng.normal(-0.3, 1.0, ic.A[0].bias.shape), dtype=torch.float32))
+    out = {f"sd0/{k}": a for k, a in sd_to_np(m.state_dict()).items()}
+    nb, B, epochs = 6, 64, 2
+    X = rng.normal(0, 1.5, (nb, B, 2)).astype(np.float32)
+    eps = rng.normal(0, 1.0, (epochs * nb, B, 2)).astype(np.float32)
+    out["X"], out["eps"] = X, eps
+    loader = [(torch.tensor(X[i]), torch.zeros(B, dtype=torch.int64)) for i in range(nb)]
+    draws = iter(eps)
+    real_randn_like = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: torch.tensor(next(draws), dtype=t.dtype)
+    losses = []
+    real_loss = m.loss
+
+    def recording_loss(*a, **k):
+        r = real_loss(*a, **k)
+        losses.append([float(r[0]), float(r[1]), float(r[2])])
+        return r
+    m.loss = recording_loss
+    try:
+        ref_lipschitz.train_model(m, loader, epochs, 1e-3, "cpu")
+    finally:
+        torch.randn_like = real_randn_like
+        del m.loss
+    out["losses"] = np.array(losses, dtype=np.float64)
+    for k, a in sd_to_np(m.state_dict()).items():
+        out[f"sd1/{k}"] = a
+    out["cfg"] = np.array([nb, B, epochs])
+    np.savez_compressed(os.path.join(OUT, "train_trajectory.npz"), **out)
+    print("train_trajectory.npz:", len(out), "arrays; first / last loss", losses[0][0], losses[-1][0])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref_module, ref_model, ref_utils = import_reference()
@@ -339,6 +386,7 @@ def main():
     gen_losses(ref_model, ref_utils)
     gen_lipschitz(ref_model, ref_utils)
     gen_families(ref_model)
+    gen_train_trajectory(ref_model)
 
 
 if __name__ == "__main__":

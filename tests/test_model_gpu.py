@@ -283,3 +283,42 @@ def test_fused_encoder_matches_stock_modules(hidden, training):
             close_report(a.grad.cpu().numpy(), b.grad.cpu().numpy(), 2e-4, "grad " + k, floor=1e-5 * gscale)
     for (k, a), (_, b) in zip(m.encoder.named_buffers(), ref.encoder.named_buffers()):
         close_report(a.float().cpu().numpy(), b.float().cpu().numpy(), 1e-5, "buffer " + k)
+
+
+def test_train_model_follows_the_reference_trajectory():
+    """a10 (lipschitz.py:23-44): 12 Adam steps of the UNMODIFIED reference's train_model on a small LIDVAE (fp32, CPU; golden
+    from oracle/make_golden.py::gen_train_trajectory) against train.train_model on the GPU kernels -- same initial
+    state_dict, same batches, same eps draws (torch.randn_like wrapped on both sides): per-step losses and the final
+    parameters / BatchNorm buffers must agree."""
+    from vae_song_b200 import model, train
+    G = np.load(os.path.join(GOLDEN, "train_trajectory.npz"))
+    nb, B, epochs = (int(v) for v in G["cfg"])
+    m = model.LIDVAE(dataset="pinwheel", icnn_channels=[32, 64], hidden_channels=[16, 8], inverse_lipschitz=0.2, beta=0.3)
+    sd0 = {k[4:]: torch.tensor(G[k]) for k in G.files if k.startswith("sd0/")}
+    m.load_state_dict(sd0)
+    loader = [(torch.tensor(G["X"][i]), torch.zeros(B, dtype=torch.int64)) for i in range(nb)]
+    draws = iter(G["eps"])
+    real_randn_like, losses, real_loss = torch.randn_like, [], m.loss
+
+    def recording_loss(*a, **k):
+        r = real_loss(*a, **k)
+        losses.append([float(r[0].detach()), float(r[1]), float(r[2])])
+        return r
+    m.loss = recording_loss
+    torch.randn_like = lambda t, *a, **k: torch.tensor(next(draws), dtype=t.dtype, device=t.device)
+    try:
+        train.train_model(m, loader, epochs, 1e-3, "cuda")
+    finally:
+        torch.randn_like = real_randn_like
+        del m.loss
+    np.testing.assert_allclose(np.array(losses), G["losses"], rtol=2e-4, err_msg="per-step (total, recon, KL) losses")
+    assert G["losses"][-1, 0] < G["losses"][0, 0]
+    sd1 = m.state_dict()
+    for k in G.files:
+        if not k.startswith("sd1/"):
+            continue
+        ours, ref = sd1[k[4:]].detach().cpu().numpy(), G[k]
+        if ref.dtype.kind != "f":
+            assert np.array_equal(ours, ref), k
+        else:      # 12 Adam steps amplify fp32 rounding differences of tiny gradients (update = lr * g/|g|): absolute floor
+            np.testing.assert_allclose(ours, ref, rtol=2e-3, atol=2e-4, err_msg=k)
