@@ -21,6 +21,7 @@ for ic in (m.decoder[0], m.decoder[1]):
     vutils.trained_like_icnn_(ic, rng)
 
 def sync(): torch.cuda.synchronize()
+train.train_model(m, [b for _, b in zip(range(8), loader)], 1, 1e-3, dev)     # warm-up: module loading, allocator, cuBLAS
 sync(); t0 = time.perf_counter()
 train.train_model(m, loader, 1, 1e-3, dev)
 sync(); t_eager = (time.perf_counter() - t0) / len(loader)
