@@ -36,6 +36,7 @@ print(f"C3 train step, batch {B}, precision {prec}: eager loop {t_eager * 1e3:.3
       f"whole-step CUDA graph {t_graph * 1e3:.3f} ms/step ({B / t_graph / 1e3:.1f} k samples/s)")
 
 m.eval()
+L.evaluate(m, ds, K, Kz, -3.0, 3.0, 2, dev)          # warm-up (allocator growth for the 512k-row batched decodes)
 sync(); t0 = time.perf_counter()
 res = L.evaluate(m, ds, K, Kz, -3.0, 3.0, 2, dev)
 sync(); t_batched = time.perf_counter() - t0
