@@ -84,10 +84,21 @@ class ICNN(nn.Module):
             return ops.icnn_potential_wide(input, self._mode(), *self._flat_params())
         return ops.IcnnPotentialFn.apply(input, self._mode(), self._prec(), *self._flat_params())
 
+    FP32_TILED_BELOW = 8192   # FP32 batches below one wave of 128-sample CTAs: the tiled GEMM chain is the faster FP32 path
+
     def brenier(self, input, kappa=0.0):
-        """(psi [B], xhat [B,d]).  For wide ICNNs `input` may be [B,nz] with nz < d: zero-padded to d inside the kernels."""
-        fn = ops.IcnnBrenierWideFn if self.in_channel > self.FUSED_MAX_D else ops.IcnnBrenierFn
-        return fn.apply(input, float(kappa), self._mode(), self._prec(), *self._flat_params())
+        """(psi [B], xhat [B,d]).  For wide ICNNs `input` may be [B,nz] with nz < d: zero-padded to d inside the kernels.
+
+        Kernel choice: d > 4 -> the wide-input kernels (tcgen05 or FP32 tile GEMMs).  d <= 4: the fused sample-stationary
+        kernels (tcgen05 pair kernels for tf32 / tf32x3; FP32 SIMT for fp32) -- except FP32 at small batches, where one CTA
+        per 128 samples would leave most of the 148 SMs idle (a batch-256 step ran on 2 SMs): those go through the FP32
+        tile-GEMM chain of csrc/icnn_wide.cu, which tiles over the hidden width as well (same arithmetic, same bounds)."""
+        prec = self._prec()
+        wide = self.in_channel > self.FUSED_MAX_D or (
+            prec == _C.PREC_FP32 and input.dim() == 2 and input.shape[0] < self.FP32_TILED_BELOW
+            and input.shape[1] == self.in_channel)
+        fn = ops.IcnnBrenierWideFn if wide else ops.IcnnBrenierFn
+        return fn.apply(input, float(kappa), self._mode(), prec, *self._flat_params())
 
 
 def _bn_act(norm, act=True):
