@@ -87,7 +87,7 @@ struct ARow {
       for (int e = 0; e < 8; ++e) r[e] = (rv && kb + e < K) ? (mp[e] ? 1.f : kSlope) * __ldg(P1 + kb + e) : 0.f;
     } else {
       const float* sp = src + (size_t)row * ld + kb;
-      if (rv && kb + 7 < K && ((ld & 3) == 0)) {
+      if (rv && kb + 7 < K && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(sp)), b = __ldg(reinterpret_cast<const float4*>(sp) + 1);
         r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
       } else {
@@ -149,7 +149,7 @@ struct BMat {
     for (int h = 0; h < 2; ++h) {
       const int k = kbeg + kt * kBK + rr + 8 * h, n = n0 + c4;
       const float* sp = Mx + (size_t)k * ld + n;
-      if (k < kend && n + 3 < N && ((ld & 3) == 0)) {
+      if (k < kend && n + 3 < N && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(Mx) & 15u) == 0)) {
         cp_async16(&Bs[rr + 8 * h][c4], sp);
       } else {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -553,13 +553,15 @@ extern "C" int b200vae_icnn_wide_fwd(const float* z, int B, int d, int nz, int H
   if (precision < B200VAE_PREC_FP32 || precision > B200VAE_PREC_TF32X3 || precision == B200VAE_PREC_BF16) return B200VAE_EUNSUP;
   const WideWs L = wide_layout(B, d, H, false);
   if (ws_bytes < b200vae_icnn_wide_workspace_bytes(B, d, H, precision, 0)) return B200VAE_EWS;
-  if (!aligned16(workspace) || !aligned16(z) || !aligned16(h0) || !aligned16(p->A0w) || !aligned16(p->A1w) ||
-      (g0 && !aligned16(g0)) || (xhat && !aligned16(xhat)) || !aligned16(p->A0b) || !aligned16(p->A1b) || !aligned16(p->A2w))
+  if (!aligned16(workspace) || !aligned16(z) || !aligned16(h0) || !aligned4(p->A0w) || !aligned4(p->A1w) ||
+      (g0 && !aligned16(g0)) || (xhat && !aligned16(xhat)))
     return B200VAE_EALIGN;
+  // the tcgen05 epilogues read b0, b1, A2 with 16-byte loads; parameters at odd offsets take the FP32 kernels
+  const bool p16 = aligned16(p->A0b) && aligned16(p->A1b) && aligned16(p->A2w);
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
   static const bool tc_on = [] { const char* e = getenv("B200VAE_WIDE_TC"); return !e || atoi(e) != 0; }();
-  if (precision != B200VAE_PREC_FP32 && tc_on && wide_tc_supported(d, nz, H, precision)) {   // tcgen05 forward
+  if (precision != B200VAE_PREC_FP32 && tc_on && p16 && wide_tc_supported(d, nz, H, precision)) {   // tcgen05 forward
     const int rc_tc = wide_tc_fwd(z, B, d, nz, H, p, weight_mode, kappa, psi, xhat, h0, mask1, s2, g0, ws, precision, st);
     if (rc_tc != B200VAE_EUNSUP) return rc_tc;
   }
@@ -595,7 +597,7 @@ extern "C" int b200vae_icnn_wide_bwd(const float* z, const float* v, const float
   const WideWs L = wide_layout(B, d, H, true);
   if (ws_bytes < b200vae_icnn_wide_workspace_bytes(B, d, H, precision, 1)) return B200VAE_EWS;
   if (!aligned16(workspace) || !aligned16(z) || !aligned16(v) || !aligned16(h0) || !aligned16(u0) || !aligned16(q1) ||
-      !aligned16(g0) || !aligned16(t0) || !aligned16(p->A0w) || !aligned16(p->A1w) || (dz && !aligned16(dz)))
+      !aligned16(g0) || !aligned16(t0) || !aligned4(p->A0w) || !aligned4(p->A1w) || (dz && !aligned16(dz)))
     return B200VAE_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;

@@ -124,10 +124,11 @@ class FlatParams:
         params = [p for p in model.parameters() if p.requires_grad]
         if not params:
             raise ValueError("model has no trainable parameters")
-        dev, n = params[0].device, sum(p.numel() for p in params)
+        pad4 = lambda k: (k + 3) // 4 * 4        # every parameter starts on a 16-byte boundary (vector loads, TMA, cp.async)
+        dev, n = params[0].device, sum(pad4(p.numel()) for p in params)
         self.params = params
         if alloc is None:
-            self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+            self.flat = torch.zeros(n, dtype=torch.float32, device=dev)        # padding between parameters stays 0
             self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         else:
             self.flat, self.grad = alloc(n), alloc(n)
@@ -140,7 +141,7 @@ class FlatParams:
             p.data = self.flat[off:off + k].view_as(p.data)
             p.grad = self.grad[off:off + k].view_as(p.data)
             self.views.append(p.grad)
-            off += k
+            off += pad4(k)
         self.numel = n
         self._had = [False] * len(params)
 
@@ -169,13 +170,9 @@ class FlatParams:
 
     def zero_grad(self):
         self.grad.zero_()
-        off = 0
-        for p in self.params:   # autograd may have replaced .grad; re-attach the views
-            k = p.numel()
-            view = self.grad[off:off + k].view_as(p.data)
+        for p, view in zip(self.params, self.views):   # autograd may have replaced .grad; re-attach the views
             if p.grad is None or p.grad.data_ptr() != view.data_ptr():
                 p.grad = view
-            off += k
 
 
 def shard_rows(n_rows, rank, world):
