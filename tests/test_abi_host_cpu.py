@@ -163,7 +163,10 @@ def test_flat_params_views():
     from vae_song_b200 import train
     m = _ToyVAE()
     fp = train.FlatParams(m)
-    assert fp.numel == sum(p.numel() for p in m.parameters())
+    # every parameter starts on a 16-byte boundary inside the flat buffer (padding stays zero)
+    assert fp.numel == sum((p.numel() + 3) // 4 * 4 for p in m.parameters()) and fp.numel % 4 == 0
+    assert all(v.data_ptr() % 16 == fp.grad.data_ptr() % 16 for v in fp.views)
+    assert all(p.data_ptr() % 16 == fp.flat.data_ptr() % 16 for p in m.parameters())
     m.enc[0].weight.data.fill_(2.0)
     assert float(fp.flat[:12].sum()) == 24.0
     x = torch.randn(5, 2)
