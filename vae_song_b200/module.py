@@ -84,7 +84,7 @@ class ICNN(nn.Module):
             return ops.icnn_potential_wide(input, self._mode(), *self._flat_params())
         return ops.IcnnPotentialFn.apply(input, self._mode(), self._prec(), *self._flat_params())
 
-    FP32_TILED_BELOW = 8192   # FP32 batches below one wave of 128-sample CTAs: the tiled GEMM chain is the faster FP32 path
+    FP32_TILED_BELOW = 6144   # measured crossover (scripts/fp32_crossover.py): below it the tiled GEMM chain is the faster FP32 path
 
     def brenier(self, input, kappa=0.0):
         """(psi [B], xhat [B,d]).  For wide ICNNs `input` may be [B,nz] with nz < d: zero-padded to d inside the kernels.
