@@ -329,3 +329,46 @@ def test_train_model_follows_the_reference_trajectory():
             assert np.array_equal(ours, ref), k
         else:      # 12 Adam steps amplify fp32 rounding differences of tiny gradients (update = lr * g/|g|): absolute floor
             np.testing.assert_allclose(ours, ref, rtol=2e-3, atol=2e-4, err_msg=k)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_flexible_vae_fused_mlp_stacks_match_stock_modules(training):
+    """FlexibleVAE-family 1-D MLP stacks (BASELINE configs[0]: pinwheel LR-VAE, encoder ENDING in BatchNorm + LeakyReLU,
+    decoder ending in a bare Linear) through the fused layer kernels vs the very same nn.Modules run by PyTorch: the
+    whole forward (two decodes, two encodes, L = 2), the loss parts, every gradient and the BatchNorm buffers."""
+    from vae_song_b200 import model
+    import copy
+    torch.manual_seed(0)
+    m = model.LRVAE(alpha=0.3, beta=0.2, dataset="pinwheel", hidden_channels=[16, 16, 16], encoder_type="mlp", decoder_type="mlp").cuda()
+    m.wu_alpha = 1.0
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm1d):
+                mod.weight.uniform_(0.5, 1.5); mod.bias.uniform_(-0.5, 0.5)
+                mod.running_mean.uniform_(-0.2, 0.2); mod.running_var.uniform_(0.5, 1.5)
+    ref = copy.deepcopy(m)
+    ref.fused_mlp = False
+    m.train(training); ref.train(training)
+    pe, pd = m._stack_plan("encoder"), m._stack_plan("decoder")
+    assert pe is not None and pe.identity_tail and pd is not None and not pd.identity_tail
+    assert sum(p.numel() for p in m.parameters()) == sum(p.numel() for p in ref.parameters())     # the identity layer is not a parameter
+    x = torch.randn(300, 2, device="cuda")
+    eps = torch.randn(2, 300, m.latent_channel, device="cuda")
+    outs = []
+    for mm in (m, ref):
+        res = mm(x, L=2, eps=eps)
+        parts = mm.loss(x, *res)
+        parts[0].backward()
+        outs.append((res, parts))
+    for a, b, name in zip(outs[0][0], outs[1][0], ("recon", "mu", "log_var", "z", "z_recon")):
+        close_report(a.detach().cpu().numpy(), b.detach().cpu().numpy(), 5e-5, name)
+    for a, b, name in zip(outs[0][1], outs[1][1], ("total", "recon", "reg", "lr")):
+        assert abs(float(a) - float(b)) <= 1e-4 * max(1.0, abs(float(b))), name
+    gscale = max(float(q.grad.abs().max()) for q in ref.parameters())
+    for (k, a), (_, b) in zip(m.named_parameters(), ref.named_parameters()):
+        if bn_shadowed(k, m):
+            assert float(a.grad.abs().max()) <= 1e-4 * gscale, k
+        else:
+            close_report(a.grad.cpu().numpy(), b.grad.cpu().numpy(), 5e-4, "grad " + k, floor=1e-4 * gscale)
+    for (k, a), (_, b) in zip(m.named_buffers(), ref.named_buffers()):
+        close_report(a.float().cpu().numpy(), b.float().cpu().numpy(), 2e-5, "buffer " + k)

@@ -212,13 +212,31 @@ class FlexibleVAE(VAE):
         return nn.Sequential(*blocks)
 
     # ---- hot path ----
+    fused_mlp = True      # 1-D MLP stacks (Linear -> BatchNorm1d -> LeakyReLU chains) run through the fused layer kernels
+
+    def _stack_plan(self, name):
+        """Cached ops.MlpPlan of self.encoder / self.decoder, or None when the stack is not a plain MLP chain."""
+        seq = getattr(self, name)
+        cache = self.__dict__.setdefault("_mlp_plans", {})
+        plan = cache.get(name, False)
+        if plan is False or (plan is not None and not ops.mlp_plan_is_current(plan, seq)):
+            plan = ops.mlp_plan_from_modules(seq) if (self.data_type == "1d" and not self.residual_connection) else None
+            cache[name] = plan
+        return plan
+
+    def _run_stack(self, name, input):
+        plan = self._stack_plan(name) if (self.fused_mlp and input.is_cuda and input.dim() == 2) else None
+        if plan is not None and plan.linears[0].weight.device == input.device:
+            return ops.fused_mlp(plan, input, self.training)
+        return getattr(self, name)(input)
+
     def encode(self, input):
-        ret = self.encoder(input)
+        ret = self._run_stack("encoder", input)
         mu, log_var = ret.split(ret.shape[1] // 2, 1)
         return mu, log_var
 
     def decode(self, input):
-        return self.decoder(input)
+        return self._run_stack("decoder", input)
 
     def forward(self, input, latent_rand_sampling=True, L=1, eps=None):
         """-> (recon, mu, log_var, z_stack.detach() [L,B,D], z_recon_stack [L,B,D])   (model.py:418-447).

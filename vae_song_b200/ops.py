@@ -398,6 +398,59 @@ class MlpPlan:
         return MlpPlan(lin, bns, float(slopes[0]))
 
 
+def _leaf_modules(mod):
+    nn = torch.nn
+    if isinstance(mod, nn.Sequential):
+        out = []
+        for c in mod:
+            out += _leaf_modules(c)
+        return out
+    return [mod]
+
+
+def mlp_plan_from_modules(seq):
+    """MlpPlan for ANY nesting of Sequentials whose leaves read (Linear, BatchNorm1d, LeakyReLU)+ [Linear] -- the 1-D MLP
+    stacks of FlexibleVAE (model.py:186-208, 360-374: the encoder ENDS in BN + LeakyReLU, the decoder in a bare Linear) as
+    well as LIDVAE's encoder.  A stack without the trailing Linear gets a frozen identity layer appended (not registered
+    anywhere: act(BN(y)) . I + 0 is exact), so that the last BatchNorm + activation is applied by the same layer kernels.
+    Returns None when the modules do not match; `plan.source` holds the leaf identities for staleness checks."""
+    nn = torch.nn
+    leaves = _leaf_modules(seq)
+    mods = [m for m in leaves if not isinstance(m, nn.Flatten)]
+    lin, bns, slopes, i = [], [], [], 0
+    while i + 2 < len(mods) + 0 and isinstance(mods[i], nn.Linear) and isinstance(mods[i + 1], nn.BatchNorm1d) \
+            and isinstance(mods[i + 2], nn.LeakyReLU):
+        lin.append(mods[i]); bns.append(mods[i + 1]); slopes.append(mods[i + 2].negative_slope)
+        i += 3
+    rest = mods[i:]
+    if not lin or len(rest) > 1 or (rest and not isinstance(rest[0], nn.Linear)):
+        return None
+    identity = not rest
+    if identity:
+        w = lin[-1].out_features
+        tail = nn.Linear(w, w).to(lin[-1].weight.device)
+        with torch.no_grad():
+            tail.weight.copy_(torch.eye(w)); tail.bias.zero_()
+        tail.weight.requires_grad_(False); tail.bias.requires_grad_(False)
+        lin.append(tail)
+    else:
+        lin.append(rest[0])
+    ok_w = all(1 <= l.out_features <= 128 and (l.out_features & (l.out_features - 1)) == 0 for l in lin)
+    ok_w = ok_w and 1 <= lin[0].in_features <= 128
+    ok_bn = all(b.affine and b.track_running_stats and b.momentum is not None for b in bns)
+    if not (ok_w and ok_bn and len(set(slopes)) == 1 and all(l.bias is not None for l in lin)):
+        return None
+    plan = MlpPlan(lin, bns, float(slopes[0]))
+    plan.source = tuple(id(m) for m in leaves)
+    plan.identity_tail = identity
+    return plan
+
+
+def mlp_plan_is_current(plan, seq):
+    return plan is not None and getattr(plan, "source", None) == tuple(id(m) for m in _leaf_modules(seq)) \
+        and plan.linears[0].weight.device == plan.linears[-1].weight.device
+
+
 def _bn_group(bn):
     """Process group for cross-rank statistics (train.SyncBatchNorm1d carries one), or None for local BN."""
     import torch.distributed as dist
