@@ -1,5 +1,6 @@
 """BASELINE configs[0] (configs/config_pinwheel.yaml: pinwheel LR-VAE, 12 x 16 MLP encoder / decoder, batch 1024, staged
-backward of main.py:255-292): train-step time with the fused MLP layer kernels vs the same nn.Modules run by PyTorch."""
+backward of main.py:255-292): train-step time with the fused MLP layer kernels (opt-in, FlexibleVAE.fused_mlp) vs the same
+nn.Modules run by PyTorch (default).  The eager staged backward is host bound: the stock modules win here."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

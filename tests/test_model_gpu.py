@@ -347,7 +347,7 @@ def test_flexible_vae_fused_mlp_stacks_match_stock_modules(training):
                 mod.weight.uniform_(0.5, 1.5); mod.bias.uniform_(-0.5, 0.5)
                 mod.running_mean.uniform_(-0.2, 0.2); mod.running_var.uniform_(0.5, 1.5)
     ref = copy.deepcopy(m)
-    ref.fused_mlp = False
+    m.fused_mlp, ref.fused_mlp = True, False
     m.train(training); ref.train(training)
     pe, pd = m._stack_plan("encoder"), m._stack_plan("decoder")
     assert pe is not None and pe.identity_tail and pd is not None and not pd.identity_tail

@@ -212,7 +212,11 @@ class FlexibleVAE(VAE):
         return nn.Sequential(*blocks)
 
     # ---- hot path ----
-    fused_mlp = True      # 1-D MLP stacks (Linear -> BatchNorm1d -> LeakyReLU chains) run through the fused layer kernels
+    # 1-D MLP stacks (Linear -> BatchNorm1d -> LeakyReLU chains) CAN run through the fused layer kernels (set True).  Off by
+    # default: this family trains through main.py's staged, eagerly launched backward, which is HOST bound -- there the
+    # Python-side autograd.Function costs more than the launches it saves (scripts/c1_run.py: 19.5 vs 14.2 ms per step at
+    # batch 1024); it pays off when the step is replayed as a CUDA graph or the batch is large.
+    fused_mlp = False
 
     def _stack_plan(self, name):
         """Cached ops.MlpPlan of self.encoder / self.decoder, or None when the stack is not a plain MLP chain."""
