@@ -191,13 +191,19 @@ class DataParallelTrainer:
     kernel is used and there is no fallback)."""
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None,
-                 grad_clip=None, sync_bn=True, optimizer_step=None, comm="auto"):
+                 grad_clip=None, sync_bn=True, optimizer_step=None, comm="auto", staged_backward=False,
+                 forward_kwargs=None):
         """comm: "peer" = exchanges as kernels over NVLink peer memory (csrc/peer.cuh): BatchNorm statistics inside
         the fused encoder's finalize kernels, gradient all-reduce fused with Adam; "nccl" = torch.distributed
         collectives; "auto" = peer when CUDA IPC mapping works between all ranks, else nccl."""
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
         self.pg = process_group
+        # staged_backward: the three-pass backward of main.py:262-284 (latent-recon term first, encoder gradients scaled by
+        # 1e-4, then KL, then reconstruction) instead of one total.backward() -- no host sync in it, so the whole staged
+        # step still captures into one CUDA graph (the reference's LR-VAE loop is otherwise host bound at its batch sizes)
+        self.staged = bool(staged_backward)
+        self.forward_kwargs = dict(forward_kwargs or {})       # e.g. {"L": 4}: num_mc_samples of main.py:259
         if self.world > 1 and sync_bn:
             model = convert_sync_batchnorm(model, process_group)
         self.model = model
@@ -285,14 +291,21 @@ class DataParallelTrainer:
     def step(self, x_local, eps_local=None):
         model, W = self.model, self.world
         self.fp.begin_step()
-        kw = {} if eps_local is None else {"eps": eps_local}
+        kw = dict(self.forward_kwargs)
+        if eps_local is not None:
+            kw["eps"] = eps_local
         out = model(x_local, **kw)
         total, rec, reg, lr_term = model.loss(x_local, *out)
-        if W > 1 and torch.is_tensor(lr_term) and lr_term.requires_grad:
-            # latent-recon term sums over the batch (Appendix B.2): global value = SUM over ranks, while
-            # every other term is a batch mean -> compensate before the 1/W gradient averaging
-            total = total + (W - 1) * lr_term
-        total.backward()
+        lr_attached = torch.is_tensor(lr_term) and lr_term.requires_grad
+        if self.staged:
+            from .main import staged_backward
+            # the latent-recon term sums over the batch (Appendix B.2): its global value is the SUM over ranks
+            staged_backward(model, total, rec, reg, lr_term * W if (W > 1 and lr_attached) else lr_term)
+        else:
+            if W > 1 and lr_attached:
+                # ... while every other term is a batch mean -> compensate before the 1/W gradient averaging
+                total = total + (W - 1) * lr_term
+            total.backward()
         self.fp.gather()
         clip = bool(self.grad_clip and self.grad_clip.get("enabled", False))
         if self.peer is not None and not clip:
@@ -302,7 +315,7 @@ class DataParallelTrainer:
             ops.peer_allreduce_adam_(self.peer, self._adam_slot, self._peer_bufs[1], self._peer_bufs[0], self.m, self.v,
                                      self.fp.flat.numel(), self.t_dev, self.hp["lr"], self.hp["betas"], self.hp["eps"],
                                      self.hp["weight_decay"], 1.0 / W)
-            return total.detach(), rec, reg
+            return total.detach(), (rec.detach() if torch.is_tensor(rec) else rec), (reg.detach() if torch.is_tensor(reg) else reg)
         if W > 1:
             dist.all_reduce(self.fp.grad, op=dist.ReduceOp.SUM, group=self.pg)
         scale = 1.0 / W
@@ -312,7 +325,7 @@ class DataParallelTrainer:
             apply_grad_clip(model, self.grad_clip)
         self.t += 1
         self._opt(self.fp.flat, self.fp.grad, self.m, self.v, self.t, scale, self.hp)
-        return total.detach(), rec, reg
+        return total.detach(), (rec.detach() if torch.is_tensor(rec) else rec), (reg.detach() if torch.is_tensor(reg) else reg)
 
     def check(self):
         """Raise if a peer-memory exchange on this rank ever timed out (synchronises; call outside timed regions)."""
