@@ -68,6 +68,18 @@ class VAE(nn.Module):
         super().__init__()
         self.last_kl_loss = 0.0
 
+    # model.py:606 stores `loss_reg.item()` every step (one host sync per step, only ever read by the kl_adaptive warm-up once
+    # per epoch).  Here the device scalar is kept and converted when somebody reads it, so the train step stays free of
+    # host synchronisation (and capturable into a CUDA graph).
+    @property
+    def last_kl_loss(self):
+        v = self.__dict__.get("_last_kl", 0.0)
+        return float(v) if torch.is_tensor(v) else v
+
+    @last_kl_loss.setter
+    def last_kl_loss(self, v):
+        self.__dict__["_last_kl"] = v
+
     def encode(self, input):
         raise NotImplementedError
 
@@ -291,7 +303,7 @@ class LRVAE(FlexibleVAE):
             mu_zp = z_input.mean(dim=1, keepdim=True)
             logvar_zp = torch.log(((z_input - mu_zp) ** 2).mean(dim=1))
             reg = reg / 2.0 + (-0.5 * (1 + logvar_zp - mu_zp ** 2 - logvar_zp.exp())).mean(dim=1).sum() / 2.0
-        self.last_kl_loss = float(reg.detach())
+        self.last_kl_loss = reg.detach()      # device scalar; converted on access (no host sync in the step)
         w = self.alpha * self.wu_alpha
         return rec + reg * self.beta + lr * w, rec, reg * self.beta, lr * w
 
@@ -562,6 +574,6 @@ class SetLRVAE(SetVAE):
         rec = chamfer_distance(output, input)
         # [B,D] latents: dim 0 of the latent-recon mean is the batch here (no L axis); the fused kernel's Lz = B
         _, reg, lr = _vae_losses(None, None, mu, log_var, z_input, z_recon, False)
-        self.last_kl_loss = float(reg.detach())
+        self.last_kl_loss = reg.detach()      # device scalar; converted on access (no host sync in the step)
         w = self.alpha * self.wu_alpha
         return rec + self.beta * reg + w * lr, rec.detach(), (self.beta * reg).detach(), (w * lr).detach()
