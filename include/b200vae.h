@@ -139,6 +139,13 @@ int b200vae_adam_step_dev(float* param, const float* grad, float* m, float* v, l
                           float beta1, float beta2, float eps, float weight_decay, long long* step_dev,
                           float grad_scale, void* stream);
 
+/* Same, with the learning rate following a schedule evaluated ON THE DEVICE from the step counter (graph replay needs no
+ * host-side scheduler): sched_kind 0 = constant lr0, 1 = CosineAnnealingLR(T_max = sched_T, eta_min = 0) stepped after
+ * every optimiser step -- main.py:200-203, 286-287. */
+int b200vae_adam_step_sched(float* param, const float* grad, float* m, float* v, long long n, float lr0, float beta1,
+                            float beta2, float eps, float weight_decay, long long* step_dev, float grad_scale,
+                            int sched_kind, long long sched_T, void* stream);
+
 /* ---- fused [Linear -> BatchNorm1d -> LeakyReLU] encoder layers (model.py:711-734) ------------
  * Widths <= 128 (backward: powers of two).  A layer INPUT is described by the previous layer's pre-BN output
  * `*_y` [B,w] plus its BatchNorm statistics `*_stats` [4][w] = (mean, biased var, invstd, count), gamma, beta; the

@@ -25,7 +25,7 @@ _ERR = {-1: "bad shape", -2: "unsupported configuration", -3: "null or misaligne
 EXPORTS = [
     "b200vae_icnn_workspace_bytes", "b200vae_icnn_prepare", "b200vae_icnn_decode_fwd", "b200vae_icnn_decode_bwd",
     "b200vae_loss_fwd", "b200vae_loss_bwd", "b200vae_lipschitz_pairs", "b200vae_lipschitz_allpairs",
-    "b200vae_lipschitz_num_tiles", "b200vae_adam_step", "b200vae_adam_step_dev", "b200vae_mlp_scratch_bytes", "b200vae_mlp_layer_fwd",
+    "b200vae_lipschitz_num_tiles", "b200vae_adam_step", "b200vae_adam_step_dev", "b200vae_adam_step_sched", "b200vae_mlp_scratch_bytes", "b200vae_mlp_layer_fwd",
     "b200vae_mlp_layer_bwd_reduce", "b200vae_mlp_layer_bwd", "b200vae_nn_sqdist_fwd", "b200vae_nn_sqdist_bwd", "b200vae_last_cuda_error", "b200vae_version",
     "b200vae_launch_count",
     "b200vae_peer_exchange_bytes", "b200vae_peer_num_slots", "b200vae_peer_max_payload", "b200vae_peer_alloc", "b200vae_peer_open",
@@ -102,6 +102,8 @@ def load():
     lib.b200vae_adam_step.argtypes = [vp, vp, vp, vp, ll, f, f, f, f, f, ll, f, vp]
     lib.b200vae_adam_step_dev.restype = i
     lib.b200vae_adam_step_dev.argtypes = [vp, vp, vp, vp, ll, f, f, f, f, f, vp, f, vp]
+    lib.b200vae_adam_step_sched.restype = i
+    lib.b200vae_adam_step_sched.argtypes = [vp, vp, vp, vp, ll, f, f, f, f, f, vp, f, i, ll, vp]
     lib.b200vae_mlp_scratch_bytes.restype = sz
     lib.b200vae_mlp_scratch_bytes.argtypes = [i]
     lib.b200vae_mlp_layer_fwd.restype = i

@@ -187,11 +187,19 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 // graph-capturable variant: the step counter lives on the device (incremented here by block 0 *after* every
 // block has read it is not possible without a grid sync, so a 1-thread tick kernel runs first)
 __global__ void adam_tick_kernel(long long* step) { *step += 1; }
+// lr of torch.optim.lr_scheduler.CosineAnnealingLR(T_max, eta_min = 0) at 0-based scheduler step k = *step - 1 (main.py:201-203:
+// scheduler.step() after every optimizer.step()), closed form: lr0 * (1 + cos(pi k / T)) / 2
+__device__ __forceinline__ float sched_lr(float lr0, int kind, long long T, long long step1) {
+  if (kind != 1 || T <= 0) return lr0;
+  const double k = (double)(step1 - 1);
+  return (float)(0.5 * (double)lr0 * (1.0 + cos(3.14159265358979323846 * k / (double)T)));
+}
 __global__ void __launch_bounds__(256)
 adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                long long n, float lr, float b1, float b2, float eps, float wd, const long long* __restrict__ step,
-                float gscale) {
+                long long n, float lr0, float b1, float b2, float eps, float wd, const long long* __restrict__ step,
+                float gscale, int sched_kind, long long sched_T) {
   const double t = (double)*step;
+  const float lr = sched_lr(lr0, sched_kind, sched_T, *step);
   const float bc1 = (float)(1.0 - pow((double)b1, t));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
   const long long gstride = (long long)gridDim.x * blockDim.x;
@@ -282,6 +290,21 @@ extern "C" int b200vae_adam_step_dev(float* param, const float* grad, float* m, 
   int rc = check_launch();
   if (rc) return rc;
   adam_dev_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, lr, beta1, beta2, eps, weight_decay,
-                                                                step_dev, grad_scale);
+                                                                step_dev, grad_scale, 0, 0);
+  return check_launch();
+}
+
+extern "C" int b200vae_adam_step_sched(float* param, const float* grad, float* m, float* v, long long n, float lr0,
+                                       float beta1, float beta2, float eps, float weight_decay, long long* step_dev,
+                                       float grad_scale, int sched_kind, long long sched_T, void* stream) {
+  if (!param || !grad || !m || !v || !step_dev) return B200VAE_EALIGN;
+  if (n <= 0 || sched_kind < 0 || sched_kind > 1) return B200VAE_ESHAPE;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  int rc = check_launch();
+  if (rc) return rc;
+  adam_dev_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, lr0, beta1, beta2, eps, weight_decay,
+                                                                step_dev, grad_scale, sched_kind, sched_T);
   return check_launch();
 }

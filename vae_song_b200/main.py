@@ -128,8 +128,13 @@ def evaluate(model, loader, device, num_mc_samples=1):
 
 def train_and_test(model, epochs=100, batch_size=128, device="cuda", dataset_name="mnist", logfilename="log.csv",
                    resultname="res", pt_param=None, num_mc_samples=1, grad_clip=None, wu_strat="linear",
-                   loader_train=None, loader_test=None, result_root="./results", dataset_params=None, num_workers=0):
-    """main.py:174-393.  Returns {'train': [[loss, recon, reg, lr] per epoch], 'test': [...], 'name': run name}."""
+                   loader_train=None, loader_test=None, result_root="./results", dataset_params=None, num_workers=0,
+                   graph=False):
+    """main.py:174-393.  Returns {'train': [[loss, recon, reg, lr] per epoch], 'test': [...], 'name': run name}.
+
+    graph=True: the same step (forward, staged backward, clipping, Adam, cosine schedule) captured ONCE into a CUDA graph
+    and replayed (train.DataParallelTrainer): the warm-up factor and the learning rate live on the device, so no host
+    work remains per step -- these small models are otherwise bound by ~1500 eager launches per step."""
     if loader_train is None:
         dp = dataset_params or {}
         tr, te = synthetic_dataset(dataset_name, dp.get("n_train", 10000), dp.get("n_test", 2000), dp.get("seed", 42),
@@ -158,13 +163,26 @@ def train_and_test(model, epochs=100, batch_size=128, device="cuda", dataset_nam
     out_dir = os.path.join(result_root, resultname, name)
     os.makedirs(os.path.join(out_dir, "params"), exist_ok=True)
     history = {"name": name, "train": [], "test": []}
+    trainer = None
+    if graph:
+        from .train import DataParallelTrainer
+        model.train()
+        model.graph_scalars(device)
+        trainer = DataParallelTrainer(model, lr=1e-2, grad_clip=grad_clip, staged_backward=True,
+                                      forward_kwargs={"L": num_mc_samples},
+                                      lr_schedule=("cosine", max(epochs * len(loader_train), 1)))
+        trainer.capture(next(iter(loader_train))[0].to(device))
     for epoch in range(epochs):
         model.train()
         model.warmup(epoch=epoch, max_epoch=epochs, wu_strat=wu_strat)
         tot, nb = torch.zeros(4, device=device), 0
         for x, _ in loader_train:
             x = x.to(device, non_blocking=True)
-            tot += train_step(model, x, optimizer, scheduler, num_mc_samples, grad_clip)
+            if trainer is not None:
+                trainer.step_graphed(x)
+                tot += torch.stack([p.reshape(()).float() for p in trainer.last_parts])
+            else:
+                tot += train_step(model, x, optimizer, scheduler, num_mc_samples, grad_clip)
             nb += 1
         history["train"].append((tot / max(nb, 1)).tolist())                             # one sync per epoch
         if loader_test is not None:
@@ -222,7 +240,7 @@ def iter_models(config):
             raise ValueError(f"unknown experiment_type {exp_type!r}")
 
 
-def run_experiment(config_path, device="cuda", epochs=None, result_root="./results", dataset_params=None):
+def run_experiment(config_path, device="cuda", epochs=None, result_root="./results", dataset_params=None, graph=False):
     config = load_config(config_path) if isinstance(config_path, (str, os.PathLike)) else config_path
     cp, mp = config["common_params"], config["model_params"]
     res_tag = "_res" if mp.get("residual_connection", False) else ""
@@ -233,7 +251,8 @@ def run_experiment(config_path, device="cuda", epochs=None, result_root="./resul
     for tag, model, kw in iter_models(config):
         if epochs is not None:
             kw = {**kw, "epochs": epochs}
-        out[tag] = train_and_test(model, device=device, resultname=resultname, result_root=result_root, dataset_params=dp, **kw)
+        out[tag] = train_and_test(model, device=device, resultname=resultname, result_root=result_root, dataset_params=dp,
+                                  graph=graph, **kw)
     return out
 
 
@@ -243,8 +262,9 @@ def main(argv=None):
     ap.add_argument("--device", default="cuda")
     ap.add_argument("--epochs", type=int, default=None, help="override common_params.exp_epochs")
     ap.add_argument("--result_root", default="./results")
+    ap.add_argument("--graph", action="store_true", help="replay the whole train step as one CUDA graph")
     args = ap.parse_args(argv)
-    res = run_experiment(args.config, device=args.device, epochs=args.epochs, result_root=args.result_root)
+    res = run_experiment(args.config, device=args.device, epochs=args.epochs, result_root=args.result_root, graph=args.graph)
     for tag, h in res.items():
         print(tag, "final train [loss, recon, reg, lr] =", h["train"][-1] if h["train"] else None)
     return res

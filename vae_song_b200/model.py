@@ -80,6 +80,35 @@ class VAE(nn.Module):
     def last_kl_loss(self, v):
         self.__dict__["_last_kl"] = v
 
+    # wu_alpha (the warm-up factor of the latent-recon term, model.py:37-63) is a Python float in the reference.  It stays
+    # one here, but once `graph_scalars(device)` was called it is MIRRORED into a device scalar that the losses multiply
+    # with, so that a CUDA graph captured once follows the per-epoch warm-up instead of baking the value in.  Classes that
+    # never set it (LIDVAE, like the reference) have no such attribute: hasattr(model, "wu_alpha") is False for them.
+    @property
+    def wu_alpha(self):
+        try:
+            return self.__dict__["_wu_alpha"]
+        except KeyError:
+            raise AttributeError("wu_alpha") from None
+
+    @wu_alpha.setter
+    def wu_alpha(self, v):
+        self.__dict__["_wu_alpha"] = float(v)
+        dev = self.__dict__.get("_wu_dev")
+        if dev is not None:
+            dev.fill_(float(v))
+
+    def graph_scalars(self, device):
+        """Keep the warm-up factor on `device` as well (see wu_alpha); call before capturing the step into a CUDA graph."""
+        if "_wu_alpha" in self.__dict__:
+            self.__dict__["_wu_dev"] = torch.full((), self.__dict__["_wu_alpha"], dtype=torch.float32, device=device)
+        return self
+
+    def _lr_weight(self):
+        """alpha * wu_alpha as the losses use it: a float, or a device scalar after graph_scalars()."""
+        dev = self.__dict__.get("_wu_dev")
+        return self.alpha * (dev if dev is not None else self.wu_alpha)
+
     def encode(self, input):
         raise NotImplementedError
 
@@ -304,7 +333,7 @@ class LRVAE(FlexibleVAE):
             logvar_zp = torch.log(((z_input - mu_zp) ** 2).mean(dim=1))
             reg = reg / 2.0 + (-0.5 * (1 + logvar_zp - mu_zp ** 2 - logvar_zp.exp())).mean(dim=1).sum() / 2.0
         self.last_kl_loss = reg.detach()      # device scalar; converted on access (no host sync in the step)
-        w = self.alpha * self.wu_alpha
+        w = self._lr_weight()
         return rec + reg * self.beta + lr * w, rec, reg * self.beta, lr * w
 
 
@@ -575,5 +604,5 @@ class SetLRVAE(SetVAE):
         # [B,D] latents: dim 0 of the latent-recon mean is the batch here (no L axis); the fused kernel's Lz = B
         _, reg, lr = _vae_losses(None, None, mu, log_var, z_input, z_recon, False)
         self.last_kl_loss = reg.detach()      # device scalar; converted on access (no host sync in the step)
-        w = self.alpha * self.wu_alpha
+        w = self._lr_weight()
         return rec + self.beta * reg + w * lr, rec.detach(), (self.beta * reg).detach(), (w * lr).detach()

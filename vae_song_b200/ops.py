@@ -705,6 +705,15 @@ def adam_step_dev_(param, grad, m, v, step_dev, lr=1e-3, betas=(0.9, 0.999), eps
                                              _ptr(step_dev), float(grad_scale), _stream()), "adam_step_dev")
 
 
+def adam_step_sched_(param, grad, m, v, step_dev, lr0, betas, eps, weight_decay, grad_scale, sched_kind, sched_T):
+    """adam_step_dev_ with the learning rate computed on the device from the step counter (0 constant, 1 cosine annealing
+    to 0 over sched_T steps: main.py:200-203)."""
+    _C.check(_C.load().b200vae_adam_step_sched(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), float(lr0),
+                                               float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                               _ptr(step_dev), float(grad_scale), int(sched_kind), int(sched_T), _stream()),
+             "adam_step_sched")
+
+
 def peer_allreduce_adam_(comm, slot, grad_buf, param_buf, m, v, n, step_dev, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
                          weight_decay=0.0, grad_scale=1.0):
     """Gradient all-reduce fused with Adam over peer memory (include/b200vae.h b200vae_peer_allreduce_adam).

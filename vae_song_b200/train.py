@@ -192,7 +192,7 @@ class DataParallelTrainer:
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None,
                  grad_clip=None, sync_bn=True, optimizer_step=None, comm="auto", staged_backward=False,
-                 forward_kwargs=None):
+                 forward_kwargs=None, lr_schedule=None):
         """comm: "peer" = exchanges as kernels over NVLink peer memory (csrc/peer.cuh): BatchNorm statistics inside
         the fused encoder's finalize kernels, gradient all-reduce fused with Adam; "nccl" = torch.distributed
         collectives; "auto" = peer when CUDA IPC mapping works between all ranks, else nccl."""
@@ -204,6 +204,11 @@ class DataParallelTrainer:
         # step still captures into one CUDA graph (the reference's LR-VAE loop is otherwise host bound at its batch sizes)
         self.staged = bool(staged_backward)
         self.forward_kwargs = dict(forward_kwargs or {})       # e.g. {"L": 4}: num_mc_samples of main.py:259
+        # lr_schedule = ("cosine", T_max): CosineAnnealingLR stepped after every optimiser step (main.py:201-203, 287),
+        # evaluated on the device from the step counter so that graph replay follows it (single-GPU / NCCL path)
+        if lr_schedule is not None and (lr_schedule[0] != "cosine" or int(lr_schedule[1]) <= 0):
+            raise ValueError("lr_schedule must be None or ('cosine', T_max > 0)")
+        self.lr_schedule = None if lr_schedule is None else ("cosine", int(lr_schedule[1]))
         if self.world > 1 and sync_bn:
             model = convert_sync_batchnorm(model, process_group)
         self.model = model
@@ -211,7 +216,7 @@ class DataParallelTrainer:
         on_cuda = next(model.parameters()).is_cuda
         if comm not in ("auto", "peer", "nccl"):
             raise ValueError(f"comm must be auto|peer|nccl, got {comm!r}")
-        if self.world > 1 and on_cuda and comm != "nccl" and optimizer_step is None:
+        if self.world > 1 and on_cuda and comm != "nccl" and optimizer_step is None and lr_schedule is None:
             from . import peer as _peer
             self.peer = _peer.PeerComm(process_group) if comm == "peer" else _peer.try_create(process_group)
         self._peer_bufs = None
@@ -248,7 +253,11 @@ class DataParallelTrainer:
 
     def _fused_adam(self, flat, grad, m, v, t, scale, hp):
         # step count kept on the device so that the call is identical every step (CUDA-graph capturable)
-        ops.adam_step_dev_(flat, grad, m, v, self.t_dev, hp["lr"], hp["betas"], hp["eps"], hp["weight_decay"], scale)
+        if self.lr_schedule is None:
+            ops.adam_step_dev_(flat, grad, m, v, self.t_dev, hp["lr"], hp["betas"], hp["eps"], hp["weight_decay"], scale)
+        else:
+            ops.adam_step_sched_(flat, grad, m, v, self.t_dev, hp["lr"], hp["betas"], hp["eps"], hp["weight_decay"], scale, 1,
+                                 self.lr_schedule[1])
 
     # ---- whole-step CUDA graph (launch-bound regimes: small batches, multi-GPU with many tiny collectives) ----
     def capture(self, x_example, eps_example=None, warmup=3):
@@ -296,6 +305,8 @@ class DataParallelTrainer:
             kw["eps"] = eps_local
         out = model(x_local, **kw)
         total, rec, reg, lr_term = model.loss(x_local, *out)
+        det = lambda t: t.detach() if torch.is_tensor(t) else torch.as_tensor(float(t), device=x_local.device)
+        self.last_parts = (det(total), det(rec), det(reg), det(lr_term))     # static tensors under graph replay
         lr_attached = torch.is_tensor(lr_term) and lr_term.requires_grad
         if self.staged:
             from .main import staged_backward
