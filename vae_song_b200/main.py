@@ -180,7 +180,8 @@ def train_and_test(model, epochs=100, batch_size=128, device="cuda", dataset_nam
             x = x.to(device, non_blocking=True)
             if trainer is not None:
                 trainer.step_graphed(x)
-                tot += torch.stack([p.reshape(()).float() for p in trainer.last_parts])
+                tot += torch.stack([p.reshape(()).float() if torch.is_tensor(p) else torch.full((), p, device=device)
+                                    for p in trainer.last_parts])
             else:
                 tot += train_step(model, x, optimizer, scheduler, num_mc_samples, grad_clip)
             nb += 1

@@ -305,8 +305,8 @@ class DataParallelTrainer:
             kw["eps"] = eps_local
         out = model(x_local, **kw)
         total, rec, reg, lr_term = model.loss(x_local, *out)
-        det = lambda t: t.detach() if torch.is_tensor(t) else torch.as_tensor(float(t), device=x_local.device)
-        self.last_parts = (det(total), det(rec), det(reg), det(lr_term))     # static tensors under graph replay
+        det = lambda t: t.detach() if torch.is_tensor(t) else float(t)
+        self.last_parts = (det(total), det(rec), det(reg), det(lr_term))     # tensors are static under graph replay
         lr_attached = torch.is_tensor(lr_term) and lr_term.requires_grad
         if self.staged:
             from .main import staged_backward
