@@ -150,8 +150,11 @@ def test_graph_mode_follows_the_eager_loop(tmp_path):
                                        resultname="g%d" % graph, graph=graph)
     a, b = np.array(hist[False]["train"]), np.array(hist[True]["train"])
     assert a.shape == b.shape == (4, 4) and np.isfinite(b).all()
-    # the eps draws differ between the two runs (capture consumes warm-up draws), so compare the trend, not bit patterns:
-    # both must learn (loss falls) and end within a few percent of each other
-    assert b[-1, 0] < b[0, 0] and a[-1, 0] < a[0, 0]
-    assert abs(b[-1, 0] - a[-1, 0]) <= 0.15 * abs(a[-1, 0]), (a[:, 0], b[:, 0])
-    assert b[0, 3] != b[-1, 3]        # the latent-recon weight followed the warm-up inside the replayed graph
+    # the eps draws differ between the two runs (capture consumes warm-up draws), so the per-epoch means agree up to
+    # sampling noise, not bitwise: reconstruction and KL parts of every epoch within 20 %
+    np.testing.assert_allclose(b[:, 1], a[:, 1], rtol=0.2, err_msg=f"recon per epoch: eager {a[:, 1]} graph {b[:, 1]}")
+    np.testing.assert_allclose(b[:, 2], a[:, 2], rtol=0.2, err_msg=f"KL per epoch: eager {a[:, 2]} graph {b[:, 2]}")
+    assert a[-1, 1] < a[0, 1] and b[-1, 1] < b[0, 1], (a[:, 1], b[:, 1])          # both learn to reconstruct
+    # the latent-recon weight follows the linear warm-up INSIDE the replayed graph: weighted term / weight ~ comparable,
+    # and the weighted term itself grows with the epochs like in the eager loop
+    np.testing.assert_allclose(b[:, 3], a[:, 3], rtol=0.3, err_msg=f"alpha*wu*lr per epoch: eager {a[:, 3]} graph {b[:, 3]}")
