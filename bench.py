@@ -474,6 +474,16 @@ def run_ours(args, rank, local_rank, world):
                 "algorithmic_flop_per_sample": vutils.flops_decode(2, 1024),
                 "note": "achieved = algorithmic flops / CUDA-event time; tf32x3 executes 3 MMAs per algorithmic MAC, "
                         "fp32 is the SIMT parity path (FP32 FMA peak 74.4 TFLOP/s at 1965 MHz)"}
+        # the SAME kernel in the arithmetic mode the timed step ran in (tf32x3 executes 3 MMAs per MAC in GEMM1 and 2 in GEMM2,
+        # whose generated operand is exact in tf32: 2.5 executed flops per algorithmic flop)
+        sp = args.precision
+        mult = {"fp32": 1.0, "tf32": 1.0, "tf32x3": 2.5}[sp]
+        sp_peak = 74.4 if sp == "fp32" else pk["bf16_tflops"] / 2
+        roof["step_precision_kernel"] = {
+            "precision": sp, "kernel_ms": byp[sp]["decode_ms_H1024"], "achieved": byp[sp]["tflops_H1024"],
+            "executed": byp[sp]["tflops_H1024"] * mult, "peak": sp_peak, "unit": "TFLOP/s",
+            "frac": byp[sp]["tflops_H1024"] / sp_peak, "frac_executed": byp[sp]["tflops_H1024"] * mult / sp_peak,
+            "bound": "fp32 fma pipe" if sp == "fp32" else "tensor"}
         extra = {"decode_by_precision": byp, "train_step_by_precision": by_prec_train,
                  "pytorch_eager_same_gpu": eager_same_gpu(m, dev_pool[0], flush) if world == 1 else None,
                  "lipschitz_estimator": lipschitz_times(m, dev),
