@@ -866,233 +866,6 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
   tc_teardown(tmem_base);
 }
 
-// ------------------------------------------------------------------------------ dP0, n-stationary variant (default)
-// The same product with the operand ROLES SWAPPED: the EXPENSIVE operand q1 (packed FMAs, tf32 hi/lo split) becomes the
-// MMA's A operand -- M = 128 n's per CTA -- and the CHEAP one (the exact 1 + 4*bit slope pattern) its B operand, N = 2 x 256
-// o's, so one generated q1 element feeds 512 MACs instead of 256 (the kernel above is bound by generating operands, not by
-// the tensor pipe).  D[n][o] sits in TMEM as two 128 x 256 accumulators (all 512 columns); the epilogue's thread = n lane
-// writes dP0part[split][o][n] column by column: 32 lanes -> 32 consecutive n -> one coalesced 128-byte store.
-// Stage = q1 tile [16 k][128 n] (hi [, lo]: SBO = 2 KB) + two bit tiles [16 k][256 o] (SBO = 4 KB), MN-major SWIZZLE_128B.
-constexpr int kDwN = 128, kDwO = 512;
-__device__ __forceinline__ uint64_t make_desc_mn_sw128_sbo(uint32_t saddr, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
-}
-template <bool X3>
-struct DwCfg {
-  static constexpr int S = X3 ? 3 : 4;
-  static constexpr int kQBytes = 16 * kDwN * 4;                       // 8 KB: one q1 tile
-  static constexpr int kOffQlo = kQBytes, kOffO = (X3 ? 2 : 1) * kQBytes;
-  static constexpr int kStage = kOffO + 2 * kTileBytes;               // 40 KB / 48 KB (multiples of 1 KB: atom aligned)
-};
-template <int D, bool X3>
-constexpr size_t dw_smem_bytes() {
-  return (size_t)DwCfg<X3>::S * DwCfg<X3>::kStage + (size_t)2 * 256 * (2 * D + 1) * 4 + 2 * 16 * 256 * 4 +
-         (2 * DwCfg<X3>::S + 1) * 8 + 16 + 1024;
-}
-
-template <int D, bool X3>
-__global__ void __launch_bounds__(kDpThreads, 1)
-icnn_tc_dP0w_kernel(const float* __restrict__ z, const float* __restrict__ v, const uint32_t* __restrict__ mask1,
-                    const uint8_t* __restrict__ mask2, int B, int Hq, int Hw_in, int rows_per_split,
-                    const float4* __restrict__ A0q_g, float* __restrict__ dP0part) {
-  using C = DwCfg<X3>;
-  constexpr int S = C::S;
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* samp = reinterpret_cast<float*>(stages + S * C::kStage);           // [2][2D+1][256]  z, v, s2 per sample
-  uint32_t* sampw = reinterpret_cast<uint32_t*>(samp + 2 * 256 * (2 * D + 1));   // [2][16][256] mask words of the 512 o's
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sampw + 2 * 16 * 256);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-  const int n0 = blockIdx.x * kDwN, o0 = blockIdx.y * kDwO, split = blockIdx.z;
-  const bool two = o0 + 256 < Hq;                            // Hq is a multiple of 256: the last o-tile may be half
-  const int b0 = split * rows_per_split;
-  const int b1 = min(B, b0 + rows_per_split);
-  const int NKB = (max(b1 - b0, 0) + kKB - 1) / kKB;
-
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, kNW); mbar_init(empty0 + 8 * s, 1); }
-    mbar_init(accfull, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == kNW) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp_u < kNW) {
-    const int ks = tid & 15, u = tid >> 4;                   // sample-in-stage, unit 0..31
-    const int g4 = ks >> 2, kr = ks & 3;                     // group of 4 k, k-row inside the atom
-    // q1: my 4 n's = 32-wide block u>>3, 8-wide quarter (u>>1)&3, half u&1  (two packed pairs)
-    const int qblk = u >> 3, qqd = (u >> 1) & 3, qhf = u & 1;
-    float2 qx2[2], qy2[2], qz2[2], qw2[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int n = n0 + qblk * 32 + qqd * 8 + qhf * 4 + 2 * i;
-      const float4 qa = A0q_g[n], qb = A0q_g[n + 1];
-      qx2[i] = make_float2(qa.x, qb.x); qy2[i] = make_float2(qa.y, qb.y);
-      qz2[i] = make_float2(qa.z, qb.z); qw2[i] = make_float2(qa.w, qb.w);
-    }
-    const uint32_t offQ = (uint32_t)((g4 * 4 + qblk) * 512 + kr * 128) + ((uint32_t)(qqd ^ kr) << 5) + (uint32_t)(qhf * 16);
-    // bits: 8 o's in each of the two 256-wide tiles: block u>>2, quarter u&3
-    const int oblk = u >> 2, oqd = u & 3;
-    const uint32_t offO = (uint32_t)C::kOffO + (uint32_t)((g4 * 8 + oblk) * 512 + kr * 128) + ((uint32_t)(oqd ^ kr) << 5);
-    constexpr int CH = 256, ZV = 2 * D + 1;
-    const int nchunk = (NKB * kKB + CH - 1) / CH;
-    float pre_f[ZV];
-    uint32_t pre_w[8];
-    auto fetch = [&](int c) {                                // thread -> sample (tid&255), word half (tid>>8)
-      const int mrow = b0 + c * CH + (tid & 255);
-      const bool in = mrow < b1;
-      if (tid < CH) {
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-          pre_f[j] = in ? __ldg(z + (size_t)mrow * D + j) : 0.f;
-          pre_f[D + j] = in ? __ldg(v + (size_t)mrow * D + j) : 0.f;
-        }
-        pre_f[2 * D] = in ? (__ldg(mask2 + mrow) ? 1.f : kSlope) : 0.f;
-      }
-      const int w0 = (o0 >> 5) + (tid >> 8) * 8;
-#pragma unroll
-      for (int q8 = 0; q8 < 8; ++q8) pre_w[q8] = (in && w0 + q8 < Hw_in) ? __ldg(mask1 + (size_t)mrow * Hw_in + w0 + q8) : 0u;
-    };
-    auto stash = [&](int buf) {
-      float* zf = samp + buf * (CH * ZV);
-      uint32_t* mw = sampw + buf * (CH * 16);
-      if (tid < CH) {
-#pragma unroll
-        for (int j = 0; j < ZV; ++j) zf[j * CH + tid] = pre_f[j];
-      }
-#pragma unroll
-      for (int q8 = 0; q8 < 8; ++q8) mw[((tid >> 8) * 8 + q8) * CH + (tid & 255)] = pre_w[q8];
-    };
-    if (nchunk > 0) { fetch(0); stash(0); }
-    worker_bar();
-    for (int kb = 0; kb < NKB; ++kb) {
-      const int c = kb >> 4, buf = c & 1, sl = (kb & 15) * kKB + ks;
-      if ((kb & 15) == 0 && c + 1 < nchunk) fetch(c + 1);
-      const float* zf = samp + buf * (CH * ZV);
-      float zr[D], vr[D];
-#pragma unroll
-      for (int j = 0; j < D; ++j) { zr[j] = zf[j * CH + sl]; vr[j] = zf[(D + j) * CH + sl]; }
-      const float s2f = zf[2 * D * CH + sl];
-      const uint32_t bits0 = sampw[buf * (CH * 16) + oblk * CH + sl] >> (oqd * 8);
-      const uint32_t bits1 = sampw[buf * (CH * 16) + (8 + oblk) * CH + sl] >> (oqd * 8);
-      // A (M side) = s2 q1 = (2 s2 A0 v) . max(h0, 0.04 h0) for my 4 n's; B (N side) = 1 + 4*bit for my 2 x 8 o's
-      float bv[4];
-      float sv[D];
-#pragma unroll
-      for (int j = 0; j < D; ++j) sv[j] = (2.f * s2f) * vr[j];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        float2 h = __ffma2_rn(qx2[i], make_float2(zr[0], zr[0]), qw2[i]);
-        float2 uu = __fmul2_rn(qx2[i], make_float2(sv[0], sv[0]));
-        if (D > 1) {
-          h = __ffma2_rn(qy2[i], make_float2(zr[D > 1 ? 1 : 0], zr[D > 1 ? 1 : 0]), h);
-          uu = __ffma2_rn(qy2[i], make_float2(sv[D > 1 ? 1 : 0], sv[D > 1 ? 1 : 0]), uu);
-        }
-        if (D > 2) {
-          h = __ffma2_rn(qz2[i], make_float2(zr[D > 2 ? 2 : 0], zr[D > 2 ? 2 : 0]), h);
-          uu = __ffma2_rn(qz2[i], make_float2(sv[D > 2 ? 2 : 0], sv[D > 2 ? 2 : 0]), uu);
-        }
-        const float2 l = __fmul2_rn(h, make_float2(kSlope * kSlope, kSlope * kSlope));
-        const float2 x = __fmul2_rn(uu, make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y)));
-        bv[2 * i] = x.x; bv[2 * i + 1] = x.y;
-      }
-      if ((kb & 15) == 15 && c + 1 < nchunk) {               // next chunk's buffer was last read 16 stages ago
-        worker_bar();
-        stash(buf ^ 1);
-        worker_bar();
-      }
-      const uint32_t s = kb % S, ph = (kb / S) & 1;
-      mbar_wait(empty0 + 8 * s, ph ^ 1);
-      unsigned char* st = stages + s * C::kStage;
-      if (X3) {
-        const float4 hi = make_float4(rn_tf32_masked(bv[0]), rn_tf32_masked(bv[1]), rn_tf32_masked(bv[2]), rn_tf32_masked(bv[3]));
-        *reinterpret_cast<float4*>(st + offQ) = hi;
-        *reinterpret_cast<float4*>(st + C::kOffQlo + offQ) =
-            make_float4(rn_tf32_fast(bv[0] - hi.x), rn_tf32_fast(bv[1] - hi.y), rn_tf32_fast(bv[2] - hi.z), rn_tf32_fast(bv[3] - hi.w));
-      } else {
-        *reinterpret_cast<float4*>(st + offQ) =
-            make_float4(rn_tf32_masked(bv[0]), rn_tf32_masked(bv[1]), rn_tf32_masked(bv[2]), rn_tf32_masked(bv[3]));
-      }
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const uint32_t bits = t ? bits1 : bits0;
-        float av[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) av[e] = ((bits >> e) & 1u) ? 5.f : 1.f;
-        *reinterpret_cast<float4*>(st + offO + t * kTileBytes) = make_float4(av[0], av[1], av[2], av[3]);
-        *reinterpret_cast<float4*>(st + offO + t * kTileBytes + 16) = make_float4(av[4], av[5], av[6], av[7]);
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full0 + 8 * s);
-    }
-    // epilogue: TMEM lane = n, column = o.  Warp w reads its lane quadrant (w & 3) and the 128 columns of group w >> 2.
-    const int q = warp & 3, cg = warp >> 2;
-    const int n = n0 + q * 32 + lane;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 128);
-    if (two || cg < 2) {
-      float* out = dP0part + ((size_t)split * Hq + o0 + cg * 128) * Hq + n;
-      if (NKB > 0) {
-        mbar_wait(accfull, 0);
-        tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t r[32];
-          tmem_ld32(taddr + cc * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) out[(size_t)(cc * 32 + j) * Hq] = __uint_as_float(r[j]);
-        }
-      } else {
-        for (int j = 0; j < 128; ++j) out[(size_t)j * Hq] = 0.f;
-      }
-    }
-  } else {
-    // MMA issuer: whole converged warp, one elected lane issues; descriptors advance by constants
-    const uint64_t descQ = make_desc_mn_sw128_sbo(smem_u32(stages), 2048);
-    const uint64_t descO = make_desc_mn_sw128_sbo(smem_u32(stages), 4096);
-    for (int kb = 0; kb < NKB; ++kb) {
-      const uint32_t s = kb % S, ph = (kb / S) & 1;
-      mbar_wait(full0 + 8 * s, ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t so = (uint64_t)((s * C::kStage) >> 4);
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {                                            // K = 8 = two 4-k groups
-          const uint64_t a_hi = descQ + so + (uint64_t)((g * 4096) >> 4);
-          const uint32_t acc = (kb | g) ? 1u : 0u;
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (t == 1 && !two) break;
-            const uint32_t d_t = tmem_base + (uint32_t)(t * 256);
-            const uint64_t b = descO + so + (uint64_t)((C::kOffO + t * kTileBytes + g * 8192) >> 4);
-            if (X3) {                                                            // B is exact: a_lo.b + a_hi.b
-              umma_tf32(d_t, a_hi + (uint64_t)(C::kOffQlo >> 4), b, kIdescTf32MN, acc);
-              umma_tf32(d_t, a_hi, b, kIdescTf32MN, 1u);
-            } else {
-              umma_tf32(d_t, a_hi, b, kIdescTf32MN, acc);
-            }
-          }
-        }
-        umma_commit(empty0 + 8 * s);
-        if (kb == NKB - 1) umma_commit(accfull);
-      }
-      __syncwarp();
-    }
-  }
-  tc_teardown(tmem_base);
-}
-
 // ordered reduction of the row-kernel partials + chain through the positive reparam for W1.
 // grid (Hq/32, NF, 2): one block sums all `nslots` partial rows of 32 columns (8 slot lanes x 32 columns,
 // coalesced 128-byte reads, fixed summation order -> deterministic).
@@ -1243,13 +1016,8 @@ int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* 
 }
 
 // ---- backward ----
-// dP0 kernel variant: 1 = o-stationary 256 x 256 tiles (icnn_tc_dP0_kernel), 2 = n-stationary 128 x 512 (icnn_tc_dP0w_kernel)
-static int tc_dp0_variant() {
-  static const int v = [] { const char* e = getenv("B200VAE_DP0"); return e ? atoi(e) : 2; }();
-  return v == 1 ? 1 : 2;
-}
 static int tc_dp0_splits(int B, int Hq) {
-  const int tiles = tc_dp0_variant() == 1 ? (Hq / kTM) * (Hq / kTN) : (Hq / kDwN) * ((Hq + kDwO - 1) / kDwO);
+  const int tiles = (Hq / kTM) * (Hq / kTN);
   int s = 148 / tiles;                          // one wave of long-running CTAs
   const int maxs = (B + 255) / 256;
   if (s > maxs) s = maxs;
@@ -1303,17 +1071,6 @@ static int launch_tc_dp0(const float* z, const float* v, const uint32_t* mask1, 
   }
   int rows = (B + splits - 1) / splits;
   rows = round_up(rows, kKB);
-  if (tc_dp0_variant() == 2) {
-    static bool attr2_done = false;
-    if (!attr2_done) {
-      cudaFuncSetAttribute(icnn_tc_dP0w_kernel<D, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      attr2_done = true;
-    }
-    dim3 grid2(T.Hq / kDwN, (T.Hq + kDwO - 1) / kDwO, splits);
-    icnn_tc_dP0w_kernel<D, X3><<<grid2, kDpThreads, dw_smem_bytes<D, X3>(), st>>>(
-        z, v, mask1, mask2, B, T.Hq, Hw_in, rows, reinterpret_cast<const float4*>(tb + T.A0q), part);
-    return check_launch();
-  }
   dim3 grid(T.Hq / kTN, T.Hq / kTM, splits);
   icnn_tc_dP0_kernel<D, X3><<<grid, kDpThreads, smem, st>>>(z, v, mask1, mask2, B, T.Hq, Hw_in, rows,
                                                            reinterpret_cast<const float4*>(tb + T.A0q), part);
