@@ -1029,6 +1029,8 @@ int tc3_bwd_rows(const float* z, const float* v, const uint32_t* mask1, const ui
                  float* dz, float* partA, float* partB, float* a2part, float* dzpart, int precision, float* ws,
                  const float* accsave, cudaStream_t st);
 size_t tc3_bwd_ws_floats(int B, int d, int H);
+int tc3_dp0(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int Hq, int Hw_in,
+            const float* A0q, int precision, int max_splits, float* part, int* splits_out, cudaStream_t st);
 
 size_t tc_bwd_ws_floats(int B, int d, int H) {
   const TcLayout T = tc_layout(d, H);
@@ -1119,7 +1121,13 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
   if (rc || !g) return rc;
   if (g->W0) {
     float* part = dp0part;
-    const int splits = tc_dp0_splits(B, T.Hq);
+    int splits = tc_dp0_splits(B, T.Hq);
+    // CTA-pair kernel (icnn_tc3.cu) unless B200VAE_DP0=1; it never needs more slabs than the workspace holds
+    static const int dp_variant = [] { const char* e = getenv("B200VAE_DP0"); return e ? atoi(e) : 3; }();
+    rc = B200VAE_EUNSUP;
+    if (dp_variant == 3)
+      rc = tc3_dp0(z, v, mask1, mask2, B, d, T.Hq, Hw_in, tb + T.A0q, precision, splits, part, &splits, st);
+    if (rc == B200VAE_EUNSUP) {
 #define B200VAE_TCD(DD)                                                                                       \
   rc = x3 ? launch_tc_dp0<DD, true>(z, v, mask1, mask2, B, T, tb, Hw_in, splits, part, st)                    \
           : launch_tc_dp0<DD, false>(z, v, mask1, mask2, B, T, tb, Hw_in, splits, part, st)
@@ -1129,6 +1137,7 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
       default: B200VAE_TCD(3); break;
     }
 #undef B200VAE_TCD
+    }
     if (rc) return rc;
     rc = finalize_W0_launch(part, splits, H, L.Hp, T.Hq, ws + L.P0, ws + L.P1, p->W0, mode, kSlope, g->W0, st);
     if (rc) return rc;

@@ -1171,6 +1171,254 @@ static int get_maps3(const float* t3, const Tc3Layout& T3, bool x3, Tc3Maps* out
   return B200VAE_OK;
 }
 
+// =====================================================================================================
+// dP0 (batch-reduced gradient of the H x H weight) on CTA pairs:  dP0part[split][o][n] = sum_{m in split} (1 + 4 bit[m,o]) s2[m] q1[m,n]
+// The single-CTA kernel (icnn_tc_dP0_kernel, icnn_tc.cu) turned out to be bound by SHARED-MEMORY BYTES, not by generator
+// instructions or the tensor pipe (ncu: issue 36 %, tensor 45 / 69 % active; an n-stationary single-CTA variant with fewer
+// generator instructions but more generated bytes was slower): per 16-sample K-block an SM wrote 32 / 48 KB of generated
+// operands and the MMAs read 48 / 96 KB (TF32 / 3xTF32) against ~730 / 1460 tensor cycles x 128 B/clk.  Here
+//   * one tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 8) drives both SMs: an SM reads 4 KB of A and only ITS 4 KB half
+//     of B per MMA (8 KB instead of 12 KB);
+//   * the EXPENSIVE operand q1 (packed FMAs, tf32 hi/lo split) is the A operand -- each SM generates it for its own 128 n's
+//     only -- and the cheap exact slope pattern 1 + 4*bit is the B operand: two accumulators (all 512 TMEM columns) cover
+//     512 o's, of which each SM generates 2 x 128.  Generated bytes per K-block and SM: 24 / 32 KB; MMA reads 32 / 64 KB.
+// D[n][o] is written transposed by the epilogue (thread = n lane, one coalesced 128-byte store per o column).
+// Both operands MN-major, SWIZZLE_128B_BASE32B atoms of 4 k-rows x 128 B; every tile is 128 MN wide: LBO 512 B, SBO 2 KB.
+constexpr int kDpWarps = 16;                                   // generator / epilogue warps (+ 1 MMA / TMEM warp)
+constexpr int kDpThreads3 = (kDpWarps + 1) * 32;
+constexpr int kDpTile = 16 * 128 * 4;                          // 16 k x 128 MN x 4 B = 8 KB
+constexpr uint32_t k3IdescMN = k3Idesc | (1u << 15) | (1u << 16);
+__device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)(2048 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)1 << 61);           // layout type 1 = SWIZZLE_128B_BASE32B
+}
+__device__ __forceinline__ void umma_tf32_pair_mn(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(k3IdescMN), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void bar_dp() { asm volatile("bar.sync 1, %0;" ::"n"(kDpWarps * 32) : "memory"); }
+template <bool X3>
+struct DpCfg {
+  static constexpr int S = X3 ? 5 : 6;
+  static constexpr int kOffQlo = kDpTile, kOffO = (X3 ? 2 : 1) * kDpTile;
+  static constexpr int kStage = kOffO + 2 * kDpTile;           // 24 KB / 32 KB
+};
+template <int D, bool X3>
+constexpr size_t dp3_smem_bytes() {
+  return (size_t)DpCfg<X3>::S * DpCfg<X3>::kStage + (size_t)2 * 256 * (2 * D + 1) * 4 + 2 * 8 * 256 * 4 +
+         (2 * DpCfg<X3>::S + 1) * 8 + 16 + 1024;
+}
+
+template <int D, bool X3>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDpThreads3, 1)
+icnn_tc3_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, const uint32_t* __restrict__ mask1,
+                    const uint8_t* __restrict__ mask2, int B, int Hq, int Hw_in, int rows_per_split,
+                    const float4* __restrict__ A0q_g, float* __restrict__ dP0part) {
+  using C = DpCfg<X3>;
+  constexpr int S = C::S;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* samp = reinterpret_cast<float*>(stages + S * C::kStage);            // [2][2D+1][256]  z, v, s2 per sample
+  uint32_t* sampw = reinterpret_cast<uint32_t*>(samp + 2 * 256 * (2 * D + 1));    // [2][8][256] this CTA's mask words
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sampw + 2 * 8 * 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t rank = cluster_rank3();
+  const int n0 = (blockIdx.x >> 1) * 256 + (int)rank * 128;  // my 128 n's (rows of D)
+  const int o0 = blockIdx.y * 512, split = blockIdx.z;
+  const bool two = o0 + 256 < Hq;                            // Hq is a multiple of 256: the last o-tile may be half
+  const int b0 = split * rows_per_split;
+  const int b1 = min(B, b0 + rows_per_split);
+  const int NKB = (max(b1 - b0, 0) + kKB - 1) / kKB;
+
+  if (tid == 0) {
+    // full (leader's copy is the one in use): one arrival per generator warp of BOTH CTAs
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 2 * kDpWarps); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(accfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kDpWarps) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync3();                         // peer barriers initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lead_full0 = mapa3(full0, 0);
+
+  if (warp_u < kDpWarps) {
+    const int ks = tid & 15, u = tid >> 4;                   // sample-in-stage, unit 0..31: 4 consecutive MN elements
+    const int g4 = ks >> 2, kr = ks & 3;                     // group of 4 k, k-row inside the atom
+    const int blk = u >> 3, qd = (u >> 1) & 3, hf = u & 1;   // 32-wide block, 8-wide quarter (swizzle unit), 4-wide half
+    const uint32_t off = (uint32_t)((g4 * 4 + blk) * 512 + kr * 128) + ((uint32_t)(qd ^ kr) << 5) + (uint32_t)(hf * 16);
+    const int bsh = qd * 8 + hf * 4;                         // my 4 bits inside mask word `blk` (of either accumulator)
+    float2 qx2[2], qy2[2], qz2[2], qw2[2];                   // my 4 n's as two packed pairs: (w0, w1, w2, bias)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int n = n0 + blk * 32 + qd * 8 + hf * 4 + 2 * i;
+      const float4 qa = A0q_g[n], qb = A0q_g[n + 1];
+      qx2[i] = make_float2(qa.x, qb.x); qy2[i] = make_float2(qa.y, qb.y);
+      qz2[i] = make_float2(qa.z, qb.z); qw2[i] = make_float2(qa.w, qb.w);
+    }
+    // per-sample inputs (z, v, s2, this CTA's 8 mask words: o's [t*256 + rank*128, +128) of accumulator t = 0, 1) are staged
+    // through shared memory in chunks of 256 samples, fetched one chunk ahead (register staged)
+    constexpr int CH = 256, ZV = 2 * D + 1;
+    const int nchunk = (NKB * kKB + CH - 1) / CH;
+    float pre_f[ZV];
+    uint32_t pre_w[4];
+    auto fetch = [&](int c) {                                // thread -> sample (tid&255), accumulator t = tid>>8
+      const int mrow = b0 + c * CH + (tid & 255);
+      const bool in = mrow < b1;
+      if (tid < CH) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          pre_f[j] = in ? __ldg(z + (size_t)mrow * D + j) : 0.f;
+          pre_f[D + j] = in ? __ldg(v + (size_t)mrow * D + j) : 0.f;
+        }
+        pre_f[2 * D] = in ? (__ldg(mask2 + mrow) ? 1.f : kSlope) : 0.f;
+      }
+      const int w0 = (o0 >> 5) + (tid >> 8) * 8 + (int)rank * 4;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) pre_w[q4] = (in && w0 + q4 < Hw_in) ? __ldg(mask1 + (size_t)mrow * Hw_in + w0 + q4) : 0u;
+    };
+    auto stash = [&](int buf) {
+      float* zf = samp + buf * (CH * ZV);
+      uint32_t* mw = sampw + buf * (CH * 8);
+      if (tid < CH) {
+#pragma unroll
+        for (int j = 0; j < ZV; ++j) zf[j * CH + tid] = pre_f[j];
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) mw[((tid >> 8) * 4 + q4) * CH + (tid & 255)] = pre_w[q4];
+    };
+    if (nchunk > 0) { fetch(0); stash(0); }
+    bar_dp();
+    for (int kb = 0; kb < NKB; ++kb) {
+      const int c = kb >> 4, buf = c & 1, sl = (kb & 15) * kKB + ks;       // sample slot inside the chunk
+      if ((kb & 15) == 0 && c + 1 < nchunk) fetch(c + 1);
+      const float* zf = samp + buf * (CH * ZV);
+      float zr[D], vr[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) { zr[j] = zf[j * CH + sl]; vr[j] = zf[(D + j) * CH + sl]; }
+      const float s2f = zf[2 * D * CH + sl];
+      const uint32_t bits0 = sampw[buf * (CH * 8) + blk * CH + sl] >> bsh;
+      const uint32_t bits1 = sampw[buf * (CH * 8) + (4 + blk) * CH + sl] >> bsh;
+      // A = s2 q1 = (2 s2 A0 v) . max(h0, 0.04 h0) for my 4 n's, two per packed instruction
+      float qv[4];
+      float sv[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) sv[j] = (2.f * s2f) * vr[j];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float2 h = __ffma2_rn(qx2[i], make_float2(zr[0], zr[0]), qw2[i]);
+        float2 uu = __fmul2_rn(qx2[i], make_float2(sv[0], sv[0]));
+        if (D > 1) {
+          h = __ffma2_rn(qy2[i], make_float2(zr[D > 1 ? 1 : 0], zr[D > 1 ? 1 : 0]), h);
+          uu = __ffma2_rn(qy2[i], make_float2(sv[D > 1 ? 1 : 0], sv[D > 1 ? 1 : 0]), uu);
+        }
+        if (D > 2) {
+          h = __ffma2_rn(qz2[i], make_float2(zr[D > 2 ? 2 : 0], zr[D > 2 ? 2 : 0]), h);
+          uu = __ffma2_rn(qz2[i], make_float2(sv[D > 2 ? 2 : 0], sv[D > 2 ? 2 : 0]), uu);
+        }
+        const float2 l = __fmul2_rn(h, make_float2(kSlope * kSlope, kSlope * kSlope));
+        const float2 x = __fmul2_rn(uu, make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y)));
+        qv[2 * i] = x.x; qv[2 * i + 1] = x.y;
+      }
+      if ((kb & 15) == 15 && c + 1 < nchunk) {               // next chunk's buffer was last read 16 stages ago
+        bar_dp();
+        stash(buf ^ 1);
+        bar_dp();
+      }
+      const uint32_t s = kb % S, ph = (kb / S) & 1;
+      mbar_wait(empty0 + 8 * s, ph ^ 1);
+      unsigned char* st = stages + s * C::kStage + off;
+      if (X3) {
+        const float4 hi = make_float4(rn_tf32_masked(qv[0]), rn_tf32_masked(qv[1]), rn_tf32_masked(qv[2]), rn_tf32_masked(qv[3]));
+        *reinterpret_cast<float4*>(st) = hi;
+        *reinterpret_cast<float4*>(st + C::kOffQlo) =
+            make_float4(rn_tf32_fast(qv[0] - hi.x), rn_tf32_fast(qv[1] - hi.y), rn_tf32_fast(qv[2] - hi.z), rn_tf32_fast(qv[3] - hi.w));
+      } else {
+        *reinterpret_cast<float4*>(st) =
+            make_float4(rn_tf32_masked(qv[0]), rn_tf32_masked(qv[1]), rn_tf32_masked(qv[2]), rn_tf32_masked(qv[3]));
+      }
+      // B = 1 + 4*bit (the LeakyReLU slope / 0.2, exact in tf32; 0.2 and P1 are applied by finalize_W0)
+      *reinterpret_cast<float4*>(st + C::kOffO) =
+          make_float4((bits0 & 1u) ? 5.f : 1.f, (bits0 & 2u) ? 5.f : 1.f, (bits0 & 4u) ? 5.f : 1.f, (bits0 & 8u) ? 5.f : 1.f);
+      *reinterpret_cast<float4*>(st + C::kOffO + kDpTile) =
+          make_float4((bits1 & 1u) ? 5.f : 1.f, (bits1 & 2u) ? 5.f : 1.f, (bits1 & 4u) ? 5.f : 1.f, (bits1 & 8u) ? 5.f : 1.f);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(lead_full0 + 8 * s);
+    }
+    // epilogue: TMEM lane = my n, column = o (512 of them).  Warp w: lane quadrant w & 3, the 128 columns of group w >> 2.
+    const int q = warp & 3, cg = warp >> 2;
+    const int n = n0 + q * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 128);
+    if (two || cg < 2) {
+      float* out = dP0part + ((size_t)split * Hq + o0 + cg * 128) * Hq + n;
+      if (NKB > 0) {
+        mbar_wait_parked(accfull, 0, 2000);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t r[32];
+          tmem_ld32(taddr + cc * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) out[(size_t)(cc * 32 + j) * Hq] = __uint_as_float(r[j]);
+        }
+      } else {
+        for (int j = 0; j < 128; ++j) out[(size_t)j * Hq] = 0.f;
+      }
+    }
+  } else if (rank == 0) {
+    // MMA issuer (leader CTA only): whole converged warp, one elected lane issues; descriptors advance by constants
+    const uint64_t desc0 = make_desc_mn128(smem_u32(stages));
+    for (int kb = 0; kb < NKB; ++kb) {
+      const uint32_t s = kb % S, ph = (kb / S) & 1;
+      mbar_wait(full0 + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t sa = desc0 + (uint64_t)((s * C::kStage) >> 4);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {                                            // K = 8 = two 4-k groups (2 x SBO)
+          const uint64_t a_hi = sa + (uint64_t)((g * 4096) >> 4);
+          const uint32_t acc = (kb | g) ? 1u : 0u;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (t == 1 && !two) break;
+            const uint32_t d_t = tmem_base + (uint32_t)(t * 256);
+            const uint64_t b = sa + (uint64_t)((C::kOffO + t * kDpTile + g * 4096) >> 4);
+            if (X3) {                                                            // B is exact: a_lo.b + a_hi.b
+              umma_tf32_pair_mn(d_t, a_hi + (uint64_t)(C::kOffQlo >> 4), b, acc);
+              umma_tf32_pair_mn(d_t, a_hi, b, 1u);
+            } else {
+              umma_tf32_pair_mn(d_t, a_hi, b, acc);
+            }
+          }
+        }
+        umma_commit_pair(empty0 + 8 * s);                                        // frees the stage in both CTAs
+        if (kb == NKB - 1) umma_commit_pair(accfull);
+      }
+      __syncwarp();
+    }
+  }
+  // teardown: nobody may leave (or free TMEM) while the peer can still touch this CTA's smem / TMEM
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync3();
+  if (warp == kDpWarps) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 static int max_clusters_for(const void* fn, size_t smem) {
   cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaLaunchConfig_t cfg = {};
@@ -1185,6 +1433,57 @@ static int max_clusters_for(const void* fn, size_t smem) {
     n = sm_count() / 2;
   }
   return n;
+}
+
+static int max_clusters_dp(const void* fn, size_t smem) {
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * 74); cfg.blockDim = dim3(kDpThreads3); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    n = sm_count() / 2;
+  }
+  return n;
+}
+template <int D, bool X3>
+static int launch_tc3_dp0(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int Hq,
+                          int Hw_in, const float4* A0q, int max_splits, float* part, int* splits_out, cudaStream_t st) {
+  constexpr size_t smem = dp3_smem_bytes<D, X3>();
+  static_assert(smem <= 227 * 1024, "dP0 pair kernel: shared memory");
+  static int max_clusters = 0;
+  if (max_clusters == 0) max_clusters = max_clusters_dp(reinterpret_cast<const void*>(icnn_tc3_dP0_kernel<D, X3>), smem);
+  const int tn = Hq / 256, to = (Hq + 511) / 512;
+  int splits = max_clusters / (tn * to);                     // one wave of long-running clusters
+  if (splits > max_splits) splits = max_splits;              // (workspace slabs, and at least 256 samples per split)
+  if (splits < 1) splits = 1;
+  int rows = (B + splits - 1) / splits;
+  rows = round_up(rows, kKB);
+  dim3 grid(2 * tn, to, splits);
+  icnn_tc3_dP0_kernel<D, X3><<<grid, kDpThreads3, smem, st>>>(z, v, mask1, mask2, B, Hq, Hw_in, rows, A0q, part);
+  *splits_out = splits;
+  return check_launch();
+}
+// part: [splits][Hq][Hq] ordered split-K slabs (reduced by finalize_W0_kernel); *splits_out <= max_splits
+int tc3_dp0(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int Hq, int Hw_in,
+            const float* A0q, int precision, int max_splits, float* part, int* splits_out, cudaStream_t st) {
+  if (precision == B200VAE_PREC_BF16 || d > 3) return B200VAE_EUNSUP;
+  const bool x3 = (precision == B200VAE_PREC_TF32X3);
+  const float4* q = reinterpret_cast<const float4*>(A0q);
+#define B200VAE_TC3D(DD)                                                                                             \
+  return x3 ? launch_tc3_dp0<DD, true>(z, v, mask1, mask2, B, Hq, Hw_in, q, max_splits, part, splits_out, st)         \
+            : launch_tc3_dp0<DD, false>(z, v, mask1, mask2, B, Hq, Hw_in, q, max_splits, part, splits_out, st)
+  switch (d) {
+    case 1: B200VAE_TC3D(1);
+    case 2: B200VAE_TC3D(2);
+    case 3: B200VAE_TC3D(3);
+    default: return B200VAE_EUNSUP;
+  }
+#undef B200VAE_TC3D
 }
 
 template <int D, bool X3, bool SV>
