@@ -1253,9 +1253,12 @@ icnn_tc3_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, co
   const uint32_t lead_full0 = mapa3(full0, 0);
 
   if (warp_u < kDpWarps) {
-    const int ks = tid & 15, u = tid >> 4;                   // sample-in-stage, unit 0..31: 4 consecutive MN elements
-    const int g4 = ks >> 2, kr = ks & 3;                     // group of 4 k, k-row inside the atom
-    const int blk = u >> 3, qd = (u >> 1) & 3, hf = u & 1;   // 32-wide block, 8-wide quarter (swizzle unit), 4-wide half
+    // thread -> (sample ks of the stage, 4 consecutive MN elements).  A quarter warp (8 lanes = 4 k-rows x 2 halves of one
+    // 32-byte swizzle unit) stores 128 distinct bytes: conflict-free 16-byte stores (the k-groups g4 share banks, so they
+    // sit in different quarters); a warp owns one 8-wide MN unit (blk, qd) for all 16 samples
+    const int g4 = lane >> 3, hf = (lane >> 2) & 1, kr = lane & 3;   // group of 4 k, 4-wide half, k-row inside the atom
+    const int ks = g4 * 4 + kr;
+    const int blk = warp >> 2, qd = warp & 3;                // 32-wide block, 8-wide quarter (swizzle unit)
     const uint32_t off = (uint32_t)((g4 * 4 + blk) * 512 + kr * 128) + ((uint32_t)(qd ^ kr) << 5) + (uint32_t)(hf * 16);
     const int bsh = qd * 8 + hf * 4;                         // my 4 bits inside mask word `blk` (of either accumulator)
     float2 qx2[2], qy2[2], qz2[2], qw2[2];                   // my 4 n's as two packed pairs: (w0, w1, w2, bias)
