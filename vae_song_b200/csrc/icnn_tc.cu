@@ -878,16 +878,23 @@ tc_finalize_small_kernel(const float* __restrict__ partA, const float* __restric
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx, f = blockIdx.y, which = blockIdx.z;
   const float* part = (which ? partB : partA) + (size_t)f * Hq + n;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  // 16 independent partial sums per thread: the kernel is latency bound (2048 slots x 128-byte rows per block at
+  // B = 65536), so the number of loads in flight is what sets its duration
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   int sl = ty;
-  for (; sl + 24 < nslots; sl += 32) {
-    s0 += part[(size_t)sl * NF * Hq];
-    s1 += part[(size_t)(sl + 8) * NF * Hq];
-    s2 += part[(size_t)(sl + 16) * NF * Hq];
-    s3 += part[(size_t)(sl + 24) * NF * Hq];
+  const size_t stride = (size_t)NF * Hq;
+  for (; sl + 120 < nslots; sl += 128) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] += part[(size_t)(sl + 8 * i) * stride];
   }
-  for (; sl < nslots; sl += 8) s0 += part[(size_t)sl * NF * Hq];
-  red[ty][tx] = (s0 + s1) + (s2 + s3);
+  for (; sl < nslots; sl += 8) acc[0] += part[(size_t)sl * stride];
+#pragma unroll
+  for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; ++i) acc[i] += acc[i + w];
+  red[ty][tx] = acc[0];
   __syncthreads();
   if (ty == 0 && n < H) {
     float s = 0.f;
