@@ -90,7 +90,7 @@ def test_tc_unsupported_is_loud():
 
 
 def test_persistent_pair_kernels_match_single_cta_kernels():
-    """The default persistent CTA-pair kernels (icnn_tc3.cu: B200VAE_FWD=3 / B200VAE_BWD=3, read once per process)
+    """The default persistent CTA-pair kernels (icnn_tc3.cu: B200VAE_FWD=3 / B200VAE_BWD=3 / B200VAE_DP0=3, read once per process)
     against the single-CTA tcgen05 kernels (=1): same masks semantics, different operand factorisation and
     summation order, so they agree to the precision's stated bound (not bitwise).  Run in subprocesses."""
     import os, subprocess, sys, tempfile
@@ -118,7 +118,7 @@ np.savez(sys.argv[1], **out)
     res = {}
     for flag in ("1", "3"):
         with tempfile.NamedTemporaryFile(suffix=".npz") as f:
-            env = dict(os.environ, B200VAE_FWD=flag, B200VAE_BWD=flag)
+            env = dict(os.environ, B200VAE_FWD=flag, B200VAE_BWD=flag, B200VAE_DP0=flag)
             subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
             res[flag] = dict(np.load(f.name))
     for k in res["1"]:
