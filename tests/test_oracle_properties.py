@@ -106,3 +106,56 @@ def test_backward_is_linear_in_v_and_additive_over_the_batch():
         np.testing.assert_allclose(ga[k] + gb[k], g1[k], rtol=1e-9, atol=1e-11)
     # the <v, xhat> path never touches the biases of A.0 / A.1 (sigma'' = 0): exact zeros, as the reference's autograd gives
     assert not g1["A1b"].any() and not g1["A2b"].any()
+
+
+# ---------------------------------------------------------------------------------------------- loss oracle
+def _fd(f, x, h=1e-6):
+    g = np.empty_like(x)
+    it = np.nditer(x, flags=["multi_index"])
+    for _ in it:
+        i = it.multi_index
+        xp, xm = x.copy(), x.copy()
+        xp[i] += h; xm[i] -= h
+        g[i] = (f(xp) - f(xm)) / (2 * h)
+    return g
+
+
+def test_loss_gradients_match_finite_differences():
+    from oracle import loss_oracle as lo
+    rng = np.random.default_rng(2)
+    B, D, Dx = 7, 3, 5
+    mu, lv = rng.normal(0, 1, (B, D)), rng.normal(0, 0.5, (B, D))
+    x, xh = rng.normal(0, 1, (B, Dx)), rng.normal(0, 1, (B, Dx))
+    dmu, dlv = lo.kl_grad(mu, lv, 0.7)
+    np.testing.assert_allclose(dmu, _fd(lambda m: 0.7 * lo.kl(m, lv), mu), rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(dlv, _fd(lambda l: 0.7 * lo.kl(mu, l), lv), rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(lo.recon_mse_grad(x, xh, 1.3), _fd(lambda y: 1.3 * lo.recon_mse(x, y), xh), rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(lo.recon_logmse_grad(x, xh, 1.3), _fd(lambda y: 1.3 * lo.recon_logmse(x, y), xh), rtol=1e-5, atol=1e-8)
+    zi, zr = rng.normal(0, 1, (4, B, D)), rng.normal(0, 1, (4, B, D))          # [L,B,D]: mean over L (Appendix B.2)
+    np.testing.assert_allclose(lo.latent_recon_grad(zi, zr, 0.4), _fd(lambda y: 0.4 * lo.latent_recon(zi, y), zr), rtol=1e-6, atol=1e-8)
+    # KL of the standard normal posterior is zero, and it is the batch mean of the per-sample KL
+    assert abs(lo.kl(np.zeros((B, D)), np.zeros((B, D)))) == 0.0
+    np.testing.assert_allclose(lo.kl(mu, lv), lo.kl_per_sample(mu, lv).mean(), rtol=1e-12)
+
+
+def test_lipschitz_estimator_properties():
+    from oracle import loss_oracle as lo
+    rng = np.random.default_rng(4)
+    X = rng.normal(0, 1, (300, 2))
+    i1, i2 = rng.integers(0, 300, 2000), rng.integers(0, 300, 2000)
+    # an isometry has ratio 1 on every pair with |dx| >= eps (coincident pairs clamp to eps/eps = 1 as well)
+    c, s = np.cos(0.7), np.sin(0.7)
+    r = lo.lipschitz_ratios(X, X @ np.array([[c, -s], [s, c]]), i1, i2)
+    np.testing.assert_allclose(r, 1.0, rtol=1e-12)
+    # a uniform scaling by a has ratio a where the clamps are inactive, and the estimate is (1/a, a, max)
+    a = 3.0
+    keep = np.sqrt(((X[i1] - X[i2]) ** 2).sum(1)) > 1e-2
+    r = lo.lipschitz_ratios(X, a * X, i1[keep], i2[keep])
+    np.testing.assert_allclose(r, a, rtol=1e-12)
+    inv, bi, both = lo.lipschitz_from_ratios(r)
+    np.testing.assert_allclose([inv, bi, both], [1 / a, a, a], rtol=1e-12)
+    # torch.quantile's linear interpolation: exact on a ramp
+    assert lo.torch_quantile_linear(np.arange(101.0), 0.05) == 5.0 and lo.torch_quantile_linear(np.arange(101.0), 0.955) == 95.5
+    ap = lo.lipschitz_allpairs(X, a * X)
+    assert ap["count"] == 300 * 299 // 2
+    np.testing.assert_allclose([ap["max"], ap["min"], ap["sum"] / ap["count"]], [a, a, a], rtol=1e-9)
