@@ -173,3 +173,72 @@ def test_flat_params_views():
     out = m(x, eps=torch.zeros(5, 2))
     m.loss(x, *out)[0].backward()
     assert float(fp.grad.abs().sum()) > 0 and m.enc[0].weight.grad.data_ptr() == fp.grad.data_ptr()
+
+
+class _ToyLRVAE(torch.nn.Module):
+    """Stock-torch stand-in with the LR-VAE contract of model.py:418-447 / 587-616: decode attached and detached, re-encode,
+    ATTACHED loss parts, and a latent-recon term that is a mean over L but a SUM over the batch (Appendix B.2) -- the one
+    term whose global value is the sum, not the mean, of the per-rank values."""
+
+    def __init__(self):
+        super().__init__()
+        self.encoder = torch.nn.Sequential(torch.nn.Linear(2, 5), torch.nn.LeakyReLU(), torch.nn.Linear(5, 4))
+        self.decoder = torch.nn.Linear(2, 2)
+        self.beta, self.alpha = 0.3, 0.5
+
+    def forward(self, x, eps=None, L=1):
+        mu, lv = self.encoder(x).split(2, 1)
+        z = mu + eps * torch.exp(0.5 * lv)
+        z_rec = self.encoder(self.decoder(z.detach())).split(2, 1)[0]
+        return self.decoder(z), mu, lv, z.detach()[None], z_rec[None]
+
+    def loss(self, x, recon, mu, lv, z_in, z_rec):
+        rec = ((x - recon) ** 2).mean(0).sum()
+        reg = self.beta * (-0.5 * (1 + lv - mu ** 2 - lv.exp())).mean(0).sum()
+        lr = self.alpha * ((z_in - z_rec) ** 2).mean(0).sum()
+        return rec + reg + lr, rec, reg, lr
+
+
+def _train_lr(x, eps, lo, hi, staged, clip):
+    from vae_song_b200 import train
+    torch.manual_seed(321)
+    tr = train.DataParallelTrainer(_ToyLRVAE(), lr=1e-2, optimizer_step=_torch_adam, staged_backward=staged, grad_clip=clip,
+                                   forward_kwargs={"L": 1})
+    for _ in range(3):
+        tr.step(x[lo:hi], eps[lo:hi])
+    return tr.fp.flat.clone().numpy()
+
+
+def _lr_worker(rank, world, port, x, eps, staged, clip, out):
+    import torch.distributed as dist
+    from vae_song_b200 import train
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = train.shard_rows(x.shape[0], rank, world)
+    flat = _train_lr(x, eps, lo, hi, staged, clip)
+    if rank == 0:
+        out.put(flat)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("staged", [False, True], ids=["one_backward", "staged_backward"])
+@pytest.mark.parametrize("clip", [None, {"enabled": True, "clip_type": "norm", "max_norm": 0.05, "norm_type": 2.0}],
+                         ids=["noclip", "clipnorm"])
+def test_sharded_lr_vae_step_equals_single(staged, clip):
+    """Batch-sharded LR-VAE training (world 2, gloo) == single-process training on the whole batch: the batch-summed
+    latent-recon term is compensated before the 1/W gradient averaging, in the one-backward and in the staged
+    (main.py:262-284) step, with and without gradient clipping."""
+    torch.manual_seed(1)
+    x, eps = torch.randn(12, 2), torch.randn(12, 2)
+    single = _train_lr(x, eps, 0, 12, staged, clip)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_lr_worker, args=(r, 2, port, x, eps, staged, clip, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    np.testing.assert_allclose(got, single, rtol=1e-5, atol=1e-7)
