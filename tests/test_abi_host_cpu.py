@@ -180,41 +180,48 @@ class _ToyLRVAE(torch.nn.Module):
     ATTACHED loss parts, and a latent-recon term that is a mean over L but a SUM over the batch (Appendix B.2) -- the one
     term whose global value is the sum, not the mean, of the per-rank values."""
 
-    def __init__(self):
+    def __init__(self, set_style=False):
         super().__init__()
         self.encoder = torch.nn.Sequential(torch.nn.Linear(2, 5), torch.nn.LeakyReLU(), torch.nn.Linear(5, 4))
         self.decoder = torch.nn.Linear(2, 2)
         self.beta, self.alpha = 0.3, 0.5
+        # SetLRVAE (model.py:1093-1114): latents stay [B,D], so the same `.mean(dim=0)` IS a batch mean there, z_input is
+        # attached, and the loss parts come back detached -- nothing to compensate when sharding
+        self.set_style = set_style
 
     def forward(self, x, eps=None, L=1):
         mu, lv = self.encoder(x).split(2, 1)
         z = mu + eps * torch.exp(0.5 * lv)
         z_rec = self.encoder(self.decoder(z.detach())).split(2, 1)[0]
+        if self.set_style:
+            return self.decoder(z.detach()), mu, lv, z, z_rec
         return self.decoder(z), mu, lv, z.detach()[None], z_rec[None]
 
     def loss(self, x, recon, mu, lv, z_in, z_rec):
         rec = ((x - recon) ** 2).mean(0).sum()
         reg = self.beta * (-0.5 * (1 + lv - mu ** 2 - lv.exp())).mean(0).sum()
         lr = self.alpha * ((z_in - z_rec) ** 2).mean(0).sum()
+        if self.set_style:
+            return rec + reg + lr, rec.detach(), reg.detach(), lr.detach()
         return rec + reg + lr, rec, reg, lr
 
 
-def _train_lr(x, eps, lo, hi, staged, clip):
+def _train_lr(x, eps, lo, hi, staged, clip, set_style=False):
     from vae_song_b200 import train
     torch.manual_seed(321)
-    tr = train.DataParallelTrainer(_ToyLRVAE(), lr=1e-2, optimizer_step=_torch_adam, staged_backward=staged, grad_clip=clip,
+    tr = train.DataParallelTrainer(_ToyLRVAE(set_style), lr=1e-2, optimizer_step=_torch_adam, staged_backward=staged, grad_clip=clip,
                                    forward_kwargs={"L": 1})
     for _ in range(3):
         tr.step(x[lo:hi], eps[lo:hi])
     return tr.fp.flat.clone().numpy()
 
 
-def _lr_worker(rank, world, port, x, eps, staged, clip, out):
+def _lr_worker(rank, world, port, x, eps, staged, clip, out, set_style=False):
     import torch.distributed as dist
     from vae_song_b200 import train
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     lo, hi = train.shard_rows(x.shape[0], rank, world)
-    flat = _train_lr(x, eps, lo, hi, staged, clip)
+    flat = _train_lr(x, eps, lo, hi, staged, clip, set_style)
     if rank == 0:
         out.put(flat)
     dist.barrier()
@@ -228,13 +235,22 @@ def test_sharded_lr_vae_step_equals_single(staged, clip):
     """Batch-sharded LR-VAE training (world 2, gloo) == single-process training on the whole batch: the batch-summed
     latent-recon term is compensated before the 1/W gradient averaging, in the one-backward and in the staged
     (main.py:262-284) step, with and without gradient clipping."""
+    _check_sharded_lr(staged, clip, False)
+
+
+def test_sharded_set_lr_vae_step_equals_single():
+    """SetLRVAE-style losses (batch-MEAN latent-recon term, detached parts): sharding needs no compensation."""
+    _check_sharded_lr(True, None, True)
+
+
+def _check_sharded_lr(staged, clip, set_style):
     torch.manual_seed(1)
     x, eps = torch.randn(12, 2), torch.randn(12, 2)
-    single = _train_lr(x, eps, 0, 12, staged, clip)
+    single = _train_lr(x, eps, 0, 12, staged, clip, set_style)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_lr_worker, args=(r, 2, port, x, eps, staged, clip, q)) for r in range(2)]
+    procs = [ctx.Process(target=_lr_worker, args=(r, 2, port, x, eps, staged, clip, q, set_style)) for r in range(2)]
     for p in procs:
         p.start()
     got = q.get(timeout=120)
