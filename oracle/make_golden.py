@@ -376,10 +376,50 @@ def gen_train_trajectory(ref_model):
     print("train_trajectory.npz:", len(out), "arrays; first / last loss", losses[0][0], losses[-1][0])
 
 
+WARMUP_CASES = [   # (name, kwargs of VAE.warmup besides epoch/max_epoch)
+    ("linear", dict(wu_strat="linear")),
+    ("linear_up", dict(wu_strat="linear", up_amount=0.07, start_epoch=3)),
+    ("exponential", dict(wu_strat="exponential", start_epoch=2)),
+    ("exponential_up", dict(wu_strat="exponential", up_amount=0.05)),
+    ("repeat_linear", dict(wu_strat="repeat_linear", repeat_interval=4, start_epoch=1)),
+    ("kl_adaptive", dict(wu_strat="kl_adaptive")),
+]
+
+
+def gen_host_logic(ref_model, ref_utils):
+    """Host-side schedules of the reference: VAE.warmup (model.py:37-63) per strategy over 24 epochs, and
+    utils.apply_grad_clip (utils.py) on fixed gradients."""
+    out = {}
+    kl_seq = np.linspace(9.0, 1.0, 24)
+    for name, kw in WARMUP_CASES:
+        m = ref_model.LRVAE(beta=0.01, alpha=0.1, dataset="pinwheel", hidden_channels=[4], encoder_type="mlp", decoder_type="mlp")
+        seq = []
+        for epoch in range(24):
+            m.last_kl_loss = float(kl_seq[epoch])
+            m.warmup(epoch=epoch, max_epoch=20, **kw)
+            seq.append(m.wu_alpha)
+        out["warmup/" + name] = np.asarray(seq, np.float64)
+    out["warmup/kl_seq"] = kl_seq
+    rng = np.random.default_rng(11)
+    g = [rng.normal(0, 1, (3, 4)).astype(np.float32), rng.normal(0, 2, (5,)).astype(np.float32)]
+    for tag, cfg in (("norm", {"enabled": True, "clip_type": "norm", "max_norm": 0.7, "norm_type": 2.0}),
+                     ("value", {"enabled": True, "clip_type": "value", "clip_value": 0.5}),
+                     ("off", {"enabled": False, "clip_type": "norm", "max_norm": 0.1})):
+        lin = torch.nn.Linear(4, 3)
+        lin.weight.grad = torch.tensor(g[0]); lin.bias.grad = torch.tensor(g[1][:3])
+        ref_utils.apply_grad_clip(lin, cfg)
+        out[f"clip/{tag}/w"] = lin.weight.grad.numpy().copy(); out[f"clip/{tag}/b"] = lin.bias.grad.numpy().copy()
+    out["clip/g_w"], out["clip/g_b"] = g[0], g[1][:3]
+    np.savez_compressed(os.path.join(OUT, "host_cases.npz"), **out)
+    print("host_cases.npz:", len(out), "arrays")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref_module, ref_model, ref_utils = import_reference()
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "host":        # only the (cheap) host-logic fixtures
+        return gen_host_logic(ref_model, ref_utils)
     gen_icnn(ref_module)
     gen_lidvae(ref_model)
     gen_mnist_shaped(ref_model)
@@ -387,6 +427,7 @@ def main():
     gen_lipschitz(ref_model, ref_utils)
     gen_families(ref_model)
     gen_train_trajectory(ref_model)
+    gen_host_logic(ref_model, ref_utils)
 
 
 if __name__ == "__main__":
