@@ -548,6 +548,11 @@ class FusedMlpFn(torch.autograd.Function):
         scratch = ctx.scratch
         dWs, dbs, dgs, dbes = [None] * nl, [None] * nl, [None] * (nl - 1), [None] * (nl - 1)
         da = _req(dout, "grad_out")
+        # biases that feed a BatchNorm get exactly-zero gradients: ONE zero fill per backward, sliced per layer
+        zero_db = torch.zeros(sum(W.shape[0] for W in Ws[:nl - 1]), dtype=torch.float32, device=x.device) if nl > 1 else None
+        zoff = [0]
+        for W in Ws[:nl - 1]:
+            zoff.append(zoff[-1] + W.shape[0])
         for i in range(nl - 1, -1, -1):
             wo, wi = Ws[i].shape
             has_bn = i < nl - 1
@@ -564,7 +569,7 @@ class FusedMlpFn(torch.autograd.Function):
                                                                _ptr(scratch), peer.ref, plan.bns[i].peer_slots[1],
                                                                _stream()), "mlp_layer_bwd_reduce_peer")
                 dbes[i], dgs[i] = loc[0], loc[1]
-                dbs[i] = torch.zeros(wo, dtype=torch.float32, device=x.device)
+                dbs[i] = zero_db[zoff[i]:zoff[i + 1]]
                 inv_n = 1.0 / (B * peer.world)                            # equal shards (train.shard_rows)
             else:
                 _C.check(lib.b200vae_mlp_layer_bwd_reduce(_ptr(da), _ptr(ys[i]), _ptr(st), _ptr(gs[i]) if has_bn else None,
@@ -573,8 +578,12 @@ class FusedMlpFn(torch.autograd.Function):
             if peer is not None:
                 pass
             elif has_bn:
-                dbes[i], dgs[i] = sums[0].clone(), sums[1].clone()        # local sums = parameter gradients
-                dbs[i] = torch.zeros(wo, dtype=torch.float32, device=x.device)   # bias feeding a BatchNorm: exactly 0
+                # local sums = parameter gradients; copied only where `sums` is modified below (eval mode, NCCL all-reduce)
+                if (not training) or grp is not None:
+                    dbes[i], dgs[i] = sums[0].clone(), sums[1].clone()
+                else:
+                    dbes[i], dgs[i] = sums[0], sums[1]
+                dbs[i] = zero_db[zoff[i]:zoff[i + 1]]                     # bias feeding a BatchNorm: exactly 0
                 if not training:
                     sums.zero_()                                          # eval-mode BN is affine: dy = gamma*invstd*dyhat
                 else:
