@@ -33,6 +33,16 @@ def test_no_cpu_fallback():
     m = model.LIDVAE(dataset="pinwheel", icnn_channels=[32, 32])
     with pytest.raises(_C.B200VaeError):
         m.decode(torch.zeros(4, 2))
+    # every ICNN entry point, narrow and wide inputs, with and without autograd: CPU tensors are refused, never computed
+    from vae_song_b200 import module
+    for d in (2, 32):
+        ic = module.ICNN(d, 16)
+        for grad in (True, False):
+            with torch.set_grad_enabled(grad):
+                with pytest.raises(_C.B200VaeError):
+                    ic(torch.zeros(4, d, requires_grad=grad))
+                with pytest.raises(_C.B200VaeError):
+                    ic.brenier(torch.zeros(4, d), 0.1)
 
 
 def test_product_does_not_import_oracle():

@@ -247,6 +247,8 @@ def icnn_potential_wide(z, mode, A0w, A0b, A1w, A1b, A2w, A2b, W0, W1):
     semantics), so first- and second-order autograd through psi keep working for d > 4."""
     _C.load()
     ps = (A0w, A0b, A1w, A1b, A2w, A2b, W0, W1)
+    if not z.is_cuda or any(not p.is_cuda for p in ps):
+        raise _C.B200VaeError("icnn_potential_wide: expected CUDA tensors; vae_song_b200 has no CPU fallback")
     if not (torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in ps))):
         psi, _, _ = icnn_wide_fwd(_req(z, "z"), [_req(p, k) for p, k in zip(ps, PARAM_FIELDS)], mode, 0.0, False)
         return psi.unsqueeze(1)                     # inference: fused kernels, psi only
