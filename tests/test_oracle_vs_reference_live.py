@@ -76,3 +76,26 @@ def test_lidvae_decode_chain_matches_live_reference(seed, ref):
     y_ref = m.decode(torch.tensor(z, requires_grad=True)).detach().numpy()
     y, _, _, _ = io.lidvae_decode(z, p0, p1, 2, 0, il / 2.0)
     np.testing.assert_allclose(y, y_ref, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_lipschitz_estimator_oracle_matches_live_reference(seed, ref):
+    """utils.estimate_local_lipschitz (utils.py:532-567) of the unmodified reference on CPU, random maps / sizes / quantiles,
+    against the oracle fed with the same pair indices (same generator, same call order)."""
+    from oracle import loss_oracle as lo
+    _, (_, _, ref_utils) = ref
+    rng = np.random.default_rng(3000 + seed)
+    N = int(rng.integers(2, 300)); P = int(rng.choice([50, 2000, 5000])); d = int(rng.choice([2, 3, 16]))
+    q = float(rng.choice([0.05, 0.1, 0.25])); eps = float(rng.choice([1e-3, 1e-2]))
+    W = torch.tensor(rng.normal(0, 1, (d, 12)))
+    func = lambda x: torch.tanh(x @ W).reshape(-1, 3, 2, 2) * 3.0                 # image-shaped output: rows are flattened
+    X = torch.tensor(rng.normal(0, 1, (N, d)))
+    if seed % 3 == 0:
+        X[N // 2:] = X[:N - N // 2].clone()                                       # coincident points: both clamps active
+    got = ref_utils.estimate_local_lipschitz(func, X, num_pairs=P, quantile=q, eps=eps,
+                                             generator=torch.Generator().manual_seed(5 + seed))
+    g = torch.Generator().manual_seed(5 + seed)
+    i1 = torch.randint(0, N, (P,), generator=g).numpy()
+    i2 = torch.randint(0, N, (P,), generator=g).numpy()
+    r = lo.lipschitz_ratios(X.numpy(), func(X).numpy(), i1, i2, eps)
+    np.testing.assert_allclose(lo.lipschitz_from_ratios(r, q, eps), got, rtol=1e-10)
