@@ -268,3 +268,35 @@ def _check_sharded_lr(staged, clip, set_style):
         p.join(timeout=60)
         assert p.exitcode == 0
     np.testing.assert_allclose(got, single, rtol=1e-5, atol=1e-7)
+
+
+def test_flat_params_begin_step_and_gather():
+    """begin_step() detaches every .grad so autograd hands gradients over as produced; gather() moves them into the flat
+    buffer (one multi-tensor copy), re-attaches the views, and zeroes the segment of a parameter that stops receiving one."""
+    from vae_song_b200 import train
+    m = _ToyVAE()
+    fp = train.FlatParams(m)
+    x, eps = torch.randn(6, 2), torch.randn(6, 2)
+    ref = _ToyVAE(); ref.load_state_dict(m.state_dict())
+
+    def run(model, use_dec=True):
+        out = model(x, eps=eps)
+        loss = model.loss(x, *out)[0] if use_dec else out[1].pow(2).sum()      # second form: decoder gets no gradient
+        loss.backward()
+
+    fp.begin_step()
+    assert all(p.grad is None for p in m.parameters())
+    run(m)
+    fp.gather()
+    run(ref)
+    for p, q, view in zip(m.parameters(), ref.parameters(), fp.views):
+        assert p.grad.data_ptr() == view.data_ptr()
+        np.testing.assert_allclose(p.grad.numpy(), q.grad.numpy(), rtol=1e-6, atol=1e-8)
+    # padding between parameters stays zero, and the flat buffer is exactly the concatenation of the (padded) gradients
+    assert float(fp.grad.abs().sum()) == pytest.approx(sum(float(q.grad.abs().sum()) for q in ref.parameters()), rel=1e-5)
+    # next step: the decoder receives no gradient -> its segment must read zero, not the stale values
+    fp.begin_step()
+    run(m, use_dec=False)
+    fp.gather()
+    assert float(m.dec.weight.grad.abs().sum()) == 0.0 and float(m.dec.bias.grad.abs().sum()) == 0.0
+    assert float(m.enc[0].weight.grad.abs().sum()) > 0.0
