@@ -300,3 +300,43 @@ def test_flat_params_begin_step_and_gather():
     fp.gather()
     assert float(m.dec.weight.grad.abs().sum()) == 0.0 and float(m.dec.bias.grad.abs().sum()) == 0.0
     assert float(m.enc[0].weight.grad.abs().sum()) > 0.0
+
+
+def _allpairs_worker(rank, world, port, X, Y, out):
+    import torch.distributed as dist
+    from vae_song_b200 import utils
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    # this rank's share of the unordered pairs (any partition combines the same way as the kernel's tile ranges)
+    i, j = np.triu_indices(X.shape[0], 1)
+    mine = (np.arange(i.size) % world) == rank
+    dx = np.maximum(np.sqrt(((X[i[mine]] - X[j[mine]]) ** 2).sum(1)), 1e-3)
+    dy = np.maximum(np.sqrt(((Y[i[mine]] - Y[j[mine]]) ** 2).sum(1)), 1e-3)
+    r = dy / dx
+    stats = torch.tensor([r.max(), r.min(), r.sum(), float(r.size)], dtype=torch.float64)
+    hist = torch.tensor(np.histogram(np.log2(r), bins=8, range=(-4, 4))[0], dtype=torch.float64)
+    stats, hist = utils.combine_allpairs(stats, hist)
+    if rank == 0:
+        out.put((stats.numpy(), hist.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allpairs_partials_combine_across_ranks():
+    """utils.combine_allpairs: MAX / MIN / SUM all-reduce of per-rank [max, min, sum, count] (+ histogram) == the global
+    all-pairs statistics of the oracle (world 3, gloo)."""
+    from oracle import loss_oracle as lo
+    rng = np.random.default_rng(8)
+    X = rng.normal(0, 1, (90, 2)); Y = np.tanh(X @ rng.normal(0, 1, (2, 3))) * 2
+    ref = lo.lipschitz_allpairs(X, Y)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_allpairs_worker, args=(r, 3, port, X, Y, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    stats, hist = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    np.testing.assert_allclose(stats, [ref["max"], ref["min"], ref["sum"], ref["count"]], rtol=1e-10)
+    assert hist.sum() <= ref["count"] and hist.sum() > 0
