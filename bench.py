@@ -10,6 +10,11 @@ ICNN(2,1024) Brenier decoder, synthetic chessboard 2-D points, per-GPU batch 655
 forward -> loss -> backward -> gradient all-reduce (N>1) -> Adam, i.e. lipschitz.py:36-43.
 `value`  : inputs resident in HBM.           `e2e`: same step through the public module API with pinned HOST
 inputs (H2D copy) and the loss read back (D2H) inside the timed region.
+
+`--impl reference` runs the UNMODIFIED reference (oracle/_ref/, populated by oracle/fetch_ref.py in the build container):
+its own `model.LIDVAE` driven by its own loop `lipschitz.train_model` (lipschitz.py:23-44) in PyTorch on the host cores,
+on the SAME config -- batch 65536 per step, encoder and Adam included, same weights, same synthetic data.  The numpy
+oracle port is only the fallback when oracle/_ref/ is absent (the line then says kind "port").
 """
 from __future__ import annotations
 
@@ -111,10 +116,100 @@ class ClockSampler:
             self.proc.terminate()
 
 
-# ----------------------------------------------------------------------------------------- CPU (oracle) arm
+# ----------------------------------------------------------------------------------------- shared workload definition
+WORKLOAD = "configs[1]: LIDVAE(pinwheel/chessboard 2-D, latent 2, encoder [2,2,2,2], ICNN(2,512)+ICNN(2,1024)) train step"
+MODEL_KW = dict(dataset="pinwheel", inverse_lipschitz=0.2, beta=1.0)
+LR = 1e-3
+
+
+def make_config(B, world):
+    """The `config` object of BOTH arms (the reference arm runs "your arm's config"): only what defines the workload."""
+    return {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "step": "forward -> loss -> backward -> Adam(lr 1e-3): lipschitz.py:36-43", "encoder": "included", "optimizer": "Adam lr 1e-3",
+            "weights": "seed 42 init + O(1)-scale ICNN weights (numpy seed 7)", "inputs": "chessboard 2-D points, numpy seed 100+rank",
+            "l2": "flushed between timed iterations (256 MB write) on the GPU; inputs larger than cache on the CPU"}
+
+
+def trained_like_(m):
+    """O(1)-scale random ICNN weights, identical for both arms (default exp(W)~1 init gives 1e20 losses whose squares
+    overflow Adam's v).  Works on the reference's and on this package's LIDVAE (same attribute names)."""
+    import torch
+    wr = np.random.default_rng(7)
+    with torch.no_grad():
+        for ic in (m.decoder[0], m.decoder[1]):
+            H = ic.A0.weight.shape[0]
+            ic.W[0].param.copy_(torch.tensor(wr.normal(np.log(1.0 / H), 1.0, (H, H)), dtype=torch.float32))
+            ic.W[1].param.copy_(torch.tensor(wr.normal(np.log(2.0 / H), 1.0, (1, H)), dtype=torch.float32))
+            ic.A[0].bias.copy_(torch.tensor(wr.normal(-0.3, 1.0, (H,)), dtype=torch.float32))
+    return m
+
+
+# ----------------------------------------------------------------------------------------- reference arm (CPU / same GPU)
+def ref_available():
+    try:
+        from oracle import fetch_ref
+        return fetch_ref.available()
+    except Exception:
+        return False
+
+
+class _TimedLoader:
+    """Feeds `lipschitz.train_model` W + K batches and time-stamps every hand-over: the reference's own loop
+    (lipschitz.py:36-43) runs unmodified and the time between two `__next__` calls is one of its steps.  On CUDA the stamps
+    are events on the current stream (the loop launches everything there) and the L2 is flushed before each step."""
+
+    def __init__(self, batches, device, flush=None):
+        self.batches, self.device, self.flush = batches, device, flush
+        self.marks = []
+
+    def _mark(self):
+        if self.device == "cpu":
+            return time.perf_counter()
+        import torch
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def __iter__(self):
+        for x in self.batches:
+            end_prev = self._mark()
+            if self.flush is not None:
+                self.flush.fill_(1.0)
+            self.marks.append((end_prev, self._mark()))
+            yield x, None
+        self.marks.append((self._mark(), None))
+
+    def step_times_ms(self):
+        out = []
+        for i in range(len(self.marks) - 1):
+            t0, t1 = self.marks[i][1], self.marks[i + 1][0]
+            out.append((t1 - t0) * 1e3 if self.device == "cpu" else t0.elapsed_time(t1))
+        return out
+
+
+def time_reference(batches, device, warmup, flush=None):
+    """UNMODIFIED reference: model.LIDVAE (model.py:637-886) trained by lipschitz.train_model (lipschitz.py:23-44), stock
+    PyTorch (FP32, TF32 off = torch default) on `device`.  Returns per-step ms of the steps after `warmup`."""
+    import torch
+    from oracle import fetch_ref
+    ns = fetch_ref.import_ref()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(42)
+    m = trained_like_(ns.model.LIDVAE(**MODEL_KW))
+    loader = _TimedLoader(batches, "cpu" if device == "cpu" else "cuda", flush)
+    import contextlib, io
+    with contextlib.redirect_stderr(io.StringIO()):          # tqdm progress bar of train_model
+        ns.lipschitz.train_model(m, loader, epochs=1, lr=LR, device=device)
+    if device != "cpu":
+        torch.cuda.synchronize()
+    ts = loader.step_times_ms()
+    return ts[warmup:], fetch_ref.verify()
+
+
 def oracle_step_factory(seed=0):
-    """The oracle port of one LID-VAE decoder train step (decode fwd + double-backward + losses), fp32 numpy
-    (multi-threaded BLAS).  The tiny [2,2,2,2] encoder is omitted (<1% of the flops)."""
+    """FALLBACK when oracle/_ref/ is absent: the oracle port of one LID-VAE decoder train step (decode fwd + double-backward
+    + losses), fp32 numpy (multi-threaded BLAS).  The tiny [2,2,2,2] encoder and Adam are omitted (<1% of the flops)."""
     from oracle import icnn_oracle as io
     from oracle import loss_oracle as lo
     rng = np.random.default_rng(seed)
@@ -132,44 +227,42 @@ def oracle_step_factory(seed=0):
     return step
 
 
-def time_oracle(sample, budget_s=12.0):
-    """Best-of-N wall time of the oracle step on `sample` rows; N sized so that the leg is ~budget_s of CPU work
-    (bounded: 3 <= N <= 40)."""
-    rng = np.random.default_rng(1)
+def cpu_reference_times(B, steps, warmup):
+    """(per-step ms list, kind, note) of the reference's CPU path on this box's host cores at per-step batch B."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(100)
+    if ref_available():
+        batches = [torch.from_numpy(chessboard(B, rng)) for _ in range(min(4, steps + warmup))]
+        batches = [batches[i % len(batches)] for i in range(steps + warmup)]
+        ts, unmodified = time_reference(batches, "cpu", warmup)
+        return ts, "reference", ("unmodified reference (oracle/_ref: model.LIDVAE + lipschitz.train_model, PyTorch CPU FP32, "
+                                 f"{torch.get_num_threads()} threads); files match the fetch-time SHA-256: {unmodified}")
     step = oracle_step_factory()
-    x, eps = chessboard(sample, rng), rng.normal(0, 1, (sample, 2)).astype(np.float32)
-    step(x[:256], eps[:256])
-    t0 = time.perf_counter(); step(x, eps); ts = [time.perf_counter() - t0]
-    reps = max(3, min(40, int(budget_s / max(ts[0], 1e-3))))
-    for _ in range(reps - 1):
-        t0 = time.perf_counter(); step(x, eps); ts.append(time.perf_counter() - t0)
-    return sample / min(ts), float(np.mean(ts)), reps
+    x, eps = chessboard(B, rng), rng.normal(0, 1, (B, 2)).astype(np.float32)
+    ts = []
+    for i in range(steps + warmup):
+        t0 = time.perf_counter(); step(x, eps); ts.append((time.perf_counter() - t0) * 1e3)
+    return ts[warmup:], "port", "oracle/_ref absent: numpy oracle port of the decoder train step (no encoder, no Adam)"
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 8192
-    ts = []
-    rng = np.random.default_rng(1)
-    step = oracle_step_factory()
-    x, eps = chessboard(sample, rng), rng.normal(0, 1, (sample, 2)).astype(np.float32)
-    for _ in range(max(args.warmup, 1)):
-        step(x, eps)
-    for _ in range(args.steps):
-        t0 = time.perf_counter(); step(x, eps); ts.append(time.perf_counter() - t0)
-    ms = 1e3 * float(np.mean(ts))
-    val = sample / (ms * 1e-3)
+    B = args.batch
+    ts, kind, note = cpu_reference_times(B, args.steps, max(args.warmup, 1))
+    ms = float(np.mean(ts))
+    val = B / (ms * 1e-3)
     line = {"impl": "reference", "metric": "LID-VAE train samples/s", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU oracle port (numpy, multithreaded BLAS) of the decoder train step; "
-                       "the reference is pure Python/PyTorch and cannot travel to the GPU box"},
-            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} samples per step x {args.steps} steps"},
+            "config": make_config(B, max(args.gpus, 1)),
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": kind,
+                             "sample": f"{B} samples per step x {args.steps} steps (rank 0 only: one CPU process); {note}"},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def eager_same_gpu(m, x, flush, steps=5):
@@ -302,9 +395,6 @@ def mnist_shaped_times(dev, flush, precision):
     return out
 
 
-WORKLOAD = "configs[1]: LIDVAE(pinwheel/chessboard 2-D, latent 2, encoder [2,2,2,2], ICNN(2,512)+ICNN(2,1024)) train step"
-
-
 # ----------------------------------------------------------------------------------------- GPU arm
 def run_ours(args, rank, local_rank, world):
     import torch
@@ -319,15 +409,8 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(42)
     B = args.batch
-    m = model.LIDVAE(dataset="pinwheel", inverse_lipschitz=0.2, beta=1.0, precision=args.precision).to(dev).train()
-    wr = np.random.default_rng(7)
-    with torch.no_grad():   # O(1)-scale random weights (default exp(W)~1 init gives 1e20 losses whose squares overflow Adam's v)
-        for ic in (m.decoder[0], m.decoder[1]):
-            H = ic.hidden_channel
-            ic.W[0].param.copy_(torch.tensor(wr.normal(np.log(1.0 / H), 1.0, (H, H)), dtype=torch.float32))
-            ic.W[1].param.copy_(torch.tensor(wr.normal(np.log(2.0 / H), 1.0, (1, H)), dtype=torch.float32))
-            ic.A[0].bias.copy_(torch.tensor(wr.normal(-0.3, 1.0, (H,)), dtype=torch.float32))
-    tr = train.DataParallelTrainer(m, lr=1e-3, comm=args.comm)
+    m = trained_like_(model.LIDVAE(precision=args.precision, **MODEL_KW)).to(dev).train()
+    tr = train.DataParallelTrainer(m, lr=LR, comm=args.comm)
     exchange = "none (1 GPU)" if world == 1 else (
         "peer-memory kernels over NVLink: BatchNorm statistics inside the encoder finalize kernels, two-shot gradient "
         "all-reduce fused with Adam (no NCCL call in the step)" if tr.peer is not None else
@@ -463,63 +546,233 @@ def run_ours(args, rank, local_rank, world):
             byp[pname] = {"decode_ms_H512": res[512], "decode_ms_H1024": res[1024], "decode_samples_per_s": both,
                           "tflops_H1024": vutils.flops_decode(2, 1024) * Bk / (res[1024] * 1e-3) / 1e12,
                           "tflops_2icnn": both * (vutils.flops_decode(2, 512) + vutils.flops_decode(2, 1024)) / 1e12}
-        rp = args.roofline_precision
-        ach = byp[rp]["tflops_H1024"]
-        try:      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture (profiles/)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"icnn_decode_fwd_{rp}_H1024_B65536")
+        try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures
+            traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except Exception:
-            traffic = None
-        tensor_peak = pk["bf16_tflops"] / 2 if rp.startswith("tf32") else pk["bf16_tflops"]
-        roof = {"bound": "tensor", "kernel": f"icnn_decode_fwd (psi + grad psi), d=2, H=1024, B=65536, {rp}", "achieved": ach,
-                "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak, "traffic": traffic,
-                "peak_kind": f"{pk_kind} cuBLAS bf16 burst" + (" / 2 (TF32 runs at half the bf16 rate)" if rp.startswith("tf32") else ""),
-                "precision": rp, "kernel_ms": byp[rp]["decode_ms_H1024"],
-                "algorithmic_flop_per_sample": vutils.flops_decode(2, 1024),
-                "note": "achieved = algorithmic flops / CUDA-event time; tf32x3 executes 3 MMAs per algorithmic MAC, "
-                        "fp32 is the SIMT parity path (FP32 FMA peak 74.4 TFLOP/s at 1965 MHz)"}
-        # the SAME kernel in the arithmetic mode the timed step ran in (tf32x3 executes 3 MMAs per MAC in GEMM1 and 2 in GEMM2,
-        # whose generated operand is exact in tf32: 2.5 executed flops per algorithmic flop)
-        sp = args.precision
-        mult = {"fp32": 1.0, "tf32": 1.0, "tf32x3": 2.5}[sp]
-        sp_peak = 74.4 if sp == "fp32" else pk["bf16_tflops"] / 2
-        roof["step_precision_kernel"] = {
-            "precision": sp, "kernel_ms": byp[sp]["decode_ms_H1024"], "achieved": byp[sp]["tflops_H1024"],
-            "executed": byp[sp]["tflops_H1024"] * mult, "peak": sp_peak, "unit": "TFLOP/s",
-            "frac": byp[sp]["tflops_H1024"] / sp_peak, "frac_executed": byp[sp]["tflops_H1024"] * mult / sp_peak,
-            "bound": "fp32 fma pipe" if sp == "fp32" else "tensor"}
+            traffic_tab = {}
+        mult_of = {"fp32": 1.0, "tf32": 1.0, "tf32x3": 2.5}   # executed / algorithmic flops (3 MMAs per MAC in GEMM1, 2 in GEMM2)
+
+        def kernel_roof(pn):
+            peak = 74.4 if pn == "fp32" else pk["bf16_tflops"] / 2
+            ach = byp[pn]["tflops_H1024"]
+            return {"bound": "fp32 fma pipe" if pn == "fp32" else "tensor", "precision": pn,
+                    "kernel": f"icnn_decode_fwd (psi + grad psi), d=2, H=1024, B=65536, {pn}",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "executed": ach * mult_of[pn], "frac_executed": ach * mult_of[pn] / peak,
+                    "kernel_ms": byp[pn]["decode_ms_H1024"],
+                    "traffic": traffic_tab.get(f"icnn_decode_fwd_{pn}_H1024_B65536"),
+                    "traffic_source": "static: one `ncu --set full` capture of this kernel committed under profiles/ "
+                                      "(profiles/traffic.json), not re-measured in this run",
+                    "peak_kind": "FP32 FMA peak 148 SM x 128 x 2 x 1.965 GHz" if pn == "fp32" else
+                                 f"{pk_kind} cuBLAS bf16 burst / 2 (TF32 runs at half the bf16 rate)"}
+        # `roofline` describes the dominant kernel IN THE ARITHMETIC THE TIMED STEP RAN IN (dtype of this line).  achieved /
+        # frac count ALGORITHMIC flops (4H^2+8dH+2H+4d per sample); 3xTF32 executes 2.5 tensor flops per
+        # algorithmic flop, so an fp32-grade kernel that keeps the tensor pipe full sits at frac ~0.4 and frac_executed ~1.
+        # No mode is both >= 0.9 of the tensor roofline and inside the FP32 bounds: `by_precision.tf32` is the >= 0.9 mode
+        # (bounds psi 2e-4 / xhat 5e-3), the step's tf32x3 is the fp32-grade mode (bounds in DESIGN.md section 4).
+        rp = args.roofline_precision or args.precision
+        roof = kernel_roof(rp)
+        roof["algorithmic_flop_per_sample"] = vutils.flops_decode(2, 1024)
+        roof["precision_equals_step_dtype"] = (rp == args.precision)
+        roof["by_precision"] = {pn: kernel_roof(pn) for pn in ("tf32", "tf32x3", "fp32")}
+        step_flop = vutils.flops_train(2, 512) + vutils.flops_train(2, 1024)
+        step_tf = step_flop * B / (ms * 1e-3) / 1e12
+        step_peak = 74.4 if args.precision == "fp32" else pk["bf16_tflops"] / 2
+        roof["train_step"] = {"bound": roof["bound"], "precision": args.precision, "achieved": step_tf, "peak": step_peak,
+                              "unit": "TFLOP/s", "frac": step_tf / step_peak, "algorithmic_flop_per_sample": step_flop,
+                              "ms_per_step": ms, "note": "whole timed step (encoder, loss, Adam, exchange included in the time), "
+                              "decoder flops 8H^2+22dH per ICNN only"}
         extra = {"decode_by_precision": byp, "train_step_by_precision": by_prec_train,
                  "pytorch_eager_same_gpu": eager_same_gpu(m, dev_pool[0], flush) if world == 1 else None,
                  "lipschitz_estimator": lipschitz_times(m, dev),
-                 "mnist_shaped_decoder": mnist_shaped_times(dev, flush, args.precision)}
-        sample = 8192
-        cpu = None                                   # the CPU baseline is timed at N = 1 only (the other ranks would idle)
+                 "mnist_shaped_decoder": mnist_shaped_times(dev, flush, args.precision) if world == 1 else None}
+        # ---- the UNMODIFIED reference on THIS GPU (stock PyTorch eager CUDA, FP32, same config) and on the host cores ----
+        ref_gpu, cpu = None, None
         if world == 1:
-            cpu_val, cpu_s, cpu_reps = time_oracle(sample)
-            cpu = {"value": cpu_val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"oracle port (numpy fp32), decoder train step on {sample} samples, best of {cpu_reps} "
-                             f"({cpu_s:.2f} s each, {cpu_reps * cpu_s:.0f} s of CPU work)"}
+            if ref_available():
+                nref = 6
+                ts, unmodified = time_reference([dev_pool[i % n_pool] for i in range(nref + 2)], dev, 2, flush)
+                rms = float(np.mean(ts))
+                ref_gpu = {"value": B / (rms * 1e-3), "unit": "samples/s", "ms_per_step": rms, "steps": len(ts), "batch": B,
+                           "speedup_of_this_arm": rms / ms, "unmodified": unmodified,
+                           "what": "oracle/_ref model.LIDVAE + lipschitz.train_model, stock PyTorch eager on this GPU, FP32 "
+                                   "(TF32 off), same weights / batch / data, L2 flushed between steps, inputs resident"}
+            csteps = 3
+            ts, kind, note = cpu_reference_times(B, csteps, 1)
+            cms = float(np.min(ts))
+            cpu = {"value": B / (cms * 1e-3), "unit": "samples/s", "cores": os.cpu_count(), "kind": kind,
+                   "sample": f"{csteps} steps of {B} samples after 1 warm-up, best step {cms / 1e3:.2f} s "
+                             f"({sum(ts) / 1e3:.0f} s of CPU work); {note}"}
         line = {"metric": "LID-VAE train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
-                "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "precision": args.precision,
-                           "parallelism": f"dp{world}", "l2": "flushed between timed iterations (256 MB write)",
-                           "optimizer": "fused Adam lr 1e-3 over flat buffer", "exchange": exchange,
-                           "exchange_ok": exchange_ok,
-                           "cuda_graph": bool(use_graph), "own_kernel_launches_per_step": int(launches_per_step)},
+                "config": make_config(B, world),
+                "run": {"precision": args.precision, "optimizer_impl": "fused Adam over the flat parameter buffer",
+                        "exchange": exchange, "exchange_ok": exchange_ok, "cuda_graph": bool(use_graph),
+                        "own_kernel_launches_per_step": int(launches_per_step)},
                 "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 2 * 4 * world,
                         "d2h_bytes_per_step": 4 * world},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extra": extra}
-        print(json.dumps(line), flush=True)
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "reference_same_gpu": ref_gpu, "extra": extra}
     if sampler:
         sampler.stop()
+    # ---- multi-GPU: parity of the exchange path and the sharded all-pairs estimator, reported in the same line ----
     if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-    # Tearing down NCCL communicators that are referenced by a live CUDA graph can block for minutes:
-    # release the graph first and leave without the (optional) communicator destruction.
-    tr._graph = None
+        par = exchange_parity(dev, rank, world)
+        ap_sh = allpairs_sharded_times(m, dev, rank, world, tr.peer)
+        if rank == 0:
+            line["exchange_parity"] = par
+            line["extra"]["allpairs_sharded"] = ap_sh
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     sys.stdout.flush()
-    os._exit(0)
+    # Normal interpreter exit (at-exit hooks run).  The graph is released first: tearing down NCCL communicators that a
+    # live CUDA graph still references can block; a watchdog turns a stuck teardown into a plain exit after 60 s.
+    tr._graph = None
+    del tr
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    if world > 1:
+        import atexit
+
+        def _bail():
+            try:
+                atexit._run_exitfuncs()
+            finally:
+                os._exit(0)
+        wd = threading.Timer(60.0, _bail)
+        wd.daemon = True
+        wd.start()
+        dist.barrier()
+        dist.destroy_process_group()
+        wd.cancel()
+
+
+def exchange_parity(dev, rank, world, k=4):
+    """k Adam steps from a fixed seed on a small LID-VAE (ICNN 128/256, FP32 kernels, global batch 1024): the batch-sharded
+    run with the peer-memory exchange (eager and graph-replayed) and with the NCCL exchange against ONE process training on
+    the full batch.  Collective; rank 0 returns the record."""
+    import torch
+    import torch.distributed as dist
+    from vae_song_b200 import model, train
+
+    def make():
+        torch.manual_seed(0)
+        mm = model.LIDVAE(dataset="pinwheel", icnn_channels=[128, 256], hidden_channels=[16, 8], inverse_lipschitz=0.2,
+                          beta=0.5, precision="fp32")
+        rng = np.random.default_rng(3)
+        with torch.no_grad():
+            for ic in (mm.decoder[0], mm.decoder[1]):
+                H = ic.hidden_channel
+                ic.W[0].param.copy_(torch.tensor(rng.normal(np.log(1.0 / H), 1.0, (H, H)), dtype=torch.float32))
+                ic.W[1].param.copy_(torch.tensor(rng.normal(np.log(2.0 / H), 1.0, (1, H)), dtype=torch.float32))
+                ic.A[0].bias.copy_(torch.tensor(rng.normal(-0.3, 1.0, (H,)), dtype=torch.float32))
+        return mm.to(dev).train()
+
+    solo = dist.new_group(ranks=[0])
+    Bg = 1024
+    g = torch.Generator(device="cpu").manual_seed(5)
+    X = [torch.randn(Bg, 2, generator=g) for _ in range(k)]
+    E = [torch.randn(Bg, 2, generator=g) for _ in range(k)]
+    lo, hi = train.shard_rows(Bg, rank, world)
+    single_losses = single_flat = None
+    if rank == 0:
+        ref = train.DataParallelTrainer(make(), lr=1e-3, process_group=solo)
+        ref.world, ref.rank = 1, 0
+        single_losses = [float(ref.step(x.to(dev), e.to(dev))[0]) for x, e in zip(X, E)]
+        single_flat = ref.fp.flat.clone()
+    out = {"steps": k, "global_batch": Bg, "world": world}
+    flats = {}
+    for name, mode, graphed in (("nccl", "nccl", False), ("peer", "peer", False), ("peer_graph", "peer", True)):
+        try:
+            tr = train.DataParallelTrainer(make(), lr=1e-3, comm=mode)
+        except Exception as exc:                                # noqa: BLE001  (peer mapping unavailable: reported, not fatal)
+            out[name] = {"error": str(exc)[:200]}
+            continue
+        if graphed:
+            tr.capture(X[0][lo:hi].to(dev), E[0][lo:hi].to(dev))
+        losses = []
+        for x, e in zip(X, E):
+            stepf = tr.step_graphed if graphed else tr.step
+            total = stepf(x[lo:hi].to(dev), e[lo:hi].to(dev))[0]
+            losses.append(float(tr.global_losses(total)[0]))
+        timed_out = False
+        try:
+            tr.check()
+        except Exception:                                       # noqa: BLE001
+            timed_out = True
+        mine = tr.fp.flat[:tr.fp.numel].clone()
+        ref0 = mine.clone()
+        dist.broadcast(ref0, src=0)
+        flag = torch.tensor([int(torch.equal(mine, ref0))], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        flats[name] = mine
+        if rank == 0:
+            n = min(mine.numel(), single_flat.numel())
+            out[name] = {"replicas_bit_identical": bool(int(flag) == 1), "exchange_timed_out": timed_out,
+                         "max_rel_param_diff_vs_single_process": float((mine[:n] - single_flat[:n]).abs().max() / single_flat.abs().max()),
+                         "max_rel_loss_diff_vs_single_process": max(abs(p - q) / abs(q) for p, q in zip(losses, single_losses)),
+                         "losses": losses}
+        tr._graph = None
+        del tr
+    if rank == 0:
+        out["single_process_losses"] = single_losses
+        if "peer" in flats and "nccl" in flats:
+            out["max_rel_diff_peer_vs_nccl_path"] = float((flats["peer"] - flats["nccl"]).abs().max() / flats["nccl"].abs().max())
+        ok = [v for v in out.values() if isinstance(v, dict) and "replicas_bit_identical" in v]
+        out["pass"] = bool(ok) and all(v["replicas_bit_identical"] and not v["exchange_timed_out"] and
+                                       v["max_rel_param_diff_vs_single_process"] < 5e-4 and
+                                       v["max_rel_loss_diff_vs_single_process"] < 2e-4 for v in ok)
+    return out
+
+
+def allpairs_sharded_times(m, dev, rank, world, peer):
+    """north_star: "the Lipschitz estimator shards pair tiles" -- utils.estimate_lipschitz_allpairs over N ranks (decode rows
+    and pair tiles sharded, statistics combined by ONE peer-memory all-gather) against rank 0 alone, with device timings."""
+    import torch
+    import torch.distributed as dist
+    from vae_song_b200 import utils as vutils
+    solo = dist.new_group(ranks=[0])
+    res = {}
+    mm = m.eval()
+    for N in (5000, 50000):
+        torch.manual_seed(9)
+        X = torch.randn(N, 2, device=dev)
+        dist.broadcast(X, src=0)
+
+        def t(fn, n=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize(); dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                out = fn()
+            e1.record(); torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms), out
+        sh_ms, sh = t(lambda: vutils.estimate_lipschitz_allpairs(mm.decode, X, peer=peer))
+        if rank == 0:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(2):
+                one = vutils.estimate_lipschitz_allpairs(mm.decode, X, process_group=solo)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                one = vutils.estimate_lipschitz_allpairs(mm.decode, X, process_group=solo)
+            e1.record(); torch.cuda.synchronize()
+            one_ms = e0.elapsed_time(e1) / 5
+            pairs = N * (N - 1) // 2
+            res[f"N{N}"] = {"pairs": pairs, "sharded_ms": sh_ms, "single_rank_ms": one_ms, "speedup": one_ms / sh_ms,
+                            "sharded_pairs_per_s": pairs / (sh_ms * 1e-3),
+                            "equal": bool(sh["count"] == one["count"] == pairs and sh["max"] == one["max"] and sh["min"] == one["min"]
+                                          and abs(sh["mean"] - one["mean"]) <= 1e-6 * abs(one["mean"])),
+                            "includes": "decode of this rank's rows + all-gather of Y + pair tiles + combine + host read-back"}
+        dist.barrier()
+    m.train()
+    return res
 
 
 def main():
@@ -534,7 +787,8 @@ def main():
     ap.add_argument("--comm", default="auto", choices=["auto", "peer", "nccl"],
                     help="multi-GPU exchange back-end (train.DataParallelTrainer): peer-memory kernels or NCCL")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--roofline-precision", default="tf32", choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--roofline-precision", default=None, choices=["fp32", "tf32", "tf32x3"],
+                    help="precision of the kernel described by `roofline` (default: the step's --precision)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

@@ -117,14 +117,19 @@ int b200vae_loss_bwd(const float* mu, const float* lv, const float* eps, const f
 int b200vae_lipschitz_pairs(const float* X, const float* Y, const int64_t* i1, const int64_t* i2, int P,
                             int N, int dx, int dy, float eps, float* ratio, void* stream);
 
-/* Tiled all-pairs estimator (north_star kernel 4): over unordered pairs i<j whose 64x64 tile index
- * t (row-major over the upper triangle incl. diagonal tiles) satisfies tile_begin <= t < tile_end.
- *   stats [4] fp64: max, min, sum, count -- overwritten;
- *   hist [nbins] uint32 or NULL: log2-spaced histogram of ratios over [2^hist_lo, 2^hist_hi).
- * Shard tiles across ranks and combine stats with MAX/MIN/SUM all-reduces. */
+/* Tiled all-pairs estimator (north_star kernel 4; replaces the random-pair sampling of utils.py:544-562 by EVERY pair,
+ * same per-pair formula utils.py:560-562): over unordered pairs i<j whose 64x64 tile index t (row-major over the upper
+ * triangle incl. diagonal tiles) satisfies tile_begin <= t < tile_end.
+ *   stats [4] fp64: max, min, sum, count -- overwritten (an empty range gives 0, DBL_MAX, 0, 0);
+ *   hist [nbins] uint32 or NULL: log2-spaced histogram of ratios over [2^hist_lo, 2^hist_hi) -- overwritten;
+ *   scratch: b200vae_lipschitz_scratch_bytes() bytes, 16-byte aligned: ordered per-CTA partials + a ticket.  It must be
+ *   ZERO before the first call and is left ready by every call (one zero-initialised buffer per stream can be reused).
+ * ONE kernel launch; max/min/sum are combined in a fixed order (bit-reproducible).  Shard tiles across ranks and combine
+ * the per-rank stats with MAX/MIN/SUM. */
+size_t b200vae_lipschitz_scratch_bytes(void);
 int b200vae_lipschitz_allpairs(const float* X, const float* Y, int N, int dx, int dy, float eps,
                                long long tile_begin, long long tile_end, double* stats, uint32_t* hist,
-                               int nbins, float hist_lo, float hist_hi, void* stream);
+                               int nbins, float hist_lo, float hist_hi, void* scratch, void* stream);
 long long b200vae_lipschitz_num_tiles(int N);
 
 /* Fused Adam step over a flat fp32 parameter buffer (torch.optim.Adam semantics, lipschitz.py:25,43):
@@ -218,8 +223,11 @@ int b200vae_mi_logqz(const float* z, const float* mu, const float* lv, int B, in
  * 64-byte handles out of band (torch.distributed.all_gather_object), maps the others with b200vae_peer_open and
  * fills a b200vae_peer_t with buf[r] = rank r's buffer as addressable from THIS process (own buffer at buf[rank]).
  * A host barrier must separate set-up from the first exchange.  Every rank must issue the same sequence of
- * exchanges per slot (they are collective).  A peer that never arrives times out after 20 s (no GPU hang) and sets a
- * sticky per-rank flag readable with b200vae_peer_timed_out; later exchanges on that rank then no longer wait. */
+ * exchanges per slot (they are collective).  NO RANK MAY LAG ANOTHER BY MORE THAN THE TIMEOUT (20 s; environment variable
+ * B200VAE_PEER_TIMEOUT_S, read once per process, overrides): a peer that does not arrive in time sets a sticky per-rank
+ * flag (no GPU hang) readable with b200vae_peer_timed_out; later exchanges on that rank no longer wait, and from then on
+ * every exchange returns NaN payloads and b200vae_peer_allreduce_adam writes NaN parameters, so the failure cannot go
+ * unnoticed. */
 #define B200VAE_PEER_MAX_WORLD 16
 #define B200VAE_PEER_HANDLE_BYTES 64
 typedef struct b200vae_peer {

@@ -184,7 +184,10 @@ def test_tc_forward_workspace_reuse_and_mask_paths():
 def test_saved_accumulator_backward_equals_recompute(shape):
     """3xTF32 training: the pair forward keeps its GEMM2 accumulators in the for_backward workspace and the backward reads
     them back (icnn_tc3.cu SV kernels) instead of redoing that GEMM.  Re-running prepare on the workspace invalidates the
-    save (host bookkeeping, api.cu), so the same backward then RECOMPUTES -- both must give identical results."""
+    save (host bookkeeping, api.cu), so the same backward then RECOMPUTES.  The saved accumulators come from the forward's
+    K-chunked accumulation (chunks of 256 added with round-to-nearest FP32 adds, icnn_tc3.cu), the recomputed ones from one
+    plain accumulator: the two backward results agree to the accumulation error of the plain path (<= 2e-5 of the largest
+    entry; they were bit-identical before the forward accumulated in chunks) and the decode itself is unchanged."""
     from vae_song_b200 import _C, ops
     import ctypes as C
     d, H, B = shape
@@ -204,10 +207,14 @@ def test_saved_accumulator_backward_equals_recompute(shape):
         torch.cuda.synchronize()
         res.append((xhat.clone(), dz.clone(), [g.clone() for g in grads]))
     assert torch.equal(res[0][0], res[1][0])
-    assert torch.equal(res[0][1], res[1][1]), float((res[0][1] - res[1][1]).abs().max())
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+    assert rel(res[0][1], res[1][1]) <= 2e-5, rel(res[0][1], res[1][1])
     for k, a, b in zip(KEYS, res[0][2], res[1][2]):
-        assert torch.equal(a, b), (k, float((a - b).abs().max()))
-    if B > 2000:        # BASELINE batch: the bit-identity above is the size-independent check
+        if float(b.abs().max()) > 0:
+            assert rel(a, b) <= 2e-5, (k, rel(a, b))
+        else:
+            assert torch.equal(a, b), k
+    if B > 2000:        # BASELINE batch: the agreement above is the size-independent check
         return
     # and against the fp64 oracle (3xTF32 bounds)
     rdz, rg = io.icnn_brenier_backward(f32_as_f64(z.cpu().numpy()), f32_as_f64(v.cpu().numpy()), params_f32_as_f64(p), 0, 0.1, None)

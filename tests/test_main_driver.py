@@ -29,6 +29,26 @@ def test_configs_build_the_reference_models():
             assert {"epochs", "batch_size", "dataset_name", "num_mc_samples", "grad_clip"} <= set(kw)
 
 
+def test_repeats_do_not_collide_and_runs_are_seeded():
+    """niter > 1 (main.py:423: the outer repeat loop): every repeat gets its own results key and run directory suffix; the
+    run directory carries the reference's " %m%d%H%M" timestamp; run_experiment seeds random / numpy / torch with 42
+    (main.py:31-36)."""
+    import random
+    from vae_song_b200 import main as M
+    cfg = M.load_config(os.path.join(ROOT, "configs", "config_pinwheel.yaml"))
+    cfg["common_params"]["niter"] = 3
+    built = list(M.iter_models(cfg))
+    tags = [t for t, _, _ in built]
+    assert len(tags) == len(set(tags)) and all(t.rsplit("_r", 1)[1] in "012" for t in tags)
+    assert sorted({kw["run_tag"] for _, _, kw in built}) == [0, 1, 2]
+    cfg["common_params"]["niter"] = 1
+    assert all("run_tag" not in kw for _, _, kw in M.iter_models(cfg))
+    M.seed_everything()
+    a = (random.random(), float(np.random.rand()), float(torch.rand(())))
+    M.seed_everything(42)
+    assert a == (random.random(), float(np.random.rand()), float(torch.rand(())))
+
+
 def test_synthetic_datasets_have_the_reference_shapes():
     from vae_song_b200 import main as M
     for name, shape in (("pinwheel", (2,)), ("chessboard", (2,)), ("mnist", (1, 28, 28)), ("cifar10", (3, 32, 32)),
@@ -98,7 +118,9 @@ def test_run_experiment_trains(cfg, tmp_path):
         assert h["train"][-1][0] < h["train"][0][0]
     run_dir = os.path.join(str(tmp_path), os.listdir(str(tmp_path))[0])
     sub = os.path.join(run_dir, os.listdir(run_dir)[0])
-    assert os.path.exists(os.path.join(sub, "params", "3.pt")) and os.path.exists(os.path.join(sub, "history.json"))
+    # main.py:307-310: the last epoch's state_dict under its 0-based index (utils.py:365 / test.py look for model_<E-1>.pt)
+    assert os.path.exists(os.path.join(sub, "params", "model_2.pt")) and os.path.exists(os.path.join(sub, "history.json"))
+    assert h["checkpoint"].endswith(os.path.join("params", "model_2.pt"))
 
 
 @pytest.mark.gpu

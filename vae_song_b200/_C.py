@@ -25,7 +25,7 @@ _ERR = {-1: "bad shape", -2: "unsupported configuration", -3: "null or misaligne
 EXPORTS = [
     "b200vae_icnn_workspace_bytes", "b200vae_icnn_prepare", "b200vae_icnn_decode_fwd", "b200vae_icnn_decode_bwd",
     "b200vae_loss_fwd", "b200vae_loss_bwd", "b200vae_lipschitz_pairs", "b200vae_lipschitz_allpairs",
-    "b200vae_lipschitz_num_tiles", "b200vae_adam_step", "b200vae_adam_step_dev", "b200vae_adam_step_sched", "b200vae_mlp_scratch_bytes", "b200vae_mlp_layer_fwd",
+    "b200vae_lipschitz_num_tiles", "b200vae_lipschitz_scratch_bytes", "b200vae_adam_step", "b200vae_adam_step_dev", "b200vae_adam_step_sched", "b200vae_mlp_scratch_bytes", "b200vae_mlp_layer_fwd",
     "b200vae_mlp_layer_bwd_reduce", "b200vae_mlp_layer_bwd", "b200vae_nn_sqdist_fwd", "b200vae_nn_sqdist_bwd", "b200vae_last_cuda_error", "b200vae_version",
     "b200vae_launch_count",
     "b200vae_peer_exchange_bytes", "b200vae_peer_num_slots", "b200vae_peer_max_payload", "b200vae_peer_alloc", "b200vae_peer_open",
@@ -95,7 +95,9 @@ def load():
     lib.b200vae_lipschitz_pairs.restype = i
     lib.b200vae_lipschitz_pairs.argtypes = [vp, vp, vp, vp, i, i, i, i, f, vp, vp]
     lib.b200vae_lipschitz_allpairs.restype = i
-    lib.b200vae_lipschitz_allpairs.argtypes = [vp, vp, i, i, i, f, ll, ll, vp, vp, i, f, f, vp]
+    lib.b200vae_lipschitz_allpairs.argtypes = [vp, vp, i, i, i, f, ll, ll, vp, vp, i, f, f, vp, vp]
+    lib.b200vae_lipschitz_scratch_bytes.restype = sz
+    lib.b200vae_lipschitz_scratch_bytes.argtypes = []
     lib.b200vae_lipschitz_num_tiles.restype = ll
     lib.b200vae_lipschitz_num_tiles.argtypes = [i]
     lib.b200vae_adam_step.restype = i

@@ -17,6 +17,7 @@
 //     through an L2-resident scratch; a per-(tile, rank) counter orders GEMM2 after GEMM1 and elects the last
 //     unit of a tile to combine the partials in a FIXED order (bit-reproducible, no float atomics).
 // Reference lines replaced: module.py:142-148 (ICNN.forward) and model.py:820-822 / 826-828 (grad of psi).
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -149,7 +150,10 @@ struct alignas(64) Tc3Args {
   float4 *scr1, *scr2;
   uint32_t* cnt;
   float* accsave;                                 // [T*256][Hq] GEMM2 accumulators (gx1 / s2) kept for the backward, or null
+  float4* cscr;                                   // K-chunk running sums (Tc3Layout::cscr), used when NC > 1
   int B, Hq, T, NP, mask_stride, mask_rows, want_x;
+  int NC;                                         // K-chunks per unit (3xTF32: Hq / kTc3ChunkK; 1 = plain accumulation)
+  uint32_t park_ns;                               // suspend-time hint of the epilogue warps' accumulator waits
   float kappa;
 };
 
@@ -226,9 +230,46 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
     // =========================== epilogue warps: my row, 128 of the unit's 256 columns ===========================
     const int row = (warp & 3) * 32 + lane, chalf = warp >> 2;
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chalf * 128);
+    // K-chunked accumulation (NC > 1): chunks 0 .. NC-2 of a unit are only drained and added (round to nearest) into the
+    // running sums in `mysum` -- slot q of this thread = its columns 4q .. 4q+3, laid out [q][row] so that a warp's
+    // accesses are contiguous; nobody else touches these slots -- and the last chunk's epilogue starts from those sums.
+    const int NC = X3 ? a.NC : 1;
+    float4* mysum = a.cscr + ((size_t)((cid * 2 + (int)rank) * 2 + chalf) * 32) * k3Rows + row;
     int i = 0;
     for (int u = cid; u < U; u += G, ++i) {
       const Unit un = decode_unit(u, T, NP);
+      for (int ck = 0; ck + 1 < NC; ++ck, ++i) {
+        const int pbuf = i & 1;
+        mbar_wait_parked(accfull0 + 8 * pbuf, (i >> 1) & 1, a.park_ns);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t r[32];
+          tmem_ld32(taddr + pbuf * 256 + cc * 32, r);
+          tmem_ld_wait();
+          float4* slot = mysum + (size_t)(cc * 8) * k3Rows;
+          // loads batched four at a time: interleaved with the stores they would serialise into one L2 round trip each
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float4 t[4];
+            if (ck > 0) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) t[q] = __ldcg(slot + (size_t)(4 * h + q) * k3Rows);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int e = 4 * (4 * h + q);
+              float4 s = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]),
+                                     __uint_as_float(r[e + 3]));
+              if (ck > 0) { s.x += t[q].x; s.y += t[q].y; s.z += t[q].z; s.w += t[q].w; }
+              __stcg(slot + (size_t)(4 * h + q) * k3Rows, s);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(lead_accempty0 + 8 * pbuf);
+      }
       const int buf = i & 1;
       const int grow = un.t * 256 + (int)rank * k3Rows + row;
       const size_t sidx = ((size_t)grow * NP + un.p) * 2 + chalf;
@@ -237,16 +278,30 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
 #pragma unroll
         for (int j = 0; j < D; ++j) zr[j] = grow < a.B ? a.z[(size_t)grow * D + j] : 0.f;
       }
-      mbar_wait_parked(accfull0 + 8 * buf, (i >> 1) & 1, 2000);
+      mbar_wait_parked(accfull0 + 8 * buf, (i >> 1) & 1, a.park_ns);
       tc_fence_after();
+      // r = TMEM accumulator columns [32 cc, 32 cc + 32) of my row (+ the running sums of the earlier chunks)
+      auto load_acc = [&](uint32_t (&r)[32], int cc) {
+        tmem_ld32(taddr + buf * 256 + cc * 32, r);
+        tmem_ld_wait();
+        if (NC > 1) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = __ldcg(mysum + (size_t)(cc * 8 + q) * k3Rows);
+            r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + t.x);
+            r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + t.y);
+            r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + t.z);
+            r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + t.w);
+          }
+        }
+      };
       if (!un.g) {
         float h2p = 0.f, tp[3] = {0.f, 0.f, 0.f};
         uint32_t words[4];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           uint32_t r[32];
-          tmem_ld32(taddr + buf * 256 + cc * 32, r);
-          tmem_ld_wait();
+          load_acc(r, cc);
           const int nb = un.p * 256 + chalf * 128 + cc * 32;
           uint32_t word = 0;
 #pragma unroll
@@ -276,8 +331,7 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           uint32_t r[32];
-          tmem_ld32(taddr + buf * 256 + cc * 32, r);
-          tmem_ld_wait();
+          load_acc(r, cc);
           const int nb = un.p * 256 + chalf * 128 + cc * 32;
           if (a.accsave != nullptr) {            // training: the backward reads this back instead of redoing GEMM2
             float* dst = a.accsave + (size_t)grow * Hq + nb;      // 128 contiguous bytes per thread: 4 x 256-bit stores
@@ -540,47 +594,52 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
     // Converged warp, one elected lane issues.  Descriptors advance by constants: +2 (32 B) per K=8 step,
     // +kSubBytes/16 per K-block, +kStageBytes/16 per stage.
     const uint64_t descA0 = make_desc_sw64(smem_u32(stages));
+    const int NC = X3 ? a.NC : 1, kb_per_chunk = NKB / NC;                       // NKB / NC is even (chunks of whole stages)
     uint32_t it = 0;
     int i = 0;
-    for (int u = cid; u < U; u += G, ++i) {
+    for (int u = cid; u < U; u += G) {
       const Unit un = decode_unit(u, T, NP);
-      const int buf = i & 1;
       const int nreal = un.g ? NKB : NKB + 1, npad = (nreal + 1) & ~1;
-      mbar_wait(accempty0 + 8 * buf, ((i >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t d_t = tmem_base + (uint32_t)(buf * 256);
-      for (int kb = 0; kb < npad; kb += 2, it += 2) {
-        const uint32_t s = (it >> 1) % S, ph = ((it >> 1) / S) & 1;
-        mbar_wait(full0 + 8 * s, ph);
+      int kb = 0;
+      for (int ck = 0; ck < NC; ++ck, ++i) {                            // one accumulator per K-chunk
+        const int buf = i & 1;
+        const int kb0 = kb, kb1 = (ck == NC - 1) ? npad : kb + kb_per_chunk;
+        mbar_wait(accempty0 + 8 * buf, ((i >> 1) & 1) ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t a0 = descA0 + (uint64_t)(s * (C::kStageBytes >> 4));
+        const uint32_t d_t = tmem_base + (uint32_t)(buf * 256);
+        for (; kb < kb1; kb += 2, it += 2) {
+          const uint32_t s = (it >> 1) % S, ph = ((it >> 1) / S) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a0 = descA0 + (uint64_t)(s * (C::kStageBytes >> 4));
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            if (sub == 1 && kb + 1 >= nreal) break;                     // dummy block of a GEMM1 unit
+            for (int sub = 0; sub < 2; ++sub) {
+              if (sub == 1 && kb + 1 >= nreal) break;                   // dummy block of a GEMM1 unit
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t a_hi = a0 + (uint64_t)(sub * (C::kSubBytes >> 4) + ks * 2);
-              const uint64_t b_hi = a_hi + (uint64_t)(C::kOffB >> 4);
-              const uint32_t acc = (kb | sub | ks) ? 1u : 0u;
-              if (X3) {
-                const uint64_t b_lo = a_hi + (uint64_t)(C::kOffBlo >> 4);
-                if (!un.g) {                                            // GEMM2's A operand is exact: no a_lo term
-                  umma_tf32_pair(d_t, a_hi + (uint64_t)(C::kOffAlo >> 4), b_hi, acc);
-                  umma_tf32_pair(d_t, a_hi, b_lo, 1u);
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t a_hi = a0 + (uint64_t)(sub * (C::kSubBytes >> 4) + ks * 2);
+                const uint64_t b_hi = a_hi + (uint64_t)(C::kOffB >> 4);
+                const uint32_t acc = ((kb - kb0) | sub | ks) ? 1u : 0u;
+                if (X3) {
+                  const uint64_t b_lo = a_hi + (uint64_t)(C::kOffBlo >> 4);
+                  if (!un.g) {                                          // GEMM2's A operand is exact: no a_lo term
+                    umma_tf32_pair(d_t, a_hi + (uint64_t)(C::kOffAlo >> 4), b_hi, acc);
+                    umma_tf32_pair(d_t, a_hi, b_lo, 1u);
+                  } else {
+                    umma_tf32_pair(d_t, a_hi, b_lo, acc);
+                  }
+                  umma_tf32_pair(d_t, a_hi, b_hi, 1u);
                 } else {
-                  umma_tf32_pair(d_t, a_hi, b_lo, acc);
+                  umma_tf32_pair(d_t, a_hi, b_hi, acc);
                 }
-                umma_tf32_pair(d_t, a_hi, b_hi, 1u);
-              } else {
-                umma_tf32_pair(d_t, a_hi, b_hi, acc);
               }
             }
+            umma_commit_pair(empty0 + 8 * s);                           // frees the stage in both CTAs
+            if (kb + 2 >= kb1) umma_commit_pair(accfull0 + 8 * buf);    // chunk complete
           }
-          umma_commit_pair(empty0 + 8 * s);                             // frees the stage in both CTAs
-          if (kb + 2 >= npad) umma_commit_pair(accfull0 + 8 * buf);     // unit complete
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   }
@@ -1591,6 +1650,13 @@ int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float*
   args.cnt = reinterpret_cast<uint32_t*>(t3 + T3.cnt);
   args.accsave = args.want_x ? accsave : nullptr;
   args.B = B; args.Hq = T3.Hq; args.T = T3.Bp / 256; args.NP = T3.NP; args.kappa = kappa;
+  // 3xTF32: accumulate K in chunks of kTc3ChunkK (B200VAE_KCHUNK overrides: a multiple of 32 dividing Hq; 0 = one chunk)
+  static const int chunk_k = [] { const char* e = getenv("B200VAE_KCHUNK"); return e ? atoi(e) : kTc3ChunkK; }();
+  static const int park_ns = [] { const char* e = getenv("B200VAE_PARK_NS"); return e ? atoi(e) : 2000; }();
+  args.cscr = reinterpret_cast<float4*>(t3 + T3.cscr);
+  args.park_ns = (uint32_t)park_ns;
+  args.NC = 1;
+  if (x3 && chunk_k >= 32 && chunk_k % 32 == 0 && T3.Hq % chunk_k == 0) args.NC = T3.Hq / chunk_k;
   const int units = (args.want_x ? 2 : 1) * args.T * args.NP;
 #define B200VAE_TC3(DD) return x3 ? launch_tc3<DD, true>(args, units, st) : launch_tc3<DD, false>(args, units, st)
   switch (d) {

@@ -1,8 +1,9 @@
 // lipschitz.cu -- pairwise |f(x)-f(y)| / |x-y| estimators.
 //   pairs kernel    : reference semantics, utils.py:544-562 (random index pairs given by the caller,
 //                     rows flattened, p=2 norms, both norms clamped at eps)
-//   all-pairs kernel: north_star kernel 4 -- 64x64 tiles of the upper triangle, warp-shuffle
-//                     max / min / sum reduction, optional log2 histogram (for quantiles).
+//   all-pairs kernels: north_star kernel 4 -- 64x64 tiles of the upper triangle, 4x4 pairs per thread, one MUFU op per
+//                     pair, warp-shuffle max / min / sum, ordered per-CTA partials + last-block reduce (no float atomics),
+//                     optional log2 histogram (shared-memory bins flushed once per CTA).
 #include "common.cuh"
 
 namespace b200vae {
@@ -27,14 +28,17 @@ lipschitz_pairs_kernel(const float* __restrict__ X, const float* __restrict__ Y,
   }
 }
 
-constexpr int kTile = 64;
+constexpr int kTile = 64;                      // pair tile: 64 x 64 points (ABI: b200vae_lipschitz_num_tiles)
+constexpr int kApThreads = 256;                // 16 x 16 threads, 4 x 4 pairs each
+constexpr int kApMaxBlocks = 148 * 8;
+constexpr int kApMaxSmemBins = 2048;
 
+// (ti, tj) of tile t, row-major over the upper triangle (ti <= tj): row r starts at r*T - r*(r-1)/2.  A float estimate of
+// the row, made exact by integer fix-up steps.
 __device__ __forceinline__ void tile_coords(long long t, int T, int& ti, int& tj) {
-  // row-major over the upper triangle (ti <= tj): row ti starts at ti*T - ti*(ti-1)/2
-  double tt = (double)t;
-  int r = (int)floor(((2.0 * T + 1.0) - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * tt)) * 0.5);
-  if (r < 0) r = 0;
-  if (r > T - 1) r = T - 1;
+  const float b = 2.f * (float)T + 1.f;
+  int r = (int)((b - sqrtf(fmaxf(b * b - 8.f * (float)t, 0.f))) * 0.5f);
+  r = r < 0 ? 0 : (r > T - 1 ? T - 1 : r);
   auto start = [T](long long q) { return q * T - q * (q - 1) / 2; };
   while (r > 0 && start(r) > t) --r;
   while (r + 1 < T && start(r + 1) <= t) ++r;
@@ -42,80 +46,249 @@ __device__ __forceinline__ void tile_coords(long long t, int T, int& ti, int& tj
   tj = r + (int)(t - start(r));
 }
 
-// 256 threads: thread (a = tid/16 in 0..15, b = tid%16) handles rows i = a + 16*ii, cols j = b + 16*jj
-__global__ void __launch_bounds__(256)
-lipschitz_allpairs_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, int dx, int dy,
-                          float eps, long long tile_begin, long long tile_end, double* __restrict__ stats,
-                          uint32_t* __restrict__ hist, int nbins, float hist_lo, float hist_hi) {
-  extern __shared__ float sm[];   // Xi[64][dx] Xj[64][dx] Yi[64][dy] Yj[64][dy]
-  float* Xi = sm; float* Xj = Xi + kTile * dx; float* Yi = Xj + kTile * dx; float* Yj = Yi + kTile * dy;
+struct ApAcc {
+  float vmax, vmin, sum;                       // running max / min / sum of the ratios of this thread
+  unsigned cnt;
+};
+
+// ratio = clamp(|dy|, eps) / clamp(|dx|, eps) = sqrt(max(sy, eps^2) / max(sx, eps^2)) with ONE MUFU op per pair:
+// r = a * rsqrt(a * b), a = max(sy, eps^2), b = max(sx, eps^2) (utils.py:560-562 semantics, ~2 ulp).  `ok` is cleared when
+// a*b leaves the range in which that is accurate; the caller then redoes its pairs with ap_ratio_safe.
+__device__ __forceinline__ float ap_ratio(float sx, float sy, float eps2, bool& ok) {
+  const float a = fmaxf(sy, eps2), b = fmaxf(sx, eps2);
+  const float ab = a * b;
+  ok = ok && (ab > 1e-30f) && (ab < 1e38f);
+  return a * rsqrtf(ab);
+}
+__device__ __noinline__ float ap_ratio_safe(float sx, float sy, float eps2) {
+  return sqrtf(fmaxf(sy, eps2)) / sqrtf(fmaxf(sx, eps2));
+}
+__device__ __forceinline__ void ap_take(ApAcc& acc, float r) {
+  acc.vmax = fmaxf(acc.vmax, r);
+  acc.vmin = fminf(acc.vmin, r);
+  acc.sum += r;
+}
+
+// Block-level combine into ordered per-CTA slots + last-block reduce in a FIXED order (no float atomics: results are
+// bit-reproducible).  scratch: [kApMaxBlocks][4] floats, then a self-resetting ticket.
+__device__ __forceinline__ void ap_finish(ApAcc acc, float* __restrict__ scratch, double* __restrict__ stats) {
   __shared__ float red[3][8];
   __shared__ unsigned cnt_red[8];
-  const int T = (N + kTile - 1) / kTile;
-  const int tid = threadIdx.x, ta = tid >> 4, tb = tid & 15;
-  float vmax = 0.f, vmin = 3.4e38f, vsum = 0.f;
-  unsigned cnt = 0;
-  for (long long t = tile_begin + blockIdx.x; t < tile_end; t += gridDim.x) {
-    int ti, tj;
-    tile_coords(t, T, ti, tj);
-    const int i0 = ti * kTile, j0 = tj * kTile;
-    __syncthreads();
-    for (int q = tid; q < kTile * dx; q += 256) {
-      const int r = q / dx;
-      Xi[q] = (i0 + r < N) ? X[(size_t)i0 * dx + q] : 0.f;
-      Xj[q] = (j0 + r < N) ? X[(size_t)j0 * dx + q] : 0.f;
-    }
-    for (int q = tid; q < kTile * dy; q += 256) {
-      const int r = q / dy;
-      Yi[q] = (i0 + r < N) ? Y[(size_t)i0 * dy + q] : 0.f;
-      Yj[q] = (j0 + r < N) ? Y[(size_t)j0 * dy + q] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int ii = 0; ii < 4; ++ii) {
-      const int li = ta + 16 * ii, gi = i0 + li;
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int lj = tb + 16 * jj, gj = j0 + lj;
-        if (gi < N && gj < N && gi < gj) {
-          float sx = 0.f, sy = 0.f;
-          for (int q = 0; q < dx; ++q) { const float d = Xi[li * dx + q] - Xj[lj * dx + q]; sx = fmaf(d, d, sx); }
-          for (int q = 0; q < dy; ++q) { const float d = Yi[li * dy + q] - Yj[lj * dy + q]; sy = fmaf(d, d, sy); }
-          const float r = fmaxf(sqrtf(sy), eps) / fmaxf(sqrtf(sx), eps);
-          vmax = fmaxf(vmax, r); vmin = fminf(vmin, r); vsum += r; ++cnt;
-          if (hist) {
-            const float lg = log2f(r);
-            int bin = (int)floorf((lg - hist_lo) / (hist_hi - hist_lo) * (float)nbins);
-            bin = bin < 0 ? 0 : (bin >= nbins ? nbins - 1 : bin);
-            atomicAdd(hist + bin, 1u);
-          }
-        }
-      }
-    }
-  }
-  vmax = warp_max(vmax); vmin = warp_min(vmin); vsum = warp_sum(vsum);
-  cnt = __reduce_add_sync(0xffffffffu, cnt);
-  const int w = tid >> 5, l = tid & 31;
+  __shared__ int last;
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  const float vmax = warp_max(acc.vmax), vmin = warp_min(acc.vmin), vsum = warp_sum(acc.sum);
+  const unsigned cnt = __reduce_add_sync(0xffffffffu, acc.cnt);
   if (l == 0) { red[0][w] = vmax; red[1][w] = vmin; red[2][w] = vsum; cnt_red[w] = cnt; }
   __syncthreads();
+  unsigned* ticket = reinterpret_cast<unsigned*>(scratch + (size_t)kApMaxBlocks * 4);
   if (tid == 0) {
     float a = red[0][0], b = red[1][0], c = red[2][0];
     unsigned n = cnt_red[0];
     for (int q = 1; q < 8; ++q) { a = fmaxf(a, red[0][q]); b = fminf(b, red[1][q]); c += red[2][q]; n += cnt_red[q]; }
-    if (n > 0) {
-      // ratios are > 0: the IEEE bit pattern is monotone, so integer atomics give exact float max/min
-      atomicMax(reinterpret_cast<unsigned long long*>(stats + 0), (unsigned long long)__double_as_longlong((double)a));
-      atomicMin(reinterpret_cast<unsigned long long*>(stats + 1), (unsigned long long)__double_as_longlong((double)b));
-      atomicAdd(stats + 2, (double)c);
-      atomicAdd(stats + 3, (double)n);
+    float* slot = scratch + (size_t)blockIdx.x * 4;
+    slot[0] = a; slot[1] = b; slot[2] = c; slot[3] = __uint_as_float(n);
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) + 1u == gridDim.x) ? 1 : 0;
+  }
+  __syncthreads();
+  if (last && w == 0) {
+    __threadfence();
+    float a = 0.f, b = 3.4e38f;
+    double c = 0.0, n = 0.0;
+    for (int q = l; q < (int)gridDim.x; q += 32) {            // lane-strided, then a fixed shuffle tree
+      const float* slot = scratch + (size_t)q * 4;
+      a = fmaxf(a, __ldcg(slot)); b = fminf(b, __ldcg(slot + 1)); c += (double)__ldcg(slot + 2);
+      n += (double)__float_as_uint(__ldcg(slot + 3));
+    }
+    a = warp_max(a); b = warp_min(b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); n += __shfl_xor_sync(0xffffffffu, n, o); }
+    if (l == 0) {
+      const bool any = n > 0.0;
+      stats[0] = any ? (double)a : 0.0;
+      stats[1] = any ? (double)b : 1.7976931348623157e308;
+      stats[2] = c;
+      stats[3] = n;
+      *ticket = 0u;                                          // ready for the next launch
     }
   }
 }
 
-__global__ void allpairs_init_kernel(double* stats, uint32_t* hist, int nbins) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { stats[0] = 0.0; stats[1] = 1.7976931348623157e308; stats[2] = 0.0; stats[3] = 0.0; }
-  if (hist && i < nbins) hist[i] = 0u;
+__device__ __forceinline__ void ap_hist_add(uint32_t* hs, float r, int nbins, float hist_lo, float hscale) {
+  int bin = (int)floorf((__log2f(r) - hist_lo) * hscale);
+  bin = bin < 0 ? 0 : (bin >= nbins ? nbins - 1 : bin);
+  atomicAdd(hs + bin, 1u);
+}
+
+// ---- small feature widths (DX, DY <= 4): everything in registers, operands straight from global memory (L1 / L2
+// resident: N*(DX+DY)*4 bytes), thread (ta, tb) owns points i0 + 4 ta + ii and j0 + 4 tb + jj (contiguous -> wide loads).
+template <int DX, int DY, bool HIST>
+__global__ void __launch_bounds__(kApThreads)
+lipschitz_allpairs_small_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, float eps,
+                                long long tile_begin, long long tile_end, float* __restrict__ scratch,
+                                double* __restrict__ stats, uint32_t* __restrict__ hist, int nbins, float hist_lo,
+                                float hist_hi, int vec_ok) {
+  extern __shared__ uint32_t hs[];               // HIST: per-CTA histogram (nbins <= kApMaxSmemBins), flushed once
+  const int T = (N + kTile - 1) / kTile;
+  const int tid = threadIdx.x, ta = tid >> 4, tb = tid & 15;
+  const float eps2 = eps * eps;
+  const float hscale = HIST ? (float)nbins / (hist_hi - hist_lo) : 0.f;
+  uint32_t* hdst = hs;
+  if (HIST) {
+    if (nbins <= kApMaxSmemBins) { for (int q = tid; q < nbins; q += kApThreads) hs[q] = 0u; __syncthreads(); }
+    else hdst = hist;
+  }
+  ApAcc acc = {0.f, 3.4e38f, 0.f, 0u};
+  // 4 consecutive points: vector loads when all four exist (g0 is a multiple of 4, so 4*DX floats are 16-byte aligned if
+  // the base pointer is), else clamped scalar loads (out-of-range points are masked below)
+  auto load4 = [&](const float* __restrict__ F, int g0, auto& f) {
+    constexpr int DIM = sizeof(f[0]) / sizeof(float);
+    if (vec_ok && g0 + 3 < N) {
+      const float4* src = reinterpret_cast<const float4*>(F + (size_t)g0 * DIM);
+      float flat[4 * DIM];
+#pragma unroll
+      for (int q = 0; q < DIM; ++q) {
+        const float4 t = __ldg(src + q);
+        flat[4 * q] = t.x; flat[4 * q + 1] = t.y; flat[4 * q + 2] = t.z; flat[4 * q + 3] = t.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) f[k][q] = flat[k * DIM + q];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int gc = g0 + k < N ? g0 + k : N - 1;
+#pragma unroll
+        for (int q = 0; q < DIM; ++q) f[k][q] = __ldg(F + (size_t)gc * DIM + q);
+      }
+    }
+  };
+  for (long long t = tile_begin + blockIdx.x; t < tile_end; t += gridDim.x) {
+    int ti, tj;
+    tile_coords(t, T, ti, tj);
+    const int i0 = ti * kTile + 4 * ta, j0 = tj * kTile + 4 * tb;
+    float xi[4][DX], yi[4][DY], xj[4][DX], yj[4][DY];
+    load4(X, i0, xi); load4(Y, i0, yi); load4(X, j0, xj); load4(Y, j0, yj);
+    const bool full = (ti != tj) && (tj * kTile + kTile <= N);  // every pair valid (i < j, both in range)
+    float sx[4][4], sy[4][4], r[4][4];
+    bool ok = true;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        float ax = 0.f, ay = 0.f;
+#pragma unroll
+        for (int q = 0; q < DX; ++q) { const float d = xi[ii][q] - xj[jj][q]; ax = fmaf(d, d, ax); }
+#pragma unroll
+        for (int q = 0; q < DY; ++q) { const float d = yi[ii][q] - yj[jj][q]; ay = fmaf(d, d, ay); }
+        sx[ii][jj] = ax; sy[ii][jj] = ay;
+        r[ii][jj] = ap_ratio(ax, ay, eps2, ok);
+      }
+    if (!ok) {                                                  // (rare) a*b outside the fast formula's range
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) r[ii][jj] = ap_ratio_safe(sx[ii][jj], sy[ii][jj], eps2);
+    }
+    if (full) {
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          ap_take(acc, r[ii][jj]);
+          if (HIST) ap_hist_add(hdst, r[ii][jj], nbins, hist_lo, hscale);
+        }
+      acc.cnt += 16u;
+    } else {
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          if (i0 + ii < j0 + jj && j0 + jj < N) {
+            ap_take(acc, r[ii][jj]);
+            ++acc.cnt;
+            if (HIST) ap_hist_add(hdst, r[ii][jj], nbins, hist_lo, hscale);
+          }
+    }
+  }
+  if (HIST && nbins <= kApMaxSmemBins) {
+    __syncthreads();
+    for (int q = tid; q < nbins; q += kApThreads) { const uint32_t c = hs[q]; if (c) atomicAdd(hist + q, c); }
+  }
+  ap_finish(acc, scratch, stats);
+}
+
+// ---- any feature widths: 64 x 64 tile, the feature axis staged through shared memory in chunks of kApChunk, [q][point]
+// layout (conflict-free: a warp reads 2 broadcast i-rows and 16 consecutive j-points), 4 x 4 accumulator pairs per thread.
+constexpr int kApChunk = 32;
+__global__ void __launch_bounds__(kApThreads)
+lipschitz_allpairs_wide_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, int dx, int dy, float eps,
+                               long long tile_begin, long long tile_end, float* __restrict__ scratch,
+                               double* __restrict__ stats, uint32_t* __restrict__ hist, int nbins, float hist_lo,
+                               float hist_hi) {
+  __shared__ float Fi[kApChunk][kTile + 1], Fj[kApChunk][kTile + 1];
+  const int T = (N + kTile - 1) / kTile;
+  const int tid = threadIdx.x, ta = tid >> 4, tb = tid & 15;
+  const float eps2 = eps * eps;
+  const float hscale = hist ? (float)nbins / (hist_hi - hist_lo) : 0.f;
+  ApAcc acc = {0.f, 3.4e38f, 0.f, 0u};
+  for (long long t = tile_begin + blockIdx.x; t < tile_end; t += gridDim.x) {
+    int ti, tj;
+    tile_coords(t, T, ti, tj);
+    const int i0 = ti * kTile, j0 = tj * kTile;
+    float s[2][4][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) s[m][ii][jj] = 0.f;
+#pragma unroll 1
+    for (int m = 0; m < 2; ++m) {                              // m = 0: X (sx), m = 1: Y (sy)
+      const float* F = m ? Y : X;
+      const int dim = m ? dy : dx;
+      for (int c0 = 0; c0 < dim; c0 += kApChunk) {
+        const int cw = min(kApChunk, dim - c0);
+        __syncthreads();
+        for (int id = tid; id < kTile * kApChunk; id += kApThreads) {
+          const int pt = id / kApChunk, q = id - pt * kApChunk;          // consecutive threads: consecutive features
+          const bool inq = q < cw;
+          Fi[q][pt] = (inq && i0 + pt < N) ? __ldg(F + (size_t)(i0 + pt) * dim + c0 + q) : 0.f;
+          Fj[q][pt] = (inq && j0 + pt < N) ? __ldg(F + (size_t)(j0 + pt) * dim + c0 + q) : 0.f;
+        }
+        __syncthreads();
+        for (int q = 0; q < cw; ++q) {
+          float fi[4], fj[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { fi[k] = Fi[q][ta + 16 * k]; fj[k] = Fj[q][tb + 16 * k]; }
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const float d = fi[ii] - fj[jj];
+              if (m == 0) s[0][ii][jj] = fmaf(d, d, s[0][ii][jj]);
+              else s[1][ii][jj] = fmaf(d, d, s[1][ii][jj]);
+            }
+        }
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int gi = i0 + ta + 16 * ii, gj = j0 + tb + 16 * jj;
+        if (gi < gj && gj < N) {
+          bool ok = true;
+          float r = ap_ratio(s[0][ii][jj], s[1][ii][jj], eps2, ok);
+          if (!ok) r = ap_ratio_safe(s[0][ii][jj], s[1][ii][jj], eps2);
+          ap_take(acc, r);
+          ++acc.cnt;
+          if (hist) ap_hist_add(hist, r, nbins, hist_lo, hscale);
+        }
+      }
+  }
+  ap_finish(acc, scratch, stats);
 }
 
 }  // namespace b200vae
@@ -137,26 +310,55 @@ extern "C" long long b200vae_lipschitz_num_tiles(int N) {
   return T * (T + 1) / 2;
 }
 
+extern "C" size_t b200vae_lipschitz_scratch_bytes(void) { return ((size_t)kApMaxBlocks * 4 + 4) * sizeof(float); }
+
+template <int DX, int DY>
+static int launch_ap_small(const float* X, const float* Y, int N, float eps, long long tb, long long te, float* scratch,
+                           double* stats, uint32_t* hist, int nbins, float lo, float hi, int blocks, cudaStream_t st) {
+  const int vec_ok = (aligned16(X) && aligned16(Y)) ? 1 : 0;
+  if (hist) {
+    const size_t smem = nbins <= kApMaxSmemBins ? (size_t)nbins * 4 : 0;
+    lipschitz_allpairs_small_kernel<DX, DY, true><<<blocks, kApThreads, smem, st>>>(X, Y, N, eps, tb, te, scratch, stats, hist,
+                                                                                   nbins, lo, hi, vec_ok);
+  } else {
+    lipschitz_allpairs_small_kernel<DX, DY, false><<<blocks, kApThreads, 0, st>>>(X, Y, N, eps, tb, te, scratch, stats, hist,
+                                                                                  nbins, lo, hi, vec_ok);
+  }
+  return check_launch();
+}
+
 extern "C" int b200vae_lipschitz_allpairs(const float* X, const float* Y, int N, int dx, int dy, float eps,
                                           long long tile_begin, long long tile_end, double* stats, uint32_t* hist,
-                                          int nbins, float hist_lo, float hist_hi, void* stream) {
-  if (!X || !Y || !stats) return B200VAE_EALIGN;
+                                          int nbins, float hist_lo, float hist_hi, void* scratch, void* stream) {
+  if (!X || !Y || !stats || !scratch || !aligned16(scratch)) return B200VAE_EALIGN;
   if (N <= 0 || dx <= 0 || dy <= 0 || tile_begin < 0 || tile_end < tile_begin ||
       tile_end > b200vae_lipschitz_num_tiles(N))
     return B200VAE_ESHAPE;
   if (hist && (nbins <= 0 || !(hist_hi > hist_lo))) return B200VAE_ESHAPE;
-  const size_t smem = sizeof(float) * 2 * kTile * ((size_t)dx + dy);
-  if (smem > 200 * 1024) return B200VAE_EUNSUP;
   cudaStream_t st = (cudaStream_t)stream;
-  allpairs_init_kernel<<<(nbins > 0 && hist ? (nbins + 255) / 256 : 1), 256, 0, st>>>(stats, hist, nbins);
-  int rc = check_launch();
-  if (rc) return rc;
+  if (hist && cudaMemsetAsync(hist, 0, (size_t)nbins * sizeof(uint32_t), st) != cudaSuccess) return B200VAE_ECUDA;
   const long long nt = tile_end - tile_begin;
-  if (nt == 0) return B200VAE_OK;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(lipschitz_allpairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int blocks = (int)(nt < 148 * 4 ? nt : 148 * 4);
-  lipschitz_allpairs_kernel<<<blocks, 256, smem, st>>>(X, Y, N, dx, dy, eps, tile_begin, tile_end, stats, hist, nbins,
-                                                       hist_lo, hist_hi);
+  // one launch, even for an empty tile range (the kernel then only writes the neutral statistics)
+  const int per_sm = 4;
+  long long want = nt < 1 ? 1 : nt;
+  const long long cap = (long long)sm_count() * per_sm;
+  const int blocks = (int)(want < cap ? want : (cap < kApMaxBlocks ? cap : kApMaxBlocks));
+  float* scr = reinterpret_cast<float*>(scratch);
+  if (dx <= 4 && dy <= 4) {
+#define B200VAE_AP(DX_, DY_) \
+    return launch_ap_small<DX_, DY_>(X, Y, N, eps, tile_begin, tile_end, scr, stats, hist, nbins, hist_lo, hist_hi, blocks, st)
+#define B200VAE_APX(DX_) \
+    switch (dy) { case 1: B200VAE_AP(DX_, 1); case 2: B200VAE_AP(DX_, 2); case 3: B200VAE_AP(DX_, 3); default: B200VAE_AP(DX_, 4); }
+    switch (dx) {
+      case 1: B200VAE_APX(1)
+      case 2: B200VAE_APX(2)
+      case 3: B200VAE_APX(3)
+      default: B200VAE_APX(4)
+    }
+#undef B200VAE_APX
+#undef B200VAE_AP
+  }
+  lipschitz_allpairs_wide_kernel<<<blocks, kApThreads, 0, st>>>(X, Y, N, dx, dy, eps, tile_begin, tile_end, scr, stats, hist,
+                                                               nbins, hist_lo, hist_hi);
   return check_launch();
 }

@@ -36,7 +36,9 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
 __global__ void __launch_bounds__(256)
 peer_reduce_adam_kernel(PtrList L, int world, int rank, long long lo4, long long hi4, float4* __restrict__ m,
                         float4* __restrict__ v, float lr, float b1, float b2, float eps, float wd,
-                        const long long* __restrict__ step, float gscale) {
+                        const long long* __restrict__ step, float gscale, const unsigned* __restrict__ dead) {
+  // an exchange on this rank timed out (sticky flag): the gradients may be incomplete -> poison instead of a stale update
+  const float poison = (*reinterpret_cast<const volatile unsigned*>(dead) != 0u) ? __int_as_float(0x7fc00000) : 0.f;
   const double t = (double)*step;
   const float bc1 = (float)(1.0 - pow((double)b1, t));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
@@ -48,6 +50,7 @@ peer_reduce_adam_kernel(PtrList L, int world, int rank, long long lo4, long long
       const float4 g = __ldcv(L.g[q] + i);                  // peer load over NVLink (never from a stale L1 line)
       s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
     }
+    s.x += poison; s.y += poison; s.z += poison; s.w += poison;
     float4 p = L.p[rank][i], mi = m[i], vi = v[i];
     adam_one(p.x, s.x * gscale, mi.x, vi.x, b1, b2, eps, wd, step_size, bc2_sqrt);
     adam_one(p.y, s.y * gscale, mi.y, vi.y, b1, b2, eps, wd, step_size, bc2_sqrt);
@@ -150,7 +153,8 @@ extern "C" int b200vae_peer_allreduce_adam(const b200vae_peer_t* comm, int slot,
     long long blocks = (hi - lo + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
     peer_reduce_adam_kernel<<<(int)blocks, 256, 0, st>>>(L, W, r, lo, hi, (float4*)m, (float4*)v, lr, beta1, beta2, eps,
-                                                        weight_decay, step_dev, grad_scale);
+                                                        weight_decay, step_dev, grad_scale,
+                                                        &((PeerSlot*)comm->buf[r])->timed_out);
     rc = check_launch();
     if (rc) return rc;
   }

@@ -6,13 +6,19 @@
 //      counters agree without communication; they live on the device so that a CUDA-graph replay advances them);
 //   2. store this rank's payload into data[e&1][rank] of EVERY rank's slot (plain stores through the peer mapping),
 //      __threadfence_system, then release-store flag[e&1][rank] = e on every rank;
-//   3. spin (acquire loads, bounded by a 20 s timeout that sets a sticky per-rank flag) until the local
-//      flag[e&1][q] == e for every q, then read the payloads from local memory.  Results are combined in rank order,
-//      so every rank computes bit-identical values.
+//   3. spin (acquire loads, bounded by a timeout -- 20 s, B200VAE_PEER_TIMEOUT_S overrides -- that sets a sticky per-rank
+//      flag) until the local flag[e&1][q] == e for every q, then read the payloads from local memory.  Results are
+//      combined in rank order, so every rank computes bit-identical values.
+// FAILING LOUDLY: once the sticky flag is set every exchange on this rank returns NaN payloads (BatchNorm statistics and
+// hence the loss turn NaN) and the fused all-reduce + Adam kernel writes NaN parameters, so a rank that lagged by more than
+// the timeout can never silently train on stale data; the host reads the flag with b200vae_peer_timed_out
+// (train.DataParallelTrainer polls it every `check_every` steps and raises).
 // The parity double-buffer makes slot reuse safe without a trailing barrier: a rank can only publish epoch e+2 into the
 // buffers of epoch e after it passed exchange e+1, i.e. after every rank published e+1, which each does (stream order)
 // only after it finished reading epoch e.
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200vae {
@@ -20,7 +26,7 @@ namespace b200vae {
 constexpr int kPeerMaxWorld = B200VAE_PEER_MAX_WORLD;   // 16
 constexpr int kPeerPay = 400;                           // floats per rank per exchange (>= 3*128 + 1)
 constexpr int kPeerSlots = 64;
-constexpr unsigned long long kPeerTimeoutNs = 20000000000ull;  // 20 s: a missing peer must not hang the GPU
+constexpr unsigned long long kPeerTimeoutNs = 20000000000ull;  // 20 s default: a missing peer must not hang the GPU
 
 struct PeerSlot {
   float data[2][kPeerMaxWorld][kPeerPay];
@@ -32,12 +38,23 @@ struct PeerSlot {
 
 struct PeerComm {   // kernel-parameter copy of b200vae_peer_t
   int world, rank;
+  unsigned long long timeout_ns;
   PeerSlot* buf[kPeerMaxWorld];
 };
+
+inline unsigned long long peer_timeout_ns() {
+  static const unsigned long long ns = [] {
+    const char* e = getenv("B200VAE_PEER_TIMEOUT_S");
+    const double s = e ? atof(e) : 0.0;
+    return s > 0.0 ? (unsigned long long)(s * 1e9) : kPeerTimeoutNs;
+  }();
+  return ns;
+}
 
 inline PeerComm make_peer(const b200vae_peer_t* c) {
   PeerComm p;
   p.world = c->world; p.rank = c->rank;
+  p.timeout_ns = peer_timeout_ns();
   for (int r = 0; r < kPeerMaxWorld; ++r) p.buf[r] = r < c->world ? (PeerSlot*)c->buf[r] : nullptr;
   return p;
 }
@@ -91,13 +108,14 @@ __device__ __forceinline__ void peer_exchange(const PeerComm& c, int slot, const
     const unsigned long long t0 = global_timer_ns();
     while (ld_acquire_sys(&local->flag[par][threadIdx.x]) != e) {
       if (*reinterpret_cast<volatile unsigned*>(dead) != 0u) break;
-      if (global_timer_ns() - t0 > kPeerTimeoutNs) { *reinterpret_cast<volatile unsigned*>(dead) = 1u; break; }
+      if (global_timer_ns() - t0 > c.timeout_ns) { *reinterpret_cast<volatile unsigned*>(dead) = 1u; break; }
     }
   }
   __syncthreads();
+  const bool failed = *reinterpret_cast<volatile unsigned*>(&c.buf[c.rank]->timed_out) != 0u;
   for (int i = threadIdx.x; i < c.world * n; i += blockDim.x) {
     const int p = i / n, j = i - p * n;
-    all[i] = ld_relaxed_sys_f32(&local->data[par][p][j]);
+    all[i] = failed ? __int_as_float(0x7fc00000) : ld_relaxed_sys_f32(&local->data[par][p][j]);   // NaN: fail loudly
   }
   if (threadIdx.x == 0) local->epoch = e;
   __syncthreads();

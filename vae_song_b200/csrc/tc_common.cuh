@@ -148,10 +148,18 @@ inline float* tc_base(float* ws, int d, int H) {
 //   -- B dependent --
 //   scr1 float4 [Bp][NP][2]  (h2 partial, tpos_0..2) per (row, pass, column half);  scr2 float4 same shape (X_0..2)
 //   imask u32 [Bp][Hq/32]    LeakyReLU bits of h1 when the caller does not ask for mask1
+//   cscr float4 [clusters][2 CTAs][2 halves][32][128 rows]   3xTF32 only: running sums of the K-chunked accumulation.  The
+//                            tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
+//                            MMAs per accumulator; the forward therefore accumulates K in chunks of kTc3ChunkK, each in a
+//                            fresh accumulator, and the epilogue warps add the chunks with round-to-nearest FP32 adds.  A thread
+//                            re-reads only what it wrote itself; 256 KB per cluster, L2 resident.
 constexpr int kTc3MaxTiles = 16384;
+constexpr int kTc3MaxClusters = 80;
+constexpr size_t k3ScrFloatsPerCta = (size_t)128 * 256;
+constexpr int kTc3ChunkK = 256;
 struct Tc3Layout {
   int Hq, K1, NP, Bp;
-  size_t B1ahi, B1alo, B2ghi, B2glo, A0g, E1, sumV, cnt, fixed_end, scr1, scr2, imask, end;
+  size_t B1ahi, B1alo, B2ghi, B2glo, A0g, E1, sumV, cnt, fixed_end, scr1, scr2, imask, cscr, end;
 };
 inline Tc3Layout tc3_layout(int B, int d, int H) {
   (void)d;
@@ -168,6 +176,11 @@ inline Tc3Layout tc3_layout(int B, int d, int H) {
   T.scr1 = o; o += (size_t)T.Bp * T.NP * 2 * 4;
   T.scr2 = o; o += (size_t)T.Bp * T.NP * 2 * 4;
   T.imask = o; o += (size_t)T.Bp * (T.Hq / 32);
+  {
+    const size_t units = (size_t)2 * (T.Bp / 256) * T.NP;
+    const size_t cl = units < (size_t)kTc3MaxClusters ? units : (size_t)kTc3MaxClusters;
+    T.cscr = o; o += cl * 2 * k3ScrFloatsPerCta;
+  }
   T.end = o + 64;
   return T;
 }

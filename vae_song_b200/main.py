@@ -17,6 +17,8 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import random
+from datetime import datetime
 
 import numpy as np
 import torch
@@ -27,6 +29,17 @@ from . import model as Model
 from .utils import apply_grad_clip
 
 ENCODER_LR_WEIGHT = 0.0001     # `lam` of main.py:270
+SEED = 42                      # main.py:31
+
+
+def seed_everything(seed=SEED):
+    """main.py:31-36 seeds random, numpy and torch (CPU + every CUDA device) at import time; the drivers here call this
+    explicitly at the start of a run instead (importing a package should not reseed the caller's generators)."""
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
 
 
 def load_config(config_path):
@@ -111,14 +124,15 @@ def train_step(model, x, optimizer, scheduler=None, num_mc_samples=1, grad_clip=
     return torch.stack([as_t(loss), as_t(loss_recon), as_t(loss_reg), as_t(loss_lr)])
 
 
-def evaluate(model, loader, device, num_mc_samples=1):
-    """main.py:91-172 reduced to its numbers: mean loss parts over the test loader (autograd stays enabled, like the
-    reference, because its LIDVAE.decode needs it; ours does not care)."""
+def evaluate(model, loader, device):
+    """main.py:91-172 reduced to its numbers: mean loss parts over the test loader, `model(x)` with the DEFAULT number of
+    Monte-Carlo samples like main.py:103 (autograd stays enabled, like the reference, because its LIDVAE.decode needs
+    it; ours does not care)."""
     model.eval()
     tot, n = torch.zeros(4, device=device), 0
     for x, _ in loader:
         x = x.to(device)
-        result = model(x, L=num_mc_samples)
+        result = model(x)
         parts = model.loss(x, *result)
         tot += torch.stack([p.detach().float().reshape(()) if torch.is_tensor(p) else torch.tensor(float(p), device=device)
                             for p in parts])
@@ -129,7 +143,7 @@ def evaluate(model, loader, device, num_mc_samples=1):
 def train_and_test(model, epochs=100, batch_size=128, device="cuda", dataset_name="mnist", logfilename="log.csv",
                    resultname="res", pt_param=None, num_mc_samples=1, grad_clip=None, wu_strat="linear",
                    loader_train=None, loader_test=None, result_root="./results", dataset_params=None, num_workers=0,
-                   graph=False):
+                   graph=False, run_tag=None):
     """main.py:174-393.  Returns {'train': [[loss, recon, reg, lr] per epoch], 'test': [...], 'name': run name}.
 
     graph=True: the same step (forward, staged backward, clipping, Adam, cosine schedule) captured ONCE into a CUDA graph
@@ -151,10 +165,12 @@ def train_and_test(model, epochs=100, batch_size=128, device="cuda", dataset_nam
         if not os.path.exists(pt_param):
             raise FileNotFoundError(f"No such file: {pt_param}")                        # the reference calls exit()
         model.load_state_dict(torch.load(pt_param, map_location=device))
-    name = type(model).__name__
-    if not name.startswith("NaiveAE"):
+    # run directory name of main.py:211-218: class name + " %m%d%H%M" timestamp + hyper-parameters.  `run_tag` (the repeat
+    # index when a config asks for niter > 1) keeps repeats that start within the same minute from overwriting each other.
+    name = type(model).__name__ + datetime.now().strftime(" %m%d%H%M") + (f"_r{run_tag}" if run_tag is not None else "")
+    if not type(model).__name__.startswith("NaiveAE"):
         name += "_b=" + str(float(model.beta))
-    if name.startswith("LR") or name.startswith("SetLR"):
+    if type(model).__name__.startswith("LR") or type(model).__name__.startswith("SetLR"):
         name += "_a=" + str(model.alpha)
     if getattr(model, "is_log_mse", False):
         name += "_logmse"
@@ -187,8 +203,12 @@ def train_and_test(model, epochs=100, batch_size=128, device="cuda", dataset_nam
             nb += 1
         history["train"].append((tot / max(nb, 1)).tolist())                             # one sync per epoch
         if loader_test is not None:
-            history["test"].append(evaluate(model, loader_test, device, num_mc_samples))
-    torch.save(model.state_dict(), os.path.join(out_dir, "params", f"{epochs}.pt"))     # main.py:307-310
+            history["test"].append(evaluate(model, loader_test, device))
+    # main.py:307-310: the state_dict of the LAST epoch, named after its 0-based index (utils.py:365 and test.py look
+    # for params/model_<epochs-1>.pt)
+    ckpt = os.path.join(out_dir, "params", f"model_{max(epochs - 1, 0)}.pt")
+    torch.save(model.state_dict(), ckpt)
+    history["checkpoint"], history["out_dir"] = ckpt, out_dir
     with open(os.path.join(out_dir, "history.json"), "w") as f:
         json.dump(history, f)
     return history
@@ -196,7 +216,9 @@ def train_and_test(model, epochs=100, batch_size=128, device="cuda", dataset_nam
 
 # ----------------------------------------------------------------------------------------------------- config -> models
 def iter_models(config):
-    """Yield (tag, model, train kwargs) for every (alpha, beta, IL, repeat) of the config: main.py:423-578."""
+    """Yield (tag, model, train kwargs) for every (alpha, beta, IL, repeat) of the config: main.py:423-578.  With
+    niter > 1 the tag and the kwargs carry the repeat index so that repeats neither share a results key nor a run
+    directory."""
     exp_type, cp, mp = config["experiment_type"], config["common_params"], config["model_params"]
     data = cp.get("exp_data", "shapenet")
     kw = dict(epochs=cp["exp_epochs"], batch_size=cp["batch_size"], dataset_name=data, pt_param=cp.get("pt_param", None),
@@ -210,7 +232,16 @@ def iter_models(config):
                  num_encoder_layers=mp.get("num_encoder_layers", 2), num_decoder_layers=mp.get("num_decoder_layers", 2),
                  ff_dim=mp.get("ff_dim", 512), attn_dropout=mp.get("attn_dropout", 0.0))
     wu = dict(wu_strat=cp.get("wu_strat", "linear"))
-    for _ in range(cp["niter"]):
+    niter = cp["niter"]
+    for rep, item in ((r, it) for r in range(niter) for it in _iter_once(exp_type, cp, mp, data, kw, flex, setkw, wu)):
+        tag, model, k = item
+        if niter > 1:
+            tag, k = f"{tag}_r{rep}", {**k, "run_tag": rep}
+        yield tag, model, k
+
+
+def _iter_once(exp_type, cp, mp, data, kw, flex, setkw, wu):
+    if True:
         if exp_type == "lidvae":
             for beta in mp["beta_list"]:
                 for il in mp["il_list"]:
@@ -241,7 +272,10 @@ def iter_models(config):
             raise ValueError(f"unknown experiment_type {exp_type!r}")
 
 
-def run_experiment(config_path, device="cuda", epochs=None, result_root="./results", dataset_params=None, graph=False):
+def run_experiment(config_path, device="cuda", epochs=None, result_root="./results", dataset_params=None, graph=False,
+                   seed=SEED):
+    if seed is not None:
+        seed_everything(seed)                                                            # main.py:31-36
     config = load_config(config_path) if isinstance(config_path, (str, os.PathLike)) else config_path
     cp, mp = config["common_params"], config["model_params"]
     res_tag = "_res" if mp.get("residual_connection", False) else ""

@@ -101,8 +101,19 @@ class ICNN(nn.Module):
         return fn.apply(input, float(kappa), self._mode(), prec, *self._flat_params())
 
 
-def _bn_act(norm, act=True):
-    return [norm] + ([nn.LeakyReLU()] if act else [])
+class PlainConvolution(nn.Module):
+    """conv3x3-BN-LReLU twice, no skip connection (module.py:4-26; stock cuDNN layers, outside the hot path)."""
+
+    def __init__(self, in_channel, out_channel, stride=1):
+        super().__init__()
+        self.activation = nn.LeakyReLU()
+        self.conv1 = nn.Sequential(nn.Conv2d(in_channel, out_channel, 3, stride, 1), nn.BatchNorm2d(out_channel),
+                                   self.activation)
+        self.conv2 = nn.Sequential(nn.Conv2d(out_channel, out_channel, 3, 1, 1), nn.BatchNorm2d(out_channel),
+                                   self.activation)
+
+    def forward(self, input):
+        return self.conv2(self.conv1(input))
 
 
 class ResidualConvBlock(nn.Module):
@@ -138,3 +149,27 @@ class ResidualMLPBlock(nn.Module):
 
     def forward(self, input):
         return self.activation(self.mlp2(self.mlp1(input)) + self.identity(input))
+
+
+class LinearModule_EP(nn.Module):
+    """The reference's unconstrained ICNN-shaped MLP (module.py:151-187: plain Linear W layers, last W maps to in_channel;
+    not used by any model of the reference).  Kept for API parity: same attribute names, init order and forward."""
+
+    def __init__(self, in_channel, hidden_channel=128, num_layers=2):
+        super().__init__()
+        self.activation = nn.LeakyReLU(0.2)
+        W, A = [], []
+        for _ in range(num_layers - 1):
+            W.append(nn.Linear(hidden_channel, hidden_channel))
+            A.append(nn.Linear(in_channel, hidden_channel))
+        W.append(nn.Linear(hidden_channel, in_channel))
+        A.append(nn.Linear(in_channel, 1))
+        self.W = nn.Sequential(*W)
+        self.A = nn.Sequential(*A)
+        self.A0 = nn.Linear(in_channel, hidden_channel)
+
+    def forward(self, input):
+        x = self.activation(self.A0(input)).pow(2)
+        for w, a in zip(self.W, self.A):
+            x = self.activation(w(x) + a(input))
+        return x

@@ -680,6 +680,19 @@ def lipschitz_pair_ratios(X, Y, i1, i2, eps=1e-3):
     return ratio
 
 
+_ap_scratch = {}
+
+
+def _allpairs_scratch(device):
+    """Zero-initialised partials + ticket per (device, stream); the kernel leaves it ready for the next call."""
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    buf = _ap_scratch.get(key)
+    if buf is None:
+        buf = torch.zeros(_C.load().b200vae_lipschitz_scratch_bytes(), dtype=torch.uint8, device=device)
+        _ap_scratch[key] = buf
+    return buf
+
+
 def lipschitz_allpairs(X, Y, eps=1e-3, tile_begin=0, tile_end=None, nbins=0, hist_lo=-20.0, hist_hi=20.0):
     """All unordered pairs i<j in tiles [tile_begin, tile_end): returns (stats fp64 [max,min,sum,count], hist)."""
     lib = _C.load()
@@ -693,7 +706,8 @@ def lipschitz_allpairs(X, Y, eps=1e-3, tile_begin=0, tile_end=None, nbins=0, his
     hist = torch.empty(nbins, dtype=torch.int32, device=X.device) if nbins > 0 else None
     _C.check(lib.b200vae_lipschitz_allpairs(_ptr(X), _ptr(Y), N, X.shape[1], Y.shape[1], float(eps), int(tile_begin),
                                             int(tile_end), _ptr(stats), _ptr(hist), nbins, float(hist_lo),
-                                            float(hist_hi), _stream()), "lipschitz_allpairs")
+                                            float(hist_hi), _ptr(_allpairs_scratch(X.device)), _stream()),
+             "lipschitz_allpairs")
     return stats, hist
 
 

@@ -104,14 +104,20 @@ class SyncBatchNorm1d(nn.BatchNorm1d):
 
 
 def convert_sync_batchnorm(model, group=None):
-    """BatchNorm1d -> SyncBatchNorm1d (lean, works on CPU/gloo too); other BatchNorms -> nn.SyncBatchNorm."""
+    """BatchNorm1d -> SyncBatchNorm1d (lean, works on CPU/gloo too, carries the peer-exchange slots); BatchNorm2d / 3d ->
+    nn.SyncBatchNorm, converted child by child so that the SyncBatchNorm1d instances (which ARE _BatchNorm subclasses and
+    would be converted back by a whole-model nn.SyncBatchNorm.convert_sync_batchnorm) are left alone."""
+    if isinstance(model, (nn.BatchNorm2d, nn.BatchNorm3d)):
+        return nn.SyncBatchNorm.convert_sync_batchnorm(model, group)
     for name, child in list(model.named_children()):
+        if isinstance(child, SyncBatchNorm1d):
+            continue
         if type(child) is nn.BatchNorm1d:
             setattr(model, name, SyncBatchNorm1d(child, group))
+        elif isinstance(child, (nn.BatchNorm2d, nn.BatchNorm3d)):
+            setattr(model, name, nn.SyncBatchNorm.convert_sync_batchnorm(child, group))
         else:
             convert_sync_batchnorm(child, group)
-    if any(isinstance(mod, (nn.BatchNorm2d, nn.BatchNorm3d)) for mod in model.modules()):
-        model = nn.SyncBatchNorm.convert_sync_batchnorm(model, group)
     return model
 
 
@@ -192,10 +198,14 @@ class DataParallelTrainer:
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None,
                  grad_clip=None, sync_bn=True, optimizer_step=None, comm="auto", staged_backward=False,
-                 forward_kwargs=None, lr_schedule=None):
+                 forward_kwargs=None, lr_schedule=None, check_every=256):
         """comm: "peer" = exchanges as kernels over NVLink peer memory (csrc/peer.cuh): BatchNorm statistics inside
         the fused encoder's finalize kernels, gradient all-reduce fused with Adam; "nccl" = torch.distributed
         collectives; "auto" = peer when CUDA IPC mapping works between all ranks, else nccl."""
+        # check_every: with the peer-memory exchange, poll the sticky time-out flag every so many steps (one tiny D2H copy
+        # + sync) and raise -- a rank that lagged the others by more than the exchange timeout (20 s; eval or checkpointing
+        # on one rank only, a stalled data loader) also turns losses / parameters into NaN on the device (csrc/peer.cuh)
+        self.check_every = int(check_every) if check_every else 0
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
         self.pg = process_group
@@ -295,7 +305,12 @@ class DataParallelTrainer:
             self._se.copy_(eps_local, non_blocking=True)
         self._graph.replay()
         self.t += 1
+        self._poll()
         return self._sout
+
+    def _poll(self):
+        if self.peer is not None and self.check_every and self.t % self.check_every == 0:
+            self.peer.check()
 
     def step(self, x_local, eps_local=None):
         model, W = self.model, self.world
@@ -326,6 +341,8 @@ class DataParallelTrainer:
             ops.peer_allreduce_adam_(self.peer, self._adam_slot, self._peer_bufs[1], self._peer_bufs[0], self.m, self.v,
                                      self.fp.flat.numel(), self.t_dev, self.hp["lr"], self.hp["betas"], self.hp["eps"],
                                      self.hp["weight_decay"], 1.0 / W)
+            if not torch.cuda.is_current_stream_capturing():
+                self._poll()
             return total.detach(), (rec.detach() if torch.is_tensor(rec) else rec), (reg.detach() if torch.is_tensor(reg) else reg)
         if W > 1:
             dist.all_reduce(self.fp.grad, op=dist.ReduceOp.SUM, group=self.pg)

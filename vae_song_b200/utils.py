@@ -199,21 +199,39 @@ def estimate_local_lipschitz_batched(func, X_list, num_pairs=2000, quantile=0.05
     return out
 
 
-def estimate_lipschitz_allpairs(func, X, eps=1e-3, process_group=None, nbins=0, hist_range=(-20.0, 20.0)):
+def estimate_lipschitz_allpairs(func, X, eps=1e-3, process_group=None, nbins=0, hist_range=(-20.0, 20.0), peer=None,
+                                shard_decode=True):
     """All-pairs max / min / mean of |f(x)-f(y)|/|x-y| over every unordered pair (north_star kernel 4).
-    With a process group the 64x64 pair tiles are sharded round-robin-by-range across ranks and combined
-    with MAX / MIN / SUM all-reduces.  Returns dict(max, min, mean, count[, hist])."""
-    with torch.no_grad():
-        Y = func(X)
-    nt = ops.lipschitz_num_tiles(X.shape[0])
+    With a process group (X replicated on every rank) BOTH stages shard: rank r decodes rows [r*per, (r+1)*per) and the
+    outputs are all-gathered; the 64x64 pair tiles are split by range (`tile_range`) and the per-rank statistics combined
+    with ONE exchange -- `peer` (a peer.PeerComm: an own all-gather kernel over NVLink peer memory, ~13 us) or one
+    torch.distributed all_gather.  Returns dict(max, min, mean, count[, hist])."""
+    import torch.distributed as dist
     rank, world = 0, 1
-    if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-        rank = torch.distributed.get_rank(process_group)
-        world = torch.distributed.get_world_size(process_group)
+    if process_group is not None or (dist.is_available() and dist.is_initialized()):
+        rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+    N = X.shape[0]
+    with torch.no_grad():
+        if world > 1 and shard_decode and N >= world:
+            per = (N + world - 1) // world
+            lo_r, hi_r = min(rank * per, N), min((rank + 1) * per, N)
+            Yl = func(X[lo_r:hi_r]) if hi_r > lo_r else None
+            tail = tuple(Yl.shape[1:]) if Yl is not None else None
+            if tail is None:          # a rank without rows still needs the output shape: decode one row
+                tail = tuple(func(X[:1]).shape[1:])
+            pad = torch.zeros(per, *tail, dtype=torch.float32, device=X.device)
+            if Yl is not None:
+                pad[:hi_r - lo_r] = Yl
+            gathered = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(gathered, pad, group=process_group)
+            Y = torch.cat(gathered, 0)[:N]
+        else:
+            Y = func(X)
+    nt = ops.lipschitz_num_tiles(N)
     lo, hi = tile_range(nt, rank, world)
     stats, hist = ops.lipschitz_allpairs(X, Y, eps, lo, hi, nbins, *hist_range)
     if world > 1:
-        stats, hist = combine_allpairs(stats, hist, process_group)
+        stats, hist = combine_allpairs(stats, hist, process_group, peer)
     mx, mn, sm, cnt = stats.tolist()
     out = dict(max=mx, min=mn, mean=sm / max(cnt, 1.0), count=int(cnt))
     if hist is not None:
@@ -228,14 +246,19 @@ def tile_range(num_tiles, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def combine_allpairs(stats, hist, process_group=None):
-    """MAX / MIN / SUM all-reduce of per-rank [max, min, sum, count] (+ histogram)."""
+def combine_allpairs(stats, hist, process_group=None, peer=None):
+    """Combine per-rank [max, min, sum, count] fp64 statistics (+ histogram) with ONE exchange: every rank gathers all
+    ranks' statistics (peer-memory all-gather kernel when `peer` is given, else torch.distributed.all_gather) and reduces
+    them locally in rank order -- identical results on every rank."""
     import torch.distributed as dist
-    mx, mn, sc = stats[0:1].clone(), stats[1:2].clone(), stats[2:4].clone()
-    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=process_group)
-    dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=process_group)
-    dist.all_reduce(sc, op=dist.ReduceOp.SUM, group=process_group)
+    if peer is not None:
+        allst = peer.allgather(stats.view(torch.float32)).contiguous().view(torch.float64)       # [world, 4] bit-exact
+    else:
+        outs = [torch.empty_like(stats) for _ in range(dist.get_world_size(process_group))]
+        dist.all_gather(outs, stats, group=process_group)
+        allst = torch.stack(outs)
+    comb = torch.stack([allst[:, 0].max(), allst[:, 1].min(), allst[:, 2].sum(), allst[:, 3].sum()])
     if hist is not None:
         hist = hist.clone()
         dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=process_group)
-    return torch.cat([mx, mn, sc]), hist
+    return comb, hist
