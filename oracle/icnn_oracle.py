@@ -87,11 +87,16 @@ def cast_params(p, dtype):
     return {k: np.ascontiguousarray(v, dtype=dtype) for k, v in p.items()}
 
 
-def icnn_brenier(z, p, mode=MODE_EXP, kappa=0.0, keep=False):
+def icnn_brenier(z, p, mode=MODE_EXP, kappa=0.0, keep=False, masks=None):
     """psi(z) [B] and xhat = grad_z(psi(z) + kappa*|z|^2) [B,d]   (SURVEY.md Appendix A).
 
     Forward  module.py:142-148; reverse = what autograd.grad(psi, z, ones) evaluates (model.py:822).
-    Returns (psi, xhat, aux) where aux holds the masks (and, if keep, every intermediate)."""
+    Returns (psi, xhat, aux) where aux holds the masks (and, if keep, every intermediate).
+
+    masks=(mask1 [B,H] bool, mask2 [B] bool): evaluate the REVERSE sweep with these LeakyReLU branch choices for h1 / h2
+    instead of the signs of this evaluation's own pre-activations (the forward value psi is continuous across a kink and
+    keeps its own).  Given the masks xhat is linear in everything else, so a kernel whose pre-activation landed on the
+    other side of a kink within its rounding error can be checked exactly against "the oracle with the kernel's masks"."""
     dt = z.dtype.type
     P0, P1 = positive(p["W0"], mode), positive(p["W1"], mode)[0]
     h0 = z @ p["A0w"].T + p["A0b"]
@@ -104,6 +109,9 @@ def icnn_brenier(z, p, mode=MODE_EXP, kappa=0.0, keep=False):
     h2 = x2 @ P1 + z @ p["A2w"][0] + p["A2b"][0]
     s2 = _slope(h2)
     psi = h2 * s2
+    if masks is not None:
+        s1 = np.where(np.asarray(masks[0], dtype=bool), dt(1.0), dt(SLOPE))
+        s2 = np.where(np.asarray(masks[1], dtype=bool), dt(1.0), dt(SLOPE))
     g1 = (s2[:, None] * P1[None, :]) * s1
     gx1 = g1 @ P0
     g0 = gx1 * (dt(2.0) * a0 * s0)
@@ -114,14 +122,15 @@ def icnn_brenier(z, p, mode=MODE_EXP, kappa=0.0, keep=False):
     return psi, xhat, aux
 
 
-def icnn_brenier_backward(z, v, p, mode=MODE_EXP, kappa=0.0, gpsi=None):
+def icnn_brenier_backward(z, v, p, mode=MODE_EXP, kappa=0.0, gpsi=None, masks=None):
     """Gradients of  L = <v, xhat(z)> (+ <gpsi, psi(z)>)  w.r.t. z and every parameter.
 
     This is what PyTorch's double-backward through autograd.grad(create_graph=True) produces
     (model.py:822/828 then lipschitz.py:41).  Masks are constants a.e.; A1b/A2b get exact zeros
-    on the <v,xhat> path.  Returns (dz [B,d], grads dict keyed like the params)."""
+    on the <v,xhat> path.  Returns (dz [B,d], grads dict keyed like the params).
+    masks: see icnn_brenier (the LeakyReLU branch choices of h1 / h2 are then given, not derived)."""
     dt = z.dtype.type
-    psi, xhat, a = icnn_brenier(z, p, mode, kappa, keep=True)
+    psi, xhat, a = icnn_brenier(z, p, mode, kappa, keep=True, masks=masks)
     P0, P1, s0, a0, s1, s2, g1, gx1, g0 = (a[k] for k in ("P0", "P1", "s0", "a0", "s1", "s2", "g1", "gx1", "g0"))
     u0 = v @ p["A0w"].T
     u1 = v @ p["A1w"].T

@@ -414,14 +414,68 @@ def gen_host_logic(ref_model, ref_utils):
     print("host_cases.npz:", len(out), "arrays")
 
 
+BASELINE_ICNN_KW = dict(dataset="pinwheel", inverse_lipschitz=0.2, beta=1.0)      # icnn_channels = the reference default [512, 1024]
+
+
+def baseline_icnn_weights(model_obj, seed=17):
+    """The big H x H matrices (and the rows that make the LeakyReLU masks mixed) are drawn with numpy so that the test can
+    rebuild them from the seed; works on the reference's LIDVAE and on vae_song_b200's (same attribute names)."""
+    rng = np.random.default_rng(seed)
+    with torch.no_grad():
+        for ic in (model_obj.decoder[0], model_obj.decoder[1]):
+            H = ic.A0.weight.shape[0]
+            ic.W[0].param.copy_(torch.tensor(rng.normal(np.log(1.0 / H), 1.0, (H, H))).to(ic.W[0].param.dtype))
+            ic.W[1].param.copy_(torch.tensor(rng.normal(np.log(2.0 / H), 1.0, (1, H))).to(ic.W[1].param.dtype))
+            ic.A[0].bias.copy_(torch.tensor(rng.normal(-0.3, 1.0, (H,))).to(ic.A[0].bias.dtype))
+
+
+def gen_lidvae_baseline(ref_model):
+    """Model-level golden at the BASELINE widths: LIDVAE(pinwheel) with the reference's DEFAULT icnn_channels=[512,1024]
+    (model.py:644) and default encoder, fp64, batch 96: forward tuple, loss parts, dz-side tensors, every small gradient in
+    full and the two H x H gradients as strided samples + sums (the fixture stays ~100 KB).  The H x H weights are not
+    stored: the test redraws them from the numpy seed."""
+    out = {}
+    torch.manual_seed(13)
+    m = ref_model.LIDVAE(**BASELINE_ICNN_KW).double()
+    baseline_icnn_weights(m)
+    for k, a in sd_to_np(m.state_dict()).items():
+        if not k.endswith("W.0.param"):
+            out["sd/" + k] = a
+    rng = np.random.default_rng(19)
+    x = rng.normal(0, 1.5, (96, 2)).astype(np.float32)
+    eps = rng.normal(0, 1.0, (96, 2)).astype(np.float32)
+    out["x"], out["eps"] = x, eps
+    m.train()
+    xt = torch.tensor(x, dtype=torch.float64)
+    mu, lv = m.encode(xt)
+    z = mu + torch.tensor(eps, dtype=torch.float64) * torch.exp(lv * 0.5)
+    recon = m.decode(z)
+    total, lrec, lreg, _ = m.loss(xt, recon, mu, lv, z, None)
+    total.backward()
+    out["mu"], out["lv"], out["z"], out["recon"] = (t.detach().numpy() for t in (mu, lv, z, recon))
+    out["loss"] = np.array([float(total), float(lrec), float(lreg)])
+    for k, q in m.named_parameters():
+        g = q.grad.numpy()
+        if k.endswith("W.0.param"):
+            out["grad_sample/" + k] = g.reshape(-1)[::97].copy()
+            out["grad_sum/" + k] = np.array([g.sum(dtype=np.float64), np.abs(g).sum(dtype=np.float64), np.abs(g).max()])
+        else:
+            out["grad/" + k] = g.copy()
+    np.savez_compressed(os.path.join(OUT, "lidvae_baseline_icnn.npz"), **out)
+    print("lidvae_baseline_icnn.npz:", len(out), "arrays")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref_module, ref_model, ref_utils = import_reference()
     torch.set_num_threads(8)
     if len(sys.argv) > 1 and sys.argv[1] == "host":        # only the (cheap) host-logic fixtures
         return gen_host_logic(ref_model, ref_utils)
+    if len(sys.argv) > 1 and sys.argv[1] == "baseline":    # only the BASELINE-width model golden
+        return gen_lidvae_baseline(ref_model)
     gen_icnn(ref_module)
     gen_lidvae(ref_model)
+    gen_lidvae_baseline(ref_model)
     gen_mnist_shaped(ref_model)
     gen_losses(ref_model, ref_utils)
     gen_lipschitz(ref_model, ref_utils)

@@ -1,6 +1,8 @@
 """Parity of the fused ICNN kernels (through ops -> ctypes -> C ABI) against the oracle and the
 reference-generated goldens.  Tolerances: the north_star's rtol 1e-5 for psi / xhat and 1e-4 for
-parameter gradients, applied as |a-b| <= rtol*|b| + rtol*max|b| (see helpers.close_report)."""
+parameter gradients, applied as |a-b| <= rtol*|b| + rtol*max|b| (see helpers.close_report) with NO fraction of
+elements waved through: rows in which the oracle itself finds a LeakyReLU pre-activation within the kernels' rounding
+error of its kink (helpers.kink_rows, |h| < 4e-6 max|h|) are the only ones held to the loose bound instead."""
 import os
 
 import numpy as np
@@ -11,7 +13,7 @@ from oracle import icnn_oracle as io
 from oracle.make_golden import ICNN_CASES, case_inputs
 
 from conftest import GOLDEN
-from helpers import KEYS, close_report, f32_as_f64, params_f32_as_f64, params_to_torch
+from helpers import H_RTOL, KEYS, close_report, close_rows, f32_as_f64, kink_rows, params_f32_as_f64, params_to_torch
 
 pytestmark = pytest.mark.gpu
 SMALL_D = [c for c in ICNN_CASES if c[1] <= 4]
@@ -39,11 +41,11 @@ def test_fwd_bwd_vs_oracle(case):
     psi, xhat, dz, g = run_ours(p, z, v, gp, mode, kappa)
     p64, z64, v64 = params_f32_as_f64(p), f32_as_f64(z), f32_as_f64(v)
     gp64 = f32_as_f64(gpsi) if with_gpsi else None
-    rpsi, rxhat, _ = io.icnn_brenier(z64, p64, mode, kappa)
+    rpsi, rxhat, aux = io.icnn_brenier(z64, p64, mode, kappa, keep=True)
     rdz, rg = io.icnn_brenier_backward(z64, v64, p64, mode, kappa, gp64)
     close_report(psi, rpsi, 1e-5, "psi")
-    close_report(xhat, rxhat, 1e-5, "xhat", bad_frac=0.01)
-    close_report(dz, rdz, 1e-4, "dz", bad_frac=0.01)
+    close_rows(xhat, rxhat, 1e-5, "xhat", kink_rows(aux, H_RTOL[0]))
+    close_rows(dz, rdz, 1e-4, "dz", kink_rows(aux, H_RTOL[0], with_h0=True))
     for k in KEYS:
         if np.abs(rg[k]).max() == 0:
             assert np.abs(g[k]).max() == 0, k          # A1b / A2b exact zeros (not None)
@@ -59,8 +61,9 @@ def test_vs_reference_fp32_golden(case):
     p, z, v, gpsi = case_inputs(d, H, B, regime, seed)
     psi, xhat, dz, g = run_ours(p, z, v, gpsi if with_gpsi else None, mode, kappa)
     pre = f"{name}/f32/"
+    _, _, aux = io.icnn_brenier(f32_as_f64(z), params_f32_as_f64(p), mode, kappa)
     close_report(psi, G[pre + "psi"], 2e-5, "psi")
-    close_report(xhat, G[pre + "xhat"], 2e-5, "xhat", bad_frac=0.02)
+    close_rows(xhat, G[pre + "xhat"], 2e-5, "xhat", kink_rows(aux, 2 * H_RTOL[0]))      # both sides carry fp32 noise
     close_report(g["A0w"], G[pre + "g_A0w"], 2e-4, "grad A0w")
     close_report(g["W1"], G[pre + "g_W1"], 2e-4, "grad W1")
     if pre + "g_W0" in G.files:
@@ -77,11 +80,11 @@ def test_ragged_batches(B):
     z, v = rng.normal(0, 1, (B, 2)), rng.normal(0, 1, (B, 2))
     psi, xhat, dz, g = run_ours(p, z, v, None, 0, 0.2)
     p64 = params_f32_as_f64(p)
-    rpsi, rxhat, _ = io.icnn_brenier(f32_as_f64(z), p64, 0, 0.2)
+    rpsi, rxhat, aux = io.icnn_brenier(f32_as_f64(z), p64, 0, 0.2, keep=True)
     rdz, rg = io.icnn_brenier_backward(f32_as_f64(z), f32_as_f64(v), p64, 0, 0.2)
     close_report(psi, rpsi, 1e-5, "psi")
-    close_report(xhat, rxhat, 1e-5, "xhat", bad_frac=0.01)
-    close_report(dz, rdz, 1e-4, "dz", bad_frac=0.01)
+    close_rows(xhat, rxhat, 1e-5, "xhat", kink_rows(aux, H_RTOL[0]))
+    close_rows(dz, rdz, 1e-4, "dz", kink_rows(aux, H_RTOL[0], with_h0=True))
     for k in ("A0w", "A0b", "A1w", "A2w", "W0", "W1"):
         close_report(g[k], rg[k], 1e-4, "grad " + k)
 
@@ -102,9 +105,9 @@ def test_full_size_properties():
         sel = torch.arange(0, B, 257, device="cuda")
         psi_s, xhat_s = ops.IcnnBrenierFn.apply(z[sel].contiguous(), 0.1, 0, 0, *params)
         assert torch.equal(psi[sel], psi_s) and torch.equal(xhat[sel], xhat_s)
-        rpsi, rxhat, _ = io.icnn_brenier(z[sel].double().cpu().numpy(), params_f32_as_f64(p), 0, 0.1)
+        rpsi, rxhat, aux = io.icnn_brenier(z[sel].double().cpu().numpy(), params_f32_as_f64(p), 0, 0.1)
         close_report(psi_s.cpu().numpy(), rpsi, 1e-5, "psi")
-        close_report(xhat_s.cpu().numpy(), rxhat, 1e-5, "xhat", bad_frac=0.01)
+        close_rows(xhat_s.cpu().numpy(), rxhat, 1e-5, "xhat", kink_rows(aux, H_RTOL[0]))
         perm = torch.randperm(B, device="cuda")
         mono = ((xhat - xhat[perm]) * (z - z[perm])).sum(1)
         assert (mono >= -1e-3 * mono.abs().max()).all()
@@ -148,8 +151,9 @@ def test_reference_idiom_double_backward():
     xhat = torch.autograd.grad(psi, [zt], torch.ones_like(psi), create_graph=True)[0]
     (xhat * torch.tensor(v, dtype=torch.float32, device="cuda")).sum().backward()
     pre = f"{name}/f64/"
-    close_report(xhat.detach().cpu().numpy(), G[pre + "xhat"], 1e-5, "xhat", bad_frac=0.01)
-    close_report(zt.grad.cpu().numpy(), G[pre + "dz"], 1e-4, "dz", bad_frac=0.01)
+    _, _, aux = io.icnn_brenier(f32_as_f64(z), params_f32_as_f64(p), mode, kappa, keep=True)
+    close_rows(xhat.detach().cpu().numpy(), G[pre + "xhat"], 1e-5, "xhat", kink_rows(aux, H_RTOL[0]))
+    close_rows(zt.grad.cpu().numpy(), G[pre + "dz"], 1e-4, "dz", kink_rows(aux, H_RTOL[0], with_h0=True))
     close_report(icnn.W[0].param.grad.cpu().numpy(), G[pre + "g_W0"], 1e-4, "grad W0")
     close_report(icnn.A0.weight.grad.cpu().numpy(), G[pre + "g_A0w"], 1e-4, "grad A0w")
 

@@ -1,39 +1,52 @@
-"""tcgen05 (TF32 / 3xTF32) variants of the fused ICNN forward: stated, looser bounds than the FP32 path.
+"""tcgen05 (TF32 / 3xTF32) variants of the fused ICNN forward and backward.
 
-Bounds (vs the fp64 oracle on fp32-rounded inputs, |a-b| <= rtol*|b| + rtol*max|b|):
-    tf32x3 : psi 3e-5, xhat 1e-4 (kink flips excepted)   -- fp32-grade split; residual error is the tensor
-             core's truncating fp32 accumulation over K (grows ~linearly with H)
-    tf32   : psi 2e-4, xhat 5e-3 (kink flips excepted)
-The backward of these modes reuses the saved masks and runs the FP32 kernels, so parameter gradients keep
-the FP32 bound (1e-4) whenever no mask flipped."""
+Bounds (vs the fp64 oracle on fp32-rounded inputs, |a-b| <= rtol*|b| + rtol*max|b|, NO fraction of elements exempted):
+    tf32x3 : psi 1e-5, xhat 1e-5, parameter gradients / dz 1e-4  -- north_star's FP32 bounds.  fp32-grade operand split
+             (3 MMAs per product) + K accumulated in chunks of 512 with round-to-nearest adds between chunks
+             (icnn_tc3.cu; the tensor core's own accumulation truncates).
+    tf32   : psi 2e-4, xhat 5e-3, gradients 5e-3 (one MMA, operands rounded to 11 bits): the stated looser bound.
+Kink handling (helpers.py): where the kernels return their LeakyReLU masks, every mask bit that differs from the oracle's
+must belong to a unit whose pre-activation is inside the mode's rounding window (|h| < H_RTOL * max|h|) and xhat is then
+compared STRICTLY with the oracle evaluated with the kernel's masks; where only (psi, xhat) are visible, the rows the
+oracle flags as kink-adjacent are held to the loose bound and every other row to the strict one."""
 import numpy as np
 import pytest
 import torch
 
 from oracle import icnn_oracle as io
 
-from helpers import KEYS, close_report, f32_as_f64, params_f32_as_f64, params_to_torch
+from helpers import (H_RTOL, KEYS, check_decode_with_masks, close_report, close_rows, f32_as_f64, kink_rows, params_f32_as_f64,
+                     params_to_torch)
 
 pytestmark = pytest.mark.gpu
-BOUNDS = {3: (3e-5, 1e-4), 1: (2e-4, 5e-3)}
-CASES = [(2, 256, 256, "mixed"), (2, 96, 77, "mixed"), (1, 64, 300, "mixed"), (3, 512, 1000, "mixed"),
-         (2, 1024, 2048, "mixed"), (2, 512, 513, "default")]
+BOUNDS = {3: (1e-5, 1e-5), 1: (2e-4, 5e-3)}          # precision -> (psi, xhat)
+GRAD_BOUND = {3: 1e-4, 1: 5e-3}
+# (d, H, B, regime, weight mode): ragged sizes, both weight reparameterisations (exp / clamp), and the two ICNN shapes of
+# BASELINE configs[1] (ICNN(2,512), ICNN(2,1024)) in the trained-like AND the default-init regime
+CASES = [(2, 256, 256, "mixed", 0), (2, 96, 77, "mixed", 0), (1, 64, 300, "mixed", 0), (3, 512, 1000, "mixed", 0),
+         (2, 1024, 2048, "mixed", 0), (2, 512, 513, "default", 0), (2, 1024, 512, "default", 0),
+         (2, 256, 300, "clampy", 1), (3, 512, 200, "clampy", 1), (2, 1024, 256, "default", 1)]
 
 
 @pytest.mark.parametrize("prec", [3, 1], ids=["tf32x3", "tf32"])
-@pytest.mark.parametrize("case", CASES, ids=[f"d{c[0]}_h{c[1]}_b{c[2]}_{c[3]}" for c in CASES])
+@pytest.mark.parametrize("case", CASES, ids=[f"d{c[0]}_h{c[1]}_b{c[2]}_{c[3]}_mode{c[4]}" for c in CASES])
 def test_tc_forward_vs_oracle(case, prec):
     from vae_song_b200 import ops
-    d, H, B, regime = case
+    d, H, B, regime, mode = case
     rng = np.random.default_rng(H + B)
     p = io.random_params(rng, d, H, np.float64, regime)
     z = rng.normal(0, 1, (B, d))
     zt = torch.tensor(z, dtype=torch.float32, device="cuda")
-    psi, xhat = ops.IcnnBrenierFn.apply(zt, 0.15, 0, prec, *params_to_torch(p))
-    rpsi, rxhat, _ = io.icnn_brenier(f32_as_f64(z), params_f32_as_f64(p), 0, 0.15)
+    P = params_to_torch(p)
+    ws = ops.icnn_prepare(P, d, H, mode, prec, B, False)
+    psi, xhat, m1, m2 = ops.icnn_decode_fwd(zt, ws, d, H, mode, 0.15, prec, True, True, True)
     rp, rx = BOUNDS[prec]
-    close_report(psi.cpu().numpy(), rpsi, rp, "psi")
-    close_report(xhat.cpu().numpy(), rxhat, rx, "xhat", bad_frac=0.02)
+    e_psi, e_x, flips = check_decode_with_masks(psi, xhat, m1, m2, f32_as_f64(z), params_f32_as_f64(p), mode, 0.15, rp, rx,
+                                                H_RTOL[prec], f"{case}")
+    print(f"prec {prec} {case}: psi {e_psi:.2e} xhat {e_x:.2e} mask flips {flips}/{B * H}")
+    # the autograd.Function (what the modules call) returns the same rows
+    psi2, xhat2 = ops.IcnnBrenierFn.apply(zt, 0.15, mode, prec, *P)
+    assert torch.equal(psi2, psi) and torch.equal(xhat2, xhat)
 
 
 @pytest.mark.parametrize("prec", [3, 1], ids=["tf32x3", "tf32"])
@@ -55,27 +68,36 @@ def test_tc_matches_fp32_path_and_backward_runs(prec):
         outs[pr] = (psi.detach().cpu().numpy(), xhat.detach().cpu().numpy(), zt.grad.cpu().numpy(),
                     {k: t.grad.cpu().numpy() for k, t in zip(KEYS, ps)})
     rp, rx = BOUNDS[prec]
+    _, _, aux = io.icnn_brenier(f32_as_f64(z), params_f32_as_f64(p), 0, 0.1, keep=True)
     close_report(outs[prec][0], outs[0][0], rp, "psi vs fp32 path")
-    close_report(outs[prec][1], outs[0][1], rx, "xhat vs fp32 path", bad_frac=0.02)
-    gtol = 3e-4 if prec == 3 else 5e-3     # tensor-core backward (rows kernel) in the same precision
-    close_report(outs[prec][2], outs[0][2], gtol, "dz vs fp32 path", bad_frac=0.02)
+    close_rows(outs[prec][1], outs[0][1], rx, "xhat vs fp32 path", kink_rows(aux, H_RTOL[prec]))
+    gtol = GRAD_BOUND[prec]                # tensor-core backward (rows + dP0 kernels) in the same precision
+    close_rows(outs[prec][2], outs[0][2], gtol, "dz vs fp32 path", kink_rows(aux, H_RTOL[prec], with_h0=True), loose=5e-2)
     for k in ("A0w", "A0b", "A1w", "A2w", "W0", "W1"):
         close_report(outs[prec][3][k], outs[0][3][k], gtol, "grad " + k)
     assert float(np.abs(outs[prec][3]["A1b"]).max()) == 0.0 and float(np.abs(outs[prec][3]["A2b"]).max()) == 0.0
 
 
-def test_tc_full_size_tiling_invariance():
+def test_tc_full_size_tiling_invariance_and_sampled_rows_vs_oracle():
+    """BASELINE decode size B = 65536, both ICNN widths: (a) a row decoded alone equals the row decoded inside the big
+    batch, bit for bit (persistent scheduling, chunked accumulation and the ordered partial sums are tile independent);
+    (b) every 256th row (256 rows) against the fp64 oracle at the mode's bound."""
     from vae_song_b200 import ops
     rng = np.random.default_rng(3)
-    p = io.random_params(rng, 2, 1024, np.float64, "mixed")
-    params = params_to_torch(p)
-    z = torch.tensor(rng.normal(0, 1, (65536, 2)), dtype=torch.float32, device="cuda")
-    for prec in (1, 3):
-        psi, xhat = ops.IcnnBrenierFn.apply(z, 0.1, 0, prec, *params)
-        sel = torch.arange(0, 65536, 509, device="cuda")
-        psi_s, xhat_s = ops.IcnnBrenierFn.apply(z[sel].contiguous(), 0.1, 0, prec, *params)
-        assert torch.equal(psi[sel], psi_s) and torch.equal(xhat[sel], xhat_s)     # row results are tile independent
-        assert torch.isfinite(xhat).all()
+    for H in (512, 1024):
+        p = io.random_params(rng, 2, H, np.float64, "mixed")
+        params = params_to_torch(p)
+        z = torch.tensor(rng.normal(0, 1, (65536, 2)), dtype=torch.float32, device="cuda")
+        for prec in (1, 3):
+            psi, xhat = ops.IcnnBrenierFn.apply(z, 0.1, 0, prec, *params)
+            sel = torch.arange(0, 65536, 256, device="cuda")
+            psi_s, xhat_s = ops.IcnnBrenierFn.apply(z[sel].contiguous(), 0.1, 0, prec, *params)
+            assert torch.equal(psi[sel], psi_s) and torch.equal(xhat[sel], xhat_s)     # row results are tile independent
+            assert torch.isfinite(xhat).all()
+            rpsi, rx, aux = io.icnn_brenier(z[sel].double().cpu().numpy(), params_f32_as_f64(p), 0, 0.1)
+            rp, rxb = BOUNDS[prec]
+            close_report(psi_s.cpu().numpy(), rpsi, rp, f"psi H={H} prec={prec}")
+            close_rows(xhat_s.cpu().numpy(), rx, rxb, f"xhat H={H} prec={prec}", kink_rows(aux, H_RTOL[prec]))
 
 
 def test_tc_unsupported_is_loud():
@@ -121,13 +143,21 @@ np.savez(sys.argv[1], **out)
             env = dict(os.environ, B200VAE_FWD=flag, B200VAE_BWD=flag, B200VAE_DP0=flag)
             subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
             res[flag] = dict(np.load(f.name))
+    rng = np.random.default_rng(4)                      # the same draws as in the subprocesses
+    p = io.random_params(rng, 2, 512, np.float64, "mixed")
+    z = rng.normal(0, 1, (777, 2))
+    _, _, aux = io.icnn_brenier(f32_as_f64(z), params_f32_as_f64(p), 0, 0.1, keep=True)
     for k in res["1"]:
         prec = int(k[-1])
-        tol = {3: 1e-4, 1: 5e-3}[prec] if not k.startswith("psi") else BOUNDS[prec][0]
+        tol = {3: 1e-4, 1: 5e-3}[prec] if not k.startswith("psi") else 2 * BOUNDS[prec][0]
         if k.startswith("gA1b") or k.startswith("gA2b"):
             assert float(np.abs(res["3"][k]).max()) == 0.0
             continue
-        close_report(res["3"][k], res["1"][k], tol, "pair vs single " + k, bad_frac=0.02)
+        if k.startswith("xhat") or k.startswith("dz"):  # per-row outputs: each kernel may flip a kink-adjacent unit
+            close_rows(res["3"][k], res["1"][k], tol, "pair vs single " + k, kink_rows(aux, 2 * H_RTOL[prec], with_h0=True),
+                       loose=5e-2)
+        else:
+            close_report(res["3"][k], res["1"][k], tol, "pair vs single " + k)
 
 
 BWD_CASES = [(1, 64, 300, 0), (2, 96, 77, 1), (3, 512, 1000, 0), (2, 1024, 600, 0), (2, 256, 256, 1)]
@@ -135,9 +165,10 @@ BWD_CASES = [(1, 64, 300, 0), (2, 96, 77, 1), (3, 512, 1000, 0), (2, 1024, 600, 
 
 @pytest.mark.parametrize("prec", [3, 1], ids=["tf32x3", "tf32"])
 @pytest.mark.parametrize("case", BWD_CASES, ids=[f"d{c[0]}_h{c[1]}_b{c[2]}_mode{c[3]}" for c in BWD_CASES])
-def test_tc_backward_vs_fp32_kernels_same_masks(case, prec):
+def test_tc_backward_vs_fp32_kernels_same_masks_and_vs_oracle(case, prec):
     """Tensor-core double-backward (persistent pair rows kernel + dP0 kernel) against the FP32 SIMT kernels fed the SAME
-    saved masks: ragged batch, H not a multiple of 256 (padded units), d = 1..3, exp and clamp weights."""
+    saved masks, and against the fp64 oracle: ragged batch, H not a multiple of 256 (padded units), d = 1..3, exp and
+    clamp weights, tf32x3 at north_star's FP32 gradient bound (1e-4), tf32 at its stated 5e-3."""
     from vae_song_b200 import ops
     d, H, B, mode = case
     rng = np.random.default_rng(11 * H + B)
@@ -150,13 +181,25 @@ def test_tc_backward_vs_fp32_kernels_same_masks(case, prec):
     dz, g = ops.icnn_decode_bwd(z, v, None, m1, m2, P, ws, d, H, mode, 0.1, prec)
     ws0 = ops.icnn_prepare(P, d, H, mode, 0, B, True)
     dz0, g0 = ops.icnn_decode_bwd(z, v, None, m1, m2, P, ws0, d, H, mode, 0.1, 0)
-    gtol = 3e-4 if prec == 3 else 5e-3
+    gtol = GRAD_BOUND[prec]
     close_report(dz.cpu().numpy(), dz0.cpu().numpy(), gtol, "dz")
     for k, a, b in zip(KEYS, g, g0):
         if float(b.abs().max()) == 0.0:
             assert float(a.abs().max()) == 0.0, k
         else:
             close_report(a.cpu().numpy(), b.cpu().numpy(), gtol, "grad " + k)
+    # ... and against the fp64 oracle evaluated with the masks this forward saved (given the masks the backward is linear
+    # in everything else, so NO element is exempted); the masks themselves are checked by test_tc_forward_vs_oracle
+    from helpers import unpack_mask1
+    p64, z64, v64 = params_f32_as_f64(p), z.double().cpu().numpy(), v.double().cpu().numpy()
+    km = (unpack_mask1(m1, H), m2.cpu().numpy().astype(bool))
+    _, _, aux = io.icnn_brenier(z64, p64, mode, 0.1, keep=True)
+    rdz, rg = io.icnn_brenier_backward(z64, v64, p64, mode, 0.1, None, masks=km)
+    h0_kink = (np.abs(aux["h0"]) < H_RTOL[0] * np.abs(aux["h0"]).max()).any(1)      # first-layer kinks (h0 is FP32 FMA work)
+    close_rows(dz.cpu().numpy(), rdz, gtol, "dz vs oracle", h0_kink, loose=5e-2)
+    for k, a in zip(KEYS, g):
+        if np.abs(rg[k]).max() > 0:
+            close_report(a.cpu().numpy(), rg[k], gtol, "grad vs oracle " + k)
 
 
 def test_tc_forward_workspace_reuse_and_mask_paths():
@@ -217,8 +260,10 @@ def test_saved_accumulator_backward_equals_recompute(shape):
     if B > 2000:        # BASELINE batch: the agreement above is the size-independent check
         return
     # and against the fp64 oracle (3xTF32 bounds)
-    rdz, rg = io.icnn_brenier_backward(f32_as_f64(z.cpu().numpy()), f32_as_f64(v.cpu().numpy()), params_f32_as_f64(p), 0, 0.1, None)
-    close_report(res[0][1].cpu().numpy(), rdz, 3e-4, "dz", bad_frac=0.02)
+    z64, p64 = f32_as_f64(z.cpu().numpy()), params_f32_as_f64(p)
+    _, _, aux = io.icnn_brenier(z64, p64, 0, 0.1, keep=True)
+    rdz, rg = io.icnn_brenier_backward(z64, f32_as_f64(v.cpu().numpy()), p64, 0, 0.1, None)
+    close_rows(res[0][1].cpu().numpy(), rdz, 1e-4, "dz", kink_rows(aux, H_RTOL[3], with_h0=True), loose=5e-2)
     for k, g in zip(KEYS, res[0][2]):
         if np.abs(rg[k]).max() > 0:
-            close_report(g.cpu().numpy(), rg[k], 3e-4, "grad " + k, bad_frac=0.01)
+            close_report(g.cpu().numpy(), rg[k], 1e-4, "grad " + k)

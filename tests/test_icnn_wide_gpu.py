@@ -1,6 +1,7 @@
 """Parity of the fused wide-input ICNN kernels (csrc/icnn_wide.cu, d > 4: the MNIST-shaped decoder of BASELINE
 configs[3]) against the fp64 oracle and the reference-generated goldens.  FP32 bounds of the north_star: rtol 1e-5 for
-psi / xhat, 1e-4 for gradients (|a-b| <= rtol*|b| + rtol*max|b|, helpers.close_report)."""
+psi / xhat, 1e-4 for gradients (|a-b| <= rtol*|b| + rtol*max|b|, helpers.close_report); no fraction of elements is
+exempted -- only the rows the oracle flags as kink-adjacent (helpers.kink_rows) are held to the loose bound."""
 import os
 
 import numpy as np
@@ -11,7 +12,7 @@ from oracle import icnn_oracle as io
 from oracle.make_golden import ICNN_CASES, case_inputs
 
 from conftest import GOLDEN
-from helpers import KEYS, close_report, f32_as_f64, params_f32_as_f64, params_to_torch
+from helpers import H_RTOL, KEYS, close_report, close_rows, f32_as_f64, kink_rows, params_f32_as_f64, params_to_torch
 
 pytestmark = pytest.mark.gpu
 WIDE_GOLDEN = [c for c in ICNN_CASES if c[1] > 4]
@@ -40,11 +41,11 @@ def run_wide(p, z, v, mode, kappa):
 def check_against_oracle(p, z, v, mode, kappa, out):
     psi, xhat, dz, g = out
     p64, z64, v64 = params_f32_as_f64(p), f32_as_f64(z), f32_as_f64(v)
-    rpsi, rxhat, _ = io.icnn_brenier(z64, p64, mode, kappa)
+    rpsi, rxhat, aux = io.icnn_brenier(z64, p64, mode, kappa, keep=True)
     rdz, rg = io.icnn_brenier_backward(z64, v64, p64, mode, kappa, None)
     close_report(psi, rpsi, 1e-5, "psi")
-    close_report(xhat, rxhat, 1e-5, "xhat", bad_frac=0.01)
-    close_report(dz, rdz, 1e-4, "dz", bad_frac=0.01)
+    close_rows(xhat, rxhat, 1e-5, "xhat", kink_rows(aux, H_RTOL[0]))
+    close_rows(dz, rdz, 1e-4, "dz", kink_rows(aux, H_RTOL[0], with_h0=True), loose=5e-2)
     for k in KEYS:
         if np.abs(rg[k]).max() == 0:
             assert np.abs(g[k]).max() == 0, k          # A1b / A2b exact zeros (not None)
@@ -68,9 +69,10 @@ def test_wide_vs_reference_golden(case):
     p, z, v, _ = case_inputs(d, H, B, regime, seed)
     psi, xhat, dz, g = run_wide(p, z, v, mode, kappa)
     pre = f"{name}/f64/"
+    _, _, aux = io.icnn_brenier(f32_as_f64(z), params_f32_as_f64(p), mode, kappa, keep=True)
     close_report(psi, G[pre + "psi"], 2e-5, "psi")
-    close_report(xhat, G[pre + "xhat"], 2e-5, "xhat", bad_frac=0.01)
-    close_report(dz, G[pre + "dz"], 1e-4, "dz", bad_frac=0.01)
+    close_rows(xhat, G[pre + "xhat"], 2e-5, "xhat", kink_rows(aux, H_RTOL[0]))
+    close_rows(dz, G[pre + "dz"], 1e-4, "dz", kink_rows(aux, H_RTOL[0], with_h0=True), loose=5e-2)
     for k in KEYS:
         key = pre + "g_" + k
         if key in G.files and np.abs(G[key]).max() > 0:
@@ -98,7 +100,8 @@ def test_wide_is_deterministic_and_psi_only_inference():
     zt2 = torch.tensor(z, dtype=torch.float32, device="cuda", requires_grad=True)
     psi_ad = ic(zt2)                                     # autograd idiom of the reference stays available
     xh = torch.autograd.grad(psi_ad, [zt2], torch.ones_like(psi_ad), create_graph=True)[0] + 2 * 0.1 * zt2
-    close_report(xh.detach().cpu().numpy(), a[1], 1e-5, "autograd Brenier == fused", bad_frac=0.01)
+    _, _, aux = io.icnn_brenier(f32_as_f64(z), params_f32_as_f64(p), 0, 0.1)
+    close_rows(xh.detach().cpu().numpy(), a[1], 1e-5, "autograd Brenier == fused", kink_rows(aux, H_RTOL[0]))
 
 
 def test_wide_rejects_cpu_and_psi_gradient():
@@ -138,15 +141,20 @@ def test_wide_implicit_zero_pad_equals_explicit_pad():
     check_against_oracle(p, z, v, 0, 0.1, full)
 
 
-# ---- tcgen05 forward (csrc/icnn_wide_tc.cu): stated looser bounds, like the d <= 3 tensor-core kernels ----------------------
-TC_BOUNDS = {3: (3e-5, 1e-4, 3e-4), 1: (2e-4, 5e-3, 5e-3)}      # precision -> (psi, xhat, gradients)
+# ---- tcgen05 forward + backward (csrc/icnn_wide_tc.cu) ------------------------------------------------------------------------
+# precision -> (psi, xhat, gradients).  tf32x3: north_star's FP32 bounds (four TMEM accumulators per tile: K in thirds +
+# the lo-order products, icnn_wide_tc.cu); tf32: the stated looser bound (operands rounded to 11 bits; the batch-summed
+# gradients of the 784-wide layer accumulate that over K = H = 1024 and B = 256: 2e-2 of the largest entry).
+TC_BOUNDS = {3: (1e-5, 1e-5, 1e-4), 1: (2e-4, 5e-3, 2e-2)}
+# ragged shapes, both weight modes, and the two EXACT shapes of the MNIST-shaped decoder at its config batch:
+# ICNN(32,512) and ICNN(784,1024) at B = 256 (BASELINE configs[3])
 TC_SHAPES = [(32, 512, 129, "mixed", 0, 0.1, 203), (784, 256, 40, "mixed", 0, 0.05, 204), (36, 96, 1000, "clampy", 1, 0.2, 205),
-             (8, 1024, 300, "mixed", 0, 0.0, 206)]
+             (8, 1024, 300, "mixed", 0, 0.0, 206), (32, 512, 256, "mixed", 0, 0.1, 207), (784, 1024, 256, "mixed", 0, 0.1, 208)]
 
 
 @pytest.mark.parametrize("prec", [3, 1], ids=["tf32x3", "tf32"])
 @pytest.mark.parametrize("shape", TC_SHAPES, ids=[f"d{s[0]}_h{s[1]}_b{s[2]}" for s in TC_SHAPES])
-def test_wide_tc_forward_and_fp32_backward_vs_oracle(shape, prec):
+def test_wide_tc_forward_and_backward_vs_oracle(shape, prec):
     from vae_song_b200 import ops
     d, H, B, regime, mode, kappa, seed = shape
     p, z, v, _ = case_inputs(d, H, B, regime, seed)
@@ -155,30 +163,35 @@ def test_wide_tc_forward_and_fp32_backward_vs_oracle(shape, prec):
     psi, xhat = ops.IcnnBrenierWideFn.apply(zt, kappa, mode, prec, *params)
     (xhat * torch.tensor(v, dtype=torch.float32, device="cuda")).sum().backward()
     p64, z64, v64 = params_f32_as_f64(p), f32_as_f64(z), f32_as_f64(v)
-    rpsi, rxhat, _ = io.icnn_brenier(z64, p64, mode, kappa)
+    rpsi, rxhat, aux = io.icnn_brenier(z64, p64, mode, kappa, keep=True)
     rdz, rg = io.icnn_brenier_backward(z64, v64, p64, mode, kappa, None)
     bp, bx, bg = TC_BOUNDS[prec]
     close_report(psi.detach().cpu().numpy(), rpsi, bp, "psi")
-    close_report(xhat.detach().cpu().numpy(), rxhat, bx, "xhat", bad_frac=0.02)
-    close_report(zt.grad.cpu().numpy(), rdz, bg, "dz", bad_frac=0.02)
+    kr = kink_rows(aux, H_RTOL[prec])
+    print(f"prec {prec} {shape[:3]}: {int(kr.sum())}/{B} kink-adjacent rows")
+    close_rows(xhat.detach().cpu().numpy(), rxhat, bx, "xhat", kr, loose=2e-2)
+    close_rows(zt.grad.cpu().numpy(), rdz, bg, "dz", kink_rows(aux, H_RTOL[prec], with_h0=True), loose=0.2)
     for k, t in zip(KEYS, params):
         if np.abs(rg[k]).max() == 0:
             assert float(t.grad.abs().max()) == 0.0, k
         else:
-            # 1xTF32 flips more LeakyReLU masks near 0 (the FP32 backward then follows the flipped masks)
-            close_report(t.grad.cpu().numpy(), rg[k], bg, "grad " + k, bad_frac=0.01 if prec == 3 else 0.05)
+            # batch-summed: a kink-adjacent unit that lands on the other side moves one sample's share of a row, i.e.
+            # O(1 / B) of it -- the only elements allowed outside the bound, and only in proportion to the kink rows
+            close_report(t.grad.cpu().numpy(), rg[k], bg, "grad " + k, bad_frac=min(0.05, 2.0 * kr.mean() + 1e-9))
 
 
 def test_wide_tc_matches_fp32_kernels_with_implicit_pad():
     from vae_song_b200 import ops
     d, nz, H, B = 784, 32, 512, 200
     p, z, v, _ = case_inputs(d, H, B, "mixed", 41)
+    z[:, nz:] = 0.0
     params = params_to_torch(p, "cuda")
     zt = torch.tensor(z[:, :nz].copy(), dtype=torch.float32, device="cuda")
     ref = ops.IcnnBrenierWideFn.apply(zt, 0.1, 0, 0, *params)
+    _, _, aux = io.icnn_brenier(f32_as_f64(z), params_f32_as_f64(p), 0, 0.1)
     for prec in (3, 1):
         bp, bx, _ = TC_BOUNDS[prec]
         got = ops.IcnnBrenierWideFn.apply(zt, 0.1, 0, prec, *params)
         assert got[1].shape == (B, d)
-        close_report(got[0].cpu().numpy(), ref[0].cpu().numpy(), bp, "psi vs fp32 kernels")
-        close_report(got[1].cpu().numpy(), ref[1].cpu().numpy(), bx, "xhat vs fp32 kernels", bad_frac=0.02)
+        close_report(got[0].cpu().numpy(), ref[0].cpu().numpy(), 2 * bp, "psi vs fp32 kernels")
+        close_rows(got[1].cpu().numpy(), ref[1].cpu().numpy(), 2 * bx, "xhat vs fp32 kernels", kink_rows(aux, H_RTOL[prec]), loose=2e-2)

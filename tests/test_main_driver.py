@@ -115,7 +115,9 @@ def test_run_experiment_trains(cfg, tmp_path):
     assert len(h["train"]) == 3 and len(h["test"]) == 3
     if "lidvae" not in cfg:     # the ICNN's default exp(W) ~ 1 init gives ~1e20 losses: finiteness is not promised
         assert np.isfinite(h["train"]).all() and np.isfinite(h["test"]).all()
-        assert h["train"][-1][0] < h["train"][0][0]
+        # the TOTAL carries the latent-recon term whose weight is warmed up from epoch to epoch (model.warmup), so it may
+        # rise; what must fall within three epochs is the reconstruction part
+        assert h["train"][-1][1] < h["train"][0][1], h["train"]
     run_dir = os.path.join(str(tmp_path), os.listdir(str(tmp_path))[0])
     sub = os.path.join(run_dir, os.listdir(run_dir)[0])
     # main.py:307-310: the last epoch's state_dict under its 0-based index (utils.py:365 / test.py look for model_<E-1>.pt)

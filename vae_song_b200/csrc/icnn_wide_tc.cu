@@ -24,7 +24,15 @@ namespace b200vae {
 
 constexpr int kWtThreads = 10 * 32;
 constexpr int kWtStages = 4;
-constexpr int kWtATile = 128 * 64, kWtBTile = 256 * 64;
+constexpr int kWtATile = 128 * 64;
+// Accumulation accuracy at 3xTF32.  tcgen05 adds into its fp32 accumulator with truncation: a downward bias that grows with
+// the number of MMAs per accumulator times the accumulator's magnitude (measured on psi of ICNN(784,1024): 3.0e-5 with the
+// 3 MMAs of every K step in ONE accumulator).  The 3xTF32 kernel therefore uses 128-column tiles and all four 128-column
+// accumulators that fit in TMEM: the hi*hi products of the first / second / last third of K go to accumulators 0 / 1 / 2
+// and ALL lo-order products (2^-11 smaller, so their truncation is negligible) to accumulator 3; the epilogue adds the four
+// with round-to-nearest FP32 adds.  A third of the truncating adds per accumulator, each on a third of the magnitude: 1/9 of
+// the bias.  The 1xTF32 kernel keeps one 256-column accumulator (its error is the operand rounding).
+constexpr int kWtMainChunks = 3;
 
 enum { WT_XF_ID = 0, WT_XF_X1 = 1 };
 enum { WT_EPI_LIN = 0, WT_EPI_HID = 1, WT_EPI_GX1 = 2, WT_EPI_OUT = 3, WT_EPI_U = 4, WT_EPI_W1 = 5, WT_EPI_GXB = 6, WT_EPI_DZ = 7, WT_EPI_SLAB = 8 };
@@ -54,9 +62,13 @@ struct alignas(64) WtArgs {
 
 template <bool X3>
 struct WtCfg {
-  static constexpr int kStage = kWtATile * (X3 ? 2 : 1) + kWtBTile * (X3 ? 2 : 1);
-  static constexpr int kOffAlo = kWtATile, kOffB = kWtATile * (X3 ? 2 : 1), kOffBlo = kOffB + kWtBTile;
+  static constexpr int NT = X3 ? 128 : 256;                      // tile / accumulator width (columns)
+  static constexpr int kBTile = NT * 64;
+  static constexpr int kStage = kWtATile * (X3 ? 2 : 1) + kBTile * (X3 ? 2 : 1);
+  static constexpr int kOffAlo = kWtATile, kOffB = kWtATile * (X3 ? 2 : 1), kOffBlo = kOffB + kBTile;
+  static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
+inline int wt_tile_n(bool x3) { return x3 ? 128 : 256; }
 template <bool X3>
 static size_t wt_smem_bytes() { return (size_t)kWtStages * WtCfg<X3>::kStage + (3 * kWtStages + 1) * 8 + 16 + 1024; }
 
@@ -74,7 +86,8 @@ wide_tc_gemm_kernel(const __grid_constant__ WtArgs a) {
                  accfull = smem_u32(bars + 3 * S);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 256;
+  constexpr int NT = C::NT;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * NT;
   const int nkb = a.nkb1 + a.nkb2;
   const int kb_off = a.kb_per_split > 0 ? (int)blockIdx.z * a.kb_per_split : 0;   // split-K: first K-block of this CTA
 
@@ -84,7 +97,7 @@ wide_tc_gemm_kernel(const __grid_constant__ WtArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(X3 ? 512 : 256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -123,21 +136,32 @@ wide_tc_gemm_kernel(const __grid_constant__ WtArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(ready0 + 8 * s);
     }
-    // ---- epilogue: my row, 128 of the tile's 256 columns ----
+    // ---- epilogue: my row, one half of the tile's columns ----
     const int q4 = warp & 3, chalf = warp >> 2;
     const int row = m0 + q4 * 32 + lane;
     const bool rin = row < a.M;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(chalf * 128);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(chalf * (NT / 2));
     mbar_wait_parked(accfull, 0, 1000);
     tc_fence_after();
     float rowsum = 0.f;
     const float s2r = ((a.epi == WT_EPI_OUT || a.epi == WT_EPI_W1 || a.epi == WT_EPI_GXB) && rin) ? a.s2[row] : 0.f;
 #pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
+    for (int cc = 0; cc < NT / 64; ++cc) {
       uint32_t r[32];
       tmem_ld32(taddr + cc * 32, r);
       tmem_ld_wait();
-      const int c0 = n0 + chalf * 128 + cc * 32;
+      if (X3) {                                              // + the other K-chunk accumulators in use, then the lo-order one
+        const int nchunks = min(kWtMainChunks, nkb);
+#pragma unroll 1
+        for (int k = 1; k <= nchunks; ++k) {
+          uint32_t r2[32];
+          tmem_ld32(taddr + (k < nchunks ? k : kWtMainChunks) * NT + cc * 32, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
+      }
+      const int c0 = n0 + chalf * (NT / 2) + cc * 32;
       if (!rin || c0 >= a.N) continue;
       const int nv = min(32, a.N - c0);                    // N % 4 == 0: whole float4 groups
       float* orow = a.out0 + (size_t)row * a.N + c0;
@@ -257,7 +281,7 @@ wide_tc_gemm_kernel(const __grid_constant__ WtArgs a) {
         const int k0 = (kb_off + (p2 ? kb - a.nkb1 : kb)) * kKB;
         const uint32_t bar = full0 + 8 * s;
         const uint32_t dst = smem_u32(stages + s * C::kStage);
-        mbar_arrive_expect_tx(bar, kWtATile + kWtBTile * (X3 ? 2 : 1));
+        mbar_arrive_expect_tx(bar, kWtATile + C::kBTile * (X3 ? 2 : 1));
         tma_load_2d(dst, p2 ? &a.a2 : &a.a1, bar, k0, m0);
         tma_load_2d(dst + C::kOffB, p2 ? &a.b2hi : &a.b1hi, bar, k0, n0);
         if (X3) tma_load_2d(dst + C::kOffBlo, p2 ? &a.b2lo : &a.b1lo, bar, k0, n0);
@@ -267,23 +291,27 @@ wide_tc_gemm_kernel(const __grid_constant__ WtArgs a) {
   } else {
     // =========================== MMA issuer ===========================
     const uint64_t desc0 = make_desc_sw64(smem_u32(stages));
+    const int nchunks = X3 ? min(kWtMainChunks, nkb) : 1;    // K-chunks in use (every one gets at least one K-block)
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % S;
       mbar_wait(ready0 + 8 * s, (kb / S) & 1);
       tc_fence_after();
+      const int chunk = (kb * nchunks) / nkb;
+      const bool chunk_first = kb == 0 || ((kb - 1) * nchunks) / nkb != chunk;
       if (elect_one()) {
         const uint64_t a0 = desc0 + (uint64_t)(s * (C::kStage >> 4));
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
           const uint64_t a_hi = a0 + (uint64_t)(ks * 2);
           const uint64_t b_hi = a_hi + (uint64_t)(C::kOffB >> 4);
-          const uint32_t acc = (kb | ks) ? 1u : 0u;
           if (X3) {
-            umma_tf32(tmem_base, a_hi + (uint64_t)(C::kOffAlo >> 4), b_hi, kIdescTf32, acc);
-            umma_tf32(tmem_base, a_hi, a_hi + (uint64_t)(C::kOffBlo >> 4), kIdescTf32, 1u);
-            umma_tf32(tmem_base, a_hi, b_hi, kIdescTf32, 1u);
+            const uint32_t d_main = tmem_base + (uint32_t)(chunk * NT), d_lo = tmem_base + (uint32_t)(kWtMainChunks * NT);
+            const uint64_t a_lo = a_hi + (uint64_t)(C::kOffAlo >> 4), b_lo = a_hi + (uint64_t)(C::kOffBlo >> 4);
+            umma_tf32(d_lo, a_lo, b_hi, C::kIdesc, (kb | ks) ? 1u : 0u);
+            umma_tf32(d_lo, a_hi, b_lo, C::kIdesc, 1u);
+            umma_tf32(d_main, a_hi, b_hi, C::kIdesc, (chunk_first && ks == 0) ? 0u : 1u);
           } else {
-            umma_tf32(tmem_base, a_hi, b_hi, kIdescTf32, acc);
+            umma_tf32(tmem_base, a_hi, b_hi, C::kIdesc, (kb | ks) ? 1u : 0u);
           }
         }
         umma_commit(empty0 + 8 * s);
@@ -296,7 +324,7 @@ wide_tc_gemm_kernel(const __grid_constant__ WtArgs a) {
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(X3 ? 512 : 256));
   }
 }
 
@@ -310,7 +338,7 @@ static WtLayout wt_layout(int B, int d, int H) {
   WtLayout L;
   size_t o = 0;
   const size_t HH = wt_up((size_t)H * H), dH = wt_up((size_t)d * H);
-  L.mt = (B + 127) / 128; L.nt = (H + 255) / 256;
+  L.mt = (B + 127) / 128; L.nt = (H + 127) / 128;        // row partials: two per 128-column (3xTF32) / 256-column tile
   L.P0hi = o; o += HH; L.P0lo = o; o += HH; L.P0Thi = o; o += HH; L.P0Tlo = o; o += HH;
   L.A0hi = o; o += dH; L.A0lo = o; o += dH; L.A1hi = o; o += dH; L.A1lo = o; o += dH;
   L.A0Thi = o; o += dH; L.A0Tlo = o; o += dH; L.A1Thi = o; o += dH; L.A1Tlo = o; o += dH;
@@ -466,7 +494,8 @@ static int wt_launch(const WtArgs& args, int splits, cudaStream_t st) {
     cudaFuncSetAttribute(wide_tc_gemm_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_done = true;
   }
-  dim3 grid((args.M + 127) / 128, (args.N + 255) / 256, splits);
+  constexpr int NT = WtCfg<X3>::NT;
+  dim3 grid((args.M + 127) / 128, (args.N + NT - 1) / NT, splits);
   wide_tc_gemm_kernel<X3><<<grid, kWtThreads, wt_smem_bytes<X3>(), st>>>(args);
   return check_launch();
 }
@@ -484,6 +513,7 @@ int wide_tc_fwd(const float* z, int B, int d, int nz, int H, const b200vae_icnn_
                 float* xhat, float* h0, uint8_t* mask1, float* s2, float* g0, float* ws, int precision, cudaStream_t st) {
   if (!wide_tc_supported(d, nz, H, precision)) return B200VAE_EUNSUP;
   const bool x3 = precision == B200VAE_PREC_TF32X3;
+  const int bn = wt_tile_n(x3);                         // rows of a B-operand TMA box = the kernel's tile width
   const WtLayout L = wt_layout(B, d, H);
   wide_tc_prepare_kernel<<<148 * 4, 256, 0, st>>>(p->W0, p->W1, p->A0w, p->A1w, d, H, mode, ws, L);
   int rc = check_launch();
@@ -494,8 +524,8 @@ int wide_tc_fwd(const float* z, int B, int d, int nz, int H, const b200vae_icnn_
   memset(&a, 0, sizeof(a));
   // ---- lin: h0 = z A0^T + b0   (A0w is [H][d]; only its first nz columns meet non-zero inputs)
   rc = wt_map(&a.a1, z, nz, B, nz, 128);
-  if (!rc) rc = wt_map(&a.b1hi, ws + L.A0hi, nz, H, d, 256);
-  if (!rc) rc = wt_map(&a.b1lo, ws + L.A0lo, nz, H, d, 256);
+  if (!rc) rc = wt_map(&a.b1hi, ws + L.A0hi, nz, H, d, wt_tile_n(true));
+  if (!rc) rc = wt_map(&a.b1lo, ws + L.A0lo, nz, H, d, wt_tile_n(true));
   if (rc) return rc;
   a.a2 = a.a1; a.b2hi = a.b1hi; a.b2lo = a.b1lo;
   a.nkb1 = nkb(nz); a.nkb2 = 0; a.xf1 = WT_XF_ID; a.M = B; a.N = H; a.epi = WT_EPI_LIN; a.bias = p->A0b; a.out0 = h0;
@@ -505,25 +535,25 @@ int wide_tc_fwd(const float* z, int B, int d, int nz, int H, const b200vae_icnn_
   WtArgs b;
   memset(&b, 0, sizeof(b));
   rc = wt_map(&b.a1, h0, H, B, H, 128);
-  if (!rc) rc = wt_map(&b.b1hi, ws + L.P0hi, H, H, H, 256);
-  if (!rc) rc = wt_map(&b.b1lo, ws + (x3 ? L.P0lo : L.P0hi), H, H, H, 256);
-  if (!rc) rc = wt_map(&b.b2hi, ws + L.A1hi, nz, H, d, 256);
-  if (!rc) rc = wt_map(&b.b2lo, ws + (x3 ? L.A1lo : L.A1hi), nz, H, d, 256);
+  if (!rc) rc = wt_map(&b.b1hi, ws + L.P0hi, H, H, H, bn);
+  if (!rc) rc = wt_map(&b.b1lo, ws + (x3 ? L.P0lo : L.P0hi), H, H, H, bn);
+  if (!rc) rc = wt_map(&b.b2hi, ws + L.A1hi, nz, H, d, bn);
+  if (!rc) rc = wt_map(&b.b2lo, ws + (x3 ? L.A1lo : L.A1hi), nz, H, d, bn);
   if (rc) return rc;
   b.a2 = a.a1;
   b.nkb1 = nkb(H); b.nkb2 = nkb(nz); b.xf1 = WT_XF_X1; b.M = B; b.N = H; b.epi = WT_EPI_HID; b.bias = p->A1b; b.P1 = ws + L.P1;
-  b.out0 = ws + L.g1b; b.mask = mask1; b.part = ws + L.part; b.npart = L.nt * 2;
+  b.out0 = ws + L.g1b; b.mask = mask1; b.part = ws + L.part; b.npart = ((H + bn - 1) / bn) * 2;
   rc = wt_run(b, x3, st);
   if (rc) return rc;
-  wide_tc_row_kernel<<<(B + 7) / 8, 256, 0, st>>>(ws + L.part, L.nt * 2, z, p->A2w, p->A2b, B, nz, psi, s2);
+  wide_tc_row_kernel<<<(B + 7) / 8, 256, 0, st>>>(ws + L.part, b.npart, z, p->A2w, p->A2b, B, nz, psi, s2);
   rc = check_launch();
   if (rc || !xhat) return rc;
   // ---- gx1: g0' = (g1b P0) * c0(h0)      B^T[k'][n] = P0[n][k'] = P0T
   WtArgs c;
   memset(&c, 0, sizeof(c));
   rc = wt_map(&c.a1, ws + L.g1b, H, B, H, 128);
-  if (!rc) rc = wt_map(&c.b1hi, ws + L.P0Thi, H, H, H, 256);
-  if (!rc) rc = wt_map(&c.b1lo, ws + (x3 ? L.P0Tlo : L.P0Thi), H, H, H, 256);
+  if (!rc) rc = wt_map(&c.b1hi, ws + L.P0Thi, H, H, H, bn);
+  if (!rc) rc = wt_map(&c.b1lo, ws + (x3 ? L.P0Tlo : L.P0Thi), H, H, H, bn);
   if (rc) return rc;
   c.a2 = c.a1; c.b2hi = c.b1hi; c.b2lo = c.b1lo;
   c.nkb1 = nkb(H); c.nkb2 = 0; c.xf1 = WT_XF_ID; c.M = B; c.N = H; c.epi = WT_EPI_GX1; c.h0 = h0; c.out0 = g0;
@@ -533,10 +563,10 @@ int wide_tc_fwd(const float* z, int B, int d, int nz, int H, const b200vae_icnn_
   WtArgs e;
   memset(&e, 0, sizeof(e));
   rc = wt_map(&e.a1, g0, H, B, H, 128);
-  if (!rc) rc = wt_map(&e.b1hi, ws + L.A0Thi, H, d, H, 256);
-  if (!rc) rc = wt_map(&e.b1lo, ws + (x3 ? L.A0Tlo : L.A0Thi), H, d, H, 256);
-  if (!rc) rc = wt_map(&e.b2hi, ws + L.A1Thi, H, d, H, 256);
-  if (!rc) rc = wt_map(&e.b2lo, ws + (x3 ? L.A1Tlo : L.A1Thi), H, d, H, 256);
+  if (!rc) rc = wt_map(&e.b1hi, ws + L.A0Thi, H, d, H, bn);
+  if (!rc) rc = wt_map(&e.b1lo, ws + (x3 ? L.A0Tlo : L.A0Thi), H, d, H, bn);
+  if (!rc) rc = wt_map(&e.b2hi, ws + L.A1Thi, H, d, H, bn);
+  if (!rc) rc = wt_map(&e.b2lo, ws + (x3 ? L.A1Tlo : L.A1Thi), H, d, H, bn);
   if (rc) return rc;
   e.a2 = c.a1;
   e.nkb1 = nkb(H); e.nkb2 = nkb(H); e.xf1 = WT_XF_ID; e.M = B; e.N = d; e.epi = WT_EPI_OUT; e.s2 = s2; e.A2w = p->A2w; e.z = z;
@@ -552,6 +582,7 @@ int wide_tc_bwd_rows(const float* v, const float* h0, const uint8_t* mask1, cons
                      float* dW1, float* db0, float* ws, float* colpart, int precision, cudaStream_t st) {
   if (!wide_tc_supported(d, nz, H, precision)) return B200VAE_EUNSUP;
   const bool x3 = precision == B200VAE_PREC_TF32X3;
+  const int bn = wt_tile_n(x3);                         // rows of a B-operand TMA box = the kernel's tile width
   const WtLayout L = wt_layout(B, d, H);
   wide_tc_prepare_kernel<<<148 * 4, 256, 0, st>>>(p->W0, p->W1, p->A0w, p->A1w, d, H, mode, ws, L);
   int rc = check_launch();
@@ -567,8 +598,8 @@ int wide_tc_bwd_rows(const float* v, const float* h0, const uint8_t* mask1, cons
   WtArgs a;
   memset(&a, 0, sizeof(a));
   rc = wt_map(&a.a1, v, d, B, d, 128);
-  if (!rc) rc = wt_map(&a.b1hi, ws + L.A0hi, d, H, d, 256);
-  if (!rc) rc = wt_map(&a.b1lo, ws + (x3 ? L.A0lo : L.A0hi), d, H, d, 256);
+  if (!rc) rc = wt_map(&a.b1hi, ws + L.A0hi, d, H, d, bn);
+  if (!rc) rc = wt_map(&a.b1lo, ws + (x3 ? L.A0lo : L.A0hi), d, H, d, bn);
   if (rc) return rc;
   a.a2 = a.a1; a.b2hi = a.b1hi; a.b2lo = a.b1lo;
   a.nkb1 = nkb(d); a.nkb2 = 0; a.xf1 = WT_XF_ID; a.M = B; a.N = H; a.epi = WT_EPI_U; a.h0 = h0; a.out0 = u0; a.out1 = q1;
@@ -578,10 +609,10 @@ int wide_tc_bwd_rows(const float* v, const float* h0, const uint8_t* mask1, cons
   WtArgs b;
   memset(&b, 0, sizeof(b));
   rc = wt_map(&b.a1, q1, H, B, H, 128);
-  if (!rc) rc = wt_map(&b.b1hi, ws + L.P0hi, H, H, H, 256);
-  if (!rc) rc = wt_map(&b.b1lo, ws + (x3 ? L.P0lo : L.P0hi), H, H, H, 256);
-  if (!rc) rc = wt_map(&b.b2hi, ws + L.A1hi, d, H, d, 256);
-  if (!rc) rc = wt_map(&b.b2lo, ws + (x3 ? L.A1lo : L.A1hi), d, H, d, 256);
+  if (!rc) rc = wt_map(&b.b1hi, ws + L.P0hi, H, H, H, bn);
+  if (!rc) rc = wt_map(&b.b1lo, ws + (x3 ? L.P0lo : L.P0hi), H, H, H, bn);
+  if (!rc) rc = wt_map(&b.b2hi, ws + L.A1hi, d, H, d, bn);
+  if (!rc) rc = wt_map(&b.b2lo, ws + (x3 ? L.A1lo : L.A1hi), d, H, d, bn);
   if (rc) return rc;
   b.a2 = a.a1;
   b.nkb1 = nkb(H); b.nkb2 = nkb(d); b.xf1 = WT_XF_ID; b.M = B; b.N = H; b.epi = WT_EPI_W1; b.s2 = s2;
@@ -600,8 +631,8 @@ int wide_tc_bwd_rows(const float* v, const float* h0, const uint8_t* mask1, cons
   WtArgs c;
   memset(&c, 0, sizeof(c));
   rc = wt_map(&c.a1, ws + L.g1b, H, B, H, 128);
-  if (!rc) rc = wt_map(&c.b1hi, ws + L.P0Thi, H, H, H, 256);
-  if (!rc) rc = wt_map(&c.b1lo, ws + (x3 ? L.P0Tlo : L.P0Thi), H, H, H, 256);
+  if (!rc) rc = wt_map(&c.b1hi, ws + L.P0Thi, H, H, H, bn);
+  if (!rc) rc = wt_map(&c.b1lo, ws + (x3 ? L.P0Tlo : L.P0Thi), H, H, H, bn);
   if (rc) return rc;
   c.a2 = c.a1; c.b2hi = c.b1hi; c.b2lo = c.b1lo;
   c.nkb1 = nkb(H); c.nkb2 = 0; c.xf1 = WT_XF_ID; c.M = B; c.N = H; c.epi = WT_EPI_GXB; c.h0 = h0; c.u0 = u0; c.s2 = s2;
@@ -621,8 +652,8 @@ int wide_tc_bwd_rows(const float* v, const float* h0, const uint8_t* mask1, cons
   WtArgs e;
   memset(&e, 0, sizeof(e));
   rc = wt_map(&e.a1, t0, H, B, H, 128);
-  if (!rc) rc = wt_map(&e.b1hi, ws + L.A0Thi, H, nz, H, 256);
-  if (!rc) rc = wt_map(&e.b1lo, ws + (x3 ? L.A0Tlo : L.A0Thi), H, nz, H, 256);
+  if (!rc) rc = wt_map(&e.b1hi, ws + L.A0Thi, H, nz, H, bn);
+  if (!rc) rc = wt_map(&e.b1lo, ws + (x3 ? L.A0Tlo : L.A0Thi), H, nz, H, bn);
   if (rc) return rc;
   e.a2 = e.a1; e.b2hi = e.b1hi; e.b2lo = e.b1lo;
   e.nkb1 = nkb(H); e.nkb2 = 0; e.xf1 = WT_XF_ID; e.M = B; e.N = nz; e.epi = WT_EPI_DZ; e.v = v; e.ldv = d; e.kappa2 = 2.f * kappa;
@@ -658,7 +689,7 @@ int wide_tc_bwd_tn(const float* z, const float* v, const uint8_t* mask1, const f
   if (!wide_tc_supported(d, nz, H, precision)) return B200VAE_EUNSUP;
   const bool x3 = precision == B200VAE_PREC_TF32X3;
   const WtTnLayout T = wt_tn_layout(B, d, nz, H);
-  const int ldb = T.ldb;
+  const int ldb = T.ldb, bn = wt_tile_n(x3);
   int rc;
   auto transpose = [&](const float* src, int md, int C, float* hi, float* lo) {
     dim3 grid((B + 31) / 32, (C + 31) / 32);
@@ -672,12 +703,12 @@ int wide_tc_bwd_tn(const float* z, const float* v, const uint8_t* mask1, const f
     WtArgs a;
     memset(&a, 0, sizeof(a));
     int r = wt_map(&a.a1, At, B, H, ldb, 128);
-    if (!r) r = wt_map(&a.b1hi, Bhi, B, N, ldb, 256);
-    if (!r) r = wt_map(&a.b1lo, x3 ? Blo : Bhi, B, N, ldb, 256);
+    if (!r) r = wt_map(&a.b1hi, Bhi, B, N, ldb, bn);
+    if (!r) r = wt_map(&a.b1lo, x3 ? Blo : Bhi, B, N, ldb, bn);
     if (!r && At2) {
       r = wt_map(&a.a2, At2, B, H, ldb, 128);
-      if (!r) r = wt_map(&a.b2hi, B2hi, B, N2, ldb, 256);
-      if (!r) r = wt_map(&a.b2lo, x3 ? B2lo : B2hi, B, N2, ldb, 256);
+      if (!r) r = wt_map(&a.b2hi, B2hi, B, N2, ldb, bn);
+      if (!r) r = wt_map(&a.b2lo, x3 ? B2lo : B2hi, B, N2, ldb, bn);
     } else if (!r) {
       a.a2 = a.a1; a.b2hi = a.b1hi; a.b2lo = a.b1lo;
     }

@@ -149,14 +149,18 @@ inline float* tc_base(float* ws, int d, int H) {
 //   scr1 float4 [Bp][NP][2]  (h2 partial, tpos_0..2) per (row, pass, column half);  scr2 float4 same shape (X_0..2)
 //   imask u32 [Bp][Hq/32]    LeakyReLU bits of h1 when the caller does not ask for mask1
 //   cscr float4 [clusters][2 CTAs][2 halves][32][128 rows]   3xTF32 only: running sums of the K-chunked accumulation.  The
-//                            tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
-//                            MMAs per accumulator; the forward therefore accumulates K in chunks of kTc3ChunkK, each in a
-//                            fresh accumulator, and the epilogue warps add the chunks with round-to-nearest FP32 adds.  A thread
-//                            re-reads only what it wrote itself; 256 KB per cluster, L2 resident.
+//                            tensor core adds into its fp32 accumulator with truncation, a downward bias that grows with the
+//                            SQUARE of the accumulated K (measured on psi at H = 1024: 7.8e-6 / 1.2e-5 in one piece, 4.3e-6 /
+//                            5.6e-6 in chunks of 512, 2.1e-6 / 2.8e-6 in chunks of 256 -- "mixed" / "default" weights); the
+//                            forward therefore accumulates K in chunks of kTc3ChunkK, each in a fresh accumulator, and the
+//                            epilogue warps add the chunks with round-to-nearest FP32 adds.  A thread re-reads only what it
+//                            wrote itself; 256 KB per cluster, L2 resident.  Cost: 256 KB of L2 traffic per extra chunk and
+//                            CTA next to the 16 KB per K-block of TMA operand traffic (the kernel moves ~6 TB/s out of L2):
+//                            +6 % per extra chunk, hence 512 (north_star's 1e-5 is met with 1.8x margin) and not 256.
 constexpr int kTc3MaxTiles = 16384;
 constexpr int kTc3MaxClusters = 80;
 constexpr size_t k3ScrFloatsPerCta = (size_t)128 * 256;
-constexpr int kTc3ChunkK = 256;
+constexpr int kTc3ChunkK = 512;
 struct Tc3Layout {
   int Hq, K1, NP, Bp;
   size_t B1ahi, B1alo, B2ghi, B2glo, A0g, E1, sumV, cnt, fixed_end, scr1, scr2, imask, cscr, end;
