@@ -37,7 +37,9 @@ extern "C" {
 /* arithmetic of the two H x H contractions */
 #define B200VAE_PREC_FP32 0   /* FP32 SIMT FMA: the parity path (rtol 1e-5)                */
 #define B200VAE_PREC_TF32 1   /* tcgen05 kind::tf32, fp32 accumulate in TMEM               */
-#define B200VAE_PREC_BF16 2   /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate        */
+/* value 2 is RESERVED and rejected with B200VAE_EUNSUP: version 0.1 declared a bf16 (tcgen05 kind::f16) mode here that was
+ * never built.  It is not coming back for the d <= 3 kernels -- they GENERATE their A operands, so halving the tensor time
+ * per MAC would make operand generation the bound, at an 8-bit mantissa -- see DESIGN.md "Out of scope". */
 #define B200VAE_PREC_TF32X3 3 /* tcgen05 3xTF32 split (hi*hi + hi*lo + lo*hi): fp32-grade  */
 
 /* Parameters of one module.ICNN(in_channel=d, hidden_channel=H) -- module.py:117-140.

@@ -108,7 +108,7 @@ def test_tc_unsupported_is_loud():
         ops.IcnnBrenierFn.apply(torch.zeros(8, 4, device="cuda"), 0.0, 0, 1, *params_to_torch(p))   # d=4 on the TC path
     with pytest.raises(_C.B200VaeError):
         ops.IcnnBrenierFn.apply(torch.zeros(8, 2, device="cuda"), 0.0, 0, 2,
-                                *params_to_torch(io.random_params(rng, 2, 64, np.float64, "mixed")))  # bf16 not built
+                                *params_to_torch(io.random_params(rng, 2, 64, np.float64, "mixed")))  # precision id 2 is reserved (never built)
 
 
 def test_persistent_pair_kernels_match_single_cta_kernels():

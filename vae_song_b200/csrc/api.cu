@@ -87,7 +87,9 @@ static int shape_ok(int B, int d, int H) {
   if (H > 4096) return B200VAE_EUNSUP;
   return B200VAE_OK;
 }
-static bool prec_ok(int precision) { return precision >= B200VAE_PREC_FP32 && precision <= B200VAE_PREC_TF32X3; }
+static bool prec_ok(int precision) {
+  return precision == B200VAE_PREC_FP32 || precision == B200VAE_PREC_TF32 || precision == B200VAE_PREC_TF32X3;   // 2 is reserved
+}
 }  // namespace b200vae
 
 using namespace b200vae;

@@ -949,7 +949,7 @@ static int make_map(CUtensorMap* m, const float* base, int Hq) {
 
 int tc_prepare(const b200vae_icnn_params* p, int d, int H, int mode, int precision, float* ws, cudaStream_t st) {
   (void)p; (void)mode;
-  if (precision == B200VAE_PREC_BF16) return B200VAE_EUNSUP;
+  if (precision == 2 /* reserved */) return B200VAE_EUNSUP;
   if (d > 3) return B200VAE_EUNSUP;
   const WsLayout L = ws_layout(1, d, H);
   const TcLayout T = tc_layout(d, H);
@@ -1001,7 +1001,7 @@ static int get_maps(const float* tb, const TcLayout& T, TcMaps* out) {
 
 int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2,
            int precision, const float* ws, cudaStream_t st) {
-  if (precision == B200VAE_PREC_BF16 || d > 3) return B200VAE_EUNSUP;
+  if (precision == 2 /* reserved */ || d > 3) return B200VAE_EUNSUP;
   const WsLayout L = ws_layout(1, d, H);
   const TcLayout T = tc_layout(d, H);
   const float* tb = tc_base(const_cast<float*>(ws), d, H);
@@ -1089,7 +1089,7 @@ static int launch_tc_dp0(const float* z, const float* v, const uint32_t* mask1, 
 int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H,
            const b200vae_icnn_params* p, int mode, float kappa, const b200vae_icnn_grads* g, float* dz, int precision,
            float* ws, const float* accsave, cudaStream_t st) {
-  if (precision == B200VAE_PREC_BF16 || d > 3 || !v) return B200VAE_EUNSUP;
+  if (precision == 2 /* reserved */ || d > 3 || !v) return B200VAE_EUNSUP;
   const size_t extra = tc_extra_ws_floats(B, d, H, precision);
   const WsLayout L = ws_layout(B, d, H, extra);
   const TcLayout T = tc_layout(d, H);

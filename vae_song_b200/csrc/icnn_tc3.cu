@@ -1533,7 +1533,7 @@ static int launch_tc3_dp0(const float* z, const float* v, const uint32_t* mask1,
 // part: [splits][Hq][Hq] ordered split-K slabs (reduced by finalize_W0_kernel); *splits_out <= max_splits
 int tc3_dp0(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int Hq, int Hw_in,
             const float* A0q, int precision, int max_splits, float* part, int* splits_out, cudaStream_t st) {
-  if (precision == B200VAE_PREC_BF16 || d > 3) return B200VAE_EUNSUP;
+  if (precision == 2 /* reserved */ || d > 3) return B200VAE_EUNSUP;
   const bool x3 = (precision == B200VAE_PREC_TF32X3);
   const float4* q = reinterpret_cast<const float4*>(A0q);
 #define B200VAE_TC3D(DD)                                                                                             \
@@ -1564,7 +1564,7 @@ static int launch_tc3_bwd(const Tc3BwdArgs& args, cudaStream_t st) {
 int tc3_bwd_rows(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H, float kappa,
                  float* dz, float* partA, float* partB, float* a2part, float* dzpart, int precision, float* ws,
                  const float* accsave, cudaStream_t st) {
-  if (precision == B200VAE_PREC_BF16 || d > 3) return B200VAE_EUNSUP;
+  if (precision == 2 /* reserved */ || d > 3) return B200VAE_EUNSUP;
   const WsLayout L = ws_layout(1, d, H);
   const TcLayout T = tc_layout(d, H);
   const Tc3Layout T3 = tc3_layout(B, d, H);
@@ -1619,7 +1619,7 @@ static int launch_tc3(const Tc3Args& args, int units, cudaStream_t st) {
 
 int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2,
             int precision, float* ws, float* accsave, cudaStream_t st) {
-  if (precision == B200VAE_PREC_BF16 || d > 3) return B200VAE_EUNSUP;
+  if (precision == 2 /* reserved */ || d > 3) return B200VAE_EUNSUP;
   const WsLayout L = ws_layout(1, d, H);
   const TcLayout T = tc_layout(d, H);
   const Tc3Layout T3 = tc3_layout(B, d, H);

@@ -39,7 +39,7 @@ class ICNN(nn.Module):
     forward(z) -> psi [B,1], twice differentiable in z (so the reference idiom
     ``autograd.grad(icnn(z), [z], ones, create_graph=True)`` keeps working);
     brenier(z, kappa) -> (psi [B], grad_z(psi + kappa|z|^2) [B,d]) in ONE fused kernel.
-    ``precision`` selects the arithmetic of the H x H contractions: fp32 (parity), tf32, bf16, tf32x3."""
+    ``precision`` selects the arithmetic of the H x H contractions: fp32 (parity), tf32x3 (fp32-grade, tensor cores), tf32."""
 
     def __init__(self, in_channel, hidden_channel=128, num_layers=2, precision="fp32"):
         super().__init__()
