@@ -157,7 +157,10 @@ int b200vae_adam_step_sched(float* param, const float* grad, float* m, float* v,
  * Widths <= 128 (backward: powers of two).  A layer INPUT is described by the previous layer's pre-BN output
  * `*_y` [B,w] plus its BatchNorm statistics `*_stats` [4][w] = (mean, biased var, invstd, count), gamma, beta; the
  * LeakyReLU(BN(.)) is applied while loading.  `*_stats` == NULL means "raw input, no BN/activation".
- * `scratch`: b200vae_mlp_scratch_bytes(B) bytes of caller-owned device memory. */
+ * `scratch`: b200vae_mlp_scratch_bytes(B) bytes of caller-owned device memory -- ordered per-CTA partials plus, in its last
+ * 256 bytes, the ticket with which the LAST CTA of a layer kernel finalises the layer's statistics / sums / weight gradient
+ * itself (no separate finalize launch on one GPU).  The ticket must be ZERO before the first call and is left zero by
+ * every call: zero-initialise the buffer once and reuse it (per stream). */
 size_t b200vae_mlp_scratch_bytes(int B);
 /* y_out [B,wo] = act(in) W^T + bias, W [wo,wi]; if stats_out != NULL also the batch statistics of y_out (and, when
  * running_mean/var != NULL, their momentum update with the unbiased variance -- torch.nn.BatchNorm1d semantics). */
@@ -193,7 +196,8 @@ int b200vae_nn_sqdist_bwd(const float* A, const float* Bp, const int* argA, cons
  * double-backward), FP32, as a chain of fused tile GEMMs whose operands are generated while loading (csrc/icnn_wide.cu).
  * Caller-owned activations: h0 [B,H] fp32, mask1 [B,H] uint8 (h1 > 0), s2 [B] fp32 (1 or 0.2) are SAVED by the forward
  * for the backward; g0 (fwd) and u0,q1,g0,t0 (bwd) are [B,H] fp32 scratch.  psi may be NULL; xhat NULL = psi only.
- * The backward takes v = dL/dxhat only (no psi-gradient) and OVERWRITES every non-null field of `g` and dz.
+ * b200vae_icnn_wide_bwd takes v = dL/dxhat (the psi-gradient path is b200vae_icnn_wide_bwd_psi below) and OVERWRITES every
+ * non-null field of `g` and dz.
  * `precision` (forward): FP32 = the tile-GEMM chain above; TF32 / TF32X3 = the same chain on tcgen05 (csrc/icnn_wide_tc.cu:
  * TMA-fed 128x256 tiles, transform + hi/lo split of the A tile in shared memory, accumulators in TMEM) when d, nz, H are
  * multiples of 4, else FP32.  Backward with TF32 / TF32X3: the sample-stationary GEMMs (u0, w1, gx1, dz) run on the same
@@ -210,10 +214,29 @@ int b200vae_icnn_wide_bwd(const float* z, const float* v, const float* h0, const
                           const b200vae_icnn_grads* g, float* dz, float* u0, float* q1, float* g0, float* t0, int precision,
                           void* workspace, size_t ws_bytes, void* stream);
 
+/* First-order backward of psi for wide inputs (what autograd runs when module.ICNN.forward's output carries a gradient,
+ * module.py:142-148; SURVEY Appendix A last line): gradients of L = sum_b gpsi[b]*psi[b] w.r.t. z (dz [B,nz], may be NULL)
+ * and every parameter (non-null fields of `g` are OVERWRITTEN; A1b / A2b are NOT zero on this path).  h0 / mask1 / s2 as
+ * saved by b200vae_icnn_wide_fwd (any precision); x1, g0 [B,H] fp32 and s2g [B] fp32 are caller-owned scratch; workspace
+ * as for b200vae_icnn_wide_bwd with precision FP32 (this path runs on the FP32 tile kernels). */
+int b200vae_icnn_wide_bwd_psi(const float* z, const float* gpsi, const float* h0, const uint8_t* mask1, const float* s2, int B,
+                              int d, int nz, int H, const b200vae_icnn_params* p, int weight_mode,
+                              const b200vae_icnn_grads* g, float* dz, float* x1, float* g0, float* s2g, void* workspace,
+                              size_t ws_bytes, void* stream);
+
 /* ---- aggregate-posterior log-density for calc_mi (utils.py:87-107) ------------------------------------
  * logqz[i] = logsumexp_j log N(z[i]; mu[j], diag exp(lv[j])) - log B for z, mu, lv [B,nz]: tiled all-pairs with an online
  * logsumexp; the [B,B,nz] tensor of the reference is never formed. */
 int b200vae_mi_logqz(const float* z, const float* mu, const float* lv, int B, int nz, float* logqz, void* stream);
+
+/* Importance-weighted likelihood bound, utils.py:109-120 (nll_iw): out[0] = logsumexp over all (b, s) of
+ * log p(z[b,s]) - log q(z[b,s] | x_b) with z = mu + eps*exp(lv/2); mu, lv [B,nz], eps [B,S,nz] (the caller draws eps so that
+ * the random stream stays torch's).  The caller finishes  nll = -(out[0] - loss_rec - log S).  The reference materialises
+ * z [B,S,nz] and three [B,S] log-density tensors; here it is one pass with an online logsumexp (ordered: reproducible).
+ * scratch: b200vae_nll_iw_scratch_bytes() bytes, zero before the first call, left ready by every call. */
+size_t b200vae_nll_iw_scratch_bytes(void);
+int b200vae_nll_iw_lse(const float* mu, const float* lv, const float* eps, int B, int S, int nz, float* out, void* scratch,
+                       void* stream);
 
 /* ---- peer-memory exchange between the GPUs of one node (the data-parallel exchange steps) ---------------
  * The reference has no multi-GPU path; these replace what torch.distributed/NCCL would do for the LATENCY-bound

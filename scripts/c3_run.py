@@ -31,9 +31,48 @@ tr.capture(xb)
 sync(); t0 = time.perf_counter()
 for X, _ in loader:
     tr.step_graphed(X.to(dev, non_blocking=True))
-sync(); t_graph = (time.perf_counter() - t0) / len(loader)
+sync(); t_graph_loader = (time.perf_counter() - t0) / len(loader)
+# the step itself: device-resident batches, CUDA events around 200 replays (the DataLoader above costs more host time per
+# batch of 256 than the replayed step runs)
+staged = [b.to(dev) for b, _ in zip((x for x, _ in loader), range(16))]
+for i in range(20):
+    tr.step_graphed(staged[i % 16])
+sync()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(200):
+    tr.step_graphed(staged[i % 16])
+e1.record(); sync()
+t_graph = e0.elapsed_time(e1) / 200 * 1e-3
+print(f"C3 whole-step CUDA graph fed by the DataLoader (host-bound): {t_graph_loader * 1e3:.3f} ms/step")
+# the UNMODIFIED reference (oracle/_ref, populated by oracle/fetch_ref.py) on the same GPU, same loader, same loop
+t_ref = None
+try:
+    from oracle import fetch_ref
+    ns = fetch_ref.import_ref()
+    torch.manual_seed(20)
+    mr = ns.model.LIDVAE(inverse_lipschitz=0.2, beta=0.001, dataset="pinwheel", hidden_channels=[128, 64, 64, 32, 16, 8, 4, 2]).to(dev)
+    rr = np.random.default_rng(1)
+    for ic in (mr.decoder[0], mr.decoder[1]):
+        H = ic.A0.weight.shape[0]
+        with torch.no_grad():
+            ic.W[0].param.copy_(torch.tensor(rr.normal(np.log(1.0 / H), 1.0, (H, H)), dtype=torch.float32))
+            ic.W[1].param.copy_(torch.tensor(rr.normal(np.log(2.0 / H), 1.0, (1, H)), dtype=torch.float32))
+            ic.A[0].bias.copy_(torch.tensor(rr.normal(-0.3, 1.0, (H,)), dtype=torch.float32))
+    import contextlib, io
+    with contextlib.redirect_stderr(io.StringIO()):
+        ns.lipschitz.train_model(mr, [b for _, b in zip(range(8), loader)], 1, 1e-3, dev)
+        sync(); t0 = time.perf_counter()
+        ns.lipschitz.train_model(mr, loader, 1, 1e-3, dev)
+    sync(); t_ref = (time.perf_counter() - t0) / len(loader)
+    print(f"C3 train step, batch {B}: UNMODIFIED reference (oracle/_ref, stock PyTorch eager FP32) on this GPU {t_ref * 1e3:.3f} ms/step "
+          f"({B / t_ref / 1e3:.1f} k samples/s)")
+    del mr
+except Exception as exc:
+    print("reference on this GPU unavailable:", exc)
 print(f"C3 train step, batch {B}, precision {prec}: eager loop {t_eager * 1e3:.3f} ms/step ({B / t_eager / 1e3:.1f} k samples/s), "
-      f"whole-step CUDA graph {t_graph * 1e3:.3f} ms/step ({B / t_graph / 1e3:.1f} k samples/s)")
+      f"whole-step CUDA graph {t_graph * 1e3:.3f} ms/step ({B / t_graph / 1e3:.1f} k samples/s)"
+      + (f" = {t_ref / t_graph:.1f}x the unmodified reference" if t_ref else ""))
 
 m.eval()
 L.evaluate(m, ds, K, Kz, -3.0, 3.0, 2, dev)          # warm-up (allocator growth for the 512k-row batched decodes)

@@ -9,6 +9,7 @@ Each step is timed launched eagerly from Python and replayed as ONE CUDA graph (
 import copy, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from bench import eager_icnn_potential
 import numpy as np, torch, torch.nn.functional as F
 from vae_song_b200 import main as M, model, ops, train, utils as vutils
 
@@ -87,7 +88,7 @@ for prec in ("tf32x3", "tf32", "fp32"):
         kappa = ref.il_factor
 
         def brenier(ic, zz):
-            psi = ops.icnn_potential_wide(zz, ic._mode(), *ic._flat_params()) + kappa * zz.pow(2).sum(1, keepdim=True)
+            psi = eager_icnn_potential(zz, ic._mode(), *ic._flat_params()) + kappa * zz.pow(2).sum(1, keepdim=True)
             return torch.autograd.grad(psi, [zz], torch.ones_like(psi), create_graph=True)[0]
 
         def rstep(i):

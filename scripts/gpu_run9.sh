@@ -1,0 +1,7 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+python scripts/profile_allpairs.py 50000 > gpurun_out/r2_09_ap_plain.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:allpairs -c 2 -o gpurun_out/prof_r2_allpairs -f python scripts/profile_allpairs.py 50000 > gpurun_out/r2_09_ncu.log 2>&1
+python scripts/profile_decode.py --precision tf32x3 --H 1024 > gpurun_out/r2_09_dec_plain.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:icnn_tc3_fwd -c 2 -o gpurun_out/prof_r2_tc3_fwd_x3 -f python scripts/profile_decode.py --precision tf32x3 --H 1024 > gpurun_out/r2_09_ncu2.log 2>&1
+timeout 300 python bench.py --steps 5 --warmup 3 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(json.dumps(d['extra']['lipschitz_estimator']))" > gpurun_out/r2_09_ap_bench.json

@@ -3,6 +3,7 @@
 formulation (module.py:142-148 + autograd.grad(create_graph=True), model.py:818-830) with cuBLAS FP32 GEMMs."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import eager_icnn_potential
 import numpy as np, torch
 from vae_song_b200 import module, ops, utils as vutils
 
@@ -37,7 +38,7 @@ def fused(train):
 
 def eager(train):
     def brenier(ic, x):
-        psi = ops.icnn_potential_wide(x, ic._mode(), *ic._flat_params()) + kappa * x.pow(2).sum(1, keepdim=True)
+        psi = eager_icnn_potential(x, ic._mode(), *ic._flat_params()) + kappa * x.pow(2).sum(1, keepdim=True)
         return torch.autograd.grad(psi, [x], torch.ones_like(psi), create_graph=True)[0]
     x1 = brenier(ics[0], z)
     y = brenier(ics[1], torch.nn.functional.linear(x1, torch.eye(784, 32, device=dev)))

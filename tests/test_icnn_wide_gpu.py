@@ -104,17 +104,78 @@ def test_wide_is_deterministic_and_psi_only_inference():
     close_rows(xh.detach().cpu().numpy(), a[1], 1e-5, "autograd Brenier == fused", kink_rows(aux, H_RTOL[0]))
 
 
-def test_wide_rejects_cpu_and_psi_gradient():
+def test_wide_rejects_cpu():
     from vae_song_b200 import _C, ops
     p, z, v, _ = case_inputs(8, 16, 4, "mixed", 5)
     params = params_to_torch(p, "cpu")
     with pytest.raises(_C.B200VaeError):
         ops.IcnnBrenierWideFn.apply(torch.tensor(z, dtype=torch.float32), 0.0, 0, 0, *params)
+
+
+PSI_SHAPES = [(8, 16, 4, "mixed", 0, 0.0, 5), (32, 128, 70, "mixed", 0, 0.1, 301), (36, 96, 300, "clampy", 1, 0.2, 302),
+              (784, 64, 40, "mixed", 0, 0.05, 303)]
+
+
+@pytest.mark.parametrize("with_v", [False, True], ids=["gpsi", "gpsi+v"])
+@pytest.mark.parametrize("shape", PSI_SHAPES, ids=[f"d{s[0]}_h{s[1]}_b{s[2]}" for s in PSI_SHAPES])
+def test_wide_psi_gradient_vs_oracle(shape, with_v):
+    """First-order backward of psi for wide inputs (b200vae_icnn_wide_bwd_psi; SURVEY Appendix A last line), alone and
+    together with the dL/dxhat path, against oracle.icnn_brenier_backward(..., gpsi): A1b / A2b are NOT zero here."""
+    from vae_song_b200 import ops
+    d, H, B, regime, mode, kappa, seed = shape
+    p, z, v, gpsi = case_inputs(d, H, B, regime, seed)
     params = [t.requires_grad_(True) for t in params_to_torch(p, "cuda")]
     zt = torch.tensor(z, dtype=torch.float32, device="cuda", requires_grad=True)
-    psi, xhat = ops.IcnnBrenierWideFn.apply(zt, 0.0, 0, 0, *params)
-    with pytest.raises(NotImplementedError):
-        psi.sum().backward()
+    psi, xhat = ops.IcnnBrenierWideFn.apply(zt, kappa, mode, 0, *params)
+    L = (psi * torch.tensor(gpsi, dtype=torch.float32, device="cuda")).sum()
+    if with_v:
+        L = L + (xhat * torch.tensor(v, dtype=torch.float32, device="cuda")).sum()
+    L.backward()
+    p64, z64 = params_f32_as_f64(p), f32_as_f64(z)
+    _, _, aux = io.icnn_brenier(z64, p64, mode, kappa, keep=True)
+    v64 = f32_as_f64(v) if with_v else np.zeros_like(z64)
+    rdz, rg = io.icnn_brenier_backward(z64, v64, p64, mode, kappa, f32_as_f64(gpsi))
+    close_rows(zt.grad.cpu().numpy(), rdz, 1e-4, "dz", kink_rows(aux, H_RTOL[0], with_h0=True), loose=5e-2)
+    for k, t in zip(KEYS, params):
+        assert np.abs(rg[k]).max() > 0, k
+        close_report(t.grad.cpu().numpy(), rg[k], 1e-4, "grad " + k)
+
+
+def test_wide_module_forward_is_twice_differentiable_on_the_fused_kernels():
+    """module.ICNN(d > 4).forward used like the reference uses it: (a) psi.backward() -- first-order gradients through the
+    fused psi-gradient kernels (no torch.nn.functional.linear on this path); (b) autograd.grad(create_graph=True) followed by
+    backward -- the Brenier map and its double-backward (model.py:820-828)."""
+    from vae_song_b200 import module
+    d, H, B = 32, 128, 70
+    p, z, v, gpsi = case_inputs(d, H, B, "mixed", 311)
+    ic = module.ICNN(d, H).cuda()
+    with torch.no_grad():
+        for t, src in zip(ic._flat_params(), params_to_torch(p, "cuda")):
+            t.copy_(src)
+    p64, z64 = params_f32_as_f64(p), f32_as_f64(z)
+    zt = torch.tensor(z, dtype=torch.float32, device="cuda", requires_grad=True)
+    psi = ic(zt)
+    assert psi.shape == (B, 1)
+    (psi[:, 0] * torch.tensor(gpsi, dtype=torch.float32, device="cuda")).sum().backward()
+    rdz, rg = io.icnn_brenier_backward(z64, np.zeros_like(z64), p64, 0, 0.0, f32_as_f64(gpsi))
+    _, _, aux = io.icnn_brenier(z64, p64, 0, 0.0, keep=True)
+    close_rows(zt.grad.cpu().numpy(), rdz, 1e-4, "dz of <gpsi, psi>", kink_rows(aux, H_RTOL[0], with_h0=True), loose=5e-2)
+    for k, t in zip(KEYS, ic._flat_params()):
+        close_report(t.grad.cpu().numpy(), rg[k], 1e-4, "grad " + k)
+    ic.zero_grad(set_to_none=True)
+    zt2 = torch.tensor(z, dtype=torch.float32, device="cuda", requires_grad=True)
+    psi2 = ic(zt2) + 0.1 * zt2.pow(2).sum(1, keepdim=True)
+    xh = torch.autograd.grad(psi2, [zt2], torch.ones_like(psi2), create_graph=True)[0]
+    (xh * torch.tensor(v, dtype=torch.float32, device="cuda")).sum().backward()
+    rdz2, rg2 = io.icnn_brenier_backward(z64, f32_as_f64(v), p64, 0, 0.1, None)
+    _, rx, _ = io.icnn_brenier(z64, p64, 0, 0.1)
+    close_rows(xh.detach().cpu().numpy(), rx, 1e-5, "xhat via autograd.grad", kink_rows(aux, H_RTOL[0]))
+    close_rows(zt2.grad.cpu().numpy(), rdz2, 1e-4, "dz (double backward)", kink_rows(aux, H_RTOL[0], with_h0=True), loose=5e-2)
+    for k, t in zip(KEYS, ic._flat_params()):
+        if np.abs(rg2[k]).max() == 0:
+            assert t.grad is None or float(t.grad.abs().max()) == 0.0, k
+        else:
+            close_report(t.grad.cpu().numpy(), rg2[k], 1e-4, "grad2 " + k)
 
 
 def test_wide_implicit_zero_pad_equals_explicit_pad():

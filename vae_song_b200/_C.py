@@ -31,7 +31,8 @@ EXPORTS = [
     "b200vae_peer_exchange_bytes", "b200vae_peer_num_slots", "b200vae_peer_max_payload", "b200vae_peer_alloc", "b200vae_peer_open",
     "b200vae_peer_close", "b200vae_peer_free", "b200vae_peer_timed_out", "b200vae_peer_allgather", "b200vae_mlp_layer_fwd_peer",
     "b200vae_mlp_layer_bwd_reduce_peer", "b200vae_peer_allreduce_adam",
-    "b200vae_icnn_wide_workspace_bytes", "b200vae_icnn_wide_fwd", "b200vae_icnn_wide_bwd", "b200vae_mi_logqz",
+    "b200vae_icnn_wide_workspace_bytes", "b200vae_icnn_wide_fwd", "b200vae_icnn_wide_bwd", "b200vae_icnn_wide_bwd_psi",
+    "b200vae_mi_logqz", "b200vae_nll_iw_lse", "b200vae_nll_iw_scratch_bytes",
 ]
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 64
 
@@ -125,8 +126,15 @@ def load():
     lib.b200vae_icnn_wide_bwd.restype = i
     lib.b200vae_icnn_wide_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, C.POINTER(IcnnParams), i, f, C.POINTER(IcnnGrads), vp,
                                           vp, vp, vp, vp, i, vp, sz, vp]
+    lib.b200vae_icnn_wide_bwd_psi.restype = i
+    lib.b200vae_icnn_wide_bwd_psi.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, C.POINTER(IcnnParams), i, C.POINTER(IcnnGrads), vp,
+                                              vp, vp, vp, vp, sz, vp]
     lib.b200vae_mi_logqz.restype = i
     lib.b200vae_mi_logqz.argtypes = [vp, vp, vp, i, i, vp, vp]
+    lib.b200vae_nll_iw_lse.restype = i
+    lib.b200vae_nll_iw_lse.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp]
+    lib.b200vae_nll_iw_scratch_bytes.restype = sz
+    lib.b200vae_nll_iw_scratch_bytes.argtypes = []
     pp = C.POINTER(PeerStruct)
     lib.b200vae_peer_exchange_bytes.restype = sz
     lib.b200vae_peer_exchange_bytes.argtypes = []

@@ -238,7 +238,10 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
     int i = 0;
     for (int u = cid; u < U; u += G, ++i) {
       const Unit un = decode_unit(u, T, NP);
-      for (int ck = 0; ck + 1 < NC; ++ck, ++i) {
+      // only GEMM1 (h1: its sign bits and psi inherit the accumulation bias) is chunked; GEMM2's accumulator enters xhat
+      // linearly and its one-piece error (2 MMAs per K step) stays below 2e-6
+      const int nck = un.g ? 1 : NC;
+      for (int ck = 0; ck + 1 < nck; ++ck, ++i) {
         const int pbuf = i & 1;
         mbar_wait_parked(accfull0 + 8 * pbuf, (i >> 1) & 1, a.park_ns);
         tc_fence_after();
@@ -284,7 +287,7 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
       auto load_acc = [&](uint32_t (&r)[32], int cc) {
         tmem_ld32(taddr + buf * 256 + cc * 32, r);
         tmem_ld_wait();
-        if (NC > 1) {
+        if (nck > 1) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 t = __ldcg(mysum + (size_t)(cc * 8 + q) * k3Rows);
@@ -601,9 +604,10 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
       const Unit un = decode_unit(u, T, NP);
       const int nreal = un.g ? NKB : NKB + 1, npad = (nreal + 1) & ~1;
       int kb = 0;
-      for (int ck = 0; ck < NC; ++ck, ++i) {                            // one accumulator per K-chunk
+      const int nck = un.g ? 1 : NC;                                    // GEMM1 units only (see the epilogue warps)
+      for (int ck = 0; ck < nck; ++ck, ++i) {                           // one accumulator per K-chunk
         const int buf = i & 1;
-        const int kb0 = kb, kb1 = (ck == NC - 1) ? npad : kb + kb_per_chunk;
+        const int kb0 = kb, kb1 = (ck == nck - 1) ? npad : kb + kb_per_chunk;
         mbar_wait(accempty0 + 8 * buf, ((i >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_t = tmem_base + (uint32_t)(buf * 256);

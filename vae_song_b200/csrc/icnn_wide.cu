@@ -258,6 +258,7 @@ wide_lin_kernel(const float* __restrict__ src, const float* __restrict__ WT, con
 // ---- hid: acc = xf(src1[B,H]) . P0T[H,H] + src2[B,d] . A1T[d,H] ------------------------------------------------------------------
 //   mode 0 (forward): h1 = acc + b1 -> mask1, part[row][nt] = sum_cols P1*sigma(h1)
 //   mode 1 (backward): colpart[mt][col] = sum_rows s2*s1*acc
+//   mode 2 (psi-gradient backward): colpart[mt][col] = sum_rows s2[row]*sigma(acc + b1)   (s2 = gpsi*s2: dP1 of dL/dpsi)
 __global__ void __launch_bounds__(kThreads, 2)
 wide_hid_kernel(const float* __restrict__ src1, int xf1, const float* __restrict__ P0T, const float* __restrict__ src2,
                 const float* __restrict__ A1T, const float* __restrict__ b1, const float* __restrict__ P1, int B, int d, int H,
@@ -314,7 +315,13 @@ wide_hid_kernel(const float* __restrict__ src1, int xf1, const float* __restrict
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int col = n0 + tc.col(j);
-        if (col < H) cs[j] = fmaf(sr * (mask1[(size_t)row * H + col] ? 1.f : kSlope), acc[i][j], cs[j]);
+        if (col >= H) continue;
+        if (mode == 1) {
+          cs[j] = fmaf(sr * (mask1[(size_t)row * H + col] ? 1.f : kSlope), acc[i][j], cs[j]);
+        } else {
+          const float h = acc[i][j] + b1[col];
+          cs[j] = fmaf(sr, h * slope_of(h), cs[j]);
+        }
       }
     }
 #pragma unroll
@@ -345,7 +352,8 @@ wide_row_kernel(const float* __restrict__ part, int nt, const float* __restrict_
   }
 }
 
-// ---- gx1: gx1 = g1 . P0 -> g0 = gx1*c0(h0); backward also t0 = u0*2*gx1*s0^2 and its column partials (db0) ------------------------
+// ---- gx1: gx1 = g1 . P0 -> g0 = gx1*c0(h0); backward also t0 = u0*2*gx1*s0^2 and its column partials (db0); with t0 == null
+//      and colpart != null the column partials are those of g0 itself (psi-gradient backward) --------------------------------------
 __global__ void __launch_bounds__(kThreads, 2)
 wide_gx1_kernel(const uint8_t* __restrict__ mask1, const float* __restrict__ s2, const float* __restrict__ P1,
                 const float* __restrict__ P0, const float* __restrict__ h0, const float* __restrict__ u0, int B, int H,
@@ -371,15 +379,18 @@ wide_gx1_kernel(const uint8_t* __restrict__ mask1, const float* __restrict__ s2,
       if (col >= H) continue;
       const size_t idx = (size_t)row * H + col;
       const float h = h0[idx], s = slope_of(h), gx = acc[i][j];
-      g0[idx] = gx * (2.f * h * s * s);
+      const float gv = gx * (2.f * h * s * s);
+      g0[idx] = gv;
       if (t0) {
         const float t = u0[idx] * (2.f * gx) * s * s;
         t0[idx] = t;
         cs[j] += t;
+      } else if (colpart) {
+        cs[j] += gv;                                        // psi-gradient backward: db0 = column sums of gpsi*g0
       }
     }
   }
-  if (t0) {
+  if (colpart) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float s = colsum16(cs[j]);
@@ -433,6 +444,7 @@ struct TnArgs {
   const float* a2; const float* b2; int N2;      // optional second product (identity A), b2 [B,N2], N2 <= N; may be null
   const uint8_t* mask1; const float* s2; const float* P1;
   int B, Mdim, N, rows_per_split;
+  int N1;                                        // columns (= row stride) of b1; 0 = N.  Output columns >= N1 get no first product
 };
 __global__ void __launch_bounds__(kThreads, 2)
 wide_tn_kernel(TnArgs p, float* __restrict__ slabs) {
@@ -446,7 +458,8 @@ wide_tn_kernel(TnArgs p, float* __restrict__ slabs) {
   {
     ACol a; a.src = p.a1; a.mask = p.mask1; a.P1 = p.P1; a.s2 = p.s2; a.ld = p.Mdim; a.Mdim = p.Mdim; a.kbeg = kbeg; a.kend = kend;
     a.m0 = m0; a.xf = p.xf1;
-    BMat b = make_bmat(p.b1, p.N, kbeg, kend, p.N, n0);
+    const int n1 = p.N1 > 0 ? p.N1 : p.N;
+    BMat b = make_bmat(p.b1, n1, kbeg, kend, n1, n0);
     gemm_tile_acc(acc, sm, KT, a, b, tc);
   }
   if (p.a2) {
@@ -502,6 +515,55 @@ __global__ void wide_col_finalize_kernel(const float* __restrict__ colpart, int 
 __global__ void wide_zero_kernel(float* __restrict__ p, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0.f;
+}
+
+// ---- psi-gradient backward helpers --------------------------------------------------------------------------------------------
+// s2g[b] = gpsi[b]*s2[b];  x1[b][n] = sigma(h0[b][n])^2 (B operand of dP0 = (gpsi g1)^T x1)
+__global__ void wide_psi_pre_kernel(const float* __restrict__ gpsi, const float* __restrict__ s2, const float* __restrict__ h0,
+                                    int B, size_t n, float* __restrict__ s2g, float* __restrict__ x1) {
+  const size_t gstride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
+    if (i < (size_t)B) s2g[i] = gpsi[i] * s2[i];
+    const float h = h0[i], a = h * slope_of(h);
+    x1[i] = a * a;
+  }
+}
+// colpart[mt][c] = sum over the 128-row block of sc[b] * sigma'(h1[b][c])   (db1 / P1[c] of dL/dpsi)
+__global__ void __launch_bounds__(256)
+wide_maskcol_kernel(const uint8_t* __restrict__ mask1, const float* __restrict__ sc, int B, int H, float* __restrict__ colpart) {
+  const int m0 = blockIdx.x * 128, m1 = min(B, m0 + 128);
+  for (int c = blockIdx.y * 256 + threadIdx.x; c < H; c += gridDim.y * 256) {
+    float s = 0.f;
+    for (int b = m0; b < m1; ++b) s = fmaf(sc[b], mask1[(size_t)b * H + c] ? 1.f : kSlope, s);
+    colpart[(size_t)blockIdx.x * H + c] = s;
+  }
+}
+// out[0] = sum_b x[b], fixed order (one block)
+__global__ void __launch_bounds__(256)
+wide_sum_kernel(const float* __restrict__ x, int B, float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) s += x[b];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[0] = t;
+  }
+}
+// out[r][c] (row stride ld) = sum_s slabs[s][r][c] for c < cols, 0 for cols <= c < ld
+__global__ void wide_slab_finalize_ld_kernel(const float* __restrict__ slabs, int splits, int rows, int cols, int ld,
+                                             float* __restrict__ out) {
+  const size_t n = (size_t)rows * ld, gstride = (size_t)gridDim.x * blockDim.x, slab = (size_t)rows * cols;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
+    const size_t r = i / ld, c = i - r * ld;
+    float s = 0.f;
+    if (c < (size_t)cols)
+      for (int k = 0; k < splits; ++k) s += slabs[(size_t)k * slab + r * cols + c];
+    out[i] = s;
+  }
 }
 
 static int wide_prepare(const b200vae_icnn_params* p, int d, int H, int mode, float* ws, const WideWs& L, cudaStream_t st) {
@@ -658,6 +720,7 @@ extern "C" int b200vae_icnn_wide_bwd(const float* z, const float* v, const float
     }
     if (tn_done) return B200VAE_OK;
     TnArgs t;
+    t.N1 = 0;
     t.mask1 = mask1; t.s2 = s2; t.P1 = ws + L.P1; t.B = B; t.Mdim = H;
     const int splits = L.splits;
     t.rows_per_split = round_up((B + splits - 1) / splits, kBK);
@@ -683,6 +746,95 @@ extern "C" int b200vae_icnn_wide_bwd(const float* z, const float* v, const float
       wide_slab_finalize_kernel<<<fin_blocks, 256, 0, st>>>(ws + L.slabs, splits, (size_t)H * H, chain, ws + L.P0, p->W0, g->W0);
       WIDE_CHECK();
     }
+  }
+  return B200VAE_OK;
+}
+
+// First-order backward of psi for wide inputs (last line): gradients of L = sum_b gpsi[b]*psi[b].  With
+// delta2 = gpsi*s2, delta1 = delta2*P1*sigma'(h1) (= gpsi*g1), delta0 = (delta1 P0)*2a0s0 (= gpsi*g0):
+//   dA2 = delta2^T z, db2 = sum delta2, dP1 = delta2^T sigma(h1), dA1 = delta1^T z, db1 = sum delta1, dP0 = delta1^T x1,
+//   dA0 = delta0^T z, db0 = sum delta0, dz = delta0 A0 + delta1 A1 + delta2 A2.
+// Every product reuses the FP32 tile kernels above with s2 replaced by s2g = gpsi*s2 (g1 and g0 scale with it).
+extern "C" int b200vae_icnn_wide_bwd_psi(const float* z, const float* gpsi, const float* h0, const uint8_t* mask1,
+                                         const float* s2, int B, int d, int nz, int H, const b200vae_icnn_params* p,
+                                         int weight_mode, const b200vae_icnn_grads* g, float* dz, float* x1, float* g0,
+                                         float* s2g, void* workspace, size_t ws_bytes, void* stream) {
+  if (!z || !gpsi || !h0 || !mask1 || !s2 || !wide_params_ok(p) || !x1 || !g0 || !s2g || !workspace) return B200VAE_EALIGN;
+  if (B <= 0 || d <= 0 || H <= 0 || nz <= 0 || nz > d) return B200VAE_ESHAPE;
+  if (weight_mode != B200VAE_WEIGHT_EXP && weight_mode != B200VAE_WEIGHT_CLAMP) return B200VAE_EUNSUP;
+  const WideWs L = wide_layout(B, d, H, true);
+  if (ws_bytes < b200vae_icnn_wide_workspace_bytes(B, d, H, B200VAE_PREC_FP32, 1)) return B200VAE_EWS;
+  if (!aligned16(workspace) || !aligned16(z) || !aligned16(h0) || !aligned16(x1) || !aligned16(g0) || !aligned4(p->A0w) ||
+      !aligned4(p->A1w) || (dz && !aligned16(dz)))
+    return B200VAE_EALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = (float*)workspace;
+  const int chain = weight_mode == B200VAE_WEIGHT_EXP ? 1 : 2;
+  int rc = wide_prepare(p, d, H, weight_mode, ws, L, st);
+  if (rc) return rc;
+  const dim3 gH(L.mt, L.nt);
+  wide_psi_pre_kernel<<<148 * 4, 256, 0, st>>>(gpsi, s2, h0, B, (size_t)B * H, s2g, x1);
+  WIDE_CHECK();
+  // dP1 = delta2^T sigma(h1): h1 recomputed (x1 P0^T + z A1^T + b1), weighted column sums in the epilogue
+  if (g && g->W1) {
+    wide_hid_kernel<<<gH, kThreads, 0, st>>>(h0, XF_X1, ws + L.P0T, z, ws + L.A1T, p->A1b, ws + L.P1, B, nz, H, 2, nullptr, s2g,
+                                            nullptr, ws + L.colpart);
+    WIDE_CHECK();
+    wide_col_finalize_kernel<<<(H + 255) / 256, 256, 0, st>>>(ws + L.colpart, L.mt, H, chain, ws + L.P1, p->W1, g->W1);
+    WIDE_CHECK();
+  }
+  // delta0 = (delta1 P0) * 2 a0 s0 -> g0 buffer, column sums = db0
+  wide_gx1_kernel<<<gH, kThreads, 0, st>>>(mask1, s2g, ws + L.P1, ws + L.P0, h0, nullptr, B, H, g0, nullptr, ws + L.colpart);
+  WIDE_CHECK();
+  if (g && g->A0b) {
+    wide_col_finalize_kernel<<<(H + 255) / 256, 256, 0, st>>>(ws + L.colpart, L.mt, H, 0, nullptr, nullptr, g->A0b);
+    WIDE_CHECK();
+  }
+  if (dz) {
+    wide_out_kernel<<<dim3(L.mt, (nz + 127) / 128), kThreads, 0, st>>>(g0, p->A0w, 1, mask1, s2g, ws + L.P1, p->A1w, p->A2w, nullptr,
+                                                                      0, 0, 0.f, B, d, nz, H, dz);
+    WIDE_CHECK();
+  }
+  if (!g) return B200VAE_OK;
+  if (g->A1b) {       // db1[c] = P1[c] * sum_b delta2[b] sigma'(h1[b][c])
+    wide_maskcol_kernel<<<dim3(L.mt, (H + 255) / 256), 256, 0, st>>>(mask1, s2g, B, H, ws + L.colpart);
+    WIDE_CHECK();
+    wide_col_finalize_kernel<<<(H + 255) / 256, 256, 0, st>>>(ws + L.colpart, L.mt, H, 1, ws + L.P1, nullptr, g->A1b);
+    WIDE_CHECK();
+  }
+  if (g->A2w) {       // dA2[c] = sum_b delta2[b] z[b][c] for c < nz, 0 beyond (the padded inputs are zero)
+    wide_a2_kernel<<<L.mt, 256, 0, st>>>(z, s2g, B, nz, ws + L.colpart);
+    WIDE_CHECK();
+    wide_col_finalize_kernel<<<(nz + 255) / 256, 256, 0, st>>>(ws + L.colpart, L.mt, nz, 0, nullptr, nullptr, g->A2w);
+    WIDE_CHECK();
+    if (d > nz) { wide_zero_kernel<<<(d - nz + 255) / 256, 256, 0, st>>>(g->A2w + nz, d - nz); WIDE_CHECK(); }
+  }
+  if (g->A2b) { wide_sum_kernel<<<1, 256, 0, st>>>(s2g, B, g->A2b); WIDE_CHECK(); }
+  TnArgs t;
+  t.mask1 = mask1; t.s2 = s2g; t.P1 = ws + L.P1; t.B = B; t.Mdim = H; t.a2 = nullptr; t.b2 = nullptr; t.N2 = 0;
+  const int splits = L.splits;
+  t.rows_per_split = round_up((B + splits - 1) / splits, kBK);
+  const int fin_blocks = 148 * 4;
+  if (g->A0w) {       // dA0 = delta0^T z   ([H, nz] block of [H, d])
+    t.a1 = g0; t.xf1 = XF_ID; t.b1 = z; t.N = nz; t.N1 = nz;
+    wide_tn_kernel<<<dim3(L.nt, (nz + 127) / 128, splits), kThreads, 0, st>>>(t, ws + L.slabs);
+    WIDE_CHECK();
+    wide_slab_finalize_ld_kernel<<<fin_blocks, 256, 0, st>>>(ws + L.slabs, splits, H, nz, d, g->A0w);
+    WIDE_CHECK();
+  }
+  if (g->A1w) {       // dA1 = delta1^T z
+    t.a1 = nullptr; t.xf1 = XF_G1; t.b1 = z; t.N = nz; t.N1 = nz;
+    wide_tn_kernel<<<dim3(L.nt, (nz + 127) / 128, splits), kThreads, 0, st>>>(t, ws + L.slabs);
+    WIDE_CHECK();
+    wide_slab_finalize_ld_kernel<<<fin_blocks, 256, 0, st>>>(ws + L.slabs, splits, H, nz, d, g->A1w);
+    WIDE_CHECK();
+  }
+  if (g->W0) {        // dP0 = delta1^T x1 -> dW0
+    t.a1 = nullptr; t.xf1 = XF_G1; t.b1 = x1; t.N = H; t.N1 = H;
+    wide_tn_kernel<<<dim3(L.nt, L.nt, splits), kThreads, 0, st>>>(t, ws + L.slabs);
+    WIDE_CHECK();
+    wide_slab_finalize_kernel<<<fin_blocks, 256, 0, st>>>(ws + L.slabs, splits, (size_t)H * H, chain, ws + L.P0, p->W0, g->W0);
+    WIDE_CHECK();
   }
   return B200VAE_OK;
 }

@@ -52,17 +52,17 @@ struct ApAcc {
 };
 
 // ratio = clamp(|dy|, eps) / clamp(|dx|, eps) = sqrt(max(sy, eps^2) / max(sx, eps^2)) with ONE MUFU op per pair:
-// r = a * rsqrt(a * b), a = max(sy, eps^2), b = max(sx, eps^2) (utils.py:560-562 semantics, ~2 ulp).  `ok` is cleared when
-// a*b leaves the range in which that is accurate; the caller then redoes its pairs with ap_ratio_safe.
-__device__ __forceinline__ float ap_ratio(float sx, float sy, float eps2, bool& ok) {
+// r = a * rsqrt(a * b), a = max(sy, eps^2), b = max(sx, eps^2) (utils.py:560-562 semantics, ~2 ulp).  The product a*b can leave
+// the fp32 range (then r is 0, inf or NaN -- a true ratio is a positive finite number): callers check the min / max of a
+// group of pairs once and redo the group with ap_ratio_safe (rare).
+__device__ __forceinline__ float ap_ratio(float sx, float sy, float eps2) {
   const float a = fmaxf(sy, eps2), b = fmaxf(sx, eps2);
-  const float ab = a * b;
-  ok = ok && (ab > 1e-30f) && (ab < 1e38f);
-  return a * rsqrtf(ab);
+  return a * rsqrtf(a * b);
 }
 __device__ __noinline__ float ap_ratio_safe(float sx, float sy, float eps2) {
   return sqrtf(fmaxf(sy, eps2)) / sqrtf(fmaxf(sx, eps2));
 }
+__device__ __forceinline__ bool ap_valid(float rmin, float rmax) { return rmin > 0.f && rmax < 3.0e38f; }   // false for NaN too
 __device__ __forceinline__ void ap_take(ApAcc& acc, float r) {
   acc.vmax = fmaxf(acc.vmax, r);
   acc.vmin = fminf(acc.vmin, r);
@@ -121,9 +121,12 @@ __device__ __forceinline__ void ap_hist_add(uint32_t* hs, float r, int nbins, fl
 }
 
 // ---- small feature widths (DX, DY <= 4): everything in registers, operands straight from global memory (L1 / L2
-// resident: N*(DX+DY)*4 bytes), thread (ta, tb) owns points i0 + 4 ta + ii and j0 + 4 tb + jj (contiguous -> wide loads).
+// resident: N*(DX+DY)*4 bytes).  A CTA owns a CONTIGUOUS range of tile indices, i.e. it walks along a tile row: the 4 i-points
+// of a thread (i0 + 4 ta + ii) stay in registers while only its 4 j-points (j0 + 4 tb + jj, contiguous -> wide loads) are
+// reloaded per tile, and the tile coordinates advance incrementally.  Interior tiles (every pair valid) take the fast path:
+// 16 ratios, one min / max / sum merge; diagonal and edge tiles (and histogram launches) the masked, exact-division path.
 template <int DX, int DY, bool HIST>
-__global__ void __launch_bounds__(kApThreads)
+__global__ void __launch_bounds__(kApThreads, 4)
 lipschitz_allpairs_small_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, float eps,
                                 long long tile_begin, long long tile_end, float* __restrict__ scratch,
                                 double* __restrict__ stats, uint32_t* __restrict__ hist, int nbins, float hist_lo,
@@ -139,8 +142,8 @@ lipschitz_allpairs_small_kernel(const float* __restrict__ X, const float* __rest
     else hdst = hist;
   }
   ApAcc acc = {0.f, 3.4e38f, 0.f, 0u};
-  // 4 consecutive points: vector loads when all four exist (g0 is a multiple of 4, so 4*DX floats are 16-byte aligned if
-  // the base pointer is), else clamped scalar loads (out-of-range points are masked below)
+  // 4 consecutive points: vector loads when all four exist (g0 is a multiple of 4, so 4*DIM floats are 16-byte aligned if
+  // the base pointer is), else clamped scalar loads (out-of-range points are masked by the slow path)
   auto load4 = [&](const float* __restrict__ F, int g0, auto& f) {
     constexpr int DIM = sizeof(f[0]) / sizeof(float);
     if (vec_ok && g0 + 3 < N) {
@@ -164,52 +167,63 @@ lipschitz_allpairs_small_kernel(const float* __restrict__ X, const float* __rest
       }
     }
   };
-  for (long long t = tile_begin + blockIdx.x; t < tile_end; t += gridDim.x) {
-    int ti, tj;
-    tile_coords(t, T, ti, tj);
+  const long long nt = tile_end - tile_begin;
+  const long long per = (nt + gridDim.x - 1) / gridDim.x;
+  const long long t0 = tile_begin + (long long)blockIdx.x * per;
+  const long long t1 = t0 + per < tile_end ? t0 + per : tile_end;
+  int ti = 0, tj = 0;
+  float xi[4][DX], yi[4][DY];
+  if (t0 < t1) {
+    tile_coords(t0, T, ti, tj);
+    load4(X, ti * kTile + 4 * ta, xi); load4(Y, ti * kTile + 4 * ta, yi);
+  }
+  for (long long t = t0; t < t1; ++t) {
     const int i0 = ti * kTile + 4 * ta, j0 = tj * kTile + 4 * tb;
-    float xi[4][DX], yi[4][DY], xj[4][DX], yj[4][DY];
-    load4(X, i0, xi); load4(Y, i0, yi); load4(X, j0, xj); load4(Y, j0, yj);
+    float xj[4][DX], yj[4][DY];
+    load4(X, j0, xj); load4(Y, j0, yj);
+    auto sq = [&](int ii, int jj, float& ax, float& ay) {
+      ax = 0.f; ay = 0.f;
+#pragma unroll
+      for (int q = 0; q < DX; ++q) { const float d = xi[ii][q] - xj[jj][q]; ax = fmaf(d, d, ax); }
+#pragma unroll
+      for (int q = 0; q < DY; ++q) { const float d = yi[ii][q] - yj[jj][q]; ay = fmaf(d, d, ay); }
+    };
     const bool full = (ti != tj) && (tj * kTile + kTile <= N);  // every pair valid (i < j, both in range)
-    float sx[4][4], sy[4][4], r[4][4];
-    bool ok = true;
-#pragma unroll
-    for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        float ax = 0.f, ay = 0.f;
-#pragma unroll
-        for (int q = 0; q < DX; ++q) { const float d = xi[ii][q] - xj[jj][q]; ax = fmaf(d, d, ax); }
-#pragma unroll
-        for (int q = 0; q < DY; ++q) { const float d = yi[ii][q] - yj[jj][q]; ay = fmaf(d, d, ay); }
-        sx[ii][jj] = ax; sy[ii][jj] = ay;
-        r[ii][jj] = ap_ratio(ax, ay, eps2, ok);
-      }
-    if (!ok) {                                                  // (rare) a*b outside the fast formula's range
-#pragma unroll
-      for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) r[ii][jj] = ap_ratio_safe(sx[ii][jj], sy[ii][jj], eps2);
-    }
-    if (full) {
+    bool done = false;
+    if (full && !HIST) {
+      float rlo = 3.4e38f, rhi = 0.f, rs = 0.f;
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          ap_take(acc, r[ii][jj]);
-          if (HIST) ap_hist_add(hdst, r[ii][jj], nbins, hist_lo, hscale);
+          float ax, ay;
+          sq(ii, jj, ax, ay);
+          const float r = ap_ratio(ax, ay, eps2);
+          rlo = fminf(rlo, r); rhi = fmaxf(rhi, r); rs += r;
         }
-      acc.cnt += 16u;
-    } else {
+      if (ap_valid(rlo, rhi)) {
+        acc.vmin = fminf(acc.vmin, rlo); acc.vmax = fmaxf(acc.vmax, rhi); acc.sum += rs; acc.cnt += 16u;
+        done = true;
+      }
+    }
+    if (!done) {                                                // diagonal / edge tile, histogram, or a*b out of range
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj)
           if (i0 + ii < j0 + jj && j0 + jj < N) {
-            ap_take(acc, r[ii][jj]);
+            float ax, ay;
+            sq(ii, jj, ax, ay);
+            float r = ap_ratio(ax, ay, eps2);
+            if (!ap_valid(r, r)) r = ap_ratio_safe(ax, ay, eps2);
+            ap_take(acc, r);
             ++acc.cnt;
-            if (HIST) ap_hist_add(hdst, r[ii][jj], nbins, hist_lo, hscale);
+            if (HIST) ap_hist_add(hdst, r, nbins, hist_lo, hscale);
           }
+    }
+    if (++tj == T) {                                            // next tile row: its first tile is the diagonal one
+      ++ti; tj = ti;
+      if (t + 1 < t1) { load4(X, ti * kTile + 4 * ta, xi); load4(Y, ti * kTile + 4 * ta, yi); }
     }
   }
   if (HIST && nbins <= kApMaxSmemBins) {
@@ -279,9 +293,8 @@ lipschitz_allpairs_wide_kernel(const float* __restrict__ X, const float* __restr
       for (int jj = 0; jj < 4; ++jj) {
         const int gi = i0 + ta + 16 * ii, gj = j0 + tb + 16 * jj;
         if (gi < gj && gj < N) {
-          bool ok = true;
-          float r = ap_ratio(s[0][ii][jj], s[1][ii][jj], eps2, ok);
-          if (!ok) r = ap_ratio_safe(s[0][ii][jj], s[1][ii][jj], eps2);
+          float r = ap_ratio(s[0][ii][jj], s[1][ii][jj], eps2);
+          if (!ap_valid(r, r)) r = ap_ratio_safe(s[0][ii][jj], s[1][ii][jj], eps2);
           ap_take(acc, r);
           ++acc.cnt;
           if (hist) ap_hist_add(hist, r, nbins, hist_lo, hscale);
@@ -339,8 +352,10 @@ extern "C" int b200vae_lipschitz_allpairs(const float* X, const float* Y, int N,
   if (hist && cudaMemsetAsync(hist, 0, (size_t)nbins * sizeof(uint32_t), st) != cudaSuccess) return B200VAE_ECUDA;
   const long long nt = tile_end - tile_begin;
   // one launch, even for an empty tile range (the kernel then only writes the neutral statistics)
+  // one wave of resident CTAs (4 per SM: __launch_bounds__(256, 4)); a CTA walks a contiguous range of tiles, so at
+  // least ~2 tiles per CTA keep the per-CTA prologue / epilogue amortised
   const int per_sm = 4;
-  long long want = nt < 1 ? 1 : nt;
+  long long want = nt < 1 ? 1 : (nt + 1) / 2;
   const long long cap = (long long)sm_count() * per_sm;
   const int blocks = (int)(want < cap ? want : (cap < kApMaxBlocks ? cap : kApMaxBlocks));
   float* scr = reinterpret_cast<float*>(scratch);

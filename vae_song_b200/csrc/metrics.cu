@@ -52,9 +52,75 @@ mi_logqz_kernel(const float* __restrict__ z, const float* __restrict__ mu, const
   if (lane == 0 && i < B) logqz[i] = m + logf(ssum) - logf((float)B);
 }
 
+// nll_iw (utils.py:109-120): ll_iw = logsumexp over ALL (b, s) of [log p(z) - loss_rec - log q(z|x)] - log S with
+// z = mu + eps*exp(lv/2).  The 2 pi terms cancel and (z-mu)^2/var = eps^2, so the summand is
+//   w[b,s] = sum_k ( -0.5 z_k^2 + 0.5 eps_k^2 + 0.5 lv_k )  (- loss_rec, a constant shift applied on the host side).
+// One pass over eps [B,S,nz] with an online (max, sum) per thread, warp / block merges, ordered per-CTA partials and a
+// last-block merge: the [B,S,nz] z tensor and the three [B,S] log-density tensors of the reference are never formed.
+constexpr int kIwMaxBlocks = 1024;
+__device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
+  const float mm = fmaxf(m, m2);
+  s = (s > 0.f ? s * __expf(m - mm) : 0.f) + (s2 > 0.f ? s2 * __expf(m2 - mm) : 0.f);
+  m = mm;
+}
+__global__ void __launch_bounds__(256)
+nll_iw_lse_kernel(const float* __restrict__ mu, const float* __restrict__ lv, const float* __restrict__ eps, int B, int S, int nz,
+                  float* __restrict__ out, float* __restrict__ scratch) {
+  __shared__ float redm[8], reds[8];
+  __shared__ int last;
+  const long long n = (long long)B * S;
+  float m = -3.4e38f, ssum = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / S);
+    const float* e = eps + (size_t)i * nz;
+    float w = 0.f;
+    for (int k = 0; k < nz; ++k) {
+      const float l = __ldg(lv + (size_t)b * nz + k), ek = e[k];
+      const float zk = fmaf(ek, __expf(0.5f * l), __ldg(mu + (size_t)b * nz + k));
+      w += 0.5f * (ek * ek - zk * zk + l);
+    }
+    if (w > m) { ssum = ssum * __expf(m - w) + 1.f; m = w; }
+    else ssum += __expf(w - m);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+    lse_merge(m, ssum, __shfl_xor_sync(0xffffffffu, m, off), __shfl_xor_sync(0xffffffffu, ssum, off));
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  if (lane == 0) { redm[wp] = m; reds[wp] = ssum; }
+  __syncthreads();
+  unsigned* ticket = reinterpret_cast<unsigned*>(scratch + 2 * kIwMaxBlocks);
+  if (threadIdx.x == 0) {
+    float bm = redm[0], bs = reds[0];
+    for (int w = 1; w < 8; ++w) lse_merge(bm, bs, redm[w], reds[w]);
+    scratch[2 * blockIdx.x] = bm; scratch[2 * blockIdx.x + 1] = bs;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) + 1u == gridDim.x) ? 1 : 0;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float bm = -3.4e38f, bs = 0.f;
+    for (int q = 0; q < (int)gridDim.x; ++q) lse_merge(bm, bs, __ldcg(scratch + 2 * q), __ldcg(scratch + 2 * q + 1));   // fixed order
+    out[0] = bm + logf(bs);
+    *ticket = 0u;
+  }
+}
+
 }  // namespace b200vae
 
 using namespace b200vae;
+
+extern "C" size_t b200vae_nll_iw_scratch_bytes(void) { return (size_t)(2 * kIwMaxBlocks + 4) * sizeof(float); }
+extern "C" int b200vae_nll_iw_lse(const float* mu, const float* lv, const float* eps, int B, int S, int nz, float* out,
+                                  void* scratch, void* stream) {
+  if (!mu || !lv || !eps || !out || !scratch) return B200VAE_EALIGN;
+  if (B <= 0 || S <= 0 || nz <= 0) return B200VAE_ESHAPE;
+  const long long n = (long long)B * S;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  nll_iw_lse_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(mu, lv, eps, B, S, nz, out, (float*)scratch);
+  return check_launch();
+}
 
 extern "C" int b200vae_mi_logqz(const float* z, const float* mu, const float* lv, int B, int nz, float* logqz, void* stream) {
   if (!z || !mu || !lv || !logqz) return B200VAE_EALIGN;

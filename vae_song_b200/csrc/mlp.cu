@@ -84,11 +84,40 @@ struct BGenW {
   }
 };
 
+// ----------------------------------------------------------------------------------------- fused finalize ("last block")
+// Single-GPU layers fold the finalize step into the producing kernel: every CTA publishes its ordered partials, takes a
+// ticket, and the CTA that draws the last ticket combines ALL partials -- in the same fixed order as the stand-alone
+// finalize kernels, so the results stay bit-reproducible -- instead of a second launch per layer (the encoder of BASELINE
+// configs[1] went from 42 to 25 launches per step, the 8-layer encoder of configs[2] from 56 to 33).  The ticket lives at
+// the end of the caller's scratch (b200vae_mlp_scratch_bytes): zero before the first call, reset by the last block.  The
+// cross-rank (peer) layers keep their own finalize kernel: it is the one that talks to the other GPUs.
+__device__ __forceinline__ bool last_block_arrives(unsigned* ticket) {
+  __shared__ int s_last;
+  __threadfence();                               // this thread's partials are visible device-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    s_last = (t + 1u == gridDim.x) ? 1 : 0;
+    if (s_last) *ticket = 0u;                    // everyone has drawn: ready for the next launch
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+struct StatsFin {      // stats == nullptr: no fused finalize (a finalize kernel follows)
+  float* stats; float* running_mean; float* running_var; float eps, momentum; unsigned* ticket;
+};
+struct SumsFin { float* sums; unsigned* ticket; };
+struct DwFin { float* dW; unsigned* ticket; };
+
 // ----------------------------------------------------------------------------------------- forward
 // part: [nCTA][128][3] = (count, mean, M2) of this CTA's rows per output column
+__device__ __forceinline__ void chan_merge(float& cnt, float& mean, float& m2, float nb, float mb, float m2b);
+__device__ __forceinline__ void stats_finalize_block(const float* __restrict__ part, int ncta, int w, const StatsFin& f);
+
 __global__ void __launch_bounds__(kThreads, 2)
 mlp_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ bias, int B, int wo,
-               float* __restrict__ y_out, float* __restrict__ part, int do_stats) {
+               float* __restrict__ y_out, float* __restrict__ part, int do_stats, StatsFin fin) {
   __shared__ GemmSmem gs;
   __shared__ ActSmem am;
   const TileCoord tc;
@@ -128,6 +157,7 @@ mlp_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict_
       }
     }
   }
+  if (do_stats && fin.stats && last_block_arrives(fin.ticket)) stats_finalize_block(part, (int)gridDim.x, wo, fin);
 }
 
 // Chan et al. combination of the per-CTA (count, mean, M2): one WARP per column, lanes stride over the CTAs (independent
@@ -141,15 +171,15 @@ __device__ __forceinline__ void chan_merge(float& cnt, float& mean, float& m2, f
   }
   cnt = tot;
 }
-__global__ void __launch_bounds__(256)
-mlp_stats_finalize_kernel(const float* __restrict__ part, int ncta, int w, float eps, float* __restrict__ stats,
-                          float* __restrict__ running_mean, float* __restrict__ running_var, float momentum) {
-  const int lane = threadIdx.x & 31, n = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (n >= w) return;
+// column n by one warp: lanes stride over the CTAs' partials (L2 loads), fixed-order shuffle tree
+__device__ __forceinline__ void stats_finalize_column(const float* __restrict__ part, int ncta, int w, int n, float eps,
+                                                      float* __restrict__ stats, float* __restrict__ running_mean,
+                                                      float* __restrict__ running_var, float momentum) {
+  const int lane = threadIdx.x & 31;
   float cnt = 0.f, mean = 0.f, m2 = 0.f;
   for (int c = lane; c < ncta; c += 32) {
     const float* p = part + ((size_t)c * 128 + n) * 3;
-    chan_merge(cnt, mean, m2, p[0], p[1], p[2]);
+    chan_merge(cnt, mean, m2, __ldcg(p), __ldcg(p + 1), __ldcg(p + 2));
   }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -165,6 +195,34 @@ mlp_stats_finalize_kernel(const float* __restrict__ part, int ncta, int w, float
       running_var[n] = (1.f - momentum) * running_var[n] + momentum * (m2 / fmaxf(cnt - 1.f, 1.f));
     }
   }
+}
+__global__ void __launch_bounds__(256)
+mlp_stats_finalize_kernel(const float* __restrict__ part, int ncta, int w, float eps, float* __restrict__ stats,
+                          float* __restrict__ running_mean, float* __restrict__ running_var, float momentum) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= w) return;
+  stats_finalize_column(part, ncta, w, n, eps, stats, running_mean, running_var, momentum);
+}
+// the same, executed by the last CTA of the producing kernel (all its warps, columns round-robin)
+__device__ __forceinline__ void stats_finalize_block(const float* __restrict__ part, int ncta, int w, const StatsFin& f) {
+  if (ncta <= 64) {            // few partials (small batches): a THREAD per column, partials merged in CTA order
+    for (int n = threadIdx.x; n < w; n += (int)blockDim.x) {
+      float cnt = 0.f, mean = 0.f, m2 = 0.f;
+      for (int c = 0; c < ncta; ++c) {
+        const float* p = part + ((size_t)c * 128 + n) * 3;
+        chan_merge(cnt, mean, m2, __ldcg(p), __ldcg(p + 1), __ldcg(p + 2));
+      }
+      const float var = m2 / cnt;
+      f.stats[n] = mean; f.stats[w + n] = var; f.stats[2 * w + n] = rsqrtf(var + f.eps); f.stats[3 * w + n] = cnt;
+      if (f.running_mean) {
+        f.running_mean[n] = (1.f - f.momentum) * f.running_mean[n] + f.momentum * mean;
+        f.running_var[n] = (1.f - f.momentum) * f.running_var[n] + f.momentum * (m2 / fmaxf(cnt - 1.f, 1.f));
+      }
+    }
+    return;
+  }
+  for (int n = threadIdx.x >> 5; n < w; n += (int)(blockDim.x >> 5))
+    stats_finalize_column(part, ncta, w, n, f.eps, f.stats, f.running_mean, f.running_var, f.momentum);
 }
 
 // Cross-rank variant: ONE CTA of 32 warps.  Local (count, mean, M2) per column -> peer exchange -> Chan merge of the
@@ -208,11 +266,21 @@ mlp_stats_finalize_peer_kernel(const float* __restrict__ part, int ncta, int w, 
   }
 }
 
+// column n of the (S1, S2) sums by one warp (lanes stride over the blocks' partials, fixed shuffle tree)
+__device__ __forceinline__ void sums_finalize_column(const float* __restrict__ part, int nblk, int w, int n,
+                                                     float* __restrict__ sums /*[2][w]*/) {
+  const int lane = threadIdx.x & 31;
+  float a = 0.f, b = 0.f;
+  for (int c = lane; c < nblk; c += 32) { a += __ldcg(part + ((size_t)c * 128 + n) * 2); b += __ldcg(part + ((size_t)c * 128 + n) * 2 + 1); }
+  a = warp_sum(a); b = warp_sum(b);
+  if (lane == 0) { sums[n] = a; sums[w + n] = b; }
+}
+
 // ----------------------------------------------------------------------------------------- backward (1): reduce
 // dyhat = da * lrelu'(gamma*xhat+beta) ; S1 = sum dyhat ; S2 = sum dyhat*xhat.  w must divide 256 (power of two <= 128).
 __global__ void __launch_bounds__(256)
 mlp_bwd_reduce_kernel(const float* __restrict__ da, ActSrc cur, int has_bn, long long n_elem, long long per_block,
-                      float* __restrict__ dyhat, float* __restrict__ part /*[nblk][128][2]*/) {
+                      float* __restrict__ dyhat, float* __restrict__ part /*[nblk][128][2]*/, SumsFin fin) {
   __shared__ ActSmem am;
   __shared__ float red[256][2];
   am.load(cur);
@@ -239,15 +307,27 @@ mlp_bwd_reduce_kernel(const float* __restrict__ da, ActSrc cur, int has_bn, long
     part[((size_t)blockIdx.x * 128 + threadIdx.x) * 2 + 0] = a;
     part[((size_t)blockIdx.x * 128 + threadIdx.x) * 2 + 1] = b;
   }
+  if (fin.sums && last_block_arrives(fin.ticket)) {
+    const int nblk = (int)gridDim.x;
+    if (nblk <= 64) {          // few partials: a thread per column, block order
+      if (threadIdx.x < w) {
+        float a = 0.f, b = 0.f;
+        for (int c = 0; c < nblk; ++c) {
+          a += __ldcg(part + ((size_t)c * 128 + threadIdx.x) * 2);
+          b += __ldcg(part + ((size_t)c * 128 + threadIdx.x) * 2 + 1);
+        }
+        fin.sums[threadIdx.x] = a; fin.sums[w + threadIdx.x] = b;
+      }
+    } else {
+      for (int n = threadIdx.x >> 5; n < w; n += 8) sums_finalize_column(part, nblk, w, n, fin.sums);
+    }
+  }
 }
 __global__ void __launch_bounds__(256)
 mlp_sum_finalize_kernel(const float* __restrict__ part, int nblk, int w, float* __restrict__ sums /*[2][w]*/) {
-  const int lane = threadIdx.x & 31, n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (n >= w) return;
-  float a = 0.f, b = 0.f;
-  for (int c = lane; c < nblk; c += 32) { a += part[((size_t)c * 128 + n) * 2]; b += part[((size_t)c * 128 + n) * 2 + 1]; }
-  a = warp_sum(a); b = warp_sum(b);
-  if (lane == 0) { sums[n] = a; sums[w + n] = b; }
+  sums_finalize_column(part, nblk, w, n, sums);
 }
 
 // Cross-rank variant: local sums (parameter gradients of gamma/beta) and the rank-ordered global sums (for dy).
@@ -381,8 +461,9 @@ struct BGenActT {  // Bs[kk = sample][n = i]
     }
   }
 };
+__device__ __forceinline__ void dw_finalize_block(const float* __restrict__ part, int nsplit, int n, float* __restrict__ dW);
 __global__ void __launch_bounds__(kThreads, 2)
-mlp_bwd_dw_kernel(DyCtx c, ActSrc prev, int B, int rows_per_split, float* __restrict__ part /*[nsplit][wo][wi]*/) {
+mlp_bwd_dw_kernel(DyCtx c, ActSrc prev, int B, int rows_per_split, float* __restrict__ part /*[nsplit][wo][wi]*/, DwFin fin) {
   __shared__ GemmSmem gs;
   __shared__ ActSmem am, pm;
   __shared__ float s1[128], s2[128];
@@ -411,15 +492,33 @@ mlp_bwd_dw_kernel(DyCtx c, ActSrc prev, int B, int rows_per_split, float* __rest
       if (n < wi) out[(size_t)o * wi + n] = acc[i][j];
     }
   }
+  if (fin.dW && last_block_arrives(fin.ticket)) dw_finalize_block(part, (int)gridDim.x, wo * wi, fin.dW);
+}
+__device__ __forceinline__ void dw_finalize_elem(const float* __restrict__ part, int nsplit, int n, int i, float* __restrict__ dW) {
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int c = lane; c < nsplit; c += 32) s += __ldcg(part + (size_t)c * n + i);
+  s = warp_sum(s);
+  if (lane == 0) dW[i] = s;
+}
+// all n elements by ONE CTA (the last block of the producing kernel): few partials -> a thread per element (coalesced
+// over e), many partials -> a warp per element
+__device__ __forceinline__ void dw_finalize_block(const float* __restrict__ part, int nsplit, int n, float* __restrict__ dW) {
+  if (nsplit <= 32) {
+    for (int e = threadIdx.x; e < n; e += (int)blockDim.x) {
+      float s = 0.f;
+      for (int c = 0; c < nsplit; ++c) s += __ldcg(part + (size_t)c * n + e);
+      dW[e] = s;
+    }
+  } else {
+    for (int e = threadIdx.x >> 5; e < n; e += (int)(blockDim.x >> 5)) dw_finalize_elem(part, nsplit, n, e, dW);
+  }
 }
 __global__ void __launch_bounds__(256)
 mlp_dw_finalize_kernel(const float* __restrict__ part, int nsplit, int n, float* __restrict__ dW) {
-  const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= n) return;
-  float s = 0.f;
-  for (int c = lane; c < nsplit; c += 32) s += part[(size_t)c * n + i];
-  s = warp_sum(s);
-  if (lane == 0) dW[i] = s;
+  dw_finalize_elem(part, nsplit, n, i, dW);
 }
 
 // ----------------------------------------------------------------------------------------- narrow layers (w <= 8)
@@ -429,7 +528,7 @@ mlp_dw_finalize_kernel(const float* __restrict__ part, int nsplit, int n, float*
 template <int WI, int WO>
 __global__ void __launch_bounds__(256)
 mlp_narrow_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ bias, int B, int wo,
-                      float* __restrict__ y_out, float* __restrict__ part, int do_stats) {
+                      float* __restrict__ y_out, float* __restrict__ part, int do_stats, StatsFin fin) {
   __shared__ ActSmem am;
   __shared__ float Ws[WO][WI], bs[WO];
   __shared__ float red[8][WO][3];
@@ -481,13 +580,14 @@ mlp_narrow_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __re
     float* o = part + ((size_t)blockIdx.x * 128 + threadIdx.x) * 3;
     o[0] = c; o[1] = mu; o[2] = q;
   }
+  if (fin.stats && last_block_arrives(fin.ticket)) stats_finalize_block(part, (int)gridDim.x, wo, fin);
 }
 
 // da_prev = dy W and per-block partial of dW = dy^T act(prev), one row per thread
 template <int WI, int WO>
 __global__ void __launch_bounds__(256)
 mlp_narrow_bwd_kernel(DyCtx c, ActSrc prev, const float* __restrict__ W, int B, float* __restrict__ da_prev,
-                      float* __restrict__ part /*[nblk][wo*wi]*/) {
+                      float* __restrict__ part /*[nblk][wo*wi]*/, DwFin fin) {
   __shared__ ActSmem am, pm;
   __shared__ float Ws[WO][WI], s1[WO], s2[WO];
   __shared__ float red[8][WO * WI];
@@ -550,6 +650,7 @@ mlp_narrow_bwd_kernel(DyCtx c, ActSrc prev, const float* __restrict__ W, int B, 
     for (int w8 = 0; w8 < 8; ++w8) v += red[w8][threadIdx.x];
     if (o < wo && k < wi) part[(size_t)blockIdx.x * wo * wi + o * wi + k] = v;
   }
+  if (fin.dW && last_block_arrives(fin.ticket)) dw_finalize_block(part, (int)gridDim.x, wo * wi, fin.dW);
 }
 
 static int narrow_class(int w) { return w <= 2 ? 2 : (w <= 4 ? 4 : (w <= 8 ? 8 : 0)); }
@@ -557,13 +658,13 @@ static int narrow_grid(int B) { int g = (B + 255) / 256; return g > 592 ? 592 : 
 
 template <int WI, int WO>
 static void narrow_fwd_launch(const ActSrc& src, const float* W, const float* bias, int B, int wo, float* y, float* part,
-                              int do_stats, int grid, cudaStream_t st) {
-  mlp_narrow_fwd_kernel<WI, WO><<<grid, 256, 0, st>>>(src, W, bias, B, wo, y, part, do_stats);
+                              int do_stats, const StatsFin& fin, int grid, cudaStream_t st) {
+  mlp_narrow_fwd_kernel<WI, WO><<<grid, 256, 0, st>>>(src, W, bias, B, wo, y, part, do_stats, fin);
 }
 template <int WI, int WO>
-static void narrow_bwd_launch(const DyCtx& c, const ActSrc& prev, const float* W, int B, float* da_prev, float* part, int grid,
-                              cudaStream_t st) {
-  mlp_narrow_bwd_kernel<WI, WO><<<grid, 256, 0, st>>>(c, prev, W, B, da_prev, part);
+static void narrow_bwd_launch(const DyCtx& c, const ActSrc& prev, const float* W, int B, float* da_prev, float* part,
+                              const DwFin& fin, int grid, cudaStream_t st) {
+  mlp_narrow_bwd_kernel<WI, WO><<<grid, 256, 0, st>>>(c, prev, W, B, da_prev, part, fin);
 }
 #define B200VAE_NARROW_DISPATCH(FN, ci, co, ...)                                   \
   do {                                                                              \
@@ -586,13 +687,18 @@ static ActSrc make_src(const float* y, const float* stats, const float* gamma, c
 
 using namespace b200vae;
 
-extern "C" size_t b200vae_mlp_scratch_bytes(int B) {
+static size_t mlp_scratch_floats(int B) {
   const size_t ncta = (size_t)(B + 127) / 128;
   const size_t a = (ncta > 592 ? ncta : 592) * 128 * 3, b = (size_t)296 * 128 * 2, c = (size_t)296 * 128 * 128;
   size_t m = a > b ? a : b;
   if (c > m) m = c;
-  return m * sizeof(float);
+  return m;
 }
+// partials, then 64 floats holding the last-block ticket (must be zero before the first call; every call leaves it zero)
+extern "C" size_t b200vae_mlp_scratch_bytes(int B) { return (mlp_scratch_floats(B) + 64) * sizeof(float); }
+static unsigned* mlp_ticket(void* scratch, int B) { return reinterpret_cast<unsigned*>((float*)scratch + mlp_scratch_floats(B)); }
+// one CTA finalising n outputs from `nparts` partials each: worth fusing while that is a few thousand loads per warp
+static bool fuse_finalize(long long nparts, long long n) { return nparts * n <= (long long)1 << 16; }
 
 static int mlp_layer_fwd_impl(const float* in_y, const float* in_stats, const float* in_gamma, const float* in_beta,
                               float slope, const float* W, const float* bias, int B, int wi, int wo, float* y_out,
@@ -604,14 +710,19 @@ static int mlp_layer_fwd_impl(const float* in_y, const float* in_stats, const fl
   int ncta = (B + 127) / 128;
   const ActSrc src = make_src(in_y, in_stats, in_gamma, in_beta, wi, slope);
   const int ci = narrow_class(wi), co = narrow_class(wo);
+  if (ci && co) ncta = narrow_grid(B);
+  // single GPU: the last CTA of the layer kernel finalises the statistics itself (no second launch)
+  const bool fused = stats_out && !comm && fuse_finalize(ncta, wo);
+  StatsFin fin;
+  fin.stats = fused ? stats_out : nullptr; fin.running_mean = running_mean; fin.running_var = running_var; fin.eps = eps;
+  fin.momentum = momentum; fin.ticket = mlp_ticket(scratch, B);
   if (ci && co) {
-    ncta = narrow_grid(B);
-    B200VAE_NARROW_DISPATCH(narrow_fwd_launch, ci, co, src, W, bias, B, wo, y_out, (float*)scratch, stats_out ? 1 : 0, ncta, st);
+    B200VAE_NARROW_DISPATCH(narrow_fwd_launch, ci, co, src, W, bias, B, wo, y_out, (float*)scratch, stats_out ? 1 : 0, fin, ncta, st);
   } else {
-    mlp_fwd_kernel<<<ncta, kThreads, 0, st>>>(src, W, bias, B, wo, y_out, (float*)scratch, stats_out ? 1 : 0);
+    mlp_fwd_kernel<<<ncta, kThreads, 0, st>>>(src, W, bias, B, wo, y_out, (float*)scratch, stats_out ? 1 : 0, fin);
   }
   int rc = check_launch();
-  if (rc || !stats_out) return rc;
+  if (rc || !stats_out || fused) return rc;
   if (comm)
     mlp_stats_finalize_peer_kernel<<<1, 1024, 0, st>>>((const float*)scratch, ncta, wo, eps, stats_out, running_mean,
                                                       running_var, momentum, make_peer(comm), slot);
@@ -650,9 +761,11 @@ static int mlp_layer_bwd_reduce_impl(const float* da, const float* y, const floa
   long long per = (n + nblk - 1) / nblk;
   per = (per + 255) / 256 * 256;                       // keeps (element index % w) == (thread index % w)
   const ActSrc cur = make_src(y, stats, gamma, beta, w, slope);
-  mlp_bwd_reduce_kernel<<<nblk, 256, 0, st>>>(da, cur, stats ? 1 : 0, n, per, dyhat, (float*)scratch);
+  SumsFin fin;
+  fin.sums = comm ? nullptr : sums; fin.ticket = mlp_ticket(scratch, B);
+  mlp_bwd_reduce_kernel<<<nblk, 256, 0, st>>>(da, cur, stats ? 1 : 0, n, per, dyhat, (float*)scratch, fin);
   int rc = check_launch();
-  if (rc) return rc;
+  if (rc || fin.sums) return rc;
   if (comm)
     mlp_sum_finalize_peer_kernel<<<1, 1024, 0, st>>>((const float*)scratch, nblk, w, sums, sums_global, make_peer(comm), slot);
   else
@@ -690,11 +803,9 @@ extern "C" int b200vae_mlp_layer_bwd(const float* dyhat, const float* y, const f
   if (ci && co) {
     const int grid = narrow_grid(B);
     const ActSrc prev = make_src(prev_y, prev_stats, prev_gamma, prev_beta, wi, slope);
-    B200VAE_NARROW_DISPATCH(narrow_bwd_launch, ci, co, c, prev, W, B, da_prev, dW ? (float*)scratch : nullptr, grid, st);
-    rc = check_launch();
-    if (rc || !dW) return rc;
-    const int n = wo * wi;
-    mlp_dw_finalize_kernel<<<(n + 7) / 8, 256, 0, st>>>((const float*)scratch, grid, n, dW);
+    DwFin fin;
+    fin.dW = dW; fin.ticket = mlp_ticket(scratch, B);        // <= 64 outputs from <= 592 partials: always fused
+    B200VAE_NARROW_DISPATCH(narrow_bwd_launch, ci, co, c, prev, W, B, da_prev, dW ? (float*)scratch : nullptr, fin, grid, st);
     return check_launch();
   }
   if (da_prev) {
@@ -703,15 +814,21 @@ extern "C" int b200vae_mlp_layer_bwd(const float* dyhat, const float* y, const f
     if (rc) return rc;
   }
   if (dW) {
+    // split the batch (the K dimension of dW = dy^T act(prev)) over CTAs: 256 samples each at large B; at small B one
+    // 16-sample K-tile each, so that a batch-256 layer runs on 16 SMs instead of ONE CTA walking 16 dependent K-tiles
+    // (measured at B = 256: 80-114 us per layer before)
     int nsplit = (B + 255) / 256;
+    if (nsplit < 64) { const int fine = (B + kBK - 1) / kBK; nsplit = fine < 64 ? fine : 64; }
     if (nsplit > 296) nsplit = 296;
     int rows = (B + nsplit - 1) / nsplit;
     rows = round_up(rows, kBK);
     const ActSrc prev = make_src(prev_y, prev_stats, prev_gamma, prev_beta, wi, slope);
-    mlp_bwd_dw_kernel<<<nsplit, kThreads, 0, st>>>(c, prev, B, rows, (float*)scratch);
-    rc = check_launch();
-    if (rc) return rc;
     const int n = wo * wi;
+    DwFin fin;
+    fin.dW = fuse_finalize(nsplit, n) ? dW : nullptr; fin.ticket = mlp_ticket(scratch, B);
+    mlp_bwd_dw_kernel<<<nsplit, kThreads, 0, st>>>(c, prev, B, rows, (float*)scratch, fin);
+    rc = check_launch();
+    if (rc || fin.dW) return rc;
     mlp_dw_finalize_kernel<<<(n + 7) / 8, 256, 0, st>>>((const float*)scratch, nsplit, n, dW);
     rc = check_launch();
   }

@@ -79,9 +79,7 @@ class ICNN(nn.Module):
 
     def forward(self, input):
         if self.in_channel > self.FUSED_MAX_D:
-            if not input.is_cuda:
-                raise _C.B200VaeError("expected a CUDA tensor; vae_song_b200 has no CPU fallback")
-            return ops.icnn_potential_wide(input, self._mode(), *self._flat_params())
+            return ops.IcnnPotentialWideFn.apply(input, self._mode(), self._prec(), *self._flat_params())
         return ops.IcnnPotentialFn.apply(input, self._mode(), self._prec(), *self._flat_params())
 
     FP32_TILED_BELOW = 6144   # measured crossover (scripts/fp32_crossover.py): below it the tiled GEMM chain is the faster FP32 path

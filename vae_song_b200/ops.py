@@ -115,6 +115,28 @@ class IcnnBrenierFn(torch.autograd.Function):
         return (dz, None, None, None, *grads)
 
 
+class _FirstOrderOnly(torch.autograd.Function):
+    """Identity on `t` that ties it to `anchor`'s graph and fails loudly if anyone differentiates THROUGH it: the parameter
+    gradients of psi are produced by kernels without a graph, so a create_graph=True caller who went on to differentiate
+    them would otherwise silently get zeros."""
+
+    @staticmethod
+    def forward(ctx, t, anchor, what):
+        ctx.what = what
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        raise _C.B200VaeError(f"second-order derivatives through {ctx.what} are not implemented (the fused kernels "
+                              "differentiate psi twice in z -- the Brenier-map path -- not its parameter gradients)")
+
+
+def _guard_param_grads(pgrads, anchor):
+    if not (torch.is_grad_enabled() and anchor.requires_grad):
+        return pgrads
+    return [None if g is None else _FirstOrderOnly.apply(g, anchor, "the parameter gradients of psi") for g in pgrads]
+
+
 class IcnnPotentialFn(torch.autograd.Function):
     """psi = ICNN(z) [B,1] exactly as module.ICNN.forward returns it, and -- like the reference -- it stays
     differentiable TWICE in z: backward computes grad_z = gpsi * xhat through IcnnBrenierFn (itself a
@@ -152,15 +174,11 @@ class IcnnPotentialFn(torch.autograd.Function):
                 _, _, m1, m2 = icnn_decode_fwd(zz, ws, d, H, mode, 0.0, precision, False, False, True)
                 _, grads = icnn_decode_bwd(zz, None, _req(g.detach(), "grad_psi"), m1, m2, [p.detach() for p in params],
                                            ws, d, H, mode, 0.0, precision, need_dz=False, need_params=True)
-            pgrads = [gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[3:])]
+            pgrads = _guard_param_grads([gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[3:])], gpsi)
         return (dz, None, None, *pgrads)
 
 
 # ------------------------------------------------------------------------------------------ wide-input ICNN
-def _pos(W, mode):
-    return W.exp() if mode == _C.WEIGHT_EXP else W.clamp(min=1e-2)
-
-
 def _grads_struct(tensors):
     g = _C.IcnnGrads()
     for k, t in zip(PARAM_FIELDS, tensors):
@@ -222,40 +240,87 @@ class IcnnBrenierWideFn(torch.autograd.Function):
         kappa, mode, precision = ctx.cfg
         if gpsi is None and v is None:
             return (None,) * 12
-        if gpsi is not None:                       # first-order backward of psi (Appendix A, last line)
-            raise NotImplementedError("psi-gradient of the wide-input ICNN: use ICNN.forward (plain autograd) instead")
-        lib = _C.load()
-        v = _req(v, "grad_xhat")
-        B, nz = z.shape
-        H, d = params[0].shape
-        dev = z.device
         need = ctx.needs_input_grad
-        ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, precision, 1), dtype=torch.uint8, device=dev)
-        scratch = torch.empty(4, B, H, dtype=torch.float32, device=dev)          # u0, q1, g0, t0
-        grads = [torch.empty_like(p) if n else None for p, n in zip(params, need[4:])]
-        dz = torch.empty_like(z) if need[0] else None
-        ps, gs = _params_struct(params), _grads_struct(grads)
-        _C.check(lib.b200vae_icnn_wide_bwd(_ptr(z), _ptr(v), _ptr(h0), _ptr(mask1), _ptr(s2), B, d, nz, H, C.byref(ps), mode,
-                                           float(kappa), C.byref(gs), _ptr(dz), _ptr(scratch[0]), _ptr(scratch[1]),
-                                           _ptr(scratch[2]), _ptr(scratch[3]), precision, _ptr(ws), ws.numel(), _stream()),
-                 "icnn_wide_bwd")
+        dz, grads = None, [None] * len(params)
+        if v is not None:                          # double-backward of the Brenier map (dL/dxhat)
+            dz, grads = icnn_wide_bwd(z, _req(v, "grad_xhat"), h0, mask1, s2, params, mode, kappa, precision, need[0], need[4:])
+        if gpsi is not None:                       # first-order backward of psi (Appendix A, last line), FP32 tile kernels
+            dz2, g2 = icnn_wide_bwd_psi(z, _req(gpsi, "grad_psi"), h0, mask1, s2, params, mode, need[0], need[4:])
+            dz = dz2 if dz is None else (dz + dz2 if dz2 is not None else dz)
+            grads = [b if a is None else (a + b if b is not None else a) for a, b in zip(grads, g2)]
         return (dz, None, None, None, *grads)
 
 
-def icnn_potential_wide(z, mode, A0w, A0b, A1w, A1b, A2w, A2b, W0, W1):
-    """psi [B,1] of a wide-input ICNN with ordinary differentiable torch ops (module.py:142-148 verbatim
-    semantics), so first- and second-order autograd through psi keep working for d > 4."""
-    _C.load()
-    ps = (A0w, A0b, A1w, A1b, A2w, A2b, W0, W1)
-    if not z.is_cuda or any(not p.is_cuda for p in ps):
-        raise _C.B200VaeError("icnn_potential_wide: expected CUDA tensors; vae_song_b200 has no CPU fallback")
-    if not (torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in ps))):
-        psi, _, _ = icnn_wide_fwd(_req(z, "z"), [_req(p, k) for p, k in zip(ps, PARAM_FIELDS)], mode, 0.0, False)
-        return psi.unsqueeze(1)                     # inference: fused kernels, psi only
-    act = torch.nn.functional.leaky_relu
-    x = act(torch.nn.functional.linear(z, A0w, A0b), 0.2).pow(2)
-    x = act(torch.nn.functional.linear(x, _pos(W0, mode)) + torch.nn.functional.linear(z, A1w, A1b), 0.2)
-    return act(torch.nn.functional.linear(x, _pos(W1, mode)) + torch.nn.functional.linear(z, A2w, A2b), 0.2)
+def icnn_wide_bwd(z, v, h0, mask1, s2, params, mode, kappa, precision, need_dz=True, need_params=None):
+    """dL/dz and parameter gradients of L = <v, xhat> for the wide-input ICNN (b200vae_icnn_wide_bwd)."""
+    lib = _C.load()
+    B, nz = z.shape
+    H, d = params[0].shape
+    dev = z.device
+    need_params = [True] * len(params) if need_params is None else list(need_params)
+    ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, precision, 1), dtype=torch.uint8, device=dev)
+    scratch = torch.empty(4, B, H, dtype=torch.float32, device=dev)          # u0, q1, g0, t0
+    grads = [torch.empty_like(p) if n else None for p, n in zip(params, need_params)]
+    dz = torch.empty_like(z) if need_dz else None
+    ps, gs = _params_struct(params), _grads_struct(grads)
+    _C.check(lib.b200vae_icnn_wide_bwd(_ptr(z), _ptr(v), _ptr(h0), _ptr(mask1), _ptr(s2), B, d, nz, H, C.byref(ps), mode,
+                                       float(kappa), C.byref(gs), _ptr(dz), _ptr(scratch[0]), _ptr(scratch[1]),
+                                       _ptr(scratch[2]), _ptr(scratch[3]), precision, _ptr(ws), ws.numel(), _stream()),
+             "icnn_wide_bwd")
+    return dz, grads
+
+
+def icnn_wide_bwd_psi(z, gpsi, h0, mask1, s2, params, mode, need_dz=True, need_params=None):
+    """dL/dz and parameter gradients of L = <gpsi, psi> for the wide-input ICNN (b200vae_icnn_wide_bwd_psi)."""
+    lib = _C.load()
+    B, nz = z.shape
+    H, d = params[0].shape
+    dev = z.device
+    need_params = [True] * len(params) if need_params is None else list(need_params)
+    ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, _C.PREC_FP32, 1), dtype=torch.uint8, device=dev)
+    scratch = torch.empty(2, B, H, dtype=torch.float32, device=dev)          # x1, gpsi*g0
+    s2g = torch.empty(B, dtype=torch.float32, device=dev)
+    grads = [torch.empty_like(p) if n else None for p, n in zip(params, need_params)]
+    dz = torch.empty_like(z) if need_dz else None
+    ps, gs = _params_struct(params), _grads_struct(grads)
+    _C.check(lib.b200vae_icnn_wide_bwd_psi(_ptr(z), _ptr(gpsi), _ptr(h0), _ptr(mask1), _ptr(s2), B, d, nz, H, C.byref(ps), mode,
+                                           C.byref(gs), _ptr(dz), _ptr(scratch[0]), _ptr(scratch[1]), _ptr(s2g), _ptr(ws),
+                                           ws.numel(), _stream()), "icnn_wide_bwd_psi")
+    return dz, grads
+
+
+class IcnnPotentialWideFn(torch.autograd.Function):
+    """psi = ICNN(z) [B,1] for wide inputs (d > 4), exactly as module.ICNN.forward returns it and -- like the reference and
+    like IcnnPotentialFn for d <= 4 -- differentiable TWICE in z: backward computes grad_z = gpsi * xhat through
+    IcnnBrenierWideFn (a Function with its own analytic backward), and the parameter gradients of <gpsi, psi> with the
+    fused first-order backward.  Replaces module.py:142-148 for ICNN(32,.) / ICNN(784,.)."""
+
+    @staticmethod
+    def forward(ctx, z, mode, precision, *params):
+        z = _req(z, "z")
+        params = [_req(p, k) for p, k in zip(params, PARAM_FIELDS)]
+        psi, _, saved = icnn_wide_fwd(z, params, mode, 0.0, False, precision)
+        ctx.save_for_backward(z, *saved, *params)
+        ctx.cfg = (mode, precision)
+        return psi.unsqueeze(1)
+
+    @staticmethod
+    def backward(ctx, gpsi):
+        z, h0, mask1, s2, *params = ctx.saved_tensors
+        mode, precision = ctx.cfg
+        need_z, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[3:]
+        g = gpsi[:, 0]
+        dz, pgrads = None, [None] * len(params)
+        if need_z:
+            # differentiable in (z, params, gpsi) when create_graph=True: the Brenier map is a Function too
+            _, xhat = IcnnBrenierWideFn.apply(z, 0.0, mode, precision, *params)
+            dz = g.unsqueeze(1) * xhat
+        if any(need_p):
+            with torch.no_grad():
+                _, pgrads = icnn_wide_bwd_psi(z.detach(), _req(g.detach(), "grad_psi"), h0, mask1, s2,
+                                              [p.detach() for p in params], mode, False, need_p)
+            pgrads = _guard_param_grads(pgrads, gpsi)
+        return (dz, None, None, *pgrads)
 
 
 # ------------------------------------------------------------------------------------------ losses
@@ -461,6 +526,20 @@ def _bn_group(bn):
     return None
 
 
+_mlp_scratch_cache = {}
+
+
+def _mlp_scratch(nbytes, device):
+    """Per (device, stream, size) scratch of the fused layer kernels.  Its tail holds the last-block ticket, which must be
+    zero before the first call and is left zero by every call, so the buffer is zero-initialised ONCE and reused (the
+    partials in it never outlive one C call; calls on one stream are ordered)."""
+    key = (device, torch.cuda.current_stream().cuda_stream, int(nbytes))
+    buf = _mlp_scratch_cache.get(key)
+    if buf is None:
+        buf = _mlp_scratch_cache[key] = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
+    return buf
+
+
 class FusedMlpFn(torch.autograd.Function):
     """out = Linear_n( act(BN_{n-1}( ... act(BN_0(Linear_0(x))) ... )) ) through the fused layer kernels (csrc/mlp.cu)."""
 
@@ -474,7 +553,7 @@ class FusedMlpFn(torch.autograd.Function):
         bs = [_req(params[2 * i + 1], "b") for i in range(nl)]
         gs = [_req(params[2 * nl + 2 * i], "gamma") for i in range(nl - 1)]
         bes = [_req(params[2 * nl + 2 * i + 1], "beta") for i in range(nl - 1)]
-        scratch = torch.empty(lib.b200vae_mlp_scratch_bytes(B), dtype=torch.uint8, device=x.device)
+        scratch = _mlp_scratch(lib.b200vae_mlp_scratch_bytes(B), x.device)
         ys, stats, counts = [], [], []
         ticks = []                # num_batches_tracked counters, advanced by one multi-tensor launch at the end
         prev = (x, None, None, None)

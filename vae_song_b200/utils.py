@@ -95,13 +95,31 @@ def eval_inference_dist(mu, logvar, z):
     return -0.5 * (((z - mu) ** 2) / logvar.exp()).sum(dim=-1) - 0.5 * (nz * math.log(2 * math.pi) + logvar.sum(-1))
 
 
-def nll_iw(mu, log_var, loss_rec, nsamples=100):
-    """utils.py:109-120: importance-weighted NLL estimate (a scalar over the whole batch, like the reference)."""
+_iw_scratch = {}
+
+
+def nll_iw(mu, log_var, loss_rec, nsamples=100, eps=None):
+    """utils.py:109-120: importance-weighted NLL estimate (a scalar over the whole batch, like the reference).  One fused
+    kernel (b200vae_nll_iw_lse): eps is drawn exactly like utils.reparameterize does (randn_like on the expanded
+    [B,ns,nz] std), so the same seed gives the reference's samples; z and the [B,ns] log-density tensors are never formed.
+    `eps` [B,ns,nz] may be injected for tests."""
     import math
-    z = reparameterize(mu.detach(), log_var.detach(), nsamples)
-    log_pz = (-0.5 * z ** 2 - 0.5 * math.log(2 * math.pi)).sum(dim=-1)
-    tmp = log_pz - loss_rec - eval_inference_dist(mu.detach(), log_var.detach(), z)
-    return -(log_sum_exp(tmp) - math.log(nsamples)).item()
+    from . import _C
+    lib = _C.load()
+    mu, log_var = ops._req(mu.detach(), "mu"), ops._req(log_var.detach(), "log_var")
+    B, nz = mu.shape
+    if eps is None:
+        eps = torch.randn_like(mu.unsqueeze(1).expand(B, nsamples, nz))
+    eps = ops._req(eps, "eps")
+    key = (mu.device, torch.cuda.current_stream().cuda_stream)
+    scr = _iw_scratch.get(key)
+    if scr is None:
+        scr = _iw_scratch[key] = torch.zeros(lib.b200vae_nll_iw_scratch_bytes(), dtype=torch.uint8, device=mu.device)
+    out = torch.empty(1, dtype=torch.float32, device=mu.device)
+    _C.check(lib.b200vae_nll_iw_lse(ops._ptr(mu), ops._ptr(log_var), ops._ptr(eps), B, eps.shape[1], nz, ops._ptr(out),
+                                    ops._ptr(scr), ops._stream()), "nll_iw_lse")
+    rec = loss_rec.detach().float().reshape(()) if torch.is_tensor(loss_rec) else float(loss_rec)
+    return -(out[0] - rec - math.log(eps.shape[1])).item()
 
 
 def measure_pc_runmodel(model, loader, device):
@@ -222,9 +240,14 @@ def estimate_lipschitz_allpairs(func, X, eps=1e-3, process_group=None, nbins=0, 
             pad = torch.zeros(per, *tail, dtype=torch.float32, device=X.device)
             if Yl is not None:
                 pad[:hi_r - lo_r] = Yl
-            gathered = [torch.empty_like(pad) for _ in range(world)]
-            dist.all_gather(gathered, pad, group=process_group)
-            Y = torch.cat(gathered, 0)[:N]
+            if pad.is_cuda:
+                full = torch.empty(world * per, *tail, dtype=torch.float32, device=X.device)
+                dist.all_gather_into_tensor(full, pad, group=process_group)          # one NCCL call, no concatenation
+                Y = full[:N]
+            else:
+                gathered = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(gathered, pad, group=process_group)
+                Y = torch.cat(gathered, 0)[:N]
         else:
             Y = func(X)
     nt = ops.lipschitz_num_tiles(N)
