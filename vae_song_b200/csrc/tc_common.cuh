@@ -154,9 +154,10 @@ inline float* tc_base(float* ws, int d, int H) {
 //                            5.6e-6 in chunks of 512, 2.1e-6 / 2.8e-6 in chunks of 256 -- "mixed" / "default" weights); the
 //                            forward therefore accumulates K in chunks of kTc3ChunkK, each in a fresh accumulator, and the
 //                            epilogue warps add the chunks with round-to-nearest FP32 adds.  A thread re-reads only what it
-//                            wrote itself; 256 KB per cluster, L2 resident.  Cost: 256 KB of L2 traffic per extra chunk and
-//                            CTA next to the 16 KB per K-block of TMA operand traffic (the kernel moves ~6 TB/s out of L2):
-//                            +6 % per extra chunk, hence 512 (north_star's 1e-5 is met with 1.8x margin) and not 256.
+//                            wrote itself; 256 KB per cluster, L2 resident.  Cost: the drain is a read-modify-write with
+//                            dependent L2 round trips (~8 us per chunk) and the MMA warp runs at most one chunk ahead, so a
+//                            chunk must outlast its predecessor's drain: 512-wide GEMM1 chunks do (12.5 us, +1 %), 256-wide
+//                            ones do not (+16 %).  Hence 512 (north_star's 1e-5 is met with 1.8x margin), GEMM1 only.
 constexpr int kTc3MaxTiles = 16384;
 constexpr int kTc3MaxClusters = 80;
 constexpr size_t k3ScrFloatsPerCta = (size_t)128 * 256;

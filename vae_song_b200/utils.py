@@ -143,6 +143,39 @@ def measure_pc_runmodel(model, loader, device):
     return au_sum, kl_sum, mi_sum, nll_sum, var_sum
 
 
+def compute_local_reg(model, loader, K):
+    """utils.py:509-530: per grid cell, the model's regularisation loss part divided by the cell's sample count (0.0 for
+    an empty cell) -> numpy array [K*K].  `loader.dataset` carries `.X` and `.y` (cell labels)."""
+    import numpy as np
+    device = next(model.parameters()).device
+    model.eval()
+    regs = []
+    with torch.no_grad():
+        X_all, y_all = loader.dataset.X, loader.dataset.y
+        for cell in range(K * K):
+            mask = (y_all == cell)
+            if mask.sum() == 0:
+                regs.append(0.0)
+                continue
+            X_cell = X_all[mask].to(device)
+            recon, mu, log_var, z_input, z_recon = model(X_cell)
+            _, _, loss_reg_term, _ = model.loss(X_cell, recon, mu, log_var, z_input, z_recon)
+            regs.append(float(loss_reg_term) / X_cell.size(0))
+    return np.array(regs)
+
+
+def _plotting_out_of_scope(name):
+    def fn(*args, **kwargs):
+        raise NotImplementedError(f"utils.{name}: matplotlib plotting is outside the hot path this package covers (DESIGN.md, "
+                                  "'Out of scope'); the name exists so that the reference's drivers import unchanged")
+    fn.__name__ = name
+    return fn
+
+
+plot_heatmap = _plotting_out_of_scope("plot_heatmap")
+plot_2d_histogram = _plotting_out_of_scope("plot_2d_histogram")
+
+
 def estimate_local_lipschitz(func, X, num_pairs=2000, metric=2, quantile=0.05, eps=1e-3, generator=None,
                              use_grad=False):
     """Random-pair local Lipschitz estimate, reference semantics (utils.py:532-567):
