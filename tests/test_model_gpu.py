@@ -307,7 +307,6 @@ def test_lidvae_mnist_constructs_and_trains_one_step():
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
 
 
-@pytest.mark.parametrize("hidden", [[2, 2, 2, 2], [128, 64, 64, 32, 16, 8, 4, 2], [16]])
 def test_unmodified_reference_driver_runs_on_this_package():
     """Drop-in proof with the reference's OWN driver file: oracle/_ref/lipschitz.py (byte-identical copy of the reference,
     oracle/fetch_ref.py) is imported with `module`, `model`, `utils` bound to vae_song_b200's modules instead of the
@@ -359,6 +358,7 @@ def test_unmodified_reference_driver_runs_on_this_package():
         np.testing.assert_allclose(a, b, rtol=1e-4, err_msg=name)
 
 
+@pytest.mark.parametrize("hidden", [[2, 2, 2, 2], [128, 64, 64, 32, 16, 8, 4, 2], [16]])
 @pytest.mark.parametrize("training", [True, False])
 def test_fused_encoder_matches_stock_modules(hidden, training):
     """Fused Linear+BN+LeakyReLU layers (csrc/mlp.cu) vs the very same nn.Modules run by PyTorch: outputs, every

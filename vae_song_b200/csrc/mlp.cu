@@ -653,6 +653,150 @@ mlp_narrow_bwd_kernel(DyCtx c, ActSrc prev, const float* __restrict__ W, int B, 
   if (fin.dW && last_block_arrives(fin.ticket)) dw_finalize_block(part, (int)gridDim.x, wo * wi, fin.dW);
 }
 
+// ----------------------------------------------------------------------------------------- small batches (B <= kRowsMaxB)
+// At the batch sizes of BASELINE configs[2] / [3] (256) the 128x128x16 tile core runs a layer on 2 CTAs that walk up to 8
+// DEPENDENT K-tiles, each exposing a full global-load latency: 20 us per layer forward, 27 us for the two backward GEMMs
+// (warm-cache ncu, profiles/r02_launches_c3_warm.csv) -- half of the whole train step.  Here a CTA owns kRowsRT sample rows
+// and the WHOLE weight matrix sits in shared memory (<= 128 x 129 floats), loaded with all requests in flight at once; the
+// activations of the row tile are formed once (BN + LeakyReLU while loading) and every output is a dot product out of
+// shared memory.  B = 256 -> 16 CTAs, one latency per layer.
+constexpr int kRowsRT = 16;
+constexpr int kRowsMaxB = 2048;
+constexpr int kRowsLdw = 129;                      // padded row stride of W in shared memory (conflict-free across o)
+static size_t rows_smem_bytes(bool bwd) {
+  // W [128][129] + act tile [RT][128] (+ bwd: dy tile [RT][128])
+  return (size_t)(128 * kRowsLdw + kRowsRT * 128 * (bwd ? 2 : 1)) * sizeof(float);
+}
+
+// forward: y = act(prev) W^T + b for rows [r0, r0 + RT); per-column (count, mean, M2) partial of the tile; fused finalize
+__global__ void __launch_bounds__(256)
+mlp_rows_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ bias, int B, int wo,
+                    float* __restrict__ y_out, float* __restrict__ part, int do_stats, StatsFin fin) {
+  extern __shared__ float rsm[];
+  float* Ws = rsm;                                 // [wo][kRowsLdw]
+  float* As = rsm + 128 * kRowsLdw;                // [RT][128]: activations, later the output tile
+  __shared__ ActSmem am;
+  const int wi = src.w, r0 = blockIdx.x * kRowsRT, nrows = min(kRowsRT, B - r0);
+  am.load(src);
+  for (int e = threadIdx.x; e < wo * wi; e += 256) { const int o = e / wi, k = e - o * wi; Ws[o * kRowsLdw + k] = __ldg(W + e); }
+  float pre[(kRowsRT * 128) / 256];                // raw inputs first (loads in flight with the W loads), act after the sync
+#pragma unroll
+  for (int q = 0; q < (kRowsRT * 128) / 256; ++q) {
+    const int e = threadIdx.x + 256 * q, r = e >> 7, k = e & 127;
+    pre[q] = (r < nrows && k < wi) ? __ldg(src.y + (size_t)(r0 + r) * wi + k) : 0.f;
+  }
+  __syncthreads();
+  const bool has_bn = src.mean != nullptr;
+#pragma unroll
+  for (int q = 0; q < (kRowsRT * 128) / 256; ++q) {
+    const int e = threadIdx.x + 256 * q, r = e >> 7, k = e & 127;
+    As[e] = (r < nrows && k < wi) ? am.act(has_bn, src.slope, pre[q], k) : 0.f;
+  }
+  __syncthreads();
+  // thread -> column o = tid & 127, rows (tid >> 7) + 2 j: 8 dot products sharing every W element
+  const int o = threadIdx.x & 127, rb = threadIdx.x >> 7;
+  float acc[kRowsRT / 2];
+#pragma unroll
+  for (int j = 0; j < kRowsRT / 2; ++j) acc[j] = 0.f;
+  if (o < wo) {
+    const float* wrow = Ws + o * kRowsLdw;
+    for (int k = 0; k < wi; ++k) {
+      const float wv = wrow[k];
+#pragma unroll
+      for (int j = 0; j < kRowsRT / 2; ++j) acc[j] = fmaf(As[(rb + 2 * j) * 128 + k], wv, acc[j]);
+    }
+  }
+  __syncthreads();                                 // everyone is done reading As: it becomes the output tile
+  if (o < wo) {
+    const float bj = bias ? bias[o] : 0.f;
+#pragma unroll
+    for (int j = 0; j < kRowsRT / 2; ++j) {
+      const int r = rb + 2 * j;
+      const float yv = acc[j] + bj;
+      As[r * 128 + o] = yv;
+      if (r < nrows) y_out[(size_t)(r0 + r) * wo + o] = yv;
+    }
+  }
+  if (!do_stats) return;
+  __syncthreads();
+  if (threadIdx.x < wo) {                          // column statistics of this tile, rows in order
+    float sum = 0.f;
+    for (int r = 0; r < nrows; ++r) sum += As[r * 128 + threadIdx.x];
+    const float mean_c = sum / (float)nrows;
+    float m2 = 0.f;
+    for (int r = 0; r < nrows; ++r) { const float dlt = As[r * 128 + threadIdx.x] - mean_c; m2 = fmaf(dlt, dlt, m2); }
+    float* po = part + ((size_t)blockIdx.x * 128 + threadIdx.x) * 3;
+    po[0] = (float)nrows; po[1] = mean_c; po[2] = m2;
+  }
+  if (fin.stats && last_block_arrives(fin.ticket)) stats_finalize_block(part, (int)gridDim.x, wo, fin);
+}
+
+// backward: dy formed on the fly for the row tile; da_prev = dy W (may be null) and the tile's partial dW = dy^T act(prev)
+__global__ void __launch_bounds__(256)
+mlp_rows_bwd_kernel(DyCtx c, ActSrc prev, const float* __restrict__ W, int B, float* __restrict__ da_prev,
+                    float* __restrict__ part /*[nCTA][wo*wi] or null*/) {
+  extern __shared__ float rsm[];
+  float* Ws = rsm;                                 // [wo][kRowsLdw]
+  float* As = rsm + 128 * kRowsLdw;                // [RT][128] act(prev)
+  float* Ds = As + kRowsRT * 128;                  // [RT][128] dy
+  __shared__ ActSmem am, pm;
+  __shared__ float s1[128], s2[128];
+  const int wo = c.cur.w, wi = prev.w, r0 = blockIdx.x * kRowsRT, nrows = min(kRowsRT, B - r0);
+  am.load(c.cur);
+  pm.load(prev);
+  if (threadIdx.x < 128) {
+    s1[threadIdx.x] = (c.has_bn && threadIdx.x < wo) ? c.sums[threadIdx.x] : 0.f;
+    s2[threadIdx.x] = (c.has_bn && threadIdx.x < wo) ? c.sums[wo + threadIdx.x] : 0.f;
+  }
+  for (int e = threadIdx.x; e < wo * wi; e += 256) { const int o = e / wi, k = e - o * wi; Ws[o * kRowsLdw + k] = __ldg(W + e); }
+  constexpr int Q = (kRowsRT * 128) / 256;
+  float pa[Q], pg[Q], py[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int e = threadIdx.x + 256 * q, r = e >> 7, k = e & 127;
+    pa[q] = (r < nrows && k < wi) ? __ldg(prev.y + (size_t)(r0 + r) * wi + k) : 0.f;
+    pg[q] = 0.f; py[q] = 0.f;
+    if (r < nrows && k < wo) c.fetch((long long)(r0 + r) * wo + k, pg[q], py[q]);
+  }
+  __syncthreads();
+  const bool prev_bn = prev.mean != nullptr;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int e = threadIdx.x + 256 * q, r = e >> 7, k = e & 127;
+    As[e] = (r < nrows && k < wi) ? pm.act(prev_bn, prev.slope, pa[q], k) : 0.f;
+    Ds[e] = (r < nrows && k < wo) ? c.dy(am, s1, s2, pg[q], py[q], k) : 0.f;
+  }
+  __syncthreads();
+  if (da_prev) {                                   // thread -> input column k = tid & 127, rows (tid >> 7) + 2 j
+    const int k = threadIdx.x & 127, rb = threadIdx.x >> 7;
+    if (k < wi) {
+      float acc[kRowsRT / 2];
+#pragma unroll
+      for (int j = 0; j < kRowsRT / 2; ++j) acc[j] = 0.f;
+      for (int o = 0; o < wo; ++o) {
+        const float wv = Ws[o * kRowsLdw + k];
+#pragma unroll
+        for (int j = 0; j < kRowsRT / 2; ++j) acc[j] = fmaf(Ds[(rb + 2 * j) * 128 + o], wv, acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kRowsRT / 2; ++j) {
+        const int r = rb + 2 * j;
+        if (r < nrows) da_prev[(size_t)(r0 + r) * wi + k] = acc[j];
+      }
+    }
+  }
+  if (part) {                                      // dW partial of the tile: element (o, k), rows in order
+    float* out = part + (size_t)blockIdx.x * wo * wi;
+    for (int e = threadIdx.x; e < wo * wi; e += 256) {
+      const int o = e / wi, k = e - o * wi;
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < kRowsRT; ++r) s = fmaf(Ds[r * 128 + o], As[r * 128 + k], s);
+      out[e] = s;
+    }
+  }
+}
+
 static int narrow_class(int w) { return w <= 2 ? 2 : (w <= 4 ? 4 : (w <= 8 ? 8 : 0)); }
 static int narrow_grid(int B) { int g = (B + 255) / 256; return g > 592 ? 592 : (g < 1 ? 1 : g); }
 
@@ -710,7 +854,9 @@ static int mlp_layer_fwd_impl(const float* in_y, const float* in_stats, const fl
   int ncta = (B + 127) / 128;
   const ActSrc src = make_src(in_y, in_stats, in_gamma, in_beta, wi, slope);
   const int ci = narrow_class(wi), co = narrow_class(wo);
+  const bool rows = !(ci && co) && B <= kRowsMaxB;          // small batch, wide layer: row-tile kernel, W in shared memory
   if (ci && co) ncta = narrow_grid(B);
+  else if (rows) ncta = (B + kRowsRT - 1) / kRowsRT;
   // single GPU: the last CTA of the layer kernel finalises the statistics itself (no second launch)
   const bool fused = stats_out && !comm && fuse_finalize(ncta, wo);
   StatsFin fin;
@@ -718,6 +864,10 @@ static int mlp_layer_fwd_impl(const float* in_y, const float* in_stats, const fl
   fin.momentum = momentum; fin.ticket = mlp_ticket(scratch, B);
   if (ci && co) {
     B200VAE_NARROW_DISPATCH(narrow_fwd_launch, ci, co, src, W, bias, B, wo, y_out, (float*)scratch, stats_out ? 1 : 0, fin, ncta, st);
+  } else if (rows) {
+    static bool attr_done = false;
+    if (!attr_done) { cudaFuncSetAttribute(mlp_rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem_bytes(false)); attr_done = true; }
+    mlp_rows_fwd_kernel<<<ncta, 256, rows_smem_bytes(false), st>>>(src, W, bias, B, wo, y_out, (float*)scratch, stats_out ? 1 : 0, fin);
   } else {
     mlp_fwd_kernel<<<ncta, kThreads, 0, st>>>(src, W, bias, B, wo, y_out, (float*)scratch, stats_out ? 1 : 0, fin);
   }
@@ -806,6 +956,17 @@ extern "C" int b200vae_mlp_layer_bwd(const float* dyhat, const float* y, const f
     DwFin fin;
     fin.dW = dW; fin.ticket = mlp_ticket(scratch, B);        // <= 64 outputs from <= 592 partials: always fused
     B200VAE_NARROW_DISPATCH(narrow_bwd_launch, ci, co, c, prev, W, B, da_prev, dW ? (float*)scratch : nullptr, fin, grid, st);
+    return check_launch();
+  }
+  if (B <= kRowsMaxB) {            // small batch: ONE row-tile kernel for da_prev and the dW partials (W in shared memory)
+    static bool attr_done = false;
+    if (!attr_done) { cudaFuncSetAttribute(mlp_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem_bytes(true)); attr_done = true; }
+    const ActSrc prev = make_src(prev_y, prev_stats, prev_gamma, prev_beta, wi, slope);
+    const int ncta = (B + kRowsRT - 1) / kRowsRT, n = wo * wi;
+    mlp_rows_bwd_kernel<<<ncta, 256, rows_smem_bytes(true), st>>>(c, prev, W, B, da_prev, dW ? (float*)scratch : nullptr);
+    rc = check_launch();
+    if (rc || !dW) return rc;
+    mlp_dw_finalize_kernel<<<(n + 7) / 8, 256, 0, st>>>((const float*)scratch, ncta, n, dW);
     return check_launch();
   }
   if (da_prev) {

@@ -50,7 +50,7 @@ def reparameterize(mu, logvar, nsamples=1, generator=None):
     B, nz = mu.size()
     eps = torch.randn_like(mu.unsqueeze(1).expand(B, nsamples, nz))          # [B,ns,nz], same RNG stream
     z = ops.ReparamFn.apply(mu, logvar, eps.permute(1, 0, 2).contiguous())   # kernel layout [L,B,D]
-    return z.permute(1, 0, 2)
+    return z.permute(1, 0, 2).contiguous()      # the reference returns a contiguous tensor: lipschitz.py:68 calls .view() on it
 
 
 def kld(mu, log_var):
