@@ -11,6 +11,8 @@
 // Everything but y / dyhat / da stays on chip; cross-rank BatchNorm only needs the tiny (count,mean,M2) / (S1,S2)
 // vectors exchanged: the *_peer finalize kernels publish them straight into the other GPUs' memory over NVLink and
 // combine in rank order (peer.cuh), so a sharded step has no NCCL call and no torch glue per BatchNorm layer.
+#include <string.h>
+
 #include "gemm_simt.cuh"
 #include "peer.cuh"
 
@@ -104,10 +106,14 @@ __device__ __forceinline__ bool last_block_arrives(unsigned* ticket) {
   if (s_last) __threadfence();
   return s_last != 0;
 }
+// `peer` != 0: the last CTA also runs the cross-rank exchange (peer.cuh) -- publishes this rank's per-column values to every
+// GPU, waits for theirs and combines in rank order -- so a sharded layer needs no finalize launch either.  `stage`: global
+// staging for the exchange ([128*3] mine + [world][128*3] all, part of the caller's scratch).
 struct StatsFin {      // stats == nullptr: no fused finalize (a finalize kernel follows)
   float* stats; float* running_mean; float* running_var; float eps, momentum; unsigned* ticket;
+  int peer, slot; float* stage; PeerComm comm;
 };
-struct SumsFin { float* sums; unsigned* ticket; };
+struct SumsFin { float* sums; unsigned* ticket; int peer, slot; float* sums_global; float* stage; PeerComm comm; };
 struct DwFin { float* dW; unsigned* ticket; };
 
 // ----------------------------------------------------------------------------------------- forward
@@ -205,6 +211,41 @@ mlp_stats_finalize_kernel(const float* __restrict__ part, int ncta, int w, float
 }
 // the same, executed by the last CTA of the producing kernel (all its warps, columns round-robin)
 __device__ __forceinline__ void stats_finalize_block(const float* __restrict__ part, int ncta, int w, const StatsFin& f) {
+  if (f.peer) {                // cross-rank: local (count, mean, M2) per column -> exchange -> Chan merge in rank order
+    float* mine = f.stage;
+    float* all = f.stage + 3 * 128;
+    const int lane = threadIdx.x & 31;
+    for (int n = threadIdx.x >> 5; n < w; n += (int)(blockDim.x >> 5)) {
+      float cnt = 0.f, mean = 0.f, m2 = 0.f;
+      for (int c = lane; c < ncta; c += 32) {
+        const float* p = part + ((size_t)c * 128 + n) * 3;
+        chan_merge(cnt, mean, m2, __ldcg(p), __ldcg(p + 1), __ldcg(p + 2));
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const float nb = __shfl_down_sync(0xffffffffu, cnt, off), mb = __shfl_down_sync(0xffffffffu, mean, off),
+                    m2b = __shfl_down_sync(0xffffffffu, m2, off);
+        chan_merge(cnt, mean, m2, nb, mb, m2b);
+      }
+      if (lane == 0) { mine[n] = cnt; mine[w + n] = mean; mine[2 * w + n] = m2; }
+    }
+    __syncthreads();
+    peer_exchange(f.comm, f.slot, mine, 3 * w, all);
+    for (int n = threadIdx.x; n < w; n += (int)blockDim.x) {
+      float cnt = 0.f, mean = 0.f, m2 = 0.f;
+      for (int r = 0; r < f.comm.world; ++r) {
+        const float* a = all + (size_t)r * 3 * w;
+        chan_merge(cnt, mean, m2, a[n], a[w + n], a[2 * w + n]);
+      }
+      const float var = m2 / cnt;
+      f.stats[n] = mean; f.stats[w + n] = var; f.stats[2 * w + n] = rsqrtf(var + f.eps); f.stats[3 * w + n] = cnt;
+      if (f.running_mean) {
+        f.running_mean[n] = (1.f - f.momentum) * f.running_mean[n] + f.momentum * mean;
+        f.running_var[n] = (1.f - f.momentum) * f.running_var[n] + f.momentum * (m2 / fmaxf(cnt - 1.f, 1.f));
+      }
+    }
+    return;
+  }
   if (ncta <= 64) {            // few partials (small batches): a THREAD per column, partials merged in CTA order
     for (int n = threadIdx.x; n < w; n += (int)blockDim.x) {
       float cnt = 0.f, mean = 0.f, m2 = 0.f;
@@ -307,7 +348,25 @@ mlp_bwd_reduce_kernel(const float* __restrict__ da, ActSrc cur, int has_bn, long
     part[((size_t)blockIdx.x * 128 + threadIdx.x) * 2 + 0] = a;
     part[((size_t)blockIdx.x * 128 + threadIdx.x) * 2 + 1] = b;
   }
-  if (fin.sums && last_block_arrives(fin.ticket)) {
+  if (fin.peer && last_block_arrives(fin.ticket)) {       // cross-rank: local sums -> exchange -> rank-ordered global sums
+    const int nblk = (int)gridDim.x, lane = threadIdx.x & 31;
+    float* mine = fin.stage;
+    float* all = fin.stage + 2 * 128;
+    for (int n = threadIdx.x >> 5; n < w; n += 8) {
+      float a = 0.f, b = 0.f;
+      for (int c = lane; c < nblk; c += 32) { a += __ldcg(part + ((size_t)c * 128 + n) * 2); b += __ldcg(part + ((size_t)c * 128 + n) * 2 + 1); }
+      a = warp_sum(a); b = warp_sum(b);
+      if (lane == 0) { mine[n] = a; mine[w + n] = b; }
+    }
+    __syncthreads();
+    peer_exchange(fin.comm, fin.slot, mine, 2 * w, all);
+    for (int i = threadIdx.x; i < 2 * w; i += 256) {
+      float sacc = 0.f;
+      for (int r = 0; r < fin.comm.world; ++r) sacc += all[(size_t)r * 2 * w + i];
+      fin.sums_global[i] = sacc;
+      if (fin.sums) fin.sums[i] = mine[i];
+    }
+  } else if (!fin.peer && fin.sums && last_block_arrives(fin.ticket)) {
     const int nblk = (int)gridDim.x;
     if (nblk <= 64) {          // few partials: a thread per column, block order
       if (threadIdx.x < w) {
@@ -838,9 +897,12 @@ static size_t mlp_scratch_floats(int B) {
   if (c > m) m = c;
   return m;
 }
-// partials, then 64 floats holding the last-block ticket (must be zero before the first call; every call leaves it zero)
-extern "C" size_t b200vae_mlp_scratch_bytes(int B) { return (mlp_scratch_floats(B) + 64) * sizeof(float); }
+// partials, then 64 floats holding the last-block ticket (must be zero before the first call; every call leaves it zero),
+// then the staging area of the fused cross-rank exchange (this rank's values + every rank's)
+constexpr size_t kMlpStageFloats = (size_t)(kPeerMaxWorld + 1) * 3 * 128;
+extern "C" size_t b200vae_mlp_scratch_bytes(int B) { return (mlp_scratch_floats(B) + 64 + kMlpStageFloats) * sizeof(float); }
 static unsigned* mlp_ticket(void* scratch, int B) { return reinterpret_cast<unsigned*>((float*)scratch + mlp_scratch_floats(B)); }
+static float* mlp_stage(void* scratch, int B) { return (float*)scratch + mlp_scratch_floats(B) + 64; }
 // one CTA finalising n outputs from `nparts` partials each: worth fusing while that is a few thousand loads per warp
 static bool fuse_finalize(long long nparts, long long n) { return nparts * n <= (long long)1 << 16; }
 
@@ -858,10 +920,12 @@ static int mlp_layer_fwd_impl(const float* in_y, const float* in_stats, const fl
   if (ci && co) ncta = narrow_grid(B);
   else if (rows) ncta = (B + kRowsRT - 1) / kRowsRT;
   // single GPU: the last CTA of the layer kernel finalises the statistics itself (no second launch)
-  const bool fused = stats_out && !comm && fuse_finalize(ncta, wo);
+  const bool fused = stats_out && fuse_finalize(ncta, wo);
   StatsFin fin;
   fin.stats = fused ? stats_out : nullptr; fin.running_mean = running_mean; fin.running_var = running_var; fin.eps = eps;
   fin.momentum = momentum; fin.ticket = mlp_ticket(scratch, B);
+  fin.peer = comm ? 1 : 0; fin.slot = slot; fin.stage = mlp_stage(scratch, B);
+  if (comm) fin.comm = make_peer(comm); else memset(&fin.comm, 0, sizeof(fin.comm));
   if (ci && co) {
     B200VAE_NARROW_DISPATCH(narrow_fwd_launch, ci, co, src, W, bias, B, wo, y_out, (float*)scratch, stats_out ? 1 : 0, fin, ncta, st);
   } else if (rows) {
@@ -912,10 +976,12 @@ static int mlp_layer_bwd_reduce_impl(const float* da, const float* y, const floa
   per = (per + 255) / 256 * 256;                       // keeps (element index % w) == (thread index % w)
   const ActSrc cur = make_src(y, stats, gamma, beta, w, slope);
   SumsFin fin;
-  fin.sums = comm ? nullptr : sums; fin.ticket = mlp_ticket(scratch, B);
+  fin.sums = sums; fin.ticket = mlp_ticket(scratch, B);
+  fin.peer = comm ? 1 : 0; fin.slot = slot; fin.sums_global = sums_global; fin.stage = mlp_stage(scratch, B);
+  if (comm) fin.comm = make_peer(comm); else memset(&fin.comm, 0, sizeof(fin.comm));
   mlp_bwd_reduce_kernel<<<nblk, 256, 0, st>>>(da, cur, stats ? 1 : 0, n, per, dyhat, (float*)scratch, fin);
   int rc = check_launch();
-  if (rc || fin.sums) return rc;
+  if (rc || fin.sums || fin.peer) return rc;
   if (comm)
     mlp_sum_finalize_peer_kernel<<<1, 1024, 0, st>>>((const float*)scratch, nblk, w, sums, sums_global, make_peer(comm), slot);
   else
