@@ -183,9 +183,17 @@ __device__ __forceinline__ void stats_finalize_column(const float* __restrict__ 
                                                       float* __restrict__ running_var, float momentum) {
   const int lane = threadIdx.x & 31;
   float cnt = 0.f, mean = 0.f, m2 = 0.f;
-  for (int c = lane; c < ncta; c += 32) {
-    const float* p = part + ((size_t)c * 128 + n) * 3;
-    chan_merge(cnt, mean, m2, __ldcg(p), __ldcg(p + 1), __ldcg(p + 2));
+  for (int c0 = lane; c0 < ncta; c0 += 4 * 32) {   // 4 partial triples per lane in flight per L2 round trip, merged in order
+    float pc[4], pm[4], pq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + 32 * j;
+      const bool in = c < ncta;
+      const float* p = part + ((size_t)(in ? c : c0) * 128 + n) * 3;
+      pc[j] = in ? __ldcg(p) : 0.f; pm[j] = in ? __ldcg(p + 1) : 0.f; pq[j] = in ? __ldcg(p + 2) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) chan_merge(cnt, mean, m2, pc[j], pm[j], pq[j]);     // a zero count is the identity
   }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -249,9 +257,16 @@ __device__ __forceinline__ void stats_finalize_block(const float* __restrict__ p
   if (ncta <= 64) {            // few partials (small batches): a THREAD per column, partials merged in CTA order
     for (int n = threadIdx.x; n < w; n += (int)blockDim.x) {
       float cnt = 0.f, mean = 0.f, m2 = 0.f;
-      for (int c = 0; c < ncta; ++c) {
-        const float* p = part + ((size_t)c * 128 + n) * 3;
-        chan_merge(cnt, mean, m2, __ldcg(p), __ldcg(p + 1), __ldcg(p + 2));
+      for (int c0 = 0; c0 < ncta; c0 += 8) {       // 8 partial triples in flight per L2 round trip, merged in CTA order
+        float pc[8], pm[8], pq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool in = c0 + j < ncta;
+          const float* p = part + ((size_t)(in ? c0 + j : c0) * 128 + n) * 3;
+          pc[j] = in ? __ldcg(p) : 0.f; pm[j] = in ? __ldcg(p + 1) : 0.f; pq[j] = in ? __ldcg(p + 2) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) chan_merge(cnt, mean, m2, pc[j], pm[j], pq[j]);   // a zero count is the identity
       }
       const float var = m2 / cnt;
       f.stats[n] = mean; f.stats[w + n] = var; f.stats[2 * w + n] = rsqrtf(var + f.eps); f.stats[3 * w + n] = cnt;
@@ -312,7 +327,11 @@ __device__ __forceinline__ void sums_finalize_column(const float* __restrict__ p
                                                      float* __restrict__ sums /*[2][w]*/) {
   const int lane = threadIdx.x & 31;
   float a = 0.f, b = 0.f;
-  for (int c = lane; c < nblk; c += 32) { a += __ldcg(part + ((size_t)c * 128 + n) * 2); b += __ldcg(part + ((size_t)c * 128 + n) * 2 + 1); }
+#pragma unroll 4
+  for (int c = lane; c < nblk; c += 32) {          // unrolled: four float2 loads per lane go out together
+    const float2 t = __ldcg(reinterpret_cast<const float2*>(part + ((size_t)c * 128 + n) * 2));
+    a += t.x; b += t.y;
+  }
   a = warp_sum(a); b = warp_sum(b);
   if (lane == 0) { sums[n] = a; sums[w + n] = b; }
 }
@@ -566,7 +585,8 @@ __device__ __forceinline__ void dw_finalize_block(const float* __restrict__ part
   if (nsplit <= 32) {
     for (int e = threadIdx.x; e < n; e += (int)blockDim.x) {
       float s = 0.f;
-      for (int c = 0; c < nsplit; ++c) s += __ldcg(part + (size_t)c * n + e);
+#pragma unroll 8
+      for (int c = 0; c < nsplit; ++c) s += __ldcg(part + (size_t)c * n + e);     // unrolled: the loads go out together
       dW[e] = s;
     }
   } else {
