@@ -307,6 +307,42 @@ def test_lidvae_mnist_constructs_and_trains_one_step():
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
 
 
+def test_inference_workspace_cache_follows_the_weights():
+    """decode under no_grad keeps the prepared ICNN workspace (exp(W) in every kernel layout) while the weights are unchanged;
+    every way this package changes weights must invalidate it: torch optimisers / copy_ (version counters), the fused Adam
+    kernel (raw pointers) and a CUDA-graph replay of the whole step (no Python runs)."""
+    from vae_song_b200 import _C, model, train
+    torch.manual_seed(0)
+    m = model.LIDVAE(dataset="pinwheel", icnn_channels=[32, 64], hidden_channels=[8, 4], inverse_lipschitz=0.2,
+                     precision="tf32x3").cuda()
+    z = torch.randn(64, 2, device="cuda")
+    x = torch.randn(256, 2, device="cuda")
+
+    def both():
+        with torch.no_grad():
+            a = m.decode(z)
+        b = m.decode(z.clone().requires_grad_(True)).detach()      # autograd path: prepares afresh every call
+        return a, b
+    a, b = both()
+    assert torch.equal(a, b)
+    n0 = _C.launch_count()
+    with torch.no_grad():
+        m.decode(z)
+    assert _C.launch_count() - n0 == 2                              # two decode kernels, no prepare launches
+    with torch.no_grad():
+        m.decoder[1].A0.weight.mul_(1.5)                            # in-place edit: version counter
+    a2, b2 = both()
+    assert torch.equal(a2, b2) and not torch.equal(a2, a)
+    tr = train.DataParallelTrainer(m, lr=1e-2)
+    tr.step(x)                                                      # fused Adam through raw pointers
+    a3, b3 = both()
+    assert torch.equal(a3, b3) and not torch.equal(a3, a2)
+    tr.capture(x)
+    tr.step_graphed(x)                                              # graph replay
+    a4, b4 = both()
+    assert torch.equal(a4, b4) and not torch.equal(a4, a3)
+
+
 def test_unmodified_reference_driver_runs_on_this_package():
     """Drop-in proof with the reference's OWN driver file: oracle/_ref/lipschitz.py (byte-identical copy of the reference,
     oracle/fetch_ref.py) is imported with `module`, `model`, `utils` bound to vae_song_b200's modules instead of the
@@ -440,6 +476,42 @@ def test_train_model_follows_the_reference_trajectory():
             assert np.array_equal(ours, ref), k
         else:      # 12 Adam steps amplify fp32 rounding differences of tiny gradients (update = lr * g/|g|): absolute floor
             np.testing.assert_allclose(ours, ref, rtol=2e-3, atol=2e-4, err_msg=k)
+
+
+def test_inference_workspace_cache_follows_the_weights():
+    """decode under no_grad keeps the prepared ICNN workspace (exp(W) in every kernel layout) while the weights are unchanged;
+    every way this package changes weights must invalidate it: torch optimisers / copy_ (version counters), the fused Adam
+    kernel (raw pointers) and a CUDA-graph replay of the whole step (no Python runs)."""
+    from vae_song_b200 import _C, model, train
+    torch.manual_seed(0)
+    m = model.LIDVAE(dataset="pinwheel", icnn_channels=[32, 64], hidden_channels=[8, 4], inverse_lipschitz=0.2,
+                     precision="tf32x3").cuda()
+    z = torch.randn(64, 2, device="cuda")
+    x = torch.randn(256, 2, device="cuda")
+
+    def both():
+        with torch.no_grad():
+            a = m.decode(z)
+        b = m.decode(z.clone().requires_grad_(True)).detach()      # autograd path: prepares afresh every call
+        return a, b
+    a, b = both()
+    assert torch.equal(a, b)
+    n0 = _C.launch_count()
+    with torch.no_grad():
+        m.decode(z)
+    assert _C.launch_count() - n0 == 2                              # two decode kernels, no prepare launches
+    with torch.no_grad():
+        m.decoder[1].A0.weight.mul_(1.5)                            # in-place edit: version counter
+    a2, b2 = both()
+    assert torch.equal(a2, b2) and not torch.equal(a2, a)
+    tr = train.DataParallelTrainer(m, lr=1e-2)
+    tr.step(x)                                                      # fused Adam through raw pointers
+    a3, b3 = both()
+    assert torch.equal(a3, b3) and not torch.equal(a3, a2)
+    tr.capture(x)
+    tr.step_graphed(x)                                              # graph replay
+    a4, b4 = both()
+    assert torch.equal(a4, b4) and not torch.equal(a4, a3)
 
 
 def test_unmodified_reference_driver_runs_on_this_package():

@@ -198,20 +198,37 @@ __global__ void __launch_bounds__(256)
 adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                 long long n, float lr0, float b1, float b2, float eps, float wd, const long long* __restrict__ step,
                 float gscale, int sched_kind, long long sched_T) {
-  const double t = (double)*step;
-  const float lr = sched_lr(lr0, sched_kind, sched_T, *step);
-  const float bc1 = (float)(1.0 - pow((double)b1, t));
-  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
-  const long long gstride = (long long)gridDim.x * blockDim.x;
-  const float step_size = lr / bc1;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
-    float gi = g[i] * gscale;
-    const float pi = p[i];
+  // bias corrections in fp64 (torch semantics) ONCE per block: a double-precision pow per thread was most of this kernel
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const double t = (double)*step;
+    const float lr = sched_lr(lr0, sched_kind, sched_T, *step);
+    s_step_size = lr / (float)(1.0 - pow((double)b1, t));
+    s_bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const long long gstride = (long long)gridDim.x * blockDim.x, tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= gscale;
     if (wd != 0.f) gi = fmaf(wd, pi, gi);
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi; v[i] = vi;
-    p[i] = pi - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    mi = b1 * mi + (1.f - b1) * gi;
+    vi = b2 * vi + (1.f - b2) * gi * gi;
+    pi = pi - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15u) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = tid0; i < n4; i += gstride) {           // 16-byte accesses (the flat buffers are 16-byte aligned)
+    float4 pi = reinterpret_cast<float4*>(p)[i], mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i];
+    const float4 gi = reinterpret_cast<const float4*>(g)[i];
+    upd(pi.x, gi.x, mi.x, vi.x); upd(pi.y, gi.y, mi.y, vi.y); upd(pi.z, gi.z, mi.z, vi.z); upd(pi.w, gi.w, mi.w, vi.w);
+    reinterpret_cast<float4*>(p)[i] = pi; reinterpret_cast<float4*>(m)[i] = mi; reinterpret_cast<float4*>(v)[i] = vi;
+  }
+  for (long long i = 4 * n4 + tid0; i < n; i += gstride) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(pi, g[i], mi, vi);
+    p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
 
@@ -284,7 +301,7 @@ extern "C" int b200vae_adam_step_dev(float* param, const float* grad, float* m, 
                                      float grad_scale, void* stream) {
   if (!param || !grad || !m || !v || !step_dev) return B200VAE_EALIGN;
   if (n <= 0) return B200VAE_ESHAPE;
-  long long blocks = (n + 255) / 256;
+  long long blocks = (n / 4 + 255) / 256 + 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
   adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
   int rc = check_launch();

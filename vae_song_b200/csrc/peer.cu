@@ -39,10 +39,14 @@ peer_reduce_adam_kernel(PtrList L, int world, int rank, long long lo4, long long
                         const long long* __restrict__ step, float gscale, const unsigned* __restrict__ dead) {
   // an exchange on this rank timed out (sticky flag): the gradients may be incomplete -> poison instead of a stale update
   const float poison = (*reinterpret_cast<const volatile unsigned*>(dead) != 0u) ? __int_as_float(0x7fc00000) : 0.f;
-  const double t = (double)*step;
-  const float bc1 = (float)(1.0 - pow((double)b1, t));
-  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
-  const float step_size = lr / bc1;
+  __shared__ float s_step_size, s_bc2_sqrt;      // fp64 bias corrections once per block, not a double pow per thread
+  if (threadIdx.x == 0) {
+    const double t = (double)*step;
+    s_step_size = lr / (float)(1.0 - pow((double)b1, t));
+    s_bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
   const long long gstride = (long long)gridDim.x * blockDim.x;
   for (long long i = lo4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += gstride) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);

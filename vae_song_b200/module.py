@@ -95,8 +95,14 @@ class ICNN(nn.Module):
         wide = self.in_channel > self.FUSED_MAX_D or (
             prec == _C.PREC_FP32 and input.dim() == 2 and input.shape[0] < self.FP32_TILED_BELOW
             and input.shape[1] == self.in_channel)
+        params = self._flat_params()
+        if not wide and not (torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in params))):
+            # inference: no graph, and the prepared workspace is reused while the weights are unchanged
+            if not hasattr(self, "_infer_cache"):
+                self._infer_cache = {}
+            return ops.icnn_brenier_inference(input, float(kappa), self._mode(), prec, params, self._infer_cache)
         fn = ops.IcnnBrenierWideFn if wide else ops.IcnnBrenierFn
-        return fn.apply(input, float(kappa), self._mode(), prec, *self._flat_params())
+        return fn.apply(input, float(kappa), self._mode(), prec, *params)
 
 
 class PlainConvolution(nn.Module):

@@ -78,6 +78,40 @@ def icnn_decode_bwd(z, v, gpsi, mask1, mask2, params, ws, d, H, mode, kappa, pre
     return dz, grads
 
 
+_weights_epoch = [0]
+
+
+def bump_weights_epoch():
+    """Called by everything in this package that changes parameters behind autograd's back (the fused Adam kernels write
+    through raw pointers, a CUDA-graph replay of a train step runs no Python at all): invalidates every cached
+    inference workspace.  Call it yourself after replaying your OWN graph that contains b200vae_adam_* launches."""
+    _weights_epoch[0] += 1
+
+
+def _param_state(params):
+    """Identity + in-place version of every parameter tensor (torch optimisers, copy_, load_state_dict, the re-homing of
+    train.FlatParams all change one of them) + this package's own weights epoch."""
+    return (_weights_epoch[0],) + tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params)
+
+
+def icnn_brenier_inference(z, kappa, mode, precision, params, cache):
+    """(psi, xhat) without an autograd graph -- evaluation loops (utils.estimate_local_lipschitz*, lipschitz.py's per-cell
+    sweeps, decode under no_grad).  The prepared workspace (positive weights in every kernel layout: 4 launches) is kept in
+    `cache` (a dict owned by the module) and reused while the parameters are unchanged (their `_version` counters and data
+    pointers), the batch size and the precision are the same; module.py:110 re-materialises exp(W) on every call instead."""
+    z = _req(z.detach(), "z")
+    params = [_req(p.detach(), k) for p, k in zip(params, PARAM_FIELDS)]
+    H, d = params[0].shape
+    if z.dim() != 2 or z.shape[1] != d:
+        raise _C.B200VaeError(f"z must be [B,{d}], got {tuple(z.shape)}")
+    key = (z.shape[0], mode, precision, z.device, torch.cuda.current_stream().cuda_stream, _param_state(params))
+    if cache.get("key") != key:
+        cache["ws"] = icnn_prepare(params, d, H, mode, precision, z.shape[0], False)
+        cache["key"] = key
+    psi, xhat, _, _ = icnn_decode_fwd(z, cache["ws"], d, H, mode, kappa, precision, True, True, False)
+    return psi, xhat
+
+
 class IcnnBrenierFn(torch.autograd.Function):
     """(psi [B], xhat [B,d]) = fused ICNN potential + Brenier map.  Replaces module.py:142-148 followed
     by model.py:820-822.  backward = the double-backward PyTorch would run through autograd.grad."""
@@ -800,6 +834,7 @@ def adam_step_(param, grad, m, v, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, w
     _C.check(_C.load().b200vae_adam_step(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), float(lr),
                                          float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
                                          float(grad_scale), _stream()), "adam_step")
+    bump_weights_epoch()
 
 
 def adam_step_dev_(param, grad, m, v, step_dev, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
@@ -807,6 +842,7 @@ def adam_step_dev_(param, grad, m, v, step_dev, lr=1e-3, betas=(0.9, 0.999), eps
     _C.check(_C.load().b200vae_adam_step_dev(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), float(lr),
                                              float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
                                              _ptr(step_dev), float(grad_scale), _stream()), "adam_step_dev")
+    bump_weights_epoch()
 
 
 def adam_step_sched_(param, grad, m, v, step_dev, lr0, betas, eps, weight_decay, grad_scale, sched_kind, sched_T):
@@ -816,6 +852,7 @@ def adam_step_sched_(param, grad, m, v, step_dev, lr0, betas, eps, weight_decay,
                                                float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
                                                _ptr(step_dev), float(grad_scale), int(sched_kind), int(sched_T), _stream()),
              "adam_step_sched")
+    bump_weights_epoch()
 
 
 def peer_allreduce_adam_(comm, slot, grad_buf, param_buf, m, v, n, step_dev, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
@@ -826,3 +863,4 @@ def peer_allreduce_adam_(comm, slot, grad_buf, param_buf, m, v, n, step_dev, lr=
     _C.check(lib.b200vae_peer_allreduce_adam(comm.ref, slot, grad_buf.ptr_array(), param_buf.ptr_array(), _ptr(_req(m, "m")),
                                              _ptr(_req(v, "v")), n, lr, betas[0], betas[1], eps, weight_decay,
                                              _ptr(step_dev), grad_scale, _stream()), "peer_allreduce_adam")
+    bump_weights_epoch()

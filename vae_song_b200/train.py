@@ -304,6 +304,7 @@ class DataParallelTrainer:
         if eps_local is not None:
             self._se.copy_(eps_local, non_blocking=True)
         self._graph.replay()
+        ops.bump_weights_epoch()          # the replayed Adam kernel changed the weights without any Python running
         self.t += 1
         self._poll()
         return self._sout
