@@ -541,7 +541,7 @@ def run_ours(args, rank, local_rank, world):
     by_prec_train = {args.precision: {"ms_per_step": ms, "samples_per_s": value}}
     if world == 1:
         import copy
-        for pname in ("fp32", "tf32x3", "tf32"):
+        for pname in ("fp32", "tf32x3", "f16x3", "tf32"):
             if pname == args.precision:
                 continue
             m2 = copy.deepcopy(m)
@@ -563,7 +563,7 @@ def run_ours(args, rank, local_rank, world):
         Bk = 65536
         z = torch.randn(Bk, 2, device=dev)
         byp = {}
-        for pname in ("fp32", "tf32x3", "tf32"):
+        for pname in ("fp32", "tf32x3", "f16x3", "tf32"):
             prec = _C.PRECISIONS[pname]
             res = {}
             for H in (512, 1024):
@@ -589,10 +589,14 @@ def run_ours(args, rank, local_rank, world):
             traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except Exception:
             traffic_tab = {}
-        mult_of = {"fp32": 1.0, "tf32": 1.0, "tf32x3": 2.5}   # executed / algorithmic flops (3 MMAs per MAC in GEMM1, 2 in GEMM2)
+        # executed / algorithmic flops (hi/lo operand splits: 3 MMAs per MAC in GEMM1, 2 in GEMM2)
+        mult_of = {"fp32": 1.0, "tf32": 1.0, "tf32x3": 2.5, "f16x3": 2.5}
+
+        def tensor_peak(pn):      # kind::f16 MMAs (f16x3) run at the bf16 rate, kind::tf32 at half of it
+            return 74.4 if pn == "fp32" else (pk["bf16_tflops"] if pn == "f16x3" else pk["bf16_tflops"] / 2)
 
         def kernel_roof(pn):
-            peak = 74.4 if pn == "fp32" else pk["bf16_tflops"] / 2
+            peak = tensor_peak(pn)
             ach = byp[pn]["tflops_H1024"]
             return {"bound": "fp32 fma pipe" if pn == "fp32" else "tensor", "precision": pn,
                     "kernel": f"icnn_decode_fwd (psi + grad psi), d=2, H=1024, B=65536, {pn}",
@@ -603,20 +607,22 @@ def run_ours(args, rank, local_rank, world):
                     "traffic_source": "static: one `ncu --set full` capture of this kernel committed under profiles/ "
                                       "(profiles/traffic.json), not re-measured in this run",
                     "peak_kind": "FP32 FMA peak 148 SM x 128 x 2 x 1.965 GHz" if pn == "fp32" else
-                                 f"{pk_kind} cuBLAS bf16 burst / 2 (TF32 runs at half the bf16 rate)"}
+                                 (f"{pk_kind} cuBLAS bf16 burst (kind::f16 MMAs on fp16 hi/lo operands run at the bf16 rate)"
+                                  if pn == "f16x3" else f"{pk_kind} cuBLAS bf16 burst / 2 (TF32 runs at half the bf16 rate)")}
         # `roofline` describes the dominant kernel IN THE ARITHMETIC THE TIMED STEP RAN IN (dtype of this line).  achieved /
         # frac count ALGORITHMIC flops (4H^2+8dH+2H+4d per sample); 3xTF32 executes 2.5 tensor flops per
         # algorithmic flop, so an fp32-grade kernel that keeps the tensor pipe full sits at frac ~0.4 and frac_executed ~1.
-        # No mode is both >= 0.9 of the tensor roofline and inside the FP32 bounds: `by_precision.tf32` is the >= 0.9 mode
-        # (bounds psi 2e-4 / xhat 5e-3), the step's tf32x3 is the fp32-grade mode (bounds in DESIGN.md section 4).
+        # f16x3 (fp16 hi/lo operands on kind::f16 MMAs, the default) executes the same 2.5 MMAs per MAC at twice the rate.
+        # No mode is both >= 0.9 ALGORITHMIC of the tensor roofline and inside the FP32 bounds: `by_precision.tf32` is the
+        # >= 0.9 mode (bounds psi 2e-4 / xhat 5e-3), f16x3 / tf32x3 are the fp32-grade modes (bounds in DESIGN.md section 4).
         rp = args.roofline_precision or args.precision
         roof = kernel_roof(rp)
         roof["algorithmic_flop_per_sample"] = vutils.flops_decode(2, 1024)
         roof["precision_equals_step_dtype"] = (rp == args.precision)
-        roof["by_precision"] = {pn: kernel_roof(pn) for pn in ("tf32", "tf32x3", "fp32")}
+        roof["by_precision"] = {pn: kernel_roof(pn) for pn in ("tf32", "f16x3", "tf32x3", "fp32")}
         step_flop = vutils.flops_train(2, 512) + vutils.flops_train(2, 1024)
         step_tf = step_flop * B / (ms * 1e-3) / 1e12
-        step_peak = 74.4 if args.precision == "fp32" else pk["bf16_tflops"] / 2
+        step_peak = tensor_peak(args.precision)
         roof["train_step"] = {"bound": roof["bound"], "precision": args.precision, "achieved": step_tf, "peak": step_peak,
                               "unit": "TFLOP/s", "frac": step_tf / step_peak, "algorithmic_flop_per_sample": step_flop,
                               "ms_per_step": ms, "note": "whole timed step (encoder, loss, Adam, exchange included in the time), "
@@ -821,12 +827,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="per-GPU batch")
-    ap.add_argument("--precision", default=os.environ.get("B200VAE_PRECISION", "tf32x3"), choices=["fp32", "tf32", "tf32x3"],
+    ap.add_argument("--precision", default=os.environ.get("B200VAE_PRECISION", "f16x3"), choices=["fp32", "tf32", "tf32x3", "f16x3"],
                     help="arithmetic of the H x H contractions in the train step (fp32 = SIMT parity path)")
     ap.add_argument("--comm", default="auto", choices=["auto", "peer", "nccl"],
                     help="multi-GPU exchange back-end (train.DataParallelTrainer): peer-memory kernels or NCCL")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--roofline-precision", default=None, choices=["fp32", "tf32", "tf32x3"],
+    ap.add_argument("--roofline-precision", default=None, choices=["fp32", "tf32", "tf32x3", "f16x3"],
                     help="precision of the kernel described by `roofline` (default: the step's --precision)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

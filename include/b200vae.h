@@ -41,6 +41,11 @@ extern "C" {
  * never built.  It is not coming back for the d <= 3 kernels -- they GENERATE their A operands, so halving the tensor time
  * per MAC would make operand generation the bound, at an 8-bit mantissa -- see DESIGN.md "Out of scope". */
 #define B200VAE_PREC_TF32X3 3 /* tcgen05 3xTF32 split (hi*hi + hi*lo + lo*hi): fp32-grade  */
+/* fp32-grade at half the tensor time of 3xTF32: both operands split into FP16 hi/lo pairs (22 mantissa bits, like a tf32
+ * pair), three tcgen05 kind::f16 MMAs per K step, every operand scaled by an exact power of two into the fp16 range (per
+ * tensor for the prepared weights, per sample row for the generated operands) and unscaled in the epilogue.  Same bounds as
+ * TF32X3 / FP32.  d <= 3 and H <= 1024 (the CTA-pair kernels); other shapes and the wide-input entry points run TF32X3. */
+#define B200VAE_PREC_F16X3 4
 
 /* Parameters of one module.ICNN(in_channel=d, hidden_channel=H) -- module.py:117-140.
  * Field <- state_dict key:  A0w<-A0.weight [H,d]  A0b<-A0.bias [H]  A1w<-A.0.weight [H,d]

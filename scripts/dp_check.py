@@ -117,7 +117,7 @@ if rank == 0:
 # ---- 3. timing on the bench workload --------------------------------------------------------------------------------------
 if "--time" in sys.argv:
     B = 65536
-    for prec in ("tf32x3", "tf32"):
+    for prec in ("f16x3", "tf32x3", "tf32"):
         for mode in ("nccl", "peer"):
             torch.manual_seed(1)
             m = model.LIDVAE(dataset="pinwheel", inverse_lipschitz=0.2, beta=1.0, precision=prec).to(dev).train()

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from vae_song_b200 import model, train, utils as vutils
-prec = sys.argv[1] if len(sys.argv) > 1 else "tf32x3"
+prec = sys.argv[1] if len(sys.argv) > 1 else "f16x3"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 torch.manual_seed(0)
 m = model.LIDVAE(inverse_lipschitz=0.2, beta=0.001, dataset="pinwheel", hidden_channels=[128, 64, 64, 32, 16, 8, 4, 2], precision=prec).cuda()

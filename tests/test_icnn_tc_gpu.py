@@ -1,9 +1,11 @@
-"""tcgen05 (TF32 / 3xTF32) variants of the fused ICNN forward and backward.
+"""tcgen05 (TF32 / 3xTF32 / 3xFP16) variants of the fused ICNN forward and backward.
 
 Bounds (vs the fp64 oracle on fp32-rounded inputs, |a-b| <= rtol*|b| + rtol*max|b|, NO fraction of elements exempted):
     tf32x3 : psi 1e-5, xhat 1e-5, parameter gradients / dz 1e-4  -- north_star's FP32 bounds.  fp32-grade operand split
              (3 MMAs per product) + K accumulated in chunks of 512 with round-to-nearest adds between chunks
              (icnn_tc3.cu; the tensor core's own accumulation truncates).
+    f16x3  : the same bounds.  Operands split into FP16 hi/lo pairs (22 mantissa bits like a tf32 pair), scaled by exact
+             powers of two into the fp16 range (per tensor / per sample row), three kind::f16 MMAs per K step.
     tf32   : psi 2e-4, xhat 5e-3, gradients 5e-3 (one MMA, operands rounded to 11 bits): the stated looser bound.
 Kink handling (helpers.py): where the kernels return their LeakyReLU masks, every mask bit that differs from the oracle's
 must belong to a unit whose pre-activation is inside the mode's rounding window (|h| < H_RTOL * max|h|) and xhat is then
@@ -19,8 +21,9 @@ from helpers import (H_RTOL, KEYS, check_decode_with_masks, close_report, close_
                      params_to_torch)
 
 pytestmark = pytest.mark.gpu
-BOUNDS = {3: (1e-5, 1e-5), 1: (2e-4, 5e-3)}          # precision -> (psi, xhat)
-GRAD_BOUND = {3: 1e-4, 1: 5e-3}
+BOUNDS = {4: (1e-5, 1e-5), 3: (1e-5, 1e-5), 1: (2e-4, 5e-3)}          # precision -> (psi, xhat)
+GRAD_BOUND = {4: 1e-4, 3: 1e-4, 1: 5e-3}
+PRECS, PREC_IDS = [4, 3, 1], ["f16x3", "tf32x3", "tf32"]
 # (d, H, B, regime, weight mode): ragged sizes, both weight reparameterisations (exp / clamp), and the two ICNN shapes of
 # BASELINE configs[1] (ICNN(2,512), ICNN(2,1024)) in the trained-like AND the default-init regime
 CASES = [(2, 256, 256, "mixed", 0), (2, 96, 77, "mixed", 0), (1, 64, 300, "mixed", 0), (3, 512, 1000, "mixed", 0),
@@ -28,7 +31,7 @@ CASES = [(2, 256, 256, "mixed", 0), (2, 96, 77, "mixed", 0), (1, 64, 300, "mixed
          (2, 256, 300, "clampy", 1), (3, 512, 200, "clampy", 1), (2, 1024, 256, "default", 1)]
 
 
-@pytest.mark.parametrize("prec", [3, 1], ids=["tf32x3", "tf32"])
+@pytest.mark.parametrize("prec", PRECS, ids=PREC_IDS)
 @pytest.mark.parametrize("case", CASES, ids=[f"d{c[0]}_h{c[1]}_b{c[2]}_{c[3]}_mode{c[4]}" for c in CASES])
 def test_tc_forward_vs_oracle(case, prec):
     from vae_song_b200 import ops
@@ -49,7 +52,7 @@ def test_tc_forward_vs_oracle(case, prec):
     assert torch.equal(psi2, psi) and torch.equal(xhat2, xhat)
 
 
-@pytest.mark.parametrize("prec", [3, 1], ids=["tf32x3", "tf32"])
+@pytest.mark.parametrize("prec", PRECS, ids=PREC_IDS)
 def test_tc_matches_fp32_path_and_backward_runs(prec):
     """Same module, precision switched: outputs agree with the FP32 kernels within the stated bound, and the
     training backward (masks from the tensor-core forward) matches the oracle evaluated with those masks'
@@ -88,7 +91,7 @@ def test_tc_full_size_tiling_invariance_and_sampled_rows_vs_oracle():
         p = io.random_params(rng, 2, H, np.float64, "mixed")
         params = params_to_torch(p)
         z = torch.tensor(rng.normal(0, 1, (65536, 2)), dtype=torch.float32, device="cuda")
-        for prec in (1, 3):
+        for prec in (1, 3, 4):
             psi, xhat = ops.IcnnBrenierFn.apply(z, 0.1, 0, prec, *params)
             sel = torch.arange(0, 65536, 256, device="cuda")
             psi_s, xhat_s = ops.IcnnBrenierFn.apply(z[sel].contiguous(), 0.1, 0, prec, *params)
@@ -163,7 +166,7 @@ np.savez(sys.argv[1], **out)
 BWD_CASES = [(1, 64, 300, 0), (2, 96, 77, 1), (3, 512, 1000, 0), (2, 1024, 600, 0), (2, 256, 256, 1)]
 
 
-@pytest.mark.parametrize("prec", [3, 1], ids=["tf32x3", "tf32"])
+@pytest.mark.parametrize("prec", PRECS, ids=PREC_IDS)
 @pytest.mark.parametrize("case", BWD_CASES, ids=[f"d{c[0]}_h{c[1]}_b{c[2]}_mode{c[3]}" for c in BWD_CASES])
 def test_tc_backward_vs_fp32_kernels_same_masks_and_vs_oracle(case, prec):
     """Tensor-core double-backward (persistent pair rows kernel + dP0 kernel) against the FP32 SIMT kernels fed the SAME
@@ -210,7 +213,7 @@ def test_tc_forward_workspace_reuse_and_mask_paths():
     d, H, B = 2, 512, 1111
     P = params_to_torch(io.random_params(rng, d, H, np.float64, "mixed"))
     z = torch.tensor(rng.normal(0, 1, (B, d)), dtype=torch.float32, device="cuda")
-    for prec in (1, 3):
+    for prec in (1, 3, 4):
         ws = ops.icnn_prepare(P, d, H, 0, prec, B, True)
         psi_a, xhat_a, m1, m2 = ops.icnn_decode_fwd(z, ws, d, H, 0, 0.1, prec, True, True, True)
         psi_b, xhat_b, _, _ = ops.icnn_decode_fwd(z, ws, d, H, 0, 0.1, prec, True, True, False)
@@ -222,10 +225,11 @@ def test_tc_forward_workspace_reuse_and_mask_paths():
         assert torch.equal(m2.bool(), psi_a > 0)
 
 
+@pytest.mark.parametrize("prec", [3, 4], ids=["tf32x3", "f16x3"])
 @pytest.mark.parametrize("shape", [(2, 512, 700), (3, 1024, 300), (1, 256, 1000), (2, 1024, 65536)],
                          ids=["d2_h512", "d3_h1024", "d1_h256", "d2_h1024_b65536"])
-def test_saved_accumulator_backward_equals_recompute(shape):
-    """3xTF32 training: the pair forward keeps its GEMM2 accumulators in the for_backward workspace and the backward reads
+def test_saved_accumulator_backward_equals_recompute(shape, prec):
+    """3xTF32 / 3xFP16 training: the pair forward keeps its GEMM2 accumulators in the for_backward workspace and the backward reads
     them back (icnn_tc3.cu SV kernels) instead of redoing that GEMM.  Re-running prepare on the workspace invalidates the
     save (host bookkeeping, api.cu), so the same backward then RECOMPUTES.  The saved accumulators come from the forward's
     K-chunked accumulation (chunks of 256 added with round-to-nearest FP32 adds, icnn_tc3.cu), the recomputed ones from one
@@ -241,12 +245,12 @@ def test_saved_accumulator_backward_equals_recompute(shape):
     v = torch.tensor(rng.normal(0, 1, (B, d)), dtype=torch.float32, device="cuda")
     res = []
     for invalidate in (False, True):
-        ws = ops.icnn_prepare(params, d, H, 0, 3, B, True)
-        psi, xhat, m1, m2 = ops.icnn_decode_fwd(z, ws, d, H, 0, 0.1, 3, True, True, True)
+        ws = ops.icnn_prepare(params, d, H, 0, prec, B, True)
+        psi, xhat, m1, m2 = ops.icnn_decode_fwd(z, ws, d, H, 0, 0.1, prec, True, True, True)
         if invalidate:      # same parameters, so nothing changes numerically -- but the saved accumulators are forgotten
             ps = ops._params_struct(params)
-            _C.check(_C.load().b200vae_icnn_prepare(C.byref(ps), d, H, 0, 3, ops._ptr(ws), ws.numel(), ops._stream()), "prepare")
-        dz, grads = ops.icnn_decode_bwd(z, v, None, m1, m2, params, ws, d, H, 0, 0.1, 3)
+            _C.check(_C.load().b200vae_icnn_prepare(C.byref(ps), d, H, 0, prec, ops._ptr(ws), ws.numel(), ops._stream()), "prepare")
+        dz, grads = ops.icnn_decode_bwd(z, v, None, m1, m2, params, ws, d, H, 0, 0.1, prec)
         torch.cuda.synchronize()
         res.append((xhat.clone(), dz.clone(), [g.clone() for g in grads]))
     assert torch.equal(res[0][0], res[1][0])
@@ -267,3 +271,39 @@ def test_saved_accumulator_backward_equals_recompute(shape):
     for k, g in zip(KEYS, res[0][2]):
         if np.abs(rg[k]).max() > 0:
             close_report(g.cpu().numpy(), rg[k], 1e-4, "grad " + k)
+
+
+@pytest.mark.parametrize("zscale,vscale", [(1e-3, 1e-6), (1.0, 1.5e-5), (300.0, 1e4), (1e-2, 1.0)],
+                         ids=["tiny_z_tiny_v", "unit_z_batchmean_v", "huge_z_huge_v", "small_z_unit_v"])
+def test_f16x3_is_scale_robust(zscale, vscale):
+    """FP16 has a 5-bit exponent: the 3xFP16 mode scales every operand by an exact power of two (per sample row for the
+    generated operands, per tensor for the prepared weights).  Inputs and cotangents far from 1 -- |z| ~ 1e-3 .. 3e2,
+    v ~ 1e-6 (a batch-mean loss at B = 65536) .. 1e4 -- and weights spread over e^{+-4} must meet the same FP32 bounds
+    relative to the size of the result."""
+    from vae_song_b200 import ops
+    from helpers import unpack_mask1
+    d, H, B, mode, prec = 2, 512, 600, 0, 4
+    rng = np.random.default_rng(int(zscale * 1e3) + 17)
+    p = io.random_params(rng, d, H, np.float64, "mixed")
+    p["W0"] = p["W0"] + rng.normal(0, 2.0, p["W0"].shape)          # exp(W) over ~4 decades
+    P = params_to_torch(p)
+    z = rng.normal(0, zscale, (B, d))
+    v = rng.normal(0, vscale, (B, d))
+    zt = torch.tensor(z, dtype=torch.float32, device="cuda")
+    vt = torch.tensor(v, dtype=torch.float32, device="cuda")
+    ws = ops.icnn_prepare(P, d, H, mode, prec, B, True)
+    psi, xhat, m1, m2 = ops.icnn_decode_fwd(zt, ws, d, H, mode, 0.15, prec, True, True, True)
+    assert torch.isfinite(psi).all() and torch.isfinite(xhat).all()
+    p64 = params_f32_as_f64(p)
+    check_decode_with_masks(psi, xhat, m1, m2, f32_as_f64(z), p64, mode, 0.15, 1e-5, 1e-5, H_RTOL[prec], f"scale {zscale}")
+    dz, g = ops.icnn_decode_bwd(zt, vt, None, m1, m2, P, ws, d, H, mode, 0.15, prec)
+    z64, v64 = zt.double().cpu().numpy(), vt.double().cpu().numpy()
+    km = (unpack_mask1(m1, H), m2.cpu().numpy().astype(bool))
+    _, _, aux = io.icnn_brenier(z64, p64, mode, 0.15, keep=True)
+    rdz, rg = io.icnn_brenier_backward(z64, v64, p64, mode, 0.15, None, masks=km)
+    h0_kink = (np.abs(aux["h0"]) < H_RTOL[0] * np.abs(aux["h0"]).max()).any(1)
+    close_rows(dz.cpu().numpy(), rdz, 1e-4, "dz vs oracle", h0_kink, loose=5e-2)
+    for k, a in zip(KEYS, g):
+        assert torch.isfinite(a).all(), k
+        if np.abs(rg[k]).max() > 0:
+            close_report(a.cpu().numpy(), rg[k], 1e-4, "grad vs oracle " + k)

@@ -57,7 +57,8 @@ def _decoder_kink_rows(m, z, h_rtol):
     return kink_rows(a0, h_rtol) | kink_rows(a1, h_rtol)
 
 
-@pytest.mark.parametrize("precision,rtol_y,rtol_g", [("fp32", 2e-5, 2e-4), ("tf32x3", 2e-5, 2e-4), ("tf32", 1e-2, 1e-2)])
+@pytest.mark.parametrize("precision,rtol_y,rtol_g", [("fp32", 2e-5, 2e-4), ("tf32x3", 2e-5, 2e-4), ("f16x3", 2e-5, 2e-4),
+                                                     ("tf32", 1e-2, 1e-2)])
 def test_lidvae_baseline_widths_vs_reference_golden(precision, rtol_y, rtol_g):
     """The BASELINE model itself -- LIDVAE(pinwheel) with the reference's default icnn_channels=[512,1024] (model.py:644)
     and default encoder -- against what the unmodified reference produced in fp64 (oracle/make_golden.py
@@ -78,7 +79,7 @@ def test_lidvae_baseline_widths_vs_reference_golden(precision, rtol_y, rtol_g):
     total.backward()
     close_report(mu.detach().cpu().numpy(), G["mu"], 2e-5, "mu")
     close_report(z.detach().cpu().numpy(), G["z"], 2e-5, "z")
-    prec_id = {"fp32": 0, "tf32x3": 3, "tf32": 1}[precision]
+    prec_id = {"fp32": 0, "tf32x3": 3, "f16x3": 4, "tf32": 1}[precision]
     kr = _decoder_kink_rows(m, z, 2 * H_RTOL[prec_id])
     close_rows(recon.detach().cpu().numpy(), G["recon"], rtol_y, "recon", kr, loose=5e-2)
     np.testing.assert_allclose([float(total), float(lrec), float(lreg)], G["loss"], rtol=10 * rtol_y)

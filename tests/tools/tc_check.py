@@ -31,9 +31,11 @@ def run(d, H, B, regime, prec, kappa=0.1, seed=0):
     return zt, ws
 
 if __name__ == "__main__":
-    names = {0: "fp32", 1: "tf32", 3: "tf32x3"}
+    names = {0: "fp32", 1: "tf32", 3: "tf32x3", 4: "f16x3"}
     fwd_only = "--fwd-only" in sys.argv
-    precs = (3, 1) if fwd_only else (0, 3, 1)
+    precs = (4, 3, 1) if fwd_only else (0, 4, 3, 1)
+    if "--precs" in sys.argv:
+        precs = tuple(int(x) for x in sys.argv[sys.argv.index("--precs") + 1].split(","))
     print("B200VAE_FWD =", os.environ.get("B200VAE_FWD", "3"))
     for prec in precs:
         for (d, H, B, regime) in ((2, 256, 256, "mixed"), (2, 96, 77, "mixed"), (3, 512, 1000, "mixed"), (2, 1024, 4096, "mixed"), (2, 1024, 512, "default")):

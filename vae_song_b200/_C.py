@@ -15,8 +15,8 @@ LIB_PATH = os.environ.get("B200VAE_LIB", os.path.join(_HERE, "libb200vae.so"))  
 CSRC = os.path.join(_HERE, "csrc")
 
 WEIGHT_EXP, WEIGHT_CLAMP = 0, 1
-PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 3          # 2 is reserved (include/b200vae.h)
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3}
+PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_F16X3 = 0, 1, 3, 4          # 2 is reserved (include/b200vae.h)
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3, "f16x3": PREC_F16X3}
 LOSS_OUT_FLOATS = 2048
 
 _ERR = {-1: "bad shape", -2: "unsupported configuration", -3: "null or misaligned pointer",

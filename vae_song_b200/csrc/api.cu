@@ -72,7 +72,7 @@ static size_t bwd_floats_without_save(int B, int d, int H, int precision) {
   return (L.end + (extra ? tc_bwd_ws_floats(B, d, H) : 0) + 63) / 64 * 64;
 }
 static size_t accsave_floats(int B, int d, int H, int precision) {
-  if (precision != B200VAE_PREC_TF32X3 || d > 3 || !save_enabled()) return 0;
+  if ((precision != B200VAE_PREC_TF32X3 && precision != B200VAE_PREC_F16X3) || d > 3 || !save_enabled()) return 0;
   const Tc3Layout T3 = tc3_layout(B, d, H);
   return (size_t)T3.Bp * T3.Hq + 64;
 }
@@ -88,7 +88,8 @@ static int shape_ok(int B, int d, int H) {
   return B200VAE_OK;
 }
 static bool prec_ok(int precision) {
-  return precision == B200VAE_PREC_FP32 || precision == B200VAE_PREC_TF32 || precision == B200VAE_PREC_TF32X3;   // 2 is reserved
+  return precision == B200VAE_PREC_FP32 || precision == B200VAE_PREC_TF32 || precision == B200VAE_PREC_TF32X3 ||
+         precision == B200VAE_PREC_F16X3;   // 2 is reserved
 }
 }  // namespace b200vae
 

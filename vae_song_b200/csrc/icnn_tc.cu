@@ -1008,7 +1008,7 @@ int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* 
   TcMaps maps;
   int rc = get_maps(tb, T, &maps);
   if (rc) return rc;
-  const bool x3 = (precision == B200VAE_PREC_TF32X3);
+  const bool x3 = (precision == B200VAE_PREC_TF32X3 || precision == B200VAE_PREC_F16X3);   // single-CTA kernels: 3xTF32 for both
   const int Hw_out = L.Hp / 32;
 #define B200VAE_TC(DD)                                                                                          \
   return x3 ? launch_tc<DD, true>(maps, z, B, T, tb, ws + L.A2p, Hw_out, kappa, psi, xhat, mask1, mask2, st)   \
@@ -1101,7 +1101,7 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
   float* partA = ws + L.end;
   float* partB = partA + nmt * 8 * (d + 1) * T.Hq;
   float* a2part = partB + nmt * 8 * (d + 1) * T.Hq;
-  const bool x3 = (precision == B200VAE_PREC_TF32X3);
+  const bool x3 = (precision == B200VAE_PREC_TF32X3 || precision == B200VAE_PREC_F16X3);   // single-CTA kernels: 3xTF32 for both
   const int Hw_in = L.Hp / 32;
   // rows part: persistent pair kernel (icnn_tc3.cu) unless B200VAE_BWD=1 or it does not fit (H > 1024)
   static const int variant = [] { const char* e = getenv("B200VAE_BWD"); return e ? atoi(e) : 3; }();

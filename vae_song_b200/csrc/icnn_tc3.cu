@@ -21,9 +21,24 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace b200vae {
+
+// Arithmetic of the pair kernels.  kTf32: one kind::tf32 MMA per product.  kX3: 3xTF32 (operands split tf32 hi/lo).
+// kF16: operands split into FP16 hi/lo pairs and fed to kind::f16 MMAs (a_lo.b_hi + a_hi.b_lo + a_hi.b_hi): an fp16 pair
+// carries 22 mantissa bits like a tf32 pair, but kind::f16 runs at twice the tf32 rate and the operand bytes halve, so
+// the fp32-grade contraction costs 1.5 instead of 3 tf32-MMA times.  FP16 has a 5-bit exponent, so every operand is
+// scaled by a power of two (exact) into the fp16 range and the accumulator is unscaled in the epilogue:
+//   * prepared B operands: one scale per tensor, from the tensor's maximum (tc3_rowmax_kernel), maximum -> [2^14, 2^15);
+//   * generated A operands: one scale per sample row, from an upper bound of the row's largest element computed from
+//     (z, v) and max |A0| -- the generator and the epilogue evaluate the same function (row_scale_*, explicit intrinsics
+//     so that both sites round identically).
+// An element more than 2^17 below its row / tensor maximum lands in the fp16 subnormal range and keeps an ABSOLUTE error
+// of 2^-25 (scaled units), i.e. < 2^-39 of the maximum: far below fp32 rounding of the sum.
+constexpr int kTf32 = 0, kX3 = 1, kF16 = 2;
 
 constexpr int k3Rows = 128;                       // sample rows per CTA
 constexpr int k3Threads = 18 * 32;                // 8 epilogue warps, 8 generator warps, TMA warp, MMA warp
@@ -67,6 +82,65 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, 
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(k3Idesc), "r"(acc) : "memory");
+}
+constexpr uint32_t k3IdescF16 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // A = B = F16, D = F32
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(k3IdescF16), "r"(acc) : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t acc) {
+  if (F16) umma_f16_pair(tmem_d, adesc, bdesc, acc);
+  else umma_tf32_pair(tmem_d, adesc, bdesc, acc);
+}
+// ---- FP16 hi/lo operands --------------------------------------------------------------------------------------------
+// (a, b) -> packed fp16 pairs: hi = rn16(x), lo = rn16(x - hi); a in the low half (lower address = lower k)
+__device__ __forceinline__ void split_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// two LeakyReLU bits (bit 0, bit 1 of w) -> packed fp16 (1.0 | 5.0, 1.0 | 5.0): 0x3C00 + 0x0900 = 0x4500
+__device__ __forceinline__ uint32_t pat2_f16(uint32_t w) { return 0x3C003C00u + ((w & 1u) | ((w & 2u) << 15)) * 0x0900u; }
+// biased exponent of a non-negative float, clamped
+__device__ __forceinline__ uint32_t bexp_of(float x, uint32_t lo, uint32_t hi) {
+  const uint32_t e = (__float_as_uint(x) >> 23) & 0xffu;
+  return min(max(e, lo), hi);
+}
+// upper bound of max_k |A0 z + b0|_k:  am = (max|A0w_0|, max|A0w_1|, max|A0w_2|, max|A0b|)
+template <int D>
+__device__ __forceinline__ float h0_bound(const float (&z)[D], const float4 am) {
+  float b = fmaf(am.x, fabsf(z[0]), am.w);
+  if (D > 1) b = fmaf(am.y, fabsf(z[D > 1 ? 1 : 0]), b);
+  if (D > 2) b = fmaf(am.z, fabsf(z[D > 2 ? 2 : 0]), b);
+  return b;
+}
+// GEMM1 rows: h0 is scaled by t = 2^(6 - floor(log2 bound)) so that x1 = leaky(h0)^2 t^2 < 2^14; inv = t^-2
+template <int D>
+__device__ __forceinline__ void row_scale_x1(const float (&z)[D], const float4 am, float& t, float& inv) {
+  const uint32_t e = bexp_of(h0_bound<D>(z, am), 70u, 196u);
+  t = __uint_as_float((260u - e) << 23);
+  inv = __uint_as_float((2u * e - 139u) << 23);
+}
+// backward B-units: q1 = 2 (A0 v) h0 s0^2 is bounded by (sum_j max|A0w_j| |2 v_j|) * bound(h0); t = 2^(13 - floor(log2 bound))
+template <int D>
+__device__ __forceinline__ void row_scale_q1(const float (&z)[D], const float (&v)[D], const float4 am, float& t, float& inv) {
+  float bu = __fmul_rn(am.x, fabsf(2.f * v[0]));
+  if (D > 1) bu = fmaf(am.y, fabsf(2.f * v[D > 1 ? 1 : 0]), bu);
+  if (D > 2) bu = fmaf(am.z, fabsf(2.f * v[D > 2 ? 2 : 0]), bu);
+  const uint32_t e = bexp_of(__fmul_rn(bu, h0_bound<D>(z, am)), 30u, 220u);
+  t = __uint_as_float((267u - e) << 23);
+  inv = __uint_as_float((e - 13u) << 23);
+}
+// tensor scale from the bit pattern of the tensor's maximum: maximum * s in [2^14, 2^15)
+__device__ __forceinline__ void tensor_scale(uint32_t maxbits, float& s, float& inv) {
+  const uint32_t e = min(max((maxbits >> 23) & 0xffu, 15u), 253u);
+  s = __uint_as_float((268u - e) << 23);
+  inv = __uint_as_float((e - 14u) << 23);
 }
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -129,13 +203,79 @@ __global__ void tc3_prepare_kernel(const float* __restrict__ P0, const float* __
     if (want_lo) B1alo[(size_t)r * K1 + c] = 0.f;
   }
 }
-// sumV[j] = sum_o E1[o].(y,z,w)[j]  (fixed order: one warp, strided partials then a shuffle tree)
-__global__ void tc3_sumv_kernel(const float4* __restrict__ E1, int Hq, float* __restrict__ sumV) {
-  float s[3] = {0.f, 0.f, 0.f};
-  for (int o = threadIdx.x; o < Hq; o += 32) { const float4 q = E1[o]; s[0] += q.y; s[1] += q.z; s[2] += q.w; }
+// sumV[j] = sum_o E1[o].(y,z,w)[j]  (fixed order: one warp, strided partials then a shuffle tree);
+// sumV[24..27] = (max |A0w_0|, max |A0w_1|, max |A0w_2|, max |A0b|) for the row scales of the FP16 mode
+__global__ void tc3_sumv_kernel(const float4* __restrict__ E1, const float4* __restrict__ A0g, int Hq, float* __restrict__ sumV) {
+  float s[3] = {0.f, 0.f, 0.f}, m[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int o = threadIdx.x; o < Hq; o += 32) {
+    const float4 q = E1[o];
+    s[0] += q.y; s[1] += q.z; s[2] += q.w;
+    const float4 w = A0g[o];                                 // generator order: a maximum does not care
+    m[0] = fmaxf(m[0], fabsf(w.x)); m[1] = fmaxf(m[1], fabsf(w.y)); m[2] = fmaxf(m[2], fabsf(w.z)); m[3] = fmaxf(m[3], fabsf(w.w));
+  }
 #pragma unroll
   for (int j = 0; j < 3; ++j) s[j] = warp_sum(s[j]);
-  if (threadIdx.x == 0) { sumV[0] = s[0]; sumV[1] = s[1]; sumV[2] = s[2]; sumV[3] = 0.f; }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) m[j] = warp_max(m[j]);
+  if (threadIdx.x == 0) {
+    sumV[0] = s[0]; sumV[1] = s[1]; sumV[2] = s[2]; sumV[3] = 0.f;
+    sumV[24] = m[0]; sumV[25] = m[1]; sumV[26] = m[2]; sumV[27] = m[3];
+  }
+}
+
+// ---- FP16 mode: the prepared B operands as fp16 hi/lo pairs, scaled per tensor ---------------------------------------
+// mx[0] = max P0, mx[1] = max_{o,i} (0.2 P1[o]) P0[o][i] as bit patterns (non-negative floats order like unsigned ints, and a
+// maximum is order independent: deterministic).  One block per output unit o; mx zeroed before the launch.
+__global__ void __launch_bounds__(256) tc3_rowmax_kernel(const float* __restrict__ P0, const float* __restrict__ P1, int Hp,
+                                                         uint32_t* __restrict__ mx) {
+  __shared__ float red[8];
+  const int o = blockIdx.x;
+  float m = 0.f;
+  for (int c = threadIdx.x; c < Hp; c += 256) m = fmaxf(m, P0[(size_t)o * Hp + c]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    atomicMax(mx, __float_as_uint(m));
+    atomicMax(mx + 1, __float_as_uint((kSlope * P1[o]) * m));
+  }
+}
+// grid (Hq/256, Hq): B1[o=r][i=c] = P[o][i] s1,  B2[i=r][o=c] = 0.2 P1[o] P[o][i] s2;  row 0 also packs the tables
+// (A0g in the FP16 generator order: unit 32kb + 8cc + e sits at 32kb + 4e + cc) and the scale constants scl = (s1, 1/s1, s2, 1/s2)
+__global__ void tc3_prepare_f16_kernel(const float* __restrict__ P0, const float* __restrict__ P0T, const float* __restrict__ P1,
+                                       const float* __restrict__ A0p, const float* __restrict__ A1p, int d, int Hp, int Hq,
+                                       const uint32_t* __restrict__ mx, __half* __restrict__ B1hi, __half* __restrict__ B1lo,
+                                       __half* __restrict__ B2hi, __half* __restrict__ B2lo, float4* __restrict__ A0g,
+                                       float4* __restrict__ E1, float* __restrict__ scl) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= Hq) return;
+  float s1, i1, s2, i2;
+  tensor_scale(mx[0], s1, i1);
+  tensor_scale(mx[1], s2, i2);
+  const bool in = r < Hp && c < Hp;
+  const float a = in ? P0[(size_t)r * Hp + c] * s1 : 0.f;
+  const float b = in ? ((kSlope * P1[c]) * P0T[(size_t)r * Hp + c]) * s2 : 0.f;
+  const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
+  B1hi[(size_t)r * Hq + c] = ah;
+  B1lo[(size_t)r * Hq + c] = __float2half_rn(a - __half2float(ah));
+  B2hi[(size_t)r * Hq + c] = bh;
+  B2lo[(size_t)r * Hq + c] = __float2half_rn(b - __half2float(bh));
+  if (r == 0) {
+    const bool inr = c < Hp;
+    float w[4] = {0.f, 0.f, 0.f, 0.f}, u[4] = {0.f, 0.f, 0.f, 0.f};
+    if (inr) {
+      const float p1 = P1[c];
+      for (int j = 0; j < d; ++j) { w[j] = A0p[(size_t)c * (d + 1) + j]; u[1 + j] = p1 * A1p[(size_t)c * (d + 1) + j]; }
+      w[3] = A0p[(size_t)c * (d + 1) + d];
+      u[0] = p1;
+    }
+    const int pos = (c & ~31) | ((c & 7) << 2) | ((c >> 3) & 3);
+    A0g[pos] = make_float4(w[0], w[1], w[2], w[3]);
+    E1[c] = make_float4(u[0], u[1], u[2], u[3]);
+    if (c == 0) { scl[0] = s1; scl[1] = i1; scl[2] = s2; scl[3] = i2; }
+  }
 }
 
 // ------------------------------------------------------------------------------------ the kernel
@@ -143,7 +283,9 @@ struct alignas(64) Tc3Args {
   CUtensorMap b1hi, b1lo, b2hi, b2lo;             // boxes of 16 x 128 (this CTA's half of a 256-row B tile)
   const float* z;
   const float4 *A0g, *E1, *A0q;
-  const float *sumV, *A2p;
+  const float4* A1q;                              // FP16 mode: (A1w0, A1w1, A1w2 | spare, A1b) per unit (TcLayout::A1q)
+  const float* P1q;                               // FP16 mode: P1 per unit (TcLayout::P1q)
+  const float *sumV, *A2p;                        // sumV[16..19] = (s1, 1/s1, s2, 1/s2), sumV[24..27] = max |A0| (FP16 mode)
   float *psi, *xhat;
   uint32_t* maskg;                                // mask1 of the caller or the internal scratch (null: psi-only, no masks)
   uint8_t* mask2;
@@ -152,22 +294,26 @@ struct alignas(64) Tc3Args {
   float* accsave;                                 // [T*256][Hq] GEMM2 accumulators (gx1 / s2) kept for the backward, or null
   float4* cscr;                                   // K-chunk running sums (Tc3Layout::cscr), used when NC > 1
   int B, Hq, T, NP, mask_stride, mask_rows, want_x;
-  int NC;                                         // K-chunks per unit (3xTF32: Hq / kTc3ChunkK; 1 = plain accumulation)
+  int NC;                                         // K-chunks per unit (hi/lo modes: Hq / kTc3ChunkK; 1 = plain accumulation)
   uint32_t park_ns;                               // suspend-time hint of the epilogue warps' accumulator waits
   float kappa;
 };
 
-template <bool X3>
+template <int MODE>
 struct Tc3Cfg {
-  static constexpr int S = X3 ? 2 : 4;                                    // stages of two 16-wide K-blocks
-  static constexpr int kSubBytes = (X3 ? 4 : 2) * k3TileBytes;            // one K-block: A(hi[,lo]) + B half (hi[,lo])
+  static constexpr bool HL = MODE != kTf32;                               // operands come as hi/lo pairs
+  static constexpr bool F16 = MODE == kF16;
+  static constexpr int KBE = F16 ? 32 : 16;                               // K elements per K-block (64-byte rows)
+  static constexpr int S = HL ? 2 : 4;                                    // stages of two K-blocks
+  static constexpr int kSubBytes = (HL ? 4 : 2) * k3TileBytes;            // one K-block: A(hi[,lo]) + B half (hi[,lo])
   static constexpr int kStageBytes = 2 * kSubBytes;
-  static constexpr int kOffAlo = k3TileBytes, kOffB = (X3 ? 2 : 1) * k3TileBytes, kOffBlo = 3 * k3TileBytes;
+  static constexpr int kOffAlo = k3TileBytes, kOffB = (HL ? 2 : 1) * k3TileBytes, kOffBlo = 3 * k3TileBytes;
 };
-template <bool X3>
+template <int MODE>
 static size_t tc3_smem_bytes(int Hq) {
-  using C = Tc3Cfg<X3>;
-  return (size_t)C::S * C::kStageBytes + (size_t)Hq * 48 + 2 * k3Rows * k3MaskStride * 4 + (2 * C::S + 4) * 8 + 64 + 1024;
+  using C = Tc3Cfg<MODE>;
+  return (size_t)C::S * C::kStageBytes + (size_t)Hq * (C::F16 ? 52 : 48) + 2 * k3Rows * k3MaskStride * 4 + (2 * C::S + 4) * 8 +
+         64 + 1024;
 }
 
 struct Unit { int g, t, p; };
@@ -181,19 +327,22 @@ __device__ __forceinline__ Unit decode_unit(int u, int T, int NP) {
   return x;
 }
 
-template <int D, bool X3>
+template <int D, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k3Threads, 1)
 icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
-  using C = Tc3Cfg<X3>;
+  using C = Tc3Cfg<MODE>;
   constexpr int S = C::S;
+  constexpr bool X3 = C::HL, F16 = C::F16;                                 // X3: hi/lo operands, three (two) MMAs per K step
+  constexpr int KBE = C::KBE;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stages = smem;
   const int Hq = a.Hq;
   float4* A0gs = reinterpret_cast<float4*>(smem + S * C::kStageBytes);     // generator order
-  float4* E1s = A0gs + Hq;
+  float4* E1s = A0gs + Hq;                                                 // FP16 mode: A1q = (A1w, A1b) instead
   float4* A0qs = E1s + Hq;
-  uint32_t* maskbuf = reinterpret_cast<uint32_t*>(A0qs + Hq);              // [2][128][36]
+  float* P1s = reinterpret_cast<float*>(A0qs + Hq);                        // FP16 mode only
+  uint32_t* maskbuf = reinterpret_cast<uint32_t*>(P1s + (F16 ? Hq : 0));   // [2][128][36]
   uint64_t* bars = reinterpret_cast<uint64_t*>(maskbuf + 2 * k3Rows * k3MaskStride);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
   volatile int* flags = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [0] finalize (epilogue), [1] prefetch ok (generators)
@@ -204,9 +353,12 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);     // provably warp-uniform role index
   const uint32_t rank = cluster_rank3();
   const int cid = (int)cluster_id3(), G = (int)num_clusters3();
-  const int T = a.T, NP = a.NP, NKB = Hq / kKB;
+  const int T = a.T, NP = a.NP, NKB = Hq / KBE;
   const int U = (a.want_x ? 2 : 1) * T * NP;
   const uint32_t target = (uint32_t)((a.want_x ? 2 : 1) * NP);
+  // FP16 mode: tensor scales of the prepared operands and max |A0| (row scales)
+  const float inv_s1 = F16 ? a.sumV[17] : 1.f, inv_s2 = F16 ? a.sumV[19] : 1.f;
+  const float4 amax = F16 ? make_float4(a.sumV[24], a.sumV[25], a.sumV[26], a.sumV[27]) : make_float4(0.f, 0.f, 0.f, 0.f);
 
   if (tid == 0) {
     // full: 4 generator warps (one group owns a whole stage) x 2 CTAs + the leader's 2 TMA arrivals (one per K-block)
@@ -218,7 +370,10 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
   }
-  for (int i = tid; i < Hq; i += k3Threads) { A0gs[i] = a.A0g[i]; E1s[i] = a.E1[i]; A0qs[i] = a.A0q[i]; }
+  for (int i = tid; i < Hq; i += k3Threads) {
+    A0gs[i] = a.A0g[i]; E1s[i] = F16 ? a.A1q[i] : a.E1[i]; A0qs[i] = a.A0q[i];
+    if (F16) P1s[i] = a.P1q[i];
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync3();                         // peer barriers initialised before any remote arrive / multicast commit
@@ -277,9 +432,15 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
       const int grow = un.t * 256 + (int)rank * k3Rows + row;
       const size_t sidx = ((size_t)grow * NP + un.p) * 2 + chalf;
       float zr[D];
-      if (un.g) {
+      if (un.g || F16) {
 #pragma unroll
         for (int j = 0; j < D; ++j) zr[j] = grow < a.B ? a.z[(size_t)grow * D + j] : 0.f;
+      }
+      float cinv = 1.f;                                       // FP16 mode, GEMM1: acc = h1 (without its affine part) / cinv
+      if (F16 && !un.g) {
+        float t_r, inv_x;
+        row_scale_x1<D>(zr, amax, t_r, inv_x);
+        cinv = inv_x * inv_s1;
       }
       mbar_wait_parked(accfull0 + 8 * buf, (i >> 1) & 1, a.park_ns);
       tc_fence_after();
@@ -309,15 +470,28 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
           uint32_t word = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float4 q = E1s[nb + j];                       // (P1, P1*A1w0, P1*A1w1, P1*A1w2)
-            const float h1 = __uint_as_float(r[j]);             // affine part included by the lin K-block
-            const bool pos = h1 > 0.f;
-            h2p = fmaf(q.x, fmaxf(h1, kSlope * h1), h2p);       // leaky(h) = max(h, 0.2 h)
-            if (pos) {
-              tp[0] += q.y;
-              if (D > 1) tp[1] += q.z;
-              if (D > 2) tp[2] += q.w;
-              word |= 1u << j;
+            if (F16) {
+              const float4 q = E1s[nb + j];                     // (A1w0, A1w1, A1w2 | spare, A1b)
+              const float p1 = P1s[nb + j];
+              const float h1 = fmaf(__uint_as_float(r[j]), cinv, lin_of<D>(q, zr));   // unscale, affine part in FP32
+              h2p = fmaf(p1, fmaxf(h1, kSlope * h1), h2p);
+              if (h1 > 0.f) {
+                tp[0] = fmaf(p1, q.x, tp[0]);
+                if (D > 1) tp[1] = fmaf(p1, q.y, tp[1]);
+                if (D > 2) tp[2] = fmaf(p1, q.z, tp[2]);
+                word |= 1u << j;
+              }
+            } else {
+              const float4 q = E1s[nb + j];                     // (P1, P1*A1w0, P1*A1w1, P1*A1w2)
+              const float h1 = __uint_as_float(r[j]);           // affine part included by the lin K-block
+              const bool pos = h1 > 0.f;
+              h2p = fmaf(q.x, fmaxf(h1, kSlope * h1), h2p);     // leaky(h) = max(h, 0.2 h)
+              if (pos) {
+                tp[0] += q.y;
+                if (D > 1) tp[1] += q.z;
+                if (D > 2) tp[2] += q.w;
+                word |= 1u << j;
+              }
             }
           }
           words[cc] = word;
@@ -336,6 +510,10 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
           uint32_t r[32];
           load_acc(r, cc);
           const int nb = un.p * 256 + chalf * 128 + cc * 32;
+          if (F16) {                             // undo the tensor scale of B2g
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * inv_s2);
+          }
           if (a.accsave != nullptr) {            // training: the backward reads this back instead of redoing GEMM2
             float* dst = a.accsave + (size_t)grow * Hq + nb;      // 128 contiguous bytes per thread: 4 x 256-bit stores
 #pragma unroll
@@ -449,71 +627,120 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
         for (int pr = 0; pr < 2; ++pr)
 #pragma unroll
           for (int j = 0; j < D; ++j) zp[pr][j] = make_float2(z4[2 * pr][j], z4[2 * pr + 1][j]);
-        int st = (int)((stg ^ (uint32_t)kh) & 1u);             // my first stage of this unit
-        for (; st < NST; st += 2) {
-          float v[2][4][4];
+        if constexpr (F16) {
+          // FP16 hi/lo operands: thread = 16-byte chunk c (8 consecutive k) of rows rb + 32r, both K-blocks of its stages.
+          // h0 is scaled per row by a power of two (exact): x1 t^2 < 2^14
+          float2 tq[2];
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub)
+          for (int pr = 0; pr < 2; ++pr) {
+            float t0, t1, iv;
+            row_scale_x1<D>(z4[2 * pr], amax, t0, iv);
+            row_scale_x1<D>(z4[2 * pr + 1], amax, t1, iv);
+            tq[pr] = make_float2(t0, t1);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float4 q = A0gs[(2 * st + sub) * kKB + e * 4 + c];
+            for (int j = 0; j < D; ++j) zp[pr][j] = __fmul2_rn(zp[pr][j], tq[pr]);
+          }
+          for (int st = (int)((stg ^ (uint32_t)kh) & 1u); st < NST; st += 2) {
 #pragma unroll
-              for (int pr = 0; pr < 2; ++pr) {
-                float2 h = __ffma2_rn(make_float2(q.x, q.x), zp[pr][0], make_float2(q.w, q.w));
-                if (D > 1) h = __ffma2_rn(make_float2(q.y, q.y), zp[pr][D > 1 ? 1 : 0], h);
-                if (D > 2) h = __ffma2_rn(make_float2(q.z, q.z), zp[pr][D > 2 ? 2 : 0], h);
-                const float2 l = __fmul2_rn(h, make_float2(kSlope, kSlope));
-                const float2 a0 = make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y));
-                const float2 x = __fmul2_rn(a0, a0);
-                v[sub][2 * pr][e] = x.x; v[sub][2 * pr + 1][e] = x.y;
+            for (int sub = 0; sub < 2; ++sub) {
+              float x[4][8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float4 q = A0gs[(2 * st + sub) * KBE + e * 4 + c];
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                  float2 h = __ffma2_rn(make_float2(q.x, q.x), zp[pr][0], __fmul2_rn(make_float2(q.w, q.w), tq[pr]));
+                  if (D > 1) h = __ffma2_rn(make_float2(q.y, q.y), zp[pr][D > 1 ? 1 : 0], h);
+                  if (D > 2) h = __ffma2_rn(make_float2(q.z, q.z), zp[pr][D > 2 ? 2 : 0], h);
+                  const float2 l = __fmul2_rn(h, make_float2(kSlope, kSlope));
+                  const float2 a0 = make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y));
+                  const float2 xx = __fmul2_rn(a0, a0);
+                  x[2 * pr][e] = xx.x; x[2 * pr + 1][e] = xx.y;
+                }
+              }
+              if (sub == 0) wait_stage(stg + st);
+              unsigned char* At = stage_ptr(stg + st) + sub * C::kSubBytes;
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                uint4 hi, lo;
+                split_f16(x[r][0], x[r][1], hi.x, lo.x);
+                split_f16(x[r][2], x[r][3], hi.y, lo.y);
+                split_f16(x[r][4], x[r][5], hi.z, lo.z);
+                split_f16(x[r][6], x[r][7], hi.w, lo.w);
+                *reinterpret_cast<uint4*>(At + r * 2048) = hi;
+                *reinterpret_cast<uint4*>(At + C::kOffAlo + r * 2048) = lo;
               }
             }
-          wait_stage(stg + st);
-          unsigned char* At = stage_ptr(stg + st);
+            publish(stg + st);
+          }
+          stg += NST;
+        } else {
+          int st = (int)((stg ^ (uint32_t)kh) & 1u);           // my first stage of this unit
+          for (; st < NST; st += 2) {
+            float v[2][4][4];
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub)
+            for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 q = A0gs[(2 * st + sub) * kKB + e * 4 + c];
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                  float2 h = __ffma2_rn(make_float2(q.x, q.x), zp[pr][0], make_float2(q.w, q.w));
+                  if (D > 1) h = __ffma2_rn(make_float2(q.y, q.y), zp[pr][D > 1 ? 1 : 0], h);
+                  if (D > 2) h = __ffma2_rn(make_float2(q.z, q.z), zp[pr][D > 2 ? 2 : 0], h);
+                  const float2 l = __fmul2_rn(h, make_float2(kSlope, kSlope));
+                  const float2 a0 = make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y));
+                  const float2 x = __fmul2_rn(a0, a0);
+                  v[sub][2 * pr][e] = x.x; v[sub][2 * pr + 1][e] = x.y;
+                }
+              }
+            wait_stage(stg + st);
+            unsigned char* At = stage_ptr(stg + st);
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                unsigned char* dst = At + sub * C::kSubBytes + r * 2048;
+                if (X3) {
+                  const float4 hi = make_float4(rn_tf32_masked(v[sub][r][0]), rn_tf32_masked(v[sub][r][1]),
+                                                rn_tf32_masked(v[sub][r][2]), rn_tf32_masked(v[sub][r][3]));
+                  *reinterpret_cast<float4*>(dst) = hi;
+                  *reinterpret_cast<float4*>(dst + C::kOffAlo) =
+                      make_float4(rn_tf32_fast(v[sub][r][0] - hi.x), rn_tf32_fast(v[sub][r][1] - hi.y),
+                                  rn_tf32_fast(v[sub][r][2] - hi.z), rn_tf32_fast(v[sub][r][3] - hi.w));
+                } else {
+                  *reinterpret_cast<float4*>(dst) = make_float4(rn_tf32_fast(v[sub][r][0]), rn_tf32_fast(v[sub][r][1]),
+                                                                rn_tf32_fast(v[sub][r][2]), rn_tf32_fast(v[sub][r][3]));
+                }
+              }
+            publish(stg + st);
+          }
+          if (st == NST) {
+            // last stage of the unit: the lin block in K-block 0; K-block 1 is a dummy the MMA warp skips
+            wait_stage(stg + st);
+            unsigned char* At = stage_ptr(stg + st);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-              unsigned char* dst = At + sub * C::kSubBytes + r * 2048;
-              if (X3) {
-                const float4 hi = make_float4(rn_tf32_masked(v[sub][r][0]), rn_tf32_masked(v[sub][r][1]),
-                                              rn_tf32_masked(v[sub][r][2]), rn_tf32_masked(v[sub][r][3]));
-                *reinterpret_cast<float4*>(dst) = hi;
-                *reinterpret_cast<float4*>(dst + C::kOffAlo) =
-                    make_float4(rn_tf32_fast(v[sub][r][0] - hi.x), rn_tf32_fast(v[sub][r][1] - hi.y),
-                                rn_tf32_fast(v[sub][r][2] - hi.z), rn_tf32_fast(v[sub][r][3] - hi.w));
-              } else {
-                *reinterpret_cast<float4*>(dst) = make_float4(rn_tf32_fast(v[sub][r][0]), rn_tf32_fast(v[sub][r][1]),
-                                                              rn_tf32_fast(v[sub][r][2]), rn_tf32_fast(v[sub][r][3]));
+              float col[16];
+#pragma unroll
+              for (int m = 0; m < 16; ++m) col[m] = 0.f;
+#pragma unroll
+              for (int j = 0; j < D; ++j) {
+                const float zh = rn_tf32_masked(z4[r][j]);
+                col[3 * j] = zh; col[3 * j + 1] = rn_tf32_masked(z4[r][j] - zh); col[3 * j + 2] = zh;
               }
+              col[3 * D] = 1.f; col[3 * D + 1] = 1.f;
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc)
+                if (cc == c) {
+                  *reinterpret_cast<float4*>(At + r * 2048) = make_float4(col[4 * cc], col[4 * cc + 1], col[4 * cc + 2], col[4 * cc + 3]);
+                  if (X3) *reinterpret_cast<float4*>(At + C::kOffAlo + r * 2048) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
-          publish(stg + st);
-        }
-        if (st == NST) {
-          // last stage of the unit: the lin block in K-block 0; K-block 1 is a dummy the MMA warp skips
-          wait_stage(stg + st);
-          unsigned char* At = stage_ptr(stg + st);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            float col[16];
-#pragma unroll
-            for (int m = 0; m < 16; ++m) col[m] = 0.f;
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-              const float zh = rn_tf32_masked(z4[r][j]);
-              col[3 * j] = zh; col[3 * j + 1] = rn_tf32_masked(z4[r][j] - zh); col[3 * j + 2] = zh;
-            }
-            col[3 * D] = 1.f; col[3 * D + 1] = 1.f;
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
-              if (cc == c) {
-                *reinterpret_cast<float4*>(At + r * 2048) = make_float4(col[4 * cc], col[4 * cc + 1], col[4 * cc + 2], col[4 * cc + 3]);
-                if (X3) *reinterpret_cast<float4*>(At + C::kOffAlo + r * 2048) = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
+            publish(stg + st);
           }
-          publish(stg + st);
+          stg += NST + 1;
         }
-        stg += NST + 1;
       } else {
         // ---------------- GEMM2: A = 1 + 4*bit (LeakyReLU slope / 0.2), exact in tf32 ----------------
         const int mb = n2 & 1;
@@ -540,19 +767,35 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
         if (prefetched) load_masks(decode_unit(u + G, T, NP).t, mb ^ 1);
         const uint32_t* mrow = maskbuf + mb * (k3Rows * k3MaskStride) + rb * k3MaskStride;
         for (int st = (int)((stg ^ (uint32_t)kh) & 1u); st < NST; st += 2) {
-          uint32_t w4[4];                                      // word st of my 4 rows: bits of K-blocks 2st (low half), 2st+1
+          if constexpr (F16) {
+            uint2 w2[4];                                       // words 2st, 2st+1 of my 4 rows = K-blocks 2st, 2st+1 (32 bits each)
 #pragma unroll
-          for (int r = 0; r < 4; ++r) w4[r] = mrow[r * 32 * k3MaskStride + st] >> (c * 4);
-          wait_stage(stg + st);
-          unsigned char* At = stage_ptr(stg + st);
+            for (int r = 0; r < 4; ++r) w2[r] = *reinterpret_cast<const uint2*>(mrow + r * 32 * k3MaskStride + 2 * st);
+            wait_stage(stg + st);
+            unsigned char* At = stage_ptr(stg + st);
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub)
+            for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              const uint32_t w = w4[r] >> (16 * sub);
-              *reinterpret_cast<float4*>(At + sub * C::kSubBytes + r * 2048) =
-                  make_float4((w & 1u) ? 5.f : 1.f, (w & 2u) ? 5.f : 1.f, (w & 4u) ? 5.f : 1.f, (w & 8u) ? 5.f : 1.f);
-            }
+              for (int r = 0; r < 4; ++r) {
+                const uint32_t w = (sub ? w2[r].y : w2[r].x) >> (c * 8);
+                *reinterpret_cast<uint4*>(At + sub * C::kSubBytes + r * 2048) =
+                    make_uint4(pat2_f16(w), pat2_f16(w >> 2), pat2_f16(w >> 4), pat2_f16(w >> 6));
+              }
+          } else {
+            uint32_t w4[4];                                    // word st of my 4 rows: bits of K-blocks 2st (low half), 2st+1
+#pragma unroll
+            for (int r = 0; r < 4; ++r) w4[r] = mrow[r * 32 * k3MaskStride + st] >> (c * 4);
+            wait_stage(stg + st);
+            unsigned char* At = stage_ptr(stg + st);
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const uint32_t w = w4[r] >> (16 * sub);
+                *reinterpret_cast<float4*>(At + sub * C::kSubBytes + r * 2048) =
+                    make_float4((w & 1u) ? 5.f : 1.f, (w & 2u) ? 5.f : 1.f, (w & 4u) ? 5.f : 1.f, (w & 8u) ? 5.f : 1.f);
+              }
+          }
           publish(stg + st);
         }
         stg += NST;
@@ -568,7 +811,7 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
       const Unit un = decode_unit(u, T, NP);
       const CUtensorMap* mhi = un.g ? &a.b2hi : &a.b1hi;
       const CUtensorMap* mlo = un.g ? &a.b2lo : &a.b1lo;
-      const int nreal = un.g ? NKB : NKB + 1, npad = (nreal + 1) & ~1;
+      const int nreal = (un.g || F16) ? NKB : NKB + 1, npad = (nreal + 1) & ~1;   // FP16 mode has no lin block
       const int rowc = un.p * 256 + (int)rank * k3Rows;
       for (int kb = 0; kb < npad; kb += 2, it += 2) {                  // one stage = two K-blocks
         const uint32_t s = (it >> 1) % S, ph = ((it >> 1) / S) & 1;
@@ -582,11 +825,11 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
             else mbar_arrive(full0 + 8 * s);
           }
           const uint32_t dst = smem_u32(stages + s * C::kStageBytes);
-          tma_load_2d_pair(dst + C::kOffB, mhi, bar, kb * kKB, rowc);
-          if (X3) tma_load_2d_pair(dst + C::kOffBlo, mlo, bar, kb * kKB, rowc);
+          tma_load_2d_pair(dst + C::kOffB, mhi, bar, kb * KBE, rowc);
+          if (X3) tma_load_2d_pair(dst + C::kOffBlo, mlo, bar, kb * KBE, rowc);
           if (real1) {
-            tma_load_2d_pair(dst + C::kSubBytes + C::kOffB, mhi, bar, (kb + 1) * kKB, rowc);
-            if (X3) tma_load_2d_pair(dst + C::kSubBytes + C::kOffBlo, mlo, bar, (kb + 1) * kKB, rowc);
+            tma_load_2d_pair(dst + C::kSubBytes + C::kOffB, mhi, bar, (kb + 1) * KBE, rowc);
+            if (X3) tma_load_2d_pair(dst + C::kSubBytes + C::kOffBlo, mlo, bar, (kb + 1) * KBE, rowc);
           }
         }
         __syncwarp();
@@ -602,7 +845,7 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
     int i = 0;
     for (int u = cid; u < U; u += G) {
       const Unit un = decode_unit(u, T, NP);
-      const int nreal = un.g ? NKB : NKB + 1, npad = (nreal + 1) & ~1;
+      const int nreal = (un.g || F16) ? NKB : NKB + 1, npad = (nreal + 1) & ~1;
       int kb = 0;
       const int nck = un.g ? 1 : NC;                                    // GEMM1 units only (see the epilogue warps)
       for (int ck = 0; ck < nck; ++ck, ++i) {                           // one accumulator per K-chunk
@@ -628,14 +871,14 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
                 if (X3) {
                   const uint64_t b_lo = a_hi + (uint64_t)(C::kOffBlo >> 4);
                   if (!un.g) {                                          // GEMM2's A operand is exact: no a_lo term
-                    umma_tf32_pair(d_t, a_hi + (uint64_t)(C::kOffAlo >> 4), b_hi, acc);
-                    umma_tf32_pair(d_t, a_hi, b_lo, 1u);
+                    umma_pair<F16>(d_t, a_hi + (uint64_t)(C::kOffAlo >> 4), b_hi, acc);
+                    umma_pair<F16>(d_t, a_hi, b_lo, 1u);
                   } else {
-                    umma_tf32_pair(d_t, a_hi, b_lo, acc);
+                    umma_pair<F16>(d_t, a_hi, b_lo, acc);
                   }
-                  umma_tf32_pair(d_t, a_hi, b_hi, 1u);
+                  umma_pair<F16>(d_t, a_hi, b_hi, 1u);
                 } else {
-                  umma_tf32_pair(d_t, a_hi, b_hi, acc);
+                  umma_pair<F16>(d_t, a_hi, b_hi, acc);
                 }
               }
             }
@@ -674,6 +917,8 @@ struct alignas(64) Tc3BwdArgs {
   const uint32_t* mask1;
   const uint8_t* mask2;
   const float4 *A0g, *E1, *A0q;
+  const float4* A1q;                              // FP16 mode: (A1w, A1b) per unit, read from global memory by the B-part
+  const float* sumV;                              // FP16 mode: scale constants (see Tc3Args)
   float *partA, *partB;
   float4* dzpart;
   const float* accsave;                           // SV kernels: the forward's GEMM2 accumulators [T*256][Hq]
@@ -709,11 +954,13 @@ __device__ __forceinline__ void fold8(float (&vals)[NV], int lane) {
 // all.  The unit list is then the B-units only; for each one the epilogue warps FIRST do the A-part of the same
 // (tile, pass) from global memory -- while the B-unit's MMAs are in flight -- and then drain the B accumulator.  At 3xTF32
 // the kernel is tensor bound, so dropping 2 of the 5 MMAs per element pair shortens it by ~40 %; HBM is idle anyway.
-template <int D, bool X3, bool SV>
+template <int D, int MODE, bool SV>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k3Threads, 1)
 icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
-  using C = Tc3Cfg<X3>;
+  using C = Tc3Cfg<MODE>;
   constexpr int S = C::S;
+  constexpr bool X3 = C::HL, F16 = C::F16;
+  constexpr int KBE = C::KBE;
   constexpr int NF = D + 1;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -732,8 +979,10 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const uint32_t rank = cluster_rank3();
   const int cid = (int)cluster_id3(), G = (int)num_clusters3();
-  const int T = a.T, NP = a.NP, NKB = Hq / kKB;
+  const int T = a.T, NP = a.NP, NKB = Hq / KBE;
   const int U = (SV ? 1 : 2) * T * NP;
+  const float inv_s1 = F16 ? a.sumV[17] : 1.f, inv_s2 = F16 ? a.sumV[19] : 1.f;
+  const float4 amax = F16 ? make_float4(a.sumV[24], a.sumV[25], a.sumV[26], a.sumV[27]) : make_float4(0.f, 0.f, 0.f, 0.f);
   auto unit_of = [&](int u) {
     if (SV) { Unit x; x.g = 1; x.t = u / NP; x.p = u - x.t * NP; return x; }
     return decode_unit(u, T, NP);
@@ -783,6 +1032,15 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
         mw[r] = (un.g && in && w0 < a.Hw_in) ? *reinterpret_cast<const uint4*>(a.mask1 + (size_t)gr * a.Hw_in + w0)
                                               : make_uint4(0u, 0u, 0u, 0u);
       }
+      float qinv[4] = {1.f, 1.f, 1.f, 1.f};                    // FP16 mode, B-part: P q1 = acc * qinv (row and tensor scales)
+      if (F16 && un.g) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float t_r, iv;
+          row_scale_q1<D>(zr[r], vr[r], amax, t_r, iv);
+          qinv[r] = iv * inv_s1;
+        }
+      }
       // one part of the unit: isB = B-unit maths (w1 column sums) else A-unit maths (t0, g0, dz);  from_global = the
       // accumulator comes from the forward's saved GEMM2 output instead of TMEM (SV kernels, A-part only)
       auto do_part = [&](const bool isB, const bool from_global) {
@@ -830,7 +1088,7 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
                 for (int r = 0; r < 4; ++r) {
                   const float acc = __uint_as_float((r < 2 ? ra : rb)[4 * n + 2 * (r & 1) + e]);
                   const float h0 = lin_of<D>(q, zr[r]), u0 = dot_of<D>(q, vr[r]);
-                  const float s2x2 = 2.f * s2r[r];
+                  const float s2x2 = (F16 && !from_global) ? (2.f * inv_s2) * s2r[r] : 2.f * s2r[r];   // (tensor scale of B2g)
                   const float mc = acc * (h0 > 0.f ? s2x2 : (kSlope * kSlope) * s2x2);   // 2 s2 s0^2 acc
                   const float t0 = mc * u0;                                               // u0 2 gx1 s0^2
 #pragma unroll
@@ -859,7 +1117,8 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
                   const float c1 = ((wd >> bitpos) & 1u) ? s2r[r] : kSlope * s2r[r];      // s2 s1
 #pragma unroll
                   for (int j = 0; j < D; ++j) ef[j] = fmaf(c1, vr[r][j], ef[j]);
-                  ef[D] = fmaf(c1, w1, ef[D]);
+                  // FP16 mode: the accumulator holds P q1 only (scaled); the A1 v part of w1 is added after the fold
+                  ef[D] = fmaf(F16 ? c1 * qinv[r] : c1, w1, ef[D]);
                 }
 #pragma unroll
                 for (int f = 0; f < NF; ++f) vals[(2 * n + e) * NF + f] = ef[f];
@@ -869,6 +1128,12 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
           const int cs = (lane >> 2) & 7;                          // my column slot after the fold
           const int col = nb + 8 * (cs >> 1) + cp2 + (cs & 1);
           const float p1 = isB ? E1s[col].x : 1.f;                 // dA1w carries P1 (g1 = s2 P1 s1)
+          if (F16 && isB) {                                        // sum_b s2 s1 (A1 v)[col] = sum_j A1w[col][j] sum_b s2 s1 v_j
+            const float4 q1w = a.A1q[col];
+            vals[D] = fmaf(q1w.x, vals[0], vals[D]);
+            if (D > 1) vals[D] = fmaf(q1w.y, vals[D > 1 ? 1 : 0], vals[D]);
+            if (D > 2) vals[D] = fmaf(q1w.z, vals[D > 2 ? 2 : 0], vals[D]);
+          }
 #pragma unroll
           for (int f = 0; f < NF; ++f) part[(size_t)f * Hq + col] = (f < D) ? vals[f] * p1 : vals[f];
         }
@@ -941,19 +1206,35 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
         if (prefetched) load_masks(decode_unit(u + G, T, NP).t, mb ^ 1);
         const uint32_t* mrow = maskbuf + mb * (k3Rows * k3MaskStride) + rb * k3MaskStride;
         for (int st = (int)((stg ^ (uint32_t)kh) & 1u); st < NST; st += 2) {
-          uint32_t w4[4];
+          if constexpr (F16) {
+            uint2 w2[4];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) w4[r] = mrow[r * 32 * k3MaskStride + st] >> (c * 4);
-          wait_stage(stg + st);
-          unsigned char* At = stage_ptr(stg + st);
+            for (int r = 0; r < 4; ++r) w2[r] = *reinterpret_cast<const uint2*>(mrow + r * 32 * k3MaskStride + 2 * st);
+            wait_stage(stg + st);
+            unsigned char* At = stage_ptr(stg + st);
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub)
+            for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              const uint32_t w = w4[r] >> (16 * sub);
-              *reinterpret_cast<float4*>(At + sub * C::kSubBytes + r * 2048) =
-                  make_float4((w & 1u) ? 5.f : 1.f, (w & 2u) ? 5.f : 1.f, (w & 4u) ? 5.f : 1.f, (w & 8u) ? 5.f : 1.f);
-            }
+              for (int r = 0; r < 4; ++r) {
+                const uint32_t w = (sub ? w2[r].y : w2[r].x) >> (c * 8);
+                *reinterpret_cast<uint4*>(At + sub * C::kSubBytes + r * 2048) =
+                    make_uint4(pat2_f16(w), pat2_f16(w >> 2), pat2_f16(w >> 4), pat2_f16(w >> 6));
+              }
+          } else {
+            uint32_t w4[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) w4[r] = mrow[r * 32 * k3MaskStride + st] >> (c * 4);
+            wait_stage(stg + st);
+            unsigned char* At = stage_ptr(stg + st);
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const uint32_t w = w4[r] >> (16 * sub);
+                *reinterpret_cast<float4*>(At + sub * C::kSubBytes + r * 2048) =
+                    make_float4((w & 1u) ? 5.f : 1.f, (w & 2u) ? 5.f : 1.f, (w & 4u) ? 5.f : 1.f, (w & 8u) ? 5.f : 1.f);
+              }
+          }
           publish(stg + st);
         }
         stg += NST;
@@ -977,76 +1258,129 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
             zp[pr][j] = make_float2(z4[2 * pr][j], z4[2 * pr + 1][j]);
             vp[pr][j] = make_float2(2.f * v4[2 * pr][j], 2.f * v4[2 * pr + 1][j]);
           }
-        int st = (int)((stg ^ (uint32_t)kh) & 1u);
-        for (; st < NST; st += 2) {
-          float vv[2][4][4];
+        if constexpr (F16) {
+          // FP16 hi/lo operands; q1 is scaled per row by a power of two (through v): |q1| t < 2^14
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub)
+          for (int pr = 0; pr < 2; ++pr) {
+            float t0, t1, iv;
+            row_scale_q1<D>(z4[2 * pr], v4[2 * pr], amax, t0, iv);
+            row_scale_q1<D>(z4[2 * pr + 1], v4[2 * pr + 1], amax, t1, iv);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float4 q = A0gs[(2 * st + sub) * kKB + e * 4 + c];
+            for (int j = 0; j < D; ++j) vp[pr][j] = __fmul2_rn(vp[pr][j], make_float2(t0, t1));
+          }
+          for (int st = (int)((stg ^ (uint32_t)kh) & 1u); st < NST; st += 2) {
 #pragma unroll
-              for (int pr = 0; pr < 2; ++pr) {
-                float2 h = __ffma2_rn(make_float2(q.x, q.x), zp[pr][0], make_float2(q.w, q.w));
-                float2 uu = __fmul2_rn(make_float2(q.x, q.x), vp[pr][0]);
-                if (D > 1) {
-                  h = __ffma2_rn(make_float2(q.y, q.y), zp[pr][D > 1 ? 1 : 0], h);
-                  uu = __ffma2_rn(make_float2(q.y, q.y), vp[pr][D > 1 ? 1 : 0], uu);
+            for (int sub = 0; sub < 2; ++sub) {
+              float x[4][8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float4 q = A0gs[(2 * st + sub) * KBE + e * 4 + c];
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                  float2 h = __ffma2_rn(make_float2(q.x, q.x), zp[pr][0], make_float2(q.w, q.w));
+                  float2 uu = __fmul2_rn(make_float2(q.x, q.x), vp[pr][0]);
+                  if (D > 1) {
+                    h = __ffma2_rn(make_float2(q.y, q.y), zp[pr][D > 1 ? 1 : 0], h);
+                    uu = __ffma2_rn(make_float2(q.y, q.y), vp[pr][D > 1 ? 1 : 0], uu);
+                  }
+                  if (D > 2) {
+                    h = __ffma2_rn(make_float2(q.z, q.z), zp[pr][D > 2 ? 2 : 0], h);
+                    uu = __ffma2_rn(make_float2(q.z, q.z), vp[pr][D > 2 ? 2 : 0], uu);
+                  }
+                  const float2 l = __fmul2_rn(h, make_float2(kSlope * kSlope, kSlope * kSlope));
+                  const float2 f0 = make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y));        // a0 s0 = h0 s0^2
+                  const float2 xx = __fmul2_rn(uu, f0);
+                  x[2 * pr][e] = xx.x; x[2 * pr + 1][e] = xx.y;
                 }
-                if (D > 2) {
-                  h = __ffma2_rn(make_float2(q.z, q.z), zp[pr][D > 2 ? 2 : 0], h);
-                  uu = __ffma2_rn(make_float2(q.z, q.z), vp[pr][D > 2 ? 2 : 0], uu);
-                }
-                const float2 l = __fmul2_rn(h, make_float2(kSlope * kSlope, kSlope * kSlope));
-                const float2 f0 = make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y));        // a0 s0 = h0 s0^2
-                const float2 x = __fmul2_rn(uu, f0);
-                vv[sub][2 * pr][e] = x.x; vv[sub][2 * pr + 1][e] = x.y;
+              }
+              if (sub == 0) wait_stage(stg + st);
+              unsigned char* At = stage_ptr(stg + st) + sub * C::kSubBytes;
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                uint4 hi, lo;
+                split_f16(x[r][0], x[r][1], hi.x, lo.x);
+                split_f16(x[r][2], x[r][3], hi.y, lo.y);
+                split_f16(x[r][4], x[r][5], hi.z, lo.z);
+                split_f16(x[r][6], x[r][7], hi.w, lo.w);
+                *reinterpret_cast<uint4*>(At + r * 2048) = hi;
+                *reinterpret_cast<uint4*>(At + C::kOffAlo + r * 2048) = lo;
               }
             }
-          wait_stage(stg + st);
-          unsigned char* At = stage_ptr(stg + st);
+            publish(stg + st);
+          }
+          stg += NST;
+        } else {
+          int st = (int)((stg ^ (uint32_t)kh) & 1u);
+          for (; st < NST; st += 2) {
+            float vv[2][4][4];
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub)
+            for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 q = A0gs[(2 * st + sub) * kKB + e * 4 + c];
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                  float2 h = __ffma2_rn(make_float2(q.x, q.x), zp[pr][0], make_float2(q.w, q.w));
+                  float2 uu = __fmul2_rn(make_float2(q.x, q.x), vp[pr][0]);
+                  if (D > 1) {
+                    h = __ffma2_rn(make_float2(q.y, q.y), zp[pr][D > 1 ? 1 : 0], h);
+                    uu = __ffma2_rn(make_float2(q.y, q.y), vp[pr][D > 1 ? 1 : 0], uu);
+                  }
+                  if (D > 2) {
+                    h = __ffma2_rn(make_float2(q.z, q.z), zp[pr][D > 2 ? 2 : 0], h);
+                    uu = __ffma2_rn(make_float2(q.z, q.z), vp[pr][D > 2 ? 2 : 0], uu);
+                  }
+                  const float2 l = __fmul2_rn(h, make_float2(kSlope * kSlope, kSlope * kSlope));
+                  const float2 f0 = make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y));        // a0 s0 = h0 s0^2
+                  const float2 x = __fmul2_rn(uu, f0);
+                  vv[sub][2 * pr][e] = x.x; vv[sub][2 * pr + 1][e] = x.y;
+                }
+              }
+            wait_stage(stg + st);
+            unsigned char* At = stage_ptr(stg + st);
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                unsigned char* dst = At + sub * C::kSubBytes + r * 2048;
+                if (X3) {
+                  const float4 hi = make_float4(rn_tf32_masked(vv[sub][r][0]), rn_tf32_masked(vv[sub][r][1]),
+                                                rn_tf32_masked(vv[sub][r][2]), rn_tf32_masked(vv[sub][r][3]));
+                  *reinterpret_cast<float4*>(dst) = hi;
+                  *reinterpret_cast<float4*>(dst + C::kOffAlo) =
+                      make_float4(rn_tf32_fast(vv[sub][r][0] - hi.x), rn_tf32_fast(vv[sub][r][1] - hi.y),
+                                  rn_tf32_fast(vv[sub][r][2] - hi.z), rn_tf32_fast(vv[sub][r][3] - hi.w));
+                } else {
+                  *reinterpret_cast<float4*>(dst) = make_float4(rn_tf32_fast(vv[sub][r][0]), rn_tf32_fast(vv[sub][r][1]),
+                                                                rn_tf32_fast(vv[sub][r][2]), rn_tf32_fast(vv[sub][r][3]));
+                }
+              }
+            publish(stg + st);
+          }
+          if (st == NST) {
+            wait_stage(stg + st);
+            unsigned char* At = stage_ptr(stg + st);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-              unsigned char* dst = At + sub * C::kSubBytes + r * 2048;
-              if (X3) {
-                const float4 hi = make_float4(rn_tf32_masked(vv[sub][r][0]), rn_tf32_masked(vv[sub][r][1]),
-                                              rn_tf32_masked(vv[sub][r][2]), rn_tf32_masked(vv[sub][r][3]));
-                *reinterpret_cast<float4*>(dst) = hi;
-                *reinterpret_cast<float4*>(dst + C::kOffAlo) =
-                    make_float4(rn_tf32_fast(vv[sub][r][0] - hi.x), rn_tf32_fast(vv[sub][r][1] - hi.y),
-                                rn_tf32_fast(vv[sub][r][2] - hi.z), rn_tf32_fast(vv[sub][r][3] - hi.w));
-              } else {
-                *reinterpret_cast<float4*>(dst) = make_float4(rn_tf32_fast(vv[sub][r][0]), rn_tf32_fast(vv[sub][r][1]),
-                                                              rn_tf32_fast(vv[sub][r][2]), rn_tf32_fast(vv[sub][r][3]));
+              float col[16];
+#pragma unroll
+              for (int m = 0; m < 16; ++m) col[m] = 0.f;
+#pragma unroll
+              for (int j = 0; j < D; ++j) {
+                const float vh = rn_tf32_masked(v4[r][j]);
+                col[3 * j] = vh; col[3 * j + 1] = rn_tf32_masked(v4[r][j] - vh); col[3 * j + 2] = vh;
               }
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc)
+                if (cc == c) {
+                  *reinterpret_cast<float4*>(At + r * 2048) = make_float4(col[4 * cc], col[4 * cc + 1], col[4 * cc + 2], col[4 * cc + 3]);
+                  if (X3) *reinterpret_cast<float4*>(At + C::kOffAlo + r * 2048) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
-          publish(stg + st);
-        }
-        if (st == NST) {
-          wait_stage(stg + st);
-          unsigned char* At = stage_ptr(stg + st);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            float col[16];
-#pragma unroll
-            for (int m = 0; m < 16; ++m) col[m] = 0.f;
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-              const float vh = rn_tf32_masked(v4[r][j]);
-              col[3 * j] = vh; col[3 * j + 1] = rn_tf32_masked(v4[r][j] - vh); col[3 * j + 2] = vh;
-            }
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
-              if (cc == c) {
-                *reinterpret_cast<float4*>(At + r * 2048) = make_float4(col[4 * cc], col[4 * cc + 1], col[4 * cc + 2], col[4 * cc + 3]);
-                if (X3) *reinterpret_cast<float4*>(At + C::kOffAlo + r * 2048) = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
+            publish(stg + st);
           }
-          publish(stg + st);
+          stg += NST + 1;
         }
-        stg += NST + 1;
       }
     }
     cp_async_wait_all();
@@ -1057,7 +1391,7 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
       const Unit un = unit_of(u);
       const CUtensorMap* mhi = un.g ? &a.b1hi : &a.b2hi;
       const CUtensorMap* mlo = un.g ? &a.b1lo : &a.b2lo;
-      const int nreal = un.g ? NKB + 1 : NKB, npad = (nreal + 1) & ~1;
+      const int nreal = (un.g && !F16) ? NKB + 1 : NKB, npad = (nreal + 1) & ~1;
       const int rowc = un.p * 256 + (int)rank * k3Rows;
       for (int kb = 0; kb < npad; kb += 2, it += 2) {
         const uint32_t s = (it >> 1) % S, ph = ((it >> 1) / S) & 1;
@@ -1071,11 +1405,11 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
             else mbar_arrive(full0 + 8 * s);
           }
           const uint32_t dst = smem_u32(stages + s * C::kStageBytes);
-          tma_load_2d_pair(dst + C::kOffB, mhi, bar, kb * kKB, rowc);
-          if (X3) tma_load_2d_pair(dst + C::kOffBlo, mlo, bar, kb * kKB, rowc);
+          tma_load_2d_pair(dst + C::kOffB, mhi, bar, kb * KBE, rowc);
+          if (X3) tma_load_2d_pair(dst + C::kOffBlo, mlo, bar, kb * KBE, rowc);
           if (real1) {
-            tma_load_2d_pair(dst + C::kSubBytes + C::kOffB, mhi, bar, (kb + 1) * kKB, rowc);
-            if (X3) tma_load_2d_pair(dst + C::kSubBytes + C::kOffBlo, mlo, bar, (kb + 1) * kKB, rowc);
+            tma_load_2d_pair(dst + C::kSubBytes + C::kOffB, mhi, bar, (kb + 1) * KBE, rowc);
+            if (X3) tma_load_2d_pair(dst + C::kSubBytes + C::kOffBlo, mlo, bar, (kb + 1) * KBE, rowc);
           }
         }
         __syncwarp();
@@ -1089,7 +1423,7 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
     for (int u = cid; u < U; u += G, ++i) {
       const Unit un = unit_of(u);
       const int buf = i & 1;
-      const int nreal = un.g ? NKB + 1 : NKB, npad = (nreal + 1) & ~1;
+      const int nreal = (un.g && !F16) ? NKB + 1 : NKB, npad = (nreal + 1) & ~1;
       mbar_wait(accempty0 + 8 * buf, ((i >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_t = tmem_base + (uint32_t)(buf * 256);
@@ -1110,14 +1444,14 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
               if (X3) {
                 const uint64_t b_lo = a_hi + (uint64_t)(C::kOffBlo >> 4);
                 if (un.g) {                                             // A-units' operand is exact: no a_lo term
-                  umma_tf32_pair(d_t, a_hi + (uint64_t)(C::kOffAlo >> 4), b_hi, acc);
-                  umma_tf32_pair(d_t, a_hi, b_lo, 1u);
+                  umma_pair<F16>(d_t, a_hi + (uint64_t)(C::kOffAlo >> 4), b_hi, acc);
+                  umma_pair<F16>(d_t, a_hi, b_lo, 1u);
                 } else {
-                  umma_tf32_pair(d_t, a_hi, b_lo, acc);
+                  umma_pair<F16>(d_t, a_hi, b_lo, acc);
                 }
-                umma_tf32_pair(d_t, a_hi, b_hi, 1u);
+                umma_pair<F16>(d_t, a_hi, b_hi, 1u);
               } else {
-                umma_tf32_pair(d_t, a_hi, b_hi, acc);
+                umma_pair<F16>(d_t, a_hi, b_hi, acc);
               }
             }
           }
@@ -1174,7 +1508,12 @@ tc3_bwd_dz_kernel(const float4* __restrict__ dzpart, const float* __restrict__ v
 typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_map3(CUtensorMap* m, const float* base, int K, int rows) {
+// arithmetic of the pair kernels for an ABI precision id: FP16 hi/lo where its tables fit in shared memory (Hq <= 1024)
+static int tc3_mode(int precision, int Hq) {
+  if (precision == B200VAE_PREC_F16X3) return tc3_smem_bytes<kF16>(Hq) <= (size_t)227 * 1024 ? kF16 : kX3;
+  return precision == B200VAE_PREC_TF32X3 ? kX3 : kTf32;
+}
+static int make_map3(CUtensorMap* m, const float* base, int K, int rows, bool f16 = false) {
   static EncodeTiledFn3 fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -1183,11 +1522,12 @@ static int make_map3(CUtensorMap* m, const float* base, int K, int rows) {
       fn = reinterpret_cast<EncodeTiledFn3>(p);
   }
   if (!fn) return B200VAE_ECUDA;
+  // 64-byte rows either way: 16 fp32 / 32 fp16 K elements x this CTA's 128 rows
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)k3Rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * (f16 ? sizeof(__half) : sizeof(float))};
+  const cuuint32_t box[2] = {(cuuint32_t)(f16 ? 32 : kKB), (cuuint32_t)k3Rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { g_last_cuda_error = 100000 + (int)r; return B200VAE_ECUDA; }
@@ -1200,14 +1540,30 @@ int tc3_prepare(int d, int H, int precision, float* ws, cudaStream_t st) {
   const TcLayout T = tc_layout(d, H);
   const Tc3Layout T3 = tc3_layout(1, d, H);
   float* t3 = tc_base(ws, d, H) + T.end;
-  const int want_lo = precision == B200VAE_PREC_TF32X3 ? 1 : 0;
-  dim3 grid((T3.K1 + 255) / 256, T3.Hq);
-  tc3_prepare_kernel<<<grid, 256, 0, st>>>(ws + L.P0, ws + L.P0T, ws + L.P1, ws + L.A0p, ws + L.A1p, d, L.Hp, T3.Hq, T3.K1,
-                                           want_lo, t3 + T3.B1ahi, t3 + T3.B1alo, t3 + T3.B2ghi, t3 + T3.B2glo,
-                                           reinterpret_cast<float4*>(t3 + T3.A0g), reinterpret_cast<float4*>(t3 + T3.E1));
-  int rc = check_launch();
+  const int mode = tc3_mode(precision, T3.Hq);
+  int rc;
+  if (mode == kF16) {
+    // the fp16 copies live in the (larger) fp32 operand regions: hi/lo of B1 [Hq][Hq], hi/lo of B2g [Hq][Hq]
+    uint32_t* mx = reinterpret_cast<uint32_t*>(t3 + T3.sumV + 8);
+    if (cudaMemsetAsync(mx, 0, 2 * sizeof(uint32_t), st) != cudaSuccess) return B200VAE_ECUDA;
+    tc3_rowmax_kernel<<<L.Hp, 256, 0, st>>>(ws + L.P0, ws + L.P1, L.Hp, mx);
+    rc = check_launch();
+    if (rc) return rc;
+    dim3 grid((T3.Hq + 255) / 256, T3.Hq);
+    tc3_prepare_f16_kernel<<<grid, 256, 0, st>>>(
+        ws + L.P0, ws + L.P0T, ws + L.P1, ws + L.A0p, ws + L.A1p, d, L.Hp, T3.Hq, mx, reinterpret_cast<__half*>(t3 + T3.B1ahi),
+        reinterpret_cast<__half*>(t3 + T3.B1alo), reinterpret_cast<__half*>(t3 + T3.B2ghi), reinterpret_cast<__half*>(t3 + T3.B2glo),
+        reinterpret_cast<float4*>(t3 + T3.A0g), reinterpret_cast<float4*>(t3 + T3.E1), t3 + T3.sumV + 16);
+  } else {
+    dim3 grid((T3.K1 + 255) / 256, T3.Hq);
+    tc3_prepare_kernel<<<grid, 256, 0, st>>>(ws + L.P0, ws + L.P0T, ws + L.P1, ws + L.A0p, ws + L.A1p, d, L.Hp, T3.Hq, T3.K1,
+                                             mode == kX3 ? 1 : 0, t3 + T3.B1ahi, t3 + T3.B1alo, t3 + T3.B2ghi, t3 + T3.B2glo,
+                                             reinterpret_cast<float4*>(t3 + T3.A0g), reinterpret_cast<float4*>(t3 + T3.E1));
+  }
+  rc = check_launch();
   if (rc) return rc;
-  tc3_sumv_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const float4*>(t3 + T3.E1), T3.Hq, t3 + T3.sumV);
+  tc3_sumv_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const float4*>(t3 + T3.E1), reinterpret_cast<const float4*>(t3 + T3.A0g),
+                                    T3.Hq, t3 + T3.sumV);
   rc = check_launch();
   if (rc) return rc;
   if (cudaMemsetAsync(t3 + T3.cnt, 0, (size_t)2 * kTc3MaxTiles * sizeof(uint32_t), st) != cudaSuccess) return B200VAE_ECUDA;
@@ -1215,18 +1571,20 @@ int tc3_prepare(int d, int H, int precision, float* ws, cudaStream_t st) {
 }
 
 struct Tc3Maps { CUtensorMap b1hi, b1lo, b2hi, b2lo; };
-static int get_maps3(const float* t3, const Tc3Layout& T3, bool x3, Tc3Maps* out) {
+static int get_maps3(const float* t3, const Tc3Layout& T3, int mode, Tc3Maps* out) {
   static std::mutex mu;
-  static std::unordered_map<uint64_t, Tc3Maps> cache;       // tensor maps only encode (address, shape)
+  static std::unordered_map<uint64_t, Tc3Maps> cache;       // tensor maps only encode (address, shape, element type)
   std::lock_guard<std::mutex> lk(mu);
-  const uint64_t key = reinterpret_cast<uint64_t>(t3) ^ ((uint64_t)T3.Hq << 48) ^ ((uint64_t)x3 << 63);
+  const uint64_t key = reinterpret_cast<uint64_t>(t3) ^ ((uint64_t)T3.Hq << 48) ^ ((uint64_t)mode << 62);
   auto itc = cache.find(key);
   if (itc != cache.end()) { *out = itc->second; return B200VAE_OK; }
   Tc3Maps mp;
-  int rc = make_map3(&mp.b1hi, t3 + T3.B1ahi, T3.K1, T3.Hq);
-  if (!rc) rc = make_map3(&mp.b1lo, t3 + (x3 ? T3.B1alo : T3.B1ahi), T3.K1, T3.Hq);
-  if (!rc) rc = make_map3(&mp.b2hi, t3 + T3.B2ghi, T3.Hq, T3.Hq);
-  if (!rc) rc = make_map3(&mp.b2lo, t3 + (x3 ? T3.B2glo : T3.B2ghi), T3.Hq, T3.Hq);
+  const bool hl = mode != kTf32, f16 = mode == kF16;
+  const int K1 = f16 ? T3.Hq : T3.K1;
+  int rc = make_map3(&mp.b1hi, t3 + T3.B1ahi, K1, T3.Hq, f16);
+  if (!rc) rc = make_map3(&mp.b1lo, t3 + (hl ? T3.B1alo : T3.B1ahi), K1, T3.Hq, f16);
+  if (!rc) rc = make_map3(&mp.b2hi, t3 + T3.B2ghi, T3.Hq, T3.Hq, f16);
+  if (!rc) rc = make_map3(&mp.b2lo, t3 + (hl ? T3.B2glo : T3.B2ghi), T3.Hq, T3.Hq, f16);
   if (rc) return rc;
   if (cache.size() > 256) cache.clear();
   cache.emplace(key, mp);
@@ -1538,7 +1896,8 @@ static int launch_tc3_dp0(const float* z, const float* v, const uint32_t* mask1,
 int tc3_dp0(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int Hq, int Hw_in,
             const float* A0q, int precision, int max_splits, float* part, int* splits_out, cudaStream_t st) {
   if (precision == 2 /* reserved */ || d > 3) return B200VAE_EUNSUP;
-  const bool x3 = (precision == B200VAE_PREC_TF32X3);
+  // both operands of this kernel are generated (nothing prepared): the FP16 mode runs the 3xTF32 instantiation
+  const bool x3 = (precision == B200VAE_PREC_TF32X3 || precision == B200VAE_PREC_F16X3);
   const float4* q = reinterpret_cast<const float4*>(A0q);
 #define B200VAE_TC3D(DD)                                                                                             \
   return x3 ? launch_tc3_dp0<DD, true>(z, v, mask1, mask2, B, Hq, Hw_in, q, max_splits, part, splits_out, st)         \
@@ -1552,15 +1911,15 @@ int tc3_dp0(const float* z, const float* v, const uint32_t* mask1, const uint8_t
 #undef B200VAE_TC3D
 }
 
-template <int D, bool X3, bool SV>
+template <int D, int MODE, bool SV>
 static int launch_tc3_bwd(const Tc3BwdArgs& args, cudaStream_t st) {
-  const size_t smem = tc3_smem_bytes<X3>(args.Hq);
+  const size_t smem = tc3_smem_bytes<MODE>(args.Hq);
   if (smem > 227 * 1024) return B200VAE_EUNSUP;
   static int max_clusters = 0;
-  if (max_clusters == 0) max_clusters = max_clusters_for(reinterpret_cast<const void*>(icnn_tc3_bwd_kernel<D, X3, SV>), smem);
+  if (max_clusters == 0) max_clusters = max_clusters_for(reinterpret_cast<const void*>(icnn_tc3_bwd_kernel<D, MODE, SV>), smem);
   const int units = (SV ? 1 : 2) * args.T * args.NP;
   const int G = units < max_clusters ? units : max_clusters;
-  icnn_tc3_bwd_kernel<D, X3, SV><<<2 * G, k3Threads, smem, st>>>(args);
+  icnn_tc3_bwd_kernel<D, MODE, SV><<<2 * G, k3Threads, smem, st>>>(args);
   return check_launch();
 }
 
@@ -1574,9 +1933,9 @@ int tc3_bwd_rows(const float* z, const float* v, const uint32_t* mask1, const ui
   const Tc3Layout T3 = tc3_layout(B, d, H);
   float* tb = tc_base(ws, d, H);
   float* t3 = tb + T.end;
-  const bool x3 = (precision == B200VAE_PREC_TF32X3);
+  const int mode = tc3_mode(precision, T3.Hq);
   Tc3Maps mp;
-  int rc = get_maps3(t3, T3, x3, &mp);
+  int rc = get_maps3(t3, T3, mode, &mp);
   if (rc) return rc;
   Tc3BwdArgs args;
   args.b1hi = mp.b1hi; args.b1lo = mp.b1lo; args.b2hi = mp.b2hi; args.b2lo = mp.b2lo;
@@ -1584,15 +1943,18 @@ int tc3_bwd_rows(const float* z, const float* v, const uint32_t* mask1, const ui
   args.A0g = reinterpret_cast<const float4*>(t3 + T3.A0g);
   args.E1 = reinterpret_cast<const float4*>(t3 + T3.E1);
   args.A0q = reinterpret_cast<const float4*>(tb + T.A0q);
+  args.A1q = reinterpret_cast<const float4*>(tb + T.A1q);
+  args.sumV = t3 + T3.sumV;
   args.partA = partA; args.partB = partB;
   args.dzpart = reinterpret_cast<float4*>(dzpart);
   args.accsave = accsave;
   args.B = B; args.Hq = T3.Hq; args.T = T3.Bp / 256; args.NP = T3.NP; args.Hw_in = L.Hp / 32;
   // the saved-accumulator kernels pay off where the kernel is tensor bound (3xTF32); at 1xTF32 the epilogue warps are the
   // bottleneck either way and recomputing GEMM2 is free
-#define B200VAE_TC3B(DD)                                                                                      \
-  rc = x3 ? (accsave ? launch_tc3_bwd<DD, true, true>(args, st) : launch_tc3_bwd<DD, true, false>(args, st)) \
-          : launch_tc3_bwd<DD, false, false>(args, st)
+#define B200VAE_TC3B(DD)                                                                                                  \
+  rc = mode == kF16 ? (accsave ? launch_tc3_bwd<DD, kF16, true>(args, st) : launch_tc3_bwd<DD, kF16, false>(args, st))    \
+       : mode == kX3 ? (accsave ? launch_tc3_bwd<DD, kX3, true>(args, st) : launch_tc3_bwd<DD, kX3, false>(args, st))     \
+                     : launch_tc3_bwd<DD, kTf32, false>(args, st)
   switch (d) {
     case 1: B200VAE_TC3B(1); break;
     case 2: B200VAE_TC3B(2); break;
@@ -1609,15 +1971,15 @@ size_t tc3_bwd_ws_floats(int B, int d, int H) {
   return (size_t)T3.Bp * T3.NP * 2 * 4 + 64;
 }
 
-template <int D, bool X3>
+template <int D, int MODE>
 static int launch_tc3(const Tc3Args& args, int units, cudaStream_t st) {
-  const size_t smem = tc3_smem_bytes<X3>(args.Hq);
+  const size_t smem = tc3_smem_bytes<MODE>(args.Hq);
   if (smem > 227 * 1024) return B200VAE_EUNSUP;
   static int max_clusters = 0;
-  if (max_clusters == 0) max_clusters = max_clusters_for(reinterpret_cast<const void*>(icnn_tc3_fwd_kernel<D, X3>), smem);
+  if (max_clusters == 0) max_clusters = max_clusters_for(reinterpret_cast<const void*>(icnn_tc3_fwd_kernel<D, MODE>), smem);
   // every cluster must be resident (GEMM2 units wait for GEMM1 units of other clusters): never exceed one wave
   const int G = units < max_clusters ? units : max_clusters;
-  icnn_tc3_fwd_kernel<D, X3><<<2 * G, k3Threads, smem, st>>>(args);
+  icnn_tc3_fwd_kernel<D, MODE><<<2 * G, k3Threads, smem, st>>>(args);
   return check_launch();
 }
 
@@ -1630,11 +1992,12 @@ int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float*
   if (T3.Bp / 256 > kTc3MaxTiles) return B200VAE_EUNSUP;
   float* tb = tc_base(ws, d, H);
   float* t3 = tb + T.end;
-  const bool x3 = (precision == B200VAE_PREC_TF32X3);
+  const int mode = tc3_mode(precision, T3.Hq);
+  const bool x3 = mode != kTf32;
   Tc3Args args;
   {
     Tc3Maps mp;
-    int rc = get_maps3(t3, T3, x3, &mp);
+    int rc = get_maps3(t3, T3, mode, &mp);
     if (rc) return rc;
     args.b1hi = mp.b1hi; args.b1lo = mp.b1lo; args.b2hi = mp.b2hi; args.b2lo = mp.b2lo;
   }
@@ -1642,6 +2005,8 @@ int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float*
   args.A0g = reinterpret_cast<const float4*>(t3 + T3.A0g);
   args.E1 = reinterpret_cast<const float4*>(t3 + T3.E1);
   args.A0q = reinterpret_cast<const float4*>(tb + T.A0q);
+  args.A1q = reinterpret_cast<const float4*>(tb + T.A1q);
+  args.P1q = tb + T.P1q;
   args.sumV = t3 + T3.sumV;
   args.A2p = ws + L.A2p;
   args.psi = psi; args.xhat = xhat; args.mask2 = mask2;
@@ -1654,15 +2019,20 @@ int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float*
   args.cnt = reinterpret_cast<uint32_t*>(t3 + T3.cnt);
   args.accsave = args.want_x ? accsave : nullptr;
   args.B = B; args.Hq = T3.Hq; args.T = T3.Bp / 256; args.NP = T3.NP; args.kappa = kappa;
-  // 3xTF32: accumulate K in chunks of kTc3ChunkK (B200VAE_KCHUNK overrides: a multiple of 32 dividing Hq; 0 = one chunk)
-  static const int chunk_k = [] { const char* e = getenv("B200VAE_KCHUNK"); return e ? atoi(e) : kTc3ChunkK; }();
+  // hi/lo modes: accumulate K in chunks of kTc3ChunkK (B200VAE_KCHUNK overrides: a multiple of 64 dividing Hq; 0 = one
+  // chunk).  FP16 mode at H = 1024, default-init weights: psi error 8.7e-6 in one piece (0.459 ms), 4.0e-6 in two chunks
+  // (0.49 ms, wherever the split point lies -- 512 ... 768 measured), 2.0e-6 in four (0.544 ms)
+  static const int chunk_env = [] { const char* e = getenv("B200VAE_KCHUNK"); return e ? atoi(e) : -1; }();
+  const int chunk_k = chunk_env >= 0 ? chunk_env : kTc3ChunkK;
   static const int park_ns = [] { const char* e = getenv("B200VAE_PARK_NS"); return e ? atoi(e) : 2000; }();
   args.cscr = reinterpret_cast<float4*>(t3 + T3.cscr);
   args.park_ns = (uint32_t)park_ns;
   args.NC = 1;
-  if (x3 && chunk_k >= 32 && chunk_k % 32 == 0 && T3.Hq % chunk_k == 0) args.NC = T3.Hq / chunk_k;
+  if (x3 && chunk_k >= 64 && chunk_k % 64 == 0 && T3.Hq % chunk_k == 0) args.NC = T3.Hq / chunk_k;
   const int units = (args.want_x ? 2 : 1) * args.T * args.NP;
-#define B200VAE_TC3(DD) return x3 ? launch_tc3<DD, true>(args, units, st) : launch_tc3<DD, false>(args, units, st)
+#define B200VAE_TC3(DD)                                                       \
+  return mode == kF16 ? launch_tc3<DD, kF16>(args, units, st)                 \
+         : mode == kX3 ? launch_tc3<DD, kX3>(args, units, st) : launch_tc3<DD, kTf32>(args, units, st)
   switch (d) {
     case 1: B200VAE_TC3(1);
     case 2: B200VAE_TC3(2);

@@ -612,6 +612,7 @@ extern "C" int b200vae_icnn_wide_fwd(const float* z, int B, int d, int nz, int H
   if (!z || !wide_params_ok(p) || !h0 || !mask1 || !s2 || !workspace || (xhat && !g0)) return B200VAE_EALIGN;
   if (B <= 0 || d <= 0 || H <= 0 || nz <= 0 || nz > d) return B200VAE_ESHAPE;
   if (weight_mode != B200VAE_WEIGHT_EXP && weight_mode != B200VAE_WEIGHT_CLAMP) return B200VAE_EUNSUP;
+  if (precision == B200VAE_PREC_F16X3) precision = B200VAE_PREC_TF32X3;   // the wide kernels read their operands from HBM: no fp16 variant
   if (precision < B200VAE_PREC_FP32 || precision > B200VAE_PREC_TF32X3 || precision == 2 /* reserved */) return B200VAE_EUNSUP;
   const WideWs L = wide_layout(B, d, H, false);
   if (ws_bytes < b200vae_icnn_wide_workspace_bytes(B, d, H, precision, 0)) return B200VAE_EWS;
@@ -655,6 +656,7 @@ extern "C" int b200vae_icnn_wide_bwd(const float* z, const float* v, const float
   if (!z || !v || !h0 || !mask1 || !s2 || !wide_params_ok(p) || !u0 || !q1 || !g0 || !t0 || !workspace) return B200VAE_EALIGN;
   if (B <= 0 || d <= 0 || H <= 0 || nz <= 0 || nz > d) return B200VAE_ESHAPE;
   if (weight_mode != B200VAE_WEIGHT_EXP && weight_mode != B200VAE_WEIGHT_CLAMP) return B200VAE_EUNSUP;
+  if (precision == B200VAE_PREC_F16X3) precision = B200VAE_PREC_TF32X3;   // the wide kernels read their operands from HBM: no fp16 variant
   if (precision < B200VAE_PREC_FP32 || precision > B200VAE_PREC_TF32X3 || precision == 2 /* reserved */) return B200VAE_EUNSUP;
   const WideWs L = wide_layout(B, d, H, true);
   if (ws_bytes < b200vae_icnn_wide_workspace_bytes(B, d, H, precision, 1)) return B200VAE_EWS;

@@ -192,7 +192,7 @@ def build_parser():
     p.add_argument("--wu_start_epoch", type=int, default=0)
     p.add_argument("--wu_up_amount", type=float, default=None)
     p.add_argument("--wu_repeat_interval", type=int, default=10)
-    p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "tf32x3", "tf32"],
+    p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "f16x3", "tf32x3", "tf32"],
                    help="arithmetic of the ICNN contractions (extension; fp32 = the parity path)")
     return p
 

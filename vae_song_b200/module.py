@@ -39,7 +39,8 @@ class ICNN(nn.Module):
     forward(z) -> psi [B,1], twice differentiable in z (so the reference idiom
     ``autograd.grad(icnn(z), [z], ones, create_graph=True)`` keeps working);
     brenier(z, kappa) -> (psi [B], grad_z(psi + kappa|z|^2) [B,d]) in ONE fused kernel.
-    ``precision`` selects the arithmetic of the H x H contractions: fp32 (parity), tf32x3 (fp32-grade, tensor cores), tf32."""
+    ``precision`` selects the arithmetic of the H x H contractions: fp32 (parity), f16x3 / tf32x3 (fp32-grade, tensor
+    cores: fp16 / tf32 hi-lo operand pairs, three MMAs per product; f16x3 runs at twice the MMA rate), tf32."""
 
     def __init__(self, in_channel, hidden_channel=128, num_layers=2, precision="fp32"):
         super().__init__()
@@ -88,7 +89,7 @@ class ICNN(nn.Module):
         """(psi [B], xhat [B,d]).  For wide ICNNs `input` may be [B,nz] with nz < d: zero-padded to d inside the kernels.
 
         Kernel choice: d > 4 -> the wide-input kernels (tcgen05 or FP32 tile GEMMs).  d <= 4: the fused sample-stationary
-        kernels (tcgen05 pair kernels for tf32 / tf32x3; FP32 SIMT for fp32) -- except FP32 at small batches, where one CTA
+        kernels (tcgen05 pair kernels for tf32 / tf32x3 / f16x3; FP32 SIMT for fp32) -- except FP32 at small batches, where one CTA
         per 128 samples would leave most of the 148 SMs idle (a batch-256 step ran on 2 SMs): those go through the FP32
         tile-GEMM chain of csrc/icnn_wide.cu, which tiles over the hidden width as well (same arithmetic, same bounds)."""
         prec = self._prec()

@@ -227,8 +227,8 @@ def icnn_wide_fwd(z, params, mode, kappa, want_xhat=True, precision=0):
     B, nz = z.shape
     H, d = params[0].shape
     dev = z.device
-    if precision not in (_C.PREC_FP32, _C.PREC_TF32, _C.PREC_TF32X3):
-        raise _C.B200VaeError(f"unknown precision id {precision}; use fp32, tf32x3 or tf32")
+    if precision not in (_C.PREC_FP32, _C.PREC_TF32, _C.PREC_TF32X3, _C.PREC_F16X3):
+        raise _C.B200VaeError(f"unknown precision id {precision}; use fp32, f16x3, tf32x3 or tf32")
     ws = torch.empty(lib.b200vae_icnn_wide_workspace_bytes(B, d, H, precision, 0), dtype=torch.uint8, device=dev)
     psi = torch.empty(B, dtype=torch.float32, device=dev)
     h0 = torch.empty(B, H, dtype=torch.float32, device=dev)
