@@ -1037,7 +1037,7 @@ int tc3_bwd_rows(const float* z, const float* v, const uint32_t* mask1, const ui
                  const float* accsave, cudaStream_t st);
 size_t tc3_bwd_ws_floats(int B, int d, int H);
 int tc3_dp0(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int Hq, int Hw_in,
-            const float* A0q, int precision, int max_splits, float* part, int* splits_out, cudaStream_t st);
+            const float* A0q, const float* sumV, int precision, int max_splits, float* part, int* splits_out, cudaStream_t st);
 
 size_t tc_bwd_ws_floats(int B, int d, int H) {
   const TcLayout T = tc_layout(d, H);
@@ -1133,7 +1133,8 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
     static const int dp_variant = [] { const char* e = getenv("B200VAE_DP0"); return e ? atoi(e) : 3; }();
     rc = B200VAE_EUNSUP;
     if (dp_variant == 3)
-      rc = tc3_dp0(z, v, mask1, mask2, B, d, T.Hq, Hw_in, tb + T.A0q, precision, splits, part, &splits, st);
+      rc = tc3_dp0(z, v, mask1, mask2, B, d, T.Hq, Hw_in, tb + T.A0q, tb + T.end + tc3_layout(1, d, H).sumV, precision, splits,
+                   part, &splits, st);
     if (rc == B200VAE_EUNSUP) {
 #define B200VAE_TCD(DD)                                                                                       \
   rc = x3 ? launch_tc_dp0<DD, true>(z, v, mask1, mask2, B, T, tb, Hw_in, splits, part, st)                    \

@@ -1843,6 +1843,252 @@ icnn_tc3_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, co
   }
 }
 
+// ---- dP0 in the FP16 mode ----------------------------------------------------------------------------------------------
+// Same CTA-pair scheme on kind::f16 MMAs (M = 256, N = 256, K = 16): the expensive operand s2 q1 as an FP16 hi/lo pair (two
+// MMAs per accumulator and K step: half the tensor time of the 3xTF32 instantiation, whose tensor pipe is 95 % busy), the slope
+// pattern 1 | 5 exact in fp16.  FP16 range: the samples are the K dimension here, so a per-sample scale could not be undone
+// after the sum; instead every CTA first scans ITS samples for the largest bound of |s2 q1| (the bound of row_scale_q1) and
+// scales the whole operand by ONE power of two G (exact), |s2 q1| G < 2^14, undone in the epilogue.  A sample far below the
+// split's maximum keeps an absolute error of 2^-25 / G -- 2^-39 of the largest element, nothing against the fp32 rounding of
+// the sum.  Both CTAs of a pair scan the same samples, so they agree on G.
+// 16-bit MN-major operands: SWIZZLE_128B atoms of 8 k-rows x 128 B (64 MN elements), the 16-byte chunks of a row XOR-ed with
+// the k-row; a tile is 128 MN wide: LBO = 1 KB between the two atoms, SBO = 2 KB between groups of 8 k.  A stage holds 32
+// samples (two K = 16 steps): A hi, A lo, B (accumulator 0), B (accumulator 1), 8 KB each.
+constexpr int kDpTile16 = 32 * 128 * 2;                        // 32 k x 128 MN x 2 B = 8 KB
+constexpr int kDpStage16 = 4 * kDpTile16;
+constexpr int kDpS16 = 5;
+constexpr uint32_t k3IdescF16MN = k3IdescF16 | (1u << 15) | (1u << 16);
+__device__ __forceinline__ uint64_t make_desc_mn128_b16(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(2048 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);           // layout type 2 = SWIZZLE_128B
+}
+__device__ __forceinline__ void umma_f16_pair_mn(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(k3IdescF16MN), "r"(acc) : "memory");
+}
+template <int D>
+constexpr size_t dp3_f16_smem_bytes() {
+  return (size_t)kDpS16 * kDpStage16 + (size_t)2 * 256 * (2 * D + 1) * 4 + 2 * 8 * 256 * 4 + (2 * kDpS16 + 1) * 8 + 16 + 64 + 1024;
+}
+
+template <int D>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDpThreads3, 1)
+icnn_tc3_dP0_f16_kernel(const float* __restrict__ z, const float* __restrict__ v, const uint32_t* __restrict__ mask1,
+                        const uint8_t* __restrict__ mask2, int B, int Hq, int Hw_in, int rows_per_split,
+                        const float4* __restrict__ A0q_g, const float* __restrict__ sumV, float* __restrict__ dP0part) {
+  constexpr int S = kDpS16, KS = 32;                         // samples per stage
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* samp = reinterpret_cast<float*>(stages + S * kDpStage16);           // [2][2D+1][256]  z, v, s2 per sample
+  uint32_t* sampw = reinterpret_cast<uint32_t*>(samp + 2 * 256 * (2 * D + 1));    // [2][8][256] this CTA's mask words
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sampw + 2 * 8 * 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+  float* redmax = reinterpret_cast<float*>(tmem_slot + 2);                   // [16] per-warp maxima of the scale scan
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S), accfull = smem_u32(bars + 2 * S);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t rank = cluster_rank3();
+  const int n0 = (blockIdx.x >> 1) * 256 + (int)rank * 128;  // my 128 n's (rows of D)
+  const int o0 = blockIdx.y * 512, split = blockIdx.z;
+  const bool two = o0 + 256 < Hq;                            // Hq is a multiple of 256: the last o-tile may be half
+  const int b0 = split * rows_per_split;
+  const int b1 = min(B, b0 + rows_per_split);
+  const int NSG = (max(b1 - b0, 0) + KS - 1) / KS;           // stages
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 2 * kDpWarps); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(accfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kDpWarps) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync3();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lead_full0 = mapa3(full0, 0);
+
+  if (warp_u < kDpWarps) {
+    // thread -> (sample ks of the stage, 8 consecutive MN elements = one 16-byte chunk).  The 8 lanes of a quarter warp hold the
+    // 8 chunks of one 128-byte row (conflict-free 16-byte stores); a warp covers the k-rows kr of all four 8-k groups.
+    const int ncl = lane & 7, kg = lane >> 3, atom = warp & 1, kr = warp >> 1;
+    const int ks = kg * 8 + kr;
+    const uint32_t off = (uint32_t)(kg * 2048 + atom * 1024 + kr * 128) + ((uint32_t)(ncl ^ kr) << 4);
+    const int wsel = atom * 2 + (ncl >> 2), bsh = (ncl & 3) * 8;   // my 8 bits: word wsel of either accumulator's 4 words
+    float2 qx2[4], qy2[4], qz2[4], qw2[4];                   // my 8 n's as four packed pairs: (w0, w1, w2, bias)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + atom * 64 + ncl * 8 + 2 * i;
+      const float4 qa = A0q_g[n], qb = A0q_g[n + 1];
+      qx2[i] = make_float2(qa.x, qb.x); qy2[i] = make_float2(qa.y, qb.y);
+      qz2[i] = make_float2(qa.z, qb.z); qw2[i] = make_float2(qa.w, qb.w);
+    }
+    // ---- the split's scale: largest bound of |s2 q1| over my samples -> one power of two for the whole accumulation ----
+    const float4 amax = make_float4(sumV[24], sumV[25], sumV[26], sumV[27]);
+    float bmax = 0.f;
+    for (int m = b0 + tid; m < b1; m += kDpWarps * 32) {
+      float zr[D], vr[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) { zr[j] = __ldg(z + (size_t)m * D + j); vr[j] = __ldg(v + (size_t)m * D + j); }
+      float bu = __fmul_rn(amax.x, fabsf(2.f * vr[0]));
+      if (D > 1) bu = fmaf(amax.y, fabsf(2.f * vr[D > 1 ? 1 : 0]), bu);
+      if (D > 2) bu = fmaf(amax.z, fabsf(2.f * vr[D > 2 ? 2 : 0]), bu);
+      bmax = fmaxf(bmax, __fmul_rn(bu, h0_bound<D>(zr, amax)));
+    }
+    bmax = warp_max(bmax);
+    if (lane == 0) redmax[warp] = bmax;
+    bar_dp();
+#pragma unroll
+    for (int w = 0; w < kDpWarps; ++w) bmax = fmaxf(bmax, redmax[w]);
+    const uint32_t eb = bexp_of(bmax, 30u, 220u);
+    const float G = __uint_as_float((267u - eb) << 23), invG = __uint_as_float((eb - 13u) << 23);
+
+    constexpr int CH = 256, ZV = 2 * D + 1, SPC = CH / KS;   // stages per staged chunk of samples
+    const int nchunk = (NSG * KS + CH - 1) / CH;
+    float pre_f[ZV];
+    uint32_t pre_w[4];
+    auto fetch = [&](int c) {                                // thread -> sample (tid&255), accumulator t = tid>>8
+      const int mrow = b0 + c * CH + (tid & 255);
+      const bool in = mrow < b1;
+      if (tid < CH) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          pre_f[j] = in ? __ldg(z + (size_t)mrow * D + j) : 0.f;
+          pre_f[D + j] = in ? __ldg(v + (size_t)mrow * D + j) : 0.f;
+        }
+        pre_f[2 * D] = in ? (__ldg(mask2 + mrow) ? 1.f : kSlope) : 0.f;
+      }
+      const int w0 = (o0 >> 5) + (tid >> 8) * 8 + (int)rank * 4;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) pre_w[q4] = (in && w0 + q4 < Hw_in) ? __ldg(mask1 + (size_t)mrow * Hw_in + w0 + q4) : 0u;
+    };
+    auto stash = [&](int buf) {
+      float* zf = samp + buf * (CH * ZV);
+      uint32_t* mw = sampw + buf * (CH * 8);
+      if (tid < CH) {
+#pragma unroll
+        for (int j = 0; j < ZV; ++j) zf[j * CH + tid] = pre_f[j];
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) mw[((tid >> 8) * 4 + q4) * CH + (tid & 255)] = pre_w[q4];
+    };
+    if (nchunk > 0) { fetch(0); stash(0); }
+    bar_dp();
+    for (int sg = 0; sg < NSG; ++sg) {
+      const int c = sg / SPC, buf = c & 1, sl = (sg % SPC) * KS + ks;      // sample slot inside the chunk
+      if ((sg % SPC) == 0 && c + 1 < nchunk) fetch(c + 1);
+      const float* zf = samp + buf * (CH * ZV);
+      float zr[D], vr[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) { zr[j] = zf[j * CH + sl]; vr[j] = zf[(D + j) * CH + sl]; }
+      const float s2f = zf[2 * D * CH + sl];
+      const uint32_t bits0 = sampw[buf * (CH * 8) + wsel * CH + sl] >> bsh;
+      const uint32_t bits1 = sampw[buf * (CH * 8) + (4 + wsel) * CH + sl] >> bsh;
+      // A = G s2 q1 = (2 G s2 A0 v) . max(h0, 0.04 h0) for my 8 n's, two per packed instruction
+      float qv[8];
+      float sv[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) sv[j] = ((2.f * s2f) * G) * vr[j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 h = __ffma2_rn(qx2[i], make_float2(zr[0], zr[0]), qw2[i]);
+        float2 uu = __fmul2_rn(qx2[i], make_float2(sv[0], sv[0]));
+        if (D > 1) {
+          h = __ffma2_rn(qy2[i], make_float2(zr[D > 1 ? 1 : 0], zr[D > 1 ? 1 : 0]), h);
+          uu = __ffma2_rn(qy2[i], make_float2(sv[D > 1 ? 1 : 0], sv[D > 1 ? 1 : 0]), uu);
+        }
+        if (D > 2) {
+          h = __ffma2_rn(qz2[i], make_float2(zr[D > 2 ? 2 : 0], zr[D > 2 ? 2 : 0]), h);
+          uu = __ffma2_rn(qz2[i], make_float2(sv[D > 2 ? 2 : 0], sv[D > 2 ? 2 : 0]), uu);
+        }
+        const float2 l = __fmul2_rn(h, make_float2(kSlope * kSlope, kSlope * kSlope));
+        const float2 x = __fmul2_rn(uu, make_float2(fmaxf(h.x, l.x), fmaxf(h.y, l.y)));
+        qv[2 * i] = x.x; qv[2 * i + 1] = x.y;
+      }
+      if ((sg % SPC) == SPC - 1 && c + 1 < nchunk) {          // next chunk's buffer was last read SPC stages ago
+        bar_dp();
+        stash(buf ^ 1);
+        bar_dp();
+      }
+      const uint32_t s = sg % S, ph = (sg / S) & 1;
+      mbar_wait(empty0 + 8 * s, ph ^ 1);
+      unsigned char* st = stages + s * kDpStage16 + off;
+      uint4 hi, lo;
+      split_f16(qv[0], qv[1], hi.x, lo.x);
+      split_f16(qv[2], qv[3], hi.y, lo.y);
+      split_f16(qv[4], qv[5], hi.z, lo.z);
+      split_f16(qv[6], qv[7], hi.w, lo.w);
+      *reinterpret_cast<uint4*>(st) = hi;
+      *reinterpret_cast<uint4*>(st + kDpTile16) = lo;
+      // B = 1 + 4*bit (the LeakyReLU slope / 0.2, exact in fp16; 0.2 and P1 are applied by finalize_W0)
+      *reinterpret_cast<uint4*>(st + 2 * kDpTile16) = make_uint4(pat2_f16(bits0), pat2_f16(bits0 >> 2), pat2_f16(bits0 >> 4), pat2_f16(bits0 >> 6));
+      *reinterpret_cast<uint4*>(st + 3 * kDpTile16) = make_uint4(pat2_f16(bits1), pat2_f16(bits1 >> 2), pat2_f16(bits1 >> 4), pat2_f16(bits1 >> 6));
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(lead_full0 + 8 * s);
+    }
+    // epilogue: TMEM lane = my n, column = o (512 of them).  Warp w: lane quadrant w & 3, the 128 columns of group w >> 2.
+    const int q = warp & 3, cg = warp >> 2;
+    const int n = n0 + q * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 128);
+    if (two || cg < 2) {
+      float* out = dP0part + ((size_t)split * Hq + o0 + cg * 128) * Hq + n;
+      if (NSG > 0) {
+        mbar_wait_parked(accfull, 0, 2000);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t r[32];
+          tmem_ld32(taddr + cc * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) out[(size_t)(cc * 32 + j) * Hq] = __uint_as_float(r[j]) * invG;
+        }
+      } else {
+        for (int j = 0; j < 128; ++j) out[(size_t)j * Hq] = 0.f;
+      }
+    }
+  } else if (rank == 0) {
+    const uint64_t desc0 = make_desc_mn128_b16(smem_u32(stages));
+    for (int sg = 0; sg < NSG; ++sg) {
+      const uint32_t s = sg % S, ph = (sg / S) & 1;
+      mbar_wait(full0 + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t sa = desc0 + (uint64_t)((s * kDpStage16) >> 4);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {                                            // K = 16 = two 8-k groups (2 x SBO = 4 KB)
+          const uint64_t a_hi = sa + (uint64_t)((g * 4096) >> 4);
+          const uint32_t acc = (sg | g) ? 1u : 0u;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (t == 1 && !two) break;
+            const uint32_t d_t = tmem_base + (uint32_t)(t * 256);
+            const uint64_t b = sa + (uint64_t)(((2 + t) * kDpTile16 + g * 4096) >> 4);
+            umma_f16_pair_mn(d_t, a_hi + (uint64_t)(kDpTile16 >> 4), b, acc);     // B is exact: a_lo.b + a_hi.b
+            umma_f16_pair_mn(d_t, a_hi, b, 1u);
+          }
+        }
+        umma_commit_pair(empty0 + 8 * s);
+        if (sg == NSG - 1) umma_commit_pair(accfull);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync3();
+  if (warp == kDpWarps) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 static int max_clusters_for(const void* fn, size_t smem) {
   cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaLaunchConfig_t cfg = {};
@@ -1892,13 +2138,40 @@ static int launch_tc3_dp0(const float* z, const float* v, const uint32_t* mask1,
   *splits_out = splits;
   return check_launch();
 }
-// part: [splits][Hq][Hq] ordered split-K slabs (reduced by finalize_W0_kernel); *splits_out <= max_splits
+template <int D>
+static int launch_tc3_dp0_f16(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int Hq,
+                              int Hw_in, const float4* A0q, const float* sumV, int max_splits, float* part, int* splits_out,
+                              cudaStream_t st) {
+  constexpr size_t smem = dp3_f16_smem_bytes<D>();
+  static_assert(smem <= 227 * 1024, "dP0 pair kernel (fp16): shared memory");
+  static int max_clusters = 0;
+  if (max_clusters == 0) max_clusters = max_clusters_dp(reinterpret_cast<const void*>(icnn_tc3_dP0_f16_kernel<D>), smem);
+  const int tn = Hq / 256, to = (Hq + 511) / 512;
+  int splits = max_clusters / (tn * to);                     // one wave of long-running clusters
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int rows = (B + splits - 1) / splits;
+  rows = round_up(rows, 32);
+  dim3 grid(2 * tn, to, splits);
+  icnn_tc3_dP0_f16_kernel<D><<<grid, kDpThreads3, smem, st>>>(z, v, mask1, mask2, B, Hq, Hw_in, rows, A0q, sumV, part);
+  *splits_out = splits;
+  return check_launch();
+}
+// part: [splits][Hq][Hq] ordered split-K slabs (reduced by finalize_W0_kernel); *splits_out <= max_splits.
+// sumV: Tc3Layout::sumV of the prepared workspace (max |A0| for the FP16 mode's scale)
 int tc3_dp0(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int Hq, int Hw_in,
-            const float* A0q, int precision, int max_splits, float* part, int* splits_out, cudaStream_t st) {
+            const float* A0q, const float* sumV, int precision, int max_splits, float* part, int* splits_out, cudaStream_t st) {
   if (precision == 2 /* reserved */ || d > 3) return B200VAE_EUNSUP;
-  // both operands of this kernel are generated (nothing prepared): the FP16 mode runs the 3xTF32 instantiation
-  const bool x3 = (precision == B200VAE_PREC_TF32X3 || precision == B200VAE_PREC_F16X3);
   const float4* q = reinterpret_cast<const float4*>(A0q);
+  static const int dp_f16 = [] { const char* e = getenv("B200VAE_DP0_F16"); return e ? atoi(e) : 1; }();
+  if (precision == B200VAE_PREC_F16X3 && dp_f16) {
+    switch (d) {
+      case 1: return launch_tc3_dp0_f16<1>(z, v, mask1, mask2, B, Hq, Hw_in, q, sumV, max_splits, part, splits_out, st);
+      case 2: return launch_tc3_dp0_f16<2>(z, v, mask1, mask2, B, Hq, Hw_in, q, sumV, max_splits, part, splits_out, st);
+      default: return launch_tc3_dp0_f16<3>(z, v, mask1, mask2, B, Hq, Hw_in, q, sumV, max_splits, part, splits_out, st);
+    }
+  }
+  const bool x3 = (precision == B200VAE_PREC_TF32X3 || precision == B200VAE_PREC_F16X3);
 #define B200VAE_TC3D(DD)                                                                                             \
   return x3 ? launch_tc3_dp0<DD, true>(z, v, mask1, mask2, B, Hq, Hw_in, q, max_splits, part, splits_out, st)         \
             : launch_tc3_dp0<DD, false>(z, v, mask1, mask2, B, Hq, Hw_in, q, max_splits, part, splits_out, st)
