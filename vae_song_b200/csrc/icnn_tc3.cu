@@ -146,6 +146,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
+__device__ __forceinline__ int round_up_dev(int x, int m) { return (x + m - 1) / m * m; }
 __device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void bar_gen() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
@@ -304,9 +305,12 @@ struct Tc3Cfg {
   static constexpr bool HL = MODE != kTf32;                               // operands come as hi/lo pairs
   static constexpr bool F16 = MODE == kF16;
   static constexpr int KBE = F16 ? 32 : 16;                               // K elements per K-block (64-byte rows)
-  static constexpr int S = HL ? 2 : 4;                                    // stages of two K-blocks
+  // K-blocks per stage: a generator thread produces 32 elements per stage either way (two 16-wide tf32 blocks or one 32-wide
+  // fp16 block) -- all of them computed BEFORE it waits for the stage to drain, so that only the stores follow the wait
+  static constexpr int KPS = F16 ? 1 : 2;
+  static constexpr int S = F16 ? 4 : (HL ? 2 : 4);                        // stages
   static constexpr int kSubBytes = (HL ? 4 : 2) * k3TileBytes;            // one K-block: A(hi[,lo]) + B half (hi[,lo])
-  static constexpr int kStageBytes = 2 * kSubBytes;
+  static constexpr int kStageBytes = KPS * kSubBytes;
   static constexpr int kOffAlo = k3TileBytes, kOffB = (HL ? 2 : 1) * k3TileBytes, kOffBlo = 3 * k3TileBytes;
 };
 template <int MODE>
@@ -333,7 +337,7 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
   using C = Tc3Cfg<MODE>;
   constexpr int S = C::S;
   constexpr bool X3 = C::HL, F16 = C::F16;                                 // X3: hi/lo operands, three (two) MMAs per K step
-  constexpr int KBE = C::KBE;
+  constexpr int KBE = C::KBE, KPS = C::KPS;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stages = smem;
@@ -361,8 +365,8 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
   const float4 amax = F16 ? make_float4(a.sumV[24], a.sumV[25], a.sumV[26], a.sumV[27]) : make_float4(0.f, 0.f, 0.f, 0.f);
 
   if (tid == 0) {
-    // full: 4 generator warps (one group owns a whole stage) x 2 CTAs + the leader's 2 TMA arrivals (one per K-block)
-    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 8 + 2); mbar_init(empty0 + 8 * s, 1); }
+    // full: 4 generator warps (one group owns a whole stage) x 2 CTAs + the leader's TMA arrivals (one per K-block)
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 8 + C::KPS); mbar_init(empty0 + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(accfull0 + 8 * b, 1); mbar_init(accempty0 + 8 * b, 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -611,7 +615,7 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
       }
       cp_async_commit();
     };
-    const int NST = NKB / 2;                                   // full stages per unit
+    const int NST = NKB / KPS;                                 // full stages per unit
     for (int u = cid; u < U; u += G) {
       const Unit un = decode_unit(u, T, NP);
       const int m0 = un.t * 256 + (int)rank * k3Rows;
@@ -641,12 +645,12 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
             for (int j = 0; j < D; ++j) zp[pr][j] = __fmul2_rn(zp[pr][j], tq[pr]);
           }
           for (int st = (int)((stg ^ (uint32_t)kh) & 1u); st < NST; st += 2) {
-#pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
+            uint4 hi[4], lo[4];
+            {
               float x[4][8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const float4 q = A0gs[(2 * st + sub) * KBE + e * 4 + c];
+                const float4 q = A0gs[st * KBE + e * 4 + c];
 #pragma unroll
                 for (int pr = 0; pr < 2; ++pr) {
                   float2 h = __ffma2_rn(make_float2(q.x, q.x), zp[pr][0], __fmul2_rn(make_float2(q.w, q.w), tq[pr]));
@@ -658,18 +662,20 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
                   x[2 * pr][e] = xx.x; x[2 * pr + 1][e] = xx.y;
                 }
               }
-              if (sub == 0) wait_stage(stg + st);
-              unsigned char* At = stage_ptr(stg + st) + sub * C::kSubBytes;
 #pragma unroll
               for (int r = 0; r < 4; ++r) {
-                uint4 hi, lo;
-                split_f16(x[r][0], x[r][1], hi.x, lo.x);
-                split_f16(x[r][2], x[r][3], hi.y, lo.y);
-                split_f16(x[r][4], x[r][5], hi.z, lo.z);
-                split_f16(x[r][6], x[r][7], hi.w, lo.w);
-                *reinterpret_cast<uint4*>(At + r * 2048) = hi;
-                *reinterpret_cast<uint4*>(At + C::kOffAlo + r * 2048) = lo;
+                split_f16(x[r][0], x[r][1], hi[r].x, lo[r].x);
+                split_f16(x[r][2], x[r][3], hi[r].y, lo[r].y);
+                split_f16(x[r][4], x[r][5], hi[r].z, lo[r].z);
+                split_f16(x[r][6], x[r][7], hi[r].w, lo[r].w);
               }
+            }
+            wait_stage(stg + st);
+            unsigned char* At = stage_ptr(stg + st);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              *reinterpret_cast<uint4*>(At + r * 2048) = hi[r];
+              *reinterpret_cast<uint4*>(At + C::kOffAlo + r * 2048) = lo[r];
             }
             publish(stg + st);
           }
@@ -768,19 +774,16 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
         const uint32_t* mrow = maskbuf + mb * (k3Rows * k3MaskStride) + rb * k3MaskStride;
         for (int st = (int)((stg ^ (uint32_t)kh) & 1u); st < NST; st += 2) {
           if constexpr (F16) {
-            uint2 w2[4];                                       // words 2st, 2st+1 of my 4 rows = K-blocks 2st, 2st+1 (32 bits each)
+            uint4 pat[4];                                      // word st of my 4 rows = K-block st (32 bits), my byte c of it
 #pragma unroll
-            for (int r = 0; r < 4; ++r) w2[r] = *reinterpret_cast<const uint2*>(mrow + r * 32 * k3MaskStride + 2 * st);
+            for (int r = 0; r < 4; ++r) {
+              const uint32_t w = mrow[r * 32 * k3MaskStride + st] >> (c * 8);
+              pat[r] = make_uint4(pat2_f16(w), pat2_f16(w >> 2), pat2_f16(w >> 4), pat2_f16(w >> 6));
+            }
             wait_stage(stg + st);
             unsigned char* At = stage_ptr(stg + st);
 #pragma unroll
-            for (int sub = 0; sub < 2; ++sub)
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const uint32_t w = (sub ? w2[r].y : w2[r].x) >> (c * 8);
-                *reinterpret_cast<uint4*>(At + sub * C::kSubBytes + r * 2048) =
-                    make_uint4(pat2_f16(w), pat2_f16(w >> 2), pat2_f16(w >> 4), pat2_f16(w >> 6));
-              }
+            for (int r = 0; r < 4; ++r) *reinterpret_cast<uint4*>(At + r * 2048) = pat[r];
           } else {
             uint32_t w4[4];                                    // word st of my 4 rows: bits of K-blocks 2st (low half), 2st+1
 #pragma unroll
@@ -811,25 +814,25 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
       const Unit un = decode_unit(u, T, NP);
       const CUtensorMap* mhi = un.g ? &a.b2hi : &a.b1hi;
       const CUtensorMap* mlo = un.g ? &a.b2lo : &a.b1lo;
-      const int nreal = (un.g || F16) ? NKB : NKB + 1, npad = (nreal + 1) & ~1;   // FP16 mode has no lin block
+      const int nreal = (un.g || F16) ? NKB : NKB + 1, npad = round_up_dev(nreal, KPS);   // FP16 mode has no lin block
       const int rowc = un.p * 256 + (int)rank * k3Rows;
-      for (int kb = 0; kb < npad; kb += 2, it += 2) {                  // one stage = two K-blocks
-        const uint32_t s = (it >> 1) % S, ph = ((it >> 1) / S) & 1;
+      for (int kb = 0; kb < npad; kb += KPS, it += KPS) {              // one stage = KPS K-blocks
+        const uint32_t s = (it / KPS) % S, ph = ((it / KPS) / S) & 1;
         mbar_wait(empty0 + 8 * s, ph ^ 1);
-        const bool real1 = kb + 1 < nreal;
         if (elect_one()) {
           const uint32_t bar = lead_full0 + 8 * s;
-          if (rank == 0) {                                              // expect both CTAs' halves of the stage
-            mbar_arrive_expect_tx(full0 + 8 * s, 2 * (X3 ? 2 : 1) * k3TileBytes);
-            if (real1) mbar_arrive_expect_tx(full0 + 8 * s, 2 * (X3 ? 2 : 1) * k3TileBytes);
-            else mbar_arrive(full0 + 8 * s);
-          }
           const uint32_t dst = smem_u32(stages + s * C::kStageBytes);
-          tma_load_2d_pair(dst + C::kOffB, mhi, bar, kb * KBE, rowc);
-          if (X3) tma_load_2d_pair(dst + C::kOffBlo, mlo, bar, kb * KBE, rowc);
-          if (real1) {
-            tma_load_2d_pair(dst + C::kSubBytes + C::kOffB, mhi, bar, (kb + 1) * KBE, rowc);
-            if (X3) tma_load_2d_pair(dst + C::kSubBytes + C::kOffBlo, mlo, bar, (kb + 1) * KBE, rowc);
+#pragma unroll
+          for (int sub = 0; sub < KPS; ++sub) {
+            const bool real = kb + sub < nreal;                         // (the block after a lin block is a dummy)
+            if (rank == 0) {                                            // expect both CTAs' halves of the K-block
+              if (real) mbar_arrive_expect_tx(full0 + 8 * s, 2 * (X3 ? 2 : 1) * k3TileBytes);
+              else mbar_arrive(full0 + 8 * s);
+            }
+            if (real) {
+              tma_load_2d_pair(dst + sub * C::kSubBytes + C::kOffB, mhi, bar, (kb + sub) * KBE, rowc);
+              if (X3) tma_load_2d_pair(dst + sub * C::kSubBytes + C::kOffBlo, mlo, bar, (kb + sub) * KBE, rowc);
+            }
           }
         }
         __syncwarp();
@@ -840,12 +843,12 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
     // Converged warp, one elected lane issues.  Descriptors advance by constants: +2 (32 B) per K=8 step,
     // +kSubBytes/16 per K-block, +kStageBytes/16 per stage.
     const uint64_t descA0 = make_desc_sw64(smem_u32(stages));
-    const int NC = X3 ? a.NC : 1, kb_per_chunk = NKB / NC;                       // NKB / NC is even (chunks of whole stages)
+    const int NC = X3 ? a.NC : 1, kb_per_chunk = NKB / NC;                       // chunks of whole stages
     uint32_t it = 0;
     int i = 0;
     for (int u = cid; u < U; u += G) {
       const Unit un = decode_unit(u, T, NP);
-      const int nreal = (un.g || F16) ? NKB : NKB + 1, npad = (nreal + 1) & ~1;
+      const int nreal = (un.g || F16) ? NKB : NKB + 1, npad = round_up_dev(nreal, KPS);
       int kb = 0;
       const int nck = un.g ? 1 : NC;                                    // GEMM1 units only (see the epilogue warps)
       for (int ck = 0; ck < nck; ++ck, ++i) {                           // one accumulator per K-chunk
@@ -854,15 +857,15 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
         mbar_wait(accempty0 + 8 * buf, ((i >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_t = tmem_base + (uint32_t)(buf * 256);
-        for (; kb < kb1; kb += 2, it += 2) {
-          const uint32_t s = (it >> 1) % S, ph = ((it >> 1) / S) & 1;
+        for (; kb < kb1; kb += KPS, it += KPS) {
+          const uint32_t s = (it / KPS) % S, ph = ((it / KPS) / S) & 1;
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t a0 = descA0 + (uint64_t)(s * (C::kStageBytes >> 4));
 #pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-              if (sub == 1 && kb + 1 >= nreal) break;                   // dummy block of a GEMM1 unit
+            for (int sub = 0; sub < KPS; ++sub) {
+              if (kb + sub >= nreal) break;                             // dummy block of a GEMM1 unit
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
                 const uint64_t a_hi = a0 + (uint64_t)(sub * (C::kSubBytes >> 4) + ks * 2);
@@ -883,7 +886,7 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
               }
             }
             umma_commit_pair(empty0 + 8 * s);                           // frees the stage in both CTAs
-            if (kb + 2 >= kb1) umma_commit_pair(accfull0 + 8 * buf);    // chunk complete
+            if (kb + KPS >= kb1) umma_commit_pair(accfull0 + 8 * buf);  // chunk complete
           }
           __syncwarp();
         }
@@ -960,7 +963,7 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
   using C = Tc3Cfg<MODE>;
   constexpr int S = C::S;
   constexpr bool X3 = C::HL, F16 = C::F16;
-  constexpr int KBE = C::KBE;
+  constexpr int KBE = C::KBE, KPS = C::KPS;
   constexpr int NF = D + 1;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -989,7 +992,7 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
   };
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 8 + 2); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 8 + C::KPS); mbar_init(empty0 + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(accfull0 + 8 * b, 1); mbar_init(accempty0 + 8 * b, 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1191,7 +1194,7 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
       }
       cp_async_commit();
     };
-    const int NST = NKB / 2;
+    const int NST = NKB / KPS;
     for (int u = cid; u < U; u += G) {
       const Unit un = unit_of(u);
       const int m0 = un.t * 256 + (int)rank * k3Rows;
@@ -1207,19 +1210,16 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
         const uint32_t* mrow = maskbuf + mb * (k3Rows * k3MaskStride) + rb * k3MaskStride;
         for (int st = (int)((stg ^ (uint32_t)kh) & 1u); st < NST; st += 2) {
           if constexpr (F16) {
-            uint2 w2[4];
+            uint4 pat[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) w2[r] = *reinterpret_cast<const uint2*>(mrow + r * 32 * k3MaskStride + 2 * st);
+            for (int r = 0; r < 4; ++r) {
+              const uint32_t w = mrow[r * 32 * k3MaskStride + st] >> (c * 8);
+              pat[r] = make_uint4(pat2_f16(w), pat2_f16(w >> 2), pat2_f16(w >> 4), pat2_f16(w >> 6));
+            }
             wait_stage(stg + st);
             unsigned char* At = stage_ptr(stg + st);
 #pragma unroll
-            for (int sub = 0; sub < 2; ++sub)
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const uint32_t w = (sub ? w2[r].y : w2[r].x) >> (c * 8);
-                *reinterpret_cast<uint4*>(At + sub * C::kSubBytes + r * 2048) =
-                    make_uint4(pat2_f16(w), pat2_f16(w >> 2), pat2_f16(w >> 4), pat2_f16(w >> 6));
-              }
+            for (int r = 0; r < 4; ++r) *reinterpret_cast<uint4*>(At + r * 2048) = pat[r];
           } else {
             uint32_t w4[4];
 #pragma unroll
@@ -1269,12 +1269,12 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
             for (int j = 0; j < D; ++j) vp[pr][j] = __fmul2_rn(vp[pr][j], make_float2(t0, t1));
           }
           for (int st = (int)((stg ^ (uint32_t)kh) & 1u); st < NST; st += 2) {
-#pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
+            uint4 hi[4], lo[4];
+            {
               float x[4][8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const float4 q = A0gs[(2 * st + sub) * KBE + e * 4 + c];
+                const float4 q = A0gs[st * KBE + e * 4 + c];
 #pragma unroll
                 for (int pr = 0; pr < 2; ++pr) {
                   float2 h = __ffma2_rn(make_float2(q.x, q.x), zp[pr][0], make_float2(q.w, q.w));
@@ -1293,18 +1293,20 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
                   x[2 * pr][e] = xx.x; x[2 * pr + 1][e] = xx.y;
                 }
               }
-              if (sub == 0) wait_stage(stg + st);
-              unsigned char* At = stage_ptr(stg + st) + sub * C::kSubBytes;
 #pragma unroll
               for (int r = 0; r < 4; ++r) {
-                uint4 hi, lo;
-                split_f16(x[r][0], x[r][1], hi.x, lo.x);
-                split_f16(x[r][2], x[r][3], hi.y, lo.y);
-                split_f16(x[r][4], x[r][5], hi.z, lo.z);
-                split_f16(x[r][6], x[r][7], hi.w, lo.w);
-                *reinterpret_cast<uint4*>(At + r * 2048) = hi;
-                *reinterpret_cast<uint4*>(At + C::kOffAlo + r * 2048) = lo;
+                split_f16(x[r][0], x[r][1], hi[r].x, lo[r].x);
+                split_f16(x[r][2], x[r][3], hi[r].y, lo[r].y);
+                split_f16(x[r][4], x[r][5], hi[r].z, lo[r].z);
+                split_f16(x[r][6], x[r][7], hi[r].w, lo[r].w);
               }
+            }
+            wait_stage(stg + st);
+            unsigned char* At = stage_ptr(stg + st);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              *reinterpret_cast<uint4*>(At + r * 2048) = hi[r];
+              *reinterpret_cast<uint4*>(At + C::kOffAlo + r * 2048) = lo[r];
             }
             publish(stg + st);
           }
@@ -1391,25 +1393,25 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
       const Unit un = unit_of(u);
       const CUtensorMap* mhi = un.g ? &a.b1hi : &a.b2hi;
       const CUtensorMap* mlo = un.g ? &a.b1lo : &a.b2lo;
-      const int nreal = (un.g && !F16) ? NKB + 1 : NKB, npad = (nreal + 1) & ~1;
+      const int nreal = (un.g && !F16) ? NKB + 1 : NKB, npad = round_up_dev(nreal, KPS);
       const int rowc = un.p * 256 + (int)rank * k3Rows;
-      for (int kb = 0; kb < npad; kb += 2, it += 2) {
-        const uint32_t s = (it >> 1) % S, ph = ((it >> 1) / S) & 1;
+      for (int kb = 0; kb < npad; kb += KPS, it += KPS) {
+        const uint32_t s = (it / KPS) % S, ph = ((it / KPS) / S) & 1;
         mbar_wait(empty0 + 8 * s, ph ^ 1);
-        const bool real1 = kb + 1 < nreal;
         if (elect_one()) {
           const uint32_t bar = lead_full0 + 8 * s;
-          if (rank == 0) {
-            mbar_arrive_expect_tx(full0 + 8 * s, 2 * (X3 ? 2 : 1) * k3TileBytes);
-            if (real1) mbar_arrive_expect_tx(full0 + 8 * s, 2 * (X3 ? 2 : 1) * k3TileBytes);
-            else mbar_arrive(full0 + 8 * s);
-          }
           const uint32_t dst = smem_u32(stages + s * C::kStageBytes);
-          tma_load_2d_pair(dst + C::kOffB, mhi, bar, kb * KBE, rowc);
-          if (X3) tma_load_2d_pair(dst + C::kOffBlo, mlo, bar, kb * KBE, rowc);
-          if (real1) {
-            tma_load_2d_pair(dst + C::kSubBytes + C::kOffB, mhi, bar, (kb + 1) * KBE, rowc);
-            if (X3) tma_load_2d_pair(dst + C::kSubBytes + C::kOffBlo, mlo, bar, (kb + 1) * KBE, rowc);
+#pragma unroll
+          for (int sub = 0; sub < KPS; ++sub) {
+            const bool real = kb + sub < nreal;                         // (the block after a lin block is a dummy)
+            if (rank == 0) {                                            // expect both CTAs' halves of the K-block
+              if (real) mbar_arrive_expect_tx(full0 + 8 * s, 2 * (X3 ? 2 : 1) * k3TileBytes);
+              else mbar_arrive(full0 + 8 * s);
+            }
+            if (real) {
+              tma_load_2d_pair(dst + sub * C::kSubBytes + C::kOffB, mhi, bar, (kb + sub) * KBE, rowc);
+              if (X3) tma_load_2d_pair(dst + sub * C::kSubBytes + C::kOffBlo, mlo, bar, (kb + sub) * KBE, rowc);
+            }
           }
         }
         __syncwarp();
@@ -1423,19 +1425,19 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
     for (int u = cid; u < U; u += G, ++i) {
       const Unit un = unit_of(u);
       const int buf = i & 1;
-      const int nreal = (un.g && !F16) ? NKB + 1 : NKB, npad = (nreal + 1) & ~1;
+      const int nreal = (un.g && !F16) ? NKB + 1 : NKB, npad = round_up_dev(nreal, KPS);
       mbar_wait(accempty0 + 8 * buf, ((i >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_t = tmem_base + (uint32_t)(buf * 256);
-      for (int kb = 0; kb < npad; kb += 2, it += 2) {
-        const uint32_t s = (it >> 1) % S, ph = ((it >> 1) / S) & 1;
+      for (int kb = 0; kb < npad; kb += KPS, it += KPS) {
+        const uint32_t s = (it / KPS) % S, ph = ((it / KPS) / S) & 1;
         mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t a0 = descA0 + (uint64_t)(s * (C::kStageBytes >> 4));
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            if (sub == 1 && kb + 1 >= nreal) break;
+          for (int sub = 0; sub < KPS; ++sub) {
+            if (kb + sub >= nreal) break;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const uint64_t a_hi = a0 + (uint64_t)(sub * (C::kSubBytes >> 4) + ks * 2);
@@ -1456,7 +1458,7 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
             }
           }
           umma_commit_pair(empty0 + 8 * s);
-          if (kb + 2 >= npad) umma_commit_pair(accfull0 + 8 * buf);
+          if (kb + KPS >= npad) umma_commit_pair(accfull0 + 8 * buf);
         }
         __syncwarp();
       }
