@@ -607,3 +607,42 @@ def test_flexible_vae_fused_mlp_stacks_match_stock_modules(training):
             close_report(a.grad.cpu().numpy(), b.grad.cpu().numpy(), 5e-4, "grad " + k, floor=1e-4 * gscale)
     for (k, a), (_, b) in zip(m.named_buffers(), ref.named_buffers()):
         close_report(a.float().cpu().numpy(), b.float().cpu().numpy(), 2e-5, "buffer " + k)
+
+
+def test_early_prepare_on_side_streams_changes_nothing():
+    """LIDVAE.forward starts preparing both ICNNs' operands on side streams before the encoder runs
+    (ops.icnn_prepare_early); results and gradients are bit-identical to preparing at the point of use, eagerly and when
+    the whole step is replayed as a CUDA graph, and no parked workspace is left behind."""
+    import copy
+    from vae_song_b200 import model, ops, train
+    torch.manual_seed(3)
+    m0 = model.LIDVAE(dataset="pinwheel", icnn_channels=[64, 128], hidden_channels=[8, 4], inverse_lipschitz=0.2,
+                      precision="f16x3").cuda().train()
+    x, eps = torch.randn(300, 2, device="cuda"), torch.randn(300, 2, device="cuda")
+    outs = []
+    for early in (True, False):
+        m = copy.deepcopy(m0)
+        m.early_prepare = early
+        recon, mu, lv, z, _ = m(x, eps=eps)
+        total, _, _, _ = m.loss(x, recon, mu, lv, z, None)
+        total.backward()
+        torch.cuda.synchronize()
+        assert not ops._EARLY
+        outs.append((recon.detach().clone(), float(total), [p.grad.clone() for p in m.parameters()]))
+    assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+    for a, b in zip(outs[0][2], outs[1][2]):
+        assert torch.equal(a, b)
+    # graph replay of the whole step with the forked prepare branches == the eager step without them (same eps)
+    ma, mb = copy.deepcopy(m0), copy.deepcopy(m0)
+    mb.early_prepare = False
+    ta, tb = train.DataParallelTrainer(ma, lr=1e-3), train.DataParallelTrainer(mb, lr=1e-3)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xs = [torch.randn(300, 2, device="cuda", generator=g) for _ in range(4)]
+    es = [torch.randn(300, 2, device="cuda", generator=g) for _ in range(4)]
+    ta.capture(xs[0], es[0])
+    for xb, eb in zip(xs, es):
+        la = ta.step_graphed(xb, eb)[0].clone()
+        lb = tb.step(xb, eb)[0]
+        assert float(la) == float(lb)
+    torch.cuda.synchronize()
+    assert torch.equal(ta.fp.flat, tb.fp.flat) and not ops._EARLY

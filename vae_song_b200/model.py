@@ -14,12 +14,13 @@ image datasets, forward() accepts and ignores L, decode() needs no autograd grap
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import module, ops
+from . import _C, module, ops
 
 # dataset -> (in_channel, latent_channel, default hidden_channels, input_dim)
 _FLEX_PRESETS = {
@@ -421,6 +422,21 @@ class LIDVAE(VAE):
         _, y = self.decoder[1].brenier(x, self.il_factor)
         return self.decoder[2](y)
 
+    def _prepare_decoder_early(self, input):
+        """Training steps on the fused d <= 4 kernels: start building both ICNNs' prepared operands (they depend on the
+        weights only) on side streams before the encoder runs -- ops.icnn_prepare_early.  Anything this cannot predict
+        (wide inputs, FP32 small-batch routing, inference) simply prepares at the point of use as before."""
+        if not (input.is_cuda and input.dim() == 2 and torch.is_grad_enabled() and self.early_prepare):
+            return
+        for slot, ic in enumerate((self.decoder[0], self.decoder[1])):
+            ic.precision = self.precision
+            prec, params = ic._prec(), ic._flat_params()
+            if ic.in_channel > module.ICNN.FUSED_MAX_D or prec == _C.PREC_FP32 or not any(p.requires_grad for p in params):
+                continue
+            ops.icnn_prepare_early(params, ic.in_channel, ic.hidden_channel, ic._mode(), prec, input.shape[0], True, slot)
+
+    early_prepare = os.environ.get("B200VAE_EARLY_PREPARE", "1") != "0"      # A/B switch
+
     def _B_is_eye(self):
         v = self.__dict__.get("_b_eye_cache")
         if v is None or v[0] != self.B._version or v[1] != self.B.data_ptr():
@@ -432,6 +448,7 @@ class LIDVAE(VAE):
     def forward(self, input, latent_recon=False, latent_rand_sampling=True, L=None, eps=None):
         """-> (recon, mu, log_var, z, None | z_recon).  `L` is accepted and ignored (reference defect D2);
         `eps` may be injected for tests."""
+        self._prepare_decoder_early(input)
         mu, log_var = self.encode(input)
         if latent_rand_sampling:
             if eps is None:
