@@ -1046,13 +1046,33 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
       }
       // one part of the unit: isB = B-unit maths (w1 column sums) else A-unit maths (t0, g0, dz);  from_global = the
       // accumulator comes from the forward's saved GEMM2 output instead of TMEM (SV kernels, A-part only)
+      // the per-element maths runs on packed f32x2 instructions over ROW PAIRS (rows r0 + 8r, r = (0,1) and (2,3): the two halves
+      // of ra / rb): the kernel is issue bound (60 % of the issue slots at 73 % tensor activity), and packing halves the
+      // floating-point instructions of the epilogue
+      float2 zp[2][D], vp[2][D], s2p[2], qinvp[2];
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          zp[pr][j] = make_float2(zr[2 * pr][j], zr[2 * pr + 1][j]);
+          vp[pr][j] = make_float2(vr[2 * pr][j], vr[2 * pr + 1][j]);
+        }
+        s2p[pr] = make_float2(s2r[2 * pr], s2r[2 * pr + 1]);
+        qinvp[pr] = make_float2(qinv[2 * pr], qinv[2 * pr + 1]);
+      }
       auto do_part = [&](const bool isB, const bool from_global) {
         float* part = (isB ? a.partB : a.partA) + (size_t)((un.t * 8 + (int)rank * 4 + q4) * NF) * Hq;
-        float dz4[4][D];
+        float2 dzp[2][D];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int pr = 0; pr < 2; ++pr)
 #pragma unroll
-          for (int j = 0; j < D; ++j) dz4[r][j] = 0.f;
+          for (int j = 0; j < D; ++j) dzp[pr][j] = make_float2(0.f, 0.f);
+        float2 s2x2p[2];                                       // 2 s2 (and the tensor scale of B2g when the accumulator is raw)
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+          const float k2 = (F16 && !from_global) ? 2.f * inv_s2 : 2.f;
+          s2x2p[pr] = __fmul2_rn(s2p[pr], make_float2(k2, k2));
+        }
         if (!from_global) {
           mbar_wait_parked(accfull0 + 8 * buf, (i >> 1) & 1, 2000);
           tc_fence_after();
@@ -1078,53 +1098,69 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
             tmem_ld_wait();
           }
           float vals[8 * NF];
+          uint32_t wsh[4];                                         // my rows' mask words of this chunk, my column pair at bit 0
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            wsh[r] = (cc == 0 ? mw[r].x : (cc == 1 ? mw[r].y : (cc == 2 ? mw[r].z : mw[r].w))) >> cp2;
           if (!isB) {
 #pragma unroll
             for (int n = 0; n < 4; ++n)
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const float4 q = A0qs[nb + 8 * n + cp2 + e];
-                float ef[NF];
+                float2 ef[NF];
 #pragma unroll
-                for (int f = 0; f < NF; ++f) ef[f] = 0.f;
+                for (int f = 0; f < NF; ++f) ef[f] = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                  const float acc = __uint_as_float((r < 2 ? ra : rb)[4 * n + 2 * (r & 1) + e]);
-                  const float h0 = lin_of<D>(q, zr[r]), u0 = dot_of<D>(q, vr[r]);
-                  const float s2x2 = (F16 && !from_global) ? (2.f * inv_s2) * s2r[r] : 2.f * s2r[r];   // (tensor scale of B2g)
-                  const float mc = acc * (h0 > 0.f ? s2x2 : (kSlope * kSlope) * s2x2);   // 2 s2 s0^2 acc
-                  const float t0 = mc * u0;                                               // u0 2 gx1 s0^2
+                for (int pr = 0; pr < 2; ++pr) {
+                  const uint32_t* rr = pr ? rb : ra;
+                  const float2 acc = make_float2(__uint_as_float(rr[4 * n + e]), __uint_as_float(rr[4 * n + 2 + e]));
+                  float2 h0 = __ffma2_rn(make_float2(q.x, q.x), zp[pr][0], make_float2(q.w, q.w));
+                  float2 u0 = __fmul2_rn(make_float2(q.x, q.x), vp[pr][0]);
+                  if (D > 1) {
+                    h0 = __ffma2_rn(make_float2(q.y, q.y), zp[pr][D > 1 ? 1 : 0], h0);
+                    u0 = __ffma2_rn(make_float2(q.y, q.y), vp[pr][D > 1 ? 1 : 0], u0);
+                  }
+                  if (D > 2) {
+                    h0 = __ffma2_rn(make_float2(q.z, q.z), zp[pr][D > 2 ? 2 : 0], h0);
+                    u0 = __ffma2_rn(make_float2(q.z, q.z), vp[pr][D > 2 ? 2 : 0], u0);
+                  }
+                  const float2 s0sq = make_float2(h0.x > 0.f ? 1.f : kSlope * kSlope, h0.y > 0.f ? 1.f : kSlope * kSlope);
+                  const float2 mc = __fmul2_rn(__fmul2_rn(acc, s2x2p[pr]), s0sq);         // 2 s2 s0^2 acc
+                  const float2 t0 = __fmul2_rn(mc, u0);                                   // u0 2 gx1 s0^2
 #pragma unroll
                   for (int j = 0; j < D; ++j) {
-                    dz4[r][j] = fmaf(comp(q, j), t0, dz4[r][j]);
-                    ef[j] = fmaf(mc, fmaf(h0, vr[r][j], u0 * zr[r][j]), ef[j]);           // g0 v_j + t0 z_j
+                    const float qj = comp(q, j);
+                    dzp[pr][j] = __ffma2_rn(make_float2(qj, qj), t0, dzp[pr][j]);
+                    ef[j] = __ffma2_rn(mc, __ffma2_rn(h0, vp[pr][j], __fmul2_rn(u0, zp[pr][j])), ef[j]);   // g0 v_j + t0 z_j
                   }
-                  ef[D] += t0;
+                  ef[D] = __fadd2_rn(ef[D], t0);
                 }
 #pragma unroll
-                for (int f = 0; f < NF; ++f) vals[(2 * n + e) * NF + f] = ef[f];
+                for (int f = 0; f < NF; ++f) vals[(2 * n + e) * NF + f] = ef[f].x + ef[f].y;
               }
           } else {
 #pragma unroll
             for (int n = 0; n < 4; ++n)
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const int bitpos = 8 * n + cp2 + e;
-                float ef[NF];
+                const uint32_t bit = 1u << (8 * n + e);                    // (shifted by cp2 below: cp2 is a run-time lane value)
+                float2 ef[NF];
 #pragma unroll
-                for (int f = 0; f < NF; ++f) ef[f] = 0.f;
+                for (int f = 0; f < NF; ++f) ef[f] = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                  const uint32_t wd = cc == 0 ? mw[r].x : (cc == 1 ? mw[r].y : (cc == 2 ? mw[r].z : mw[r].w));
-                  const float w1 = __uint_as_float((r < 2 ? ra : rb)[4 * n + 2 * (r & 1) + e]);
-                  const float c1 = ((wd >> bitpos) & 1u) ? s2r[r] : kSlope * s2r[r];      // s2 s1
+                for (int pr = 0; pr < 2; ++pr) {
+                  const uint32_t* rr = pr ? rb : ra;
+                  const float2 w1 = make_float2(__uint_as_float(rr[4 * n + e]), __uint_as_float(rr[4 * n + 2 + e]));
+                  const float2 c1 = make_float2((wsh[2 * pr] & bit) ? s2p[pr].x : kSlope * s2p[pr].x,
+                                                (wsh[2 * pr + 1] & bit) ? s2p[pr].y : kSlope * s2p[pr].y);   // s2 s1
 #pragma unroll
-                  for (int j = 0; j < D; ++j) ef[j] = fmaf(c1, vr[r][j], ef[j]);
+                  for (int j = 0; j < D; ++j) ef[j] = __ffma2_rn(c1, vp[pr][j], ef[j]);
                   // FP16 mode: the accumulator holds P q1 only (scaled); the A1 v part of w1 is added after the fold
-                  ef[D] = fmaf(F16 ? c1 * qinv[r] : c1, w1, ef[D]);
+                  ef[D] = __ffma2_rn(F16 ? __fmul2_rn(c1, qinvp[pr]) : c1, w1, ef[D]);
                 }
 #pragma unroll
-                for (int f = 0; f < NF; ++f) vals[(2 * n + e) * NF + f] = ef[f];
+                for (int f = 0; f < NF; ++f) vals[(2 * n + e) * NF + f] = ef[f].x + ef[f].y;
               }
           }
           fold8<8 * NF>(vals, lane);
@@ -1151,7 +1187,7 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
             float o[3] = {0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-              float t = dz4[r][j];
+              float t = (r & 1) ? dzp[r >> 1][j].y : dzp[r >> 1][j].x;
               t += __shfl_xor_sync(0xffffffffu, t, 1);
               t += __shfl_xor_sync(0xffffffffu, t, 2);
               o[j] = t;
