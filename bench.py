@@ -497,8 +497,8 @@ def run_ours(args, rank, local_rank, world):
         run_step(dev_pool[i % n_pool])
 
     def step_e2e(i):
-        if use_graph:
-            total, _, _ = tr.step_graphed(host_pool[i % n_pool])          # H2D straight into the graph's input
+        if use_graph:      # H2D of THIS step's batch was started by the previous call (next_x): it overlaps that step
+            total, _, _ = tr.step_graphed(host_pool[i % n_pool], next_x=host_pool[(i + 1) % n_pool])
         else:
             total, _, _ = tr.step(host_pool[i % n_pool].to(dev, non_blocking=True))
         loss_host.copy_(total.reshape(1), non_blocking=True)
@@ -513,7 +513,7 @@ def run_ours(args, rank, local_rank, world):
 
     def step_e2e_pipelined(i):
         if use_graph:
-            total, _, _ = tr.step_graphed(host_pool[i % n_pool])
+            total, _, _ = tr.step_graphed(host_pool[i % n_pool], next_x=host_pool[(i + 1) % n_pool])
         else:
             total, _, _ = tr.step(host_pool[i % n_pool].to(dev, non_blocking=True))
         loss_ring[i & 1:(i & 1) + 1].copy_(total.reshape(1), non_blocking=True)
@@ -676,8 +676,9 @@ def run_ours(args, rank, local_rank, world):
                         "own_kernel_launches_per_step": int(launches_per_step)},
                 "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 2 * 4 * world,
                         "d2h_bytes_per_step": 4 * world,
-                        "how": "every step: pinned host batch -> device, whole-step graph, loss -> pinned host, host blocks "
-                               "on the stream before the next step",
+                        "how": "every step: pinned host batch -> device (copy stream, started one step ahead like a prefetching "
+                               "loader: step_graphed(x, next_x=...)), whole-step graph, loss -> pinned host, host blocks on the "
+                               "stream before the next step",
                         "pipelined": {"value": world * B / (ms_e2e_pipe * 1e-3), "ms_per_step": ms_e2e_pipe,
                                       "how": "same copies every step; the host reads loss i after enqueueing step i+1",
                                       "losses_read": len(seen)}},

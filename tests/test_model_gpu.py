@@ -646,3 +646,25 @@ def test_early_prepare_on_side_streams_changes_nothing():
         assert float(la) == float(lb)
     torch.cuda.synchronize()
     assert torch.equal(ta.fp.flat, tb.fp.flat) and not ops._EARLY
+
+
+def test_step_graphed_prefetch_of_the_next_host_batch():
+    """step_graphed(x, next_x=...) starts the next batch's host-to-device copy on a copy stream while this step runs; the
+    following call recognises the tensor and takes the staged copy.  Same trajectory as feeding device tensors."""
+    import copy
+    from vae_song_b200 import train
+    m, _ = _load("pin_small")
+    m2 = copy.deepcopy(m)
+    a, b = train.DataParallelTrainer(m, lr=1e-3), train.DataParallelTrainer(m2, lr=1e-3)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    xs = [torch.randn(256, 2, device="cuda", generator=g) for _ in range(6)]
+    es = [torch.randn(256, 2, device="cuda", generator=g) for _ in range(6)]
+    hs = [x.cpu().pin_memory() for x in xs]
+    a.capture(xs[0], es[0]); b.capture(xs[0], es[0])
+    for i in range(6):
+        nxt = hs[i + 1] if i + 1 < 6 and i != 2 else None          # one step without a prefetch in the middle
+        la = a.step_graphed(hs[i], es[i], next_x=nxt)[0].clone()
+        lb = b.step_graphed(xs[i], es[i])[0].clone()
+        assert float(la) == float(lb), i
+    torch.cuda.synchronize()
+    assert torch.equal(a.fp.flat, b.fp.flat)

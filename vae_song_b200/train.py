@@ -214,6 +214,8 @@ class DataParallelTrainer:
         # step still captures into one CUDA graph (the reference's LR-VAE loop is otherwise host bound at its batch sizes)
         self.staged = bool(staged_backward)
         self.forward_kwargs = dict(forward_kwargs or {})       # e.g. {"L": 4}: num_mc_samples of main.py:259
+        self._staged = None            # (host tensor, staging slot, copy-done event) of a prefetched batch (step_graphed)
+        self._stage = None
         # lr_schedule = ("cosine", T_max): CosineAnnealingLR stepped after every optimiser step (main.py:201-203, 287),
         # evaluated on the device from the step counter so that graph replay follows it (single-GPU / NCCL path)
         if lr_schedule is not None and (lr_schedule[0] != "cosine" or int(lr_schedule[1]) <= 0):
@@ -297,17 +299,47 @@ class DataParallelTrainer:
         self._graph = g
         return self
 
-    def step_graphed(self, x_local, eps_local=None):
+    def step_graphed(self, x_local, eps_local=None, next_x=None):
+        """Replay the captured step on `x_local` (device or pinned host tensor).  `next_x`: the NEXT step's batch, if it is a
+        host tensor -- its host-to-device copy is started on a copy stream right away and overlaps this step (a prefetching
+        loader in one argument); the next call recognises the tensor and takes the staged copy."""
         if self._graph is None:
             raise RuntimeError("call capture() first")
-        self._sx.copy_(x_local, non_blocking=True)
+        cur = torch.cuda.current_stream(self._sx.device)
+        if self._staged is not None and x_local is self._staged[0]:
+            _, slot, ev = self._staged
+            cur.wait_event(ev)
+            self._sx.copy_(self._stage[slot], non_blocking=True)
+            self._stage_read[slot].record(cur)
+        else:
+            self._sx.copy_(x_local, non_blocking=True)
+        self._staged = None
         if eps_local is not None:
             self._se.copy_(eps_local, non_blocking=True)
         self._graph.replay()
         ops.bump_weights_epoch()          # the replayed Adam kernel changed the weights without any Python running
+        if next_x is not None and not next_x.is_cuda:
+            self._prefetch(next_x)
         self.t += 1
         self._poll()
         return self._sout
+
+    def _prefetch(self, x_host):
+        dev = self._sx.device
+        if self._stage is None:
+            self._stage = [torch.empty_like(self._sx) for _ in range(2)]
+            self._stage_read = [torch.cuda.Event() for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage_slot = 0
+            for ev in self._stage_read:
+                ev.record(torch.cuda.current_stream(dev))
+        slot = self._stage_slot = 1 - self._stage_slot
+        self._copy_stream.wait_event(self._stage_read[slot])       # the step that last read this staging slot is done with it
+        with torch.cuda.stream(self._copy_stream):
+            self._stage[slot].copy_(x_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._staged = (x_host, slot, ev)
 
     def _poll(self):
         if self.peer is not None and self.check_every and self.t % self.check_every == 0:
