@@ -8,7 +8,7 @@
 //   row : h2 = sum partials + A2 z + b2 -> psi, s2            (small SIMT kernel)
 //   gx1 : g0' = (g1b P0) * 2 a0 s0                            (s2 factored out: it is a per-row scalar)
 //   out : xhat = s2 * (g0' A0 + g1b A1 + A2) + 2 kappa z
-// Kernel: CTA tile 128 x 256, K in 16-float blocks (64-byte rows, SWIZZLE_64B), 4-stage ring.  Warp 8 streams BOTH
+// Kernel: CTA tile 128 x 256, K in 16-float blocks (64-byte rows, SWIZZLE_64B), 6- / 8-stage ring.  Warp 8 streams BOTH
 // operands with TMA (out-of-bounds rows/columns are zero filled: ragged B, d, H need no special cases); warps 0-7 apply
 // the elementwise transform to the raw A tile IN PLACE in shared memory (the swizzle does not matter for an elementwise
 // pass) and split it into tf32 hi / lo; warp 9 issues tcgen05.mma.kind::tf32 (3 MMAs per product at 3xTF32, B hi/lo
@@ -23,7 +23,6 @@
 namespace b200vae {
 
 constexpr int kWtThreads = 10 * 32;
-constexpr int kWtStages = 4;
 constexpr int kWtATile = 128 * 64;
 // Accumulation accuracy at 3xTF32.  tcgen05 adds into its fp32 accumulator with truncation: a downward bias that grows with
 // the number of MMAs per accumulator times the accumulator's magnitude (measured on psi of ICNN(784,1024): 3.0e-5 with the
@@ -67,16 +66,20 @@ struct WtCfg {
   static constexpr int kStage = kWtATile * (X3 ? 2 : 1) + kBTile * (X3 ? 2 : 1);
   static constexpr int kOffAlo = kWtATile, kOffB = kWtATile * (X3 ? 2 : 1), kOffBlo = kOffB + kBTile;
   static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // ring depth (template parameter of the kernel): as many stages as fit -- 6 x 32 KB / 8 x 24 KB -- where the grid is at
+  // most one wave: at the configs' own batch (256 rows = 2 row tiles) a GEMM is a latency chain TMA -> transform -> MMA per
+  // K-block and its time is (K-blocks / stages) x that latency (B = 256 decode 0.344 -> 0.309 ms).  Larger 3xTF32 grids keep
+  // 4 stages: the deep ring leaves ~30 KB of L1 for the epilogue's parameter reads (B = 8192 decode 0.58 -> 0.82 ms with 6).
+  static constexpr int kDeep = X3 ? 6 : 8, kShallow = X3 ? 4 : 8;
 };
 inline int wt_tile_n(bool x3) { return x3 ? 128 : 256; }
 template <bool X3>
-static size_t wt_smem_bytes() { return (size_t)kWtStages * WtCfg<X3>::kStage + (3 * kWtStages + 1) * 8 + 16 + 1024; }
+static size_t wt_smem_bytes(int S) { return (size_t)S * WtCfg<X3>::kStage + (3 * S + 1) * 8 + 16 + 1024; }
 
-template <bool X3>
+template <bool X3, int S>
 __global__ void __launch_bounds__(kWtThreads, 1)
 wide_tc_gemm_kernel(const __grid_constant__ WtArgs a) {
   using C = WtCfg<X3>;
-  constexpr int S = kWtStages;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stages = smem;
@@ -487,17 +490,23 @@ static int wt_map(CUtensorMap* m, const float* base, int K, int rows, int ld, in
   return B200VAE_OK;
 }
 
-template <bool X3>
-static int wt_launch(const WtArgs& args, int splits, cudaStream_t st) {
+template <bool X3, int S>
+static int wt_launch_s(const WtArgs& args, dim3 grid, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(wide_tc_gemm_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(wide_tc_gemm_kernel<X3, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_done = true;
   }
+  wide_tc_gemm_kernel<X3, S><<<grid, kWtThreads, wt_smem_bytes<X3>(S), st>>>(args);
+  return check_launch();
+}
+template <bool X3>
+static int wt_launch(const WtArgs& args, int splits, cudaStream_t st) {
   constexpr int NT = WtCfg<X3>::NT;
   dim3 grid((args.M + 127) / 128, (args.N + NT - 1) / NT, splits);
-  wide_tc_gemm_kernel<X3><<<grid, kWtThreads, wt_smem_bytes<X3>(), st>>>(args);
-  return check_launch();
+  const bool one_wave = (long long)grid.x * grid.y * grid.z <= sm_count();
+  if (WtCfg<X3>::kDeep != WtCfg<X3>::kShallow && !one_wave) return wt_launch_s<X3, WtCfg<X3>::kShallow>(args, grid, st);
+  return wt_launch_s<X3, WtCfg<X3>::kDeep>(args, grid, st);
 }
 static int wt_run(const WtArgs& args, bool x3, cudaStream_t st, int splits = 1) {
   return x3 ? wt_launch<true>(args, splits, st) : wt_launch<false>(args, splits, st);
