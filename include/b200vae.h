@@ -44,7 +44,9 @@ extern "C" {
 /* fp32-grade at half the tensor time of 3xTF32: both operands split into FP16 hi/lo pairs (22 mantissa bits, like a tf32
  * pair), three tcgen05 kind::f16 MMAs per K step, every operand scaled by an exact power of two into the fp16 range (per
  * tensor for the prepared weights, per sample row for the generated operands) and unscaled in the epilogue.  Same bounds as
- * TF32X3 / FP32.  d <= 3 and H <= 1024 (the CTA-pair kernels); other shapes and the wide-input entry points run TF32X3. */
+ * TF32X3 / FP32.  The wide-input entry points run TF32X3 for it.
+ * Every tensor-core precision (TF32, TF32X3, F16X3) of the d <= 4 entry points needs d <= 3 and H <= 1024 and returns
+ * B200VAE_EUNSUP otherwise; FP32 takes d <= 4, H <= 4096. */
 #define B200VAE_PREC_F16X3 4
 
 /* Parameters of one module.ICNN(in_channel=d, hidden_channel=H) -- module.py:117-140.

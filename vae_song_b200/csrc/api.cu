@@ -136,7 +136,7 @@ extern "C" int b200vae_icnn_decode_fwd(const float* z, int B, int d, int H, int 
   if (precision == B200VAE_PREC_FP32)
     return simt_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, ws_base(ws), (cudaStream_t)stream);
   // forward kernel variant, B200VAE_FWD = 3 (default): persistent CTA pairs (icnn_tc3.cu), falling back to 1 where it
-  // does not fit (H > 1024); 1: single-CTA kernel (icnn_tc.cu)
+  // does not take the shape; 1: single-CTA kernel (icnn_tc.cu).  H > 1024 fits neither: EUNSUP
   static const int variant = [] { const char* e = getenv("B200VAE_FWD"); return e ? atoi(e) : 3; }();
   if (variant == 3) {
     float* accsave = nullptr;

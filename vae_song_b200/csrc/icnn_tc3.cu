@@ -44,6 +44,8 @@ constexpr int k3Rows = 128;                       // sample rows per CTA
 constexpr int k3Threads = 18 * 32;                // 8 epilogue warps, 8 generator warps, TMA warp, MMA warp
 constexpr int k3TileBytes = k3Rows * 64;          // 128 rows x 64 B = 8 KB (A tile, and this CTA's half of a B tile)
 constexpr int k3MaskStride = 36;                  // words per row of the shared mask buffer (16 B aligned, conflict free)
+constexpr int kTc3MaxHq = 1024;                   // a mask row must fit the buffer (Hq / 32 <= 36, Hq a multiple of 256): wider
+                                                  // ICNNs run the single-CTA kernels of icnn_tc.cu
 constexpr uint32_t k3Idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 __device__ __forceinline__ uint32_t cluster_rank3() {
@@ -1548,7 +1550,7 @@ typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 // arithmetic of the pair kernels for an ABI precision id: FP16 hi/lo where its tables fit in shared memory (Hq <= 1024)
 static int tc3_mode(int precision, int Hq) {
-  if (precision == B200VAE_PREC_F16X3) return tc3_smem_bytes<kF16>(Hq) <= (size_t)227 * 1024 ? kF16 : kX3;
+  if (precision == B200VAE_PREC_F16X3) return (Hq <= kTc3MaxHq && tc3_smem_bytes<kF16>(Hq) <= (size_t)227 * 1024) ? kF16 : kX3;
   return precision == B200VAE_PREC_TF32X3 ? kX3 : kTf32;
 }
 static int make_map3(CUtensorMap* m, const float* base, int K, int rows, bool f16 = false) {
@@ -2225,7 +2227,7 @@ int tc3_dp0(const float* z, const float* v, const uint32_t* mask1, const uint8_t
 template <int D, int MODE, bool SV>
 static int launch_tc3_bwd(const Tc3BwdArgs& args, cudaStream_t st) {
   const size_t smem = tc3_smem_bytes<MODE>(args.Hq);
-  if (smem > 227 * 1024) return B200VAE_EUNSUP;
+  if (smem > 227 * 1024 || args.Hq > kTc3MaxHq) return B200VAE_EUNSUP;
   static int max_clusters = 0;
   if (max_clusters == 0) max_clusters = max_clusters_for(reinterpret_cast<const void*>(icnn_tc3_bwd_kernel<D, MODE, SV>), smem);
   const int units = (SV ? 1 : 2) * args.T * args.NP;
@@ -2285,7 +2287,7 @@ size_t tc3_bwd_ws_floats(int B, int d, int H) {
 template <int D, int MODE>
 static int launch_tc3(const Tc3Args& args, int units, cudaStream_t st) {
   const size_t smem = tc3_smem_bytes<MODE>(args.Hq);
-  if (smem > 227 * 1024) return B200VAE_EUNSUP;
+  if (smem > 227 * 1024 || args.Hq > kTc3MaxHq) return B200VAE_EUNSUP;
   static int max_clusters = 0;
   if (max_clusters == 0) max_clusters = max_clusters_for(reinterpret_cast<const void*>(icnn_tc3_fwd_kernel<D, MODE>), smem);
   // every cluster must be resident (GEMM2 units wait for GEMM1 units of other clusters): never exceed one wave
