@@ -2333,8 +2333,9 @@ int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float*
   args.accsave = args.want_x ? accsave : nullptr;
   args.B = B; args.Hq = T3.Hq; args.T = T3.Bp / 256; args.NP = T3.NP; args.kappa = kappa;
   // hi/lo modes: accumulate K in chunks of kTc3ChunkK (B200VAE_KCHUNK overrides: a multiple of 64 dividing Hq; 0 = one
-  // chunk).  FP16 mode at H = 1024, default-init weights: psi error 8.7e-6 in one piece (0.459 ms), 4.0e-6 in two chunks
-  // (0.49 ms, wherever the split point lies -- 512 ... 768 measured), 2.0e-6 in four (0.544 ms)
+  // chunk).  FP16 mode at H = 1024, default-init weights: psi error 8.7e-6 in one piece (0.453 ms), 4.0e-6 in two chunks
+  // (0.474 ms, wherever the split point lies -- 512 ... 768 measured; the 21 us are the drain's L2 traffic: 14 us its
+  // stores, 6 us the loads of the last chunk's epilogue -- measured by leaving each out), 2.0e-6 in four (0.544 ms)
   static const int chunk_env = [] { const char* e = getenv("B200VAE_KCHUNK"); return e ? atoi(e) : -1; }();
   const int chunk_k = chunk_env >= 0 ? chunk_env : kTc3ChunkK;
   static const int park_ns = [] { const char* e = getenv("B200VAE_PARK_NS"); return e ? atoi(e) : 2000; }();
