@@ -867,29 +867,29 @@ icnn_tc_dP0_kernel(const float* __restrict__ z, const float* __restrict__ v, con
 }
 
 // ordered reduction of the row-kernel partials + chain through the positive reparam for W1.
-// grid (Hq/32, NF, 2): one block sums all `nslots` partial rows of 32 columns (8 slot lanes x 32 columns,
+// grid (Hq/32, NF, 2): one block of 1024 threads sums all `nslots` partial rows of 32 columns (32 slot lanes x 32 columns,
 // coalesced 128-byte reads, fixed summation order -> deterministic).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 tc_finalize_small_kernel(const float* __restrict__ partA, const float* __restrict__ partB,
                          const float* __restrict__ a2part, int nslots, int nmt, int d, int H, int Hq,
                          const float* __restrict__ P1, const float* __restrict__ W1raw, int mode, b200vae_icnn_grads g) {
-  __shared__ float red[8][33];
+  __shared__ float red[32][33];
   const int NF = d + 1;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx, f = blockIdx.y, which = blockIdx.z;
   const float* part = (which ? partB : partA) + (size_t)f * Hq + n;
-  // 16 independent partial sums per thread: the kernel is latency bound (2048 slots x 128-byte rows per block at
-  // B = 65536), so the number of loads in flight is what sets its duration
+  // 16 independent partial sums per thread, 32 slot lanes per block: the kernel is latency bound (2048 slots x 128-byte
+  // rows per block at B = 65536), so the number of loads in flight is what sets its duration (8 slot lanes: 21 us)
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   int sl = ty;
   const size_t stride = (size_t)NF * Hq;
-  for (; sl + 120 < nslots; sl += 128) {
+  for (; sl + 480 < nslots; sl += 512) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] += part[(size_t)(sl + 8 * i) * stride];
+    for (int i = 0; i < 16; ++i) acc[i] += part[(size_t)(sl + 32 * i) * stride];
   }
-  for (; sl < nslots; sl += 8) acc[0] += part[(size_t)sl * stride];
+  for (; sl < nslots; sl += 32) acc[0] += part[(size_t)sl * stride];
 #pragma unroll
   for (int w = 8; w >= 1; w >>= 1)
 #pragma unroll
@@ -899,7 +899,7 @@ tc_finalize_small_kernel(const float* __restrict__ partA, const float* __restric
   if (ty == 0 && n < H) {
     float s = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) s += red[q][tx];
+    for (int q = 0; q < 32; ++q) s += red[q][tx];
     if (!which) {
       if (f < d) { if (g.A0w) g.A0w[(size_t)n * d + f] = s; }
       else if (g.A0b) g.A0b[n] = s;
@@ -1151,7 +1151,7 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
     if (rc) return rc;
   }
   dim3 fgrid(T.Hq / 32, d + 1, 2);
-  tc_finalize_small_kernel<<<fgrid, 256, 0, st>>>(partA, partB, a2part, (int)nmt * 8, (int)nmt, d, H, T.Hq, ws + L.P1,
+  tc_finalize_small_kernel<<<fgrid, 1024, 0, st>>>(partA, partB, a2part, (int)nmt * 8, (int)nmt, d, H, T.Hq, ws + L.P1,
                                                   p->W1, mode, *g);
   return check_launch();
 }
