@@ -93,6 +93,18 @@ int b200vae_icnn_decode_bwd(const float* z, const float* v, const float* gpsi, c
                             const b200vae_icnn_grads* grads, float* dz, int precision, void* ws,
                             size_t ws_bytes, void* stream);
 
+/* Second half of b200vae_icnn_decode_bwd for the tensor-core precisions, so that a training step can take it off its critical
+ * path: call b200vae_icnn_decode_bwd with grads = NULL first (dz + the ordered column partials, left in the workspace), hand
+ * dz to the encoder's backward, and run THIS call -- the batch-reduced H x H weight gradient and the finalize kernels, about
+ * 40 % of the backward's time -- on another stream while the encoder's small kernels leave the GPU mostly idle.  Same z, v,
+ * masks, sizes and workspace as the first call; the caller orders the two calls (this one after the first) and joins the
+ * streams before reading `grads`.  Replaces nothing new in the reference: it is the parameter half of what autograd runs
+ * for lipschitz.py:41.  FP32 precision: B200VAE_EUNSUP (use the one-call form). */
+int b200vae_icnn_decode_bwd_params(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B,
+                                   int d, int H, const b200vae_icnn_params* p, int weight_mode,
+                                   const b200vae_icnn_grads* grads, int precision, void* ws, size_t ws_bytes,
+                                   void* stream);
+
 /* Fused reparameterisation + Gaussian KL + reconstruction (+ latent reconstruction).
  * Replaces model.py:843 / :423-424 (z = mu + eps*exp(lv/2)), :884/:550/:606 (KL), :870/:542/:589
  * (MSE) or :872-882 (log-MSE), :551/:603 (latent recon, mean over dim 0 = L).

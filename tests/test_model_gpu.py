@@ -583,3 +583,44 @@ def test_step_graphed_prefetch_of_the_next_host_batch():
         assert float(la) == float(lb), i
     torch.cuda.synchronize()
     assert torch.equal(a.fp.flat, b.fp.flat)
+
+
+def test_deferred_parameter_gradients_change_nothing():
+    """DataParallelTrainer.step launches the parameter half of every tensor-core ICNN backward (b200vae_icnn_decode_bwd_params)
+    on a side stream beside the encoder's backward and joins before it gathers the gradients: bit-identical training,
+    eagerly and as a replayed graph; a model that uses one ICNN twice in a step falls back to in-order execution."""
+    import copy
+    from vae_song_b200 import model, ops, train
+    torch.manual_seed(4)
+    m0 = model.LIDVAE(dataset="pinwheel", icnn_channels=[64, 128], hidden_channels=[8, 4], inverse_lipschitz=0.2,
+                      precision="f16x3").cuda().train()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    xs = [torch.randn(300, 2, device="cuda", generator=g) for _ in range(5)]
+    es = [torch.randn(300, 2, device="cuda", generator=g) for _ in range(5)]
+    ma, mb, mc = copy.deepcopy(m0), copy.deepcopy(m0), copy.deepcopy(m0)
+    ta, tb, tc_ = (train.DataParallelTrainer(m, lr=1e-3) for m in (ma, mb, mc))
+    tb.defer_param_grads = False
+    assert ta.defer_param_grads
+    tc_.capture(xs[0], es[0])
+    for x, e in zip(xs, es):
+        la, lb, lc = ta.step(x, e)[0], tb.step(x, e)[0], tc_.step_graphed(x, e)[0].clone()
+        assert float(la) == float(lb) == float(lc)
+    torch.cuda.synchronize()
+    assert torch.equal(ta.fp.flat, tb.fp.flat) and torch.equal(ta.fp.flat, tc_.fp.flat)
+    assert not ops._DEFER["keep"] and not ops._DEFER["seen"] and not ops._DEFER["on"]
+    # the same ICNN twice inside one deferred backward: second call joins first, gradients add up correctly
+    ic = m0.decoder[0]
+    z1 = torch.randn(64, 2, device="cuda", requires_grad=True)
+    z2 = torch.randn(64, 2, device="cuda", requires_grad=True)
+
+    def twice():
+        for p in ic.parameters():
+            p.grad = None
+        (ic.brenier(z1, 0.1)[1].sum() + 2.0 * ic.brenier(z2, 0.1)[1].sum()).backward()
+        return [p.grad.clone() for p in ic.parameters()]
+    want = twice()
+    with ops.deferred_param_grads():
+        got = twice()
+    torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)

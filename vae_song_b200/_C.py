@@ -24,6 +24,7 @@ _ERR = {-1: "bad shape", -2: "unsupported configuration", -3: "null or misaligne
 
 EXPORTS = [
     "b200vae_icnn_workspace_bytes", "b200vae_icnn_prepare", "b200vae_icnn_decode_fwd", "b200vae_icnn_decode_bwd",
+    "b200vae_icnn_decode_bwd_params",
     "b200vae_loss_fwd", "b200vae_loss_bwd", "b200vae_lipschitz_pairs", "b200vae_lipschitz_allpairs",
     "b200vae_lipschitz_num_tiles", "b200vae_lipschitz_scratch_bytes", "b200vae_adam_step", "b200vae_adam_step_dev", "b200vae_adam_step_sched", "b200vae_mlp_scratch_bytes", "b200vae_mlp_layer_fwd",
     "b200vae_mlp_layer_bwd_reduce", "b200vae_mlp_layer_bwd", "b200vae_nn_sqdist_fwd", "b200vae_nn_sqdist_bwd", "b200vae_last_cuda_error", "b200vae_version",
@@ -88,6 +89,9 @@ def load():
     lib.b200vae_icnn_decode_bwd.restype = i
     lib.b200vae_icnn_decode_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, C.POINTER(IcnnParams), i, f,
                                             C.POINTER(IcnnGrads), vp, i, vp, sz, vp]
+    lib.b200vae_icnn_decode_bwd_params.restype = i
+    lib.b200vae_icnn_decode_bwd_params.argtypes = [vp, vp, vp, vp, i, i, i, C.POINTER(IcnnParams), i, C.POINTER(IcnnGrads), i,
+                                                   vp, sz, vp]
     lib.b200vae_loss_fwd.restype = i
     lib.b200vae_loss_fwd.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp, i, i, vp, vp, vp, i, i, i, vp, vp]
     lib.b200vae_loss_bwd.restype = i

@@ -37,7 +37,7 @@ size_t tc_extra_ws_floats(int B, int d, int H, int precision);
 size_t tc_bwd_ws_floats(int B, int d, int H);
 int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H,
            const b200vae_icnn_params* p, int mode, float kappa, const b200vae_icnn_grads* g, float* dz, int precision,
-           float* ws, const float* accsave, cudaStream_t st);
+           float* ws, const float* accsave, int phase, cudaStream_t st);
 
 // ---- saved GEMM2 accumulators (training, 3xTF32) ------------------------------------------------------------------------
 // With a for_backward workspace and both masks requested, the pair forward kernel also stores its GEMM2 accumulators
@@ -165,12 +165,25 @@ extern "C" int b200vae_icnn_decode_bwd(const float* z, const float* v, const flo
     const float* accsave = nullptr;
     if (accsave_floats(B, d, H, precision) && save_matches(ws_base(ws), z, B, d, H))
       accsave = ws_base(ws) + bwd_floats_without_save(B, d, H, precision);
-    return tc_bwd(z, v, mask1, mask2, B, d, H, p, weight_mode, kappa, grads, dz, precision, ws_base(ws), accsave,
+    return tc_bwd(z, v, mask1, mask2, B, d, H, p, weight_mode, kappa, grads, dz, precision, ws_base(ws), accsave, 0,
                   (cudaStream_t)stream);
   }
   const size_t extra = (precision != B200VAE_PREC_FP32) ? tc_extra_ws_floats(B, d, H, precision) : 0;
   return simt_bwd(z, v, gpsi, mask1, mask2, B, d, H, p, weight_mode, kappa, grads, dz, ws_base(ws), extra,
                   (cudaStream_t)stream);
+}
+
+extern "C" int b200vae_icnn_decode_bwd_params(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2,
+                                              int B, int d, int H, const b200vae_icnn_params* p, int weight_mode,
+                                              const b200vae_icnn_grads* grads, int precision, void* ws, size_t ws_bytes,
+                                              void* stream) {
+  if (!z || !v || !mask1 || !mask2 || !ws || !grads || !params_ok(p)) return B200VAE_EALIGN;
+  int rc = shape_ok(B, d, H);
+  if (rc) return rc;
+  if (!prec_ok(precision) || precision == B200VAE_PREC_FP32) return B200VAE_EUNSUP;
+  if (ws_bytes < b200vae_icnn_workspace_bytes(B, d, H, precision, 1)) return B200VAE_EWS;
+  return tc_bwd(z, v, mask1, mask2, B, d, H, p, weight_mode, 0.f, grads, nullptr, precision, ws_base(ws), nullptr, 2,
+                (cudaStream_t)stream);
 }
 
 extern "C" int b200vae_last_cuda_error(void) { return g_last_cuda_error; }

@@ -1086,9 +1086,11 @@ static int launch_tc_dp0(const float* z, const float* v, const uint32_t* mask1, 
   return check_launch();
 }
 
+// phase 0: everything; 1: the rows part only (dz + the ordered column partials in the workspace); 2: the parameter
+// gradients only (dP0 + the finalize kernels), from the partials a phase-1 call left in the SAME workspace
 int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t* mask2, int B, int d, int H,
            const b200vae_icnn_params* p, int mode, float kappa, const b200vae_icnn_grads* g, float* dz, int precision,
-           float* ws, const float* accsave, cudaStream_t st) {
+           float* ws, const float* accsave, int phase, cudaStream_t st) {
   if (precision == 2 /* reserved */ || d > 3 || !v) return B200VAE_EUNSUP;
   const size_t extra = tc_extra_ws_floats(B, d, H, precision);
   const WsLayout L = ws_layout(B, d, H, extra);
@@ -1107,8 +1109,8 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
   static const int variant = [] { const char* e = getenv("B200VAE_BWD"); return e ? atoi(e) : 3; }();
   float* dp0part = a2part + nmt * 4 + 64;
   dp0part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dp0part) + 15) & ~(uintptr_t)15);
-  rc = B200VAE_EUNSUP;
-  if (variant == 3) {
+  rc = phase == 2 ? B200VAE_OK : B200VAE_EUNSUP;
+  if (variant == 3 && phase != 2) {
     float* dzpart = dp0part + (size_t)tc_dp0_splits(B, T.Hq) * T.Hq * T.Hq;
     dzpart = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dzpart) + 15) & ~(uintptr_t)15);
     rc = tc3_bwd_rows(z, v, mask1, mask2, B, d, H, kappa, dz, partA, partB, a2part, dzpart, precision, ws, accsave, st);
@@ -1125,7 +1127,7 @@ int tc_bwd(const float* z, const float* v, const uint32_t* mask1, const uint8_t*
   }
 #undef B200VAE_TCB
   }
-  if (rc || !g) return rc;
+  if (rc || !g || phase == 1) return rc;
   if (g->W0) {
     float* part = dp0part;
     int splits = tc_dp0_splits(B, T.Hq);

@@ -105,6 +105,40 @@ def icnn_decode_fwd(z, ws, d, H, mode, kappa, precision, want_psi=True, want_xha
     return psi, xhat, mask1, mask2
 
 
+# ---- parameter gradients off the critical path ------------------------------------------------------------------------
+# The backward of an ICNN has two halves: the rows part (dz, needed by whatever produced z -- the encoder) and the parameter
+# gradients (the batch-reduced H x H weight gradient + finalize kernels, ~40 % of the time, needed only by the optimiser).
+# Inside `deferred_param_grads()` the second half of every tensor-core backward is launched on a side stream, so that it
+# overlaps the encoder's backward (a dozen small latency-bound kernels that leave the GPU mostly idle); leaving the context
+# makes the current stream wait for it.  Only code that reads the gradients AFTER the context may use it -- the trainers of
+# this package do (train.DataParallelTrainer.step); plain autograd users never see a gradient from another stream.
+_DEFER = {"on": False, "stream": None, "keep": [], "seen": set()}
+
+
+def _join_deferred(device=None):
+    """Make the current stream wait for the deferred parameter-gradient work, hand the gradients to their parameters and
+    release the tensors the side stream was reading."""
+    if _DEFER["keep"]:
+        torch.cuda.current_stream(device).wait_stream(_DEFER["stream"])
+        for _, _, _, _, _, params, grads in _DEFER["keep"]:
+            for p, g in zip(params, grads):
+                if p.requires_grad:
+                    p.grad = g if p.grad is None else p.grad + g
+        _DEFER["keep"].clear()
+    _DEFER["seen"].clear()
+
+
+class deferred_param_grads:
+    def __enter__(self):
+        _DEFER["on"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _DEFER["on"] = False
+        _join_deferred()
+        return False
+
+
 def icnn_decode_bwd(z, v, gpsi, mask1, mask2, params, ws, d, H, mode, kappa, precision, need_dz=True,
                     need_params=True):
     lib = _C.load()
@@ -116,6 +150,32 @@ def icnn_decode_bwd(z, v, gpsi, mask1, mask2, params, ws, d, H, mode, kappa, pre
         for k, t in zip(PARAM_FIELDS, grads):
             setattr(gs, k, t.data_ptr())
     ps = _params_struct(params)
+    if _DEFER["on"] and grads is not None and gpsi is None and v is not None and precision != _C.PREC_FP32 \
+            and params[6].data_ptr() in _DEFER["seen"]:
+        # the same ICNN a second time in one backward: autograd will ADD the two gradients on this stream right away, so the
+        # first one must be complete -- join, then run this call in one piece
+        _join_deferred(z.device)
+    elif _DEFER["on"] and grads is not None and gpsi is None and v is not None and precision != _C.PREC_FP32:
+        # rows part here (grads = NULL), parameter part on the side stream, ordered after it
+        _C.check(lib.b200vae_icnn_decode_bwd(_ptr(z), _ptr(v), None, _ptr(mask1), _ptr(mask2), B, d, H, C.byref(ps), mode,
+                                             float(kappa), None, _ptr(dz), precision, _ptr(ws), ws.numel(), _stream()),
+                 "icnn_decode_bwd")
+        main = torch.cuda.current_stream(z.device)
+        if _DEFER["stream"] is None or _DEFER["stream"].device != z.device:
+            _DEFER["stream"] = torch.cuda.Stream(z.device)
+        side = _DEFER["stream"]
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _C.check(lib.b200vae_icnn_decode_bwd_params(_ptr(z), _ptr(v), _ptr(mask1), _ptr(mask2), B, d, H, C.byref(ps), mode,
+                                                        C.byref(gs), precision, _ptr(ws), ws.numel(), _stream()),
+                     "icnn_decode_bwd_params")
+        # What the side stream reads must not be recycled by the allocator before the join (autograd frees the saved tensors
+        # as soon as this node has run).  The gradients do NOT travel through autograd (None is returned for them): it would
+        # accumulate -- or, if anybody else holds a reference, clone -- them on THIS stream at once, before the side stream
+        # has written them; the join assigns them to `.grad` instead (`params` are the leaf tensors themselves).
+        _DEFER["keep"].append((z, v, mask1, mask2, ws, params, grads))
+        _DEFER["seen"].add(params[6].data_ptr())
+        return dz, None
     _C.check(lib.b200vae_icnn_decode_bwd(_ptr(z), _ptr(v), _ptr(gpsi), _ptr(mask1), _ptr(mask2), B, d, H, C.byref(ps),
                                          mode, float(kappa), C.byref(gs) if grads is not None else None, _ptr(dz),
                                          precision, _ptr(ws), ws.numel(), _stream()), "icnn_decode_bwd")

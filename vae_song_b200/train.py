@@ -9,6 +9,8 @@ DataParallelTrainer   one process per GPU: batch sharded by rank, parameters and
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 from torch import nn
@@ -214,6 +216,7 @@ class DataParallelTrainer:
         # step still captures into one CUDA graph (the reference's LR-VAE loop is otherwise host bound at its batch sizes)
         self.staged = bool(staged_backward)
         self.forward_kwargs = dict(forward_kwargs or {})       # e.g. {"L": 4}: num_mc_samples of main.py:259
+        self.defer_param_grads = os.environ.get("B200VAE_DEFER_PARAM_GRADS", "1") != "0"      # A/B switch
         self._staged = None            # (host tensor, staging slot, copy-done event) of a prefetched batch (step_graphed)
         self._stage = None
         # lr_schedule = ("cosine", T_max): CosineAnnealingLR stepped after every optimiser step (main.py:201-203, 287),
@@ -364,7 +367,12 @@ class DataParallelTrainer:
             if W > 1 and lr_attached:
                 # ... while every other term is a batch mean -> compensate before the 1/W gradient averaging
                 total = total + (W - 1) * lr_term
-            total.backward()
+            if total.is_cuda and self.defer_param_grads:
+                # the ICNNs' parameter gradients run on a side stream beside the encoder's backward; joined on exit
+                with ops.deferred_param_grads():
+                    total.backward()
+            else:
+                total.backward()
         self.fp.gather()
         clip = bool(self.grad_clip and self.grad_clip.get("enabled", False))
         if self.peer is not None and not clip:
