@@ -411,6 +411,7 @@ class LIDVAE(VAE):
         needed (works under no_grad and on plain tensors, unlike the reference)."""
         for ic in (self.decoder[0], self.decoder[1]):
             ic.precision = self.precision
+        self.decoder[1].defer_param_grads_ok = False     # its dz feeds the first ICNN's backward, not the encoder
         _, x = self.decoder[0].brenier(input, self.il_factor)
         Dx, D = self.B.shape
         # x = x1 B^T (model.py:824): with B = eye(Dx, D) this is a zero-pad, which the wide kernels take implicitly

@@ -103,7 +103,11 @@ class ICNN(nn.Module):
                 self._infer_cache = {}
             return ops.icnn_brenier_inference(input, float(kappa), self._mode(), prec, params, self._infer_cache)
         fn = ops.IcnnBrenierWideFn if wide else ops.IcnnBrenierFn
+        if not wide:
+            ops.set_defer_hint(self.defer_param_grads_ok)
         return fn.apply(input, float(kappa), self._mode(), prec, *params)
+
+    defer_param_grads_ok = True      # see ops.set_defer_hint; model.LIDVAE clears it on its second ICNN
 
 
 class PlainConvolution(nn.Module):

@@ -112,7 +112,14 @@ def icnn_decode_fwd(z, ws, d, H, mode, kappa, precision, want_psi=True, want_xha
 # overlaps the encoder's backward (a dozen small latency-bound kernels that leave the GPU mostly idle); leaving the context
 # makes the current stream wait for it.  Only code that reads the gradients AFTER the context may use it -- the trainers of
 # this package do (train.DataParallelTrainer.step); plain autograd users never see a gradient from another stream.
-_DEFER = {"on": False, "stream": None, "keep": [], "seen": set()}
+_DEFER = {"on": False, "stream": None, "keep": [], "seen": set(), "hint": True}
+
+
+def set_defer_hint(ok):
+    """Called by a module right before it applies IcnnBrenierFn: may THIS call's parameter gradients be deferred?  Deferring
+    pays where the consumer of dz is light (the encoder); where dz feeds another ICNN's backward -- a kernel that wants the
+    whole GPU -- the deferred kernels would only delay it (LIDVAE: second ICNN no, first ICNN yes)."""
+    _DEFER["hint"] = bool(ok)
 
 
 def _join_deferred(device=None):
@@ -140,7 +147,7 @@ class deferred_param_grads:
 
 
 def icnn_decode_bwd(z, v, gpsi, mask1, mask2, params, ws, d, H, mode, kappa, precision, need_dz=True,
-                    need_params=True):
+                    need_params=True, allow_defer=True):
     lib = _C.load()
     B = z.shape[0]
     dz = torch.empty_like(z) if need_dz else None
@@ -150,12 +157,12 @@ def icnn_decode_bwd(z, v, gpsi, mask1, mask2, params, ws, d, H, mode, kappa, pre
         for k, t in zip(PARAM_FIELDS, grads):
             setattr(gs, k, t.data_ptr())
     ps = _params_struct(params)
-    if _DEFER["on"] and grads is not None and gpsi is None and v is not None and precision != _C.PREC_FP32 \
-            and params[6].data_ptr() in _DEFER["seen"]:
+    defer = _DEFER["on"] and allow_defer and grads is not None and gpsi is None and v is not None and precision != _C.PREC_FP32
+    if _DEFER["on"] and grads is not None and params[6].data_ptr() in _DEFER["seen"]:
         # the same ICNN a second time in one backward: autograd will ADD the two gradients on this stream right away, so the
         # first one must be complete -- join, then run this call in one piece
         _join_deferred(z.device)
-    elif _DEFER["on"] and grads is not None and gpsi is None and v is not None and precision != _C.PREC_FP32:
+    elif defer:
         # rows part here (grads = NULL), parameter part on the side stream, ordered after it
         _C.check(lib.b200vae_icnn_decode_bwd(_ptr(z), _ptr(v), None, _ptr(mask1), _ptr(mask2), B, d, H, C.byref(ps), mode,
                                              float(kappa), None, _ptr(dz), precision, _ptr(ws), ws.numel(), _stream()),
@@ -235,6 +242,7 @@ class IcnnBrenierFn(torch.autograd.Function):
         if needs_bwd:
             ctx.save_for_backward(z, m1, m2, ws, *params)
             ctx.cfg = (d, H, mode, float(kappa), precision)
+            ctx.defer_ok, _DEFER["hint"] = _DEFER["hint"], True
         ctx.set_materialize_grads(False)
         return psi, xhat
 
@@ -249,7 +257,7 @@ class IcnnBrenierFn(torch.autograd.Function):
         gp = None if gpsi is None else _req(gpsi, "grad_psi")
         need_params = any(ctx.needs_input_grad[4:])
         dz, grads = icnn_decode_bwd(z, v, gp, m1, m2, params, ws, d, H, mode, kappa, precision,
-                                    need_dz=ctx.needs_input_grad[0], need_params=need_params)
+                                    need_dz=ctx.needs_input_grad[0], need_params=need_params, allow_defer=ctx.defer_ok)
         if grads is None:
             grads = [None] * len(params)
         return (dz, None, None, None, *grads)
