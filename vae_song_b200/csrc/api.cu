@@ -187,5 +187,5 @@ extern "C" int b200vae_icnn_decode_bwd_params(const float* z, const float* v, co
 }
 
 extern "C" int b200vae_last_cuda_error(void) { return g_last_cuda_error; }
-extern "C" const char* b200vae_version(void) { return "b200vae 0.1 (sm_100a)"; }
+extern "C" const char* b200vae_version(void) { return "b200vae 0.2 (sm_100a)"; }
 extern "C" long long b200vae_launch_count(void) { return g_launch_count; }
