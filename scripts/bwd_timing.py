@@ -17,6 +17,13 @@ for H in (512, 1024):
         for prec in precs:
             ws = ops.icnn_prepare(P, 2, H, 0, prec, B, True)
             _, _, m1, m2 = ops.icnn_decode_fwd(z, ws, 2, H, 0, 0.1, prec, True, True, True)
+            tf = []
+            for it in range(6):          # the training-variant forward (masks + saved accumulators)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); ops.icnn_decode_fwd(z, ws, 2, H, 0, 0.1, prec, True, True, True); e1.record()
+                torch.cuda.synchronize()
+                tf.append(e0.elapsed_time(e1))
+            print(f"H={H} prec={prec} training forward: " + " ".join(f"{t:.3f}" for t in tf) + " ms", flush=True)
             ts = []
             for it in range(6):
                 n0 = _C.launch_count()

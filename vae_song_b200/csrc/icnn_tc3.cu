@@ -149,6 +149,10 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ int round_up_dev(int x, int m) { return (x + m - 1) / m * m; }
+// float offset of the saved-accumulator block (tile, cta rank, pass, column half, 32-column chunk): [32 columns][128 rows]
+__device__ __forceinline__ size_t k3_save_block(int tile, int rank, int NP, int pass, int chalf, int cc) {
+  return ((((size_t)(tile * 2 + rank) * NP + pass) * 2 + chalf) * 4 + cc) * (size_t)(32 * 128);
+}
 __device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void bar_gen() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
@@ -294,7 +298,11 @@ struct alignas(64) Tc3Args {
   uint8_t* mask2;
   float4 *scr1, *scr2;
   uint32_t* cnt;
-  float* accsave;                                 // [T*256][Hq] GEMM2 accumulators (gx1 / s2) kept for the backward, or null
+  float* accsave;                                 // GEMM2 accumulators (gx1 / s2) kept for the backward, or null.  Bp x Hq floats in
+                                                  // blocks [tile][cta rank][pass][column half][32-column chunk] of [32 columns][128
+                                                  // rows] (k3SaveBlock): the TMEM-native order, so that a warp's store of one
+                                                  // column is ONE 128-byte line (row-major rows made every 256-bit store touch 32
+                                                  // lines: a quarter of the LSU's time during a GEMM2 unit)
   float4* cscr;                                   // K-chunk running sums (Tc3Layout::cscr), used when NC > 1
   int B, Hq, T, NP, mask_stride, mask_rows, want_x;
   int NC;                                         // K-chunks per unit (hi/lo modes: Hq / kTc3ChunkK; 1 = plain accumulation)
@@ -521,12 +529,9 @@ icnn_tc3_fwd_kernel(const __grid_constant__ Tc3Args a) {
             for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * inv_s2);
           }
           if (a.accsave != nullptr) {            // training: the backward reads this back instead of redoing GEMM2
-            float* dst = a.accsave + (size_t)grow * Hq + nb;      // 128 contiguous bytes per thread: 4 x 256-bit stores
+            float* dst = a.accsave + k3_save_block(un.t, (int)rank, NP, un.p, chalf, cc) + row;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * j), "r"(r[8 * j]),
-                           "r"(r[8 * j + 1]), "r"(r[8 * j + 2]), "r"(r[8 * j + 3]), "r"(r[8 * j + 4]), "r"(r[8 * j + 5]),
-                           "r"(r[8 * j + 6]), "r"(r[8 * j + 7]) : "memory");
+            for (int j = 0; j < 32; ++j) __stcs(dst + j * k3Rows, __uint_as_float(r[j]));    // lane = row: coalesced
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -1086,12 +1091,11 @@ icnn_tc3_bwd_kernel(const __grid_constant__ Tc3BwdArgs a) {
           if (from_global) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-              const float* src = a.accsave + (size_t)(m0 + r0 + 8 * r) * Hq + nb + cp2;
+              const float* src = a.accsave + k3_save_block(un.t, (int)rank, NP, un.p, chalf, cc) + (size_t)cp2 * k3Rows + r0 + 8 * r;
 #pragma unroll
               for (int n = 0; n < 4; ++n) {
-                const float2 t = __ldcs(reinterpret_cast<const float2*>(src + 8 * n));
-                (r < 2 ? ra : rb)[4 * n + 2 * (r & 1)] = __float_as_uint(t.x);
-                (r < 2 ? ra : rb)[4 * n + 2 * (r & 1) + 1] = __float_as_uint(t.y);
+                (r < 2 ? ra : rb)[4 * n + 2 * (r & 1)] = __float_as_uint(__ldcs(src + (8 * n) * k3Rows));
+                (r < 2 ? ra : rb)[4 * n + 2 * (r & 1) + 1] = __float_as_uint(__ldcs(src + (8 * n + 1) * k3Rows));
               }
             }
           } else {
