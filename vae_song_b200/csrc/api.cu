@@ -28,8 +28,6 @@ int simt_bwd(const float* z, const float* v, const float* gpsi, const uint32_t* 
              const b200vae_icnn_grads* g, float* dz, float* ws, size_t mid_extra, cudaStream_t st);
 // tensor-core (tcgen05) variants, icnn_tc.cu
 int tc_prepare(const b200vae_icnn_params* p, int d, int H, int mode, int precision, float* ws, cudaStream_t st);
-int tc_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1,
-           uint8_t* mask2, int precision, const float* ws, cudaStream_t st);
 int tc3_prepare(int d, int H, int precision, float* ws, cudaStream_t st);
 int tc3_fwd(const float* z, int B, int d, int H, float kappa, float* psi, float* xhat, uint32_t* mask1, uint8_t* mask2,
             int precision, float* ws, float* accsave, cudaStream_t st);
@@ -135,20 +133,15 @@ extern "C" int b200vae_icnn_decode_fwd(const float* z, int B, int d, int H, int 
   if (ws_bytes < b200vae_icnn_workspace_bytes(B, d, H, precision, 0)) return B200VAE_EWS;
   if (precision == B200VAE_PREC_FP32)
     return simt_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, ws_base(ws), (cudaStream_t)stream);
-  // forward kernel variant, B200VAE_FWD = 3 (default): persistent CTA pairs (icnn_tc3.cu), falling back to 1 where it
-  // does not take the shape; 1: single-CTA kernel (icnn_tc.cu).  H > 1024 fits neither: EUNSUP
-  static const int variant = [] { const char* e = getenv("B200VAE_FWD"); return e ? atoi(e) : 3; }();
-  if (variant == 3) {
-    float* accsave = nullptr;
-    if (mask1 && mask2 && xhat && accsave_floats(B, d, H, precision) &&
-        ws_bytes >= b200vae_icnn_workspace_bytes(B, d, H, precision, 1))
-      accsave = ws_base(ws) + bwd_floats_without_save(B, d, H, precision);
-    save_forget(ws_base(ws));
-    rc = tc3_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), accsave, (cudaStream_t)stream);
-    if (rc == B200VAE_OK && accsave) save_record(ws_base(ws), z, B, d, H);
-    if (rc != B200VAE_EUNSUP) return rc;
-  }
-  return tc_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), (cudaStream_t)stream);
+  // persistent CTA pairs (icnn_tc3.cu); B200VAE_EUNSUP where they do not take the shape (d > 3, H > 1024)
+  float* accsave = nullptr;
+  if (mask1 && mask2 && xhat && accsave_floats(B, d, H, precision) &&
+      ws_bytes >= b200vae_icnn_workspace_bytes(B, d, H, precision, 1))
+    accsave = ws_base(ws) + bwd_floats_without_save(B, d, H, precision);
+  save_forget(ws_base(ws));
+  rc = tc3_fwd(z, B, d, H, kappa, psi, xhat, mask1, mask2, precision, ws_base(ws), accsave, (cudaStream_t)stream);
+  if (rc == B200VAE_OK && accsave) save_record(ws_base(ws), z, B, d, H);
+  return rc;
 }
 
 extern "C" int b200vae_icnn_decode_bwd(const float* z, const float* v, const float* gpsi, const uint32_t* mask1,

@@ -1,6 +1,6 @@
 // icnn_tc3.cu -- persistent CTA-pair (tcgen05 cta_group::2) fused ICNN potential + Brenier map (forward).
 //
-// Why a third forward kernel: ncu showed the single-CTA kernel (icnn_tc.cu) to be ISSUE bound, not tensor bound
+// Why this design: ncu showed round 1's single-CTA kernel (one 256-row tile per CTA, since deleted) to be ISSUE bound, not tensor bound
 // (about 2000 warp instructions per 16-wide K-block against 512 tensor cycles), with the epilogue exposed
 // (D[256x256] fills TMEM) and 256 tiles on 148 SMs.  This kernel removes all three:
 //   * lean operand generators.  GEMM1's A = leaky(A0 z + b0)^2 is computed with packed f32x2 FMAs and rounded to
@@ -45,7 +45,7 @@ constexpr int k3Threads = 18 * 32;                // 8 epilogue warps, 8 generat
 constexpr int k3TileBytes = k3Rows * 64;          // 128 rows x 64 B = 8 KB (A tile, and this CTA's half of a B tile)
 constexpr int k3MaskStride = 36;                  // words per row of the shared mask buffer (16 B aligned, conflict free)
 constexpr int kTc3MaxHq = 1024;                   // a mask row must fit the buffer (Hq / 32 <= 36, Hq a multiple of 256): wider
-                                                  // ICNNs run the single-CTA kernels of icnn_tc.cu
+                                                  // ICNNs are refused (B200VAE_EUNSUP): FP32 kernels only
 constexpr uint32_t k3Idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 __device__ __forceinline__ uint32_t cluster_rank3() {
@@ -1638,7 +1638,7 @@ static int get_maps3(const float* t3, const Tc3Layout& T3, int mode, Tc3Maps* ou
 
 // =====================================================================================================
 // dP0 (batch-reduced gradient of the H x H weight) on CTA pairs:  dP0part[split][o][n] = sum_{m in split} (1 + 4 bit[m,o]) s2[m] q1[m,n]
-// The single-CTA kernel (icnn_tc_dP0_kernel, icnn_tc.cu) turned out to be bound by SHARED-MEMORY BYTES, not by generator
+// Round 1's single-CTA kernel (since deleted) turned out to be bound by SHARED-MEMORY BYTES, not by generator
 // instructions or the tensor pipe (ncu: issue 36 %, tensor 45 / 69 % active; an n-stationary single-CTA variant with fewer
 // generator instructions but more generated bytes was slower): per 16-sample K-block an SM wrote 32 / 48 KB of generated
 // operands and the MMAs read 48 / 96 KB (TF32 / 3xTF32) against ~730 / 1460 tensor cycles x 128 B/clk.  Here

@@ -110,21 +110,17 @@ constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)
 __device__ __forceinline__ uint32_t sw64_off(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
 // ------------------------------------------------------------------------------------ TC workspace
-// (floats, after the SIMT layout's `end`)  Hq = H rounded up to 256.
-//   B1hi,B1lo [Hq][Hq]  B1[o][i] = P[o][i]   (GEMM1: rows = output unit o, K = input unit i)
-//   B2hi,B2lo [Hq][Hq]  B2[i][o] = P[o][i]   (GEMM2: rows = input unit i,  K = output unit o)
+// (floats, after the SIMT layout's `end`)  Hq = H rounded up to 256.  Per-unit parameter tables in natural unit order:
 //   A0q, A1q  float4[Hq] = (w0, w1, w2, bias)   P1q [Hq]
 struct TcLayout {
   int Hq;
-  size_t B1hi, B1lo, B2hi, B2lo, A0q, A1q, P1q, end;
+  size_t A0q, A1q, P1q, end;
 };
 inline TcLayout tc_layout(int d, int H) {
   (void)d;
   TcLayout T;
   T.Hq = round_up(H, 256);
-  const size_t q = (size_t)T.Hq * T.Hq;
   size_t o = 0;
-  T.B1hi = o; o += q; T.B1lo = o; o += q; T.B2hi = o; o += q; T.B2lo = o; o += q;
   T.A0q = o; o += (size_t)4 * T.Hq; T.A1q = o; o += (size_t)4 * T.Hq; T.P1q = o; o += T.Hq;
   T.end = o + 64;
   return T;
