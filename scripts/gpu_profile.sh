@@ -1,4 +1,4 @@
-# ncu captures (launch list + --set full) used for profiles/: gpurun --timeout 1800 -- "bash scripts/gpu_profile.sh"
+# ncu captures (launch list + --set full) used for profiles/: gpurun --timeout 1800 -- "bash scripts/gpu_profile.sh" (round-2 tf32x3 / all-pairs captures; the f16x3 evidence pass is scripts/gpu_evidence.sh)
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 python scripts/profile_allpairs.py 50000 > gpurun_out/profile_ap_plain.log 2>&1 || exit 1
