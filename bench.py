@@ -661,7 +661,7 @@ def run_ours(args, rank, local_rank, world):
                            "speedup_of_this_arm": rms / ms, "unmodified": unmodified,
                            "what": "oracle/_ref model.LIDVAE + lipschitz.train_model, stock PyTorch eager on this GPU, FP32 "
                                    "(TF32 off), same weights / batch / data, L2 flushed between steps, inputs resident"}
-            csteps = 3
+            csteps = 8                                    # ~10 s of CPU work (1.2 s per 65536-sample step)
             ts, kind, note = cpu_reference_times(B, csteps, 1)
             cms = float(np.min(ts))
             cpu = {"value": B / (cms * 1e-3), "unit": "samples/s", "cores": os.cpu_count(), "kind": kind,
